@@ -1,0 +1,188 @@
+/*
+ * xworld_b200.h -- C ABI of the B200-native batched XWorld2D simulator.
+ *
+ * This is the drop-in boundary for ONE hot path of PaddlePaddle/XWorld:
+ *   SimulatorInterface::take_actions  (simulator_interface.cpp:126-137)
+ *     -> XWorldSimulator::take_action (games/xworld/xworld_simulator.cpp:200-265)
+ *     -> XAgent::act / XMap::move_item (games/xworld/xworld/xitem.cpp:89-155, xmap.cpp:76-101)
+ *     -> Teacher::teach + task reward rules (teacher.cpp:207-230, teaching_task.cpp:64-116,
+ *        games/xworld3d/tasks/xworld3d_task.py:451-482, games/xworld/tasks/xworld_task.py:184-223)
+ *     -> XWorldSimulator::get_screen    (xworld_simulator.cpp:278-307,508-545; xmap.cpp:125-146)
+ * replayed for N environments at once by hand-written sm_100a CUDA kernels.
+ *
+ * Plain C: pointers and sizes only, no torch / STL types.  Every entry point names the
+ * reference interface it replaces.  All functions return 0 on success, a negative
+ * xw_status on failure (never abort -- the reference CHECK/LOG(FATAL)s instead,
+ * e.g. xworld_simulator.cpp:254); xw_last_error() gives the message.
+ *
+ * Pointers called d_* are DEVICE pointers (cudaMalloc'ed / torch CUDA tensors),
+ * h_* are HOST pointers.  `stream` is a cudaStream_t passed as void* (0 = default).
+ */
+#ifndef XWORLD_B200_H_
+#define XWORLD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XW_ABI_VERSION 1
+#define XW_MAX_GOALS 8   /* goals per map (XWorldNav uses 2..4, XWorldNav.py:31-32) */
+#define XW_MAX_DIM 16    /* map side in cells (reference hard-codes 8, XWorldNav.py:10-11) */
+#define XW_ICON_SIZE 64  /* XItem::item_size_, xitem.h:151 */
+
+typedef enum {
+    XW_OK = 0,
+    XW_ERR_INVALID_ARG = -1,
+    XW_ERR_CUDA = -2,
+    XW_ERR_NO_DEVICE = -3,
+    XW_ERR_INVALID_ACTION = -4, /* reference: CHECK_LT(action_idx, num_actions) aborts */
+    XW_ERR_UNSUPPORTED = -5
+} xw_status;
+
+/* Which game the handle simulates (SimulatorInterface ctor, simulator_interface.cpp:37-85). */
+typedef enum {
+    XW_GAME_XWORLD = 0,      /* "xworld"      -> CUDA */
+    XW_GAME_SIMPLE_GAME = 1, /* "simple_game" -> host (BASELINE config 1: CPU plumbing) */
+    XW_GAME_SIMPLE_RACE = 2  /* "simple_race" -> CUDA, fp32 */
+} xw_game;
+
+/* Teacher rule set = the task group of the conf json (teacher.cpp:70-99). */
+typedef enum {
+    XW_RULES_NAV3D = 0, /* confs/navigation2d.json: XWorld3DNav{Target,TargetNear,TargetBetween,
+                           TargetDirection,TargetAvoid} (games/xworld3d/tasks/) */
+    XW_RULES_NAV2D = 1  /* confs/walls.json: XWorldNav{Target,Near,ColorTarget,Between} +
+                           XWorldRec* (games/xworld/tasks/) */
+} xw_rules;
+
+/* GameOverCode bitmask, simulator.h:42-48. */
+enum { XW_ALIVE = 0, XW_MAX_STEP = 1, XW_DEAD = 2, XW_SUCCESS = 4, XW_LOST_LIFE = 8 };
+
+/* Teacher event of the last step (TeachingEnvBuffer::event, simulator.h:267-291). */
+enum { XW_EVENT_NONE = 0, XW_EVENT_CORRECT_GOAL = 1, XW_EVENT_WRONG_GOAL = 2, XW_EVENT_TIME_UP = 3 };
+
+/* Task stage (Task::current_stage_, teaching_task.h:51-104). */
+enum { XW_STAGE_IDLE = 0, XW_STAGE_NAVIGATION = 1, XW_STAGE_TERMINAL = 2 };
+
+/* Task ids in conf-json order (TaskGroup::run_stage indexes task_list_, teaching_task.cpp:204-222). */
+enum {
+    XW_T3_TARGET = 0, XW_T3_NEAR = 1, XW_T3_BETWEEN = 2, XW_T3_DIRECTION = 3, XW_T3_AVOID = 4,
+    XW_T2_TARGET = 0, XW_T2_NEAR = 1, XW_T2_COLOR_TARGET = 2, XW_T2_BETWEEN = 3
+};
+
+/* Grid cell codes (one item per cell in navigation maps; XMap::item_ptr_cube_, xmap.h:95). */
+enum { XW_CELL_EMPTY = 0, XW_CELL_BLOCK = 1, XW_CELL_AGENT = 2, XW_CELL_GOAL0 = 3 };
+
+/* Icon catalog = what XWorldEnv.set_goal_subtrees builds from item_path
+ * (games/xworld/maps/xworld_env.py:244-268) plus properties.txt colours (:88-94). */
+typedef struct {
+    int32_t n_icons;          /* icons in the atlas */
+    int32_t brick_icon;       /* block/brick_1.jpg */
+    int32_t agent_icon;       /* agent/robot_1.jpg */
+    int32_t n_names;          /* goal class names in canonical (sorted) order */
+    const int32_t* name_first;   /* [n_names+1] CSR offsets into name_icons */
+    const int32_t* name_icons;   /* icon ids of each name's variants, sorted by path */
+    const uint8_t* icon_colored; /* [n_icons] 1 iff properties.txt colour != "na" */
+    const uint8_t* atlas64;   /* HOST, [n_icons][64][64][3] BGR bytes as cv::imread(path,1)
+                                 returns them (xitem.cpp:38); parity is defined post-decode */
+} xw_catalog;
+
+/* Per-batch options = the reference's process-global gflags (simulator.cpp:21-27,
+ * xworld_simulator.cpp:22-37, teacher.cpp:22-25, simulator_util.cpp:27) without the globals. */
+typedef struct {
+    int32_t abi_version;      /* XW_ABI_VERSION */
+    int32_t game;             /* xw_game */
+    /* ---- xworld ---- */
+    int32_t height, width;    /* map size in cells (XWorldNav max_height/max_width) */
+    int32_t n_goals, n_blocks;/* XWorldNav.py num_goals_seq / num_blocks_seq entries */
+    int32_t rules;            /* xw_rules */
+    int32_t out_h, out_w;     /* frame size; 0 = reference rule height*12 (xworld_simulator.cpp:52-61) */
+    int32_t context;          /* --context (frames stacked, simulator.cpp:21) */
+    int32_t max_steps;        /* --max_steps, 0 = off (simulator.h:68-74) */
+    int32_t max_steps_factor; /* --max_steps_factor (xworld3d_task.py:38), default 10 */
+    int32_t visible_radius;   /* --visible_radius; only 0 (fully observed) is implemented */
+    int32_t auto_reset;       /* 0 = reference behaviour (caller resets) */
+    int32_t simulator_seed;   /* --simulator_seed: env i seeds minstd_rand0 like the reference's
+                                 i-th thread (simulator_util.cpp:38-55) */
+    uint64_t seed;            /* Philox key for the draws the reference takes from Python's
+                                 unseeded `random` (map generation, task idle stages) */
+    int64_t env_id_offset;    /* global id of local env 0 (multi-GPU sharding) */
+    /* ---- simple_game ---- */
+    int32_t array_size;       /* --array_size (simple_game_simulator.cpp:18) */
+    /* ---- simple_race (simple_race_simulator.cpp:17-26) ---- */
+    int32_t track_type;       /* 0 straight, 1 circle */
+    float track_width, track_length, track_radius;
+    int32_t race_full_manouver;
+    int32_t race_random;      /* only 0 implemented */
+    int32_t difficulty;       /* 0 easy, 1 hard */
+    float reward_scale;
+    int32_t reserved[8];
+} xw_config;
+
+typedef struct xw_sim xw_sim; /* opaque handle: one batch of n_envs environments on one GPU */
+
+/* Fill *cfg with the reference's flag defaults. */
+void xw_config_init(xw_config* cfg);
+
+/* SimulatorInterface::SimulatorInterface(name) (simulator_interface.cpp:37-85) for a batch.
+ * catalog may be NULL for simple_game / simple_race.  device < 0: current device. */
+int xw_create(const xw_config* cfg, const xw_catalog* catalog, int32_t n_envs, int32_t device,
+              xw_sim** out);
+void xw_destroy(xw_sim* sim);
+const char* xw_last_error(void);
+
+/* SimulatorInterface::reset_game (simulator_interface.cpp:95-105): game reset, teacher reset +
+ * first teach(), first frame.  d_mask: optional device u8[n_envs], reset only envs with mask!=0
+ * (NULL = all). */
+int xw_reset(xw_sim* sim, const uint8_t* d_mask, void* stream);
+
+/* SimulatorInterface::take_actions (simulator_interface.cpp:126-137) for every env:
+ * act_rep x take_action -> teach -> reward -> (render if d_frames != NULL).
+ *   d_actions   i32[n_envs]   action ids (StatePacket "action", xworld_simulator.cpp:231)
+ *   d_reward    f32[n_envs]   return value of take_actions
+ *   d_game_over i32[n_envs]   SimulatorInterface::game_over() right after the step
+ *   d_frames    u8[n_envs][context*C][out_h][out_w] or NULL (get_state()["screen"] bytes)
+ * An invalid action marks the env in the error flags (xw_error_flags) and leaves it untouched. */
+int xw_step(xw_sim* sim, const int32_t* d_actions, int32_t act_rep, float* d_reward,
+            int32_t* d_game_over, uint8_t* d_frames, void* stream);
+
+/* GameSimulator::make_context_screens -> XWorldSimulator::get_screen (simulator.cpp:62-85,
+ * xworld_simulator.cpp:278-285): render the current state of every env. */
+int xw_render(xw_sim* sim, uint8_t* d_frames, void* stream);
+
+/* Same call with HOST buffers (pinned or pageable); copies in/out on the handle's stream and
+ * synchronises.  h_frames may be NULL.  This is the end-to-end path bench.py times. */
+int xw_step_host(xw_sim* sim, const int32_t* h_actions, int32_t act_rep, float* h_reward,
+                 int32_t* h_game_over, uint8_t* h_frames);
+int xw_reset_host(xw_sim* sim, const uint8_t* h_mask, uint8_t* h_frames);
+
+/* get_num_actions / get_screen_out_dimensions / get_num_steps / get_lives
+ * (simulator_interface.h:52-63). */
+int32_t xw_num_envs(const xw_sim* sim);
+int32_t xw_num_actions(const xw_sim* sim);
+int xw_screen_dims(const xw_sim* sim, int32_t* h, int32_t* w, int32_t* c, int32_t* context);
+size_t xw_frame_bytes(const xw_sim* sim); /* context*C*out_h*out_w */
+int xw_num_steps(xw_sim* sim, int64_t* h_num_steps /* [n_envs] host */);
+
+/* State fields by name, copied to host (tests, checkpointing, get_extra_info).  Fields:
+ * "grid" u8[n][H*W], "agent_x","agent_y","facing","task","stage","event","action_success",
+ * "target_mask","aux0","aux1","aux2" u8[n]; "goal_x","goal_y" u8[n][XW_MAX_GOALS];
+ * "goal_icon" i32[n][XW_MAX_GOALS]; "steps_in_task","num_steps","episode","n_success",
+ * "n_failure","success_steps","minstd","error" i32[n].
+ * Race: "pos_x","pos_y","angle" f32[n], "steps" i32[n], "state" f32[n][4]. */
+int xw_get_field(xw_sim* sim, const char* name, void* h_out, size_t bytes);
+int xw_set_field(xw_sim* sim, const char* name, const void* h_in, size_t bytes);
+
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+int64_t xw_launch_count(const xw_sim* sim);
+/* CUDA-event timing of the render kernel alone: average ms over the launches since the last
+ * call with reset != 0.  Returns <0 if timing is disabled.  xw_enable_timing(sim, 1) first. */
+int xw_enable_timing(xw_sim* sim, int32_t on);
+double xw_render_ms(xw_sim* sim, int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XWORLD_B200_H_ */

@@ -1,0 +1,99 @@
+/*
+ * xw_oracle.h -- CPU oracle for the XWorld2D hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library.  Nothing under xworld_b200/ links or calls it.
+ *
+ * Every function restates one piece of /root/reference (file:line in the .c file).
+ */
+#ifndef XW_ORACLE_H_
+#define XW_ORACLE_H_
+#include <stdint.h>
+#include "../include/xworld_b200.h" /* xw_config / xw_catalog / enums only (the interface) */
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Philox substream ids: one per reference call site that draws from Python's `random`. */
+enum {
+    XO_SITE_NAMES = 1,     /* XWorldNav._configure: random.shuffle(goal_names)            XWorldNav.py:60 */
+    XO_SITE_MAZE = 2,      /* maze2d.dfs: random.shuffle(moves), 3 draws per visited node  maze2d.py:95 */
+    XO_SITE_BLOCKS = 3,    /* __instantiate_entities: random.shuffle(blocks)               xworld_env.py:424 */
+    XO_SITE_GOAL_LOC = 4,  /* set_property: loc = choice(available_grids), index = goal#   xworld_env.py:190 */
+    XO_SITE_GOAL_ASSET = 5,/* set_property: asset_path = choice(items[type][name])         xworld_env.py:198 */
+    XO_SITE_AGENT_LOC = 6, /* set_property on the agent                                    xworld_env.py:190 */
+    XO_SITE_TASK_A = 7,    /* task idle: first choice (sel_goal / tile)                    XWorld3DNav*.py idle */
+    XO_SITE_TASK_B = 8,    /* task idle: second choice (referent / empty grid e)           */
+    XO_SITE_TASK_SHUF = 9, /* task idle: random.shuffle(goals); g1, g2 = goals[:2]         */
+    XO_SITE_TASK_AGENT = 10/* task idle: agent.loc = choice(new_a)                         */
+};
+
+typedef struct {
+    int32_t H, W;
+    uint8_t grid[XW_MAX_DIM * XW_MAX_DIM];
+    int32_t agent_x, agent_y;
+    double agent_yaw;
+    int32_t n_goals;
+    int32_t goal_x[XW_MAX_GOALS], goal_y[XW_MAX_GOALS], goal_icon[XW_MAX_GOALS], goal_name[XW_MAX_GOALS];
+    int32_t task, stage, event, action_success;
+    int32_t target_mask, aux0, aux1, aux2;
+    int32_t steps_in_task;
+    int64_t num_steps;
+    int32_t episode;
+    int32_t n_success, n_failure, success_steps;
+    uint32_t minstd;
+    int32_t error;
+    int64_t env_gid;
+} xo_env;
+
+/* ---- RNG ---- */
+void xo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+uint32_t xo_draw(uint64_t seed, int64_t env_gid, uint32_t episode, uint32_t attempt, uint32_t site,
+                 uint32_t index);
+uint32_t xo_randbelow(uint32_t u, uint32_t n);
+uint64_t xo_std_hash_bytes(const void* p, uint64_t len); /* libstdc++ std::hash<std::string> */
+uint32_t xo_minstd_seed_for_thread(int32_t simulator_seed, int32_t thread_no);
+int32_t xo_get_rand_ind(uint32_t* minstd, int32_t size); /* simulator_util.cpp:66-73 */
+
+/* ---- map pieces (exposed for unit tests) ---- */
+void xo_maze(uint64_t seed, int64_t env_gid, uint32_t episode, uint32_t attempt, int D, char* maze /* D*D */);
+
+/* ---- env ---- */
+void xo_env_init(const xw_config* cfg, xo_env* e, int64_t env_gid);
+int xo_reset(const xw_config* cfg, const xw_catalog* cat, xo_env* e);
+int xo_step(const xw_config* cfg, const xw_catalog* cat, xo_env* e, int32_t action, int32_t act_rep,
+            float* reward, int32_t* game_over);
+/* teacher stage run once on an explicit state (used to pin rules against the reference python) */
+int xo_teach(const xw_config* cfg, const xw_catalog* cat, xo_env* e, int32_t collided_cell_code,
+             double* reward);
+
+/* ---- render ---- */
+void xo_resize_tables(int src, int dst, int32_t* ofs, int16_t* a0, int16_t* a1);
+void xo_resize_linear_8uc3(const uint8_t* src, int sh, int sw, uint8_t* dst, int dh, int dw);
+/* The reference pipeline: white canvas -> per-item icon blit -> HWC->CHW -> CHW->HWC -> resize ->
+ * HWC->CHW (B,G,R planes).  scratch must hold 3 * (H*64)*(W*64)*3 bytes (or NULL: malloc). */
+void xo_render(const xw_config* cfg, const xw_catalog* cat, const xo_env* e, uint8_t* frame_out);
+void xo_frame_dims(const xw_config* cfg, int* oh, int* ow);
+
+/* ---- batch helpers (OpenMP over envs) for the CPU baseline ---- */
+int xo_batch_reset(const xw_config* cfg, const xw_catalog* cat, xo_env* envs, int n, int threads);
+int xo_batch_step(const xw_config* cfg, const xw_catalog* cat, xo_env* envs, int n, const int32_t* actions,
+                  int act_rep, float* reward, int32_t* game_over, uint8_t* frames /* or NULL */, int threads);
+int xo_sizeof_env(void);
+
+/* ---- simple_game (games/simple_game/simple_game_simulator.cpp) ---- */
+typedef struct { int32_t array_size, cur_pos; float rewards[64]; uint8_t state[64]; } xo_simple_game;
+void xo_sg_reset(xo_simple_game* g, int array_size);
+float xo_sg_act(xo_simple_game* g, int action);
+int xo_sg_game_over(const xo_simple_game* g);
+
+/* ---- simple_race (games/simple_race/simple_race_simulator.cpp) ---- */
+typedef struct { float pos_x, pos_y, angle; int32_t steps; } xo_race;
+void xo_race_reset(const xw_config* cfg, xo_race* r);
+float xo_race_act(const xw_config* cfg, xo_race* r, int action_index, float state[4], int32_t* game_over);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

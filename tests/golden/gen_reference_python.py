@@ -1,0 +1,429 @@
+#!/usr/bin/env python
+"""Golden-vector generator: runs the REFERENCE's own Python (map generator + teacher tasks) and
+records what it does, so the C oracle (oracle/xw_oracle.c) can be pinned against it.
+
+Runs only in the build container (needs /root/reference).  Output: tests/golden/refpy_traces.json.gz.
+
+What is executed unmodified (loaded from /root/reference, never copied):
+    games/xworld/maps/xworld_env.py, XWorldNav.py      map/entity schema + generator
+    python/maze2d.py, python/py_util.py                maze DFS, bfs, flood_fill
+    games/xworld3d/tasks/xworld3d_task.py + XWorld3DNav{Target,TargetNear,TargetBetween,
+        TargetDirection,TargetAvoid}.py                navigation2d.json task set
+    games/xworld/tasks/xworld_task.py + XWorldNav{Target,Near,ColorTarget,Between}.py   walls.json
+
+What the harness supplies instead of the C++ host (and cites):
+    * Python-2 -> 3 source fix-ups at load time: integer `/` on three lines (maze2d.py:89,
+      xworld_env.py:129-130), dict.iteritems(), dict.keys() used as a list (xworld_env.py:292).
+    * py_gflags.get_flag (python/py_init.cpp:37-58) -> a dict of the flags.
+    * context_free_grammar.CFG -> inert stub (sentences are out of scope).
+    * the `random` module -> ReplayRandom: every call site the reference draws from is mapped onto the
+      oracle's Philox substream of the same name (oracle/xw_oracle.h XO_SITE_*), with the sequence
+      put in a canonical order first wherever the reference's order is a CPython set/dict order.
+    * XMap::move_item / XAgent::act (xmap.cpp:76-101, xitem.cpp:89-155) and Task::py_stage's
+      C++<->Python sync (teaching_task.cpp:64-116) -> ~40 lines below (the compiled reference
+      XMap/XAgent in oracle/_ref is checked against the same rules in tests/test_ref_lib.py).
+    * XWorldNav's hard-coded 8x8 / goal / block counts (XWorldNav.py:10-11,31-32) are parametrised
+      by text substitution for the 7x7 / 11x11 / 15x15 BASELINE configs; the 8x8 case runs as is.
+"""
+import json
+import os
+import re
+import sys
+import types
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+
+import oracle  # noqa: E402  (only for xo_draw / xo_randbelow: the shared RNG definition)
+from xworld_b200.catalog import Catalog  # noqa: E402
+
+ITEM_PATH = os.path.join(REF, "games/xworld/images")
+
+FLAGS = {"visible_radius": 0, "curriculum": 0, "task_mode": "lang_acquisition", "max_steps_factor": 10}
+
+
+# ----------------------------------------------------------------------------- ReplayRandom
+class Ctx(object):
+    seed = 0
+    env_gid = 0
+    episode = 0
+    attempt = 0
+    maze_visits = 0
+    goal_no = 0
+    step_no = 0
+    idle_calls = 0
+
+
+def cell_key(p):  # canonical row-major (y, x)
+    return (p[1], p[0])
+
+
+class ReplayRandom(types.ModuleType):
+    """Stands in for the `random` module inside the reference's Python."""
+
+    def __init__(self):
+        types.ModuleType.__init__(self, "random")
+
+    def _u(self, site, index):
+        return oracle.draw(Ctx.seed, Ctx.env_gid, Ctx.episode, Ctx.attempt, site, index)
+
+    def _fy(self, x, site, base=0):  # python's shuffle: Fisher-Yates from the end
+        for k, i in enumerate(reversed(range(1, len(x)))):
+            j = oracle.randbelow(self._u(site, base + k), i + 1)
+            x[i], x[j] = x[j], x[i]
+
+    def shuffle(self, x):
+        caller = sys._getframe(1).f_code.co_name
+        if caller in ("__generate_all_grids", "_XWorldEnv__generate_all_grids", "update_entities_from_cpp", "bfs"):
+            return  # result order is never observed (set() / canonicalised later / reachability only)
+        if caller == "_configure":
+            x.sort()
+            self._fy(x, oracle.SITE_NAMES)
+        elif caller == "dfs":
+            self._fy(x, oracle.SITE_MAZE, base=3 * Ctx.maze_visits)
+            Ctx.maze_visits += 1
+        elif caller in ("__instantiate_entities", "_XWorldEnv__instantiate_entities"):
+            self._fy(x, oracle.SITE_BLOCKS)  # blocks already in row-major generation order
+        elif caller == "idle":
+            if x and hasattr(x[0], "type"):  # random.shuffle(goals); g1, g2 = goals[:2]
+                x.sort(key=lambda e: int(e.id.split("_")[-1]))
+                self._fy(x, oracle.SITE_TASK_SHUF)
+            else:  # random.shuffle(tiles); tiles[0]  == uniform pick (only element 0 is used)
+                if x:
+                    k = oracle.randbelow(self._u(oracle.SITE_TASK_A, 0), len(x))
+                    x[0], x[k] = x[k], x[0]
+        else:
+            raise RuntimeError("unmapped shuffle call site: " + caller)
+
+    def choice(self, seq):
+        f1 = sys._getframe(1)
+        caller = f1.f_code.co_name
+        seq = list(seq)
+        if caller == "check_or_get_value":
+            ent = f1.f_back.f_locals["entity"]
+            if isinstance(seq[0], tuple):  # loc = choice(available_grids)
+                seq.sort(key=cell_key)
+                if ent.type == "goal":
+                    u = self._u(oracle.SITE_GOAL_LOC, Ctx.goal_no)
+                else:
+                    assert ent.type == "agent"
+                    u = self._u(oracle.SITE_AGENT_LOC, 0)
+                return seq[oracle.randbelow(u, len(seq))]
+            seq.sort()
+            if len(seq) == 1:
+                return seq[0]
+            assert ent.type == "goal" and seq[0].endswith(".jpg")  # asset_path = choice(items[type][name])
+            v = seq[oracle.randbelow(self._u(oracle.SITE_GOAL_ASSET, Ctx.goal_no), len(seq))]
+            Ctx.goal_no += 1
+            return v
+        if caller == "idle":
+            cls = f1.f_locals["self"].__class__.__name__
+            Ctx.idle_calls += 1
+            if cls.startswith("XWorldNav"):  # 2-D tasks: one choice per idle stage, keyed by step
+                return seq[oracle.randbelow(self._u(oracle.SITE_TASK_A, Ctx.step_no), len(seq))]
+            if isinstance(seq[0], tuple) and isinstance(seq[0][0], tuple):  # choice(new_a): ((x,y,0), step)
+                return seq[oracle.randbelow(self._u(oracle.SITE_TASK_AGENT, 0), len(seq))]
+            if isinstance(seq[0], tuple):  # choice(empty_grids)
+                seq.sort(key=cell_key)
+                return seq[oracle.randbelow(self._u(oracle.SITE_TASK_B, 0), len(seq))]
+            # entities: first choice = sel_goal (A), second = referent (B)
+            site = oracle.SITE_TASK_A if Ctx.idle_calls == 1 else oracle.SITE_TASK_B
+            seq.sort(key=lambda e: int(e.id.split("_")[-1]))
+            return seq[oracle.randbelow(self._u(site, 0), len(seq))]
+        raise RuntimeError("unmapped choice call site: " + caller)
+
+    def uniform(self, a, b):
+        raise RuntimeError("unmapped uniform()")
+
+    def randint(self, a, b):
+        raise RuntimeError("unmapped randint()")
+
+    def random(self):
+        raise RuntimeError("unmapped random()")
+
+
+# ----------------------------------------------------------------------------- module loading
+def load_reference_python(dim, n_goals, n_blocks):
+    """exec the reference sources (with the py2->3 fix-ups) into fresh modules."""
+    rnd = ReplayRandom()
+    mods = {}
+
+    def mk(name, path, subs=()):
+        src = open(os.path.join(REF, path)).read()
+        for a, b in subs:
+            assert re.search(a, src), (path, a)
+            src = re.sub(a, b, src)
+        m = types.ModuleType(name)
+        m.__file__ = os.path.join(REF, path)
+        sys.modules[name] = m
+        mods[name] = m
+        exec(compile(src, m.__file__, "exec"), m.__dict__)
+        return m
+
+    gf = types.ModuleType("py_gflags")
+    gf.get_flag = lambda k: FLAGS[k]
+    sys.modules["py_gflags"] = gf
+    cfgm = types.ModuleType("context_free_grammar")
+
+    class CFG(object):
+        def __init__(self, *a, **k): pass
+        def bind(self, *a): pass
+        def generate(self, *a): return ""
+        def generate_all(self, *a): return []
+        def set_production_rule(self, *a): pass
+        def total_possible_sentences(self): return 0
+        def show(self): pass
+    cfgm.CFG = CFG
+    sys.modules["context_free_grammar"] = cfgm
+    saved = sys.modules.get("random")
+    sys.modules["random"] = rnd
+    try:
+        mk("py_util", "python/py_util.py")
+        mk("maze2d", "python/maze2d.py", [(r"\(X \+ 1\) / 2, \(Y \+ 1\) / 2", "(X + 1) // 2, (Y + 1) // 2")])
+        mk("xworld_env", "games/xworld/maps/xworld_env.py", [
+            (r"\(self\.max_height - h\) / 2", "(self.max_height - h) // 2"),
+            (r"\(self\.max_width - w\) / 2", "(self.max_width - w) // 2"),
+            (r"return self\.items\[type\]\.keys\(\)", "return list(self.items[type].keys())")])
+        nav_subs = []
+        if (dim, n_goals, n_blocks) != (8, 4, 16):
+            nav_subs = [(r"max_height=8,", "max_height=%d," % dim), (r"max_width=8,", "max_width=%d," % dim),
+                        (r"num_goals_seq = \[2, 2, 2, 4, 4, 4\]", "num_goals_seq = [%d] * n_levels" % n_goals),
+                        (r"num_blocks_seq = \[0, 3, 6, 9, 12, 16\]", "num_blocks_seq = [%d] * n_levels" % n_blocks)]
+        mk("XWorldNav", "games/xworld/maps/XWorldNav.py", nav_subs)
+        mk("xworld3d_task", "games/xworld3d/tasks/xworld3d_task.py")
+        for t in ("XWorld3DNavTarget", "XWorld3DNavTargetNear", "XWorld3DNavTargetBetween",
+                  "XWorld3DNavTargetDirection", "XWorld3DNavTargetAvoid"):
+            mk(t, "games/xworld3d/tasks/%s.py" % t)
+        mk("xworld_task", "games/xworld/tasks/xworld_task.py", [(r"iteritems", "items")])
+        for t in ("XWorldNavTarget", "XWorldNavNear", "XWorldNavColorTarget", "XWorldNavBetween"):
+            mk(t, "games/xworld/tasks/%s.py" % t)
+    finally:
+        if saved is not None:
+            sys.modules["random"] = saved
+    return mods
+
+
+T3 = ["XWorld3DNavTarget", "XWorld3DNavTargetNear", "XWorld3DNavTargetBetween", "XWorld3DNavTargetDirection",
+      "XWorld3DNavTargetAvoid"]  # confs/navigation2d.json order
+T2 = ["XWorldNavTarget", "XWorldNavNear", "XWorldNavColorTarget", "XWorldNavBetween"]  # confs/walls.json order
+DIRS = {"front": 1, "behind": 2, "left": 3, "right": 4}
+
+
+# ----------------------------------------------------------------------------- host emulation
+class Host(object):
+    """What XWorldSimulator/XWorld/XMap/Teacher do around the Python (C++ side), for one env."""
+
+    def __init__(self, mods, cat, rules, dim):
+        self.mods, self.cat, self.rules, self.dim = mods, cat, rules, dim
+        self.env = mods["XWorldNav"].XWorldNav(ITEM_PATH)
+        names = T3 if rules == 0 else T2
+        self.tasks = [getattr(mods[n], n)(self.env) for n in names]  # Task::init_py_task
+        self.path2icon = {os.path.join(ITEM_PATH, m["path"]): i for i, m in enumerate(cat.icon_meta)}
+        self.stage = "idle"
+        self.busy = None
+        self.minstd = None
+
+    # XWorld::reset (xworld.cpp:109-151): entity dicts in cpp_get_entities order
+    def pull_entities(self):
+        self.entities = [dict(e) for e in self.env.cpp_get_entities()]
+        for e in self.entities:
+            e["loc"] = tuple(float(v) for v in e["loc"])  # Entity ctor: doubles (simulator_entity.h:88-101)
+
+    def cell(self, x, y):
+        for e in self.entities:
+            if int(e["loc"][0]) == x and int(e["loc"][1]) == y:
+                return e
+        return None
+
+    def agent(self):
+        return [e for e in self.entities if e["type"] == "agent"][0]
+
+    # XAgent::act + XMap::move_item
+    def move(self, action):
+        a = self.agent()
+        dx, dy = [(0, -1), (0, 1), (-1, 0), (1, 0)][action]
+        tx, ty = int(a["loc"][0]) + dx, int(a["loc"][1]) + dy
+        contacts = []
+        ok = False
+        if 0 <= tx < self.dim and 0 <= ty < self.dim:
+            it = self.cell(tx, ty)
+            if it is None:
+                a["loc"] = (float(tx), float(ty), 0.0)
+                ok = True
+            elif it["id"] != a["id"]:
+                contacts.append(it["id"])
+        return ok, contacts
+
+    # Task::py_stage (teaching_task.cpp:64-116)
+    def py_stage(self, task, stage, success, game_event):
+        env = self.env
+        env.update_entities_from_cpp([dict(e) for e in self.entities])
+        env.update_agent_sentence_from_cpp("")
+        env.update_agent_action_success_from_cpp(success)
+        env.update_game_event_from_cpp(game_event)
+        Ctx.idle_calls = 0
+        ret = getattr(task, stage)()
+        if env.env_changed():
+            self.pull_entities()  # XWorldSimulator::update_environment -> XWorld::reset(false)
+        event = task.get_event()
+        assert len(ret) == 3
+        return ret[0], float(ret[1]), event
+
+    def snapshot(self):
+        D = self.dim
+        grid = [[0] * D for _ in range(D)]
+        goals = sorted([e for e in self.entities if e["type"] == "goal"], key=lambda e: int(e["id"].split("_")[-1]))
+        for e in self.entities:
+            x, y = int(e["loc"][0]), int(e["loc"][1])
+            if e["type"] == "block":
+                grid[y][x] = 1
+            elif e["type"] == "agent":
+                grid[y][x] = 2
+            else:
+                grid[y][x] = 3 + goals.index(e)
+        a = self.agent()
+        return {
+            "grid": [v for row in grid for v in row],
+            "agent": [int(a["loc"][0]), int(a["loc"][1])],
+            "goal_x": [int(g["loc"][0]) for g in goals], "goal_y": [int(g["loc"][1]) for g in goals],
+            "goal_name": [self.cat.names.index(g["name"]) for g in goals],
+            "goal_icon": [self.path2icon[g["asset_path"]] for g in goals],
+        }
+
+    def goal_index(self, ent):
+        return int(ent.id.split("_")[-1])
+
+    def task_record(self, t, task):
+        """target bookkeeping in the oracle's encoding (xo_env.target_mask / aux*)."""
+        rec = {}
+        if self.rules == 0:
+            name = T3[t]
+            if name in ("XWorld3DNavTarget", "XWorld3DNavTargetAvoid", "XWorld3DNavTargetNear"):
+                rec["target_mask"] = sum(1 << self.goal_index(g) for g in task.target)
+            elif name == "XWorld3DNavTargetBetween":
+                o1, o2 = task.target
+                rec["mid"] = [int((o1[0] + o2[0]) // 2), int((o1[1] + o2[1]) // 2)]
+            else:
+                referent, direction = task.target
+                rec["referent"] = self.goal_index(referent)
+                rec["direction"] = DIRS[direction]
+        return rec
+
+
+def run_case(mods, cat, rules, dim, n_goals, n_blocks, seed, simulator_seed, env_gid, n_episodes, n_steps, act_seed):
+    """One env, several episodes; returns the trace the oracle must reproduce."""
+    L = oracle.lib()
+    import ctypes as C
+    host = Host(mods, cat, rules, dim)
+    minstd = C.c_uint32(L.xo_minstd_seed_for_thread(simulator_seed, env_gid + 1))
+    Ctx.seed, Ctx.env_gid = seed, env_gid
+    episodes = []
+    import numpy as np
+    arng = np.random.RandomState(act_seed)
+    for ep in range(1, n_episodes + 1):
+        Ctx.episode = ep
+        rec = {"episode": ep}
+        # ---- SimulatorInterface::reset_game
+        if rules == 0:
+            t = L.xo_get_rand_ind(C.byref(minstd), 5)  # TaskGroup::run_stage (seeded C++ engine)
+            task = host.tasks[t]
+            ok = False
+            for att in range(64):
+                Ctx.attempt, Ctx.maze_visits, Ctx.goal_no, Ctx.step_no = att, 0, 0, 0
+                host.env.reset()
+                assert host.env.env_changed()
+                host.pull_entities()
+                task.reset()
+                try:
+                    stage, r0, ev0 = host.py_stage(task, "idle", False, "")
+                    ok = True
+                    break
+                except AssertionError as ex:
+                    if "crowded" not in str(ex):
+                        raise
+            assert ok
+            rec["attempts"] = att + 1
+            assert stage == "navigation_reward" and r0 == 0.0
+        else:
+            Ctx.attempt, Ctx.maze_visits, Ctx.goal_no, Ctx.step_no = 0, 0, 0, 0
+            host.env.reset()
+            host.pull_entities()
+            stage, task, t = "idle", None, -1
+        rec["task"] = t
+        rec["reset"] = host.snapshot()
+        if rules == 0:
+            rec.update(host.task_record(t, task))
+        steps = []
+        num_steps = 0
+
+        def teach2d(success, game_event):
+            nonlocal stage, task, t
+            if stage == "idle":
+                t = L.xo_get_rand_ind(C.byref(minstd), 4)
+                task = host.tasks[t]
+                task.reset()
+                stage, r, ev = host.py_stage(task, "idle", success, game_event)
+            else:
+                stage, r, ev = host.py_stage(task, stage, success, game_event)
+            # XWorldRec group: one engine draw per teach, event overwritten with ""
+            minstd.value = (minstd.value * 16807) % 2147483647
+            return r, ""
+
+        if rules == 1:
+            r, ev = teach2d(False, "")
+            rec["reset_stage"] = stage
+            rec["reset_task"] = t
+        for s in range(n_steps):
+            a = int(arng.randint(0, 4))
+            num_steps += 1
+            Ctx.step_no = num_steps
+            ok, contacts = host.move(a)
+            game_event = ("collision:" + "|".join(contacts) + "\n") if contacts else ""
+            if rules == 0:
+                stage, r, ev = host.py_stage(task, stage, ok, game_event)
+            else:
+                r, ev = teach2d(ok, game_event)
+            ag = host.agent()
+            steps.append({"a": a, "ok": int(ok), "r": r, "ev": ev, "stage": stage, "task": t,
+                          "agent": [int(ag["loc"][0]), int(ag["loc"][1])]})
+            if rules == 0 and stage == "terminal" and s + 3 < n_steps and len(steps) > 2 and steps[-2]["stage"] == "terminal" \
+                    and steps[-3]["stage"] == "terminal":
+                break  # a few terminal-stage steps are enough
+        rec["steps"] = steps
+        rec["minstd"] = minstd.value
+        episodes.append(rec)
+    return episodes
+
+
+def main():
+    cat = Catalog.from_item_path(ITEM_PATH)
+    meta_names = Catalog(Catalog.metadata(), __import__("numpy").zeros((363, 64, 64, 3), "uint8")).names
+    assert meta_names == cat.names
+    cases = [  # (tag, rules, dim, goals, blocks, n_envs, episodes, steps)
+        ("nav3d_8x8_reference_defaults", 0, 8, 4, 16, 6, 6, 80),
+        ("nav3d_7x7", 0, 7, 4, 12, 10, 8, 80),
+        ("nav3d_15x15", 0, 15, 4, 56, 3, 3, 60),
+        ("nav2d_11x11", 1, 11, 4, 30, 6, 3, 60),
+        ("nav2d_8x8_reference_defaults", 1, 8, 4, 16, 4, 3, 40),
+    ]
+    out = {"generator": "tests/golden/gen_reference_python.py", "cases": []}
+    for tag, rules, dim, G, B, n_envs, n_ep, n_st in cases:
+        mods = load_reference_python(dim, G, B)
+        envs = []
+        for gid in range(n_envs):
+            envs.append({"env_gid": gid,
+                         "episodes": run_case(mods, cat, rules, dim, G, B, seed=1234, simulator_seed=1,
+                                              env_gid=gid, n_episodes=n_ep, n_steps=n_st, act_seed=1000 + gid)})
+        out["cases"].append({"tag": tag, "rules": rules, "dim": dim, "n_goals": G, "n_blocks": B, "seed": 1234,
+                             "simulator_seed": 1, "envs": envs})
+        print(tag, "ok")
+    import gzip
+    path = os.path.join(HERE, "refpy_traces.json.gz")
+    with gzip.GzipFile(path, "wb", mtime=0) as f:
+        f.write(json.dumps(out, separators=(",", ":")).encode())
+    print("wrote", path, os.path.getsize(path))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,150 @@
+"""ctypes mirror of include/xworld_b200.h (the C ABI) and the loader of the in-tree CUDA library.
+
+The product path has no CPU fallback: if libxworld_b200.so is missing, `load()` raises.
+"""
+import ctypes as C
+import os
+
+XW_ABI_VERSION = 1
+XW_MAX_GOALS = 8
+XW_MAX_DIM = 16
+XW_ICON_SIZE = 64
+
+XW_GAME_XWORLD, XW_GAME_SIMPLE_GAME, XW_GAME_SIMPLE_RACE = 0, 1, 2
+XW_RULES_NAV3D, XW_RULES_NAV2D = 0, 1
+XW_ALIVE, XW_MAX_STEP, XW_DEAD, XW_SUCCESS, XW_LOST_LIFE = 0, 1, 2, 4, 8
+XW_EVENT_NONE, XW_EVENT_CORRECT_GOAL, XW_EVENT_WRONG_GOAL, XW_EVENT_TIME_UP = 0, 1, 2, 3
+XW_STAGE_IDLE, XW_STAGE_NAVIGATION, XW_STAGE_TERMINAL = 0, 1, 2
+XW_CELL_EMPTY, XW_CELL_BLOCK, XW_CELL_AGENT, XW_CELL_GOAL0 = 0, 1, 2, 3
+
+
+class XwCatalog(C.Structure):
+    _fields_ = [
+        ("n_icons", C.c_int32),
+        ("brick_icon", C.c_int32),
+        ("agent_icon", C.c_int32),
+        ("n_names", C.c_int32),
+        ("name_first", C.POINTER(C.c_int32)),
+        ("name_icons", C.POINTER(C.c_int32)),
+        ("icon_colored", C.POINTER(C.c_uint8)),
+        ("atlas64", C.POINTER(C.c_uint8)),
+    ]
+
+
+class XwConfig(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32),
+        ("game", C.c_int32),
+        ("height", C.c_int32),
+        ("width", C.c_int32),
+        ("n_goals", C.c_int32),
+        ("n_blocks", C.c_int32),
+        ("rules", C.c_int32),
+        ("out_h", C.c_int32),
+        ("out_w", C.c_int32),
+        ("context", C.c_int32),
+        ("max_steps", C.c_int32),
+        ("max_steps_factor", C.c_int32),
+        ("visible_radius", C.c_int32),
+        ("auto_reset", C.c_int32),
+        ("simulator_seed", C.c_int32),
+        ("seed", C.c_uint64),
+        ("env_id_offset", C.c_int64),
+        ("array_size", C.c_int32),
+        ("track_type", C.c_int32),
+        ("track_width", C.c_float),
+        ("track_length", C.c_float),
+        ("track_radius", C.c_float),
+        ("race_full_manouver", C.c_int32),
+        ("race_random", C.c_int32),
+        ("difficulty", C.c_int32),
+        ("reward_scale", C.c_float),
+        ("reserved", C.c_int32 * 8),
+    ]
+
+
+def default_config(**kw):
+    """Reference flag defaults (simulator.cpp:21-27, xworld_simulator.cpp:22-37,
+    simple_game_simulator.cpp:18, simple_race_simulator.cpp:17-26)."""
+    cfg = XwConfig()
+    cfg.abi_version = XW_ABI_VERSION
+    cfg.game = XW_GAME_XWORLD
+    cfg.height = cfg.width = 8
+    cfg.n_goals, cfg.n_blocks = 4, 16
+    cfg.rules = XW_RULES_NAV3D
+    cfg.context = 1
+    cfg.max_steps = 0
+    cfg.max_steps_factor = 10
+    cfg.array_size = 6
+    cfg.track_width, cfg.track_length, cfg.track_radius = 20.0, 100.0, 30.0
+    cfg.reward_scale = 1.0
+    for k, v in kw.items():
+        if not hasattr(cfg, k):
+            raise TypeError("unknown xw_config field: %s" % k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+_LIB = None
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libxworld_b200.so")
+
+# every symbol include/xworld_b200.h declares
+SYMBOLS = [
+    "xw_config_init", "xw_create", "xw_destroy", "xw_last_error", "xw_reset", "xw_step", "xw_render",
+    "xw_step_host", "xw_reset_host", "xw_num_envs", "xw_num_actions", "xw_screen_dims",
+    "xw_frame_bytes", "xw_num_steps", "xw_get_field", "xw_set_field", "xw_launch_count",
+    "xw_enable_timing", "xw_render_ms",
+]
+
+
+def load():
+    """dlopen the in-tree CUDA library and declare the prototypes.  Fails loudly if absent."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "xworld_b200: %s not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+            "there is no CPU fallback" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    lib.xw_config_init.argtypes = [C.POINTER(XwConfig)]
+    lib.xw_config_init.restype = None
+    lib.xw_create.argtypes = [C.POINTER(XwConfig), C.POINTER(XwCatalog), i32, i32, C.POINTER(vp)]
+    lib.xw_create.restype = C.c_int
+    lib.xw_destroy.argtypes = [vp]
+    lib.xw_destroy.restype = None
+    lib.xw_last_error.argtypes = []
+    lib.xw_last_error.restype = C.c_char_p
+    lib.xw_reset.argtypes = [vp, vp, vp]
+    lib.xw_reset.restype = C.c_int
+    lib.xw_step.argtypes = [vp, vp, i32, vp, vp, vp, vp]
+    lib.xw_step.restype = C.c_int
+    lib.xw_render.argtypes = [vp, vp, vp]
+    lib.xw_render.restype = C.c_int
+    lib.xw_step_host.argtypes = [vp, vp, i32, vp, vp, vp]
+    lib.xw_step_host.restype = C.c_int
+    lib.xw_reset_host.argtypes = [vp, vp, vp]
+    lib.xw_reset_host.restype = C.c_int
+    lib.xw_num_envs.argtypes = [vp]
+    lib.xw_num_envs.restype = i32
+    lib.xw_num_actions.argtypes = [vp]
+    lib.xw_num_actions.restype = i32
+    lib.xw_screen_dims.argtypes = [vp] + [C.POINTER(i32)] * 4
+    lib.xw_screen_dims.restype = C.c_int
+    lib.xw_frame_bytes.argtypes = [vp]
+    lib.xw_frame_bytes.restype = C.c_size_t
+    lib.xw_num_steps.argtypes = [vp, vp]
+    lib.xw_num_steps.restype = C.c_int
+    lib.xw_get_field.argtypes = [vp, C.c_char_p, vp, C.c_size_t]
+    lib.xw_get_field.restype = C.c_int
+    lib.xw_set_field.argtypes = [vp, C.c_char_p, vp, C.c_size_t]
+    lib.xw_set_field.restype = C.c_int
+    lib.xw_launch_count.argtypes = [vp]
+    lib.xw_launch_count.restype = i64
+    lib.xw_enable_timing.argtypes = [vp, i32]
+    lib.xw_enable_timing.restype = C.c_int
+    lib.xw_render_ms.argtypes = [vp, i32]
+    lib.xw_render_ms.restype = C.c_double
+    _LIB = lib
+    return lib
