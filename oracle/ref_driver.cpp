@@ -1,0 +1,120 @@
+// ref_driver.cpp -- C entry points over the REFERENCE's own translation units, compiled unmodified
+// from /root/reference against oracle/shim (see oracle/Makefile).  TEST INFRASTRUCTURE ONLY.
+//
+// Exposes: SimpleGame (games/simple_game), SimpleRaceGame physics (games/simple_race), XMap/XAgent
+// step logic (games/xworld/xworld/xmap.cpp, xitem.cpp) and util::get_rand_ind (simulator_util.cpp).
+#include <cstring>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#include "games/simple_game/simple_game_simulator.h"
+#include "games/simple_race/simple_race_simulator.h"
+#include "games/xworld/xworld/xmap.h"
+#include "simulator_util.h"
+
+DECLARE_int32(array_size);
+DECLARE_int32(simulator_seed);
+DECLARE_int32(max_steps);
+DECLARE_string(track_type);
+DECLARE_double(track_width);
+DECLARE_double(track_length);
+DECLARE_double(track_radius);
+DECLARE_bool(race_full_manouver);
+DECLARE_bool(random);
+DECLARE_string(difficulty);
+DECLARE_double(reward_scale);
+DEFINE_int32(visible_radius, 0, "xworld_simulator.cpp:26 (that TU is not compiled here)");
+
+using namespace simulator;
+
+extern "C" {
+
+// ---- SimpleGame through the GameSimulator interface (tests/test_simple_game_simulator.cpp) ----
+void* ref_sg_create(int array_size) { FLAGS_array_size = array_size; return new simple_game::SimpleGame(); }
+void ref_sg_destroy(void* p) { delete (simple_game::SimpleGame*)p; }
+void ref_sg_reset(void* p) { ((simple_game::SimpleGame*)p)->reset_game(); }
+float ref_sg_take_action(void* p, int a) {
+    StatePacket act;
+    act.add_buffer_id("action", {a});
+    return ((simple_game::SimpleGame*)p)->take_action(act);
+}
+int ref_sg_game_over(void* p) { return ((simple_game::SimpleGame*)p)->game_over(); }
+void ref_sg_screen(void* p, uint8_t* out, int n) {
+    StatePacket s;
+    ((simple_game::SimpleGame*)p)->get_screen(s);
+    std::memcpy(out, s.get_buffer("screen")->get_value<uint8_t>(), n);
+}
+
+// ---- SimpleRace ----
+void* ref_race_create(int track_type, double width, double length, double radius, int full, int hard, double scale, int max_steps) {
+    FLAGS_track_type = track_type == 0 ? "straight" : "circle";
+    FLAGS_track_width = width; FLAGS_track_length = length; FLAGS_track_radius = radius;
+    FLAGS_race_full_manouver = full != 0; FLAGS_random = false;
+    FLAGS_difficulty = hard ? "hard" : "easy"; FLAGS_reward_scale = scale; FLAGS_max_steps = max_steps;
+    return new simple_race::SimpleRaceGame();
+}
+void ref_race_destroy(void* p) { delete (simple_race::SimpleRaceGame*)p; }
+void ref_race_reset(void* p) { ((simple_race::SimpleRaceGame*)p)->reset_game(); }
+float ref_race_step(void* p, int action_index, float* state4, int* game_over) {
+    auto* g = (simple_race::SimpleRaceGame*)p;
+    StatePacket act;
+    act.add_buffer_id("action", {action_index});
+    float r = g->take_action(act);
+    StatePacket s;
+    g->get_screen(s);
+    std::memcpy(state4, s.get_buffer("screen")->get_value<float>(), 4 * sizeof(float));
+    *game_over = g->game_over();
+    return r;
+}
+
+// ---- XMap + XAgent (xmap.cpp:76-101, xitem.cpp:89-155) ----
+struct RefMap {
+    xwd::XMap map;
+    std::vector<xwd::XItemPtr> items;
+    xwd::XItemPtr agent;
+};
+// types[i]: 0 block, 1 goal, 2 agent; ids are "e<i>"
+void* ref_map_create(int h, int w, int n, const int* types, const int* xs, const int* ys, double agent_yaw, int visible_radius) {
+    FLAGS_visible_radius = visible_radius;
+    RefMap* m = new RefMap();
+    m->map = xwd::XMap(h, w);
+    for (int i = 0; i < n; ++i) {
+        Entity e;
+        e.type = types[i] == 0 ? "block" : types[i] == 1 ? "goal" : "agent";
+        e.id = "e" + std::to_string(i);
+        e.loc = Vec3(xs[i], ys[i], 0);
+        e.yaw = types[i] == 2 ? agent_yaw : 1.5707963;
+        e.scale = 1.0; e.offset = 0.0;
+        e.name = e.type; e.asset_path = ""; e.color = "na";
+        auto it = xwd::XItem::create_item(e);
+        m->items.push_back(it);
+        if (types[i] == 2) m->agent = it;
+    }
+    m->map.add_items(m->items);
+    return m;
+}
+void ref_map_destroy(void* p) { delete (RefMap*)p; }
+// XWorld::act (xworld.cpp:162-166).  contact = index of the first contacted entity or -1.
+int ref_map_act(void* p, int action, int* ax, int* ay, double* yaw, int* contact, int* n_contacts) {
+    RefMap* m = (RefMap*)p;
+    std::vector<std::string> contacts;
+    xwd::Loc target = m->agent->act(action);
+    bool ok = m->map.move_item(m->agent, target, contacts);
+    xwd::Loc l = m->agent->get_item_location();
+    *ax = l.x; *ay = l.y; *yaw = m->agent->get_item_yaw();
+    *n_contacts = (int)contacts.size();
+    *contact = contacts.empty() ? -1 : std::stoi(contacts[0].substr(1));
+    return ok ? 1 : 0;
+}
+int ref_map_num_actions(void* p) { return ((RefMap*)p)->agent->get_num_actions(); }
+
+// ---- util::get_rand_ind on fresh threads (tests/test_simulator_seed.cpp) ----
+void ref_rand_ind_threads(int simulator_seed, int n_threads, int size, int* out) {
+    FLAGS_simulator_seed = simulator_seed;
+    for (int i = 0; i < n_threads; ++i) {
+        std::thread th([&, i]() { out[i] = util::get_rand_ind(size); });
+        th.join();
+    }
+}
+}

@@ -667,6 +667,13 @@ int xo_reset(const xw_config* cfg, const xw_catalog* cat, xo_env* e) {
         if (rc) return rc;
         double r;
         xo_teach(cfg, cat, e, 0, &r);
+        /* bookkeeping only (the engine keeps these per-episode constants in aux1/aux2; the
+         * restatement above recomputes reachability at every idle stage, as the reference does) */
+        e->aux1 = e->aux2 = 0;
+        for (int g = 0; g < e->n_goals; ++g) {
+            if (reachable(e, cell_of(e, e->agent_x, e->agent_y), cell_of(e, e->goal_x[g], e->goal_y[g]), 0)) e->aux1 |= 1 << g;
+            if (cat->icon_colored[e->goal_icon[g]]) e->aux2 |= 1 << g;
+        }
     }
     return 0;
 }
@@ -914,7 +921,7 @@ static void race_track_init(const xw_config* cfg, race_track* t) {
         t->outer = t->inner + t->width;
     }
 }
-static float race_norm(float x, float y) { return (float)sqrt((double)x * x + (double)y * y); }
+static double race_norm(float x, float y) { return sqrt((double)x * x + (double)y * y); } /* cv::norm(Point2f) -> double */
 
 void xo_race_reset(const xw_config* cfg, xo_race* r) { /* RaceEngine::reset_game :267-284, random=false */
     race_track t;
@@ -928,12 +935,12 @@ void xo_race_reset(const xw_config* cfg, xo_race* r) { /* RaceEngine::reset_game
 static int race_out_of_bound(const xw_config* cfg, const race_track* t, float px, float py) {
     if (cfg->track_type == 0) /* :182-186 */
         return (px < t->mid_x - t->width / 2) || (px > t->mid_x + t->width / 2) || (py < t->start_y) || (py > t->end_y);
-    float rr = race_norm(px - t->mid_x, py - t->mid_y); /* :72-76 */
+    float rr = (float)race_norm(px - t->mid_x, py - t->mid_y); /* :72-76 */
     return rr < t->inner || rr > t->outer;
 }
 static float race_hdisp(const xw_config* cfg, const race_track* t, float px, float py) {
     if (cfg->track_type == 0) return 2 * (px - t->mid_x) / t->width; /* :204-206 */
-    return (float)((2 * (double)race_norm(px - t->mid_x, py - t->mid_y) - t->inner - t->outer) / t->width); /* :88-91 */
+    return (float)((2 * race_norm(px - t->mid_x, py - t->mid_y) - t->inner - t->outer) / t->width); /* :88-91 */
 }
 static float race_vdisp(const xw_config* cfg, const race_track* t, float px, float py) {
     (void)px;
@@ -943,7 +950,7 @@ static float race_vdisp(const xw_config* cfg, const race_track* t, float px, flo
 static void race_tangent(const xw_config* cfg, const race_track* t, float px, float py, float* tx, float* ty) {
     if (cfg->track_type == 0) { *tx = 0.0f; *ty = 1.0f; return; } /* :220-222 */
     float ax = t->mid_y - py, ay = px - t->mid_x;              /* :97-100 */
-    double s = 1 / (double)race_norm(ax, ay);
+    double s = 1 / race_norm(ax, ay);
     *tx = (float)(ax * s); *ty = (float)(ay * s);
 }
 

@@ -1,0 +1,183 @@
+// hostsim.cpp -- TEST-ONLY host build of the engine's per-env device functions
+// (xworld_b200/csrc/*.cuh compiled with XW_HD = inline).  It lets the CPU test-suite run the exact
+// code the CUDA kernels inline -- reset, step, compose, straddle fix-up -- against the oracle in a
+// container without a GPU.  It is NOT a product path: nothing in xworld_b200/ loads it, and the C ABI
+// returns XW_ERR_NO_DEVICE when there is no GPU.
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../xworld_b200/csrc/xw_common.cuh"
+#include "../../xworld_b200/csrc/xw_race.cuh"
+#include "../../xworld_b200/csrc/xw_render.cuh"
+#include "../../xworld_b200/csrc/xw_render_host.hpp"
+#include "../../xworld_b200/csrc/xw_reset.cuh"
+#include "../../xworld_b200/csrc/xw_step.cuh"
+
+struct HostSim {
+    xw_config cfg;
+    XwDev d;
+    XwRender r;
+    XwRenderTables tab;
+    std::vector<std::vector<uint8_t>> bufs;
+    std::vector<uint8_t> T;
+    XwRaceCfg race;
+};
+
+template <typename T>
+static T* halloc(HostSim* s, size_t count) {
+    s->bufs.emplace_back(count * sizeof(T) + 16, 0);
+    return (T*)s->bufs.back().data();
+}
+
+static uint32_t minstd_seed(int32_t simulator_seed, int64_t thread_no) {
+    int32_t seed = (int32_t)(uint32_t)std::hash<std::string>()(std::to_string((int)(simulator_seed + thread_no)));
+    uint64_t x = ((uint64_t)(int64_t)seed) % 2147483647ull;
+    return x == 0 ? 1u : (uint32_t)x;
+}
+
+extern "C" {
+
+HostSim* hs_create(const xw_config* c, const xw_catalog* cat, int n) {
+    HostSim* s = new HostSim();
+    s->cfg = *c;
+    if (c->game == XW_GAME_SIMPLE_RACE) {
+        XwRaceCfg& r = s->race;
+        memset(&r, 0, sizeof r);
+        r.n = n; r.track_type = c->track_type; r.full_manouver = c->race_full_manouver; r.difficulty = c->difficulty;
+        r.max_steps = c->max_steps; r.auto_reset = c->auto_reset; r.reward_scale = (double)c->reward_scale;
+        r.mid_x = 480 / 2; r.mid_y = 720 / 2;
+        if (c->track_type == 0) {
+            r.length = c->track_length; r.width = c->track_width;
+            r.start_y = r.mid_y - (float)(0.4 * r.length);
+            r.end_y = r.mid_y + (float)(0.6 * r.length);
+            r.start_px = r.mid_x - 0.0f; r.start_py = r.start_y;
+        } else {
+            r.inner = c->track_radius; r.width = c->track_width; r.outer = r.inner + r.width;
+            r.start_px = (r.inner + r.width / 2) + r.mid_x; r.start_py = 0.0f + r.mid_y;
+        }
+        r.pos_x = halloc<float>(s, n); r.pos_y = halloc<float>(s, n); r.angle = halloc<float>(s, n);
+        r.state = halloc<float>(s, (size_t)n * 4); r.steps = halloc<int32_t>(s, n);
+        return s;
+    }
+    XwDev& d = s->d;
+    memset(&d, 0, sizeof d);
+    d.n = n; d.H = c->height; d.W = c->width; d.CS = (c->height * c->width + 15) & ~15;
+    d.G = c->n_goals; d.n_blocks = c->n_blocks; d.rules = c->rules; d.max_steps = c->max_steps;
+    d.max_steps_factor = c->max_steps_factor; d.auto_reset = c->auto_reset; d.seed = c->seed; d.gid0 = c->env_id_offset;
+    d.grid = halloc<uint8_t>(s, (size_t)n * d.CS);
+    uint8_t** u8s[] = {&d.agent_x, &d.agent_y, &d.facing, &d.task, &d.stage, &d.event, &d.succ, &d.tmask, &d.aux0, &d.aux1, &d.aux2};
+    for (auto p : u8s) *p = halloc<uint8_t>(s, n);
+    d.goal_x = halloc<uint8_t>(s, (size_t)n * XW_MAX_GOALS); d.goal_y = halloc<uint8_t>(s, (size_t)n * XW_MAX_GOALS);
+    d.goal_icon = halloc<int32_t>(s, (size_t)n * XW_MAX_GOALS); d.goal_name = halloc<int32_t>(s, (size_t)n * XW_MAX_GOALS);
+    int32_t** i32s[] = {&d.steps_in_task, &d.num_steps, &d.episode, &d.n_success, &d.n_failure, &d.success_steps, &d.error};
+    for (auto p : i32s) *p = halloc<int32_t>(s, n);
+    d.minstd = halloc<uint32_t>(s, n);
+    d.reset_count = halloc<int32_t>(s, 2); d.reset_list = halloc<int32_t>(s, n);
+    for (int i = 0; i < n; ++i) d.minstd[i] = minstd_seed(c->simulator_seed, c->env_id_offset + i + 1);
+    d.n_names = cat->n_names; d.brick_icon = cat->brick_icon; d.agent_icon = cat->agent_icon;
+    d.name_first = cat->name_first; d.name_icons = cat->name_icons; d.icon_colored = cat->icon_colored;
+    int OH = c->out_h > 0 ? c->out_h : c->height * 12, OW = c->out_w > 0 ? c->out_w : c->width * 12;
+    s->tab = xw_build_render_tables(c->height, c->width, OH, OW);
+    XwRenderTables& t = s->tab;
+    XwRender& r = s->r;
+    memset(&r, 0, sizeof r);
+    r.OH = OH; r.OW = OW; r.WR = t.WR; r.FB = t.FB; r.H = c->height; r.W = c->width; r.R = t.R; r.rpg = t.rpg;
+    r.n_sc = (int)t.sc.size(); r.n_sr = (int)t.sr.size();
+    r.n_icons = cat->n_icons; r.brick_icon = cat->brick_icon; r.agent_icon = cat->agent_icon;
+    r.xofs = t.xofs.data(); r.xa0 = t.xa0.data(); r.xa1 = t.xa1.data();
+    r.yofs = t.yofs.data(); r.ya0 = t.ya0.data(); r.ya1 = t.ya1.data();
+    r.rowcell = t.rowcell.data(); r.bandend = t.bandend.data(); r.colpair = t.colpair.data();
+    r.sc = t.sc.data(); r.sr = t.sr.data();
+    r.atlas64 = cat->atlas64;
+    return s;
+}
+
+// Build the phase atlas only for the icons in use (the full 363-icon table takes a while on one core).
+void hs_build_phase_atlas(HostSim* s, const int32_t* icons, int n_icons) {
+    XwRender& r = s->r;
+    s->T.assign((size_t)r.n_icons * r.FB, 0);
+    r.T = s->T.data();
+    for (int q = 0; q < n_icons; ++q) {
+        int icon = icons[q];
+        for (int i = 0; i < r.FB; ++i) {
+            int c = i / (r.OH * r.OW), p = i % (r.OH * r.OW);
+            s->T[(size_t)icon * r.FB + i] = xw_phase_px(r, icon, c, p / r.OW, p % r.OW);
+        }
+    }
+}
+
+int hs_fast_ok(HostSim* s) { return s->tab.fast_ok; }
+int hs_threads(HostSim* s) { return s->tab.threads; }
+void hs_destroy(HostSim* s) { delete s; }
+
+void hs_reset(HostSim* s, const uint8_t* mask) {
+    if (s->cfg.game == XW_GAME_SIMPLE_RACE) { for (int e = 0; e < s->race.n; ++e) if (!mask || mask[e]) xw_race_reset_env(s->race, e); return; }
+    for (int e = 0; e < s->d.n; ++e) if (!mask || mask[e]) xw_reset_env(s->d, e);
+}
+
+void hs_step(HostSim* s, const int32_t* actions, int act_rep, float* reward, int32_t* over) {
+    if (s->cfg.game == XW_GAME_SIMPLE_RACE) {
+        for (int e = 0; e < s->race.n; ++e) if (xw_race_step_env(s->race, e, actions[e], &reward[e], &over[e])) xw_race_reset_env(s->race, e);
+        return;
+    }
+    for (int e = 0; e < s->d.n; ++e)
+        if (xw_step_env(s->d, e, actions[e], act_rep, &reward[e], &over[e])) xw_reset_env(s->d, e);
+}
+
+// Emulates one k_render CTA per env: celldesc, compose for every tid, fix-up list, copy out.
+void hs_render(HostSim* s, uint8_t* frames) {
+    XwRender& r = s->r;
+    XwDev& d = s->d;
+    std::vector<uint32_t> cell(XW_MAX_DIM * XW_MAX_DIM), fb(r.FB / 4 + 4);
+    const uint8_t* hot = r.T + (size_t)r.brick_icon * r.FB;
+    for (int e = 0; e < d.n; ++e) {
+        for (int c = 0; c < d.H * d.W; ++c) cell[c] = xw_cell_desc(d, e, d.grid[(size_t)e * d.CS + c]);
+        std::fill(fb.begin(), fb.end(), 0x5a5a5a5au);
+        for (int tid = 0; tid < s->tab.threads; ++tid)
+            xw_compose_thread(r, tid, cell.data(), r.rowcell, r.bandend, r.colpair, hot, fb.data());
+        for (int i = 0; i < xw_fix_count(r); ++i) xw_fix_item(r, i, cell.data(), r.sc, r.sr, (uint8_t*)fb.data());
+        memcpy(frames + (size_t)e * r.FB, fb.data(), r.FB);
+    }
+}
+
+// test-only: overwrite env 0's grid and goal icons (golden-frame tests)
+void hs_set_grid(HostSim* s, const uint8_t* grid, const int32_t* goal_icons) {
+    memcpy(s->d.grid, grid, (size_t)s->d.H * s->d.W);
+    for (int k = 0; k < s->d.G; ++k) s->d.goal_icon[(size_t)k * s->d.n] = goal_icons[k];
+}
+
+int hs_get_field(HostSim* s, const char* name, void* out) {
+    XwDev& d = s->d;
+    std::string k(name);
+    size_t n = d.n;
+    if (s->cfg.game == XW_GAME_SIMPLE_RACE) {
+        XwRaceCfg& r = s->race;
+        n = r.n;
+        if (k == "pos_x") memcpy(out, r.pos_x, 4 * n); else if (k == "pos_y") memcpy(out, r.pos_y, 4 * n);
+        else if (k == "angle") memcpy(out, r.angle, 4 * n); else if (k == "steps") memcpy(out, r.steps, 4 * n);
+        else if (k == "state") memcpy(out, r.state, 16 * n); else return -1;
+        return 0;
+    }
+    if (k == "grid") { for (size_t e = 0; e < n; ++e) memcpy((uint8_t*)out + e * d.H * d.W, d.grid + e * d.CS, d.H * d.W); return 0; }
+    struct { const char* nm; uint8_t* p; } u8t[] = {{"agent_x", d.agent_x}, {"agent_y", d.agent_y}, {"facing", d.facing}, {"task", d.task},
+        {"stage", d.stage}, {"event", d.event}, {"action_success", d.succ}, {"target_mask", d.tmask}, {"aux0", d.aux0}, {"aux1", d.aux1}, {"aux2", d.aux2}};
+    for (auto& t : u8t) if (k == t.nm) { memcpy(out, t.p, n); return 0; }
+    struct { const char* nm; void* p; } i32t[] = {{"steps_in_task", d.steps_in_task}, {"num_steps", d.num_steps}, {"episode", d.episode},
+        {"n_success", d.n_success}, {"n_failure", d.n_failure}, {"success_steps", d.success_steps}, {"minstd", d.minstd}, {"error", d.error}};
+    for (auto& t : i32t) if (k == t.nm) { memcpy(out, t.p, 4 * n); return 0; }
+    if (k == "goal_x" || k == "goal_y") {
+        uint8_t* src = k == "goal_x" ? d.goal_x : d.goal_y;
+        for (size_t g = 0; g < XW_MAX_GOALS; ++g) for (size_t e = 0; e < n; ++e) ((uint8_t*)out)[e * XW_MAX_GOALS + g] = src[g * n + e];
+        return 0;
+    }
+    if (k == "goal_icon" || k == "goal_name") {
+        int32_t* src = k == "goal_icon" ? d.goal_icon : d.goal_name;
+        for (size_t g = 0; g < XW_MAX_GOALS; ++g) for (size_t e = 0; e < n; ++e) ((int32_t*)out)[e * XW_MAX_GOALS + g] = src[g * n + e];
+        return 0;
+    }
+    return -1;
+}
+}

@@ -1,0 +1,173 @@
+"""Parity harness shared by the CPU (hostsim) and GPU (C ABI) tests: drives a backend and the
+oracle with the same seeded action stream and compares every output bit for bit."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+import oracle
+from xworld_b200 import _abi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+U8 = ["agent_x", "agent_y", "facing", "task", "stage", "event", "action_success", "target_mask", "aux0", "aux1", "aux2"]
+I32 = ["steps_in_task", "num_steps", "episode", "n_success", "n_failure", "success_steps", "minstd"]
+
+CONFIGS = {
+    # BASELINE.json configs: C2, C3, C4 + the reference's own 8x8 default
+    "c2_nav3d_7x7_84": dict(height=7, width=7, n_goals=4, n_blocks=12, rules=_abi.XW_RULES_NAV3D),
+    "c3_nav2d_11x11_84": dict(height=11, width=11, n_goals=4, n_blocks=30, rules=_abi.XW_RULES_NAV2D, out_h=84, out_w=84,
+                              max_steps=242),
+    "c4_nav3d_15x15_128": dict(height=15, width=15, n_goals=4, n_blocks=56, rules=_abi.XW_RULES_NAV3D, out_h=128, out_w=128),
+    "ref_nav3d_8x8_96": dict(height=8, width=8, n_goals=4, n_blocks=16, rules=_abi.XW_RULES_NAV3D),
+    "ref_nav2d_8x8_96": dict(height=8, width=8, n_goals=4, n_blocks=16, rules=_abi.XW_RULES_NAV2D, max_steps=64),
+}
+
+
+def make_cfg(name, **over):
+    kw = dict(CONFIGS[name])
+    kw.setdefault("seed", 1234)
+    kw.setdefault("simulator_seed", 1)
+    kw.update(over)
+    return _abi.default_config(**kw)
+
+
+def actions_for(step, n, n_actions, seed=99):
+    """i.i.d. uniform actions, a pure function of (seed, step)."""
+    return np.random.RandomState((seed * 1000003 + step) % (2 ** 31)).randint(0, n_actions, size=n).astype(np.int32)
+
+
+class HostSim(object):
+    """tests/hostsim/libhostsim.so: the engine's per-env device functions compiled for the host."""
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            src = os.path.join(HERE, "hostsim", "hostsim.cpp")
+            so = os.path.join(HERE, "hostsim", "libhostsim.so")
+            deps = [src] + [os.path.join(HERE, "..", "xworld_b200", "csrc", f)
+                            for f in os.listdir(os.path.join(HERE, "..", "xworld_b200", "csrc"))]
+            if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
+                subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src])
+            L = C.CDLL(so)
+            L.hs_create.restype = C.c_void_p
+            L.hs_create.argtypes = [C.POINTER(_abi.XwConfig), C.POINTER(_abi.XwCatalog), C.c_int]
+            L.hs_destroy.argtypes = [C.c_void_p]
+            L.hs_reset.argtypes = [C.c_void_p, C.c_void_p]
+            L.hs_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+            L.hs_render.argtypes = [C.c_void_p, C.c_void_p]
+            L.hs_get_field.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+            L.hs_build_phase_atlas.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+            L.hs_fast_ok.argtypes = [C.c_void_p]
+            L.hs_threads.argtypes = [C.c_void_p]
+            cls._lib = L
+        return cls._lib
+
+    def __init__(self, cfg, catalog, n):
+        self.L = self.lib()
+        self.cfg, self.catalog, self.n = cfg, catalog, n
+        self.cat_c = catalog.as_c() if catalog is not None else None
+        self.h = self.L.hs_create(C.byref(cfg), C.byref(self.cat_c) if catalog is not None else None, n)
+        self.out_h = cfg.out_h or cfg.height * 12
+        self.out_w = cfg.out_w or cfg.width * 12
+        self._atlas_icons = set()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.hs_destroy(self.h)
+            self.h = None
+
+    def reset(self, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        self.L.hs_reset(self.h, None if m is None else m.ctypes.data)
+
+    def step(self, actions, act_rep=1, render=False):
+        a = np.ascontiguousarray(actions, np.int32)
+        r = np.zeros(self.n, np.float32)
+        o = np.zeros(self.n, np.int32)
+        self.L.hs_step(self.h, a.ctypes.data, act_rep, r.ctypes.data, o.ctypes.data)
+        return r, o, (self.render() if render else None)
+
+    def render(self):
+        icons = set(self.field("goal_icon")[:, :self.cfg.n_goals].ravel().tolist())
+        icons |= {self.catalog.brick_icon, self.catalog.agent_icon}
+        if not icons <= self._atlas_icons:
+            self._atlas_icons |= icons
+            arr = np.array(sorted(self._atlas_icons), np.int32)
+            self.L.hs_build_phase_atlas(self.h, arr.ctypes.data, len(arr))
+        out = np.zeros((self.n, 3, self.out_h, self.out_w), np.uint8)
+        self.L.hs_render(self.h, out.ctypes.data)
+        return out
+
+    def field(self, name):
+        n = self.n
+        if name == "grid":
+            out = np.zeros((n, self.cfg.height * self.cfg.width), np.uint8)
+        elif name in ("goal_x", "goal_y"):
+            out = np.zeros((n, _abi.XW_MAX_GOALS), np.uint8)
+        elif name in ("goal_icon", "goal_name"):
+            out = np.zeros((n, _abi.XW_MAX_GOALS), np.int32)
+        elif name in U8:
+            out = np.zeros(n, np.uint8)
+        elif name == "state":
+            out = np.zeros((n, 4), np.float32)
+        elif name in ("pos_x", "pos_y", "angle"):
+            out = np.zeros(n, np.float32)
+        else:
+            out = np.zeros(n, np.int32)
+        rc = self.L.hs_get_field(self.h, name.encode(), out.ctypes.data)
+        assert rc == 0, name
+        return out
+
+
+def compare_state(backend, orc, tag=""):
+    G = orc.cfg.n_goals
+    for f in ["grid"] + U8 + I32:
+        a, b = backend.field(f), orc.field(f)
+        if f == "minstd":
+            a, b = a.astype(np.uint32), b.astype(np.uint32)
+        bad = np.nonzero(np.atleast_2d(a.reshape(len(a), -1) != b.reshape(len(b), -1)).any(axis=1))[0]
+        assert bad.size == 0, "%s field %s differs for envs %s: got %s want %s" % (
+            tag, f, bad[:5], a[bad[:3]], b[bad[:3]])
+    for f in ["goal_x", "goal_y", "goal_icon"]:
+        a, b = backend.field(f)[:, :G], orc.field(f)[:, :G]
+        assert (a == b).all(), "%s field %s differs" % (tag, f)
+
+
+def run_parity(backend, orc, n_steps, render_every=0, act_rep=1, check_state_every=1, auto_reset=False, seed=99):
+    """Same actions into both; compare reward bits, game_over, state, frames.  Returns stats."""
+    n = orc.n
+    backend.reset()
+    orc.reset()
+    compare_state(backend, orc, "after reset")
+    stats = {"events": {}, "frames": 0, "resets": 0}
+    if render_every:
+        fa, fb = backend.render(), orc.render()
+        assert (fa == fb).all(), "first frame differs: %d px" % (fa != fb).sum()
+        stats["frames"] += n
+    for s in range(n_steps):
+        a = actions_for(s, n, 4, seed)
+        do_render = bool(render_every) and (s % render_every == 0)
+        r1, o1, f1 = backend.step(a, act_rep, render=do_render)
+        r2, o2, f2 = orc.step(a, act_rep, render=do_render)
+        assert (r1.view(np.uint32) == r2.view(np.uint32)).all(), "step %d reward bits differ: %s vs %s" % (
+            s, r1[(r1.view(np.uint32) != r2.view(np.uint32))][:4], r2[(r1.view(np.uint32) != r2.view(np.uint32))][:4])
+        assert (o1 == o2).all(), "step %d game_over differs" % s
+        for v in np.unique(o2):
+            stats["events"][int(v)] = stats["events"].get(int(v), 0) + int((o2 == v).sum())
+        if not auto_reset and (o2 != 0).any():  # reference behaviour: the caller resets finished games
+            m = (o2 != 0)
+            backend.reset(m)
+            orc.reset(m)
+            stats["resets"] += int(m.sum())
+            if do_render:
+                f1, f2 = backend.render(), orc.render()
+        if check_state_every and s % check_state_every == 0:
+            compare_state(backend, orc, "step %d" % s)
+        if do_render:
+            assert (f1 == f2).all(), "step %d: %d frame bytes differ" % (s, (f1 != f2).sum())
+            stats["frames"] += n
+    compare_state(backend, orc, "final")
+    return stats

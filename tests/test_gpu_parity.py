@@ -1,0 +1,206 @@
+"""The parity tests proper: the CUDA engine, called through the C ABI, against the oracle on the
+same seeded inputs -- bit-exact state / reward bits / game_over, pixel-exact frames."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+import parity
+from test_oracle_render import golden_cases
+from xworld_b200 import Simulator, _abi
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def backend_cls():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from gpu_backend import EngineBackend
+    return EngineBackend
+
+
+@pytest.mark.parametrize("name", sorted(parity.CONFIGS))
+def test_engine_matches_oracle(name, backend_cls, synthetic_catalog):
+    cfg = parity.make_cfg(name)
+    n = 1024 if cfg.height <= 8 else 512
+    eng = backend_cls(cfg, synthetic_catalog, n)
+    orc = oracle.Oracle(cfg, synthetic_catalog, n, threads=8)
+    stats = parity.run_parity(eng, orc, 128, render_every=16, check_state_every=8)
+    assert stats["frames"] >= 8 * n
+    assert eng.sim.launch_count() > 128
+
+
+def test_config2_full_size_256_steps(backend_cls, synthetic_catalog):
+    """BASELINE config 2: 7x7, 84x84x3, 4096 envs, bit-exact over 256 steps."""
+    cfg = parity.make_cfg("c2_nav3d_7x7_84")
+    eng = backend_cls(cfg, synthetic_catalog, 4096)
+    orc = oracle.Oracle(cfg, synthetic_catalog, 4096, threads=8)
+    stats = parity.run_parity(eng, orc, 256, render_every=64, check_state_every=32)
+    assert stats["events"].get(_abi.XW_SUCCESS, 0) > 0 and stats["events"].get(_abi.XW_DEAD, 0) > 0
+
+
+def test_auto_reset_and_act_rep(backend_cls, synthetic_catalog):
+    cfg = parity.make_cfg("c2_nav3d_7x7_84", auto_reset=1, max_steps=30)
+    eng = backend_cls(cfg, synthetic_catalog, 2048)
+    orc = oracle.Oracle(cfg, synthetic_catalog, 2048, threads=8)
+    st = parity.run_parity(eng, orc, 100, render_every=25, auto_reset=True, check_state_every=10)
+    assert st["events"].get(_abi.XW_MAX_STEP, 0) > 0
+    cfg = parity.make_cfg("c3_nav2d_11x11_84", auto_reset=1)
+    eng = backend_cls(cfg, synthetic_catalog, 512)
+    orc = oracle.Oracle(cfg, synthetic_catalog, 512, threads=8)
+    parity.run_parity(eng, orc, 300, render_every=100, auto_reset=True, act_rep=2, check_state_every=50)
+
+
+def test_golden_frames_from_real_opencv(backend_cls):
+    """The GPU compositor vs frames the real OpenCV produced from the reference call sequence."""
+    n = 0
+    for tag, cfg, cat, grid, gi, want in golden_cases():
+        eng = backend_cls(cfg, cat, 1)
+        eng.reset()
+        eng.sim.set_field("grid", np.asarray(grid, np.uint8)[None, :])
+        icons = np.zeros((1, _abi.XW_MAX_GOALS), np.int32)
+        icons[0, :4] = gi
+        eng.sim.set_field("goal_icon", icons)
+        got = eng.render()[0]
+        assert (got == want).all(), (tag, int((got != want).sum()))
+        n += 1
+    assert n == 12
+
+
+def test_generic_render_path_matches(backend_cls, synthetic_catalog):
+    """Frame sizes the shared-memory compositor does not take (width % 4 != 0) use the generic kernel."""
+    cfg = parity.make_cfg("c2_nav3d_7x7_84", out_h=50, out_w=70)
+    eng = backend_cls(cfg, synthetic_catalog, 64)
+    orc = oracle.Oracle(cfg, synthetic_catalog, 64, threads=4)
+    parity.run_parity(eng, orc, 20, render_every=5)
+
+
+def test_full_size_properties_c3(backend_cls, synthetic_catalog):
+    """BASELINE config 3 at full size (65536 envs): size-independent properties -- every frame is a
+    pure function of (grid, goal icons): envs sampled at random are pixel-exact vs the oracle; the
+    white fraction equals the empty-cell fraction; re-rendering is idempotent."""
+    cfg = parity.make_cfg("c3_nav2d_11x11_84", auto_reset=1)
+    n = 65536
+    eng = backend_cls(cfg, synthetic_catalog, n)
+    eng.reset()
+    for s in range(20):
+        eng.step(parity.actions_for(s, n, 4), render=False)
+    f1 = eng.render()
+    f2 = eng.render()
+    assert (f1 == f2).all()
+    grid, icons = eng.field("grid"), eng.field("goal_icon")
+    assert ((grid == _abi.XW_CELL_AGENT).sum(axis=1) == 1).all() and ((grid == _abi.XW_CELL_BLOCK).sum(axis=1) == 30).all()
+    rng = np.random.RandomState(0)
+    lib = oracle.lib()
+    for i in rng.choice(n, 64, replace=False):
+        e = oracle.XoEnv()
+        lib.xo_env_init(C.byref(cfg), C.byref(e), 0)
+        for c, v in enumerate(grid[i]):
+            e.grid[c] = int(v)
+        for k in range(4):
+            e.goal_icon[k] = int(icons[i, k])
+        want = np.zeros((3, 84, 84), np.uint8)
+        lib.xo_render(C.byref(cfg), C.byref(synthetic_catalog.as_c()), C.byref(e), want.ctypes.data)
+        assert (f1[i] == want).all(), i
+
+
+def test_sharded_engine_equals_single_batch(backend_cls, synthetic_catalog):
+    from xworld_b200.sharding import shard_range
+    n = 512
+    full = backend_cls(parity.make_cfg("c2_nav3d_7x7_84"), synthetic_catalog, n)
+    full.reset()
+    lo, hi = shard_range(n, 1, 2)
+    part = backend_cls(parity.make_cfg("c2_nav3d_7x7_84", env_id_offset=lo), synthetic_catalog, hi - lo)
+    part.reset()
+    for s in range(20):
+        a = parity.actions_for(s, n, 4)
+        r1, o1, f1 = full.step(a, render=(s == 19))
+        r2, o2, f2 = part.step(a[lo:hi], render=(s == 19))
+        assert (r1[lo:hi].view(np.uint32) == r2.view(np.uint32)).all() and (o1[lo:hi] == o2).all()
+    assert (f1[lo:hi] == f2).all()
+
+
+def test_python_api_single_env(synthetic_catalog, tmp_path):
+    """The reference's Python surface with n_envs == 1 (py_simulator.cpp:310-329)."""
+    conf = tmp_path / "navigation2d.json"
+    conf.write_text('{"item_path": "images", "map": "XWorldNav", "task_groups": {"XWorld3DNav": {"weight": 1, '
+                    '"schedule": "random", "tasks": {"XWorld3DNavTarget": 1, "XWorld3DNavTargetNear": 1, '
+                    '"XWorld3DNavTargetBetween": 1, "XWorld3DNavTargetDirection": 1, "XWorld3DNavTargetAvoid": 1}}}}')
+    opts = {"xwd_conf_path": str(conf), "task_mode": "lang_acquisition", "color": True, "catalog": synthetic_catalog,
+            "simulator_seed": 1, "seed": 1234}
+    sim = Simulator.create("xworld", opts)
+    assert sim.get_num_actions() == 4 and sim.get_screen_out_dimensions() == [96, 96, 3, 1]
+    sim.reset_game()
+    assert sim.game_over() == "alive" and sim.get_lives() == 1
+    st = sim.get_state()
+    assert len(st["screen"]) == 3 * 96 * 96 and 0.0 <= min(st["screen"]) and max(st["screen"]) <= 1.0
+    total = 0.0
+    for s in range(30):
+        r = sim.take_actions({"action": int(s % 4)}, 1, False)
+        assert isinstance(r, float)
+        total += r
+        if sim.game_over() != "alive":
+            break
+    assert sim.get_num_steps() == s + 1
+    with pytest.raises(RuntimeError):
+        Simulator.create("xworld", dict(opts, task_mode="one_channel"))
+    # invalid action: flagged, never aborts (the reference CHECK-fails, xworld_simulator.cpp:254)
+    sim.take_actions({"action": 7})
+    assert sim.get_field("error")[0] == -4
+
+
+def test_context_frames(backend_cls, synthetic_catalog):
+    """--context K: K frames per env, oldest first, newest last (simulator.cpp:51-85)."""
+    cfg = parity.make_cfg("c2_nav3d_7x7_84", context=3)
+    n = 128
+    eng = backend_cls(cfg, synthetic_catalog, n)
+    one = backend_cls(parity.make_cfg("c2_nav3d_7x7_84"), synthetic_catalog, n)
+    eng.reset()
+    one.reset()
+    hist = [one.render().copy()]
+    scr = eng.sim.screen().cpu().numpy()
+    assert (scr[:, :6] == 0).all() and (scr[:, 6:] == hist[0]).all()
+    for s in range(4):
+        a = parity.actions_for(s, n, 4)
+        eng.step(a, render=True)
+        _, _, f = one.step(a, render=True)
+        hist.append(f.copy())
+    scr = eng.sim.screen().cpu().numpy()
+    assert (scr[:, 0:3] == hist[-3]).all() and (scr[:, 3:6] == hist[-2]).all() and (scr[:, 6:9] == hist[-1]).all()
+
+
+def test_simple_race_vs_oracle_1e6(backend_cls):
+    """BASELINE config 5 (tol 1e-6 on reward and the 4-float state); reports exact-bit agreement."""
+    import torch
+    lib = oracle.lib()
+    for tt, full, hard in [(0, 0, 0), (1, 1, 1)]:
+        cfg = _abi.default_config(game=_abi.XW_GAME_SIMPLE_RACE, track_type=tt, race_full_manouver=full, difficulty=hard,
+                                  auto_reset=1)
+        n = 4096
+        eng = backend_cls(cfg, None, n)
+        eng.reset()
+        orcs = (oracle.XoRace * n)()
+        for o in orcs:
+            lib.xo_race_reset(C.byref(cfg), C.byref(o))
+        rng = np.random.RandomState(11)
+        exact = total = 0
+        for s in range(60):
+            a = rng.randint(0, 9 if full else 2, n).astype(np.int32)
+            r, ov, _ = eng.step(a)
+            st = eng.field("state")
+            r2 = np.zeros(n, np.float32)
+            st2 = np.zeros((n, 4), np.float32)
+            ov2 = np.zeros(n, np.int32)
+            for i in range(n):
+                buf, o2 = (C.c_float * 4)(), C.c_int32()
+                r2[i] = lib.xo_race_act(C.byref(cfg), C.byref(orcs[i]), int(a[i]), buf, C.byref(o2))
+                st2[i] = list(buf)
+                ov2[i] = o2.value
+                if o2.value:
+                    lib.xo_race_reset(C.byref(cfg), C.byref(orcs[i]))
+            assert np.abs(r - r2).max() <= 1e-6 and np.abs(st - st2).max() <= 1e-6 and (ov == ov2).all(), (tt, s)
+            exact += int((r.view(np.uint32) == r2.view(np.uint32)).sum())
+            total += n
+        assert exact >= 0.999 * total, (exact, total)

@@ -1,0 +1,91 @@
+// xw_common.cuh -- shared definitions of the batched XWorld2D engine (device state, RNG).
+//
+// State lives in HBM as a structure of arrays indexed by env (one warp lane steps one env, so
+// every scalar field is a coalesced load); the item grid is an [env][cell] byte matrix with a
+// 16-byte-multiple row stride because both its consumers want a whole env's cells at once
+// (render) or one data-dependent cell (step), neither of which a [cell][env] layout coalesces.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/xworld_b200.h"
+
+#if defined(__CUDACC__)
+#define XW_HD __host__ __device__ __forceinline__
+#else
+#define XW_HD inline
+#endif
+
+// Philox substreams: one per reference call site that draws from Python's unseeded `random`
+// (the reference file:line of each site is listed in DESIGN.md §RNG).
+enum {
+    XW_SITE_NAMES = 1, XW_SITE_MAZE = 2, XW_SITE_BLOCKS = 3, XW_SITE_GOAL_LOC = 4, XW_SITE_GOAL_ASSET = 5,
+    XW_SITE_AGENT_LOC = 6, XW_SITE_TASK_A = 7, XW_SITE_TASK_B = 8, XW_SITE_TASK_SHUF = 9, XW_SITE_TASK_AGENT = 10
+};
+
+// directions relative to a heading (XWorld3DNavTargetDirection.__compute_triple_direction)
+enum { XW_DIR_FALSE = 0, XW_DIR_FRONT = 1, XW_DIR_BEHIND = 2, XW_DIR_LEFT = 3, XW_DIR_RIGHT = 4 };
+
+struct XwDev {
+    int32_t n;                 // envs on this device
+    int32_t H, W, CS;          // map size, grid row stride (bytes)
+    int32_t G, n_blocks, rules, max_steps, max_steps_factor, auto_reset;
+    uint64_t seed;
+    int64_t gid0;              // global id of env 0
+    // ---- per-env state (SoA) ----
+    uint8_t* grid;             // [n][CS]
+    uint8_t *agent_x, *agent_y, *facing, *task, *stage, *event, *succ, *tmask, *aux0, *aux1, *aux2;
+    uint8_t *goal_x, *goal_y;  // [XW_MAX_GOALS][n]
+    int32_t* goal_icon;        // [XW_MAX_GOALS][n]
+    int32_t* goal_name;        // [XW_MAX_GOALS][n]
+    int32_t *steps_in_task, *num_steps, *episode, *n_success, *n_failure, *success_steps, *error;
+    uint32_t* minstd;
+    // ---- catalog ----
+    int32_t n_names, brick_icon, agent_icon;
+    const int32_t *name_first, *name_icons;
+    const uint8_t* icon_colored;
+    // ---- auto-reset queue (ping-pong counters) ----
+    int32_t* reset_count;      // [2]
+    int32_t* reset_list;       // [n]
+};
+
+// ------------------------------------------------------------------------------------ RNG
+XW_HD uint32_t xw_mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
+// Philox4x32-10 (Salmon et al. 2011); counter = (env id lo, hi, episode, attempt|site|index/4).
+XW_HD uint32_t xw_draw(uint64_t seed, int64_t gid, uint32_t episode, uint32_t attempt, uint32_t site, uint32_t index) {
+    uint32_t c0 = (uint32_t)(uint64_t)gid, c1 = (uint32_t)((uint64_t)gid >> 32), c2 = episode;
+    uint32_t c3 = ((attempt & 0xffu) << 24) | ((site & 0xffu) << 16) | ((index >> 2) & 0xffffu);
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t h0 = xw_mulhi32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = xw_mulhi32(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    uint32_t lane = index & 3u;
+    return lane == 0 ? c0 : lane == 1 ? c1 : lane == 2 ? c2 : c3;
+}
+XW_HD uint32_t xw_randbelow(uint32_t u, uint32_t n) { return xw_mulhi32(u, n); }
+
+// std::minstd_rand0 step + std::uniform_int_distribution<int>(0, size-1) as libstdc++ evaluates
+// util::get_rand_ind (simulator_util.cpp:66-73) -- the teacher's task sampling stream.
+XW_HD uint32_t xw_minstd_next(uint32_t& s) {
+    s = (uint32_t)(((uint64_t)s * 16807ull) % 2147483647ull);
+    return s;
+}
+XW_HD int32_t xw_get_rand_ind(uint32_t& s, int32_t size) {
+    const uint32_t urngrange = 2147483645u;
+    const uint32_t scaling = urngrange / (uint32_t)size;
+    const uint32_t past = (uint32_t)size * scaling;
+    uint32_t ret;
+    do ret = xw_minstd_next(s) - 1u; while (ret >= past);
+    return (int32_t)(ret / scaling);
+}

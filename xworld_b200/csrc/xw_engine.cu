@@ -1,0 +1,633 @@
+// xw_engine.cu -- the C ABI of include/xworld_b200.h: handle management, kernel launches.
+// Built in-tree as xworld_b200/libxworld_b200.so for sm_100a.  No torch types, no CPU fallback for
+// the CUDA games: every entry point either launches kernels or returns an error.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "xw_common.cuh"
+#include "xw_race.cuh"
+#include "xw_render.cuh"
+#include "xw_render_host.hpp"
+#include "xw_reset.cuh"
+#include "xw_step.cuh"
+
+// ------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_TRY(x)                                                                              \
+    do {                                                                                         \
+        cudaError_t e_ = (x);                                                                    \
+        if (e_ != cudaSuccess) return set_err(XW_ERR_CUDA, "%s: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------ kernels
+// mode: list != NULL -> envs list[0..*count); else every env (optionally filtered by mask)
+__global__ void __launch_bounds__(128) k_reset(XwDev d, const uint8_t* mask, const int32_t* list, const int32_t* count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int e;
+    if (list) { if (i >= *count) return; e = list[i]; }
+    else { if (i >= d.n) return; e = i; if (mask && !mask[e]) return; }
+    xw_reset_env(d, e);
+}
+
+__global__ void __launch_bounds__(256) k_step(XwDev d, const int32_t* __restrict__ actions, int act_rep,
+                                              float* __restrict__ reward, int32_t* __restrict__ over, int parity) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e == 0) d.reset_count[parity ^ 1] = 0;  // consumed by the previous step's reset launch
+    if (e >= d.n) return;
+    float r; int32_t o;
+    bool need = xw_step_env(d, e, actions[e], act_rep, &r, &o);
+    reward[e] = r; over[e] = o;
+    if (need) {  // warp-aggregated append to the auto-reset queue
+        unsigned m = __activemask();
+        int leader = __ffs(m) - 1, lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&d.reset_count[parity], __popc(m));
+        base = __shfl_sync(m, base, leader);
+        d.reset_list[base + __popc(m & ((1u << lane) - 1))] = e;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_race_reset(XwRaceCfg r, const uint8_t* mask) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= r.n || (mask && !mask[e])) return;
+    xw_race_reset_env(r, e);
+}
+__global__ void __launch_bounds__(256) k_race_step(XwRaceCfg r, const int32_t* __restrict__ actions, int n_actions,
+                                                   float* __restrict__ reward, int32_t* __restrict__ over, int32_t* error) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= r.n) return;
+    int a = actions[e];
+    if (a < 0 || a >= n_actions) { error[e] = XW_ERR_INVALID_ACTION; reward[e] = 0.f; over[e] = 0; return; }
+    float rw; int32_t o;
+    bool need = xw_race_step_env(r, e, a, &rw, &o);
+    reward[e] = rw; over[e] = o;
+    if (need) xw_race_reset_env(r, e);  // the race reset is two stores: done in place
+}
+
+// ------------------------------------------------------------------------------------ handle
+struct SimpleGameEnv {  // games/simple_game/simple_game_simulator.cpp (host; BASELINE config 1)
+    int cur_pos; int64_t num_steps; std::vector<uint8_t> state; std::vector<float> rewards;
+};
+
+struct xw_sim {
+    xw_config cfg;
+    int n = 0, device = 0;
+    cudaStream_t own_stream = nullptr;
+    int64_t launches = 0;
+    int step_parity = 0;
+    // xworld
+    XwDev d;
+    XwRender r;
+    XwRenderTables tab;
+    std::vector<void*> allocs;
+    int n_sms = 148, render_grid = 0, render_smem = 0;
+    int C = 3;
+    // race
+    XwRaceCfg race;
+    int32_t* race_error = nullptr;
+    // simple game
+    std::vector<SimpleGameEnv> sg;
+    // host staging (pinned)
+    int32_t *h_act = nullptr, *h_over = nullptr, *d_act = nullptr, *d_over = nullptr;
+    float *h_rew = nullptr, *d_rew = nullptr;
+    uint8_t *d_mask = nullptr, *d_frames = nullptr;
+    // timing
+    bool timing = false;
+    std::vector<cudaEvent_t> ev;
+    size_t ev_used = 0;
+};
+
+template <typename T>
+static int dalloc(xw_sim* s, T** p, size_t count, bool zero = true) {
+    void* q = nullptr;
+    CUDA_TRY(cudaMalloc(&q, count * sizeof(T) + 16));
+    if (zero) CUDA_TRY(cudaMemset(q, 0, count * sizeof(T) + 16));
+    s->allocs.push_back(q);
+    *p = (T*)q;
+    return 0;
+}
+template <typename T>
+static int dupload(xw_sim* s, const T** p, const T* host, size_t count) {
+    T* q = nullptr;
+    int rc = dalloc(s, &q, count, false);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpy(q, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    *p = q;
+    return 0;
+}
+
+static cudaStream_t pick_stream(xw_sim* s, void* stream) { return stream ? (cudaStream_t)stream : s->own_stream; }
+
+// ThreadCounter seed of the reference's i-th simulator thread (simulator_util.cpp:38-52):
+// int seed = std::hash<std::string>()(std::to_string(FLAGS_simulator_seed + i)); reng_.seed(seed)
+static uint32_t minstd_seed(int32_t simulator_seed, int64_t thread_no) {
+    int32_t seed = (int32_t)(uint32_t)std::hash<std::string>()(std::to_string((int)(simulator_seed + thread_no)));
+    uint64_t x = ((uint64_t)(int64_t)seed) % 2147483647ull;  // linear_congruential_engine::seed
+    return x == 0 ? 1u : (uint32_t)x;
+}
+
+extern "C" {
+
+const char* xw_last_error(void) { return g_err; }
+
+void xw_config_init(xw_config* c) {
+    memset(c, 0, sizeof *c);
+    c->abi_version = XW_ABI_VERSION;
+    c->game = XW_GAME_XWORLD;
+    c->height = c->width = 8;  // XWorldNav.py:10-11
+    c->n_goals = 4; c->n_blocks = 16;  // XWorldNav.py:31-32, last level
+    c->rules = XW_RULES_NAV3D;
+    c->context = 1;
+    c->max_steps_factor = 10;
+    c->array_size = 6;
+    c->track_width = 20.f; c->track_length = 100.f; c->track_radius = 30.f;
+    c->reward_scale = 1.f;
+}
+
+static int create_xworld(xw_sim* s, const xw_catalog* cat) {
+    const xw_config& c = s->cfg;
+    const int n = s->n;
+    if (!cat || !cat->atlas64 || cat->n_icons <= 0) return set_err(XW_ERR_INVALID_ARG, "xworld needs an icon catalog");
+    if (c.height != c.width) return set_err(XW_ERR_INVALID_ARG, "only square maps (maze2d.py:78)");
+    if (c.height < 3 || c.height > XW_MAX_DIM) return set_err(XW_ERR_INVALID_ARG, "map side must be in [3,%d]", XW_MAX_DIM);
+    if (c.n_goals < 1 || c.n_goals > XW_MAX_GOALS) return set_err(XW_ERR_INVALID_ARG, "n_goals must be in [1,%d]", XW_MAX_GOALS);
+    if (cat->n_names < c.n_goals) return set_err(XW_ERR_INVALID_ARG, "catalog has fewer goal names than n_goals");
+    if (c.visible_radius != 0) return set_err(XW_ERR_UNSUPPORTED, "visible_radius > 0 (first-person view) is not implemented");
+    if (c.context < 1 || c.context > 16) return set_err(XW_ERR_INVALID_ARG, "context must be in [1,16]");
+    if (c.rules != XW_RULES_NAV3D && c.rules != XW_RULES_NAV2D) return set_err(XW_ERR_INVALID_ARG, "unknown rules");
+    {  // the maze must offer n_blocks wall cells ("too many blocks for a valid maze", xworld_env.py:443)
+        int D = c.height, X = (D % 2 == 0) ? D - 1 : D, nx = (X + 1) / 2;
+        int walls = X * X - nx * nx - (nx * nx - 1) + ((D % 2 == 0) ? (X / 2) + (D / 2) : 0);
+        if (c.n_blocks < 0 || c.n_blocks > walls) return set_err(XW_ERR_INVALID_ARG, "n_blocks %d > %d maze wall cells", c.n_blocks, walls);
+        if (D * D - walls < c.n_goals + 1) return set_err(XW_ERR_INVALID_ARG, "map too small for goals + agent");
+    }
+    XwDev& d = s->d;
+    memset(&d, 0, sizeof d);
+    d.n = n; d.H = c.height; d.W = c.width; d.CS = (c.height * c.width + 15) & ~15;
+    d.G = c.n_goals; d.n_blocks = c.n_blocks; d.rules = c.rules; d.max_steps = c.max_steps;
+    d.max_steps_factor = c.max_steps_factor; d.auto_reset = c.auto_reset;
+    d.seed = c.seed; d.gid0 = c.env_id_offset;
+    int rc = 0;
+    rc |= dalloc(s, &d.grid, (size_t)n * d.CS);
+    uint8_t** u8s[] = {&d.agent_x, &d.agent_y, &d.facing, &d.task, &d.stage, &d.event, &d.succ, &d.tmask, &d.aux0, &d.aux1, &d.aux2};
+    for (auto p : u8s) rc |= dalloc(s, p, (size_t)n);
+    rc |= dalloc(s, &d.goal_x, (size_t)n * XW_MAX_GOALS);
+    rc |= dalloc(s, &d.goal_y, (size_t)n * XW_MAX_GOALS);
+    rc |= dalloc(s, &d.goal_icon, (size_t)n * XW_MAX_GOALS);
+    rc |= dalloc(s, &d.goal_name, (size_t)n * XW_MAX_GOALS);
+    int32_t** i32s[] = {&d.steps_in_task, &d.num_steps, &d.episode, &d.n_success, &d.n_failure, &d.success_steps, &d.error};
+    for (auto p : i32s) rc |= dalloc(s, p, (size_t)n);
+    rc |= dalloc(s, &d.minstd, (size_t)n);
+    rc |= dalloc(s, &d.reset_count, 2);
+    rc |= dalloc(s, &d.reset_list, (size_t)n);
+    if (rc) return rc;
+    {
+        std::vector<uint32_t> seeds(n);
+        for (int i = 0; i < n; ++i) seeds[i] = minstd_seed(c.simulator_seed, c.env_id_offset + i + 1);
+        CUDA_TRY(cudaMemcpy(d.minstd, seeds.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice));
+    }
+    // catalog
+    d.n_names = cat->n_names; d.brick_icon = cat->brick_icon; d.agent_icon = cat->agent_icon;
+    rc |= dupload(s, &d.name_first, cat->name_first, (size_t)cat->n_names + 1);
+    rc |= dupload(s, &d.name_icons, cat->name_icons, (size_t)cat->name_first[cat->n_names]);
+    rc |= dupload(s, &d.icon_colored, cat->icon_colored, (size_t)cat->n_icons);
+    if (rc) return rc;
+    // renderer
+    int OH = c.out_h > 0 ? c.out_h : c.height * 12, OW = c.out_w > 0 ? c.out_w : c.width * 12;  // xworld_simulator.cpp:52-61
+    if (OH > XW_MAX_OUT || OW > XW_MAX_OUT) return set_err(XW_ERR_INVALID_ARG, "frame side must be <= %d", XW_MAX_OUT);
+    s->tab = xw_build_render_tables(c.height, c.width, OH, OW);
+    XwRenderTables& t = s->tab;
+    XwRender& r = s->r;
+    memset(&r, 0, sizeof r);
+    r.OH = OH; r.OW = OW; r.WR = t.WR; r.FB = t.FB; r.H = c.height; r.W = c.width; r.R = t.R; r.rpg = t.rpg;
+    r.n_sc = (int)t.sc.size(); r.n_sr = (int)t.sr.size();
+    r.n_icons = cat->n_icons; r.brick_icon = cat->brick_icon; r.agent_icon = cat->agent_icon;
+    static const int16_t zero16 = 0;
+    rc |= dupload(s, &r.xofs, t.xofs.data(), t.xofs.size());
+    rc |= dupload(s, &r.xa0, t.xa0.data(), t.xa0.size());
+    rc |= dupload(s, &r.xa1, t.xa1.data(), t.xa1.size());
+    rc |= dupload(s, &r.yofs, t.yofs.data(), t.yofs.size());
+    rc |= dupload(s, &r.ya0, t.ya0.data(), t.ya0.size());
+    rc |= dupload(s, &r.ya1, t.ya1.data(), t.ya1.size());
+    rc |= dupload(s, &r.rowcell, t.rowcell.data(), t.rowcell.size());
+    rc |= dupload(s, &r.bandend, t.bandend.data(), t.bandend.size());
+    if (t.fast_ok) rc |= dupload(s, &r.colpair, t.colpair.data(), t.colpair.size());
+    rc |= dupload(s, &r.sc, t.sc.empty() ? &zero16 : t.sc.data(), t.sc.empty() ? 1 : t.sc.size());
+    rc |= dupload(s, &r.sr, t.sr.empty() ? &zero16 : t.sr.data(), t.sr.empty() ? 1 : t.sr.size());
+    rc |= dupload(s, &r.atlas64, cat->atlas64, (size_t)cat->n_icons * 64 * 64 * 3);
+    uint8_t* T = nullptr;
+    rc |= dalloc(s, &T, (size_t)cat->n_icons * r.FB, false);
+    if (rc) return rc;
+    r.T = T;
+    k_build_phase_atlas<<<s->n_sms * 8, 256, 0, s->own_stream>>>(r);
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (t.fast_ok) {
+        XwRenderSmem L = xw_render_smem(r);
+        int max_optin = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
+        if (L.total > max_optin) t.fast_ok = false;
+        else {
+            s->render_smem = L.total;
+            CUDA_TRY(cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+            int per_sm = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_render, t.threads, L.total));
+            if (per_sm < 1) t.fast_ok = false;
+            s->render_grid = s->n_sms * (per_sm < 1 ? 1 : per_sm);
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(s->own_stream));
+    return 0;
+}
+
+static int create_race(xw_sim* s) {
+    const xw_config& c = s->cfg;
+    if (c.race_random) return set_err(XW_ERR_UNSUPPORTED, "simple_race --random is not implemented");
+    XwRaceCfg& r = s->race;
+    memset(&r, 0, sizeof r);
+    r.n = s->n; r.track_type = c.track_type; r.full_manouver = c.race_full_manouver; r.difficulty = c.difficulty;
+    r.max_steps = c.max_steps; r.auto_reset = c.auto_reset; r.reward_scale = (double)c.reward_scale;
+    r.mid_x = 480 / 2; r.mid_y = 720 / 2;  // WINDOW_WIDTH/HEIGHT, simple_race_simulator.cpp:31-32,446
+    if (c.track_type == 0) {  // StraightTrack ctor :103-109
+        r.length = c.track_length; r.width = c.track_width;
+        r.start_y = r.mid_y - (float)(0.4 * r.length);
+        r.end_y = r.mid_y + (float)(0.6 * r.length);
+        r.start_px = r.mid_x - 0.0f; r.start_py = r.start_y;
+    } else {  // CircleTrack ctor :50-54, get_start_pos :76-79
+        r.inner = c.track_radius; r.width = c.track_width; r.outer = r.inner + r.width;
+        r.start_px = (r.inner + r.width / 2) + r.mid_x; r.start_py = 0.0f + r.mid_y;
+    }
+    int rc = 0;
+    rc |= dalloc(s, &r.pos_x, (size_t)s->n);
+    rc |= dalloc(s, &r.pos_y, (size_t)s->n);
+    rc |= dalloc(s, &r.angle, (size_t)s->n);
+    rc |= dalloc(s, &r.state, (size_t)s->n * 4);
+    rc |= dalloc(s, &r.steps, (size_t)s->n);
+    rc |= dalloc(s, &s->race_error, (size_t)s->n);
+    return rc;
+}
+
+int xw_create(const xw_config* cfg, const xw_catalog* catalog, int32_t n_envs, int32_t device, xw_sim** out) {
+    if (!cfg || !out) return set_err(XW_ERR_INVALID_ARG, "null argument");
+    if (cfg->abi_version != XW_ABI_VERSION) return set_err(XW_ERR_INVALID_ARG, "abi_version %d != %d", cfg->abi_version, XW_ABI_VERSION);
+    if (n_envs < 1) return set_err(XW_ERR_INVALID_ARG, "n_envs must be >= 1");
+    xw_sim* s = new xw_sim();
+    s->cfg = *cfg;
+    s->n = n_envs;
+    int rc = 0;
+    if (cfg->game == XW_GAME_SIMPLE_GAME) {
+        if (cfg->array_size < 2 || cfg->array_size > 4096) { delete s; return set_err(XW_ERR_INVALID_ARG, "array_size"); }
+        s->sg.resize(n_envs);
+        *out = s;
+        xw_reset_host(s, nullptr, nullptr);
+        return 0;
+    }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        delete s;
+        return set_err(XW_ERR_NO_DEVICE, "no CUDA device: the xworld / simple_race paths have no CPU fallback");
+    }
+    if (device < 0) cudaGetDevice(&device);
+    s->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->n_sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) { delete s; return set_err(XW_ERR_CUDA, "device init: %s", cudaGetErrorString(e)); }
+    if (cfg->game == XW_GAME_XWORLD) rc = create_xworld(s, catalog);
+    else if (cfg->game == XW_GAME_SIMPLE_RACE) rc = create_race(s);
+    else rc = set_err(XW_ERR_INVALID_ARG, "unknown game %d", cfg->game);
+    if (rc) { xw_destroy(s); return rc; }
+    *out = s;
+    return 0;
+}
+
+void xw_destroy(xw_sim* s) {
+    if (!s) return;
+    if (s->own_stream) cudaStreamSynchronize(s->own_stream);
+    for (void* p : s->allocs) cudaFree(p);
+    if (s->h_act) cudaFreeHost(s->h_act);
+    if (s->h_over) cudaFreeHost(s->h_over);
+    if (s->h_rew) cudaFreeHost(s->h_rew);
+    for (auto ev : s->ev) cudaEventDestroy(ev);
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    delete s;
+}
+
+int32_t xw_num_envs(const xw_sim* s) { return s->n; }
+
+int32_t xw_num_actions(const xw_sim* s) {
+    if (s->cfg.game == XW_GAME_XWORLD) return s->cfg.visible_radius == 0 ? 4 : 6;  // xitem.cpp:82-86
+    if (s->cfg.game == XW_GAME_SIMPLE_GAME) return 2;
+    return s->cfg.race_full_manouver ? 9 : 2;  // simple_race_simulator.cpp:432-440
+}
+
+int xw_screen_dims(const xw_sim* s, int32_t* h, int32_t* w, int32_t* c, int32_t* context) {
+    if (s->cfg.game == XW_GAME_XWORLD) { *h = s->r.OH; *w = s->r.OW; *c = 3; }
+    else if (s->cfg.game == XW_GAME_SIMPLE_GAME) { *h = 1; *w = s->cfg.array_size; *c = 1; }  // simple_game_simulator.cpp:101-107
+    else { *h = 1; *w = 4; *c = 1; }
+    *context = s->cfg.context;
+    return 0;
+}
+
+size_t xw_frame_bytes(const xw_sim* s) {
+    int32_t h, w, c, k;
+    xw_screen_dims(s, &h, &w, &c, &k);
+    return (size_t)h * w * c * k * (s->cfg.game == XW_GAME_SIMPLE_RACE ? sizeof(float) : 1);
+}
+
+int64_t xw_launch_count(const xw_sim* s) { return s->launches; }
+
+int xw_enable_timing(xw_sim* s, int32_t on) { s->timing = on != 0; return 0; }
+
+double xw_render_ms(xw_sim* s, int32_t reset) {
+    if (!s->timing && s->ev_used == 0) return -1.0;
+    if (s->own_stream) cudaStreamSynchronize(s->own_stream);
+    cudaDeviceSynchronize();
+    double total = 0;
+    size_t pairs = s->ev_used / 2;
+    for (size_t i = 0; i < pairs; ++i) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, s->ev[2 * i], s->ev[2 * i + 1]);
+        total += ms;
+    }
+    double avg = pairs ? total / pairs : -1.0;
+    if (reset) s->ev_used = 0;
+    return avg;
+}
+
+static int launch_render(xw_sim* s, uint8_t* d_frames, cudaStream_t st) {
+    XwRender& r = s->r;
+    const int K = s->cfg.context;
+    const size_t env_stride = (size_t)K * r.FB;
+    if (K > 1) {  // GameSimulator::shift_context (simulator.cpp:51-60)
+        if (r.FB % 16) return set_err(XW_ERR_UNSUPPORTED, "context > 1 needs a frame size divisible by 16");
+        k_shift_context<<<s->n_sms * 4, 256, 0, st>>>(d_frames, s->n, K, r.FB);
+        s->launches++;
+    }
+    uint8_t* dst = d_frames + (size_t)(K - 1) * r.FB;  // newest frame last
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (s->timing) {
+        if (s->ev_used + 2 > s->ev.size()) {
+            for (int i = 0; i < 2; ++i) { cudaEvent_t ev; CUDA_TRY(cudaEventCreate(&ev)); s->ev.push_back(ev); }
+        }
+        e0 = s->ev[s->ev_used]; e1 = s->ev[s->ev_used + 1];
+        s->ev_used += 2;
+        CUDA_TRY(cudaEventRecord(e0, st));
+    }
+    if (s->tab.fast_ok) {
+        int grid = s->render_grid < s->n ? s->render_grid : s->n;
+        k_render<<<grid, s->tab.threads, s->render_smem, st>>>(s->d, r, dst, env_stride);
+    } else {
+        k_render_generic<<<s->n_sms * 8, 256, 0, st>>>(s->d, r, dst, env_stride);
+    }
+    s->launches++;
+    if (s->timing) CUDA_TRY(cudaEventRecord(e1, st));
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int xw_render(xw_sim* s, uint8_t* d_frames, void* stream) {
+    if (s->cfg.game != XW_GAME_XWORLD) return set_err(XW_ERR_UNSUPPORTED, "xw_render: xworld only");
+    if (!d_frames) return set_err(XW_ERR_INVALID_ARG, "null frames");
+    return launch_render(s, d_frames, pick_stream(s, stream));
+}
+
+int xw_reset(xw_sim* s, const uint8_t* d_mask, void* stream) {
+    cudaStream_t st = pick_stream(s, stream);
+    if (s->cfg.game == XW_GAME_XWORLD) {
+        k_reset<<<(s->n + 127) / 128, 128, 0, st>>>(s->d, d_mask, nullptr, nullptr);
+        s->launches++;
+    } else if (s->cfg.game == XW_GAME_SIMPLE_RACE) {
+        k_race_reset<<<(s->n + 255) / 256, 256, 0, st>>>(s->race, d_mask);
+        s->launches++;
+    } else {
+        return set_err(XW_ERR_UNSUPPORTED, "simple_game runs on the host: use xw_reset_host");
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int xw_step(xw_sim* s, const int32_t* d_actions, int32_t act_rep, float* d_reward, int32_t* d_game_over,
+            uint8_t* d_frames, void* stream) {
+    if (!d_actions || !d_reward || !d_game_over) return set_err(XW_ERR_INVALID_ARG, "null buffer");
+    if (act_rep < 1) return set_err(XW_ERR_INVALID_ARG, "act_rep must be >= 1");
+    cudaStream_t st = pick_stream(s, stream);
+    if (s->cfg.game == XW_GAME_XWORLD) {
+        k_step<<<(s->n + 255) / 256, 256, 0, st>>>(s->d, d_actions, act_rep, d_reward, d_game_over, s->step_parity);
+        s->launches++;
+        if (s->cfg.auto_reset) {
+            k_reset<<<(s->n + 127) / 128, 128, 0, st>>>(s->d, nullptr, s->d.reset_list, s->d.reset_count + s->step_parity);
+            s->launches++;
+        }
+        s->step_parity ^= 1;
+        CUDA_TRY(cudaGetLastError());
+        if (d_frames) return launch_render(s, d_frames, st);
+        return 0;
+    }
+    if (s->cfg.game == XW_GAME_SIMPLE_RACE) {
+        for (int rep = 0; rep < act_rep; ++rep) {  // GameSimulator::take_actions repeats the action
+            if (rep > 0) return set_err(XW_ERR_UNSUPPORTED, "simple_race: act_rep > 1 not implemented");
+            k_race_step<<<(s->n + 255) / 256, 256, 0, st>>>(s->race, d_actions, xw_num_actions(s), d_reward, d_game_over, s->race_error);
+            s->launches++;
+        }
+        CUDA_TRY(cudaGetLastError());
+        if (d_frames)  // "screen" of simple_race = the 4-float state vector
+            CUDA_TRY(cudaMemcpyAsync(d_frames, s->race.state, sizeof(float) * 4 * s->n, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+    return set_err(XW_ERR_UNSUPPORTED, "simple_game runs on the host: use xw_step_host");
+}
+
+static int ensure_staging(xw_sim* s, bool frames) {
+    if (!s->h_act) {
+        CUDA_TRY(cudaMallocHost((void**)&s->h_act, sizeof(int32_t) * s->n));
+        CUDA_TRY(cudaMallocHost((void**)&s->h_over, sizeof(int32_t) * s->n));
+        CUDA_TRY(cudaMallocHost((void**)&s->h_rew, sizeof(float) * s->n));
+        int rc = dalloc(s, &s->d_act, (size_t)s->n) | dalloc(s, &s->d_over, (size_t)s->n) | dalloc(s, &s->d_rew, (size_t)s->n) |
+                 dalloc(s, &s->d_mask, (size_t)s->n);
+        if (rc) return rc;
+    }
+    if (frames && !s->d_frames) return dalloc(s, &s->d_frames, (size_t)s->n * xw_frame_bytes(s));
+    return 0;
+}
+
+// ---- simple_game on the host (SimpleGameEngine, simple_game_simulator.cpp:24-76) ----
+static void sg_reset(const xw_config& c, SimpleGameEnv& g) {
+    g.cur_pos = c.array_size / 2;
+    g.num_steps = 0;
+    g.state.assign(c.array_size, 0);
+    g.rewards.assign(c.array_size, 0.f);
+    g.state[g.cur_pos] = 1;
+    g.rewards[c.array_size - 1] = 4.0f / 2;  // DEST_REWARD / 2
+    g.rewards[0] = 4.0f;
+}
+static bool sg_over(const SimpleGameEnv& g) { return g.cur_pos <= 0 || g.cur_pos >= (int)g.state.size() - 1; }
+static float sg_reward(SimpleGameEnv& g) {
+    float reward = -0.1f;  // MOVE_REWARD
+    if (g.cur_pos >= 0 && g.cur_pos < (int)g.state.size() && g.rewards[g.cur_pos] != 0.0) {
+        reward = g.rewards[g.cur_pos];
+        g.rewards[g.cur_pos] = 0.0;
+    }
+    return reward;
+}
+static float sg_act(SimpleGameEnv& g, int a) {
+    if (sg_over(g)) return sg_reward(g);
+    g.state[g.cur_pos] = 0;
+    if (a == 0) --g.cur_pos; else ++g.cur_pos;
+    if (g.cur_pos >= 0 && g.cur_pos < (int)g.state.size()) g.state[g.cur_pos] = 1;
+    return sg_reward(g);
+}
+
+int xw_reset_host(xw_sim* s, const uint8_t* h_mask, uint8_t* h_frames) {
+    if (s->cfg.game == XW_GAME_SIMPLE_GAME) {
+        for (int i = 0; i < s->n; ++i) {
+            if (h_mask && !h_mask[i]) continue;
+            sg_reset(s->cfg, s->sg[i]);
+        }
+        if (h_frames)
+            for (int i = 0; i < s->n; ++i) memcpy(h_frames + (size_t)i * s->cfg.array_size, s->sg[i].state.data(), s->cfg.array_size);
+        return 0;
+    }
+    int rc = ensure_staging(s, h_frames != nullptr);
+    if (rc) return rc;
+    cudaStream_t st = s->own_stream;
+    if (h_mask) CUDA_TRY(cudaMemcpyAsync(s->d_mask, h_mask, s->n, cudaMemcpyHostToDevice, st));
+    rc = xw_reset(s, h_mask ? s->d_mask : nullptr, st);
+    if (rc) return rc;
+    if (h_frames) {
+        if (s->cfg.game == XW_GAME_XWORLD) {
+            if (s->cfg.context > 1 && !h_mask)  // init_screen: zero-filled context, newest frame last
+                CUDA_TRY(cudaMemsetAsync(s->d_frames, 0, (size_t)s->n * xw_frame_bytes(s), st));
+            rc = launch_render(s, s->d_frames, st);
+            if (rc) return rc;
+        } else {
+            CUDA_TRY(cudaMemsetAsync(s->d_frames, 0, (size_t)s->n * xw_frame_bytes(s), st));
+        }
+        CUDA_TRY(cudaMemcpyAsync(h_frames, s->d_frames, (size_t)s->n * xw_frame_bytes(s), cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int xw_step_host(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float* h_reward, int32_t* h_game_over, uint8_t* h_frames) {
+    if (!h_actions || !h_reward || !h_game_over) return set_err(XW_ERR_INVALID_ARG, "null buffer");
+    if (s->cfg.game == XW_GAME_SIMPLE_GAME) {
+        for (int i = 0; i < s->n; ++i) {
+            SimpleGameEnv& g = s->sg[i];
+            if (h_actions[i] < 0 || h_actions[i] >= 2) return set_err(XW_ERR_INVALID_ACTION, "undefined action_id: %d", h_actions[i]);
+            float r = 0;
+            g.num_steps++;
+            for (int rep = 0; rep < act_rep; ++rep) r += sg_act(g, h_actions[i]);
+            h_reward[i] = r;
+            int over = 0;
+            if (s->cfg.max_steps > 0 && g.num_steps >= s->cfg.max_steps) over |= XW_MAX_STEP;
+            if (sg_over(g)) over |= XW_SUCCESS;  // SimpleGame::game_over, simple_game_simulator.cpp:83-85
+            h_game_over[i] = over;
+            if (h_frames) memcpy(h_frames + (size_t)i * s->cfg.array_size, g.state.data(), s->cfg.array_size);
+        }
+        return 0;
+    }
+    int rc = ensure_staging(s, h_frames != nullptr);
+    if (rc) return rc;
+    cudaStream_t st = s->own_stream;
+    memcpy(s->h_act, h_actions, sizeof(int32_t) * s->n);
+    CUDA_TRY(cudaMemcpyAsync(s->d_act, s->h_act, sizeof(int32_t) * s->n, cudaMemcpyHostToDevice, st));
+    rc = xw_step(s, s->d_act, act_rep, s->d_rew, s->d_over, h_frames ? s->d_frames : nullptr, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(s->h_rew, s->d_rew, sizeof(float) * s->n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(s->h_over, s->d_over, sizeof(int32_t) * s->n, cudaMemcpyDeviceToHost, st));
+    if (h_frames) CUDA_TRY(cudaMemcpyAsync(h_frames, s->d_frames, (size_t)s->n * xw_frame_bytes(s), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    memcpy(h_reward, s->h_rew, sizeof(float) * s->n);
+    memcpy(h_game_over, s->h_over, sizeof(int32_t) * s->n);
+    return 0;
+}
+
+int xw_num_steps(xw_sim* s, int64_t* h) {
+    if (s->cfg.game == XW_GAME_SIMPLE_GAME) { for (int i = 0; i < s->n; ++i) h[i] = s->sg[i].num_steps; return 0; }
+    std::vector<int32_t> tmp(s->n);
+    const int32_t* src = s->cfg.game == XW_GAME_XWORLD ? s->d.num_steps : s->race.steps;
+    CUDA_TRY(cudaStreamSynchronize(s->own_stream));
+    CUDA_TRY(cudaMemcpy(tmp.data(), src, sizeof(int32_t) * s->n, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < s->n; ++i) h[i] = tmp[i];
+    return 0;
+}
+
+// ---- named state fields ----
+struct FieldRef { void* ptr; size_t elem; size_t per_env; bool goal_major; };
+static bool find_field(xw_sim* s, const char* name, FieldRef* f) {
+    std::string k(name);
+    if (s->cfg.game == XW_GAME_XWORLD) {
+        XwDev& d = s->d;
+        struct { const char* n; void* p; size_t elem, per; bool gm; } tbl[] = {
+            {"grid", d.grid, 1, (size_t)d.CS, false},
+            {"agent_x", d.agent_x, 1, 1, false}, {"agent_y", d.agent_y, 1, 1, false}, {"facing", d.facing, 1, 1, false},
+            {"task", d.task, 1, 1, false}, {"stage", d.stage, 1, 1, false}, {"event", d.event, 1, 1, false},
+            {"action_success", d.succ, 1, 1, false}, {"target_mask", d.tmask, 1, 1, false},
+            {"aux0", d.aux0, 1, 1, false}, {"aux1", d.aux1, 1, 1, false}, {"aux2", d.aux2, 1, 1, false},
+            {"goal_x", d.goal_x, 1, XW_MAX_GOALS, true}, {"goal_y", d.goal_y, 1, XW_MAX_GOALS, true},
+            {"goal_icon", d.goal_icon, 4, XW_MAX_GOALS, true}, {"goal_name", d.goal_name, 4, XW_MAX_GOALS, true},
+            {"steps_in_task", d.steps_in_task, 4, 1, false}, {"num_steps", d.num_steps, 4, 1, false},
+            {"episode", d.episode, 4, 1, false}, {"n_success", d.n_success, 4, 1, false},
+            {"n_failure", d.n_failure, 4, 1, false}, {"success_steps", d.success_steps, 4, 1, false},
+            {"minstd", d.minstd, 4, 1, false}, {"error", d.error, 4, 1, false}};
+        for (auto& t : tbl) if (k == t.n) { *f = {t.p, t.elem, t.per, t.gm}; return true; }
+    } else if (s->cfg.game == XW_GAME_SIMPLE_RACE) {
+        XwRaceCfg& r = s->race;
+        struct { const char* n; void* p; size_t elem, per; } tbl[] = {
+            {"pos_x", r.pos_x, 4, 1}, {"pos_y", r.pos_y, 4, 1}, {"angle", r.angle, 4, 1}, {"steps", r.steps, 4, 1},
+            {"state", r.state, 4, 4}, {"error", s->race_error, 4, 1}};
+        for (auto& t : tbl) if (k == t.n) { *f = {t.p, t.elem, t.per, false}; return true; }
+    }
+    return false;
+}
+
+static int field_io(xw_sim* s, const char* name, void* h, size_t bytes, bool get) {
+    FieldRef f;
+    if (!find_field(s, name, &f)) return set_err(XW_ERR_INVALID_ARG, "unknown field '%s'", name);
+    const size_t n = s->n;
+    CUDA_TRY(cudaStreamSynchronize(s->own_stream));
+    if (std::string(name) == "grid") {  // host layout [n][H*W], device rows are CS wide
+        const size_t hw = (size_t)s->d.H * s->d.W;
+        if (bytes != n * hw) return set_err(XW_ERR_INVALID_ARG, "field grid: expected %zu bytes", n * hw);
+        if (get) CUDA_TRY(cudaMemcpy2D(h, hw, f.ptr, s->d.CS, hw, n, cudaMemcpyDeviceToHost));
+        else CUDA_TRY(cudaMemcpy2D(f.ptr, s->d.CS, h, hw, hw, n, cudaMemcpyHostToDevice));
+        return 0;
+    }
+    const size_t total = n * f.per_env * f.elem;
+    if (bytes != total) return set_err(XW_ERR_INVALID_ARG, "field %s: expected %zu bytes, got %zu", name, total, bytes);
+    if (!f.goal_major) {
+        if (get) CUDA_TRY(cudaMemcpy(h, f.ptr, total, cudaMemcpyDeviceToHost));
+        else CUDA_TRY(cudaMemcpy(f.ptr, h, total, cudaMemcpyHostToDevice));
+        return 0;
+    }
+    // device [goal][env] <-> host [env][goal]
+    std::vector<uint8_t> tmp(total);
+    if (get) {
+        CUDA_TRY(cudaMemcpy(tmp.data(), f.ptr, total, cudaMemcpyDeviceToHost));
+        for (size_t g = 0; g < f.per_env; ++g)
+            for (size_t e = 0; e < n; ++e) memcpy((uint8_t*)h + (e * f.per_env + g) * f.elem, tmp.data() + (g * n + e) * f.elem, f.elem);
+    } else {
+        for (size_t g = 0; g < f.per_env; ++g)
+            for (size_t e = 0; e < n; ++e) memcpy(tmp.data() + (g * n + e) * f.elem, (const uint8_t*)h + (e * f.per_env + g) * f.elem, f.elem);
+        CUDA_TRY(cudaMemcpy(f.ptr, tmp.data(), total, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+int xw_get_field(xw_sim* s, const char* name, void* h_out, size_t bytes) { return field_io(s, name, h_out, bytes, true); }
+int xw_set_field(xw_sim* s, const char* name, const void* h_in, size_t bytes) { return field_io(s, name, (void*)h_in, bytes, false); }
+
+}  // extern "C"

@@ -1,0 +1,105 @@
+// xw_race.cuh -- SimpleRace step for one env (fp32 state; BASELINE config 5, render off).
+//
+// Replaces games/simple_race/simple_race_simulator.cpp: BaseCar::move :227-235, RaceEngine::act
+// :290-341, get_reward :386-410, get_screen :412-430, reset_game :267-284, StraightTrack /
+// CircleTrack geometry :50-101,103-109,182-222, SimpleRaceGame::game_over :465-467.
+//
+// Numerics: the reference stores floats but its cos/sin/sqrt/fabs resolve to the C double
+// functions, so each transcendental is evaluated in fp64 and rounded once to
+// fp32; products and sums are single fp32 operations (no FMA contraction: __fmul_rn/__fadd_rn).
+#pragma once
+#include <math.h>
+
+#include "xw_common.cuh"
+
+#define XW_RACE_PI 3.1415926  // simple_race_simulator.h:39
+
+#if defined(__CUDA_ARCH__)
+#define XW_FM(a, b) __fmul_rn((a), (b))
+#define XW_FA(a, b) __fadd_rn((a), (b))
+#define XW_FD(a, b) __fdiv_rn((a), (b))
+#else
+#define XW_FM(a, b) ((float)((float)(a) * (float)(b)))
+#define XW_FA(a, b) ((float)((float)(a) + (float)(b)))
+#define XW_FD(a, b) ((float)((float)(a) / (float)(b)))
+#endif
+
+struct XwRaceCfg {
+    int32_t n, track_type, full_manouver, difficulty, max_steps, auto_reset;
+    float mid_x, mid_y, start_y, end_y, length, width, inner, outer;
+    float start_px, start_py;
+    double reward_scale;
+    float *pos_x, *pos_y, *angle, *state;  // state: [n][4]
+    int32_t* steps;
+};
+
+// cv::norm(Point2f) returns double: sqrt((double)x*x + (double)y*y)
+XW_HD double xw_race_norm(float x, float y) { return sqrt((double)x * (double)x + (double)y * (double)y); }
+
+XW_HD float xw_race_hdisp(const XwRaceCfg& r, float px, float py) {
+    if (r.track_type == 0) return XW_FD(XW_FM(2.f, XW_FA(px, -r.mid_x)), r.width);
+    return (float)((2 * xw_race_norm(XW_FA(px, -r.mid_x), XW_FA(py, -r.mid_y)) - (double)r.inner - (double)r.outer) / (double)r.width);
+}
+
+XW_HD void xw_race_reset_env(const XwRaceCfg& r, int e) {
+    r.pos_x[e] = r.start_px; r.pos_y[e] = r.start_py;
+    r.angle[e] = (float)(XW_RACE_PI / 2);
+    r.steps[e] = 0;
+}
+
+XW_HD bool xw_race_step_env(const XwRaceCfg& r, int e, int action_index, float* reward_out, int32_t* over_out) {
+    int a = r.full_manouver ? action_index : (action_index == 0 ? 4 : 7);
+    const float delta_ang = (float)(XW_RACE_PI / 10), delta_fwd = 1.f;
+    float d_forward = 0.f, d_turn = 0.f;
+    int m = a % 3;
+    if (m == 1) d_forward = delta_fwd; else if (m == 2) d_forward = -delta_fwd;
+    m = (a / 3) % 3;
+    if (m == 1) d_turn = delta_ang; else if (m == 2) d_turn = -delta_ang;
+    float ang = XW_FA(r.angle[e], d_turn);
+    if ((double)ang > 2 * XW_RACE_PI) ang = (float)((double)ang - 2 * XW_RACE_PI);
+    else if (ang < 0) ang = (float)((double)ang + 2 * XW_RACE_PI);
+    const double ca = cos((double)ang), sa = sin((double)ang);
+    const float cx = (float)ca, sx = (float)sa;
+    const float px = XW_FA(r.pos_x[e], XW_FM(d_forward, cx));
+    const float py = XW_FA(r.pos_y[e], XW_FM(d_forward, sx));
+    const int steps = r.steps[e] + 1;
+    // tangent
+    float tx, ty;
+    if (r.track_type == 0) { tx = 0.f; ty = 1.f; }
+    else {
+        float ax = XW_FA(r.mid_y, -py), ay = XW_FA(px, -r.mid_x);
+        double s = 1 / xw_race_norm(ax, ay);
+        tx = (float)((double)ax * s); ty = (float)((double)ay * s);
+    }
+    const float reward_speed = XW_FM(XW_FA(XW_FM(cx, tx), XW_FM(sx, ty)), d_forward);
+    const bool finish = (r.track_type == 0) && (py > r.end_y);
+    bool oob;
+    if (r.track_type == 0) {
+        const float hw = XW_FD(r.width, 2.f);
+        oob = (px < XW_FA(r.mid_x, -hw)) || (px > XW_FA(r.mid_x, hw)) || (py < r.start_y) || (py > r.end_y);
+    } else {
+        float rr = (float)xw_race_norm(XW_FA(px, -r.mid_x), XW_FA(py, -r.mid_y));
+        oob = rr < r.inner || rr > r.outer;
+    }
+    const float hd = xw_race_hdisp(r, px, py);
+    const float reward_finish = finish ? 2.f : 0.f;
+    const float reward_boundary = r.difficulty == 0 ? (float)(-fabs((double)hd)) : ((oob && !finish) ? -2.f : 0.f);
+    float reward = XW_FA(XW_FA(reward_finish, reward_boundary), reward_speed);
+    reward = (float)((double)reward * r.reward_scale);
+    // state (get_screen)
+    double ct = (double)tx * ca + (double)ty * sa;
+    ct = ct < -1.0 ? -1.0 : (ct > 1.0 ? 1.0 : ct);
+    const float cos_theta = (float)ct;
+    float sin_theta = (float)sqrt((double)XW_FA(1.f, -XW_FM(cos_theta, cos_theta)));
+    if (ca * (double)ty + sa * (double)tx < 0) sin_theta = -sin_theta;
+    float* st = r.state + (size_t)e * 4;
+    st[0] = cos_theta; st[1] = sin_theta; st[2] = hd;
+    st[3] = r.track_type == 0 ? XW_FD(XW_FM(2.f, XW_FA(py, -r.mid_y)), r.length) : 0.f;
+    int over = 0;
+    if (r.max_steps > 0 && steps >= r.max_steps) over |= XW_MAX_STEP;
+    if (oob) over |= XW_DEAD;
+    r.pos_x[e] = px; r.pos_y[e] = py; r.angle[e] = ang; r.steps[e] = steps;
+    *reward_out = reward;
+    *over_out = over;
+    return r.auto_reset && over != 0;
+}

@@ -1,0 +1,437 @@
+// xw_reset.cuh -- episode start for one env: map generation + the teacher's first teach().
+//
+// Replaces, per env (reference file:line):
+//   XWorld::reset                       games/xworld/xworld/xworld.cpp:109-151
+//   XWorldEnv.reset/__instantiate_entities   games/xworld/maps/xworld_env.py:95-101,412-452
+//   XWorldNav._configure (curriculum 0)  games/xworld/maps/XWorldNav.py:16-67
+//   spanning_tree_maze_generator, bfs, flood_fill   python/maze2d.py:21-114
+//   Teacher::reset_after_game_reset + teach -> TaskGroup::run_stage  teacher.cpp:207-237, teaching_task.cpp:204-222
+//   the idle() stages of games/xworld3d/tasks/XWorld3DNav*.py and games/xworld/tasks/XWorldNav*.py
+//
+// One thread per env.  Occupancy is kept as 256-bit masks (cells <= 16x16) so "k-th free cell",
+// neighbourhood and tile tests are popcount/bit operations rather than list scans.
+#pragma once
+#include "xw_common.cuh"
+
+struct XwMask { uint64_t w[4]; };
+
+XW_HD int xw_popc64(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+    return __popcll(v);
+#else
+    return __builtin_popcountll(v);
+#endif
+}
+XW_HD void m_zero(XwMask& m) { m.w[0] = m.w[1] = m.w[2] = m.w[3] = 0; }
+XW_HD bool m_get(const XwMask& m, int c) { return (m.w[c >> 6] >> (c & 63)) & 1ull; }
+XW_HD void m_set(XwMask& m, int c) { m.w[c >> 6] |= 1ull << (c & 63); }
+XW_HD void m_clr(XwMask& m, int c) { m.w[c >> 6] &= ~(1ull << (c & 63)); }
+XW_HD int m_count(const XwMask& m) { return xw_popc64(m.w[0]) + xw_popc64(m.w[1]) + xw_popc64(m.w[2]) + xw_popc64(m.w[3]); }
+// index of the k-th set bit (row-major cell order); -1 if fewer
+XW_HD int m_nth(const XwMask& m, int k) {
+    for (int i = 0; i < 4; ++i) {
+        int c = xw_popc64(m.w[i]);
+        if (k < c) {
+            uint64_t v = m.w[i];
+            for (int j = 0; j < k; ++j) v &= v - 1;  // drop k lowest set bits
+#if defined(__CUDA_ARCH__)
+            return i * 64 + (__ffsll((long long)v) - 1);
+#else
+            return i * 64 + __builtin_ctzll(v);
+#endif
+        }
+        k -= c;
+    }
+    return -1;
+}
+
+struct XwMapCtx {
+    int H, W;
+    XwMask inrange;  // cells of the map
+    XwMask block;    // wall bricks
+    XwMask goal;     // goal cells
+    int agent;       // agent cell or -1 while "deleted"
+    int gcell[XW_MAX_GOALS];
+    int gname[XW_MAX_GOALS];
+    int gicon[XW_MAX_GOALS];
+};
+
+XW_HD bool ctx_free(const XwMapCtx& c, int x, int y) {  // (x,y,0) in env.available_grids
+    if (x < 0 || y < 0 || x >= c.W || y >= c.H) return false;
+    int cell = y * c.W + x;
+    return !m_get(c.block, cell) && !m_get(c.goal, cell) && cell != c.agent;
+}
+
+// -------------------------------------------------------------------------- maze + entities
+// Returns 0 on success.  `wall` receives the maze's '#' cells.
+XW_HD int xw_gen_map(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, XwMapCtx& c) {
+    const int D = d.H;
+    c.H = d.H; c.W = d.W;
+    m_zero(c.inrange); m_zero(c.block); m_zero(c.goal);
+    for (int i = 0; i < D * D; ++i) m_set(c.inrange, i);
+    // ---- goal names: shuffle(goal_names) then pop() per goal == partial Fisher-Yates from the end;
+    //      the touched positions are kept in a tiny sparse map instead of an n_names array
+    {
+        int keys[2 * XW_MAX_GOALS], vals[2 * XW_MAX_GOALS], cnt = 0;
+        const int n = d.n_names;
+        for (int k = 0; k < d.G; ++k) {
+            int i = n - 1 - k, vi = i;
+            for (int q = 0; q < cnt; ++q) if (keys[q] == i) vi = vals[q];
+            if (i >= 1) {
+                int j = (int)xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_NAMES, (uint32_t)k), (uint32_t)i + 1);
+                int vj = j, qj = -1;
+                for (int q = 0; q < cnt; ++q) if (keys[q] == j) { vj = vals[q]; qj = q; }
+                // a[i] <-> a[j]; position i is final, only a[j] needs remembering
+                if (qj >= 0) vals[qj] = vi; else { keys[cnt] = j; vals[cnt] = vi; ++cnt; }
+                vi = vj;
+            }
+            c.gname[k] = vi;
+        }
+    }
+    // ---- maze: walls as a bit mask, carved by an explicit-stack DFS with 3 draws per visited node
+    XwMask wall; m_zero(wall);
+    const int pad = (D % 2 == 0), X = pad ? D - 1 : D, nx = (X + 1) / 2;
+    for (int y = 0; y < X; ++y)
+        for (int x = 0; x < X; ++x)
+            if ((x | y) & 1) m_set(wall, y * D + x);
+    {
+        uint8_t sx[64], sy[64], snext[64], sorder[64];
+        uint64_t visited = 0;
+        int sp = 0;
+        uint32_t visit_no = 0;
+        int px = 0, py = 0;
+        bool push = true;
+        while (true) {
+            if (push) {
+                uint32_t o0 = 0, o1 = 1, o2 = 2, o3 = 3;  // moves (-1,0),(1,0),(0,1),(0,-1)
+                uint32_t ord[4] = {o0, o1, o2, o3};
+                for (int i = 3; i >= 1; --i) {
+                    uint32_t j = xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_MAZE, visit_no * 3 + (uint32_t)(3 - i)), (uint32_t)i + 1);
+                    uint32_t t = ord[i]; ord[i] = ord[j]; ord[j] = t;
+                }
+                sx[sp] = (uint8_t)px; sy[sp] = (uint8_t)py; snext[sp] = 0;
+                sorder[sp] = (uint8_t)(ord[0] | (ord[1] << 2) | (ord[2] << 4) | (ord[3] << 6));
+                visited |= 1ull << (py * nx + px);
+                ++visit_no; ++sp;
+                push = false;
+            }
+            if (sp == 0) break;
+            int top = sp - 1;
+            if (snext[top] == 4) { --sp; continue; }
+            int m = (sorder[top] >> (2 * snext[top])) & 3;
+            ++snext[top];
+            int qx = sx[top] + (m == 0 ? -1 : m == 1 ? 1 : 0);
+            int qy = sy[top] + (m == 2 ? 1 : m == 3 ? -1 : 0);
+            if (qx >= 0 && qx < nx && qy >= 0 && qy < nx && !((visited >> (qy * nx + qx)) & 1ull)) {
+                m_clr(wall, (sy[top] + qy) * D + (sx[top] + qx));
+                px = qx; py = qy; push = true;
+            }
+        }
+    }
+    if (pad) {
+        for (int i = 0; i < X; ++i) if (i & 1) m_set(wall, X * D + i);
+        for (int i = 0; i < D; ++i) if (i & 1) m_set(wall, i * D + X);
+    }
+    const int nb = m_count(wall);
+    if (nb < d.n_blocks) return 1;
+    // ---- goals (loc + icon variant), in creation order
+    XwMask avail;
+    for (int i = 0; i < 4; ++i) avail.w[i] = c.inrange.w[i] & ~wall.w[i];
+    for (int k = 0; k < d.G; ++k) {
+        int nf = m_count(avail);
+        if (nf == 0) return 1;
+        int cell = m_nth(avail, (int)xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_GOAL_LOC, (uint32_t)k), (uint32_t)nf));
+        m_clr(avail, cell); m_set(c.goal, cell);
+        c.gcell[k] = cell;
+        int f = d.name_first[c.gname[k]], nv = d.name_first[c.gname[k] + 1] - f;
+        c.gicon[k] = d.name_icons[f + (int)xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_GOAL_ASSET, (uint32_t)k), (uint32_t)nv)];
+    }
+    // ---- blocks: shuffle(blocks) + pop() per block entity == partial Fisher-Yates over the wall list
+    {
+        uint8_t bl[XW_MAX_DIM * XW_MAX_DIM / 2 + 8];
+        int n = 0;
+        for (int i = 0; i < D * D; ++i) if (m_get(wall, i)) bl[n++] = (uint8_t)i;
+        for (int k = 0; k < d.n_blocks; ++k) {
+            int i = nb - 1 - k;
+            if (i >= 1) {
+                int j = (int)xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_BLOCKS, (uint32_t)k), (uint32_t)i + 1);
+                uint8_t t = bl[i]; bl[i] = bl[j]; bl[j] = t;
+            }
+            m_set(c.block, bl[i]);
+        }
+    }
+    // ---- agent
+    {
+        int nf = m_count(avail);
+        if (nf == 0) return 1;
+        c.agent = m_nth(avail, (int)xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_AGENT_LOC, 0), (uint32_t)nf));
+    }
+    return 0;
+}
+
+// -------------------------------------------------------------------------- BFS
+// Breadth-first discovery from `seed`; obstacles = `obst` (the cell `pass`, if >= 0, is always
+// enterable).  order[] receives the discovered cells (seed excluded) in maze2d.flood_fill order
+// (moves (-1,0),(1,0),(0,-1),(0,1)).  Returns their count; stops early when `stop_at` is found (-2).
+XW_HD int xw_bfs(const XwMapCtx& c, const XwMask& obst, int seed, int pass, int stop_at, uint8_t* order) {
+    XwMask vis; m_zero(vis);
+    m_set(vis, seed);
+    int head = -1, n = 0;  // queue = seed, order[0..n)
+    while (head < n) {
+        int cur = head < 0 ? seed : order[head];
+        ++head;
+        if (cur == stop_at) return -2;
+        int cx = cur % c.W, cy = cur / c.W;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            int x = cx + (m == 0 ? -1 : m == 1 ? 1 : 0), y = cy + (m == 2 ? -1 : m == 3 ? 1 : 0);
+            if (x < 0 || y < 0 || x >= c.W || y >= c.H) continue;
+            int q = y * c.W + x;
+            if (m_get(vis, q)) continue;
+            if (q != pass && m_get(obst, q)) continue;
+            m_set(vis, q);
+            order[n++] = (uint8_t)q;
+        }
+    }
+    return n;
+}
+
+XW_HD bool xw_reachable(const XwMapCtx& c, const XwMask& obst, int start, int end, uint8_t* scratch) {
+    if (start == end) return true;
+    return xw_bfs(c, obst, start, end, end, scratch) == -2;
+}
+
+// -------------------------------------------------------------------------- tiles
+// Enumerates the reference's p/t/l tiles in its own order; returns the count and, when
+// pick >= 0, the pick-th pair in (a, b).  Two passes (count, then pick) avoid materialising lists.
+XW_HD int n_free4(const XwMapCtx& c, int x, int y, int excl) {
+    int n = 0;
+    if (ctx_free(c, x, y - 1) && (y - 1) * c.W + x != excl) ++n;
+    if (ctx_free(c, x - 1, y) && y * c.W + x - 1 != excl) ++n;
+    if (ctx_free(c, x + 1, y) && y * c.W + x + 1 != excl) ++n;
+    if (ctx_free(c, x, y + 1) && (y + 1) * c.W + x != excl) ++n;
+    return n;
+}
+#define XW_EMIT(A, B) do { if (n == pick) { a = (A); b = (B); } ++n; } while (0)
+XW_HD int xw_tiles(const XwMapCtx& c, int kind, int pick, int& a, int& b) {
+    int n = 0;
+    const int W = c.W;
+    for (int y = 0; y < c.H; ++y)
+        for (int x = 0; x < c.W; ++x) {
+            if (kind == XW_T3_NEAR) {  // _get_p_tiles, xworld3d_task.py:226-251
+                for (int k = 0; k < 3; ++k) {
+                    int x2 = x + (k != 1), y2 = y + (k != 0);
+                    if (ctx_free(c, x, y) && ctx_free(c, x2, y2)) {
+                        int p1 = y * W + x, p2 = y2 * W + x2;
+                        if (n_free4(c, x2, y2, p1) > 0) XW_EMIT(p1, p2);
+                        if (n_free4(c, x, y, p2) > 0) XW_EMIT(p2, p1);
+                    }
+                }
+            } else if (kind == XW_T3_BETWEEN) {  // _get_t_tiles, :253-276
+                if (ctx_free(c, x, y)) {
+                    if (ctx_free(c, x - 1, y) && ctx_free(c, x + 1, y) && (ctx_free(c, x, y - 1) || ctx_free(c, x, y + 1)))
+                        XW_EMIT(y * W + x - 1, y * W + x + 1);
+                    if (ctx_free(c, x, y - 1) && ctx_free(c, x, y + 1) && (ctx_free(c, x - 1, y) || ctx_free(c, x + 1, y)))
+                        XW_EMIT((y - 1) * W + x, (y + 1) * W + x);
+                }
+            } else {  // _get_l_tiles, :302-322
+                if (ctx_free(c, x, y) && ctx_free(c, x, y + 1) && ctx_free(c, x, y + 2)) {
+                    XW_EMIT(y * W + x, (y + 1) * W + x);
+                    XW_EMIT((y + 1) * W + x, (y + 2) * W + x);
+                }
+                if (ctx_free(c, x, y) && ctx_free(c, x + 1, y) && ctx_free(c, x + 2, y)) {
+                    XW_EMIT(y * W + x, y * W + x + 1);
+                    XW_EMIT(y * W + x + 1, y * W + x + 2);
+                }
+            }
+        }
+    return n;
+}
+#undef XW_EMIT
+
+// direction of `r` seen from `t` when looking along the unit axis vector (vx,vy):
+// XWorld3DNavTargetDirection.__compute_triple_direction (:98-126) collapsed to integers for
+// axis-aligned headings and adjacent cells (2-D world: sign>0 => "right").
+XW_HD int xw_axis_direction(int vx, int vy, int dx, int dy) {
+    if (dx == 0 && dy == 0) return XW_DIR_FALSE;
+    if (dx == vx && dy == vy) return XW_DIR_FRONT;
+    if (dx == -vx && dy == -vy) return XW_DIR_BEHIND;
+    return (vy * dx - vx * dy) > 0 ? XW_DIR_RIGHT : XW_DIR_LEFT;
+}
+
+struct XwTaskOut { int tmask, aux0, aux1, aux2; };
+
+// idle() of the five XWorld3DNav* tasks.  false = the reference's `assert ..., "map too crowded?"`.
+XW_HD bool xw_idle3d(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, int task, XwMapCtx& c, XwTaskOut& o) {
+    uint8_t order[XW_MAX_DIM * XW_MAX_DIM];
+    o.tmask = o.aux0 = o.aux1 = o.aux2 = 0;
+    const int G = d.G;
+    XwMask obst;
+    for (int i = 0; i < 4; ++i) obst.w[i] = c.block.w[i] | c.goal.w[i];
+    if (task == XW_T3_TARGET || task == XW_T3_AVOID) {
+        int cand = 0, nc = 0;
+        for (int g = 0; g < G; ++g)
+            if (xw_reachable(c, obst, c.agent, c.gcell[g], order)) { cand |= 1 << g; ++nc; }
+        if (nc == 0) return false;
+        int k = (int)xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_TASK_A, 0), (uint32_t)nc);
+        int sel = 0;
+        for (int g = 0; g < G; ++g) if (cand & (1 << g)) { if (k == 0) { sel = g; break; } --k; }
+        if (task == XW_T3_TARGET) {
+            for (int g = 0; g < G; ++g) if (c.gname[g] == c.gname[sel]) o.tmask |= 1 << g;
+            o.aux0 = sel;
+        } else {
+            int refs = 0, nr = 0;
+            for (int g = 0; g < G; ++g) if (c.gname[g] != c.gname[sel]) { refs |= 1 << g; ++nr; }
+            if (nr == 0) return false;
+            int kr = (int)xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_TASK_B, 0), (uint32_t)nr);
+            int ref = 0;
+            for (int g = 0; g < G; ++g) if (refs & (1 << g)) { if (kr == 0) { ref = g; break; } --kr; }
+            for (int g = 0; g < G; ++g) if (c.gname[g] != c.gname[ref]) o.tmask |= 1 << g;
+            o.aux0 = ref;
+        }
+        return true;
+    }
+    if (G < 2) return false;
+    // random.shuffle(goals); g1, g2 = goals[:2]
+    int perm[XW_MAX_GOALS];
+    for (int i = 0; i < G; ++i) perm[i] = i;
+    for (int i = G - 1; i >= 1; --i) {
+        int j = (int)xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_TASK_SHUF, (uint32_t)(G - 1 - i)), (uint32_t)i + 1);
+        int t = perm[i]; perm[i] = perm[j]; perm[j] = t;
+    }
+    const int g1 = perm[0], g2 = perm[1];
+    // delete agent, g1, g2
+    c.agent = -1;
+    m_clr(c.goal, c.gcell[g1]); m_clr(c.goal, c.gcell[g2]);
+    int a = 0, b = 0;
+    int nt = xw_tiles(c, task, -1, a, b);
+    if (nt == 0) return false;
+    xw_tiles(c, task, (int)xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_TASK_A, 0), (uint32_t)nt), a, b);
+    c.gcell[g1] = a; c.gcell[g2] = b;
+    m_set(c.goal, a); m_set(c.goal, b);
+    for (int i = 0; i < 4; ++i) obst.w[i] = c.block.w[i] | c.goal.w[i];
+    const int W = c.W;
+    if (task == XW_T3_NEAR) {
+        int nf = xw_bfs(c, obst, b, b, -1, order);
+        if (nf == 0) return false;
+        c.agent = order[xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_TASK_AGENT, 0), (uint32_t)nf)];
+        // goals within 1.5 (+1e-3) of g1, g1 itself excluded: the 8-neighbourhood
+        for (int g = 0; g < G; ++g) {
+            int dx = c.gcell[g] % W - a % W, dy = c.gcell[g] / W - a / W;
+            if ((dx | dy) != 0 && dx * dx + dy * dy <= 2) o.tmask |= 1 << g;
+        }
+        o.aux0 = g1;
+    } else if (task == XW_T3_BETWEEN) {
+        int mx = (a % W + b % W) / 2, my = (a / W + b / W) / 2;
+        int mid = my * W + mx;
+        int nf = xw_bfs(c, obst, mid, mid, -1, order);
+        if (nf == 0) return false;
+        c.agent = order[xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_TASK_AGENT, 0), (uint32_t)nf)];
+        o.aux0 = g1; o.aux1 = mx; o.aux2 = my;
+    } else {
+        int target = g1, referent = g2;
+        int tx = a % W, ty = a / W;
+        int ne = n_free4(c, tx, ty, -1);
+        if (ne == 0) {
+            tx = b % W; ty = b / W;
+            ne = n_free4(c, tx, ty, -1);
+            if (ne == 0) return false;
+            target = g2; referent = g1;
+        }
+        int k = (int)xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_TASK_B, 0), (uint32_t)ne);
+        // k-th free 4-neighbour in row-major order: up, left, right, down
+        int ex = 0, ey = 0;
+        const int NX[4] = {0, -1, 1, 0}, NY[4] = {-1, 0, 0, 1};
+        for (int m = 0; m < 4; ++m)
+            if (ctx_free(c, tx + NX[m], ty + NY[m])) { if (k == 0) { ex = tx + NX[m]; ey = ty + NY[m]; break; } --k; }
+        int rcell = c.gcell[referent];
+        int dir = xw_axis_direction(tx - ex, ty - ey, rcell % W - tx, rcell / W - ty);
+        int ecell = ey * W + ex;
+        int nf = 1 + xw_bfs(c, obst, ecell, ecell, -1, order);  // inclusive: seed first
+        int pick = (int)xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_TASK_AGENT, 0), (uint32_t)nf);
+        c.agent = pick == 0 ? ecell : order[pick - 1];
+        o.aux0 = referent; o.aux1 = dir; o.aux2 = target;
+    }
+    return true;
+}
+
+// idle() of XWorldNav{Target,Near,ColorTarget,Between} (walls.json).  In the reference commit NavNear
+// and NavBetween never leave idle (they pass 2-tuples to a 3-tuple BFS, XWorldNavNear.py:13-16,
+// XWorldNavBetween.py:11-13, maze2d.py:49-63); NavTarget/NavColorTarget start iff a (coloured) goal
+// is reachable with only blocks as obstacles.  reach/colour masks are per-episode constants.
+XW_HD void xw_idle2d(const XwDev& d, int64_t gid, uint32_t ep, uint32_t step_no, uint32_t& minstd, int reach_mask,
+                     int color_mask, int& task, int& stage, int& tmask, int& aux0, int32_t& steps_in_task) {
+    task = xw_get_rand_ind(minstd, 4);
+    steps_in_task = 0;
+    tmask = 0; aux0 = 0;
+    if (task == XW_T2_TARGET || task == XW_T2_COLOR_TARGET) {
+        int cand = reach_mask & (task == XW_T2_COLOR_TARGET ? color_mask : 0xff);
+        int nc = xw_popc64((uint64_t)cand);
+        if (nc > 0) {
+            int k = (int)xw_randbelow(xw_draw(d.seed, gid, ep, 0, XW_SITE_TASK_A, step_no), (uint32_t)nc);
+            int sel = 0;
+            for (int g = 0; g < XW_MAX_GOALS; ++g) if (cand & (1 << g)) { if (k == 0) { sel = g; break; } --k; }
+            aux0 = sel; tmask = 1 << sel;
+            stage = XW_STAGE_NAVIGATION;
+        }
+    }
+}
+
+// SimulatorInterface::reset_game for env `e` (simulator_interface.cpp:95-105).
+XW_HD void xw_reset_env(const XwDev& d, int e) {
+    const int n = d.n;
+    const int64_t gid = d.gid0 + e;
+    const uint32_t ep = (uint32_t)(d.episode[e] + 1);
+    d.episode[e] = (int32_t)ep;
+    uint32_t minstd = d.minstd[e];
+    int task = 0, stage = XW_STAGE_IDLE;
+    XwMapCtx c;
+    XwTaskOut o; o.tmask = o.aux0 = o.aux1 = o.aux2 = 0;
+    bool ok = false;
+    if (d.rules == XW_RULES_NAV3D) {
+        task = xw_get_rand_ind(minstd, 5);  // TaskGroup::run_stage, schedule "random"
+        for (uint32_t att = 0; att < 64 && !ok; ++att) {
+            if (xw_gen_map(d, gid, ep, att, c)) break;
+            ok = xw_idle3d(d, gid, ep, att, task, c, o);
+        }
+        stage = XW_STAGE_NAVIGATION;
+    } else {
+        ok = xw_gen_map(d, gid, ep, 0, c) == 0;
+    }
+    if (!ok) { d.error[e] = XW_ERR_INVALID_ARG; return; }
+    // ---- commit the map
+    uint8_t* g = d.grid + (size_t)e * d.CS;
+    for (int i = 0; i < d.CS; ++i) g[i] = XW_CELL_EMPTY;
+    for (int i = 0; i < d.H * d.W; ++i) if (m_get(c.block, i)) g[i] = XW_CELL_BLOCK;
+    for (int k = 0; k < d.G; ++k) {
+        g[c.gcell[k]] = (uint8_t)(XW_CELL_GOAL0 + k);
+        d.goal_x[(size_t)k * n + e] = (uint8_t)(c.gcell[k] % d.W);
+        d.goal_y[(size_t)k * n + e] = (uint8_t)(c.gcell[k] / d.W);
+        d.goal_icon[(size_t)k * n + e] = c.gicon[k];
+        d.goal_name[(size_t)k * n + e] = c.gname[k];
+    }
+    g[c.agent] = XW_CELL_AGENT;
+    d.agent_x[e] = (uint8_t)(c.agent % d.W);
+    d.agent_y[e] = (uint8_t)(c.agent / d.W);
+    d.facing[e] = 1;  // yaw 1.5707963 == "down" (xworld_env.py:42, xitem.cpp:65-78)
+    int32_t steps_in_task = 0;
+    if (d.rules == XW_RULES_NAV2D) {
+        // per-episode constants for the 2-D idle stages: goals reachable through non-block cells,
+        // goals whose icon has a colour (properties.txt)
+        uint8_t order[XW_MAX_DIM * XW_MAX_DIM];
+        int reach = 0, colored = 0;
+        for (int k = 0; k < d.G; ++k) {
+            if (xw_reachable(c, c.block, c.agent, c.gcell[k], order)) reach |= 1 << k;
+            if (d.icon_colored[c.gicon[k]]) colored |= 1 << k;
+        }
+        o.aux1 = reach; o.aux2 = colored;
+        // first teach(): nav group idle stage, then the XWorldRec group's engine draw
+        xw_idle2d(d, gid, ep, 0, minstd, reach, colored, task, stage, o.tmask, o.aux0, steps_in_task);
+        xw_minstd_next(minstd);
+    }
+    d.task[e] = (uint8_t)task; d.stage[e] = (uint8_t)stage; d.event[e] = XW_EVENT_NONE; d.succ[e] = 0;
+    d.tmask[e] = (uint8_t)o.tmask; d.aux0[e] = (uint8_t)o.aux0; d.aux1[e] = (uint8_t)o.aux1; d.aux2[e] = (uint8_t)o.aux2;
+    d.steps_in_task[e] = steps_in_task;
+    d.num_steps[e] = 0;
+    d.minstd[e] = minstd;
+}

@@ -1,0 +1,123 @@
+// xw_step.cuh -- one SimulatorInterface::take_actions for one env (one warp lane per env).
+//
+// Replaces (reference file:line):
+//   SimulatorInterface::take_actions      simulator_interface.cpp:126-137
+//   GameSimulator::take_actions           simulator.cpp:98-108      (num_steps counts calls)
+//   XWorldSimulator::take_action          games/xworld/xworld_simulator.cpp:200-265
+//   XAgent::act / XMap::move_item         games/xworld/xworld/xitem.cpp:89-155, xmap.cpp:76-101
+//   Teacher::teach -> Task::py_stage      teacher.cpp:207-230, teaching_task.cpp:64-116
+//   XWorld3DTask._time_reward/_reach_object/_successful_goal/_failed_goal
+//                                         games/xworld3d/tasks/xworld3d_task.py:451-482
+//   XWorldTask.simple_navigation_reward   games/xworld/tasks/xworld_task.py:184-223
+//   XWorldSimulator::game_over + AgentSpecificSimulator::game_over
+//                                         xworld_simulator.cpp:165-198, simulator.cpp:158-161
+#pragma once
+#include "xw_common.cuh"
+#include "xw_reset.cuh"
+
+// Rewards are the float32 images of the reference's double sums (Python double -> C++ double
+// buffer -> `float r += double`), SURVEY §8a-R.  Written as double expressions folded at compile
+// time, so no fp64 instruction reaches the GPU.
+#define XW_R3_STEP ((float)(-0.01))
+#define XW_R3_CORRECT ((float)(-0.01 + 1.0))
+#define XW_R3_WRONG ((float)(-0.01 + -1.0))
+#define XW_R2_STEP ((float)(-0.1))
+#define XW_R2_STEP_FAILED ((float)(-0.1 + -0.2))
+
+// Returns true when the env must be reset (auto_reset and the episode ended).
+XW_HD bool xw_step_env(const XwDev& d, int e, int action, int act_rep, float* reward_out, int32_t* over_out) {
+    const int n = d.n;
+    if (action < 0 || action >= 4) {  // CHECK_LT(action_idx, get_num_actions()) aborts in the reference
+        d.error[e] = XW_ERR_INVALID_ACTION;
+        *reward_out = 0.f;
+        *over_out = 0;
+        return false;
+    }
+    uint8_t* g = d.grid + (size_t)e * d.CS;
+    int ax = d.agent_x[e], ay = d.agent_y[e];
+    const int facing = d.facing[e];
+    // MOVE_UP(0,-1) MOVE_DOWN(0,+1) MOVE_LEFT(-1,0) MOVE_RIGHT(+1,0); heading codes 0 right 1 down 2 left 3 up
+    const int dx = action == 2 ? -1 : action == 3 ? 1 : 0;
+    const int dy = action == 0 ? -1 : action == 1 ? 1 : 0;
+    const int move_dir = action == 0 ? 3 : action == 1 ? 1 : action == 2 ? 2 : 0;
+    int num_steps = d.num_steps[e] + 1;
+    int collided = XW_CELL_EMPTY, success = 0;
+    for (int rep = 0; rep < act_rep; ++rep) {
+        int tx = ax + dx, ty = ay + dy;
+        if (tx < 0 || ty < 0 || tx >= d.W || ty >= d.H) { success = 0; break; }  // blocked for all repeats
+        int code = g[ty * d.W + tx];
+        if (code != XW_CELL_EMPTY) { success = 0; collided = code; break; }
+        g[ay * d.W + ax] = XW_CELL_EMPTY;
+        g[ty * d.W + tx] = XW_CELL_AGENT;
+        ax = tx; ay = ty; success = 1;
+    }
+    // ---- teacher
+    float reward = 0.f;
+    int event = XW_EVENT_NONE;
+    int stage = d.stage[e];
+    if (d.rules == XW_RULES_NAV2D) {
+        uint32_t minstd = d.minstd[e];
+        if (stage == XW_STAGE_IDLE) {
+            int task = d.task[e], tmask = d.tmask[e], aux0 = d.aux0[e];
+            int32_t sit = d.steps_in_task[e];
+            xw_idle2d(d, d.gid0 + e, (uint32_t)d.episode[e], (uint32_t)num_steps, minstd, d.aux1[e], d.aux2[e],
+                      task, stage, tmask, aux0, sit);
+            d.task[e] = (uint8_t)task; d.tmask[e] = (uint8_t)tmask; d.aux0[e] = (uint8_t)aux0;
+            d.steps_in_task[e] = sit;
+        } else {
+            reward = success ? XW_R2_STEP : XW_R2_STEP_FAILED;
+            d.steps_in_task[e] += 1;
+        }
+        xw_minstd_next(minstd);  // XWorldRec group's weighted task sampling: one engine draw per teach
+        d.minstd[e] = minstd;
+    } else if (stage == XW_STAGE_NAVIGATION) {
+        reward = XW_R3_STEP;
+        int sit = d.steps_in_task[e] + 1;
+        d.steps_in_task[e] = sit;
+        if (sit >= d.H * d.W * d.max_steps_factor) {
+            d.n_failure[e] += 1;
+            event = XW_EVENT_TIME_UP;
+            stage = XW_STAGE_TERMINAL;
+        } else {
+            // _reach_object: |angle(heading, agent->goal)| < pi/4 and goal id in collisions  <=>
+            // the blocking item is a goal and the move was along the heading
+            const int gr = (collided >= XW_CELL_GOAL0 && move_dir == facing) ? collided - XW_CELL_GOAL0 : -1;
+            const int task = d.task[e];
+            bool correct = false, wrong = false;
+            if (task == XW_T3_BETWEEN) {
+                if (gr >= 0) wrong = true;
+                else correct = (ax == d.aux1[e] && ay == d.aux2[e]);  // dist(agent, middle) < 0.5
+            } else if (task == XW_T3_DIRECTION) {
+                if (gr >= 0) {
+                    const int ref = d.aux0[e];
+                    const int rdx = (int)d.goal_x[(size_t)ref * n + e] - (int)d.goal_x[(size_t)gr * n + e];
+                    const int rdy = (int)d.goal_y[(size_t)ref * n + e] - (int)d.goal_y[(size_t)gr * n + e];
+                    const int fx = facing == 0 ? 1 : facing == 2 ? -1 : 0, fy = facing == 1 ? 1 : facing == 3 ? -1 : 0;
+                    const bool close = (rdx * rdx + rdy * rdy) <= 1;  // dist < 1 + 1e-3
+                    correct = close && (rdx | rdy) != 0 && xw_axis_direction(fx, fy, rdx, rdy) == d.aux1[e];
+                    wrong = !correct;
+                }
+            } else {  // Target / Near / Avoid: membership in the target set
+                if (gr >= 0) { correct = (d.tmask[e] >> gr) & 1; wrong = !correct; }
+            }
+            if (correct) {
+                d.n_success[e] += 1; d.success_steps[e] += sit;
+                event = XW_EVENT_CORRECT_GOAL; reward = XW_R3_CORRECT; stage = XW_STAGE_TERMINAL;
+            } else if (wrong) {
+                d.n_failure[e] += 1;
+                event = XW_EVENT_WRONG_GOAL; reward = XW_R3_WRONG; stage = XW_STAGE_TERMINAL;
+            }
+        }
+    }  // XW_STAGE_TERMINAL: ["terminal", 0, ""]
+    int over = 0;
+    if (d.max_steps > 0 && num_steps >= d.max_steps) over |= XW_MAX_STEP;
+    if (event == XW_EVENT_CORRECT_GOAL) over |= XW_SUCCESS;
+    else if (event == XW_EVENT_WRONG_GOAL) over |= XW_DEAD;
+    else if (event == XW_EVENT_TIME_UP) over |= XW_MAX_STEP;
+    d.agent_x[e] = (uint8_t)ax; d.agent_y[e] = (uint8_t)ay;
+    d.num_steps[e] = num_steps;
+    d.stage[e] = (uint8_t)stage; d.event[e] = (uint8_t)event; d.succ[e] = (uint8_t)success;
+    *reward_out = reward;
+    *over_out = over;
+    return d.auto_reset && over != 0;
+}

@@ -1,0 +1,302 @@
+"""Host-side mirror of the reference's Python API, over the C ABI.
+
+    from xworld_b200 import Simulator
+    sim = Simulator.create("xworld", {"xwd_conf_path": ".../confs/navigation2d.json", "n_envs": 65536})
+
+keeps the method names and semantics of `py_simulator.Simulator` (python/py_simulator.cpp:310-329):
+create, reset_game, game_over, get_num_actions, get_lives, get_screen_out_dimensions, take_actions,
+take_action, get_state, get_num_steps.  With n_envs == 1 (the default) the return types are the
+reference's (float reward, "alive|dead|..." string, dict with a [0,1] float screen list); with
+n_envs > 1 the same calls take / return arrays, and CUDA tensors stay on the device.
+
+There is no CPU fallback for xworld / simple_race: without the CUDA library or a GPU, create() raises.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+
+from . import _abi
+from .catalog import Catalog
+
+_CODE_NAMES = ((_abi.XW_MAX_STEP, "max_step"), (_abi.XW_DEAD, "dead"), (_abi.XW_SUCCESS, "success"),
+               (_abi.XW_LOST_LIFE, "lost_life"))
+
+
+def decode_game_over_code(code):
+    """GameSimulator::decode_game_over_code (simulator.cpp:125-144)."""
+    if code == 0:
+        return "alive"
+    return "|".join(n for bit, n in _CODE_NAMES if code & bit)
+
+
+def _opt(opts, key, required, default):
+    """extract_py_dict_val (py_simulator.cpp:36-56): missing required key -> RuntimeError."""
+    if key in opts:
+        return opts[key]
+    if required:
+        raise RuntimeError("Key '%s' is required" % key)
+    return default
+
+
+def rules_from_conf(conf):
+    """Which teacher rule set a conf json selects (teacher.cpp:70-99 reads task_groups)."""
+    groups = conf.get("task_groups", {})
+    tasks = [t for g in groups.values() for t in g.get("tasks", {})]
+    if any(t.startswith("XWorld3DNav") for t in tasks):
+        return _abi.XW_RULES_NAV3D
+    if any(t.startswith("XWorldNav") for t in tasks):
+        return _abi.XW_RULES_NAV2D
+    raise RuntimeError("conf has no navigation task group this engine implements: %s" % sorted(groups))
+
+
+class Simulator(object):
+    def __init__(self, name, cfg, catalog, n_envs, device):
+        self._lib = _abi.load()
+        self.name, self.cfg, self.catalog, self.n_envs = name, cfg, catalog, n_envs
+        h = C.c_void_p()
+        rc = self._lib.xw_create(C.byref(cfg), C.byref(catalog.as_c()) if catalog is not None else None,
+                                 n_envs, device, C.byref(h))
+        if rc != 0:
+            raise RuntimeError("xw_create failed (%d): %s" % (rc, self._lib.xw_last_error().decode()))
+        self._h = h
+        dims = [C.c_int32() for _ in range(4)]
+        self._lib.xw_screen_dims(h, *[C.byref(d) for d in dims])
+        self.height, self.width, self.channels, self.context = [d.value for d in dims]
+        self._on_gpu = cfg.game != _abi.XW_GAME_SIMPLE_GAME
+        self._last_over = np.zeros(n_envs, np.int32)
+        self._last_reward = np.zeros(n_envs, np.float32)
+        self._screen = None  # device tensor (gpu games) or numpy (simple_game)
+        self._torch = None
+        if self._on_gpu:
+            import torch
+            self._torch = torch
+            self._dev = torch.device("cuda", torch.cuda.current_device() if device < 0 else device)
+            dt = torch.float32 if cfg.game == _abi.XW_GAME_SIMPLE_RACE else torch.uint8
+            self._screen = torch.zeros((n_envs, self.context * self.channels, self.height, self.width), dtype=dt,
+                                       device=self._dev)
+            self._d_reward = torch.zeros(n_envs, dtype=torch.float32, device=self._dev)
+            self._d_over = torch.zeros(n_envs, dtype=torch.int32, device=self._dev)
+        else:
+            self._screen = np.zeros((n_envs, self.width), np.uint8)
+
+    # ------------------------------------------------------------------ factory
+    @staticmethod
+    def create(name, opts=None):
+        """py_simulator.Simulator.create(name, dict) (py_simulator.cpp:169-191)."""
+        opts = dict(opts or {})
+        n_envs = int(opts.pop("n_envs", 1))
+        device = int(opts.pop("device", -1))
+        catalog = None
+        if name == "simple_game":
+            cfg = _abi.default_config(game=_abi.XW_GAME_SIMPLE_GAME, array_size=int(_opt(opts, "array_size", True, 0)))
+        elif name == "simple_race":
+            cfg = _abi.default_config(
+                game=_abi.XW_GAME_SIMPLE_RACE,
+                track_type={"straight": 0, "circle": 1}[_opt(opts, "track_type", False, "straight")],
+                track_width=float(_opt(opts, "track_width", True, 20.0)),
+                track_length=float(_opt(opts, "track_length", True, 100.0)),
+                track_radius=float(_opt(opts, "track_radius", True, 30.0)),
+                race_full_manouver=int(bool(_opt(opts, "race_full_manouver", False, False))),
+                race_random=int(bool(_opt(opts, "random", False, False))),
+                difficulty={"easy": 0, "hard": 1}[_opt(opts, "difficulty", False, "easy")],
+                reward_scale=float(opts.get("reward_scale", 1.0)))
+        elif name == "xworld":
+            conf_path = _opt(opts, "xwd_conf_path", True, "")
+            with open(conf_path) as f:
+                conf = json.load(f)
+            if conf.get("map") != "XWorldNav":
+                raise RuntimeError("map '%s' is not implemented (XWorldNav only)" % conf.get("map"))
+            task_mode = _opt(opts, "task_mode", False, "one_channel")  # py default, py_simulator.cpp:129
+            if task_mode != "lang_acquisition":
+                raise RuntimeError("task_mode '%s' is not implemented (lang_acquisition only)" % task_mode)
+            if not _opt(opts, "color", False, False):
+                raise RuntimeError("color=False (grayscale) is not implemented; pass {'color': True}")
+            if float(_opt(opts, "curriculum", False, 0)) != 0:
+                raise RuntimeError("curriculum > 0 is not implemented")
+            catalog = opts.get("catalog")
+            if catalog is None:
+                item_path = opts.get("item_path")
+                if item_path is None:  # xworld.cpp:86: <games/xworld>/<item_path>
+                    for rel in ("..", os.path.join("..", "games", "xworld")):
+                        cand = os.path.join(os.path.dirname(os.path.abspath(conf_path)), rel, conf["item_path"])
+                        if os.path.isdir(cand):
+                            item_path = cand
+                            break
+                if item_path is None:
+                    raise RuntimeError("cannot locate item_path '%s' next to %s; pass opts['item_path'] or "
+                                       "opts['catalog']" % (conf["item_path"], conf_path))
+                catalog = Catalog.from_item_path(item_path)
+            dim = int(opts.get("map_size", 8))  # XWorldNav.py:10-11 hard-codes 8
+            default_blocks = {7: 12, 8: 16, 11: 30, 15: 56}.get(dim, 2 * dim)
+            cfg = _abi.default_config(
+                game=_abi.XW_GAME_XWORLD, height=dim, width=dim,
+                n_goals=int(opts.get("n_goals", 4)), n_blocks=int(opts.get("n_blocks", default_blocks)),
+                rules=rules_from_conf(conf), out_h=int(opts.get("out_h", 0)), out_w=int(opts.get("out_w", 0)),
+                context=int(_opt(opts, "context", False, 1)), visible_radius=int(_opt(opts, "visible_radius", False, 0)),
+                max_steps=int(opts.get("max_steps", 0)), max_steps_factor=int(opts.get("max_steps_factor", 10)))
+        else:
+            raise RuntimeError("Unrecognized game type: " + name)
+        cfg.auto_reset = int(bool(opts.get("auto_reset", False)))
+        cfg.seed = int(opts.get("seed", 0))
+        cfg.simulator_seed = int(opts.get("simulator_seed", 0))
+        cfg.env_id_offset = int(opts.get("env_id_offset", 0))
+        if "max_steps" in opts:
+            cfg.max_steps = int(opts["max_steps"])
+        return Simulator(name, cfg, catalog, n_envs, device)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.xw_destroy(h)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError("xworld_b200 error %d: %s" % (rc, self._lib.xw_last_error().decode()))
+
+    def _stream(self):
+        return C.c_void_p(self._torch.cuda.current_stream(self._dev).cuda_stream)
+
+    # ------------------------------------------------------------------ reference API
+    def reset_game(self, mask=None):
+        """SimulatorInterface::reset_game (simulator_interface.cpp:95-105)."""
+        if not self._on_gpu:
+            m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+            self._check(self._lib.xw_reset_host(self._h, None if m is None else m.ctypes.data, self._screen.ctypes.data))
+        else:
+            t = self._torch
+            dm = None
+            if mask is not None:
+                dm = t.as_tensor(mask).to(device=self._dev, dtype=t.uint8).contiguous()
+            with t.cuda.device(self._dev):
+                if self.context > 1 and mask is None:
+                    self._screen.zero_()
+                self._check(self._lib.xw_reset(self._h, None if dm is None else dm.data_ptr(), self._stream()))
+                if self.cfg.game == _abi.XW_GAME_XWORLD:
+                    self._check(self._lib.xw_render(self._h, self._screen.data_ptr(), self._stream()))
+        self._last_over[:] = 0
+
+    def game_over(self):
+        """'alive' | 'max_step' | 'dead' | 'success' | 'lost_life' (|-joined); a list when n_envs > 1."""
+        if self.n_envs == 1:
+            return decode_game_over_code(int(self._last_over[0]))
+        return [decode_game_over_code(int(c)) for c in self._last_over]
+
+    def game_over_codes(self):
+        return self._last_over.copy()
+
+    def get_num_actions(self):
+        return int(self._lib.xw_num_actions(self._h))
+
+    def get_lives(self):
+        """XWorldSimulator::get_lives: game_over() ? 0 : 1 (xworld_simulator.cpp:506)."""
+        lives = (self._last_over == 0).astype(np.int32)
+        return int(lives[0]) if self.n_envs == 1 else lives
+
+    def get_screen_out_dimensions(self):
+        return [self.height, self.width, self.channels, self.context]
+
+    def get_num_steps(self):
+        out = np.zeros(self.n_envs, np.int64)
+        self._check(self._lib.xw_num_steps(self._h, out.ctypes.data))
+        return int(out[0]) if self.n_envs == 1 else out
+
+    def take_actions(self, actions, act_rep=1, show_screen=False):
+        """SimulatorInterface::take_actions (simulator_interface.cpp:126-137).
+
+        actions: the reference's dict {"action": int[, "pred_sentence": str]} (n_envs == 1), a host
+        int array [n_envs], or a CUDA int32 tensor [n_envs] (stays on the device: returns CUDA tensors
+        (reward, game_over) and refreshes the device screen)."""
+        if show_screen:
+            raise RuntimeError("show_screen is not supported (no GUI in the batched engine)")
+        t = self._torch
+        if t is not None and isinstance(actions, t.Tensor) and actions.is_cuda:
+            a = actions.to(dtype=t.int32).contiguous()
+            if a.numel() != self.n_envs:
+                raise RuntimeError("expected %d actions" % self.n_envs)
+            with t.cuda.device(self._dev):
+                self._check(self._lib.xw_step(self._h, a.data_ptr(), int(act_rep), self._d_reward.data_ptr(),
+                                              self._d_over.data_ptr(), self._screen.data_ptr(), self._stream()))
+            return self._d_reward, self._d_over
+        if isinstance(actions, dict):
+            if len(actions) == 0:
+                raise RuntimeError("You can't take an empty action")
+            a = np.full(self.n_envs, int(actions.get("action", 0)), np.int32)
+        else:
+            a = np.ascontiguousarray(actions, np.int32).reshape(-1)
+            if a.size != self.n_envs:
+                raise RuntimeError("expected %d actions" % self.n_envs)
+        r = np.zeros(self.n_envs, np.float32)
+        o = np.zeros(self.n_envs, np.int32)
+        if not self._on_gpu:
+            self._check(self._lib.xw_step_host(self._h, a.ctypes.data, int(act_rep), r.ctypes.data, o.ctypes.data,
+                                               self._screen.ctypes.data))
+        else:
+            da = t.from_numpy(a).to(self._dev)
+            with t.cuda.device(self._dev):
+                self._check(self._lib.xw_step(self._h, da.data_ptr(), int(act_rep), self._d_reward.data_ptr(),
+                                              self._d_over.data_ptr(), self._screen.data_ptr(), self._stream()))
+            r = self._d_reward.cpu().numpy()
+            o = self._d_over.cpu().numpy()
+        self._last_reward, self._last_over = r, o
+        return float(r[0]) if self.n_envs == 1 else r
+
+    def take_action(self, actions, show_screen=False):
+        return self.take_actions(actions, 1, show_screen)
+
+    def screen(self):
+        """The raw screen bytes: CUDA uint8 tensor [n_envs, context*C, H, W] (planes B, G, R)."""
+        return self._screen
+
+    def get_state(self):
+        """PySimulatorInterface::get_state (py_simulator.cpp:246-285).  n_envs == 1: the reference dict
+        (uint8 screen scaled by 1/255 into a float list); n_envs > 1: {"screen": raw tensor}."""
+        if self.n_envs > 1:
+            return {"screen": self._screen}
+        if self._on_gpu:
+            scr = self._screen[0].reshape(-1).cpu().numpy()
+        else:
+            scr = self._screen[0]
+        d = {}
+        if self.cfg.game == _abi.XW_GAME_SIMPLE_RACE:
+            d["screen"] = [float(x) for x in scr]
+        else:
+            scale = np.float32(1 / 255.0)
+            d["screen"] = [float(np.float32(x) * scale) for x in scr]
+        if self.cfg.game == _abi.XW_GAME_XWORLD:
+            d["sentence"] = "-"  # teacher sentences are out of scope
+            ev = int(self.get_field("event")[0])
+            d["task"] = ""
+            d["event"] = ["", "correct_goal", "wrong_goal", "time_up"][ev]
+            d["height"], d["width"] = str(self.cfg.height), str(self.cfg.width)
+        return d
+
+    # ------------------------------------------------------------------ state access
+    def get_field(self, name):
+        n = self.n_envs
+        if name == "grid":
+            out = np.zeros((n, self.cfg.height * self.cfg.width), np.uint8)
+        elif name in ("goal_x", "goal_y"):
+            out = np.zeros((n, _abi.XW_MAX_GOALS), np.uint8)
+        elif name in ("goal_icon", "goal_name"):
+            out = np.zeros((n, _abi.XW_MAX_GOALS), np.int32)
+        elif name in ("agent_x", "agent_y", "facing", "task", "stage", "event", "action_success", "target_mask",
+                      "aux0", "aux1", "aux2"):
+            out = np.zeros(n, np.uint8)
+        elif name == "state":
+            out = np.zeros((n, 4), np.float32)
+        elif name in ("pos_x", "pos_y", "angle"):
+            out = np.zeros(n, np.float32)
+        else:
+            out = np.zeros(n, np.int32)
+        self._check(self._lib.xw_get_field(self._h, name.encode(), out.ctypes.data, out.nbytes))
+        return out
+
+    def set_field(self, name, value):
+        cur = self.get_field(name)
+        v = np.ascontiguousarray(value, cur.dtype).reshape(cur.shape)
+        self._check(self._lib.xw_set_field(self._h, name.encode(), v.ctypes.data, v.nbytes))
+
+    def launch_count(self):
+        return int(self._lib.xw_launch_count(self._h))
