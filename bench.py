@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec (step + teacher reward + render) of the batched XWorld2D engine.
+
+Workload (BASELINE.json `metric`: "... at 64k envs"; configs[2]): XWorld2D walls.json rules,
+11x11 spanning-tree maze, 4 goals, 30 blocks, 84x84x3 uint8 observations, 65536 envs PER GPU
+(weak scaling), i.i.d. uniform actions, auto-reset on (max_steps = 2*H*W = 242), synthetic icons.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this engine
+    python bench.py --impl reference [...]                         # CPU arm: the oracle port on host cores
+    torchrun --nproc-per-node N bench.py --gpus N ...              # one rank per GPU, NCCL
+
+One JSON line on rank 0 (contract in the task description): value = whole-job env-steps/s with
+inputs resident in HBM; e2e = the same metric through the host-buffer C ABI (xw_step_hd: host actions
+in, host reward + game_over out, frames left in HBM for a co-located learner) with the copies inside
+the timed region; roofline = the render kernel's algorithmic bytes / its CUDA-event time vs the
+measured HBM peak; cpu_baseline = the oracle port timed on this box's host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+ENVS_PER_GPU = 65536
+WORKLOAD = dict(height=11, width=11, n_goals=4, n_blocks=30, rules=1, out_h=84, out_w=84, max_steps=242,
+                auto_reset=1, seed=1234, simulator_seed=1)
+WORKLOAD_NAME = "XWorld2D walls.json rules, 11x11 maze, 84x84x3 u8 obs, 65536 envs/GPU (BASELINE configs[2])"
+# 3*84*84 frame write + 121 grid bytes + 28 bytes of action/reward/game_over/agent state
+BYTES_PER_ENV_STEP = 3 * 84 * 84 + 11 * 11 + 28
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_arm(steps, warmup, sample_envs, threads):
+    """The reference's CPU path for this workload = the oracle port (the reference cannot link OpenCV
+    here): step + teacher + the full canvas/resize render pipeline, all host threads."""
+    import numpy as np
+    import oracle
+    from xworld_b200 import _abi
+    from xworld_b200.catalog import Catalog
+    cfg = _abi.default_config(**WORKLOAD)
+    cat = Catalog.synthetic(seed=0)
+    orc = oracle.Oracle(cfg, cat, sample_envs, threads=threads)
+    orc.reset()
+    rng = np.random.RandomState(0)
+    acts = [rng.randint(0, 4, sample_envs).astype(np.int32) for _ in range(8)]
+    for s in range(warmup):
+        orc.step(acts[s % 8], render=True)
+    t0 = time.perf_counter()
+    for s in range(steps):
+        orc.step(acts[s % 8], render=True)
+    dt = time.perf_counter() - t0
+    return sample_envs * steps / dt, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    threads = os.cpu_count() or 1
+    config = {"workload": WORKLOAD_NAME, "map": "11x11", "obs": "84x84x3 u8 (B,G,R planes)", "rules": "walls.json",
+              "envs_per_gpu": args.envs_per_gpu, "auto_reset": True, "max_steps": 242, "actions": "iid uniform{0..3}",
+              "l2": "each step writes 1.39 GB of frames per GPU (>> 126 MB L2), so no L2 flush is needed",
+              "bytes_per_env_step": BYTES_PER_ENV_STEP}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        sample = 1024
+        steps = max(1, args.steps)
+        steps = min(steps, 40)  # bounded: ~2-3k frames/s on 8 cores
+        v, dt = cpu_reference_arm(steps, min(args.warmup, 3), sample, threads)
+        line = {"impl": "reference", "metric": "env_steps_per_sec", "value": v, "unit": "env-steps/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": dt / steps * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": dict(config, sample="%d envs per step (bounded sample of the 65536-env workload)" % sample),
+                "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port",
+                                 "sample": "%d envs x %d steps, OpenMP over envs" % (sample, steps)},
+                "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import numpy as np
+    import torch
+    from xworld_b200 import _abi
+    from xworld_b200.catalog import Catalog
+    from xworld_b200.sharding import gather_throughput
+    from xworld_b200.simulator import Simulator
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.envs_per_gpu
+    cfg = _abi.default_config(**WORKLOAD)
+    cfg.env_id_offset = rank * n  # contiguous global env ids: the union of ranks is one logical batch
+    sim = Simulator("xworld", cfg, Catalog.synthetic(seed=0), n, local_rank)
+    lib, h = sim._lib, sim._h
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(99 + rank)
+    acts = [torch.randint(0, 4, (n,), dtype=torch.int32, device=dev, generator=gen) for _ in range(8)]
+    frames = sim.screen()
+    reward = torch.zeros(n, dtype=torch.float32, device=dev)
+    over = torch.zeros(n, dtype=torch.int32, device=dev)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    sim.reset_game()
+
+    def step(i):
+        rc = lib.xw_step(h, acts[i % 8].data_ptr(), 1, reward.data_ptr(), over.data_ptr(), frames.data_ptr(), stream)
+        if rc:
+            raise RuntimeError(lib.xw_last_error().decode())
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    lib.xw_enable_timing(h, 1)
+    lib.xw_render_ms(h, 1)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = sim.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = sim.launch_count() - launches0
+    render_ms = lib.xw_render_ms(h, 1)
+    lib.xw_enable_timing(h, 0)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    total_steps, _, per_rank = gather_throughput(n * args.steps, int(ms * 1e6), device=dev)
+    value = total_steps / (ms_max / 1e3)
+
+    # ---- end to end through the host-buffer C ABI (pinned host actions in, host reward/over out)
+    e2e = None
+    if not args.no_e2e:
+        h_act = [torch.randint(0, 4, (n,), dtype=torch.int32).pin_memory() for _ in range(4)]
+        h_rew = torch.zeros(n, dtype=torch.float32).pin_memory()
+        h_over = torch.zeros(n, dtype=torch.int32).pin_memory()
+        k2 = max(10, args.steps // 4)
+        for i in range(3):
+            lib.xw_step_hd(h, h_act[i % 4].data_ptr(), 1, h_rew.data_ptr(), h_over.data_ptr(), frames.data_ptr())
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(k2):
+            rc = lib.xw_step_hd(h, h_act[i % 4].data_ptr(), 1, h_rew.data_ptr(), h_over.data_ptr(), frames.data_ptr())
+            assert rc == 0
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": n * world * k2 / float(tt.item()), "unit": "env-steps/s", "h2d_bytes_per_step": 4 * n,
+               "d2h_bytes_per_step": 8 * n, "steps": k2,
+               "what": "xw_step_hd: pinned host actions -> H2D, step+reset+render kernels, reward+game_over D2H, "
+                       "stream sync; frames stay in HBM (consumer = co-located learner)"}
+        if rank == 0 and world == 1:  # frames to the host too (PCIe-bound), reported beside it
+            hf = torch.empty((n, 3, 84, 84), dtype=torch.uint8).pin_memory()
+            for i in range(2):
+                lib.xw_step_host(h, h_act[0].data_ptr(), 1, h_rew.data_ptr(), h_over.data_ptr(), hf.data_ptr())
+            t0 = time.perf_counter()
+            k3 = 5
+            for i in range(k3):
+                lib.xw_step_host(h, h_act[i % 4].data_ptr(), 1, h_rew.data_ptr(), h_over.data_ptr(), hf.data_ptr())
+            dt = time.perf_counter() - t0
+            e2e["with_frames_to_host"] = {"value": n * k3 / dt, "unit": "env-steps/s",
+                                          "d2h_bytes_per_step": 8 * n + n * 3 * 84 * 84}
+            del hf
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+    peak, peak_src = hbm_peak()
+    achieved = BYTES_PER_ENV_STEP * n / (render_ms * 1e-3) / 1e9 if render_ms and render_ms > 0 else None
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "render_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    line = {
+        "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
+        "roofline": {"bound": "hbm", "kernel": "k_render", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                     "kernel_ms": render_ms, "kernel_share_of_step": (render_ms / (ms / args.steps)) if render_ms else None,
+                     "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n},
+        "gpu_launches": launches, "clocks": clocks, "per_rank": per_rank,
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if world == 1 and not args.no_cpu_baseline:
+        sample, ksteps = 1024, 20
+        v, dt = cpu_reference_arm(ksteps, 2, sample, threads)
+        line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port",
+                                "sample": "%d envs x %d steps of the same workload (%.1f s), oracle C port, OpenMP" % (
+                                    sample, ksteps, dt)}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -157,6 +157,10 @@ int xw_render(xw_sim* sim, uint8_t* d_frames, void* stream);
 int xw_step_host(xw_sim* sim, const int32_t* h_actions, int32_t act_rep, float* h_reward,
                  int32_t* h_game_over, uint8_t* h_frames);
 int xw_reset_host(xw_sim* sim, const uint8_t* h_mask, uint8_t* h_frames);
+/* Host actions / reward / game_over, frames rendered into a DEVICE buffer (NULL = no render): the
+ * call a trainer with a co-located GPU learner makes.  Copies + synchronises like xw_step_host. */
+int xw_step_hd(xw_sim* sim, const int32_t* h_actions, int32_t act_rep, float* h_reward,
+               int32_t* h_game_over, uint8_t* d_frames);
 
 /* get_num_actions / get_screen_out_dimensions / get_num_steps / get_lives
  * (simulator_interface.h:52-63). */

@@ -91,7 +91,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libxworld_b
 # every symbol include/xworld_b200.h declares
 SYMBOLS = [
     "xw_config_init", "xw_create", "xw_destroy", "xw_last_error", "xw_reset", "xw_step", "xw_render",
-    "xw_step_host", "xw_reset_host", "xw_num_envs", "xw_num_actions", "xw_screen_dims",
+    "xw_step_host", "xw_reset_host", "xw_step_hd", "xw_num_envs", "xw_num_actions", "xw_screen_dims",
     "xw_frame_bytes", "xw_num_steps", "xw_get_field", "xw_set_field", "xw_launch_count",
     "xw_enable_timing", "xw_render_ms",
 ]
@@ -124,6 +124,8 @@ def load():
     lib.xw_render.restype = C.c_int
     lib.xw_step_host.argtypes = [vp, vp, i32, vp, vp, vp]
     lib.xw_step_host.restype = C.c_int
+    lib.xw_step_hd.argtypes = [vp, vp, i32, vp, vp, vp]
+    lib.xw_step_hd.restype = C.c_int
     lib.xw_reset_host.argtypes = [vp, vp, vp]
     lib.xw_reset_host.restype = C.c_int
     lib.xw_num_envs.argtypes = [vp]

@@ -555,6 +555,24 @@ int xw_step_host(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float* h_
     return 0;
 }
 
+int xw_step_hd(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float* h_reward, int32_t* h_game_over, uint8_t* d_frames) {
+    if (!h_actions || !h_reward || !h_game_over) return set_err(XW_ERR_INVALID_ARG, "null buffer");
+    if (s->cfg.game == XW_GAME_SIMPLE_GAME) return set_err(XW_ERR_UNSUPPORTED, "simple_game has no device frames");
+    int rc = ensure_staging(s, false);
+    if (rc) return rc;
+    cudaStream_t st = s->own_stream;
+    memcpy(s->h_act, h_actions, sizeof(int32_t) * s->n);
+    CUDA_TRY(cudaMemcpyAsync(s->d_act, s->h_act, sizeof(int32_t) * s->n, cudaMemcpyHostToDevice, st));
+    rc = xw_step(s, s->d_act, act_rep, s->d_rew, s->d_over, d_frames, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(s->h_rew, s->d_rew, sizeof(float) * s->n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(s->h_over, s->d_over, sizeof(int32_t) * s->n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    memcpy(h_reward, s->h_rew, sizeof(float) * s->n);
+    memcpy(h_game_over, s->h_over, sizeof(int32_t) * s->n);
+    return 0;
+}
+
 int xw_num_steps(xw_sim* s, int64_t* h) {
     if (s->cfg.game == XW_GAME_SIMPLE_GAME) { for (int i = 0; i < s->n; ++i) h[i] = s->sg[i].num_steps; return 0; }
     std::vector<int32_t> tmp(s->n);
