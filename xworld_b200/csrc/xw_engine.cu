@@ -128,7 +128,8 @@ static int dupload(xw_sim* s, const T** p, const T* host, size_t count) {
     return 0;
 }
 
-static cudaStream_t pick_stream(xw_sim* s, void* stream) { return stream ? (cudaStream_t)stream : s->own_stream; }
+// `stream` is the caller's cudaStream_t; NULL is the legacy default stream, as in the CUDA runtime.
+static cudaStream_t pick_stream(xw_sim*, void* stream) { return (cudaStream_t)stream; }
 
 // ThreadCounter seed of the reference's i-th simulator thread (simulator_util.cpp:38-52):
 // int seed = std::hash<std::string>()(std::to_string(FLAGS_simulator_seed + i)); reng_.seed(seed)
@@ -577,7 +578,7 @@ int xw_num_steps(xw_sim* s, int64_t* h) {
     if (s->cfg.game == XW_GAME_SIMPLE_GAME) { for (int i = 0; i < s->n; ++i) h[i] = s->sg[i].num_steps; return 0; }
     std::vector<int32_t> tmp(s->n);
     const int32_t* src = s->cfg.game == XW_GAME_XWORLD ? s->d.num_steps : s->race.steps;
-    CUDA_TRY(cudaStreamSynchronize(s->own_stream));
+    CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemcpy(tmp.data(), src, sizeof(int32_t) * s->n, cudaMemcpyDeviceToHost));
     for (int i = 0; i < s->n; ++i) h[i] = tmp[i];
     return 0;
@@ -616,7 +617,7 @@ static int field_io(xw_sim* s, const char* name, void* h, size_t bytes, bool get
     FieldRef f;
     if (!find_field(s, name, &f)) return set_err(XW_ERR_INVALID_ARG, "unknown field '%s'", name);
     const size_t n = s->n;
-    CUDA_TRY(cudaStreamSynchronize(s->own_stream));
+    CUDA_TRY(cudaDeviceSynchronize());
     if (std::string(name) == "grid") {  // host layout [n][H*W], device rows are CS wide
         const size_t hw = (size_t)s->d.H * s->d.W;
         if (bytes != n * hw) return set_err(XW_ERR_INVALID_ARG, "field grid: expected %zu bytes", n * hw);
