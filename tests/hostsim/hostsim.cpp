@@ -23,6 +23,7 @@ struct HostSim {
     XwRenderTables tab;
     std::vector<std::vector<uint8_t>> bufs;
     std::vector<uint8_t> T;
+    std::vector<uint16_t> ecol, uv;
     XwRaceCfg race;
 };
 
@@ -84,13 +85,34 @@ HostSim* hs_create(const xw_config* c, const xw_catalog* cat, int n) {
     XwRenderTables& t = s->tab;
     XwRender& r = s->r;
     memset(&r, 0, sizeof r);
-    r.OH = OH; r.OW = OW; r.WR = t.WR; r.FB = t.FB; r.H = c->height; r.W = c->width; r.R = t.R; r.rpg = t.rpg;
-    r.n_sc = (int)t.sc.size(); r.n_sr = (int)t.sr.size();
+    r.OH = OH; r.OW = OW; r.WR = t.WR; r.FB = t.FB; r.H = c->height; r.W = c->width;
+    r.n_items = (int)t.items.size();
     r.n_icons = cat->n_icons; r.brick_icon = cat->brick_icon; r.agent_icon = cat->agent_icon;
-    r.xofs = t.xofs.data(); r.xa0 = t.xa0.data(); r.xa1 = t.xa1.data();
-    r.yofs = t.yofs.data(); r.ya0 = t.ya0.data(); r.ya1 = t.ya1.data();
-    r.rowcell = t.rowcell.data(); r.bandend = t.bandend.data(); r.colpair = t.colpair.data();
-    r.sc = t.sc.data(); r.sr = t.sr.data();
+    r.taps.xofs = t.xofs.data(); r.taps.xa0 = t.xa0.data(); r.taps.xa1 = t.xa1.data();
+    r.taps.yofs = t.yofs.data(); r.taps.ya0 = t.ya0.data(); r.taps.ya1 = t.ya1.data();
+    r.items = t.items.data();
+    for (int i = 0; i <= XW_ITEM_TYPES; ++i) r.seg[i] = t.seg[i];
+    r.n_sr = (int)t.sr.size();
+    r.sr = t.sr.data();
+    r.atlas64 = cat->atlas64;
+    if (t.fast_ok) {  // k_build_edge_tables
+        s->ecol.resize((size_t)(cat->n_icons + 1) * 2 * 3 * OH);
+        s->uv.resize((size_t)(cat->n_icons + 1) * r.n_sr * 2 * 3 * OW + 8);
+        for (size_t i = 0; i < (size_t)(cat->n_icons + 1) * 2 * 3 * OH; ++i) {
+            size_t j = i;
+            const int dy = (int)(j % OH); j /= OH;
+            const int cc = (int)(j % 3); j /= 3;
+            s->ecol[i] = xw_ecol_entry(r, (uint32_t)(j / 2), (int)(j % 2), cc, dy);
+        }
+        for (size_t i = 0; i < (size_t)(cat->n_icons + 1) * r.n_sr * 2 * 3 * OW; ++i) {
+            size_t j = i;
+            const int dx = (int)(j % OW); j /= OW;
+            const int cc = (int)(j % 3); j /= 3;
+            const int role = (int)(j % 2); j /= 2;
+            s->uv[i] = xw_uv_entry(r, (uint32_t)(j / r.n_sr), (int)(j % r.n_sr), role, cc, dx);
+        }
+        r.ecol = s->ecol.data(); r.uv = s->uv.data();
+    }
     r.atlas64 = cat->atlas64;
     return s;
 }
@@ -110,7 +132,7 @@ void hs_build_phase_atlas(HostSim* s, const int32_t* icons, int n_icons) {
 }
 
 int hs_fast_ok(HostSim* s) { return s->tab.fast_ok; }
-int hs_threads(HostSim* s) { return s->tab.threads; }
+int hs_threads(HostSim* s) { return XW_RENDER_THREADS; }
 void hs_destroy(HostSim* s) { delete s; }
 
 void hs_reset(HostSim* s, const uint8_t* mask) {
@@ -127,19 +149,32 @@ void hs_step(HostSim* s, const int32_t* actions, int act_rep, float* reward, int
         if (xw_step_env(s->d, e, actions[e], act_rep, &reward[e], &over[e])) xw_reset_env(s->d, e);
 }
 
-// Emulates one k_render CTA per env: celldesc, compose for every tid, fix-up list, copy out.
+// Emulates one k_render warp group per env: celldesc, every item of the plan, copy out.  Configs the
+// compositor does not take go through the generic per-pixel rule (k_render_generic's arithmetic).
 void hs_render(HostSim* s, uint8_t* frames) {
     XwRender& r = s->r;
     XwDev& d = s->d;
-    std::vector<uint32_t> cell(XW_MAX_DIM * XW_MAX_DIM), fb(r.FB / 4 + 4);
-    const uint8_t* hot = r.T + (size_t)r.brick_icon * r.FB;
+    std::vector<uint32_t> cell(XW_CELL_STRIDE, 0), fb(r.FB / 4 + 4), yb(r.OH);
+    alignas(16) static const uint8_t white[16] = {255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255};
+    for (int i = 0; i < r.OH; ++i) yb[i] = (uint32_t)(uint16_t)r.taps.ya0[i] | ((uint32_t)(uint16_t)r.taps.ya1[i] << 16);
+    XwComposeCtx x;
+    x.hot = r.T + (size_t)r.brick_icon * r.FB; x.white = white; x.yb = yb.data();
     for (int e = 0; e < d.n; ++e) {
         for (int c = 0; c < d.H * d.W; ++c) cell[c] = xw_cell_desc(d, e, d.grid[(size_t)e * d.CS + c]);
-        std::fill(fb.begin(), fb.end(), 0x5a5a5a5au);
-        for (int tid = 0; tid < s->tab.threads; ++tid)
-            xw_compose_thread(r, tid, cell.data(), r.rowcell, r.bandend, r.colpair, hot, fb.data());
-        for (int i = 0; i < xw_fix_count(r); ++i) xw_fix_item(r, i, cell.data(), r.sc, r.sr, (uint8_t*)fb.data());
-        memcpy(frames + (size_t)e * r.FB, fb.data(), r.FB);
+        if (s->tab.fast_ok) {
+            std::fill(fb.begin(), fb.end(), 0x5a5a5a5au);
+            for (int i = 0; i < 3 * r.n_items; ++i) {
+                int c;
+                const XwItem it = r.items[xw_plan_lookup(r, i, &c)];
+                xw_compose_item(r, x, it, c, cell.data(), fb.data());
+            }
+            memcpy(frames + (size_t)e * r.FB, fb.data(), r.FB);
+        } else {
+            for (int i = 0; i < r.FB; ++i) {
+                const int c = i / (r.OH * r.OW), p = i % (r.OH * r.OW);
+                frames[(size_t)e * r.FB + i] = xw_exact_px(r, cell.data(), c, p / r.OW, p % r.OW);
+            }
+        }
     }
 }
 

@@ -212,21 +212,26 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
     XwRenderTables& t = s->tab;
     XwRender& r = s->r;
     memset(&r, 0, sizeof r);
-    r.OH = OH; r.OW = OW; r.WR = t.WR; r.FB = t.FB; r.H = c.height; r.W = c.width; r.R = t.R; r.rpg = t.rpg;
-    r.n_sc = (int)t.sc.size(); r.n_sr = (int)t.sr.size();
+    r.OH = OH; r.OW = OW; r.WR = t.WR; r.FB = t.FB; r.H = c.height; r.W = c.width;
+    r.n_items = (int)t.items.size();
+    for (int i = 0; i <= XW_ITEM_TYPES; ++i) r.seg[i] = t.seg[i];
+    r.n_sr = (int)t.sr.size();
     r.n_icons = cat->n_icons; r.brick_icon = cat->brick_icon; r.agent_icon = cat->agent_icon;
-    static const int16_t zero16 = 0;
-    rc |= dupload(s, &r.xofs, t.xofs.data(), t.xofs.size());
-    rc |= dupload(s, &r.xa0, t.xa0.data(), t.xa0.size());
-    rc |= dupload(s, &r.xa1, t.xa1.data(), t.xa1.size());
-    rc |= dupload(s, &r.yofs, t.yofs.data(), t.yofs.size());
-    rc |= dupload(s, &r.ya0, t.ya0.data(), t.ya0.size());
-    rc |= dupload(s, &r.ya1, t.ya1.data(), t.ya1.size());
-    rc |= dupload(s, &r.rowcell, t.rowcell.data(), t.rowcell.size());
-    rc |= dupload(s, &r.bandend, t.bandend.data(), t.bandend.size());
-    if (t.fast_ok) rc |= dupload(s, &r.colpair, t.colpair.data(), t.colpair.size());
-    rc |= dupload(s, &r.sc, t.sc.empty() ? &zero16 : t.sc.data(), t.sc.empty() ? 1 : t.sc.size());
-    rc |= dupload(s, &r.sr, t.sr.empty() ? &zero16 : t.sr.data(), t.sr.empty() ? 1 : t.sr.size());
+    rc |= dupload(s, &r.taps.xofs, t.xofs.data(), t.xofs.size());
+    rc |= dupload(s, &r.taps.xa0, t.xa0.data(), t.xa0.size());
+    rc |= dupload(s, &r.taps.xa1, t.xa1.data(), t.xa1.size());
+    rc |= dupload(s, &r.taps.yofs, t.yofs.data(), t.yofs.size());
+    rc |= dupload(s, &r.taps.ya0, t.ya0.data(), t.ya0.size());
+    rc |= dupload(s, &r.taps.ya1, t.ya1.data(), t.ya1.size());
+    if (t.fast_ok) {
+        static const int16_t zero16 = 0;
+        uint16_t *ecol = nullptr, *uv = nullptr;
+        rc |= dupload(s, &r.items, t.items.data(), t.items.size());
+        rc |= dupload(s, &r.sr, t.sr.empty() ? &zero16 : t.sr.data(), t.sr.empty() ? 1 : t.sr.size());
+        rc |= dalloc(s, &ecol, (size_t)(cat->n_icons + 1) * 2 * 3 * OH, false);
+        rc |= dalloc(s, &uv, (size_t)(cat->n_icons + 1) * r.n_sr * 2 * 3 * OW + 8, false);
+        r.ecol = ecol; r.uv = uv;
+    }
     rc |= dupload(s, &r.atlas64, cat->atlas64, (size_t)cat->n_icons * 64 * 64 * 3);
     uint8_t* T = nullptr;
     rc |= dalloc(s, &T, (size_t)cat->n_icons * r.FB, false);
@@ -234,19 +239,28 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
     r.T = T;
     k_build_phase_atlas<<<s->n_sms * 8, 256, 0, s->own_stream>>>(r);
     s->launches++;
+    if (t.fast_ok) {
+        k_build_edge_tables<<<s->n_sms * 2, 256, 0, s->own_stream>>>(r);
+        s->launches++;
+    }
     CUDA_TRY(cudaGetLastError());
     if (t.fast_ok) {
-        XwRenderSmem L = xw_render_smem(r);
+        // warp groups per CTA: as many private frame buffers as shared memory holds, each group wide
+        // enough to prefetch a whole map (H*W <= 2*GT)
         int max_optin = 0;
         CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
-        if (L.total > max_optin) t.fast_ok = false;
+        int G = XW_RENDER_MAX_GROUPS;
+        while (G >= 1) {
+            int GT = (XW_RENDER_THREADS / G) / 32 * 32;
+            if (xw_render_smem(r, G).total <= max_optin && 2 * GT >= c.height * c.width) break;
+            --G;
+        }
+        if (G < 1) t.fast_ok = false;
         else {
-            s->render_smem = L.total;
-            CUDA_TRY(cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-            int per_sm = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_render, t.threads, L.total));
-            if (per_sm < 1) t.fast_ok = false;
-            s->render_grid = s->n_sms * (per_sm < 1 ? 1 : per_sm);
+            r.G = G; r.GT = (XW_RENDER_THREADS / G) / 32 * 32;
+            s->render_smem = xw_render_smem(r, G).total;
+            CUDA_TRY(cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, s->render_smem));
+            s->render_grid = s->n_sms;
         }
     }
     CUDA_TRY(cudaStreamSynchronize(s->own_stream));
@@ -388,8 +402,9 @@ static int launch_render(xw_sim* s, uint8_t* d_frames, cudaStream_t st) {
         CUDA_TRY(cudaEventRecord(e0, st));
     }
     if (s->tab.fast_ok) {
-        int grid = s->render_grid < s->n ? s->render_grid : s->n;
-        k_render<<<grid, s->tab.threads, s->render_smem, st>>>(s->d, r, dst, env_stride);
+        const int need = (s->n + r.G - 1) / r.G;  // CTAs that get at least one env
+        const int grid = s->render_grid < need ? s->render_grid : need;
+        k_render<<<grid, XW_RENDER_THREADS, s->render_smem, st>>>(s->d, r, dst, env_stride);
     } else {
         k_render_generic<<<s->n_sms * 8, 256, 0, st>>>(s->d, r, dst, env_stride);
     }

@@ -11,70 +11,101 @@
 // pixel whose 2x2 taps fall inside one cell is a pure function of (icon in that cell, pixel):
 //     T[icon][c][dy][dx] = resize(canvas tiled with `icon`)[c][dy][dx]         ("phase atlas")
 // is built once per handle with the exact fixed-point arithmetic, and a frame is then a per-cell
-// SELECT from those tables: out = T[icon(owner(dy,dx))].  The few output columns/rows whose taps
-// straddle a cell border (2 of 84 at 11x11->84, none at 7x7->84) are re-evaluated exactly from
-// the 64-px atlas in a fix-up pass.  Frames are composed in shared memory and leave the SM as one
-// TMA bulk store (cp.async.bulk.global.shared::cta) per env; the brick table (the icon most cells
-// hold) is staged into shared memory once per CTA by a TMA bulk load.
+// SELECT from those tables, done one 4-pixel word at a time: word(A) and word(B) of the two cells a
+// word can touch are merged with one PRMT.  The few output columns / rows whose taps straddle a
+// cell border (2 of 84 each at 11x11->84, none at 7x7->84) are evaluated exactly from two small
+// per-icon edge tables: raw edge taps for straddling columns, and for straddling rows the two
+// vertical partial terms U, V of cv::resize's  (U + V + 2) >> 2  -- the rule is separable there.
+//
+// Kernel shape (k_render): one persistent CTA per SM split into G warp groups; each group composes
+// one env's frame at a time in its own shared-memory frame buffer, following a precomputed plan of
+// typed work items (xw_render_host.hpp) so that warps do not diverge, and hands the frame to the
+// TMA engine (cp.async.bulk.global.shared::cta, one bulk store per frame, full-line HBM writes)
+// while the other groups keep composing.  The brick table -- the icon most non-empty cells hold --
+// is staged into shared memory once per CTA by a TMA bulk load; other tables stay L2-resident.
 #pragma once
 #include "xw_common.cuh"
+#include "xw_render_host.hpp"
 
-#define XW_MAX_OUT 256  // max frame side
+#define XW_MAX_OUT 252        // max frame side
+#define XW_RENDER_THREADS 1024
+#define XW_RENDER_MAX_GROUPS 8
+
+struct alignas(8) XwU2 { uint32_t x, y; };
+struct XwTaps { const int16_t *xofs, *xa0, *xa1, *yofs, *ya0, *ya1; };  // cv::resize tables
 
 struct XwRender {
     int32_t OH, OW, WR, FB;   // frame rows, cols, words per row, bytes per frame (3*OH*OW)
     int32_t H, W;
-    int32_t R, rpg;           // row groups per plane, rows per group
-    int32_t n_sc, n_sr;       // straddling columns / rows
+    int32_t n_items;          // items in the per-plane plan
+    int32_t seg[XW_ITEM_TYPES + 1];
+    int32_t G, GT;            // warp groups per CTA, threads per group
     int32_t n_icons, brick_icon, agent_icon;
-    // LUTs (device): all int16 / uint8 so the whole set is < 4 KB
-    const int16_t *xofs, *xa0, *xa1, *yofs, *ya0, *ya1;  // cv::resize tables
-    const uint8_t *rowcell, *bandend;                    // [OH] owner cell row; [H] first row of next band
-    const uint32_t* colpair;                             // [WR] txA | txB<<8 | prmt_sel<<16
-    const int16_t *sc, *sr;                              // straddle column / row indices
-    const uint8_t* T;                                    // [n_icons][3][OH][OW]
-    const uint8_t* atlas64;                              // [n_icons][64][64][3] BGR
+    int32_t n_sr;             // straddling rows
+    XwTaps taps;
+    const int16_t* sr;        // [n_sr] the straddling rows
+    const XwItem* items;      // [n_items]
+    const uint8_t* T;         // [n_icons][3][OH][OW] phase atlas
+    // edge tables, indexed by cell descriptor (0 = white, icon + 1 otherwise)
+    const uint16_t* ecol;     // [n_icons+1][2][3][OH]  role 0: taps of icon column 63, role 1: column 0;
+                              //   low byte = tap row of yofs[dy], high byte = the row below it
+    const uint16_t* uv;       // [n_icons+1][n_sr][2][3][OW]  role 0: U from icon row 63, role 1: V from row 0
+    const uint8_t* atlas64;   // [n_icons][64][64][3] BGR
 };
 
 // ---- exact cv::resize arithmetic --------------------------------------------------------
 // One output pixel of the bilinear resize given its four taps (HResizeLinear + VResizeLinear,
 // INTER_RESIZE_COEF_BITS = 11, FixedPtCast shift 22 split as >>4, >>16, +2, >>2).
+XW_HD int xw_vterm(int p0, int p1, int a0, int a1, int b) { return (b * ((p0 * a0 + p1 * a1) >> 4)) >> 16; }
 XW_HD uint8_t xw_resize_px(int p00, int p01, int p10, int p11, int a0, int a1, int b0, int b1) {
-    int S0 = p00 * a0 + p01 * a1;
-    int S1 = p10 * a0 + p11 * a1;
-    return (uint8_t)((((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2);
-}
-
-// Phase-atlas entry: canvas tiled with `icon` everywhere.
-XW_HD uint8_t xw_phase_px(const XwRender& r, int icon, int c, int dy, int dx) {
-    const uint8_t* I = r.atlas64 + (size_t)icon * (64 * 64 * 3);
-    int sx0 = r.xofs[dx], sy0 = r.yofs[dy];
-    int a0 = r.xa0[dx], a1 = r.xa1[dx], b0 = r.ya0[dy], b1 = r.ya1[dy];
-    int sx1 = a1 ? sx0 + 1 : sx0, sy1 = b1 ? sy0 + 1 : sy0;
-    int p00 = I[((sy0 & 63) * 64 + (sx0 & 63)) * 3 + c], p01 = I[((sy0 & 63) * 64 + (sx1 & 63)) * 3 + c];
-    int p10 = I[((sy1 & 63) * 64 + (sx0 & 63)) * 3 + c], p11 = I[((sy1 & 63) * 64 + (sx1 & 63)) * 3 + c];
-    return xw_resize_px(p00, p01, p10, p11, a0, a1, b0, b1);
+    return (uint8_t)((xw_vterm(p00, p01, a0, a1, b0) + xw_vterm(p10, p11, a0, a1, b1) + 2) >> 2);
 }
 
 // One tap of the virtual canvas: cell descriptor (icon+1, 0 = empty = white) -> pixel.
-XW_HD int xw_canvas_tap(const XwRender& r, const uint32_t* celldesc, int sy, int sx, int c) {
-    uint32_t dsc = celldesc[(sy >> 6) * r.W + (sx >> 6)];
+XW_HD int xw_canvas_tap(const XwRender& r, uint32_t dsc, int sy, int sx, int c) {
     if (dsc == 0) return 255;
     return r.atlas64[(size_t)(dsc - 1) * (64 * 64 * 3) + ((sy & 63) * 64 + (sx & 63)) * 3 + c];
 }
 
-// Exact value of output pixel (c,dy,dx) on the real canvas; `same` reports whether all four taps
-// lie in cells holding the same descriptor (then the phase atlas already has the right value).
-XW_HD uint8_t xw_exact_px(const XwRender& r, const uint32_t* celldesc, int c, int dy, int dx, bool* same) {
-    int sx0 = r.xofs[dx], sy0 = r.yofs[dy];
-    int a0 = r.xa0[dx], a1 = r.xa1[dx], b0 = r.ya0[dy], b1 = r.ya1[dy];
+// Phase-atlas entry: canvas tiled with `icon` everywhere.
+XW_HD uint8_t xw_phase_px(const XwRender& r, int icon, int c, int dy, int dx) {
+    const XwTaps& t = r.taps;
+    const uint32_t dsc = (uint32_t)icon + 1;
+    int sx0 = t.xofs[dx], sy0 = t.yofs[dy];
+    int a1 = t.xa1[dx], b1 = t.ya1[dy];
+    int sx1 = a1 ? sx0 + 1 : sx0, sy1 = b1 ? sy0 + 1 : sy0;
+    return xw_resize_px(xw_canvas_tap(r, dsc, sy0, sx0, c), xw_canvas_tap(r, dsc, sy0, sx1, c),
+                        xw_canvas_tap(r, dsc, sy1, sx0, c), xw_canvas_tap(r, dsc, sy1, sx1, c),
+                        t.xa0[dx], a1, t.ya0[dy], b1);
+}
+
+// Edge-table entries (built once per handle for every descriptor).
+XW_HD uint16_t xw_ecol_entry(const XwRender& r, uint32_t dsc, int role, int c, int dy) {
+    const XwTaps& t = r.taps;
+    int sy0 = t.yofs[dy], sy1 = t.ya1[dy] ? sy0 + 1 : sy0;
+    int sx = role == 0 ? 63 : 0;
+    return (uint16_t)(xw_canvas_tap(r, dsc, sy0, sx, c) | (xw_canvas_tap(r, dsc, sy1, sx, c) << 8));
+}
+XW_HD uint16_t xw_uv_entry(const XwRender& r, uint32_t dsc, int q, int role, int c, int dx) {
+    const XwTaps& t = r.taps;
+    const int dy = r.sr[q];
+    int sx0 = t.xofs[dx], sx1 = t.xa1[dx] ? sx0 + 1 : sx0;
+    int sy = role == 0 ? 63 : 0;
+    return (uint16_t)xw_vterm(xw_canvas_tap(r, dsc, sy, sx0, c), xw_canvas_tap(r, dsc, sy, sx1, c), t.xa0[dx], t.xa1[dx],
+                              role == 0 ? t.ya0[dy] : t.ya1[dy]);
+}
+
+// Value of output pixel (c,dy,dx) on the real canvas, from the 64-px atlas (any four cells).
+XW_HD uint8_t xw_exact_px(const XwRender& r, const uint32_t* celldesc, int c, int dy, int dx) {
+    const XwTaps& t = r.taps;
+    int sx0 = t.xofs[dx], sy0 = t.yofs[dy];
+    int a1 = t.xa1[dx], b1 = t.ya1[dy];
     int sx1 = a1 ? sx0 + 1 : sx0, sy1 = b1 ? sy0 + 1 : sy0;
     uint32_t d00 = celldesc[(sy0 >> 6) * r.W + (sx0 >> 6)], d01 = celldesc[(sy0 >> 6) * r.W + (sx1 >> 6)];
     uint32_t d10 = celldesc[(sy1 >> 6) * r.W + (sx0 >> 6)], d11 = celldesc[(sy1 >> 6) * r.W + (sx1 >> 6)];
-    if (d00 == d01 && d00 == d10 && d00 == d11) { *same = true; return 0; }
-    *same = false;
-    return xw_resize_px(xw_canvas_tap(r, celldesc, sy0, sx0, c), xw_canvas_tap(r, celldesc, sy0, sx1, c),
-                        xw_canvas_tap(r, celldesc, sy1, sx0, c), xw_canvas_tap(r, celldesc, sy1, sx1, c), a0, a1, b0, b1);
+    return xw_resize_px(xw_canvas_tap(r, d00, sy0, sx0, c), xw_canvas_tap(r, d01, sy0, sx1, c),
+                        xw_canvas_tap(r, d10, sy1, sx0, c), xw_canvas_tap(r, d11, sy1, sx1, c),
+                        t.xa0[dx], a1, t.ya0[dy], b1);
 }
 
 XW_HD uint32_t xw_prmt(uint32_t a, uint32_t b, uint32_t sel) {
@@ -88,51 +119,78 @@ XW_HD uint32_t xw_prmt(uint32_t a, uint32_t b, uint32_t sel) {
 #endif
 }
 
-// ---- compose: one thread owns output word column k of plane c for a group of rows ---------
-// celldesc: [H*W] u32 (icon+1 / 0); hot: the brick table in shared memory; fb: the frame being built.
-XW_HD void xw_compose_thread(const XwRender& r, int tid, const uint32_t* celldesc, const uint8_t* rowcell,
-                             const uint8_t* bandend, const uint32_t* colpair, const uint8_t* hot, uint32_t* fb) {
-    const int items = 3 * r.R * r.WR;
-    if (tid >= items) return;
-    const int k = tid % r.WR, t2 = tid / r.WR, rg = t2 % r.R, c = t2 / r.R;
-    const uint32_t pair = colpair[k];
-    const int txA = pair & 0xff, txB = (pair >> 8) & 0xff;
-    const uint32_t sel = pair >> 16;
-    const int r0 = rg * r.rpg, r1 = (r0 + r.rpg < r.OH) ? r0 + r.rpg : r.OH;
-    int dy = r0;
-    while (dy < r1) {
-        const int ty = rowcell[dy];
-        int e = bandend[ty];
-        if (e > r1) e = r1;
-        const uint32_t dA = celldesc[ty * r.W + txA], dB = celldesc[ty * r.W + txB];
-        const uint8_t* pA = dA == 0 ? nullptr : ((int)dA - 1 == r.brick_icon ? hot : r.T + (size_t)(dA - 1) * r.FB);
-        const uint8_t* pB = dB == 0 ? nullptr : ((int)dB - 1 == r.brick_icon ? hot : r.T + (size_t)(dB - 1) * r.FB);
-        int widx = (c * r.OH + dy) * r.WR + k;
-        if (pA == nullptr && pB == nullptr) {
-            for (; dy < e; ++dy, widx += r.WR) fb[widx] = 0xffffffffu;
-        } else if (dA == dB) {
-            for (; dy < e; ++dy, widx += r.WR) fb[widx] = *(const uint32_t*)(pA + (size_t)widx * 4);
-        } else {
-            for (; dy < e; ++dy, widx += r.WR) {
-                uint32_t wa = pA ? *(const uint32_t*)(pA + (size_t)widx * 4) : 0xffffffffu;
-                uint32_t wb = pB ? *(const uint32_t*)(pB + (size_t)widx * 4) : 0xffffffffu;
-                fb[widx] = xw_prmt(wa, wb, sel);
-            }
+// What the compositor reads besides the per-env cells: shared-memory copies on the device.
+struct XwComposeCtx {
+    const uint8_t* hot;     // brick phase table [FB]
+    const uint8_t* white;   // 16 bytes of 0xff
+    const uint32_t* yb;     // [OH] ya0 | ya1 << 16
+};
+
+// Source of a cell's words: word w of the frame comes from *(base + w*mul).  White cells read one
+// constant word (mul = 0) so that every lane runs the same instructions.
+struct XwSrc { const uint8_t* base; uint32_t mul; };
+XW_HD XwSrc xw_src_of(const XwRender& r, const XwComposeCtx& x, uint32_t dsc) {
+    XwSrc s;
+    if (dsc == 0) { s.base = x.white; s.mul = 0; }
+    else if ((int)dsc - 1 == r.brick_icon) { s.base = x.hot; s.mul = 4; }
+    else { s.base = r.T + (size_t)(dsc - 1) * r.FB; s.mul = 4; }
+    return s;
+}
+XW_HD uint32_t xw_src_word(const XwSrc& s, int w) { return *(const uint32_t*)(s.base + (size_t)((uint32_t)w * s.mul)); }
+
+// ---- compose one item of plane c into the frame being built (fb, words) ----------------------
+XW_HD void xw_compose_item(const XwRender& r, const XwComposeCtx& x, const XwItem& it, int c, const uint32_t* celldesc,
+                           uint32_t* fb) {
+    const int WR = r.WR;
+    int w = c * r.OH * WR + it.woff;
+    if (it.type == XW_ITEM_M1) {
+        const XwSrc sA = xw_src_of(r, x, celldesc[it.cellA]);
+        for (int i = 0; i < it.nrows; ++i, w += WR) fb[w] = xw_src_word(sA, w);
+    } else if (it.type == XW_ITEM_M2) {
+        const XwSrc sA = xw_src_of(r, x, celldesc[it.cellA]), sB = xw_src_of(r, x, celldesc[it.cellB]);
+        const uint32_t sel = it.sel;
+        for (int i = 0; i < it.nrows; ++i, w += WR) fb[w] = xw_prmt(xw_src_word(sA, w), xw_src_word(sB, w), sel);
+    } else if (it.type == XW_ITEM_M3) {
+        const XwSrc sA = xw_src_of(r, x, celldesc[it.cellA]), sB = xw_src_of(r, x, celldesc[it.cellB]);
+        const uint32_t sel = it.sel;
+        const uint16_t* eL = r.ecol + ((size_t)(celldesc[it.scell] * 2 + 0) * 3 + c) * r.OH;
+        const uint16_t* eR = r.ecol + ((size_t)(celldesc[it.scell + 1] * 2 + 1) * 3 + c) * r.OH;
+        const int dx = 4 * it.k + it.sbyte, a0 = r.taps.xa0[dx], a1 = r.taps.xa1[dx];
+        const int sh = 8 * it.sbyte;
+        const uint32_t keep = ~(0xffu << sh);
+        for (int i = 0, dy = it.y0; i < it.nrows; ++i, ++dy, w += WR) {
+            const uint32_t word = xw_prmt(xw_src_word(sA, w), xw_src_word(sB, w), sel);
+            const uint32_t tl = eL[dy], tr = eR[dy], b = x.yb[dy];
+            const uint32_t v = xw_resize_px(tl & 255, tr & 255, tl >> 8, tr >> 8, a0, a1, b & 0xffff, b >> 16);
+            fb[w] = (word & keep) | (v << sh);
         }
+    } else {  // R / RC: one word of straddling row q: out = (U[top cell] + V[bottom cell] + 2) >> 2
+        const size_t per_desc = (size_t)r.n_sr * 2 * 3 * r.OW, urow = ((size_t)it.q * 2 * 3 + c) * r.OW + 4 * it.k,
+                     vrow = urow + (size_t)3 * r.OW;
+        const XwU2 uA = *(const XwU2*)(r.uv + celldesc[it.cellA] * per_desc + urow);
+        const XwU2 uB = *(const XwU2*)(r.uv + celldesc[it.cellB] * per_desc + urow);
+        const XwU2 vA = *(const XwU2*)(r.uv + celldesc[it.cellA + r.W] * per_desc + vrow);
+        const XwU2 vB = *(const XwU2*)(r.uv + celldesc[it.cellB + r.W] * per_desc + vrow);
+        // packed u16 pairs: no carry between halves (U + V + 2 <= 2042)
+        const uint32_t a_lo = ((uA.x + vA.x + 0x00020002u) >> 2) & 0x00ff00ffu, a_hi = ((uA.y + vA.y + 0x00020002u) >> 2) & 0x00ff00ffu;
+        const uint32_t b_lo = ((uB.x + vB.x + 0x00020002u) >> 2) & 0x00ff00ffu, b_hi = ((uB.y + vB.y + 0x00020002u) >> 2) & 0x00ff00ffu;
+        uint32_t word = xw_prmt(xw_prmt(a_lo, a_hi, 0x6420), xw_prmt(b_lo, b_hi, 0x6420), it.sel);
+        if (it.type == XW_ITEM_RC) {
+            const int sh = 8 * it.sbyte;
+            word = (word & ~(0xffu << sh)) | ((uint32_t)xw_exact_px(r, celldesc, c, it.y0, 4 * it.k + it.sbyte) << sh);
+        }
+        fb[w] = word;
     }
 }
 
-// ---- straddle fix-up: item i of the list -> one exact pixel ---------------------------------
-XW_HD int xw_fix_count(const XwRender& r) { return 3 * (r.n_sc * r.OH + r.n_sr * r.OW); }
-XW_HD void xw_fix_item(const XwRender& r, int i, const uint32_t* celldesc, const int16_t* sc, const int16_t* sr, uint8_t* fb) {
-    const int per_plane = r.n_sc * r.OH + r.n_sr * r.OW;
-    const int c = i / per_plane;
-    int j = i - c * per_plane, dy, dx;
-    if (j < r.n_sc * r.OH) { dx = sc[j / r.OH]; dy = j % r.OH; }
-    else { j -= r.n_sc * r.OH; dy = sr[j / r.OW]; dx = j % r.OW; }
-    bool same;
-    uint8_t v = xw_exact_px(r, celldesc, c, dy, dx, &same);
-    if (!same) fb[(c * r.OH + dy) * r.OW + dx] = v;
+// plan index i in [0, 3*n_items) -> (item, plane): inside each type segment the three planes follow
+// one another, so a warp stays on one type.
+XW_HD int xw_plan_lookup(const XwRender& r, int i, int* c) {
+    int t = 0;
+    while (i >= 3 * r.seg[t + 1]) ++t;
+    const int n = r.seg[t + 1] - r.seg[t], rel = i - 3 * r.seg[t];
+    *c = (rel >= n) + (rel >= 2 * n);
+    return r.seg[t] + rel - *c * n;
 }
 
 // celldesc for one cell: grid code -> icon + 1
@@ -143,6 +201,25 @@ XW_HD uint32_t xw_cell_desc(const XwDev& d, int e, int code) {
     return (uint32_t)d.goal_icon[(size_t)(code - XW_CELL_GOAL0) * d.n + e] + 1;
 }
 
+// Dynamic shared memory layout (bytes), all sections 16-byte aligned:
+//   brick phase table (TMA bulk load, once) | G frame buffers | the plan | yb | white | G cell arrays | mbarrier
+#define XW_CELL_STRIDE (XW_MAX_DIM * XW_MAX_DIM + XW_MAX_DIM + 2)  // + the (never drawn) row below the map
+struct XwRenderSmem { int hot, fb, items, yb, white, cell, bar, total; };
+XW_HD int xw_align16(int v) { return (v + 15) & ~15; }
+XW_HD XwRenderSmem xw_render_smem(const XwRender& r, int G) {
+    XwRenderSmem s;
+    int o = 0;
+    s.hot = o; o += xw_align16(r.FB);
+    s.fb = o; o += G * xw_align16(r.FB);
+    s.items = o; o += r.n_items * (int)sizeof(XwItem);
+    s.yb = o; o += xw_align16(r.OH * 4);
+    s.white = o; o += 16;
+    s.cell = o; o += G * XW_CELL_STRIDE * 4;
+    s.bar = o; o += 16;
+    s.total = o;
+    return s;
+}
+
 #if defined(__CUDACC__)
 // ------------------------------------------------------------------------------------ kernels
 __global__ void k_build_phase_atlas(XwRender r) {
@@ -151,6 +228,23 @@ __global__ void k_build_phase_atlas(XwRender r) {
         int icon = (int)(i / r.FB), rem = (int)(i % r.FB);
         int c = rem / (r.OH * r.OW), p = rem % (r.OH * r.OW);
         ((uint8_t*)r.T)[i] = xw_phase_px(r, icon, c, p / r.OW, p % r.OW);
+    }
+}
+__global__ void k_build_edge_tables(XwRender r) {
+    const size_t n_ecol = (size_t)(r.n_icons + 1) * 2 * 3 * r.OH, n_uv = (size_t)(r.n_icons + 1) * r.n_sr * 2 * 3 * r.OW;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_ecol + n_uv; i += (size_t)gridDim.x * blockDim.x) {
+        if (i < n_ecol) {
+            size_t j = i;
+            const int dy = (int)(j % r.OH); j /= r.OH;
+            const int c = (int)(j % 3); j /= 3;
+            ((uint16_t*)r.ecol)[i] = xw_ecol_entry(r, (uint32_t)(j / 2), (int)(j % 2), c, dy);
+        } else {
+            size_t j = i - n_ecol;
+            const int dx = (int)(j % r.OW); j /= r.OW;
+            const int c = (int)(j % 3); j /= 3;
+            const int role = (int)(j % 2); j /= 2;
+            ((uint16_t*)r.uv)[i - n_ecol] = xw_uv_entry(r, (uint32_t)(j / r.n_sr), (int)(j % r.n_sr), role, c, dx);
+        }
     }
 }
 
@@ -187,42 +281,20 @@ template <int N> __device__ __forceinline__ void tma_wait_all() {
     asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// Dynamic shared memory layout (bytes), all sections 16-byte aligned:
-//   [0, FB)            brick phase table (TMA bulk load, once)
-//   [FB, 2FB) [2FB,3FB) two frame buffers (compose target / TMA bulk-store source)
-//   then LUTs, celldesc[256] u32, one mbarrier
-struct XwRenderSmem { int hot, fb0, fb1, rowcell, bandend, colpair, sc, sr, celldesc, bar, total; };
-XW_HD int xw_align16(int v) { return (v + 15) & ~15; }
-XW_HD XwRenderSmem xw_render_smem(const XwRender& r) {
-    XwRenderSmem s;
-    int o = 0;
-    s.hot = o; o += xw_align16(r.FB);
-    s.fb0 = o; o += xw_align16(r.FB);
-    s.fb1 = o; o += xw_align16(r.FB);
-    s.rowcell = o; o += xw_align16(r.OH);
-    s.bandend = o; o += xw_align16(r.H);
-    s.colpair = o; o += xw_align16(r.WR * 4);
-    s.sc = o; o += xw_align16(r.n_sc * 2 + 2);
-    s.sr = o; o += xw_align16(r.n_sr * 2 + 2);
-    s.celldesc = o; o += XW_MAX_DIM * XW_MAX_DIM * 4;
-    s.bar = o; o += 16;
-    s.total = o;
-    return s;
+__device__ __forceinline__ void group_bar(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// Persistent CTAs; CTA b renders envs b, b+gridDim.x, ...  dst frame of env e = frames + e*env_stride.
-__global__ void __launch_bounds__(1024, 1)
+// Persistent CTAs.  Group g of CTA b renders envs (b*G + g) + i * gridDim.x*G; the frame of env e goes
+// to frames + e*env_stride.
+__global__ void __launch_bounds__(XW_RENDER_THREADS, 1)
 k_render(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const XwRenderSmem L = xw_render_smem(r);
+    const int G = r.G, GT = r.GT;
+    const XwRenderSmem L = xw_render_smem(r, G);
     uint8_t* hot = smem + L.hot;
-    uint8_t* s_rowcell = smem + L.rowcell;
-    uint8_t* s_bandend = smem + L.bandend;
-    uint32_t* s_colpair = (uint32_t*)(smem + L.colpair);
-    int16_t* s_sc = (int16_t*)(smem + L.sc);
-    int16_t* s_sr = (int16_t*)(smem + L.sr);
-    uint32_t* s_cell = (uint32_t*)(smem + L.celldesc);
+    XwItem* s_items = (XwItem*)(smem + L.items);
+    uint32_t* s_yb = (uint32_t*)(smem + L.yb);
     uint64_t* bar = (uint64_t*)(smem + L.bar);
     const int tid = threadIdx.x, nt = blockDim.x;
     const int HW = r.H * r.W;
@@ -236,51 +308,70 @@ k_render(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
         mbar_expect_tx(bar, (uint32_t)r.FB);
         tma_load_1d(hot, r.T + (size_t)r.brick_icon * r.FB, (uint32_t)r.FB, bar);
     }
-    for (int i = tid; i < r.OH; i += nt) s_rowcell[i] = r.rowcell[i];
-    for (int i = tid; i < r.H; i += nt) s_bandend[i] = r.bandend[i];
-    for (int i = tid; i < r.WR; i += nt) s_colpair[i] = r.colpair[i];
-    for (int i = tid; i < r.n_sc; i += nt) s_sc[i] = r.sc[i];
-    for (int i = tid; i < r.n_sr; i += nt) s_sr[i] = r.sr[i];
-
-    // register prefetch of the first env's cell descriptors
-    int env = blockIdx.x;
-    uint32_t next_desc = 0;
-    if (env < d.n && tid < HW) next_desc = xw_cell_desc(d, env, d.grid[(size_t)env * d.CS + tid]);
+    {  // plan + row weights -> shared memory
+        const uint4* src = (const uint4*)r.items;
+        uint4* dst = (uint4*)s_items;
+        for (int i = tid; i < r.n_items; i += nt) dst[i] = src[i];
+        for (int i = tid; i < r.OH; i += nt) s_yb[i] = (uint32_t)(uint16_t)r.taps.ya0[i] | ((uint32_t)(uint16_t)r.taps.ya1[i] << 16);
+        if (tid < 4) ((uint32_t*)(smem + L.white))[tid] = 0xffffffffu;
+    }
     mbar_wait(bar, 0);
+    __syncthreads();
 
-    const int nfix = xw_fix_count(r);
-    for (int it = 0; env < d.n; env += gridDim.x, ++it) {
-        uint8_t* fb = smem + ((it & 1) ? L.fb1 : L.fb0);
-        if (tid < HW) s_cell[tid] = next_desc;
-        if (tid == 0) tma_wait_read<1>();  // the store issued two envs ago has drained this buffer
-        __syncthreads();
+    const int g = tid / GT, gt = tid - g * GT;
+    if (g >= G) return;  // spare warps (G*GT < blockDim.x)
+    uint32_t* s_cell = (uint32_t*)(smem + L.cell) + g * XW_CELL_STRIDE;
+    uint32_t* fb = (uint32_t*)(smem + L.fb + (size_t)g * xw_align16(r.FB));
+    XwComposeCtx x;
+    x.hot = hot; x.white = smem + L.white; x.yb = s_yb;
+    const int bar_id = 1 + g;
+    const int n_plan = 3 * r.n_items;
+    const int gstride = gridDim.x * G;
+    int env = blockIdx.x * G + g;
+
+    // register prefetch of the env's cell descriptors (HW <= 2*GT)
+    uint32_t nd0 = 0, nd1 = 0;
+    if (env < d.n) {
+        if (gt < HW) nd0 = xw_cell_desc(d, env, d.grid[(size_t)env * d.CS + gt]);
+        if (gt + GT < HW) nd1 = xw_cell_desc(d, env, d.grid[(size_t)env * d.CS + gt + GT]);
+    }
+    for (int i = HW + gt; i < XW_CELL_STRIDE; i += GT) s_cell[i] = 0;
+    for (; env < d.n; env += gstride) {
+        if (gt < HW) s_cell[gt] = nd0;
+        if (gt + GT < HW) s_cell[gt + GT] = nd1;
+        if (gt == 0) tma_wait_read<0>();  // the TMA store of this group's previous frame has drained fb
+        group_bar(bar_id, GT);
         {  // prefetch the next env's cells while this one is composed
-            const int en = env + gridDim.x;
-            if (en < d.n && tid < HW) next_desc = xw_cell_desc(d, en, d.grid[(size_t)en * d.CS + tid]);
+            const int en = env + gstride;
+            if (en < d.n) {
+                if (gt < HW) nd0 = xw_cell_desc(d, en, d.grid[(size_t)en * d.CS + gt]);
+                if (gt + GT < HW) nd1 = xw_cell_desc(d, en, d.grid[(size_t)en * d.CS + gt + GT]);
+            }
         }
-        xw_compose_thread(r, tid, s_cell, s_rowcell, s_bandend, s_colpair, hot, (uint32_t*)fb);
-        if (nfix > 0) {
-            __syncthreads();
-            for (int i = tid; i < nfix; i += nt) xw_fix_item(r, i, s_cell, s_sc, s_sr, fb);
+        for (int i = gt; i < n_plan; i += GT) {
+            int c;
+            const XwItem it = s_items[xw_plan_lookup(r, i, &c)];
+            xw_compose_item(r, x, it, c, s_cell, fb);
         }
         fence_async_smem();  // generic-proxy writes -> visible to the async (TMA) proxy
-        __syncthreads();
-        if (tid == 0) {
+        group_bar(bar_id, GT);
+        if (gt == 0) {
             tma_store_1d(frames + (size_t)env * env_stride, fb, (uint32_t)r.FB);
             tma_commit();
         }
     }
-    if (tid == 0) tma_wait_all<0>();
+    if (gt == 0) tma_wait_all<0>();
 }
 
 // General fallback (any frame size): one thread per output byte, straight to global memory.
 __global__ void k_render_generic(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
     const size_t total = (size_t)d.n * r.FB;
+    const XwTaps& t = r.taps;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int e = (int)(i / r.FB), rem = (int)(i % r.FB);
         const int c = rem / (r.OH * r.OW), p = rem % (r.OH * r.OW), dy = p / r.OW, dx = p % r.OW;
-        const int sx0 = r.xofs[dx], sy0 = r.yofs[dy];
-        const int sx1 = r.xa1[dx] ? sx0 + 1 : sx0, sy1 = r.ya1[dy] ? sy0 + 1 : sy0;
+        const int sx0 = t.xofs[dx], sy0 = t.yofs[dy];
+        const int sx1 = t.xa1[dx] ? sx0 + 1 : sx0, sy1 = t.ya1[dy] ? sy0 + 1 : sy0;
         const uint8_t* g = d.grid + (size_t)e * d.CS;
         uint32_t dd[4];
         const int cy[2] = {sy0 >> 6, sy1 >> 6}, cx[2] = {sx0 >> 6, sx1 >> 6};
@@ -289,12 +380,10 @@ __global__ void k_render_generic(XwDev d, XwRender r, uint8_t* __restrict__ fram
         if (dd[0] == dd[1] && dd[0] == dd[2] && dd[0] == dd[3]) {
             v = dd[0] == 0 ? 255 : r.T[(size_t)(dd[0] - 1) * r.FB + rem];
         } else {
-            int px[4];
             const int sy[2] = {sy0, sy1}, sx[2] = {sx0, sx1};
-            for (int q = 0; q < 4; ++q)
-                px[q] = dd[q] == 0 ? 255
-                                   : r.atlas64[(size_t)(dd[q] - 1) * (64 * 64 * 3) + ((sy[q >> 1] & 63) * 64 + (sx[q & 1] & 63)) * 3 + c];
-            v = xw_resize_px(px[0], px[1], px[2], px[3], r.xa0[dx], r.xa1[dx], r.ya0[dy], r.ya1[dy]);
+            int px[4];
+            for (int q = 0; q < 4; ++q) px[q] = xw_canvas_tap(r, dd[q], sy[q >> 1], sx[q & 1], c);
+            v = xw_resize_px(px[0], px[1], px[2], px[3], t.xa0[dx], t.xa1[dx], t.ya0[dy], t.ya1[dy]);
         }
         frames[(size_t)e * env_stride + rem] = v;
     }

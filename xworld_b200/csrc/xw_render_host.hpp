@@ -1,19 +1,44 @@
 // xw_render_host.hpp -- host-side construction of the renderer's lookup tables.
 // cv::resize(INTER_LINEAR, 8U) coefficient tables as OpenCV 3.2 computes them (imgproc/resize.cpp:
-// scale = 1/(dst/src) in double, fx in float, cvFloor, 11-bit rounded weights), plus the cell
-// ownership maps the compositing kernel uses.
+// scale = 1/(dst/src) in double, fx in float, cvFloor, 11-bit rounded weights), plus the plan the
+// compositing kernel executes: one "band-column" item per (cell row, output word column).
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include <vector>
 
+// One compositor work item = one 4-pixel word column of one colour plane over a run of rows.  Items are
+// typed so that a warp executes one code path (the plan lists them sorted by type):
+//   M1  rows of a band (cell row), word inside ONE cell:            word = table(A)
+//   M2  rows of a band, word spanning two cells:                    word = PRMT(table(A), table(B))
+//   M3  like M2, and one byte lies on a straddling column (its two tap columns are in different
+//       cells): that byte is evaluated exactly from the cells' edge-tap tables
+//   R   one word of a straddling row (tap rows in different cell rows): separable U(top)+V(bottom) rule
+//   RC  like R, and one byte is a corner (straddling row x straddling column): exact from the atlas
+// The M items of a band exclude the band's straddling last row, so every frame word has one writer.
+struct XwItem {            // 16 bytes, one LDS.128
+    uint8_t cellA, cellB;  // cell indices ty*W + tx owning the word's first / last byte (top row for R/RC)
+    uint16_t sel;          // PRMT selector merging word(A) and word(B)
+    uint16_t woff;         // word offset of the item's first row inside a plane: y0*WR + k
+    uint8_t nrows;         // rows
+    uint8_t type;          // XW_ITEM_*
+    uint8_t y0;            // first row
+    uint8_t k;             // word column
+    uint8_t sbyte;         // M3/RC: byte of the word on the straddling column
+    uint8_t scell;         // M3/RC: that column's left cell (the right one is scell + 1)
+    uint8_t q;             // R/RC: index of the straddling row in XwRenderTables::sr
+    uint8_t pad[3];
+};
+enum { XW_ITEM_M1 = 0, XW_ITEM_M2 = 1, XW_ITEM_M3 = 2, XW_ITEM_R = 3, XW_ITEM_RC = 4, XW_ITEM_TYPES = 5 };
+
 struct XwRenderTables {
-    int H = 0, W = 0, OH = 0, OW = 0, WR = 0, FB = 0, R = 1, rpg = 0, threads = 0;
+    int H = 0, W = 0, OH = 0, OW = 0, WR = 0, FB = 0;
     bool fast_ok = false;  // the shared-memory compositor applies (else: generic kernel)
     std::vector<int16_t> xofs, xa0, xa1, yofs, ya0, ya1, sc, sr;
-    std::vector<uint8_t> rowcell, bandend;
-    std::vector<uint32_t> colpair;
+    std::vector<XwItem> items;           // per-plane plan, sorted by type
+    int seg[XW_ITEM_TYPES + 1] = {0};    // items of type t are items[seg[t] .. seg[t+1])
 };
 
 inline void xw_resize_tables(int src, int dst, int16_t* ofs, int16_t* a0, int16_t* a1) {
@@ -39,47 +64,65 @@ inline XwRenderTables xw_build_render_tables(int H, int W, int OH, int OW) {
     t.yofs.resize(OH); t.ya0.resize(OH); t.ya1.resize(OH);
     xw_resize_tables(W * 64, OW, t.xofs.data(), t.xa0.data(), t.xa1.data());
     xw_resize_tables(H * 64, OH, t.yofs.data(), t.ya0.data(), t.ya1.data());
+    std::vector<uint8_t> is_sc(OW, 0), is_sr(OH, 0);
     for (int dx = 0; dx < OW; ++dx)
-        if (t.xa1[dx] != 0 && ((t.xofs[dx] + 1) >> 6) != (t.xofs[dx] >> 6)) t.sc.push_back((int16_t)dx);
+        if (t.xa1[dx] != 0 && ((t.xofs[dx] + 1) >> 6) != (t.xofs[dx] >> 6)) { t.sc.push_back((int16_t)dx); is_sc[dx] = 1; }
     for (int dy = 0; dy < OH; ++dy)
-        if (t.ya1[dy] != 0 && ((t.yofs[dy] + 1) >> 6) != (t.yofs[dy] >> 6)) t.sr.push_back((int16_t)dy);
-    t.rowcell.resize(OH);
-    t.bandend.assign(H, (uint8_t)0);
-    bool ok = (OW % 4 == 0) && (t.FB % 16 == 0) && OH <= 255 && OW <= 1020;
-    for (int dy = 0; dy < OH; ++dy) t.rowcell[dy] = (uint8_t)(t.yofs[dy] >> 6);
-    for (int ty = 0; ty < H; ++ty) {
-        int e = OH;
-        for (int dy = 0; dy < OH; ++dy) if (t.rowcell[dy] > ty) { e = dy; break; }
-        t.bandend[ty] = (uint8_t)(e > 255 ? 255 : e);
+        if (t.ya1[dy] != 0 && ((t.yofs[dy] + 1) >> 6) != (t.yofs[dy] >> 6)) { t.sr.push_back((int16_t)dy); is_sr[dy] = 1; }
+    bool ok = (OW % 4 == 0) && (t.FB % 16 == 0) && OH <= 255 && OW <= 252 && OH * (OW / 4) <= 65535 && t.sr.size() <= 255;
+    // a straddling row is the last row of its band (yofs is monotone); two in one band (upscaling)
+    // would break the plan
+    for (size_t q = 0; q < t.sr.size() && ok; ++q) {
+        int dy = t.sr[q];
+        if (dy + 1 < OH && (t.yofs[dy + 1] >> 6) == (t.yofs[dy] >> 6)) ok = false;
     }
-    if (ok) {
-        t.WR = OW / 4;
-        t.colpair.resize(t.WR);
+    if (!ok) return t;
+    t.WR = OW / 4;
+    std::vector<XwItem> all;
+    for (int ty = 0; ty < H && ok; ++ty) {
+        int y0 = -1, y1 = -1;  // rows owned by cell row ty
+        for (int dy = 0; dy < OH; ++dy)
+            if ((t.yofs[dy] >> 6) == ty) { if (y0 < 0) y0 = dy; y1 = dy + 1; }
+        if (y0 < 0) continue;
+        const bool srow = is_sr[y1 - 1] != 0;
+        int q = 0;
+        if (srow) while (t.sr[q] != y1 - 1) ++q;
         for (int k = 0; k < t.WR && ok; ++k) {
+            XwItem it;
+            memset(&it, 0, sizeof it);
             int tx[4];
             for (int i = 0; i < 4; ++i) tx[i] = t.xofs[4 * k + i] >> 6;
             const int A = tx[0], B = tx[3];
             uint32_t sel = 0;
+            int n_sc = 0;
             for (int i = 0; i < 4; ++i) {
                 if (tx[i] == A) sel |= (uint32_t)i << (4 * i);
                 else if (tx[i] == B) sel |= (uint32_t)(4 + i) << (4 * i);
                 else ok = false;  // a 4-pixel word spans 3 cells: cells narrower than 2 px
+                if (is_sc[4 * k + i]) { ++n_sc; it.sbyte = (uint8_t)i; it.scell = (uint8_t)(ty * W + tx[i]); }
             }
-            t.colpair[k] = (uint32_t)A | ((uint32_t)B << 8) | (sel << 16);
+            if (n_sc > 1) ok = false;  // two straddling columns in one word: cells narrower than 4 px
+            it.cellA = (uint8_t)(ty * W + A); it.cellB = (uint8_t)(ty * W + B);
+            it.sel = (uint16_t)sel;
+            it.woff = (uint16_t)(y0 * t.WR + k);
+            it.nrows = (uint8_t)(y1 - y0 - (srow ? 1 : 0));
+            it.y0 = (uint8_t)y0; it.k = (uint8_t)k;
+            it.type = (uint8_t)(n_sc ? XW_ITEM_M3 : (A != B ? XW_ITEM_M2 : XW_ITEM_M1));
+            if (it.nrows > 0) all.push_back(it);
+            if (srow) {
+                XwItem r = it;
+                r.woff = (uint16_t)((y1 - 1) * t.WR + k);
+                r.nrows = 1; r.y0 = (uint8_t)(y1 - 1); r.q = (uint8_t)q;
+                r.type = (uint8_t)(n_sc ? XW_ITEM_RC : XW_ITEM_R);
+                all.push_back(r);
+            }
         }
     }
-    if (ok) {
-        int R = (int)lround(256.0 / (3.0 * t.WR));
-        if (R < 1) R = 1;
-        while (3 * R * t.WR > 1024) --R;
-        if (R < 1) ok = false;
-        t.R = R < 1 ? 1 : R;
-        t.rpg = (OH + t.R - 1) / t.R;
-        int items = 3 * t.R * t.WR;
-        if (items < H * W) items = H * W;
-        t.threads = (items + 31) / 32 * 32;
-        if (t.threads > 1024) ok = false;
+    for (int ty = 0; ty < XW_ITEM_TYPES; ++ty) {
+        t.seg[ty] = (int)t.items.size();
+        for (const XwItem& it : all) if (it.type == ty) t.items.push_back(it);
     }
+    t.seg[XW_ITEM_TYPES] = (int)t.items.size();
     t.fast_ok = ok;
     return t;
 }
