@@ -86,12 +86,11 @@ HostSim* hs_create(const xw_config* c, const xw_catalog* cat, int n) {
     XwRender& r = s->r;
     memset(&r, 0, sizeof r);
     r.OH = OH; r.OW = OW; r.WR = t.WR; r.FB = t.FB; r.H = c->height; r.W = c->width;
-    r.n_items = (int)t.items.size();
+    r.n_plan = (int)t.plan.size(); r.n_aux = (int)t.aux.size(); r.aux0 = t.seg[XW_ITEM_M3];
     r.n_icons = cat->n_icons; r.brick_icon = cat->brick_icon; r.agent_icon = cat->agent_icon;
     r.taps.xofs = t.xofs.data(); r.taps.xa0 = t.xa0.data(); r.taps.xa1 = t.xa1.data();
     r.taps.yofs = t.yofs.data(); r.taps.ya0 = t.ya0.data(); r.taps.ya1 = t.ya1.data();
-    r.items = t.items.data();
-    for (int i = 0; i <= XW_ITEM_TYPES; ++i) r.seg[i] = t.seg[i];
+    r.plan = t.plan.data(); r.aux = t.aux.data();
     r.n_sr = (int)t.sr.size();
     r.sr = t.sr.data();
     r.atlas64 = cat->atlas64;
@@ -155,18 +154,16 @@ void hs_render(HostSim* s, uint8_t* frames) {
     XwRender& r = s->r;
     XwDev& d = s->d;
     std::vector<uint32_t> cell(XW_CELL_STRIDE, 0), fb(r.FB / 4 + 4), yb(r.OH);
-    alignas(16) static const uint8_t white[16] = {255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255};
     for (int i = 0; i < r.OH; ++i) yb[i] = (uint32_t)(uint16_t)r.taps.ya0[i] | ((uint32_t)(uint16_t)r.taps.ya1[i] << 16);
     XwComposeCtx x;
-    x.hot = r.T + (size_t)r.brick_icon * r.FB; x.white = white; x.yb = yb.data();
+    x.hot = r.T + (size_t)r.brick_icon * r.FB; x.yb = yb.data();
     for (int e = 0; e < d.n; ++e) {
         for (int c = 0; c < d.H * d.W; ++c) cell[c] = xw_cell_desc(d, e, d.grid[(size_t)e * d.CS + c]);
         if (s->tab.fast_ok) {
             std::fill(fb.begin(), fb.end(), 0x5a5a5a5au);
-            for (int i = 0; i < 3 * r.n_items; ++i) {
-                int c;
-                const XwItem it = r.items[xw_plan_lookup(r, i, &c)];
-                xw_compose_item(r, x, it, c, cell.data(), fb.data());
+            for (int i = 0; i < r.n_plan; ++i) {  // the test alternates the compile-time and run-time row stride
+                if (r.WR == 21 && (e & 1)) xw_compose_item<21>(r, x, r.plan[i], r.aux, i, cell.data(), fb.data());
+                else xw_compose_item<0>(r, x, r.plan[i], r.aux, i, cell.data(), fb.data());
             }
             memcpy(frames + (size_t)e * r.FB, fb.data(), r.FB);
         } else {

@@ -93,6 +93,7 @@ struct xw_sim {
     XwRenderTables tab;
     std::vector<void*> allocs;
     int n_sms = 148, render_grid = 0, render_smem = 0;
+    void (*render_fn)(XwDev, XwRender, uint8_t*, size_t) = nullptr;  // k_render<WR> for this frame width
     int C = 3;
     // race
     XwRaceCfg race;
@@ -213,8 +214,7 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
     XwRender& r = s->r;
     memset(&r, 0, sizeof r);
     r.OH = OH; r.OW = OW; r.WR = t.WR; r.FB = t.FB; r.H = c.height; r.W = c.width;
-    r.n_items = (int)t.items.size();
-    for (int i = 0; i <= XW_ITEM_TYPES; ++i) r.seg[i] = t.seg[i];
+    r.n_plan = (int)t.plan.size(); r.n_aux = (int)t.aux.size(); r.aux0 = t.seg[XW_ITEM_M3];
     r.n_sr = (int)t.sr.size();
     r.n_icons = cat->n_icons; r.brick_icon = cat->brick_icon; r.agent_icon = cat->agent_icon;
     rc |= dupload(s, &r.taps.xofs, t.xofs.data(), t.xofs.size());
@@ -226,7 +226,9 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
     if (t.fast_ok) {
         static const int16_t zero16 = 0;
         uint16_t *ecol = nullptr, *uv = nullptr;
-        rc |= dupload(s, &r.items, t.items.data(), t.items.size());
+        static const XwU2 zero2 = {0, 0};
+        rc |= dupload(s, &r.plan, t.plan.data(), t.plan.size());
+        rc |= dupload(s, &r.aux, t.aux.empty() ? &zero2 : t.aux.data(), t.aux.empty() ? 1 : t.aux.size());
         rc |= dupload(s, &r.sr, t.sr.empty() ? &zero16 : t.sr.data(), t.sr.empty() ? 1 : t.sr.size());
         rc |= dalloc(s, &ecol, (size_t)(cat->n_icons + 1) * 2 * 3 * OH, false);
         rc |= dalloc(s, &uv, (size_t)(cat->n_icons + 1) * r.n_sr * 2 * 3 * OW + 8, false);
@@ -259,7 +261,8 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
         else {
             r.G = G; r.GT = (XW_RENDER_THREADS / G) / 32 * 32;
             s->render_smem = xw_render_smem(r, G).total;
-            CUDA_TRY(cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, s->render_smem));
+            s->render_fn = r.WR == 21 ? k_render<21> : r.WR == 24 ? k_render<24> : r.WR == 32 ? k_render<32> : k_render<0>;
+            CUDA_TRY(cudaFuncSetAttribute(s->render_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, s->render_smem));
             s->render_grid = s->n_sms;
         }
     }
@@ -404,7 +407,7 @@ static int launch_render(xw_sim* s, uint8_t* d_frames, cudaStream_t st) {
     if (s->tab.fast_ok) {
         const int need = (s->n + r.G - 1) / r.G;  // CTAs that get at least one env
         const int grid = s->render_grid < need ? s->render_grid : need;
-        k_render<<<grid, XW_RENDER_THREADS, s->render_smem, st>>>(s->d, r, dst, env_stride);
+        s->render_fn<<<grid, XW_RENDER_THREADS, s->render_smem, st>>>(s->d, r, dst, env_stride);
     } else {
         k_render_generic<<<s->n_sms * 8, 256, 0, st>>>(s->d, r, dst, env_stride);
     }

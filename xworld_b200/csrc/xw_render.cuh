@@ -31,20 +31,20 @@
 #define XW_RENDER_THREADS 1024
 #define XW_RENDER_MAX_GROUPS 8
 
-struct alignas(8) XwU2 { uint32_t x, y; };
 struct XwTaps { const int16_t *xofs, *xa0, *xa1, *yofs, *ya0, *ya1; };  // cv::resize tables
 
 struct XwRender {
     int32_t OH, OW, WR, FB;   // frame rows, cols, words per row, bytes per frame (3*OH*OW)
     int32_t H, W;
-    int32_t n_items;          // items in the per-plane plan
-    int32_t seg[XW_ITEM_TYPES + 1];
+    int32_t n_plan, n_aux;    // plan entries (3 planes), aux entries
+    int32_t aux0;             // plan index of the first item with an aux entry (seg[M3])
     int32_t G, GT;            // warp groups per CTA, threads per group
     int32_t n_icons, brick_icon, agent_icon;
     int32_t n_sr;             // straddling rows
     XwTaps taps;
     const int16_t* sr;        // [n_sr] the straddling rows
-    const XwItem* items;      // [n_items]
+    const XwU2* plan;         // [n_plan] packed items (xw_render_host.hpp)
+    const XwU2* aux;          // [n_aux]
     const uint8_t* T;         // [n_icons][3][OH][OW] phase atlas
     // edge tables, indexed by cell descriptor (0 = white, icon + 1 otherwise)
     const uint16_t* ecol;     // [n_icons+1][2][3][OH]  role 0: taps of icon column 63, role 1: column 0;
@@ -122,75 +122,97 @@ XW_HD uint32_t xw_prmt(uint32_t a, uint32_t b, uint32_t sel) {
 // What the compositor reads besides the per-env cells: shared-memory copies on the device.
 struct XwComposeCtx {
     const uint8_t* hot;     // brick phase table [FB]
-    const uint8_t* white;   // 16 bytes of 0xff
     const uint32_t* yb;     // [OH] ya0 | ya1 << 16
 };
 
-// Source of a cell's words: word w of the frame comes from *(base + w*mul).  White cells read one
-// constant word (mul = 0) so that every lane runs the same instructions.
-struct XwSrc { const uint8_t* base; uint32_t mul; };
+// Source of a cell's words: word w of the frame comes from *(base + 4*w) | wmask.  White cells read
+// the brick table and OR it to 0xffffffff, so that every lane runs the same instructions.
+struct XwSrc { const uint8_t* base; uint32_t wmask; };
 XW_HD XwSrc xw_src_of(const XwRender& r, const XwComposeCtx& x, uint32_t dsc) {
     XwSrc s;
-    if (dsc == 0) { s.base = x.white; s.mul = 0; }
-    else if ((int)dsc - 1 == r.brick_icon) { s.base = x.hot; s.mul = 4; }
-    else { s.base = r.T + (size_t)(dsc - 1) * r.FB; s.mul = 4; }
+    s.wmask = dsc == 0 ? 0xffffffffu : 0u;
+    s.base = (dsc == 0 || (int)dsc - 1 == r.brick_icon) ? x.hot : r.T + (size_t)(dsc - 1) * r.FB;
     return s;
 }
-XW_HD uint32_t xw_src_word(const XwSrc& s, int w) { return *(const uint32_t*)(s.base + (size_t)((uint32_t)w * s.mul)); }
 
-// ---- compose one item of plane c into the frame being built (fb, words) ----------------------
-XW_HD void xw_compose_item(const XwRender& r, const XwComposeCtx& x, const XwItem& it, int c, const uint32_t* celldesc,
-                           uint32_t* fb) {
-    const int WR = r.WR;
-    int w = c * r.OH * WR + it.woff;
-    if (it.type == XW_ITEM_M1) {
-        const XwSrc sA = xw_src_of(r, x, celldesc[it.cellA]);
-        for (int i = 0; i < it.nrows; ++i, w += WR) fb[w] = xw_src_word(sA, w);
-    } else if (it.type == XW_ITEM_M2) {
-        const XwSrc sA = xw_src_of(r, x, celldesc[it.cellA]), sB = xw_src_of(r, x, celldesc[it.cellB]);
-        const uint32_t sel = it.sel;
-        for (int i = 0; i < it.nrows; ++i, w += WR) fb[w] = xw_prmt(xw_src_word(sA, w), xw_src_word(sB, w), sel);
-    } else if (it.type == XW_ITEM_M3) {
-        const XwSrc sA = xw_src_of(r, x, celldesc[it.cellA]), sB = xw_src_of(r, x, celldesc[it.cellB]);
-        const uint32_t sel = it.sel;
-        const uint16_t* eL = r.ecol + ((size_t)(celldesc[it.scell] * 2 + 0) * 3 + c) * r.OH;
-        const uint16_t* eR = r.ecol + ((size_t)(celldesc[it.scell + 1] * 2 + 1) * 3 + c) * r.OH;
-        const int dx = 4 * it.k + it.sbyte, a0 = r.taps.xa0[dx], a1 = r.taps.xa1[dx];
-        const int sh = 8 * it.sbyte;
-        const uint32_t keep = ~(0xffu << sh);
-        for (int i = 0, dy = it.y0; i < it.nrows; ++i, ++dy, w += WR) {
-            const uint32_t word = xw_prmt(xw_src_word(sA, w), xw_src_word(sB, w), sel);
-            const uint32_t tl = eL[dy], tr = eR[dy], b = x.yb[dy];
-            const uint32_t v = xw_resize_px(tl & 255, tr & 255, tl >> 8, tr >> 8, a0, a1, b & 0xffff, b >> 16);
-            fb[w] = (word & keep) | (v << sh);
+// ---- compose one plan item into the frame being built (fb, words) ----------------------------
+// WR_T = words per frame row when known at compile time (row offsets become immediates), 0 = use r.WR.
+// Rows go four at a time, all loads before the stores: the tables and the frame buffer may alias as
+// far as the compiler knows, and a load-store-load chain would expose one memory latency per row.
+template <int WR_T>
+XW_HD void xw_compose_item(const XwRender& r, const XwComposeCtx& x, const XwU2 e, const XwU2* aux_tab, int plan_idx,
+                           const uint32_t* celldesc, uint32_t* fb) {
+    const int WR = WR_T ? WR_T : r.WR;
+    const int type = (e.y >> 24) & 7, nrows = (e.y >> 16) & 0xff;
+    const uint32_t w0 = e.y & 0xffffu, sel = e.x >> 16;
+    const int cellA = e.x & 0xff, cellB = (e.x >> 8) & 0xff;
+    uint32_t* dst = fb + w0;
+    if (type == XW_ITEM_M1) {
+        const XwSrc sA = xw_src_of(r, x, celldesc[cellA]);
+        const uint32_t* pA = (const uint32_t*)sA.base + w0;
+        for (int i0 = 0; i0 < nrows; i0 += 4, pA += 4 * WR, dst += 4 * WR) {
+            uint32_t v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (i0 + j < nrows) v[j] = pA[j * WR];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (i0 + j < nrows) dst[j * WR] = v[j] | sA.wmask;
         }
-    } else {  // R / RC: one word of straddling row q: out = (U[top cell] + V[bottom cell] + 2) >> 2
-        const size_t per_desc = (size_t)r.n_sr * 2 * 3 * r.OW, urow = ((size_t)it.q * 2 * 3 + c) * r.OW + 4 * it.k,
-                     vrow = urow + (size_t)3 * r.OW;
-        const XwU2 uA = *(const XwU2*)(r.uv + celldesc[it.cellA] * per_desc + urow);
-        const XwU2 uB = *(const XwU2*)(r.uv + celldesc[it.cellB] * per_desc + urow);
-        const XwU2 vA = *(const XwU2*)(r.uv + celldesc[it.cellA + r.W] * per_desc + vrow);
-        const XwU2 vB = *(const XwU2*)(r.uv + celldesc[it.cellB + r.W] * per_desc + vrow);
-        // packed u16 pairs: no carry between halves (U + V + 2 <= 2042)
-        const uint32_t a_lo = ((uA.x + vA.x + 0x00020002u) >> 2) & 0x00ff00ffu, a_hi = ((uA.y + vA.y + 0x00020002u) >> 2) & 0x00ff00ffu;
-        const uint32_t b_lo = ((uB.x + vB.x + 0x00020002u) >> 2) & 0x00ff00ffu, b_hi = ((uB.y + vB.y + 0x00020002u) >> 2) & 0x00ff00ffu;
-        uint32_t word = xw_prmt(xw_prmt(a_lo, a_hi, 0x6420), xw_prmt(b_lo, b_hi, 0x6420), it.sel);
-        if (it.type == XW_ITEM_RC) {
-            const int sh = 8 * it.sbyte;
-            word = (word & ~(0xffu << sh)) | ((uint32_t)xw_exact_px(r, celldesc, c, it.y0, 4 * it.k + it.sbyte) << sh);
-        }
-        fb[w] = word;
+        return;
     }
-}
-
-// plan index i in [0, 3*n_items) -> (item, plane): inside each type segment the three planes follow
-// one another, so a warp stays on one type.
-XW_HD int xw_plan_lookup(const XwRender& r, int i, int* c) {
-    int t = 0;
-    while (i >= 3 * r.seg[t + 1]) ++t;
-    const int n = r.seg[t + 1] - r.seg[t], rel = i - 3 * r.seg[t];
-    *c = (rel >= n) + (rel >= 2 * n);
-    return r.seg[t] + rel - *c * n;
+    if (type == XW_ITEM_M2) {
+        const XwSrc sA = xw_src_of(r, x, celldesc[cellA]), sB = xw_src_of(r, x, celldesc[cellB]);
+        const uint32_t* pA = (const uint32_t*)sA.base + w0;
+        const uint32_t* pB = (const uint32_t*)sB.base + w0;
+        const uint32_t wmask = xw_prmt(sA.wmask, sB.wmask, sel);
+        for (int i0 = 0; i0 < nrows; i0 += 4, pA += 4 * WR, pB += 4 * WR, dst += 4 * WR) {
+            uint32_t va[4], vb[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (i0 + j < nrows) { va[j] = pA[j * WR]; vb[j] = pB[j * WR]; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (i0 + j < nrows) dst[j * WR] = xw_prmt(va[j], vb[j], sel) | wmask;
+        }
+        return;
+    }
+    const XwU2 a = aux_tab[plan_idx - r.aux0];
+    const int c = (e.y >> 27) & 3;
+    const int y0 = a.x & 0xff, dx = (a.x >> 8) & 0xff, scell = (a.x >> 16) & 0xff, sh = (a.x >> 24) * 8;
+    if (type == XW_ITEM_M3) {
+        const XwSrc sA = xw_src_of(r, x, celldesc[cellA]), sB = xw_src_of(r, x, celldesc[cellB]);
+        const uint32_t* pA = (const uint32_t*)sA.base + w0;
+        const uint32_t* pB = (const uint32_t*)sB.base + w0;
+        const uint32_t wmask = xw_prmt(sA.wmask, sB.wmask, sel);
+        const uint16_t* eL = r.ecol + ((size_t)(celldesc[scell] * 2 + 0) * 3 + c) * r.OH + y0;
+        const uint16_t* eR = r.ecol + ((size_t)(celldesc[scell + 1] * 2 + 1) * 3 + c) * r.OH + y0;
+        const uint32_t* yb = x.yb + y0;
+        const int a0 = r.taps.xa0[dx], a1 = r.taps.xa1[dx];
+        const uint32_t keep = ~(0xffu << sh);
+        for (int i0 = 0; i0 < nrows; i0 += 2, pA += 2 * WR, pB += 2 * WR, dst += 2 * WR, eL += 2, eR += 2, yb += 2) {
+            uint32_t va[2], vb[2], tl[2], tr[2], b[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                if (i0 + j < nrows) { va[j] = pA[j * WR]; vb[j] = pB[j * WR]; tl[j] = eL[j]; tr[j] = eR[j]; b[j] = yb[j]; }
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                if (i0 + j < nrows) {
+                    const uint32_t v = xw_resize_px(tl[j] & 255, tr[j] & 255, tl[j] >> 8, tr[j] >> 8, a0, a1, b[j] & 0xffff, b[j] >> 16);
+                    dst[j * WR] = ((xw_prmt(va[j], vb[j], sel) | wmask) & keep) | (v << sh);
+                }
+        }
+        return;
+    }
+    // R / RC: one word of straddling row q: out = (U[top cell] + V[bottom cell] + 2) >> 2
+    const int q = a.y & 0xff, k = (a.y >> 8) & 0xff;
+    const size_t per_desc = (size_t)r.n_sr * 2 * 3 * r.OW, urow = ((size_t)q * 2 * 3 + c) * r.OW + 4 * k, vrow = urow + (size_t)3 * r.OW;
+    const XwU2 uA = *(const XwU2*)(r.uv + celldesc[cellA] * per_desc + urow);
+    const XwU2 uB = *(const XwU2*)(r.uv + celldesc[cellB] * per_desc + urow);
+    const XwU2 vA = *(const XwU2*)(r.uv + celldesc[cellA + r.W] * per_desc + vrow);
+    const XwU2 vB = *(const XwU2*)(r.uv + celldesc[cellB + r.W] * per_desc + vrow);
+    // packed u16 pairs: no carry between halves (U + V + 2 <= 2042)
+    const uint32_t a_lo = ((uA.x + vA.x + 0x00020002u) >> 2) & 0x00ff00ffu, a_hi = ((uA.y + vA.y + 0x00020002u) >> 2) & 0x00ff00ffu;
+    const uint32_t b_lo = ((uB.x + vB.x + 0x00020002u) >> 2) & 0x00ff00ffu, b_hi = ((uB.y + vB.y + 0x00020002u) >> 2) & 0x00ff00ffu;
+    uint32_t word = xw_prmt(xw_prmt(a_lo, a_hi, 0x6420), xw_prmt(b_lo, b_hi, 0x6420), sel);
+    if (type == XW_ITEM_RC) word = (word & ~(0xffu << sh)) | ((uint32_t)xw_exact_px(r, celldesc, c, y0, dx) << sh);
+    *dst = word;
 }
 
 // celldesc for one cell: grid code -> icon + 1
@@ -202,18 +224,18 @@ XW_HD uint32_t xw_cell_desc(const XwDev& d, int e, int code) {
 }
 
 // Dynamic shared memory layout (bytes), all sections 16-byte aligned:
-//   brick phase table (TMA bulk load, once) | G frame buffers | the plan | yb | white | G cell arrays | mbarrier
+//   brick phase table (TMA bulk load, once) | G frame buffers | plan | aux | yb | G cell arrays | mbarrier
 #define XW_CELL_STRIDE (XW_MAX_DIM * XW_MAX_DIM + XW_MAX_DIM + 2)  // + the (never drawn) row below the map
-struct XwRenderSmem { int hot, fb, items, yb, white, cell, bar, total; };
+struct XwRenderSmem { int hot, fb, plan, aux, yb, cell, bar, total; };
 XW_HD int xw_align16(int v) { return (v + 15) & ~15; }
 XW_HD XwRenderSmem xw_render_smem(const XwRender& r, int G) {
     XwRenderSmem s;
     int o = 0;
     s.hot = o; o += xw_align16(r.FB);
     s.fb = o; o += G * xw_align16(r.FB);
-    s.items = o; o += r.n_items * (int)sizeof(XwItem);
+    s.plan = o; o += xw_align16(r.n_plan * 8);
+    s.aux = o; o += xw_align16(r.n_aux * 8 + 8);
     s.yb = o; o += xw_align16(r.OH * 4);
-    s.white = o; o += 16;
     s.cell = o; o += G * XW_CELL_STRIDE * 4;
     s.bar = o; o += 16;
     s.total = o;
@@ -287,13 +309,15 @@ __device__ __forceinline__ void group_bar(int id, int nthreads) {
 
 // Persistent CTAs.  Group g of CTA b renders envs (b*G + g) + i * gridDim.x*G; the frame of env e goes
 // to frames + e*env_stride.
+template <int WR_T>
 __global__ void __launch_bounds__(XW_RENDER_THREADS, 1)
 k_render(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int G = r.G, GT = r.GT;
     const XwRenderSmem L = xw_render_smem(r, G);
     uint8_t* hot = smem + L.hot;
-    XwItem* s_items = (XwItem*)(smem + L.items);
+    XwU2* s_plan = (XwU2*)(smem + L.plan);
+    XwU2* s_aux = (XwU2*)(smem + L.aux);
     uint32_t* s_yb = (uint32_t*)(smem + L.yb);
     uint64_t* bar = (uint64_t*)(smem + L.bar);
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -309,11 +333,9 @@ k_render(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
         tma_load_1d(hot, r.T + (size_t)r.brick_icon * r.FB, (uint32_t)r.FB, bar);
     }
     {  // plan + row weights -> shared memory
-        const uint4* src = (const uint4*)r.items;
-        uint4* dst = (uint4*)s_items;
-        for (int i = tid; i < r.n_items; i += nt) dst[i] = src[i];
+        for (int i = tid; i < r.n_plan; i += nt) s_plan[i] = r.plan[i];
+        for (int i = tid; i < r.n_aux; i += nt) s_aux[i] = r.aux[i];
         for (int i = tid; i < r.OH; i += nt) s_yb[i] = (uint32_t)(uint16_t)r.taps.ya0[i] | ((uint32_t)(uint16_t)r.taps.ya1[i] << 16);
-        if (tid < 4) ((uint32_t*)(smem + L.white))[tid] = 0xffffffffu;
     }
     mbar_wait(bar, 0);
     __syncthreads();
@@ -323,9 +345,9 @@ k_render(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
     uint32_t* s_cell = (uint32_t*)(smem + L.cell) + g * XW_CELL_STRIDE;
     uint32_t* fb = (uint32_t*)(smem + L.fb + (size_t)g * xw_align16(r.FB));
     XwComposeCtx x;
-    x.hot = hot; x.white = smem + L.white; x.yb = s_yb;
+    x.hot = hot; x.yb = s_yb;
     const int bar_id = 1 + g;
-    const int n_plan = 3 * r.n_items;
+    const int n_plan = r.n_plan;
     const int gstride = gridDim.x * G;
     int env = blockIdx.x * G + g;
 
@@ -348,11 +370,7 @@ k_render(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
                 if (gt + GT < HW) nd1 = xw_cell_desc(d, en, d.grid[(size_t)en * d.CS + gt + GT]);
             }
         }
-        for (int i = gt; i < n_plan; i += GT) {
-            int c;
-            const XwItem it = s_items[xw_plan_lookup(r, i, &c)];
-            xw_compose_item(r, x, it, c, s_cell, fb);
-        }
+        for (int i = gt; i < n_plan; i += GT) xw_compose_item<WR_T>(r, x, s_plan[i], s_aux, i, s_cell, fb);
         fence_async_smem();  // generic-proxy writes -> visible to the async (TMA) proxy
         group_bar(bar_id, GT);
         if (gt == 0) {

@@ -10,7 +10,7 @@
 #include <vector>
 
 // One compositor work item = one 4-pixel word column of one colour plane over a run of rows.  Items are
-// typed so that a warp executes one code path (the plan lists them sorted by type):
+// typed so that a warp executes one code path (the plan lists them sorted by type, planes expanded):
 //   M1  rows of a band (cell row), word inside ONE cell:            word = table(A)
 //   M2  rows of a band, word spanning two cells:                    word = PRMT(table(A), table(B))
 //   M3  like M2, and one byte lies on a straddling column (its two tap columns are in different
@@ -18,27 +18,24 @@
 //   R   one word of a straddling row (tap rows in different cell rows): separable U(top)+V(bottom) rule
 //   RC  like R, and one byte is a corner (straddling row x straddling column): exact from the atlas
 // The M items of a band exclude the band's straddling last row, so every frame word has one writer.
-struct XwItem {            // 16 bytes, one LDS.128
-    uint8_t cellA, cellB;  // cell indices ty*W + tx owning the word's first / last byte (top row for R/RC)
-    uint16_t sel;          // PRMT selector merging word(A) and word(B)
-    uint16_t woff;         // word offset of the item's first row inside a plane: y0*WR + k
-    uint8_t nrows;         // rows
-    uint8_t type;          // XW_ITEM_*
-    uint8_t y0;            // first row
-    uint8_t k;             // word column
-    uint8_t sbyte;         // M3/RC: byte of the word on the straddling column
-    uint8_t scell;         // M3/RC: that column's left cell (the right one is scell + 1)
-    uint8_t q;             // R/RC: index of the straddling row in XwRenderTables::sr
-    uint8_t pad[3];
-};
 enum { XW_ITEM_M1 = 0, XW_ITEM_M2 = 1, XW_ITEM_M3 = 2, XW_ITEM_R = 3, XW_ITEM_RC = 4, XW_ITEM_TYPES = 5 };
+
+// Packed plan entry (one LDS.64):
+//   x = cellA | cellB << 8 | sel << 16        cell indices ty*W + tx owning the word's first / last byte
+//                                             (top cell row for R/RC), PRMT selector merging word(A), word(B)
+//   y = woff | nrows << 16 | type << 24 | c << 27     word offset of the first row in the FRAME, rows, plane
+// Items of type >= M3 also have an aux entry (index = plan index - seg[M3]):
+//   x = y0 | dx << 8 | scell << 16 | sbyte << 24     first row; the straddling column, its left cell
+//                                                    (the right one is scell + 1), its byte in the word
+//   y = q | k << 8                                   R/RC: index of the straddling row; word column
+struct alignas(8) XwU2 { uint32_t x, y; };
 
 struct XwRenderTables {
     int H = 0, W = 0, OH = 0, OW = 0, WR = 0, FB = 0;
     bool fast_ok = false;  // the shared-memory compositor applies (else: generic kernel)
     std::vector<int16_t> xofs, xa0, xa1, yofs, ya0, ya1, sc, sr;
-    std::vector<XwItem> items;           // per-plane plan, sorted by type
-    int seg[XW_ITEM_TYPES + 1] = {0};    // items of type t are items[seg[t] .. seg[t+1])
+    std::vector<XwU2> plan, aux;         // plan sorted by type; aux for plan[seg[M3]..]
+    int seg[XW_ITEM_TYPES + 1] = {0};    // items of type t are plan[seg[t] .. seg[t+1])
 };
 
 inline void xw_resize_tables(int src, int dst, int16_t* ofs, int16_t* a0, int16_t* a1) {
@@ -78,7 +75,8 @@ inline XwRenderTables xw_build_render_tables(int H, int W, int OH, int OW) {
     }
     if (!ok) return t;
     t.WR = OW / 4;
-    std::vector<XwItem> all;
+    struct Item { int cellA, cellB, sel, woff, nrows, type, y0, k, sbyte, scell, dx, q; };
+    std::vector<Item> all;
     for (int ty = 0; ty < H && ok; ++ty) {
         int y0 = -1, y1 = -1;  // rows owned by cell row ty
         for (int dy = 0; dy < OH; ++dy)
@@ -88,41 +86,52 @@ inline XwRenderTables xw_build_render_tables(int H, int W, int OH, int OW) {
         int q = 0;
         if (srow) while (t.sr[q] != y1 - 1) ++q;
         for (int k = 0; k < t.WR && ok; ++k) {
-            XwItem it;
+            Item it;
             memset(&it, 0, sizeof it);
             int tx[4];
             for (int i = 0; i < 4; ++i) tx[i] = t.xofs[4 * k + i] >> 6;
             const int A = tx[0], B = tx[3];
-            uint32_t sel = 0;
             int n_sc = 0;
             for (int i = 0; i < 4; ++i) {
-                if (tx[i] == A) sel |= (uint32_t)i << (4 * i);
-                else if (tx[i] == B) sel |= (uint32_t)(4 + i) << (4 * i);
+                if (tx[i] == A) it.sel |= i << (4 * i);
+                else if (tx[i] == B) it.sel |= (4 + i) << (4 * i);
                 else ok = false;  // a 4-pixel word spans 3 cells: cells narrower than 2 px
-                if (is_sc[4 * k + i]) { ++n_sc; it.sbyte = (uint8_t)i; it.scell = (uint8_t)(ty * W + tx[i]); }
+                if (is_sc[4 * k + i]) { ++n_sc; it.sbyte = i; it.scell = ty * W + tx[i]; it.dx = 4 * k + i; }
             }
             if (n_sc > 1) ok = false;  // two straddling columns in one word: cells narrower than 4 px
-            it.cellA = (uint8_t)(ty * W + A); it.cellB = (uint8_t)(ty * W + B);
-            it.sel = (uint16_t)sel;
-            it.woff = (uint16_t)(y0 * t.WR + k);
-            it.nrows = (uint8_t)(y1 - y0 - (srow ? 1 : 0));
-            it.y0 = (uint8_t)y0; it.k = (uint8_t)k;
-            it.type = (uint8_t)(n_sc ? XW_ITEM_M3 : (A != B ? XW_ITEM_M2 : XW_ITEM_M1));
+            it.cellA = ty * W + A; it.cellB = ty * W + B;
+            it.woff = y0 * t.WR + k;
+            it.nrows = y1 - y0 - (srow ? 1 : 0);
+            it.y0 = y0; it.k = k;
+            it.type = n_sc ? XW_ITEM_M3 : (A != B ? XW_ITEM_M2 : XW_ITEM_M1);
             if (it.nrows > 0) all.push_back(it);
             if (srow) {
-                XwItem r = it;
-                r.woff = (uint16_t)((y1 - 1) * t.WR + k);
-                r.nrows = 1; r.y0 = (uint8_t)(y1 - 1); r.q = (uint8_t)q;
-                r.type = (uint8_t)(n_sc ? XW_ITEM_RC : XW_ITEM_R);
+                Item r = it;
+                r.woff = (y1 - 1) * t.WR + k;
+                r.nrows = 1; r.y0 = y1 - 1; r.q = q;
+                r.type = n_sc ? XW_ITEM_RC : XW_ITEM_R;
                 all.push_back(r);
             }
         }
     }
-    for (int ty = 0; ty < XW_ITEM_TYPES; ++ty) {
-        t.seg[ty] = (int)t.items.size();
-        for (const XwItem& it : all) if (it.type == ty) t.items.push_back(it);
+    if (3 * OH * t.WR > 65535) ok = false;  // woff is 16 bits
+    for (int ty = 0; ty < XW_ITEM_TYPES && ok; ++ty) {
+        t.seg[ty] = (int)t.plan.size();
+        for (int c = 0; c < 3; ++c)
+            for (const Item& it : all) {
+                if (it.type != ty) continue;
+                XwU2 e, a;
+                e.x = (uint32_t)it.cellA | ((uint32_t)it.cellB << 8) | ((uint32_t)it.sel << 16);
+                e.y = (uint32_t)(c * OH * t.WR + it.woff) | ((uint32_t)it.nrows << 16) | ((uint32_t)it.type << 24) | ((uint32_t)c << 27);
+                t.plan.push_back(e);
+                if (ty >= XW_ITEM_M3) {
+                    a.x = (uint32_t)it.y0 | ((uint32_t)it.dx << 8) | ((uint32_t)it.scell << 16) | ((uint32_t)it.sbyte << 24);
+                    a.y = (uint32_t)it.q | ((uint32_t)it.k << 8);
+                    t.aux.push_back(a);
+                }
+            }
     }
-    t.seg[XW_ITEM_TYPES] = (int)t.items.size();
+    t.seg[XW_ITEM_TYPES] = (int)t.plan.size();
     t.fast_ok = ok;
     return t;
 }
