@@ -24,6 +24,7 @@ struct HostSim {
     std::vector<std::vector<uint8_t>> bufs;
     std::vector<uint8_t> T;
     std::vector<uint16_t> ecol, uv;
+    std::vector<uint32_t> corner;
     XwRaceCfg race;
 };
 
@@ -86,16 +87,18 @@ HostSim* hs_create(const xw_config* c, const xw_catalog* cat, int n) {
     XwRender& r = s->r;
     memset(&r, 0, sizeof r);
     r.OH = OH; r.OW = OW; r.WR = t.WR; r.FB = t.FB; r.H = c->height; r.W = c->width;
-    r.n_plan = (int)t.plan.size(); r.n_aux = (int)t.aux.size(); r.aux0 = t.seg[XW_ITEM_M3];
     r.n_icons = cat->n_icons; r.brick_icon = cat->brick_icon; r.agent_icon = cat->agent_icon;
     r.taps.xofs = t.xofs.data(); r.taps.xa0 = t.xa0.data(); r.taps.xa1 = t.xa1.data();
     r.taps.yofs = t.yofs.data(); r.taps.ya0 = t.ya0.data(); r.taps.ya1 = t.ya1.data();
-    r.plan = t.plan.data(); r.aux = t.aux.data();
+    if (t.fast_ok) {  // odd map sides exercise the per-plane M3 split, even ones the 3-plane items
+        xw_build_plan(t, 4 + c->height % 3, c->height % 2 != 0);
+        r.plan = t.plan.data(); r.n_plan = (int)t.plan.size(); r.G = 1; r.GT = t.n_warps * 32;
+    }
     r.n_sr = (int)t.sr.size();
     r.sr = t.sr.data();
     r.atlas64 = cat->atlas64;
     if (t.fast_ok) {  // k_build_edge_tables
-        s->ecol.resize((size_t)(cat->n_icons + 1) * 2 * 3 * OH);
+        s->ecol.resize((size_t)(cat->n_icons + 1) * 2 * 3 * OH + XW_TABLE_PAD / 2);
         s->uv.resize((size_t)(cat->n_icons + 1) * r.n_sr * 2 * 3 * OW + 8);
         for (size_t i = 0; i < (size_t)(cat->n_icons + 1) * 2 * 3 * OH; ++i) {
             size_t j = i;
@@ -110,7 +113,9 @@ HostSim* hs_create(const xw_config* c, const xw_catalog* cat, int n) {
             const int role = (int)(j % 2); j /= 2;
             s->uv[i] = xw_uv_entry(r, (uint32_t)(j / r.n_sr), (int)(j % r.n_sr), role, cc, dx);
         }
-        r.ecol = s->ecol.data(); r.uv = s->uv.data();
+        s->corner.resize((size_t)(cat->n_icons + 1) * 3);
+        for (size_t j = 0; j < s->corner.size(); ++j) s->corner[j] = xw_corner_entry(r, (uint32_t)(j / 3), (int)(j % 3));
+        r.ecol = s->ecol.data(); r.uv = s->uv.data(); r.corner = s->corner.data();
     }
     r.atlas64 = cat->atlas64;
     return s;
@@ -119,7 +124,7 @@ HostSim* hs_create(const xw_config* c, const xw_catalog* cat, int n) {
 // Build the phase atlas only for the icons in use (the full 363-icon table takes a while on one core).
 void hs_build_phase_atlas(HostSim* s, const int32_t* icons, int n_icons) {
     XwRender& r = s->r;
-    s->T.assign((size_t)r.n_icons * r.FB, 0);
+    s->T.assign((size_t)r.n_icons * r.FB + XW_TABLE_PAD, 0);
     r.T = s->T.data();
     for (int q = 0; q < n_icons; ++q) {
         int icon = icons[q];
@@ -162,8 +167,8 @@ void hs_render(HostSim* s, uint8_t* frames) {
         if (s->tab.fast_ok) {
             std::fill(fb.begin(), fb.end(), 0x5a5a5a5au);
             for (int i = 0; i < r.n_plan; ++i) {  // the test alternates the compile-time and run-time row stride
-                if (r.WR == 21 && (e & 1)) xw_compose_item<21>(r, x, r.plan[i], r.aux, i, cell.data(), fb.data());
-                else xw_compose_item<0>(r, x, r.plan[i], r.aux, i, cell.data(), fb.data());
+                if (r.WR == 21 && (e & 1)) xw_compose_item<21>(r, x, r.plan[i], cell.data(), fb.data());
+                else xw_compose_item<0>(r, x, r.plan[i], cell.data(), fb.data());
             }
             memcpy(frames + (size_t)e * r.FB, fb.data(), r.FB);
         } else {

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -214,7 +215,6 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
     XwRender& r = s->r;
     memset(&r, 0, sizeof r);
     r.OH = OH; r.OW = OW; r.WR = t.WR; r.FB = t.FB; r.H = c.height; r.W = c.width;
-    r.n_plan = (int)t.plan.size(); r.n_aux = (int)t.aux.size(); r.aux0 = t.seg[XW_ITEM_M3];
     r.n_sr = (int)t.sr.size();
     r.n_icons = cat->n_icons; r.brick_icon = cat->brick_icon; r.agent_icon = cat->agent_icon;
     rc |= dupload(s, &r.taps.xofs, t.xofs.data(), t.xofs.size());
@@ -224,19 +224,44 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
     rc |= dupload(s, &r.taps.ya0, t.ya0.data(), t.ya0.size());
     rc |= dupload(s, &r.taps.ya1, t.ya1.data(), t.ya1.size());
     if (t.fast_ok) {
+        // warp groups per CTA: as many private frame buffers as shared memory holds (XW_RENDER_GROUPS /
+        // XW_RENDER_GROUP_THREADS / XW_RENDER_SPLIT_M3 override the choice, for tuning), each group wide
+        // enough to prefetch a whole map (H*W <= 2*GT)
+        int max_optin = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
+        const char* eg = getenv("XW_RENDER_GROUPS");
+        const char* et = getenv("XW_RENDER_GROUP_THREADS");
+        const char* es = getenv("XW_RENDER_SPLIT_M3");
+        const bool split = es ? atoi(es) != 0 : true;
+        int G = eg ? atoi(eg) : XW_RENDER_MAX_GROUPS;
+        if (G > XW_RENDER_MAX_GROUPS) G = XW_RENDER_MAX_GROUPS;
+        bool found = false;
+        for (; G >= 1 && !found; --G) {
+            int GT = et ? atoi(et) : (768 / G) / 32 * 32;  // 768 threads/CTA: 80 registers per thread
+            GT = GT / 32 * 32;
+            if (GT < 32 || G * GT > XW_RENDER_THREADS || 2 * GT < c.height * c.width) { if (et) break; continue; }
+            xw_build_plan(t, GT / 32, split);
+            r.n_plan = (int)t.plan.size();
+            if (xw_render_smem(r, G).total > max_optin) continue;
+            r.G = G; r.GT = GT;
+            found = true;
+        }
+        if (!found) t.fast_ok = false;
+    }
+    if (t.fast_ok) {
         static const int16_t zero16 = 0;
         uint16_t *ecol = nullptr, *uv = nullptr;
-        static const XwU2 zero2 = {0, 0};
+        uint32_t* corner = nullptr;
         rc |= dupload(s, &r.plan, t.plan.data(), t.plan.size());
-        rc |= dupload(s, &r.aux, t.aux.empty() ? &zero2 : t.aux.data(), t.aux.empty() ? 1 : t.aux.size());
         rc |= dupload(s, &r.sr, t.sr.empty() ? &zero16 : t.sr.data(), t.sr.empty() ? 1 : t.sr.size());
-        rc |= dalloc(s, &ecol, (size_t)(cat->n_icons + 1) * 2 * 3 * OH, false);
+        rc |= dalloc(s, &ecol, (size_t)(cat->n_icons + 1) * 2 * 3 * OH + XW_TABLE_PAD / 2, false);
         rc |= dalloc(s, &uv, (size_t)(cat->n_icons + 1) * r.n_sr * 2 * 3 * OW + 8, false);
-        r.ecol = ecol; r.uv = uv;
+        rc |= dalloc(s, &corner, (size_t)(cat->n_icons + 1) * 3, false);
+        r.ecol = ecol; r.uv = uv; r.corner = corner;
     }
     rc |= dupload(s, &r.atlas64, cat->atlas64, (size_t)cat->n_icons * 64 * 64 * 3);
     uint8_t* T = nullptr;
-    rc |= dalloc(s, &T, (size_t)cat->n_icons * r.FB, false);
+    rc |= dalloc(s, &T, (size_t)cat->n_icons * r.FB + XW_TABLE_PAD, false);
     if (rc) return rc;
     r.T = T;
     k_build_phase_atlas<<<s->n_sms * 8, 256, 0, s->own_stream>>>(r);
@@ -247,24 +272,14 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
     }
     CUDA_TRY(cudaGetLastError());
     if (t.fast_ok) {
-        // warp groups per CTA: as many private frame buffers as shared memory holds, each group wide
-        // enough to prefetch a whole map (H*W <= 2*GT)
-        int max_optin = 0;
-        CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
-        int G = XW_RENDER_MAX_GROUPS;
-        while (G >= 1) {
-            int GT = (XW_RENDER_THREADS / G) / 32 * 32;
-            if (xw_render_smem(r, G).total <= max_optin && 2 * GT >= c.height * c.width) break;
-            --G;
-        }
-        if (G < 1) t.fast_ok = false;
-        else {
-            r.G = G; r.GT = (XW_RENDER_THREADS / G) / 32 * 32;
-            s->render_smem = xw_render_smem(r, G).total;
-            s->render_fn = r.WR == 21 ? k_render<21> : r.WR == 24 ? k_render<24> : r.WR == 32 ? k_render<32> : k_render<0>;
-            CUDA_TRY(cudaFuncSetAttribute(s->render_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, s->render_smem));
-            s->render_grid = s->n_sms;
-        }
+        s->render_smem = xw_render_smem(r, r.G).total;
+        // instantiations: compile-time row stride for the common frame widths x register budget by CTA size
+        const int nt = r.G * r.GT;
+#define XW_PICK(WR_) (nt <= 512 ? k_render<WR_, 512> : nt <= 768 ? k_render<WR_, 768> : k_render<WR_, 1024>)
+        s->render_fn = r.WR == 21 ? XW_PICK(21) : r.WR == 24 ? XW_PICK(24) : r.WR == 32 ? XW_PICK(32) : XW_PICK(0);
+#undef XW_PICK
+        CUDA_TRY(cudaFuncSetAttribute(s->render_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, s->render_smem));
+        s->render_grid = s->n_sms;
     }
     CUDA_TRY(cudaStreamSynchronize(s->own_stream));
     return 0;
@@ -407,7 +422,7 @@ static int launch_render(xw_sim* s, uint8_t* d_frames, cudaStream_t st) {
     if (s->tab.fast_ok) {
         const int need = (s->n + r.G - 1) / r.G;  // CTAs that get at least one env
         const int grid = s->render_grid < need ? s->render_grid : need;
-        s->render_fn<<<grid, XW_RENDER_THREADS, s->render_smem, st>>>(s->d, r, dst, env_stride);
+        s->render_fn<<<grid, r.G * r.GT, s->render_smem, st>>>(s->d, r, dst, env_stride);
     } else {
         k_render_generic<<<s->n_sms * 8, 256, 0, st>>>(s->d, r, dst, env_stride);
     }

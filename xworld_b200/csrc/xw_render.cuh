@@ -30,26 +30,26 @@
 #define XW_MAX_OUT 252        // max frame side
 #define XW_RENDER_THREADS 1024
 #define XW_RENDER_MAX_GROUPS 8
+#define XW_TABLE_PAD 8192     // bytes past each table the compositor may read (and never use)
 
 struct XwTaps { const int16_t *xofs, *xa0, *xa1, *yofs, *ya0, *ya1; };  // cv::resize tables
 
 struct XwRender {
     int32_t OH, OW, WR, FB;   // frame rows, cols, words per row, bytes per frame (3*OH*OW)
     int32_t H, W;
-    int32_t n_plan, n_aux;    // plan entries (3 planes), aux entries
-    int32_t aux0;             // plan index of the first item with an aux entry (seg[M3])
+    int32_t n_plan;           // plan slots (a multiple of GT)
     int32_t G, GT;            // warp groups per CTA, threads per group
     int32_t n_icons, brick_icon, agent_icon;
     int32_t n_sr;             // straddling rows
     XwTaps taps;
     const int16_t* sr;        // [n_sr] the straddling rows
-    const XwU2* plan;         // [n_plan] packed items (xw_render_host.hpp)
-    const XwU2* aux;          // [n_aux]
+    const XwU4* plan;         // [n_plan] packed items (xw_render_host.hpp)
     const uint8_t* T;         // [n_icons][3][OH][OW] phase atlas
     // edge tables, indexed by cell descriptor (0 = white, icon + 1 otherwise)
     const uint16_t* ecol;     // [n_icons+1][2][3][OH]  role 0: taps of icon column 63, role 1: column 0;
                               //   low byte = tap row of yofs[dy], high byte = the row below it
     const uint16_t* uv;       // [n_icons+1][n_sr][2][3][OW]  role 0: U from icon row 63, role 1: V from row 0
+    const uint32_t* corner;   // [n_icons+1][3]  icon pixels (63,63) | (63,0) << 8 | (0,63) << 16 | (0,0) << 24
     const uint8_t* atlas64;   // [n_icons][64][64][3] BGR
 };
 
@@ -93,6 +93,11 @@ XW_HD uint16_t xw_uv_entry(const XwRender& r, uint32_t dsc, int q, int role, int
     int sy = role == 0 ? 63 : 0;
     return (uint16_t)xw_vterm(xw_canvas_tap(r, dsc, sy, sx0, c), xw_canvas_tap(r, dsc, sy, sx1, c), t.xa0[dx], t.xa1[dx],
                               role == 0 ? t.ya0[dy] : t.ya1[dy]);
+}
+
+XW_HD uint32_t xw_corner_entry(const XwRender& r, uint32_t dsc, int c) {
+    return (uint32_t)xw_canvas_tap(r, dsc, 63, 63, c) | ((uint32_t)xw_canvas_tap(r, dsc, 63, 0, c) << 8) |
+           ((uint32_t)xw_canvas_tap(r, dsc, 0, 63, c) << 16) | ((uint32_t)xw_canvas_tap(r, dsc, 0, 0, c) << 24);
 }
 
 // Value of output pixel (c,dy,dx) on the real canvas, from the 64-px atlas (any four cells).
@@ -140,79 +145,121 @@ XW_HD XwSrc xw_src_of(const XwRender& r, const XwComposeCtx& x, uint32_t dsc) {
 // Rows go four at a time, all loads before the stores: the tables and the frame buffer may alias as
 // far as the compiler knows, and a load-store-load chain would expose one memory latency per row.
 template <int WR_T>
-XW_HD void xw_compose_item(const XwRender& r, const XwComposeCtx& x, const XwU2 e, const XwU2* aux_tab, int plan_idx,
-                           const uint32_t* celldesc, uint32_t* fb) {
+XW_HD void xw_compose_item(const XwRender& r, const XwComposeCtx& x, const XwU4 e, const uint32_t* celldesc, uint32_t* fb) {
     const int WR = WR_T ? WR_T : r.WR;
-    const int type = (e.y >> 24) & 7, nrows = (e.y >> 16) & 0xff;
+    const int PW = r.OH * WR;  // words per plane
+    const int type = (e.y >> 24) & 7, nrows = (e.y >> 16) & 0xff, nc = e.y >> 29;
     const uint32_t w0 = e.y & 0xffffu, sel = e.x >> 16;
     const int cellA = e.x & 0xff, cellB = (e.x >> 8) & 0xff;
-    uint32_t* dst = fb + w0;
+    // The goal / agent tables live in L2: every batch of loads below costs one L2 round trip for the
+    // warp, so each batch is as wide as the register budget allows (24 words in flight).  Loads are
+    // unconditional -- rows past the band read table bytes that are never stored (the tables are
+    // padded by XW_TABLE_PAD) -- and only the stores are predicated, one predicate per row.
+    if (nc == 0) return;  // padding slot
     if (type == XW_ITEM_M1) {
         const XwSrc sA = xw_src_of(r, x, celldesc[cellA]);
         const uint32_t* pA = (const uint32_t*)sA.base + w0;
-        for (int i0 = 0; i0 < nrows; i0 += 4, pA += 4 * WR, dst += 4 * WR) {
-            uint32_t v[4];
+        uint32_t* dst = fb + w0;
+        for (int i0 = 0; i0 < nrows; i0 += 8, pA += 8 * WR, dst += 8 * WR) {
+            uint32_t v[3][8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) if (i0 + j < nrows) v[j] = pA[j * WR];
+            for (int j = 0; j < 8; ++j)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) if (i0 + j < nrows) dst[j * WR] = v[j] | sA.wmask;
+                for (int cc = 0; cc < 3; ++cc) v[cc][j] = pA[cc * PW + j * WR];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (i0 + j < nrows) {
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc) dst[cc * PW + j * WR] = v[cc][j] | sA.wmask;
+                }
         }
         return;
     }
     if (type == XW_ITEM_M2) {
         const XwSrc sA = xw_src_of(r, x, celldesc[cellA]), sB = xw_src_of(r, x, celldesc[cellB]);
+        const uint32_t wmask = xw_prmt(sA.wmask, sB.wmask, sel);
         const uint32_t* pA = (const uint32_t*)sA.base + w0;
         const uint32_t* pB = (const uint32_t*)sB.base + w0;
-        const uint32_t wmask = xw_prmt(sA.wmask, sB.wmask, sel);
+        uint32_t* dst = fb + w0;
         for (int i0 = 0; i0 < nrows; i0 += 4, pA += 4 * WR, pB += 4 * WR, dst += 4 * WR) {
-            uint32_t va[4], vb[4];
+            uint32_t va[3][4], vb[3][4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) if (i0 + j < nrows) { va[j] = pA[j * WR]; vb[j] = pB[j * WR]; }
+            for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) if (i0 + j < nrows) dst[j * WR] = xw_prmt(va[j], vb[j], sel) | wmask;
-        }
-        return;
-    }
-    const XwU2 a = aux_tab[plan_idx - r.aux0];
-    const int c = (e.y >> 27) & 3;
-    const int y0 = a.x & 0xff, dx = (a.x >> 8) & 0xff, scell = (a.x >> 16) & 0xff, sh = (a.x >> 24) * 8;
-    if (type == XW_ITEM_M3) {
-        const XwSrc sA = xw_src_of(r, x, celldesc[cellA]), sB = xw_src_of(r, x, celldesc[cellB]);
-        const uint32_t* pA = (const uint32_t*)sA.base + w0;
-        const uint32_t* pB = (const uint32_t*)sB.base + w0;
-        const uint32_t wmask = xw_prmt(sA.wmask, sB.wmask, sel);
-        const uint16_t* eL = r.ecol + ((size_t)(celldesc[scell] * 2 + 0) * 3 + c) * r.OH + y0;
-        const uint16_t* eR = r.ecol + ((size_t)(celldesc[scell + 1] * 2 + 1) * 3 + c) * r.OH + y0;
-        const uint32_t* yb = x.yb + y0;
-        const int a0 = r.taps.xa0[dx], a1 = r.taps.xa1[dx];
-        const uint32_t keep = ~(0xffu << sh);
-        for (int i0 = 0; i0 < nrows; i0 += 2, pA += 2 * WR, pB += 2 * WR, dst += 2 * WR, eL += 2, eR += 2, yb += 2) {
-            uint32_t va[2], vb[2], tl[2], tr[2], b[2];
+                for (int cc = 0; cc < 3; ++cc) { va[cc][j] = pA[cc * PW + j * WR]; vb[cc][j] = pB[cc * PW + j * WR]; }
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
-                if (i0 + j < nrows) { va[j] = pA[j * WR]; vb[j] = pB[j * WR]; tl[j] = eL[j]; tr[j] = eR[j]; b[j] = yb[j]; }
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
+            for (int j = 0; j < 4; ++j)
                 if (i0 + j < nrows) {
-                    const uint32_t v = xw_resize_px(tl[j] & 255, tr[j] & 255, tl[j] >> 8, tr[j] >> 8, a0, a1, b[j] & 0xffff, b[j] >> 16);
-                    dst[j * WR] = ((xw_prmt(va[j], vb[j], sel) | wmask) & keep) | (v << sh);
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc) dst[cc * PW + j * WR] = xw_prmt(va[cc][j], vb[cc][j], sel) | wmask;
                 }
         }
         return;
     }
-    // R / RC: one word of straddling row q: out = (U[top cell] + V[bottom cell] + 2) >> 2
-    const int q = a.y & 0xff, k = (a.y >> 8) & 0xff;
-    const size_t per_desc = (size_t)r.n_sr * 2 * 3 * r.OW, urow = ((size_t)q * 2 * 3 + c) * r.OW + 4 * k, vrow = urow + (size_t)3 * r.OW;
-    const XwU2 uA = *(const XwU2*)(r.uv + celldesc[cellA] * per_desc + urow);
-    const XwU2 uB = *(const XwU2*)(r.uv + celldesc[cellB] * per_desc + urow);
-    const XwU2 vA = *(const XwU2*)(r.uv + celldesc[cellA + r.W] * per_desc + vrow);
-    const XwU2 vB = *(const XwU2*)(r.uv + celldesc[cellB + r.W] * per_desc + vrow);
-    // packed u16 pairs: no carry between halves (U + V + 2 <= 2042)
-    const uint32_t a_lo = ((uA.x + vA.x + 0x00020002u) >> 2) & 0x00ff00ffu, a_hi = ((uA.y + vA.y + 0x00020002u) >> 2) & 0x00ff00ffu;
-    const uint32_t b_lo = ((uB.x + vB.x + 0x00020002u) >> 2) & 0x00ff00ffu, b_hi = ((uB.y + vB.y + 0x00020002u) >> 2) & 0x00ff00ffu;
-    uint32_t word = xw_prmt(xw_prmt(a_lo, a_hi, 0x6420), xw_prmt(b_lo, b_hi, 0x6420), sel);
-    if (type == XW_ITEM_RC) word = (word & ~(0xffu << sh)) | ((uint32_t)xw_exact_px(r, celldesc, c, y0, dx) << sh);
-    *dst = word;
+    const int c0 = (e.y >> 27) & 3;
+    const int y0 = e.z & 0xff, dx = (e.z >> 8) & 0xff, scell = (e.z >> 16) & 0xff, sh = (e.z >> 24) * 8;
+    if (type == XW_ITEM_M3) {
+        const XwSrc sA = xw_src_of(r, x, celldesc[cellA]), sB = xw_src_of(r, x, celldesc[cellB]);
+        const uint32_t wmask = xw_prmt(sA.wmask, sB.wmask, sel);
+        const uint16_t* eL0 = r.ecol + ((size_t)(celldesc[scell] * 2 + 0) * 3 + c0) * r.OH + y0;
+        const uint16_t* eR0 = r.ecol + ((size_t)(celldesc[scell + 1] * 2 + 1) * 3 + c0) * r.OH + y0;
+        const int a0 = r.taps.xa0[dx], a1 = r.taps.xa1[dx];
+        const uint32_t keep = ~(0xffu << sh);
+        for (int cc = 0; cc < nc; ++cc) {
+            const uint32_t* pA = (const uint32_t*)sA.base + w0 + cc * PW;
+            const uint32_t* pB = (const uint32_t*)sB.base + w0 + cc * PW;
+            uint32_t* dst = fb + w0 + cc * PW;
+            const uint16_t* eL = eL0 + cc * r.OH;
+            const uint16_t* eR = eR0 + cc * r.OH;
+            const uint32_t* yb = x.yb + y0;
+            for (int i0 = 0; i0 < nrows; i0 += 4, pA += 4 * WR, pB += 4 * WR, dst += 4 * WR, eL += 4, eR += 4, yb += 4) {
+                uint32_t va[4], vb[4], tl[4], tr[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { va[j] = pA[j * WR]; vb[j] = pB[j * WR]; tl[j] = eL[j]; tr[j] = eR[j]; }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (i0 + j < nrows) {
+                        const uint32_t b = yb[j];
+                        const uint32_t v = xw_resize_px(tl[j] & 255, tr[j] & 255, tl[j] >> 8, tr[j] >> 8, a0, a1, b & 0xffff, b >> 16);
+                        dst[j * WR] = ((xw_prmt(va[j], vb[j], sel) | wmask) & keep) | (v << sh);
+                    }
+            }
+        }
+        return;
+    }
+    // R: one word of straddling row q: out = (U[top cell] + V[bottom cell] + 2) >> 2
+    const int q = e.w & 0xff, k = (e.w >> 8) & 0xff;
+    const bool corner = (e.w >> 31) != 0;
+    const size_t per_desc = (size_t)r.n_sr * 2 * 3 * r.OW;
+    const uint16_t* u0 = r.uv + ((size_t)q * 2 * 3 + c0) * r.OW + 4 * k;
+    const uint16_t* v0 = u0 + (size_t)3 * r.OW;
+    const uint16_t *uAp = u0 + celldesc[cellA] * per_desc, *uBp = u0 + celldesc[cellB] * per_desc;
+    const uint16_t *vAp = v0 + celldesc[cellA + r.W] * per_desc, *vBp = v0 + celldesc[cellB + r.W] * per_desc;
+    XwU2 uA[3], uB[3], vA[3], vB[3];
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc)
+        if (cc < nc) {
+            uA[cc] = *(const XwU2*)(uAp + cc * r.OW); uB[cc] = *(const XwU2*)(uBp + cc * r.OW);
+            vA[cc] = *(const XwU2*)(vAp + cc * r.OW); vB[cc] = *(const XwU2*)(vBp + cc * r.OW);
+        }
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc)
+        if (cc < nc) {
+            // packed u16 pairs: no carry between halves (U + V + 2 <= 2042)
+            const uint32_t a_lo = ((uA[cc].x + vA[cc].x + 0x00020002u) >> 2) & 0x00ff00ffu, a_hi = ((uA[cc].y + vA[cc].y + 0x00020002u) >> 2) & 0x00ff00ffu;
+            const uint32_t b_lo = ((uB[cc].x + vB[cc].x + 0x00020002u) >> 2) & 0x00ff00ffu, b_hi = ((uB[cc].y + vB[cc].y + 0x00020002u) >> 2) & 0x00ff00ffu;
+            uint32_t word = xw_prmt(xw_prmt(a_lo, a_hi, 0x6420), xw_prmt(b_lo, b_hi, 0x6420), sel);
+            if (corner) {  // taps: (63,63) of the top-left cell, (63,0) top-right, (0,63) bottom-left, (0,0) bottom-right
+                const int c = c0 + cc;
+                const uint32_t t00 = r.corner[celldesc[scell] * 3 + c], t01 = r.corner[celldesc[scell + 1] * 3 + c];
+                const uint32_t t10 = r.corner[celldesc[scell + r.W] * 3 + c], t11 = r.corner[celldesc[scell + r.W + 1] * 3 + c];
+                const uint32_t b = x.yb[y0];
+                const uint32_t v = xw_resize_px(t00 & 255, (t01 >> 8) & 255, (t10 >> 16) & 255, t11 >> 24, r.taps.xa0[dx], r.taps.xa1[dx],
+                                                b & 0xffff, b >> 16);
+                word = (word & ~(0xffu << sh)) | (v << sh);
+            }
+            fb[w0 + cc * PW] = word;
+        }
 }
 
 // celldesc for one cell: grid code -> icon + 1
@@ -224,17 +271,16 @@ XW_HD uint32_t xw_cell_desc(const XwDev& d, int e, int code) {
 }
 
 // Dynamic shared memory layout (bytes), all sections 16-byte aligned:
-//   brick phase table (TMA bulk load, once) | G frame buffers | plan | aux | yb | G cell arrays | mbarrier
+//   brick phase table (TMA bulk load, once) | G frame buffers | plan | yb | G cell arrays | mbarrier
 #define XW_CELL_STRIDE (XW_MAX_DIM * XW_MAX_DIM + XW_MAX_DIM + 2)  // + the (never drawn) row below the map
-struct XwRenderSmem { int hot, fb, plan, aux, yb, cell, bar, total; };
+struct XwRenderSmem { int hot, fb, plan, yb, cell, bar, total; };
 XW_HD int xw_align16(int v) { return (v + 15) & ~15; }
 XW_HD XwRenderSmem xw_render_smem(const XwRender& r, int G) {
     XwRenderSmem s;
     int o = 0;
     s.hot = o; o += xw_align16(r.FB);
     s.fb = o; o += G * xw_align16(r.FB);
-    s.plan = o; o += xw_align16(r.n_plan * 8);
-    s.aux = o; o += xw_align16(r.n_aux * 8 + 8);
+    s.plan = o; o += r.n_plan * 16;
     s.yb = o; o += xw_align16(r.OH * 4);
     s.cell = o; o += G * XW_CELL_STRIDE * 4;
     s.bar = o; o += 16;
@@ -254,8 +300,12 @@ __global__ void k_build_phase_atlas(XwRender r) {
 }
 __global__ void k_build_edge_tables(XwRender r) {
     const size_t n_ecol = (size_t)(r.n_icons + 1) * 2 * 3 * r.OH, n_uv = (size_t)(r.n_icons + 1) * r.n_sr * 2 * 3 * r.OW;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_ecol + n_uv; i += (size_t)gridDim.x * blockDim.x) {
-        if (i < n_ecol) {
+    const size_t n_cor = (size_t)(r.n_icons + 1) * 3;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_ecol + n_uv + n_cor; i += (size_t)gridDim.x * blockDim.x) {
+        if (i >= n_ecol + n_uv) {
+            const size_t j = i - n_ecol - n_uv;
+            ((uint32_t*)r.corner)[j] = xw_corner_entry(r, (uint32_t)(j / 3), (int)(j % 3));
+        } else if (i < n_ecol) {
             size_t j = i;
             const int dy = (int)(j % r.OH); j /= r.OH;
             const int c = (int)(j % 3); j /= 3;
@@ -309,15 +359,14 @@ __device__ __forceinline__ void group_bar(int id, int nthreads) {
 
 // Persistent CTAs.  Group g of CTA b renders envs (b*G + g) + i * gridDim.x*G; the frame of env e goes
 // to frames + e*env_stride.
-template <int WR_T>
-__global__ void __launch_bounds__(XW_RENDER_THREADS, 1)
+template <int WR_T, int NT_MAX>
+__global__ void __launch_bounds__(NT_MAX, 1)
 k_render(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int G = r.G, GT = r.GT;
     const XwRenderSmem L = xw_render_smem(r, G);
     uint8_t* hot = smem + L.hot;
-    XwU2* s_plan = (XwU2*)(smem + L.plan);
-    XwU2* s_aux = (XwU2*)(smem + L.aux);
+    XwU4* s_plan = (XwU4*)(smem + L.plan);
     uint32_t* s_yb = (uint32_t*)(smem + L.yb);
     uint64_t* bar = (uint64_t*)(smem + L.bar);
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -334,7 +383,6 @@ k_render(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
     }
     {  // plan + row weights -> shared memory
         for (int i = tid; i < r.n_plan; i += nt) s_plan[i] = r.plan[i];
-        for (int i = tid; i < r.n_aux; i += nt) s_aux[i] = r.aux[i];
         for (int i = tid; i < r.OH; i += nt) s_yb[i] = (uint32_t)(uint16_t)r.taps.ya0[i] | ((uint32_t)(uint16_t)r.taps.ya1[i] << 16);
     }
     mbar_wait(bar, 0);
@@ -370,7 +418,7 @@ k_render(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
                 if (gt + GT < HW) nd1 = xw_cell_desc(d, en, d.grid[(size_t)en * d.CS + gt + GT]);
             }
         }
-        for (int i = gt; i < n_plan; i += GT) xw_compose_item<WR_T>(r, x, s_plan[i], s_aux, i, s_cell, fb);
+        for (int i = gt; i < n_plan; i += GT) xw_compose_item<WR_T>(r, x, s_plan[i], s_cell, fb);
         fence_async_smem();  // generic-proxy writes -> visible to the async (TMA) proxy
         group_bar(bar_id, GT);
         if (gt == 0) {

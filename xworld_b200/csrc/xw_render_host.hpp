@@ -7,35 +7,46 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <algorithm>
+#include <utility>
 #include <vector>
 
-// One compositor work item = one 4-pixel word column of one colour plane over a run of rows.  Items are
-// typed so that a warp executes one code path (the plan lists them sorted by type, planes expanded):
+// One compositor work item = one 4-pixel word column over a run of rows, in nc consecutive colour
+// planes.  Items are typed so that a warp executes one code path:
 //   M1  rows of a band (cell row), word inside ONE cell:            word = table(A)
 //   M2  rows of a band, word spanning two cells:                    word = PRMT(table(A), table(B))
 //   M3  like M2, and one byte lies on a straddling column (its two tap columns are in different
 //       cells): that byte is evaluated exactly from the cells' edge-tap tables
-//   R   one word of a straddling row (tap rows in different cell rows): separable U(top)+V(bottom) rule
-//   RC  like R, and one byte is a corner (straddling row x straddling column): exact from the atlas
+//   R   one word of a straddling row (tap rows in different cell rows): separable U(top)+V(bottom)
+//       rule; if the word also holds a corner (straddling row x column) that byte comes from the
+//       four cells' corner taps
 // The M items of a band exclude the band's straddling last row, so every frame word has one writer.
-enum { XW_ITEM_M1 = 0, XW_ITEM_M2 = 1, XW_ITEM_M3 = 2, XW_ITEM_R = 3, XW_ITEM_RC = 4, XW_ITEM_TYPES = 5 };
+enum { XW_ITEM_M1 = 0, XW_ITEM_M2 = 1, XW_ITEM_M3 = 2, XW_ITEM_R = 3, XW_ITEM_TYPES = 4 };
 
-// Packed plan entry (one LDS.64):
-//   x = cellA | cellB << 8 | sel << 16        cell indices ty*W + tx owning the word's first / last byte
-//                                             (top cell row for R/RC), PRMT selector merging word(A), word(B)
-//   y = woff | nrows << 16 | type << 24 | c << 27     word offset of the first row in the FRAME, rows, plane
-// Items of type >= M3 also have an aux entry (index = plan index - seg[M3]):
-//   x = y0 | dx << 8 | scell << 16 | sbyte << 24     first row; the straddling column, its left cell
-//                                                    (the right one is scell + 1), its byte in the word
-//   y = q | k << 8                                   R/RC: index of the straddling row; word column
+// Packed plan entry (one LDS.128):
+//   x = cellA | cellB << 8 | sel << 16     cell indices ty*W + tx owning the word's first / last byte
+//                                          (top cell row for R), PRMT selector merging word(A), word(B)
+//   y = woff | nrows << 16 | type << 24 | c0 << 27 | nc << 29
+//                                          word offset of the first row in the FRAME (plane c0), rows,
+//                                          first plane, number of planes (0 = padding slot)
+//   z = y0 | dx << 8 | scell << 16 | sbyte << 24    first row; M3 / R-with-corner: the straddling column,
+//                                          its left cell (the right one is scell + 1), its byte in the word
+//   w = q | k << 8 | corner << 31          R: index of the straddling row, word column, corner flag
+// The plan is a sequence of 32-slot bundles of one type; bundle b belongs to warp b % n_warps of a
+// warp group, and the host orders bundles so that the warps of a group finish together (LPT).
+struct alignas(16) XwU4 { uint32_t x, y, z, w; };
 struct alignas(8) XwU2 { uint32_t x, y; };
+
+struct XwPlanItem { int cellA, cellB, sel, woff, nrows, type, y0, k, sbyte, scell, dx, q, corner; };
 
 struct XwRenderTables {
     int H = 0, W = 0, OH = 0, OW = 0, WR = 0, FB = 0;
     bool fast_ok = false;  // the shared-memory compositor applies (else: generic kernel)
     std::vector<int16_t> xofs, xa0, xa1, yofs, ya0, ya1, sc, sr;
-    std::vector<XwU2> plan, aux;         // plan sorted by type; aux for plan[seg[M3]..]
-    int seg[XW_ITEM_TYPES + 1] = {0};    // items of type t are plan[seg[t] .. seg[t+1])
+    std::vector<XwPlanItem> items;       // per-plane items (planner input)
+    std::vector<XwU4> plan;              // bundled plan for n_warps warps per group
+    int n_warps = 0;
+    double makespan = 0, total_cost = 0; // planner's cost model (instructions per env): slowest warp, sum
 };
 
 inline void xw_resize_tables(int src, int dst, int16_t* ofs, int16_t* a0, int16_t* a1) {
@@ -75,8 +86,6 @@ inline XwRenderTables xw_build_render_tables(int H, int W, int OH, int OW) {
     }
     if (!ok) return t;
     t.WR = OW / 4;
-    struct Item { int cellA, cellB, sel, woff, nrows, type, y0, k, sbyte, scell, dx, q; };
-    std::vector<Item> all;
     for (int ty = 0; ty < H && ok; ++ty) {
         int y0 = -1, y1 = -1;  // rows owned by cell row ty
         for (int dy = 0; dy < OH; ++dy)
@@ -86,7 +95,7 @@ inline XwRenderTables xw_build_render_tables(int H, int W, int OH, int OW) {
         int q = 0;
         if (srow) while (t.sr[q] != y1 - 1) ++q;
         for (int k = 0; k < t.WR && ok; ++k) {
-            Item it;
+            XwPlanItem it;
             memset(&it, 0, sizeof it);
             int tx[4];
             for (int i = 0; i < 4; ++i) tx[i] = t.xofs[4 * k + i] >> 6;
@@ -104,34 +113,88 @@ inline XwRenderTables xw_build_render_tables(int H, int W, int OH, int OW) {
             it.nrows = y1 - y0 - (srow ? 1 : 0);
             it.y0 = y0; it.k = k;
             it.type = n_sc ? XW_ITEM_M3 : (A != B ? XW_ITEM_M2 : XW_ITEM_M1);
-            if (it.nrows > 0) all.push_back(it);
+            if (it.nrows > 0) t.items.push_back(it);
             if (srow) {
-                Item r = it;
+                XwPlanItem r = it;
                 r.woff = (y1 - 1) * t.WR + k;
                 r.nrows = 1; r.y0 = y1 - 1; r.q = q;
-                r.type = n_sc ? XW_ITEM_RC : XW_ITEM_R;
-                all.push_back(r);
+                r.type = XW_ITEM_R; r.corner = n_sc ? 1 : 0;
+                t.items.push_back(r);
             }
         }
     }
     if (3 * OH * t.WR > 65535) ok = false;  // woff is 16 bits
-    for (int ty = 0; ty < XW_ITEM_TYPES && ok; ++ty) {
-        t.seg[ty] = (int)t.plan.size();
-        for (int c = 0; c < 3; ++c)
-            for (const Item& it : all) {
-                if (it.type != ty) continue;
-                XwU2 e, a;
-                e.x = (uint32_t)it.cellA | ((uint32_t)it.cellB << 8) | ((uint32_t)it.sel << 16);
-                e.y = (uint32_t)(c * OH * t.WR + it.woff) | ((uint32_t)it.nrows << 16) | ((uint32_t)it.type << 24) | ((uint32_t)c << 27);
-                t.plan.push_back(e);
-                if (ty >= XW_ITEM_M3) {
-                    a.x = (uint32_t)it.y0 | ((uint32_t)it.dx << 8) | ((uint32_t)it.scell << 16) | ((uint32_t)it.sbyte << 24);
-                    a.y = (uint32_t)it.q | ((uint32_t)it.k << 8);
-                    t.aux.push_back(a);
-                }
-            }
-    }
-    t.seg[XW_ITEM_TYPES] = (int)t.plan.size();
     t.fast_ok = ok;
     return t;
+}
+
+// Cost model of one item (instructions), calibrated on ncu source counters (profiles/).
+inline double xw_item_cost(const XwPlanItem& it, int nc) {
+    switch (it.type) {
+        case XW_ITEM_M1: return 60 + nc * (8 + it.nrows * 5.3);
+        case XW_ITEM_M2: return 75 + nc * (8 + it.nrows * 8.0);
+        case XW_ITEM_M3: return 110 + nc * (12 + it.nrows * 30.0);
+        default: return 90 + nc * (45.0 + (it.corner ? 45.0 : 0.0));
+    }
+}
+
+// Bundle the items for groups of n_warps warps.  split_m3: M3 items per plane (three times the
+// items, a third of the rows each) instead of one item for the three planes.
+inline void xw_build_plan(XwRenderTables& t, int n_warps, bool split_m3) {
+    struct Bundle { std::vector<XwU4> slots; double cost; };
+    std::vector<Bundle> bundles;
+    const int PW = t.OH * t.WR;
+    for (int ty = 0; ty < XW_ITEM_TYPES; ++ty) {
+        std::vector<std::pair<XwPlanItem, int>> v;  // (item, first plane), nc implied
+        const bool per_plane = (ty == XW_ITEM_M3 && split_m3);
+        for (const XwPlanItem& it : t.items) {
+            if (it.type != ty) continue;
+            if (per_plane) for (int c = 0; c < 3; ++c) v.push_back({it, c});
+            else v.push_back({it, 0});
+        }
+        const int nc = per_plane ? 1 : 3;
+        std::stable_sort(v.begin(), v.end(), [&](const std::pair<XwPlanItem, int>& a, const std::pair<XwPlanItem, int>& b) {
+            return xw_item_cost(a.first, nc) > xw_item_cost(b.first, nc);
+        });
+        for (size_t i = 0; i < v.size(); i += 32) {
+            Bundle b;
+            b.cost = 0;
+            for (size_t j = i; j < i + 32; ++j) {
+                XwU4 e = {0, 0, 0, 0};
+                e.y = (uint32_t)ty << 24;  // padding slot: nc = 0
+                if (j < v.size()) {
+                    const XwPlanItem& it = v[j].first;
+                    const int c0 = v[j].second;
+                    e.x = (uint32_t)it.cellA | ((uint32_t)it.cellB << 8) | ((uint32_t)it.sel << 16);
+                    e.y = (uint32_t)(c0 * PW + it.woff) | ((uint32_t)it.nrows << 16) | ((uint32_t)ty << 24) | ((uint32_t)c0 << 27) | ((uint32_t)nc << 29);
+                    e.z = (uint32_t)it.y0 | ((uint32_t)it.dx << 8) | ((uint32_t)it.scell << 16) | ((uint32_t)it.sbyte << 24);
+                    e.w = (uint32_t)it.q | ((uint32_t)it.k << 8) | ((uint32_t)it.corner << 31);
+                    const double c = xw_item_cost(it, nc);
+                    if (c > b.cost) b.cost = c;
+                }
+                b.slots.push_back(e);
+            }
+            bundles.push_back(b);
+        }
+    }
+    // longest-processing-time-first assignment of bundles to the warps of a group
+    std::stable_sort(bundles.begin(), bundles.end(), [](const Bundle& a, const Bundle& b) { return a.cost > b.cost; });
+    std::vector<std::vector<int>> mine(n_warps);
+    std::vector<double> load(n_warps, 0.0);
+    t.total_cost = 0;
+    for (size_t b = 0; b < bundles.size(); ++b) {
+        int w = 0;
+        for (int i = 1; i < n_warps; ++i) if (load[i] < load[w]) w = i;
+        mine[w].push_back((int)b);
+        load[w] += bundles[b].cost;
+        t.total_cost += bundles[b].cost;
+    }
+    size_t rounds = 0;
+    t.makespan = 0;
+    for (int w = 0; w < n_warps; ++w) { if (mine[w].size() > rounds) rounds = mine[w].size(); if (load[w] > t.makespan) t.makespan = load[w]; }
+    t.plan.assign(rounds * n_warps * 32, XwU4{0, 0, 0, 0});
+    for (int w = 0; w < n_warps; ++w)
+        for (size_t j = 0; j < mine[w].size(); ++j)
+            for (int l = 0; l < 32; ++l) t.plan[(j * n_warps + w) * 32 + l] = bundles[mine[w][j]].slots[l];
+    t.n_warps = n_warps;
 }
