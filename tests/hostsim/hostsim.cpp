@@ -158,23 +158,28 @@ void hs_step(HostSim* s, const int32_t* actions, int act_rep, float* reward, int
 void hs_render(HostSim* s, uint8_t* frames) {
     XwRender& r = s->r;
     XwDev& d = s->d;
-    std::vector<uint32_t> cell(XW_CELL_STRIDE, 0), fb(r.FB / 4 + 4), yb(r.OH);
+    std::vector<uint32_t> fb(r.FB / 4 + 4), yb(r.OH);
+    std::vector<uint8_t> code(XW_CELL_STRIDE, 0);
+    uint32_t icon[XW_CODE_SLOTS];
     for (int i = 0; i < r.OH; ++i) yb[i] = (uint32_t)(uint16_t)r.taps.ya0[i] | ((uint32_t)(uint16_t)r.taps.ya1[i] << 16);
     XwComposeCtx x;
     x.hot = r.T + (size_t)r.brick_icon * r.FB; x.yb = yb.data();
+    XwCells cells;
+    cells.code = code.data(); cells.icon = icon;
     for (int e = 0; e < d.n; ++e) {
-        for (int c = 0; c < d.H * d.W; ++c) cell[c] = xw_cell_desc(d, e, d.grid[(size_t)e * d.CS + c]);
+        memcpy(code.data(), d.grid + (size_t)e * d.CS, d.CS);
+        for (int k = 0; k < XW_CODE_SLOTS; ++k) icon[k] = k < XW_CELL_GOAL0 + d.G ? xw_cell_desc(d, e, k) : 0;
         if (s->tab.fast_ok) {
             std::fill(fb.begin(), fb.end(), 0x5a5a5a5au);
             for (int i = 0; i < r.n_plan; ++i) {  // the test alternates the compile-time and run-time row stride
-                if (r.WR == 21 && (e & 1)) xw_compose_item<21>(r, x, r.plan[i], cell.data(), fb.data());
-                else xw_compose_item<0>(r, x, r.plan[i], cell.data(), fb.data());
+                if (r.WR == 21 && (e & 1)) xw_compose_item<21>(r, x, r.plan[i], cells, fb.data());
+                else xw_compose_item<0>(r, x, r.plan[i], cells, fb.data());
             }
             memcpy(frames + (size_t)e * r.FB, fb.data(), r.FB);
         } else {
             for (int i = 0; i < r.FB; ++i) {
                 const int c = i / (r.OH * r.OW), p = i % (r.OH * r.OW);
-                frames[(size_t)e * r.FB + i] = xw_exact_px(r, cell.data(), c, p / r.OW, p % r.OW);
+                frames[(size_t)e * r.FB + i] = xw_exact_px(r, cells, c, p / r.OW, p % r.OW);
             }
         }
     }

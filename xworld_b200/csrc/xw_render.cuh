@@ -61,6 +61,15 @@ XW_HD uint8_t xw_resize_px(int p00, int p01, int p10, int p11, int a0, int a1, i
     return (uint8_t)((xw_vterm(p00, p01, a0, a1, b0) + xw_vterm(p10, p11, a0, a1, b1) + 2) >> 2);
 }
 
+// The cells of one env as the compositor reads them: the grid's cell codes (one byte per cell, so a
+// whole 16x16 map spans 64 banks' worth of words at most twice -- lookups rarely conflict) and the
+// descriptor (0 = white, icon + 1) each code stands for in this env.
+struct XwCells {
+    const uint8_t* code;    // [XW_CELL_STRIDE] XW_CELL_* per cell; zero past the map
+    const uint32_t* icon;   // [XW_CELL_GOAL0 + XW_MAX_GOALS] descriptor per code
+    XW_HD uint32_t operator()(int cell) const { return icon[code[cell]]; }
+};
+
 // One tap of the virtual canvas: cell descriptor (icon+1, 0 = empty = white) -> pixel.
 XW_HD int xw_canvas_tap(const XwRender& r, uint32_t dsc, int sy, int sx, int c) {
     if (dsc == 0) return 255;
@@ -101,13 +110,13 @@ XW_HD uint32_t xw_corner_entry(const XwRender& r, uint32_t dsc, int c) {
 }
 
 // Value of output pixel (c,dy,dx) on the real canvas, from the 64-px atlas (any four cells).
-XW_HD uint8_t xw_exact_px(const XwRender& r, const uint32_t* celldesc, int c, int dy, int dx) {
+XW_HD uint8_t xw_exact_px(const XwRender& r, const XwCells& celldesc, int c, int dy, int dx) {
     const XwTaps& t = r.taps;
     int sx0 = t.xofs[dx], sy0 = t.yofs[dy];
     int a1 = t.xa1[dx], b1 = t.ya1[dy];
     int sx1 = a1 ? sx0 + 1 : sx0, sy1 = b1 ? sy0 + 1 : sy0;
-    uint32_t d00 = celldesc[(sy0 >> 6) * r.W + (sx0 >> 6)], d01 = celldesc[(sy0 >> 6) * r.W + (sx1 >> 6)];
-    uint32_t d10 = celldesc[(sy1 >> 6) * r.W + (sx0 >> 6)], d11 = celldesc[(sy1 >> 6) * r.W + (sx1 >> 6)];
+    uint32_t d00 = celldesc((sy0 >> 6) * r.W + (sx0 >> 6)), d01 = celldesc((sy0 >> 6) * r.W + (sx1 >> 6));
+    uint32_t d10 = celldesc((sy1 >> 6) * r.W + (sx0 >> 6)), d11 = celldesc((sy1 >> 6) * r.W + (sx1 >> 6));
     return xw_resize_px(xw_canvas_tap(r, d00, sy0, sx0, c), xw_canvas_tap(r, d01, sy0, sx1, c),
                         xw_canvas_tap(r, d10, sy1, sx0, c), xw_canvas_tap(r, d11, sy1, sx1, c),
                         t.xa0[dx], a1, t.ya0[dy], b1);
@@ -145,7 +154,7 @@ XW_HD XwSrc xw_src_of(const XwRender& r, const XwComposeCtx& x, uint32_t dsc) {
 // Rows go four at a time, all loads before the stores: the tables and the frame buffer may alias as
 // far as the compiler knows, and a load-store-load chain would expose one memory latency per row.
 template <int WR_T>
-XW_HD void xw_compose_item(const XwRender& r, const XwComposeCtx& x, const XwU4 e, const uint32_t* celldesc, uint32_t* fb) {
+XW_HD void xw_compose_item(const XwRender& r, const XwComposeCtx& x, const XwU4 e, const XwCells& celldesc, uint32_t* fb) {
     const int WR = WR_T ? WR_T : r.WR;
     const int PW = r.OH * WR;  // words per plane
     const int type = (e.y >> 24) & 7, nrows = (e.y >> 16) & 0xff, nc = e.y >> 29;
@@ -157,7 +166,7 @@ XW_HD void xw_compose_item(const XwRender& r, const XwComposeCtx& x, const XwU4 
     // padded by XW_TABLE_PAD) -- and only the stores are predicated, one predicate per row.
     if (nc == 0) return;  // padding slot
     if (type == XW_ITEM_M1) {
-        const XwSrc sA = xw_src_of(r, x, celldesc[cellA]);
+        const XwSrc sA = xw_src_of(r, x, celldesc(cellA));
         const uint32_t* pA = (const uint32_t*)sA.base + w0;
         uint32_t* dst = fb + w0;
         for (int i0 = 0; i0 < nrows; i0 += 8, pA += 8 * WR, dst += 8 * WR) {
@@ -176,7 +185,7 @@ XW_HD void xw_compose_item(const XwRender& r, const XwComposeCtx& x, const XwU4 
         return;
     }
     if (type == XW_ITEM_M2) {
-        const XwSrc sA = xw_src_of(r, x, celldesc[cellA]), sB = xw_src_of(r, x, celldesc[cellB]);
+        const XwSrc sA = xw_src_of(r, x, celldesc(cellA)), sB = xw_src_of(r, x, celldesc(cellB));
         const uint32_t wmask = xw_prmt(sA.wmask, sB.wmask, sel);
         const uint32_t* pA = (const uint32_t*)sA.base + w0;
         const uint32_t* pB = (const uint32_t*)sB.base + w0;
@@ -199,10 +208,10 @@ XW_HD void xw_compose_item(const XwRender& r, const XwComposeCtx& x, const XwU4 
     const int c0 = (e.y >> 27) & 3;
     const int y0 = e.z & 0xff, dx = (e.z >> 8) & 0xff, scell = (e.z >> 16) & 0xff, sh = (e.z >> 24) * 8;
     if (type == XW_ITEM_M3) {
-        const XwSrc sA = xw_src_of(r, x, celldesc[cellA]), sB = xw_src_of(r, x, celldesc[cellB]);
+        const XwSrc sA = xw_src_of(r, x, celldesc(cellA)), sB = xw_src_of(r, x, celldesc(cellB));
         const uint32_t wmask = xw_prmt(sA.wmask, sB.wmask, sel);
-        const uint16_t* eL0 = r.ecol + ((size_t)(celldesc[scell] * 2 + 0) * 3 + c0) * r.OH + y0;
-        const uint16_t* eR0 = r.ecol + ((size_t)(celldesc[scell + 1] * 2 + 1) * 3 + c0) * r.OH + y0;
+        const uint16_t* eL0 = r.ecol + ((size_t)(celldesc(scell) * 2 + 0) * 3 + c0) * r.OH + y0;
+        const uint16_t* eR0 = r.ecol + ((size_t)(celldesc(scell + 1) * 2 + 1) * 3 + c0) * r.OH + y0;
         const int a0 = r.taps.xa0[dx], a1 = r.taps.xa1[dx];
         const uint32_t keep = ~(0xffu << sh);
         for (int cc = 0; cc < nc; ++cc) {
@@ -233,8 +242,8 @@ XW_HD void xw_compose_item(const XwRender& r, const XwComposeCtx& x, const XwU4 
     const size_t per_desc = (size_t)r.n_sr * 2 * 3 * r.OW;
     const uint16_t* u0 = r.uv + ((size_t)q * 2 * 3 + c0) * r.OW + 4 * k;
     const uint16_t* v0 = u0 + (size_t)3 * r.OW;
-    const uint16_t *uAp = u0 + celldesc[cellA] * per_desc, *uBp = u0 + celldesc[cellB] * per_desc;
-    const uint16_t *vAp = v0 + celldesc[cellA + r.W] * per_desc, *vBp = v0 + celldesc[cellB + r.W] * per_desc;
+    const uint16_t *uAp = u0 + celldesc(cellA) * per_desc, *uBp = u0 + celldesc(cellB) * per_desc;
+    const uint16_t *vAp = v0 + celldesc(cellA + r.W) * per_desc, *vBp = v0 + celldesc(cellB + r.W) * per_desc;
     XwU2 uA[3], uB[3], vA[3], vB[3];
 #pragma unroll
     for (int cc = 0; cc < 3; ++cc)
@@ -251,8 +260,8 @@ XW_HD void xw_compose_item(const XwRender& r, const XwComposeCtx& x, const XwU4 
             uint32_t word = xw_prmt(xw_prmt(a_lo, a_hi, 0x6420), xw_prmt(b_lo, b_hi, 0x6420), sel);
             if (corner) {  // taps: (63,63) of the top-left cell, (63,0) top-right, (0,63) bottom-left, (0,0) bottom-right
                 const int c = c0 + cc;
-                const uint32_t t00 = r.corner[celldesc[scell] * 3 + c], t01 = r.corner[celldesc[scell + 1] * 3 + c];
-                const uint32_t t10 = r.corner[celldesc[scell + r.W] * 3 + c], t11 = r.corner[celldesc[scell + r.W + 1] * 3 + c];
+                const uint32_t t00 = r.corner[celldesc(scell) * 3 + c], t01 = r.corner[celldesc(scell + 1) * 3 + c];
+                const uint32_t t10 = r.corner[celldesc(scell + r.W) * 3 + c], t11 = r.corner[celldesc(scell + r.W + 1) * 3 + c];
                 const uint32_t b = x.yb[y0];
                 const uint32_t v = xw_resize_px(t00 & 255, (t01 >> 8) & 255, (t10 >> 16) & 255, t11 >> 24, r.taps.xa0[dx], r.taps.xa1[dx],
                                                 b & 0xffff, b >> 16);
@@ -262,17 +271,18 @@ XW_HD void xw_compose_item(const XwRender& r, const XwComposeCtx& x, const XwU4 
         }
 }
 
-// celldesc for one cell: grid code -> icon + 1
+// descriptor of a grid code in env e: grid code -> icon + 1
 XW_HD uint32_t xw_cell_desc(const XwDev& d, int e, int code) {
     if (code == XW_CELL_EMPTY) return 0;
     if (code == XW_CELL_BLOCK) return (uint32_t)d.brick_icon + 1;
     if (code == XW_CELL_AGENT) return (uint32_t)d.agent_icon + 1;
     return (uint32_t)d.goal_icon[(size_t)(code - XW_CELL_GOAL0) * d.n + e] + 1;
 }
+#define XW_CODE_SLOTS (XW_CELL_GOAL0 + XW_MAX_GOALS + 5)  // 16 descriptors per env
 
 // Dynamic shared memory layout (bytes), all sections 16-byte aligned:
 //   brick phase table (TMA bulk load, once) | G frame buffers | plan | yb | G cell arrays | mbarrier
-#define XW_CELL_STRIDE (XW_MAX_DIM * XW_MAX_DIM + XW_MAX_DIM + 2)  // + the (never drawn) row below the map
+#define XW_CELL_STRIDE (XW_MAX_DIM * XW_MAX_DIM + 2 * XW_MAX_DIM)  // bytes: the map + the (never drawn) row below it
 struct XwRenderSmem { int hot, fb, plan, yb, cell, bar, total; };
 XW_HD int xw_align16(int v) { return (v + 15) & ~15; }
 XW_HD XwRenderSmem xw_render_smem(const XwRender& r, int G) {
@@ -282,7 +292,7 @@ XW_HD XwRenderSmem xw_render_smem(const XwRender& r, int G) {
     s.fb = o; o += G * xw_align16(r.FB);
     s.plan = o; o += r.n_plan * 16;
     s.yb = o; o += xw_align16(r.OH * 4);
-    s.cell = o; o += G * XW_CELL_STRIDE * 4;
+    s.cell = o; o += G * (XW_CELL_STRIDE + XW_CODE_SLOTS * 4);
     s.bar = o; o += 16;
     s.total = o;
     return s;
@@ -390,35 +400,40 @@ k_render(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
 
     const int g = tid / GT, gt = tid - g * GT;
     if (g >= G) return;  // spare warps (G*GT < blockDim.x)
-    uint32_t* s_cell = (uint32_t*)(smem + L.cell) + g * XW_CELL_STRIDE;
+    uint8_t* s_code = smem + L.cell + g * (XW_CELL_STRIDE + XW_CODE_SLOTS * 4);
+    uint32_t* s_icon = (uint32_t*)(s_code + XW_CELL_STRIDE);
     uint32_t* fb = (uint32_t*)(smem + L.fb + (size_t)g * xw_align16(r.FB));
     XwComposeCtx x;
     x.hot = hot; x.yb = s_yb;
+    XwCells cells;
+    cells.code = s_code; cells.icon = s_icon;
     const int bar_id = 1 + g;
     const int n_plan = r.n_plan;
     const int gstride = gridDim.x * G;
     int env = blockIdx.x * G + g;
 
-    // register prefetch of the env's cell descriptors (HW <= 2*GT)
-    uint32_t nd0 = 0, nd1 = 0;
+    // register prefetch of the env's grid row (CS bytes = CS/4 words, CS/4 <= 64 <= GT) and goal icons
+    const int row_words = d.CS >> 2;
+    uint32_t nq = 0, ni = 0;
     if (env < d.n) {
-        if (gt < HW) nd0 = xw_cell_desc(d, env, d.grid[(size_t)env * d.CS + gt]);
-        if (gt + GT < HW) nd1 = xw_cell_desc(d, env, d.grid[(size_t)env * d.CS + gt + GT]);
+        if (gt < row_words) nq = ((const uint32_t*)(d.grid + (size_t)env * d.CS))[gt];
+        if (gt < d.G) ni = (uint32_t)d.goal_icon[(size_t)gt * d.n + env] + 1;
     }
-    for (int i = HW + gt; i < XW_CELL_STRIDE; i += GT) s_cell[i] = 0;
+    for (int i = gt; i < XW_CELL_STRIDE / 4; i += GT) ((uint32_t*)s_code)[i] = 0;
+    if (gt < XW_CODE_SLOTS) s_icon[gt] = gt == XW_CELL_BLOCK ? (uint32_t)d.brick_icon + 1 : gt == XW_CELL_AGENT ? (uint32_t)d.agent_icon + 1 : 0;
     for (; env < d.n; env += gstride) {
-        if (gt < HW) s_cell[gt] = nd0;
-        if (gt + GT < HW) s_cell[gt + GT] = nd1;
+        if (gt < row_words) ((uint32_t*)s_code)[gt] = nq;  // (every warp passed the barrier after the last compose)
+        if (gt < d.G) s_icon[XW_CELL_GOAL0 + gt] = ni;
         if (gt == 0) tma_wait_read<0>();  // the TMA store of this group's previous frame has drained fb
         group_bar(bar_id, GT);
         {  // prefetch the next env's cells while this one is composed
             const int en = env + gstride;
             if (en < d.n) {
-                if (gt < HW) nd0 = xw_cell_desc(d, en, d.grid[(size_t)en * d.CS + gt]);
-                if (gt + GT < HW) nd1 = xw_cell_desc(d, en, d.grid[(size_t)en * d.CS + gt + GT]);
+                if (gt < row_words) nq = ((const uint32_t*)(d.grid + (size_t)en * d.CS))[gt];
+                if (gt < d.G) ni = (uint32_t)d.goal_icon[(size_t)gt * d.n + en] + 1;
             }
         }
-        for (int i = gt; i < n_plan; i += GT) xw_compose_item<WR_T>(r, x, s_plan[i], s_cell, fb);
+        for (int i = gt; i < n_plan; i += GT) xw_compose_item<WR_T>(r, x, s_plan[i], cells, fb);
         fence_async_smem();  // generic-proxy writes -> visible to the async (TMA) proxy
         group_bar(bar_id, GT);
         if (gt == 0) {

@@ -156,25 +156,36 @@ inline void xw_build_plan(XwRenderTables& t, int n_warps, bool split_m3) {
         std::stable_sort(v.begin(), v.end(), [&](const std::pair<XwPlanItem, int>& a, const std::pair<XwPlanItem, int>& b) {
             return xw_item_cost(a.first, nc) > xw_item_cost(b.first, nc);
         });
-        for (size_t i = 0; i < v.size(); i += 32) {
-            Bundle b;
-            b.cost = 0;
-            for (size_t j = i; j < i + 32; ++j) {
-                XwU4 e = {0, 0, 0, 0};
-                e.y = (uint32_t)ty << 24;  // padding slot: nc = 0
-                if (j < v.size()) {
-                    const XwPlanItem& it = v[j].first;
-                    const int c0 = v[j].second;
-                    e.x = (uint32_t)it.cellA | ((uint32_t)it.cellB << 8) | ((uint32_t)it.sel << 16);
-                    e.y = (uint32_t)(c0 * PW + it.woff) | ((uint32_t)it.nrows << 16) | ((uint32_t)ty << 24) | ((uint32_t)c0 << 27) | ((uint32_t)nc << 29);
-                    e.z = (uint32_t)it.y0 | ((uint32_t)it.dx << 8) | ((uint32_t)it.scell << 16) | ((uint32_t)it.sbyte << 24);
-                    e.w = (uint32_t)it.q | ((uint32_t)it.k << 8) | ((uint32_t)it.corner << 31);
-                    const double c = xw_item_cost(it, nc);
-                    if (c > b.cost) b.cost = c;
-                }
-                b.slots.push_back(e);
+        // Spread the items over ceil(n/32) bundles so that the 32 lanes of a bundle touch 32 different
+        // shared-memory banks: every row / plane offset is the same for all lanes, so the bank of a
+        // lane's frame-buffer and brick-table words is fixed by (first word offset) mod 32.
+        const size_t nb = (v.size() + 31) / 32;
+        std::vector<Bundle> mine(nb);
+        std::vector<std::vector<int>> bank_cnt(nb, std::vector<int>(32, 0));
+        for (size_t b = 0; b < nb; ++b) mine[b].cost = 0;
+        for (size_t j = 0; j < v.size(); ++j) {
+            const XwPlanItem& it = v[j].first;
+            const int c0 = v[j].second;
+            const uint32_t w0 = (uint32_t)(c0 * PW + it.woff);
+            size_t best = nb;
+            for (size_t b = 0; b < nb; ++b) {
+                if (mine[b].slots.size() >= 32) continue;
+                if (best == nb || bank_cnt[b][w0 & 31] < bank_cnt[best][w0 & 31]) best = b;
             }
-            bundles.push_back(b);
+            XwU4 e;
+            e.x = (uint32_t)it.cellA | ((uint32_t)it.cellB << 8) | ((uint32_t)it.sel << 16);
+            e.y = w0 | ((uint32_t)it.nrows << 16) | ((uint32_t)ty << 24) | ((uint32_t)c0 << 27) | ((uint32_t)nc << 29);
+            e.z = (uint32_t)it.y0 | ((uint32_t)it.dx << 8) | ((uint32_t)it.scell << 16) | ((uint32_t)it.sbyte << 24);
+            e.w = (uint32_t)it.q | ((uint32_t)it.k << 8) | ((uint32_t)it.corner << 31);
+            mine[best].slots.push_back(e);
+            bank_cnt[best][w0 & 31]++;
+            const double c = xw_item_cost(it, nc);
+            if (c > mine[best].cost) mine[best].cost = c;
+        }
+        for (size_t b = 0; b < nb; ++b) {
+            XwU4 pad = {0, (uint32_t)ty << 24, 0, 0};  // padding slot: nc = 0
+            while (mine[b].slots.size() < 32) mine[b].slots.push_back(pad);
+            bundles.push_back(mine[b]);
         }
     }
     // longest-processing-time-first assignment of bundles to the warps of a group
