@@ -93,18 +93,22 @@ HostSim* hs_create(const xw_config* c, const xw_catalog* cat, int n) {
     if (t.fast_ok) {  // odd map sides exercise the per-plane M3 split, even ones the 3-plane items
         xw_build_plan(t, 4 + c->height % 3, c->height % 2 != 0);
         r.plan = t.plan.data(); r.n_plan = (int)t.plan.size(); r.G = 1; r.GT = t.n_warps * 32;
+        r.cellinfo = t.cellinfo.data();
     }
     r.n_sr = (int)t.sr.size();
     r.sr = t.sr.data();
     r.atlas64 = cat->atlas64;
     if (t.fast_ok) {  // k_build_edge_tables
-        s->ecol.resize((size_t)(cat->n_icons + 1) * 2 * 3 * OH + XW_TABLE_PAD / 2);
+        r.band_y0 = t.band_y0.data(); r.RB = t.RB;
+        const size_t n_ecol = (size_t)(cat->n_icons + 1) * 2 * 3 * c->height * t.RB;
+        s->ecol.resize(n_ecol + XW_TABLE_PAD / 2);
         s->uv.resize((size_t)(cat->n_icons + 1) * r.n_sr * 2 * 3 * OW + 8);
-        for (size_t i = 0; i < (size_t)(cat->n_icons + 1) * 2 * 3 * OH; ++i) {
+        for (size_t i = 0; i < n_ecol; ++i) {
             size_t j = i;
-            const int dy = (int)(j % OH); j /= OH;
+            const int row = (int)(j % t.RB); j /= t.RB;
+            const int band = (int)(j % c->height); j /= c->height;
             const int cc = (int)(j % 3); j /= 3;
-            s->ecol[i] = xw_ecol_entry(r, (uint32_t)(j / 2), (int)(j % 2), cc, dy);
+            s->ecol[i] = xw_ecol_entry(r, (uint32_t)(j / 2), (int)(j % 2), cc, band, row);
         }
         for (size_t i = 0; i < (size_t)(cat->n_icons + 1) * r.n_sr * 2 * 3 * OW; ++i) {
             size_t j = i;
@@ -171,6 +175,14 @@ void hs_render(HostSim* s, uint8_t* frames) {
         for (int k = 0; k < XW_CODE_SLOTS; ++k) icon[k] = k < XW_CELL_GOAL0 + d.G ? xw_cell_desc(d, e, k) : 0;
         if (s->tab.fast_ok) {
             std::fill(fb.begin(), fb.end(), 0x5a5a5a5au);
+            for (int cell = 0; cell < d.H * d.W; ++cell) {  // the kernel's staging pass (LDGSTS)
+                if (code[cell] < XW_CELL_AGENT) continue;
+                for (int col = 0; col < XW_STAGE_COLS; ++col) {
+                    uint32_t w0; int nrows; const uint32_t* src;
+                    if (xw_stage_column(r, cells, r.cellinfo, cell, col / 3, col % 3, &w0, &nrows, &src))
+                        for (int j = 0; j < nrows; ++j) fb[w0 + j * r.WR] = src[j * r.WR];
+                }
+            }
             for (int i = 0; i < r.n_plan; ++i) {  // the test alternates the compile-time and run-time row stride
                 if (r.WR == 21 && (e & 1)) xw_compose_item<21>(r, x, r.plan[i], cells, fb.data());
                 else xw_compose_item<0>(r, x, r.plan[i], cells, fb.data());

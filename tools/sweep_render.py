@@ -33,7 +33,9 @@ def main():
     ref = None
     if combos is None:
         combos = [(g, t, s) for g in (8, 7, 6, 5, 4, 3, 2) for t in (64, 96, 128, 160, 192, 256, 320) for s in (0, 1) if g * t <= 1024]
-    for g, t, s in combos:
+    for combo in combos:
+        g, t, s = combo[:3]
+        os.environ["XW_RENDER_CONFLICT_FREE"] = str(combo[3] if len(combo) > 3 else 0)
         os.environ["XW_RENDER_GROUPS"] = str(g)
         os.environ["XW_RENDER_GROUP_THREADS"] = str(t)
         os.environ["XW_RENDER_SPLIT_M3"] = str(s)
@@ -61,7 +63,7 @@ def main():
         if ref is None:
             ref = chk
         same = bool((chk == ref).all())
-        print(json.dumps({"G": g, "GT": t, "split": s, "ms": round(ms, 4), "GBs": round(n * fb / ms / 1e6, 1), "same_as_first": same}),
+        print(json.dumps({"G": g, "GT": t, "split": s, "cfree": combo[3] if len(combo) > 3 else 0, "ms": round(ms, 4), "GBs": round(n * fb / ms / 1e6, 1), "same_as_first": same}),
               flush=True)
         del sim
         torch.cuda.synchronize()

@@ -233,6 +233,8 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
         const char* et = getenv("XW_RENDER_GROUP_THREADS");
         const char* es = getenv("XW_RENDER_SPLIT_M3");
         const bool split = es ? atoi(es) != 0 : true;
+        const char* ec = getenv("XW_RENDER_CONFLICT_FREE");
+        const bool cfree = ec ? atoi(ec) != 0 : false;
         int G = eg ? atoi(eg) : XW_RENDER_MAX_GROUPS;
         if (G > XW_RENDER_MAX_GROUPS) G = XW_RENDER_MAX_GROUPS;
         bool found = false;
@@ -240,7 +242,7 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
             int GT = et ? atoi(et) : (768 / G) / 32 * 32;  // 768 threads/CTA: 80 registers per thread
             GT = GT / 32 * 32;
             if (GT < 32 || G * GT > XW_RENDER_THREADS || 2 * GT < c.height * c.width) { if (et) break; continue; }
-            xw_build_plan(t, GT / 32, split);
+            xw_build_plan(t, GT / 32, split, cfree);
             r.n_plan = (int)t.plan.size();
             if (xw_render_smem(r, G).total > max_optin) continue;
             r.G = G; r.GT = GT;
@@ -253,8 +255,11 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
         uint16_t *ecol = nullptr, *uv = nullptr;
         uint32_t* corner = nullptr;
         rc |= dupload(s, &r.plan, t.plan.data(), t.plan.size());
+        rc |= dupload(s, &r.cellinfo, t.cellinfo.data(), t.cellinfo.size());
         rc |= dupload(s, &r.sr, t.sr.empty() ? &zero16 : t.sr.data(), t.sr.empty() ? 1 : t.sr.size());
-        rc |= dalloc(s, &ecol, (size_t)(cat->n_icons + 1) * 2 * 3 * OH + XW_TABLE_PAD / 2, false);
+        rc |= dalloc(s, &ecol, (size_t)(cat->n_icons + 1) * 2 * 3 * c.height * t.RB + XW_TABLE_PAD / 2, false);
+        rc |= dupload(s, &r.band_y0, t.band_y0.data(), t.band_y0.size());
+        r.RB = t.RB;
         rc |= dalloc(s, &uv, (size_t)(cat->n_icons + 1) * r.n_sr * 2 * 3 * OW + 8, false);
         rc |= dalloc(s, &corner, (size_t)(cat->n_icons + 1) * 3, false);
         r.ecol = ecol; r.uv = uv; r.corner = corner;

@@ -45,9 +45,12 @@ struct XwRender {
     const int16_t* sr;        // [n_sr] the straddling rows
     const XwU4* plan;         // [n_plan] packed items (xw_render_host.hpp)
     const uint8_t* T;         // [n_icons][3][OH][OW] phase atlas
+    const uint32_t* cellinfo; // [H*W] staging geometry of each cell (xw_stage_column)
     // edge tables, indexed by cell descriptor (0 = white, icon + 1 otherwise)
-    const uint16_t* ecol;     // [n_icons+1][2][3][OH]  role 0: taps of icon column 63, role 1: column 0;
-                              //   low byte = tap row of yofs[dy], high byte = the row below it
+    const uint16_t* ecol;     // [n_icons+1][2][3][H][RB]  role 0: taps of icon column 63, role 1: column 0, for
+                              //   row j of band ty; low byte = tap row of yofs[dy], high byte = the row below it
+    const int16_t* band_y0;   // [H] first output row of each band
+    int32_t RB;               // rows per band in ecol (a multiple of 4: one 8-byte load = 4 rows)
     const uint16_t* uv;       // [n_icons+1][n_sr][2][3][OW]  role 0: U from icon row 63, role 1: V from row 0
     const uint32_t* corner;   // [n_icons+1][3]  icon pixels (63,63) | (63,0) << 8 | (0,63) << 16 | (0,0) << 24
     const uint8_t* atlas64;   // [n_icons][64][64][3] BGR
@@ -89,8 +92,10 @@ XW_HD uint8_t xw_phase_px(const XwRender& r, int icon, int c, int dy, int dx) {
 }
 
 // Edge-table entries (built once per handle for every descriptor).
-XW_HD uint16_t xw_ecol_entry(const XwRender& r, uint32_t dsc, int role, int c, int dy) {
+XW_HD uint16_t xw_ecol_entry(const XwRender& r, uint32_t dsc, int role, int c, int band, int j) {
     const XwTaps& t = r.taps;
+    const int dy = r.band_y0[band] + j;
+    if (r.band_y0[band] < 0 || dy >= r.OH) return 0;
     int sy0 = t.yofs[dy], sy1 = t.ya1[dy] ? sy0 + 1 : sy0;
     int sx = role == 0 ? 63 : 0;
     return (uint16_t)(xw_canvas_tap(r, dsc, sy0, sx, c) | (xw_canvas_tap(r, dsc, sy1, sx, c) << 8));
@@ -140,14 +145,37 @@ struct XwComposeCtx {
 };
 
 // Source of a cell's words: word w of the frame comes from *(base + 4*w) | wmask.  White cells read
-// the brick table and OR it to 0xffffffff, so that every lane runs the same instructions.
+// the brick table and OR it to 0xffffffff, so that every lane runs the same instructions.  The words
+// of the few other icons of an env (agent, goals: "special" cells) are staged into the frame buffer
+// itself before the items run (xw_stage_column), at the offsets where the items then read them.
 struct XwSrc { const uint8_t* base; uint32_t wmask; };
-XW_HD XwSrc xw_src_of(const XwRender& r, const XwComposeCtx& x, uint32_t dsc) {
+XW_HD bool xw_special(const XwRender& r, uint32_t dsc) { return dsc != 0 && (int)dsc - 1 != r.brick_icon; }
+// staged_elsewhere: the word was staged from the OTHER cell's table (both cells of the word are
+// special): read this one straight from the phase atlas.
+XW_HD XwSrc xw_src_of(const XwRender& r, const XwComposeCtx& x, uint32_t dsc, const uint32_t* fb, bool staged_elsewhere) {
     XwSrc s;
     s.wmask = dsc == 0 ? 0xffffffffu : 0u;
-    s.base = (dsc == 0 || (int)dsc - 1 == r.brick_icon) ? x.hot : r.T + (size_t)(dsc - 1) * r.FB;
+    if (!xw_special(r, dsc)) s.base = x.hot;
+    else s.base = staged_elsewhere ? r.T + (size_t)(dsc - 1) * r.FB : (const uint8_t*)fb;
     return s;
 }
+
+// Staging plan of word column wc of special cell `cell` in plane c: false = nothing to copy (the cell
+// has fewer word columns, or the column is shared with a special left neighbour, which stages it).
+// Otherwise rows j < *nrows: frame word (*w0 + j*WR) <- word (*w0 + j*WR) of the cell's phase table.
+// cellinfo[cell] = woff | nrows << 16 | nwords << 24 | first_shared << 26 (xw_render_host.hpp).
+XW_HD bool xw_stage_column(const XwRender& r, const XwCells& cells, const uint32_t* cellinfo, int cell, int c, int wc,
+                           uint32_t* w0, int* nrows, const uint32_t** src) {
+    const uint32_t info = cellinfo[cell];
+    if (wc >= (int)((info >> 24) & 3)) return false;
+    if (wc == 0 && ((info >> 26) & 1) && xw_special(r, cells(cell - 1))) return false;
+    *w0 = (uint32_t)c * r.OH * r.WR + (info & 0xffffu) + wc;
+    *nrows = (info >> 16) & 0xff;
+    *src = (const uint32_t*)(r.T + (size_t)(cells(cell) - 1) * r.FB) + *w0;
+    return true;
+}
+#define XW_STAGE_SLOTS (1 + XW_MAX_GOALS)  // agent + goals
+#define XW_STAGE_COLS 9                    // 3 planes x up to 3 word columns per cell
 
 // ---- compose one plan item into the frame being built (fb, words) ----------------------------
 // WR_T = words per frame row when known at compile time (row offsets become immediates), 0 = use r.WR.
@@ -166,7 +194,7 @@ XW_HD void xw_compose_item(const XwRender& r, const XwComposeCtx& x, const XwU4 
     // padded by XW_TABLE_PAD) -- and only the stores are predicated, one predicate per row.
     if (nc == 0) return;  // padding slot
     if (type == XW_ITEM_M1) {
-        const XwSrc sA = xw_src_of(r, x, celldesc(cellA));
+        const XwSrc sA = xw_src_of(r, x, celldesc(cellA), fb, false);
         const uint32_t* pA = (const uint32_t*)sA.base + w0;
         uint32_t* dst = fb + w0;
         for (int i0 = 0; i0 < nrows; i0 += 8, pA += 8 * WR, dst += 8 * WR) {
@@ -185,7 +213,8 @@ XW_HD void xw_compose_item(const XwRender& r, const XwComposeCtx& x, const XwU4 
         return;
     }
     if (type == XW_ITEM_M2) {
-        const XwSrc sA = xw_src_of(r, x, celldesc(cellA)), sB = xw_src_of(r, x, celldesc(cellB));
+        const uint32_t dA = celldesc(cellA), dB = celldesc(cellB);
+        const XwSrc sA = xw_src_of(r, x, dA, fb, false), sB = xw_src_of(r, x, dB, fb, xw_special(r, dA));
         const uint32_t wmask = xw_prmt(sA.wmask, sB.wmask, sel);
         const uint32_t* pA = (const uint32_t*)sA.base + w0;
         const uint32_t* pB = (const uint32_t*)sB.base + w0;
@@ -208,23 +237,28 @@ XW_HD void xw_compose_item(const XwRender& r, const XwComposeCtx& x, const XwU4 
     const int c0 = (e.y >> 27) & 3;
     const int y0 = e.z & 0xff, dx = (e.z >> 8) & 0xff, scell = (e.z >> 16) & 0xff, sh = (e.z >> 24) * 8;
     if (type == XW_ITEM_M3) {
-        const XwSrc sA = xw_src_of(r, x, celldesc(cellA)), sB = xw_src_of(r, x, celldesc(cellB));
+        const uint32_t dA = celldesc(cellA), dB = celldesc(cellB);
+        const XwSrc sA = xw_src_of(r, x, dA, fb, false), sB = xw_src_of(r, x, dB, fb, xw_special(r, dA));
         const uint32_t wmask = xw_prmt(sA.wmask, sB.wmask, sel);
-        const uint16_t* eL0 = r.ecol + ((size_t)(celldesc(scell) * 2 + 0) * 3 + c0) * r.OH + y0;
-        const uint16_t* eR0 = r.ecol + ((size_t)(celldesc(scell + 1) * 2 + 1) * 3 + c0) * r.OH + y0;
+        const int band = (e.w >> 16) & 0xff;
+        const uint16_t* eL0 = r.ecol + ((((size_t)celldesc(scell) * 2 + 0) * 3 + c0) * r.H + band) * r.RB;
+        const uint16_t* eR0 = r.ecol + ((((size_t)celldesc(scell + 1) * 2 + 1) * 3 + c0) * r.H + band) * r.RB;
         const int a0 = r.taps.xa0[dx], a1 = r.taps.xa1[dx];
         const uint32_t keep = ~(0xffu << sh);
         for (int cc = 0; cc < nc; ++cc) {
             const uint32_t* pA = (const uint32_t*)sA.base + w0 + cc * PW;
             const uint32_t* pB = (const uint32_t*)sB.base + w0 + cc * PW;
             uint32_t* dst = fb + w0 + cc * PW;
-            const uint16_t* eL = eL0 + cc * r.OH;
-            const uint16_t* eR = eR0 + cc * r.OH;
+            const uint16_t* eL = eL0 + (size_t)cc * r.H * r.RB;
+            const uint16_t* eR = eR0 + (size_t)cc * r.H * r.RB;
             const uint32_t* yb = x.yb + y0;
             for (int i0 = 0; i0 < nrows; i0 += 4, pA += 4 * WR, pB += 4 * WR, dst += 4 * WR, eL += 4, eR += 4, yb += 4) {
-                uint32_t va[4], vb[4], tl[4], tr[4];
+                uint32_t va[4], vb[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) { va[j] = pA[j * WR]; vb[j] = pB[j * WR]; tl[j] = eL[j]; tr[j] = eR[j]; }
+                for (int j = 0; j < 4; ++j) { va[j] = pA[j * WR]; vb[j] = pB[j * WR]; }
+                const XwU2 tl2 = *(const XwU2*)eL, tr2 = *(const XwU2*)eR;  // four rows of edge taps each
+                const uint32_t tl[4] = {tl2.x & 0xffffu, tl2.x >> 16, tl2.y & 0xffffu, tl2.y >> 16};
+                const uint32_t tr[4] = {tr2.x & 0xffffu, tr2.x >> 16, tr2.y & 0xffffu, tr2.y >> 16};
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     if (i0 + j < nrows) {
@@ -283,7 +317,7 @@ XW_HD uint32_t xw_cell_desc(const XwDev& d, int e, int code) {
 // Dynamic shared memory layout (bytes), all sections 16-byte aligned:
 //   brick phase table (TMA bulk load, once) | G frame buffers | plan | yb | G cell arrays | mbarrier
 #define XW_CELL_STRIDE (XW_MAX_DIM * XW_MAX_DIM + 2 * XW_MAX_DIM)  // bytes: the map + the (never drawn) row below it
-struct XwRenderSmem { int hot, fb, plan, yb, cell, bar, total; };
+struct XwRenderSmem { int hot, fb, plan, yb, cellinfo, cell, bar, total; };
 XW_HD int xw_align16(int v) { return (v + 15) & ~15; }
 XW_HD XwRenderSmem xw_render_smem(const XwRender& r, int G) {
     XwRenderSmem s;
@@ -292,7 +326,8 @@ XW_HD XwRenderSmem xw_render_smem(const XwRender& r, int G) {
     s.fb = o; o += G * xw_align16(r.FB);
     s.plan = o; o += r.n_plan * 16;
     s.yb = o; o += xw_align16(r.OH * 4);
-    s.cell = o; o += G * (XW_CELL_STRIDE + XW_CODE_SLOTS * 4);
+    s.cellinfo = o; o += XW_MAX_DIM * XW_MAX_DIM * 4;
+    s.cell = o; o += G * (XW_CELL_STRIDE + XW_CODE_SLOTS * 4 + 16);
     s.bar = o; o += 16;
     s.total = o;
     return s;
@@ -309,7 +344,7 @@ __global__ void k_build_phase_atlas(XwRender r) {
     }
 }
 __global__ void k_build_edge_tables(XwRender r) {
-    const size_t n_ecol = (size_t)(r.n_icons + 1) * 2 * 3 * r.OH, n_uv = (size_t)(r.n_icons + 1) * r.n_sr * 2 * 3 * r.OW;
+    const size_t n_ecol = (size_t)(r.n_icons + 1) * 2 * 3 * r.H * r.RB, n_uv = (size_t)(r.n_icons + 1) * r.n_sr * 2 * 3 * r.OW;
     const size_t n_cor = (size_t)(r.n_icons + 1) * 3;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_ecol + n_uv + n_cor; i += (size_t)gridDim.x * blockDim.x) {
         if (i >= n_ecol + n_uv) {
@@ -317,9 +352,10 @@ __global__ void k_build_edge_tables(XwRender r) {
             ((uint32_t*)r.corner)[j] = xw_corner_entry(r, (uint32_t)(j / 3), (int)(j % 3));
         } else if (i < n_ecol) {
             size_t j = i;
-            const int dy = (int)(j % r.OH); j /= r.OH;
+            const int row = (int)(j % r.RB); j /= r.RB;
+            const int band = (int)(j % r.H); j /= r.H;
             const int c = (int)(j % 3); j /= 3;
-            ((uint16_t*)r.ecol)[i] = xw_ecol_entry(r, (uint32_t)(j / 2), (int)(j % 2), c, dy);
+            ((uint16_t*)r.ecol)[i] = xw_ecol_entry(r, (uint32_t)(j / 2), (int)(j % 2), c, band, row);
         } else {
             size_t j = i - n_ecol;
             const int dx = (int)(j % r.OW); j /= r.OW;
@@ -363,6 +399,10 @@ template <int N> __device__ __forceinline__ void tma_wait_all() {
     asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {  // SASS: LDGSTS
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void group_bar(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -393,6 +433,7 @@ k_render(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
     }
     {  // plan + row weights -> shared memory
         for (int i = tid; i < r.n_plan; i += nt) s_plan[i] = r.plan[i];
+        for (int i = tid; i < r.H * r.W; i += nt) ((uint32_t*)(smem + L.cellinfo))[i] = r.cellinfo[i];
         for (int i = tid; i < r.OH; i += nt) s_yb[i] = (uint32_t)(uint16_t)r.taps.ya0[i] | ((uint32_t)(uint16_t)r.taps.ya1[i] << 16);
     }
     mbar_wait(bar, 0);
@@ -400,8 +441,10 @@ k_render(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
 
     const int g = tid / GT, gt = tid - g * GT;
     if (g >= G) return;  // spare warps (G*GT < blockDim.x)
-    uint8_t* s_code = smem + L.cell + g * (XW_CELL_STRIDE + XW_CODE_SLOTS * 4);
+    uint8_t* s_code = smem + L.cell + g * (XW_CELL_STRIDE + XW_CODE_SLOTS * 4 + 16);
     uint32_t* s_icon = (uint32_t*)(s_code + XW_CELL_STRIDE);
+    uint8_t* s_special = (uint8_t*)(s_icon + XW_CODE_SLOTS);  // [XW_STAGE_SLOTS] cell of the agent / goal g
+    const uint32_t* s_cellinfo = (const uint32_t*)(smem + L.cellinfo);
     uint32_t* fb = (uint32_t*)(smem + L.fb + (size_t)g * xw_align16(r.FB));
     XwComposeCtx x;
     x.hot = hot; x.yb = s_yb;
@@ -422,9 +465,28 @@ k_render(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
     for (int i = gt; i < XW_CELL_STRIDE / 4; i += GT) ((uint32_t*)s_code)[i] = 0;
     if (gt < XW_CODE_SLOTS) s_icon[gt] = gt == XW_CELL_BLOCK ? (uint32_t)d.brick_icon + 1 : gt == XW_CELL_AGENT ? (uint32_t)d.agent_icon + 1 : 0;
     for (; env < d.n; env += gstride) {
-        if (gt < row_words) ((uint32_t*)s_code)[gt] = nq;  // (every warp passed the barrier after the last compose)
+        if (gt < row_words) {  // (every warp passed the barrier after the last compose)
+            ((uint32_t*)s_code)[gt] = nq;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {  // where the agent and the goals are
+                const uint32_t code = (nq >> (8 * b)) & 0xff;
+                if (code >= XW_CELL_AGENT) s_special[code - XW_CELL_AGENT] = (uint8_t)(4 * gt + b);
+            }
+        }
         if (gt < d.G) s_icon[XW_CELL_GOAL0 + gt] = ni;
         if (gt == 0) tma_wait_read<0>();  // the TMA store of this group's previous frame has drained fb
+        group_bar(bar_id, GT);
+        // stage the agent's and goals' table words into the frame buffer (LDGSTS, no registers): one
+        // thread per (cell, plane, word column), one 4-byte copy per row
+        for (int i = gt; i < (1 + d.G) * XW_STAGE_COLS; i += GT) {
+            const int slot = i / XW_STAGE_COLS, col = i - slot * XW_STAGE_COLS, c = col / 3, wc = col - 3 * c;
+            uint32_t w0; int nrows; const uint32_t* src;
+            if (xw_stage_column(r, cells, s_cellinfo, s_special[slot], c, wc, &w0, &nrows, &src)) {
+                const int WR = WR_T ? WR_T : r.WR;
+                for (int j = 0; j < nrows; ++j) cp_async_4(fb + w0 + j * WR, src + j * WR);
+            }
+        }
+        cp_async_wait_all();
         group_bar(bar_id, GT);
         {  // prefetch the next env's cells while this one is composed
             const int en = env + gstride;

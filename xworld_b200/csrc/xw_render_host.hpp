@@ -31,18 +31,23 @@ enum { XW_ITEM_M1 = 0, XW_ITEM_M2 = 1, XW_ITEM_M3 = 2, XW_ITEM_R = 3, XW_ITEM_TY
 //                                          first plane, number of planes (0 = padding slot)
 //   z = y0 | dx << 8 | scell << 16 | sbyte << 24    first row; M3 / R-with-corner: the straddling column,
 //                                          its left cell (the right one is scell + 1), its byte in the word
-//   w = q | k << 8 | corner << 31          R: index of the straddling row, word column, corner flag
+//   w = q | k << 8 | band << 16 | corner << 31     R: index of the straddling row, word column, corner flag;
+//                                          M3: band = cell row (edge tables are stored per band)
 // The plan is a sequence of 32-slot bundles of one type; bundle b belongs to warp b % n_warps of a
 // warp group, and the host orders bundles so that the warps of a group finish together (LPT).
 struct alignas(16) XwU4 { uint32_t x, y, z, w; };
 struct alignas(8) XwU2 { uint32_t x, y; };
 
-struct XwPlanItem { int cellA, cellB, sel, woff, nrows, type, y0, k, sbyte, scell, dx, q, corner; };
+struct XwPlanItem { int cellA, cellB, sel, woff, nrows, type, y0, k, sbyte, scell, dx, q, corner, band; };
 
 struct XwRenderTables {
     int H = 0, W = 0, OH = 0, OW = 0, WR = 0, FB = 0;
     bool fast_ok = false;  // the shared-memory compositor applies (else: generic kernel)
     std::vector<int16_t> xofs, xa0, xa1, yofs, ya0, ya1, sc, sr;
+    std::vector<uint32_t> cellinfo;      // [H*W] woff | nrows << 16 | nwords << 24 | first_shared << 26: the frame
+                                         // words cell (ty,tx) owns in the M items (staging of special cells)
+    std::vector<int16_t> band_y0;        // [H] first output row of each cell row's band (-1: none)
+    int RB = 0;                          // rows per band in the edge table, a multiple of 4
     std::vector<XwPlanItem> items;       // per-plane items (planner input)
     std::vector<XwU4> plan;              // bundled plan for n_warps warps per group
     int n_warps = 0;
@@ -86,11 +91,14 @@ inline XwRenderTables xw_build_render_tables(int H, int W, int OH, int OW) {
     }
     if (!ok) return t;
     t.WR = OW / 4;
+    t.band_y0.assign(H, -1);
     for (int ty = 0; ty < H && ok; ++ty) {
         int y0 = -1, y1 = -1;  // rows owned by cell row ty
         for (int dy = 0; dy < OH; ++dy)
             if ((t.yofs[dy] >> 6) == ty) { if (y0 < 0) y0 = dy; y1 = dy + 1; }
         if (y0 < 0) continue;
+        t.band_y0[ty] = (int16_t)y0;
+        if (y1 - y0 > t.RB) t.RB = y1 - y0;
         const bool srow = is_sr[y1 - 1] != 0;
         int q = 0;
         if (srow) while (t.sr[q] != y1 - 1) ++q;
@@ -111,7 +119,7 @@ inline XwRenderTables xw_build_render_tables(int H, int W, int OH, int OW) {
             it.cellA = ty * W + A; it.cellB = ty * W + B;
             it.woff = y0 * t.WR + k;
             it.nrows = y1 - y0 - (srow ? 1 : 0);
-            it.y0 = y0; it.k = k;
+            it.y0 = y0; it.k = k; it.band = ty;
             it.type = n_sc ? XW_ITEM_M3 : (A != B ? XW_ITEM_M2 : XW_ITEM_M1);
             if (it.nrows > 0) t.items.push_back(it);
             if (srow) {
@@ -124,6 +132,22 @@ inline XwRenderTables xw_build_render_tables(int H, int W, int OH, int OW) {
         }
     }
     if (3 * OH * t.WR > 65535) ok = false;  // woff is 16 bits
+    t.RB = (t.RB + 3) / 4 * 4;
+    t.cellinfo.assign((size_t)H * W, 0);
+    for (const XwPlanItem& it : t.items) {  // per cell: first word column, number of columns, rows of the M items
+        if (it.type == XW_ITEM_R) continue;
+        const int cells[2] = {it.cellA, it.cellB};
+        for (int q = 0; q < 2; ++q) {
+            uint32_t& ci = t.cellinfo[cells[q]];
+            const int kfirst = ci ? (int)((ci & 0xffffu) - (uint32_t)it.y0 * t.WR) : it.k;
+            const int nwords = ci ? (int)((ci >> 24) & 3) : 0;
+            const int kf = it.k < kfirst ? it.k : kfirst, kl = (it.k > kfirst + nwords - 1 ? it.k : kfirst + nwords - 1);
+            if (kl - kf + 1 > 3) ok = false;  // XW_STAGE_COLS assumes a cell spans at most 3 word columns
+            ci = (uint32_t)(it.y0 * t.WR + kf) | ((uint32_t)it.nrows << 16) | ((uint32_t)(kl - kf + 1) << 24);
+        }
+    }
+    for (const XwPlanItem& it : t.items)  // first column shared with the left neighbour?
+        if (it.type != XW_ITEM_R && it.cellA != it.cellB) t.cellinfo[it.cellB] |= 1u << 26;
     t.fast_ok = ok;
     return t;
 }
@@ -140,7 +164,7 @@ inline double xw_item_cost(const XwPlanItem& it, int nc) {
 
 // Bundle the items for groups of n_warps warps.  split_m3: M3 items per plane (three times the
 // items, a third of the rows each) instead of one item for the three planes.
-inline void xw_build_plan(XwRenderTables& t, int n_warps, bool split_m3) {
+inline void xw_build_plan(XwRenderTables& t, int n_warps, bool split_m3, bool conflict_free = false) {
     struct Bundle { std::vector<XwU4> slots; double cost; };
     std::vector<Bundle> bundles;
     const int PW = t.OH * t.WR;
@@ -156,31 +180,41 @@ inline void xw_build_plan(XwRenderTables& t, int n_warps, bool split_m3) {
         std::stable_sort(v.begin(), v.end(), [&](const std::pair<XwPlanItem, int>& a, const std::pair<XwPlanItem, int>& b) {
             return xw_item_cost(a.first, nc) > xw_item_cost(b.first, nc);
         });
-        // Spread the items over ceil(n/32) bundles so that the 32 lanes of a bundle touch 32 different
-        // shared-memory banks: every row / plane offset is the same for all lanes, so the bank of a
-        // lane's frame-buffer and brick-table words is fixed by (first word offset) mod 32.
-        const size_t nb = (v.size() + 31) / 32;
+        // Spread the items over bundles so that the lanes of a bundle touch different shared-memory
+        // banks: every row / plane offset is the same for all lanes, so the bank of a lane's
+        // frame-buffer and brick-table words is fixed by (first word offset) mod 32, and one 2-way
+        // conflict doubles the wavefronts of every load and store of the bundle.  A conflict-free
+        // split needs as many bundles as the fullest bank has items.
+        if (v.empty()) continue;
+        std::vector<std::vector<size_t>> by_bank(32);
+        for (size_t j = 0; j < v.size(); ++j) by_bank[(uint32_t)(v[j].second * PW + v[j].first.woff) & 31].push_back(j);
+        size_t nb = (v.size() + 31) / 32;
+        // (conflict_free: as many bundles as the fullest bank has items; otherwise ceil(n/32) bundles and
+        // the fullest banks put two lanes on one bank)
+        if (conflict_free) for (int k = 0; k < 32; ++k) if (by_bank[k].size() > nb) nb = by_bank[k].size();
         std::vector<Bundle> mine(nb);
-        std::vector<std::vector<int>> bank_cnt(nb, std::vector<int>(32, 0));
         for (size_t b = 0; b < nb; ++b) mine[b].cost = 0;
-        for (size_t j = 0; j < v.size(); ++j) {
-            const XwPlanItem& it = v[j].first;
-            const int c0 = v[j].second;
-            const uint32_t w0 = (uint32_t)(c0 * PW + it.woff);
-            size_t best = nb;
-            for (size_t b = 0; b < nb; ++b) {
-                if (mine[b].slots.size() >= 32) continue;
-                if (best == nb || bank_cnt[b][w0 & 31] < bank_cnt[best][w0 & 31]) best = b;
+        std::vector<int> bank_order(32);
+        for (int k = 0; k < 32; ++k) bank_order[k] = k;
+        std::stable_sort(bank_order.begin(), bank_order.end(), [&](int a, int b) { return by_bank[a].size() > by_bank[b].size(); });
+        for (int kk = 0; kk < 32; ++kk) {
+            const std::vector<size_t>& js = by_bank[bank_order[kk]];
+            std::vector<size_t> order(nb);  // the emptiest bundles take this bank's items, one each
+            for (size_t b = 0; b < nb; ++b) order[b] = b;
+            std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return mine[a].slots.size() < mine[b].slots.size(); });
+            for (size_t q = 0; q < js.size(); ++q) {
+                const XwPlanItem& it = v[js[q]].first;
+                const int c0 = v[js[q]].second;
+                Bundle& bd = mine[order[q % nb]];
+                XwU4 e;
+                e.x = (uint32_t)it.cellA | ((uint32_t)it.cellB << 8) | ((uint32_t)it.sel << 16);
+                e.y = (uint32_t)(c0 * PW + it.woff) | ((uint32_t)it.nrows << 16) | ((uint32_t)ty << 24) | ((uint32_t)c0 << 27) | ((uint32_t)nc << 29);
+                e.z = (uint32_t)it.y0 | ((uint32_t)it.dx << 8) | ((uint32_t)it.scell << 16) | ((uint32_t)it.sbyte << 24);
+                e.w = (uint32_t)it.q | ((uint32_t)it.k << 8) | ((uint32_t)it.band << 16) | ((uint32_t)it.corner << 31);
+                bd.slots.push_back(e);
+                const double c = xw_item_cost(it, nc);
+                if (c > bd.cost) bd.cost = c;
             }
-            XwU4 e;
-            e.x = (uint32_t)it.cellA | ((uint32_t)it.cellB << 8) | ((uint32_t)it.sel << 16);
-            e.y = w0 | ((uint32_t)it.nrows << 16) | ((uint32_t)ty << 24) | ((uint32_t)c0 << 27) | ((uint32_t)nc << 29);
-            e.z = (uint32_t)it.y0 | ((uint32_t)it.dx << 8) | ((uint32_t)it.scell << 16) | ((uint32_t)it.sbyte << 24);
-            e.w = (uint32_t)it.q | ((uint32_t)it.k << 8) | ((uint32_t)it.corner << 31);
-            mine[best].slots.push_back(e);
-            bank_cnt[best][w0 & 31]++;
-            const double c = xw_item_cost(it, nc);
-            if (c > mine[best].cost) mine[best].cost = c;
         }
         for (size_t b = 0; b < nb; ++b) {
             XwU4 pad = {0, (uint32_t)ty << 24, 0, 0};  // padding slot: nc = 0
