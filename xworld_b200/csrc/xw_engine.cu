@@ -232,7 +232,7 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
         const char* eg = getenv("XW_RENDER_GROUPS");
         const char* et = getenv("XW_RENDER_GROUP_THREADS");
         const char* es = getenv("XW_RENDER_SPLIT_M3");
-        const bool split = es ? atoi(es) != 0 : true;
+        const bool split = es ? atoi(es) != 0 : false;
         const char* ec = getenv("XW_RENDER_CONFLICT_FREE");
         const bool cfree = ec ? atoi(ec) != 0 : false;
         int G = eg ? atoi(eg) : XW_RENDER_MAX_GROUPS;

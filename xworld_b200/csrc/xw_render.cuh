@@ -193,6 +193,10 @@ XW_HD void xw_compose_item(const XwRender& r, const XwComposeCtx& x, const XwU4 
     // unconditional -- rows past the band read table bytes that are never stored (the tables are
     // padded by XW_TABLE_PAD) -- and only the stores are predicated, one predicate per row.
     if (nc == 0) return;  // padding slot
+    // plane order of this lane: (rot + i) % 3, chosen by the planner so that the lanes of a bundle stay
+    // on different banks (xw_build_plan); po[i] = word offset of the i-th plane visited
+    const int rot = (e.w >> 24) & 3;
+    const int po[3] = {rot * PW, (rot == 2 ? 0 : rot + 1) * PW, (rot == 0 ? 2 : rot - 1) * PW};
     if (type == XW_ITEM_M1) {
         const XwSrc sA = xw_src_of(r, x, celldesc(cellA), fb, false);
         const uint32_t* pA = (const uint32_t*)sA.base + w0;
@@ -202,12 +206,12 @@ XW_HD void xw_compose_item(const XwRender& r, const XwComposeCtx& x, const XwU4 
 #pragma unroll
             for (int j = 0; j < 8; ++j)
 #pragma unroll
-                for (int cc = 0; cc < 3; ++cc) v[cc][j] = pA[cc * PW + j * WR];
+                for (int cc = 0; cc < 3; ++cc) v[cc][j] = pA[po[cc] + j * WR];
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 if (i0 + j < nrows) {
 #pragma unroll
-                    for (int cc = 0; cc < 3; ++cc) dst[cc * PW + j * WR] = v[cc][j] | sA.wmask;
+                    for (int cc = 0; cc < 3; ++cc) dst[po[cc] + j * WR] = v[cc][j] | sA.wmask;
                 }
         }
         return;
@@ -224,12 +228,12 @@ XW_HD void xw_compose_item(const XwRender& r, const XwComposeCtx& x, const XwU4 
 #pragma unroll
             for (int j = 0; j < 4; ++j)
 #pragma unroll
-                for (int cc = 0; cc < 3; ++cc) { va[cc][j] = pA[cc * PW + j * WR]; vb[cc][j] = pB[cc * PW + j * WR]; }
+                for (int cc = 0; cc < 3; ++cc) { va[cc][j] = pA[po[cc] + j * WR]; vb[cc][j] = pB[po[cc] + j * WR]; }
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 if (i0 + j < nrows) {
 #pragma unroll
-                    for (int cc = 0; cc < 3; ++cc) dst[cc * PW + j * WR] = xw_prmt(va[cc][j], vb[cc][j], sel) | wmask;
+                    for (int cc = 0; cc < 3; ++cc) dst[po[cc] + j * WR] = xw_prmt(va[cc][j], vb[cc][j], sel) | wmask;
                 }
         }
         return;
@@ -245,7 +249,8 @@ XW_HD void xw_compose_item(const XwRender& r, const XwComposeCtx& x, const XwU4 
         const uint16_t* eR0 = r.ecol + ((((size_t)celldesc(scell + 1) * 2 + 1) * 3 + c0) * r.H + band) * r.RB;
         const int a0 = r.taps.xa0[dx], a1 = r.taps.xa1[dx];
         const uint32_t keep = ~(0xffu << sh);
-        for (int cc = 0; cc < nc; ++cc) {
+        for (int ci = 0; ci < nc; ++ci) {
+            const int cc = nc == 3 ? (rot + ci >= 3 ? rot + ci - 3 : rot + ci) : ci;
             const uint32_t* pA = (const uint32_t*)sA.base + w0 + cc * PW;
             const uint32_t* pB = (const uint32_t*)sB.base + w0 + cc * PW;
             uint32_t* dst = fb + w0 + cc * PW;
@@ -280,17 +285,19 @@ XW_HD void xw_compose_item(const XwRender& r, const XwComposeCtx& x, const XwU4 
     const uint16_t *vAp = v0 + celldesc(cellA + r.W) * per_desc, *vBp = v0 + celldesc(cellB + r.W) * per_desc;
     XwU2 uA[3], uB[3], vA[3], vB[3];
 #pragma unroll
-    for (int cc = 0; cc < 3; ++cc)
-        if (cc < nc) {
-            uA[cc] = *(const XwU2*)(uAp + cc * r.OW); uB[cc] = *(const XwU2*)(uBp + cc * r.OW);
-            vA[cc] = *(const XwU2*)(vAp + cc * r.OW); vB[cc] = *(const XwU2*)(vBp + cc * r.OW);
+    for (int ci = 0; ci < 3; ++ci)
+        if (ci < nc) {
+            const int cc = nc == 3 ? (rot + ci >= 3 ? rot + ci - 3 : rot + ci) : ci;
+            uA[ci] = *(const XwU2*)(uAp + cc * r.OW); uB[ci] = *(const XwU2*)(uBp + cc * r.OW);
+            vA[ci] = *(const XwU2*)(vAp + cc * r.OW); vB[ci] = *(const XwU2*)(vBp + cc * r.OW);
         }
 #pragma unroll
-    for (int cc = 0; cc < 3; ++cc)
-        if (cc < nc) {
+    for (int ci = 0; ci < 3; ++ci)
+        if (ci < nc) {
+            const int cc = nc == 3 ? (rot + ci >= 3 ? rot + ci - 3 : rot + ci) : ci;
             // packed u16 pairs: no carry between halves (U + V + 2 <= 2042)
-            const uint32_t a_lo = ((uA[cc].x + vA[cc].x + 0x00020002u) >> 2) & 0x00ff00ffu, a_hi = ((uA[cc].y + vA[cc].y + 0x00020002u) >> 2) & 0x00ff00ffu;
-            const uint32_t b_lo = ((uB[cc].x + vB[cc].x + 0x00020002u) >> 2) & 0x00ff00ffu, b_hi = ((uB[cc].y + vB[cc].y + 0x00020002u) >> 2) & 0x00ff00ffu;
+            const uint32_t a_lo = ((uA[ci].x + vA[ci].x + 0x00020002u) >> 2) & 0x00ff00ffu, a_hi = ((uA[ci].y + vA[ci].y + 0x00020002u) >> 2) & 0x00ff00ffu;
+            const uint32_t b_lo = ((uB[ci].x + vB[ci].x + 0x00020002u) >> 2) & 0x00ff00ffu, b_hi = ((uB[ci].y + vB[ci].y + 0x00020002u) >> 2) & 0x00ff00ffu;
             uint32_t word = xw_prmt(xw_prmt(a_lo, a_hi, 0x6420), xw_prmt(b_lo, b_hi, 0x6420), sel);
             if (corner) {  // taps: (63,63) of the top-left cell, (63,0) top-right, (0,63) bottom-left, (0,0) bottom-right
                 const int c = c0 + cc;

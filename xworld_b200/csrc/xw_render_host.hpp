@@ -31,8 +31,9 @@ enum { XW_ITEM_M1 = 0, XW_ITEM_M2 = 1, XW_ITEM_M3 = 2, XW_ITEM_R = 3, XW_ITEM_TY
 //                                          first plane, number of planes (0 = padding slot)
 //   z = y0 | dx << 8 | scell << 16 | sbyte << 24    first row; M3 / R-with-corner: the straddling column,
 //                                          its left cell (the right one is scell + 1), its byte in the word
-//   w = q | k << 8 | band << 16 | corner << 31     R: index of the straddling row, word column, corner flag;
-//                                          M3: band = cell row (edge tables are stored per band)
+//   w = q | k << 8 | band << 16 | rot << 24 | corner << 31     R: index of the straddling row, word column,
+//                                          corner flag; M3: band = cell row (edge tables are stored per
+//                                          band); rot: the item visits planes (rot + i) % 3, i = 0,1,2
 // The plan is a sequence of 32-slot bundles of one type; bundle b belongs to warp b % n_warps of a
 // warp group, and the host orders bundles so that the warps of a group finish together (LPT).
 struct alignas(16) XwU4 { uint32_t x, y, z, w; };
@@ -51,6 +52,7 @@ struct XwRenderTables {
     std::vector<XwPlanItem> items;       // per-plane items (planner input)
     std::vector<XwU4> plan;              // bundled plan for n_warps warps per group
     int n_warps = 0;
+    int bank_conflicts = 0;              // lane pairs of a bundle left on one bank (0 = conflict-free plan)
     double makespan = 0, total_cost = 0; // planner's cost model (instructions per env): slowest warp, sum
 };
 
@@ -167,6 +169,7 @@ inline double xw_item_cost(const XwPlanItem& it, int nc) {
 inline void xw_build_plan(XwRenderTables& t, int n_warps, bool split_m3, bool conflict_free = false) {
     struct Bundle { std::vector<XwU4> slots; double cost; };
     std::vector<Bundle> bundles;
+    t.bank_conflicts = 0;
     const int PW = t.OH * t.WR;
     for (int ty = 0; ty < XW_ITEM_TYPES; ++ty) {
         std::vector<std::pair<XwPlanItem, int>> v;  // (item, first plane), nc implied
@@ -180,44 +183,65 @@ inline void xw_build_plan(XwRenderTables& t, int n_warps, bool split_m3, bool co
         std::stable_sort(v.begin(), v.end(), [&](const std::pair<XwPlanItem, int>& a, const std::pair<XwPlanItem, int>& b) {
             return xw_item_cost(a.first, nc) > xw_item_cost(b.first, nc);
         });
-        // Spread the items over bundles so that the lanes of a bundle touch different shared-memory
-        // banks: every row / plane offset is the same for all lanes, so the bank of a lane's
-        // frame-buffer and brick-table words is fixed by (first word offset) mod 32, and one 2-way
-        // conflict doubles the wavefronts of every load and store of the bundle.  A conflict-free
-        // split needs as many bundles as the fullest bank has items.
+        // Spread the items over ceil(n/32) bundles so that the lanes of a bundle touch different
+        // shared-memory banks: every row offset is the same for all lanes, so the bank of a lane's
+        // frame-buffer and brick-table words at plane step i is fixed by its first word offset, and one
+        // 2-way conflict doubles the wavefronts of every load and store of the bundle.  Each 3-plane
+        // item may visit the planes in a rotated order ((rot + i) % 3): two lanes on the same bank in
+        // plane 0 then never meet.  Randomised greedy, best of a few hundred tries (create-time only).
         if (v.empty()) continue;
-        std::vector<std::vector<size_t>> by_bank(32);
-        for (size_t j = 0; j < v.size(); ++j) by_bank[(uint32_t)(v[j].second * PW + v[j].first.woff) & 31].push_back(j);
-        size_t nb = (v.size() + 31) / 32;
-        // (conflict_free: as many bundles as the fullest bank has items; otherwise ceil(n/32) bundles and
-        // the fullest banks put two lanes on one bank)
-        if (conflict_free) for (int k = 0; k < 32; ++k) if (by_bank[k].size() > nb) nb = by_bank[k].size();
-        std::vector<Bundle> mine(nb);
-        for (size_t b = 0; b < nb; ++b) mine[b].cost = 0;
-        std::vector<int> bank_order(32);
-        for (int k = 0; k < 32; ++k) bank_order[k] = k;
-        std::stable_sort(bank_order.begin(), bank_order.end(), [&](int a, int b) { return by_bank[a].size() > by_bank[b].size(); });
-        for (int kk = 0; kk < 32; ++kk) {
-            const std::vector<size_t>& js = by_bank[bank_order[kk]];
-            std::vector<size_t> order(nb);  // the emptiest bundles take this bank's items, one each
-            for (size_t b = 0; b < nb; ++b) order[b] = b;
-            std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return mine[a].slots.size() < mine[b].slots.size(); });
-            for (size_t q = 0; q < js.size(); ++q) {
-                const XwPlanItem& it = v[js[q]].first;
-                const int c0 = v[js[q]].second;
-                Bundle& bd = mine[order[q % nb]];
-                XwU4 e;
-                e.x = (uint32_t)it.cellA | ((uint32_t)it.cellB << 8) | ((uint32_t)it.sel << 16);
-                e.y = (uint32_t)(c0 * PW + it.woff) | ((uint32_t)it.nrows << 16) | ((uint32_t)ty << 24) | ((uint32_t)c0 << 27) | ((uint32_t)nc << 29);
-                e.z = (uint32_t)it.y0 | ((uint32_t)it.dx << 8) | ((uint32_t)it.scell << 16) | ((uint32_t)it.sbyte << 24);
-                e.w = (uint32_t)it.q | ((uint32_t)it.k << 8) | ((uint32_t)it.band << 16) | ((uint32_t)it.corner << 31);
-                bd.slots.push_back(e);
-                const double c = xw_item_cost(it, nc);
-                if (c > bd.cost) bd.cost = c;
+        const size_t n = v.size();
+        size_t nb = (n + 31) / 32;
+        std::vector<uint32_t> w0s(n);
+        for (size_t j = 0; j < n; ++j) w0s[j] = (uint32_t)(v[j].second * PW + v[j].first.woff);
+        const int steps = nc;
+        auto bank_at = [&](size_t j, int rot, int i) { return (int)((w0s[j] + (uint32_t)(((rot + i) % 3) * PW)) & 31u); };
+        std::vector<int> best_b(n, 0), best_r(n, 0);
+        long best_conf = -1;
+        uint32_t rng = 12345u + (uint32_t)ty;
+        std::vector<size_t> order(n);
+        if (conflict_free) nb += 1;  // one spare bundle makes a conflict-free split much more likely
+        for (int attempt = 0; attempt < 400 && best_conf != 0; ++attempt) {
+            for (size_t j = 0; j < n; ++j) order[j] = j;
+            for (size_t j = n; j > 1; --j) { rng = rng * 1664525u + 1013904223u; std::swap(order[j - 1], order[(rng >> 8) % j]); }
+            std::vector<int> occ(nb * 3 * 32, 0), fill(nb, 0), ab(n), ar(n);
+            long conf = 0;
+            for (size_t oi = 0; oi < n; ++oi) {
+                const size_t j = order[oi];
+                long bc = -1; int bb = 0, br = 0;
+                for (size_t bi = 0; bi < nb; ++bi) {
+                    if (fill[bi] >= 32) continue;
+                    for (int rot = 0; rot < (steps == 3 ? 3 : 1); ++rot) {
+                        long c = 0;
+                        for (int i = 0; i < steps; ++i) c += occ[(bi * 3 + i) * 32 + bank_at(j, rot, i)];
+                        c = c * 64 + fill[bi];  // fewest conflicts first, then the emptiest bundle
+                        if (bc < 0 || c < bc) { bc = c; bb = (int)bi; br = rot; }
+                    }
+                }
+                ab[j] = bb; ar[j] = br; fill[bb]++;
+                for (int i = 0; i < steps; ++i) { int& o = occ[((size_t)bb * 3 + i) * 32 + bank_at(j, br, i)]; conf += o; ++o; }
             }
+            if (best_conf < 0 || conf < best_conf) { best_conf = conf; best_b = ab; best_r = ar; }
+        }
+        t.bank_conflicts += (int)best_conf;
+        std::vector<Bundle> mine(nb);
+        for (size_t bi = 0; bi < nb; ++bi) mine[bi].cost = 0;
+        for (size_t j = 0; j < n; ++j) {
+            const XwPlanItem& it = v[j].first;
+            const int c0 = v[j].second;
+            Bundle& bd = mine[best_b[j]];
+            XwU4 e;
+            e.x = (uint32_t)it.cellA | ((uint32_t)it.cellB << 8) | ((uint32_t)it.sel << 16);
+            e.y = w0s[j] | ((uint32_t)it.nrows << 16) | ((uint32_t)ty << 24) | ((uint32_t)c0 << 27) | ((uint32_t)nc << 29);
+            e.z = (uint32_t)it.y0 | ((uint32_t)it.dx << 8) | ((uint32_t)it.scell << 16) | ((uint32_t)it.sbyte << 24);
+            e.w = (uint32_t)it.q | ((uint32_t)it.k << 8) | ((uint32_t)it.band << 16) | ((uint32_t)best_r[j] << 24) | ((uint32_t)it.corner << 31);
+            bd.slots.push_back(e);
+            const double c = xw_item_cost(it, nc);
+            if (c > bd.cost) bd.cost = c;
         }
         for (size_t b = 0; b < nb; ++b) {
             XwU4 pad = {0, (uint32_t)ty << 24, 0, 0};  // padding slot: nc = 0
+            if (mine[b].slots.empty()) continue;
             while (mine[b].slots.size() < 32) mine[b].slots.push_back(pad);
             bundles.push_back(mine[b]);
         }
