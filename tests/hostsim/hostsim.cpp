@@ -25,6 +25,7 @@ struct HostSim {
     std::vector<uint8_t> T;
     std::vector<uint16_t> ecol, uv;
     std::vector<uint32_t> corner;
+    std::vector<uint8_t> colL, colR, rowT, rowB;
     XwRaceCfg race;
 };
 
@@ -120,6 +121,30 @@ HostSim* hs_create(const xw_config* c, const xw_catalog* cat, int n) {
         s->corner.resize((size_t)(cat->n_icons + 1) * 3);
         for (size_t j = 0; j < s->corner.size(); ++j) s->corner[j] = xw_corner_entry(r, (uint32_t)(j / 3), (int)(j % 3));
         r.ecol = s->ecol.data(); r.uv = s->uv.data(); r.corner = s->corner.data();
+        r.sc = t.sc.data(); r.n_sc = (int)t.sc.size();
+        {  // k_build_pair_tables
+            const size_t cs = xw_colpair_stride(r), rs = xw_rowpair_stride(r);
+            const size_t n_col = (size_t)(cat->n_icons + 1) * 2 * cs, n_row = (size_t)(cat->n_icons + 1) * 2 * rs;
+            s->colL.assign(n_col + 64, 0); s->colR.assign(n_col + 64, 0); s->rowT.assign(n_row + 64, 0); s->rowB.assign(n_row + 64, 0);
+            for (int role = 0; role < 2; ++role) {
+                for (size_t i = 0; i < n_col; ++i) {
+                    size_t j = i;
+                    const int row = (int)(j % r.RB); j /= r.RB;
+                    const int band = (int)(j % r.H); j /= r.H;
+                    const int cc = (int)(j % 3); j /= 3;
+                    const int si = (int)(j % r.n_sc); j /= r.n_sc;
+                    (role ? s->colR : s->colL)[i] = xw_colpair_entry(r, role, (uint32_t)(j / 2), (int)(j % 2), si, cc, band, row);
+                }
+                for (size_t i = 0; i < n_row; ++i) {
+                    size_t j = i;
+                    const int dx = (int)(j % r.OW); j /= r.OW;
+                    const int cc = (int)(j % 3); j /= 3;
+                    const int q = (int)(j % r.n_sr); j /= r.n_sr;
+                    (role ? s->rowB : s->rowT)[i] = xw_rowpair_entry(r, role, (uint32_t)(j / 2), (int)(j % 2), q, cc, dx);
+                }
+            }
+            r.colL = s->colL.data(); r.colR = s->colR.data(); r.rowT = s->rowT.data(); r.rowB = s->rowB.data();
+        }
     }
     r.atlas64 = cat->atlas64;
     return s;
@@ -168,6 +193,14 @@ void hs_render(HostSim* s, uint8_t* frames) {
     for (int i = 0; i < r.OH; ++i) yb[i] = (uint32_t)(uint16_t)r.taps.ya0[i] | ((uint32_t)(uint16_t)r.taps.ya1[i] << 16);
     XwComposeCtx x;
     x.hot = r.T + (size_t)r.brick_icon * r.FB; x.yb = yb.data();
+    std::vector<uint8_t> pair_hot;  // the kernel's shared-memory copies: [white, brick][cls][...]
+    if (s->tab.fast_ok) {
+        const size_t cs2 = 2 * xw_colpair_stride(r), rs2 = 2 * xw_rowpair_stride(r);
+        pair_hot.resize(2 * cs2 + 2 * rs2 + 64);
+        memcpy(pair_hot.data(), r.colL, cs2); memcpy(pair_hot.data() + cs2, r.colL + (size_t)(r.brick_icon + 1) * cs2, cs2);
+        memcpy(pair_hot.data() + 2 * cs2, r.rowT, rs2); memcpy(pair_hot.data() + 2 * cs2 + rs2, r.rowT + (size_t)(r.brick_icon + 1) * rs2, rs2);
+        x.colL_hot = pair_hot.data(); x.rowT_hot = pair_hot.data() + 2 * cs2;
+    }
     XwCells cells;
     cells.code = code.data(); cells.icon = icon;
     for (int e = 0; e < d.n; ++e) {

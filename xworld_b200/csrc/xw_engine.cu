@@ -224,9 +224,8 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
     rc |= dupload(s, &r.taps.ya0, t.ya0.data(), t.ya0.size());
     rc |= dupload(s, &r.taps.ya1, t.ya1.data(), t.ya1.size());
     if (t.fast_ok) {
-        // warp groups per CTA: as many private frame buffers as shared memory holds (XW_RENDER_GROUPS /
-        // XW_RENDER_GROUP_THREADS / XW_RENDER_SPLIT_M3 override the choice, for tuning), each group wide
-        // enough to prefetch a whole map (H*W <= 2*GT)
+        // warp groups per CTA: as many pairs of private frame buffers as shared memory holds
+        // (XW_RENDER_GROUPS / XW_RENDER_GROUP_THREADS / XW_RENDER_SPLIT_M3 override the choice, for tuning)
         int max_optin = 0;
         CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
         const char* eg = getenv("XW_RENDER_GROUPS");
@@ -241,7 +240,7 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
         for (; G >= 1 && !found; --G) {
             int GT = et ? atoi(et) : (768 / G) / 32 * 32;  // 768 threads/CTA: 80 registers per thread
             GT = GT / 32 * 32;
-            if (GT < 32 || G * GT > XW_RENDER_THREADS || 2 * GT < c.height * c.width) { if (et) break; continue; }
+            if (GT < 32 || G * GT > XW_RENDER_THREADS) { if (et) break; continue; }
             xw_build_plan(t, GT / 32, split, cfree);
             r.n_plan = (int)t.plan.size();
             if (xw_render_smem(r, G).total > max_optin) continue;
@@ -263,6 +262,14 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
         rc |= dalloc(s, &uv, (size_t)(cat->n_icons + 1) * r.n_sr * 2 * 3 * OW + 8, false);
         rc |= dalloc(s, &corner, (size_t)(cat->n_icons + 1) * 3, false);
         r.ecol = ecol; r.uv = uv; r.corner = corner;
+        static const int16_t zero16b = 0;
+        r.n_sc = (int)t.sc.size();
+        rc |= dupload(s, &r.sc, t.sc.empty() ? &zero16b : t.sc.data(), t.sc.empty() ? 1 : t.sc.size());
+        uint8_t *colL = nullptr, *colR = nullptr, *rowT = nullptr, *rowB = nullptr;
+        const size_t n_col = (size_t)(cat->n_icons + 1) * 2 * r.n_sc * 3 * c.height * t.RB, n_row = (size_t)(cat->n_icons + 1) * 2 * r.n_sr * 3 * OW;
+        rc |= dalloc(s, &colL, n_col + 64, false); rc |= dalloc(s, &colR, n_col + 64, false);
+        rc |= dalloc(s, &rowT, n_row + 64, false); rc |= dalloc(s, &rowB, n_row + 64, false);
+        r.colL = colL; r.colR = colR; r.rowT = rowT; r.rowB = rowB;
     }
     rc |= dupload(s, &r.atlas64, cat->atlas64, (size_t)cat->n_icons * 64 * 64 * 3);
     uint8_t* T = nullptr;
@@ -273,7 +280,8 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
     s->launches++;
     if (t.fast_ok) {
         k_build_edge_tables<<<s->n_sms * 2, 256, 0, s->own_stream>>>(r);
-        s->launches++;
+        k_build_pair_tables<<<s->n_sms * 4, 256, 0, s->own_stream>>>(r);
+        s->launches += 2;
     }
     CUDA_TRY(cudaGetLastError());
     if (t.fast_ok) {

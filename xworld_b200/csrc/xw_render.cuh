@@ -29,7 +29,7 @@
 
 #define XW_MAX_OUT 252        // max frame side
 #define XW_RENDER_THREADS 1024
-#define XW_RENDER_MAX_GROUPS 8
+#define XW_RENDER_MAX_GROUPS 4    // groups per CTA (two frame buffers each)
 #define XW_TABLE_PAD 8192     // bytes past each table the compositor may read (and never use)
 
 struct XwTaps { const int16_t *xofs, *xa0, *xa1, *yofs, *ya0, *ya1; };  // cv::resize tables
@@ -53,6 +53,12 @@ struct XwRender {
     int32_t RB;               // rows per band in ecol (a multiple of 4: one 8-byte load = 4 rows)
     const uint16_t* uv;       // [n_icons+1][n_sr][2][3][OW]  role 0: U from icon row 63, role 1: V from row 0
     const uint32_t* corner;   // [n_icons+1][3]  icon pixels (63,63) | (63,0) << 8 | (0,63) << 16 | (0,0) << 24
+    // pair tables: the finished pixel when the cell on the other side of the border is white (cls 0) or
+    // a brick (cls 1) -- all but a few per cent of the borders of a maze
+    const uint8_t *colL, *colR;  // [n_icons+1][2][n_sc][3][H][RB]  this cell left / right of straddling column s
+    const uint8_t *rowT, *rowB;  // [n_icons+1][2][n_sr][3][OW]     this cell above / below straddling row q
+    const int16_t* sc;        // [n_sc] the straddling columns
+    int32_t n_sc;
     const uint8_t* atlas64;   // [n_icons][64][64][3] BGR
 };
 
@@ -109,6 +115,29 @@ XW_HD uint16_t xw_uv_entry(const XwRender& r, uint32_t dsc, int q, int role, int
                               role == 0 ? t.ya0[dy] : t.ya1[dy]);
 }
 
+// descriptor class: 0 white, 1 brick, 2 anything else ("special": agent, goals)
+XW_HD int xw_cls(const XwRender& r, uint32_t dsc) { return dsc == 0 ? 0 : ((int)dsc - 1 == r.brick_icon ? 1 : 2); }
+XW_HD uint32_t xw_cls_desc(const XwRender& r, int cls) { return cls == 0 ? 0u : (uint32_t)r.brick_icon + 1; }
+// role 0: `dsc` is the LEFT cell and class `cls` the right one; role 1: the other way round
+XW_HD uint8_t xw_colpair_entry(const XwRender& r, int role, uint32_t dsc, int cls, int s, int c, int band, int j) {
+    const XwTaps& t = r.taps;
+    const int dy = r.band_y0[band] + j, dx = r.sc[s];
+    if (r.band_y0[band] < 0 || dy >= r.OH) return 0;
+    const uint32_t dl = role == 0 ? dsc : xw_cls_desc(r, cls), dr = role == 0 ? xw_cls_desc(r, cls) : dsc;
+    const int sy0 = t.yofs[dy], sy1 = t.ya1[dy] ? sy0 + 1 : sy0;
+    return xw_resize_px(xw_canvas_tap(r, dl, sy0, 63, c), xw_canvas_tap(r, dr, sy0, 0, c), xw_canvas_tap(r, dl, sy1, 63, c),
+                        xw_canvas_tap(r, dr, sy1, 0, c), t.xa0[dx], t.xa1[dx], t.ya0[dy], t.ya1[dy]);
+}
+// role 0: `dsc` is the cell ABOVE straddling row q and class `cls` the one below; role 1: the other way round
+XW_HD uint8_t xw_rowpair_entry(const XwRender& r, int role, uint32_t dsc, int cls, int q, int c, int dx) {
+    const XwTaps& t = r.taps;
+    const int dy = r.sr[q];
+    const uint32_t dt = role == 0 ? dsc : xw_cls_desc(r, cls), db = role == 0 ? xw_cls_desc(r, cls) : dsc;
+    const int sx0 = t.xofs[dx], sx1 = t.xa1[dx] ? sx0 + 1 : sx0;
+    return xw_resize_px(xw_canvas_tap(r, dt, 63, sx0, c), xw_canvas_tap(r, dt, 63, sx1, c), xw_canvas_tap(r, db, 0, sx0, c),
+                        xw_canvas_tap(r, db, 0, sx1, c), t.xa0[dx], t.xa1[dx], t.ya0[dy], t.ya1[dy]);
+}
+
 XW_HD uint32_t xw_corner_entry(const XwRender& r, uint32_t dsc, int c) {
     return (uint32_t)xw_canvas_tap(r, dsc, 63, 63, c) | ((uint32_t)xw_canvas_tap(r, dsc, 63, 0, c) << 8) |
            ((uint32_t)xw_canvas_tap(r, dsc, 0, 63, c) << 16) | ((uint32_t)xw_canvas_tap(r, dsc, 0, 0, c) << 24);
@@ -142,7 +171,13 @@ XW_HD uint32_t xw_prmt(uint32_t a, uint32_t b, uint32_t sel) {
 struct XwComposeCtx {
     const uint8_t* hot;     // brick phase table [FB]
     const uint32_t* yb;     // [OH] ya0 | ya1 << 16
+    const uint8_t *colL_hot, *rowT_hot;  // the white and brick entries of colL / rowT: [2 descs][2 cls][stride]
 };
+XW_HD size_t xw_colpair_stride(const XwRender& r) { return (size_t)r.n_sc * 3 * r.H * r.RB; }  // per (desc, cls)
+XW_HD size_t xw_rowpair_stride(const XwRender& r) { return (size_t)r.n_sr * 3 * r.OW; }
+XW_HD int xw_pair_hot_bytes(const XwRender& r) {  // shared-memory copies: desc in {white, brick} x cls x ...
+    return (int)(2 * 2 * (xw_colpair_stride(r) + xw_rowpair_stride(r)));
+}
 
 // Source of a cell's words: word w of the frame comes from *(base + 4*w) | wmask.  White cells read
 // the brick table and OR it to 0xffffffff, so that every lane runs the same instructions.  The words
@@ -177,6 +212,74 @@ XW_HD bool xw_stage_column(const XwRender& r, const XwCells& cells, const uint32
 #define XW_STAGE_SLOTS (1 + XW_MAX_GOALS)  // agent + goals
 #define XW_STAGE_COLS 9                    // 3 planes x up to 3 word columns per cell
 
+// the corner pixel (straddling row x straddling column): taps (63,63) of the top-left cell, (63,0) of the
+// top-right, (0,63) of the bottom-left, (0,0) of the bottom-right
+XW_HD uint32_t xw_corner_px(const XwRender& r, const XwComposeCtx& x, const XwCells& celldesc, int scell, int c, int dy, int dx) {
+    const uint32_t t00 = r.corner[celldesc(scell) * 3 + c], t01 = r.corner[celldesc(scell + 1) * 3 + c];
+    const uint32_t t10 = r.corner[celldesc(scell + r.W) * 3 + c], t11 = r.corner[celldesc(scell + r.W + 1) * 3 + c];
+    const uint32_t b = x.yb[dy];
+    return xw_resize_px(t00 & 255, (t01 >> 8) & 255, (t10 >> 16) & 255, t11 >> 24, r.taps.xa0[dx], r.taps.xa1[dx], b & 0xffff, b >> 16);
+}
+
+// ---- exact (any cells) versions of the straddling items: used when BOTH cells across a border are
+// special, which the pair tables do not cover.  Same item decode as xw_compose_item.
+template <int WR_T>
+XW_HD void xw_item_m3_exact(const XwRender& r, const XwComposeCtx& x, const XwU4 e, const XwCells& celldesc, uint32_t* fb) {
+    const int WR = WR_T ? WR_T : r.WR;
+    const int PW = r.OH * WR;
+    const int nrows = (e.y >> 16) & 0xff, nc = e.y >> 29, c0 = (e.y >> 27) & 3;
+    const uint32_t w0 = e.y & 0xffffu, sel = e.x >> 16;
+    const int cellA = e.x & 0xff, cellB = (e.x >> 8) & 0xff;
+    const int y0 = e.z & 0xff, dx = (e.z >> 8) & 0xff, scell = (e.z >> 16) & 0xff, sh = (e.z >> 24) * 8;
+    const uint32_t dA = celldesc(cellA), dB = celldesc(cellB);
+    const XwSrc sA = xw_src_of(r, x, dA, fb, false), sB = xw_src_of(r, x, dB, fb, xw_special(r, dA));
+    const uint32_t wmask = xw_prmt(sA.wmask, sB.wmask, sel);
+    const int band = (e.w >> 16) & 0xff;
+    const uint16_t* eL0 = r.ecol + ((((size_t)celldesc(scell) * 2 + 0) * 3 + c0) * r.H + band) * r.RB;
+    const uint16_t* eR0 = r.ecol + ((((size_t)celldesc(scell + 1) * 2 + 1) * 3 + c0) * r.H + band) * r.RB;
+    const int a0 = r.taps.xa0[dx], a1 = r.taps.xa1[dx];
+    const uint32_t keep = ~(0xffu << sh);
+    for (int cc = 0; cc < nc; ++cc) {
+        const uint32_t* pA = (const uint32_t*)sA.base + w0 + cc * PW;
+        const uint32_t* pB = (const uint32_t*)sB.base + w0 + cc * PW;
+        uint32_t* dst = fb + w0 + cc * PW;
+        const uint16_t* eL = eL0 + (size_t)cc * r.H * r.RB;
+        const uint16_t* eR = eR0 + (size_t)cc * r.H * r.RB;
+        for (int j = 0; j < nrows; ++j) {
+            const uint32_t tl = eL[j], tr = eR[j], b = x.yb[y0 + j];
+            const uint32_t v = xw_resize_px(tl & 255, tr & 255, tl >> 8, tr >> 8, a0, a1, b & 0xffff, b >> 16);
+            dst[j * WR] = ((xw_prmt(pA[j * WR], pB[j * WR], sel) | wmask) & keep) | (v << sh);
+        }
+    }
+}
+// one word of straddling row q: out = (U[top cell] + V[bottom cell] + 2) >> 2; corner byte from the corner taps
+template <int WR_T>
+XW_HD void xw_item_r_exact(const XwRender& r, const XwComposeCtx& x, const XwU4 e, const XwCells& celldesc, uint32_t* fb) {
+    const int WR = WR_T ? WR_T : r.WR;
+    const int PW = r.OH * WR;
+    const int nc = e.y >> 29, c0 = (e.y >> 27) & 3;
+    const uint32_t w0 = e.y & 0xffffu, sel = e.x >> 16;
+    const int cellA = e.x & 0xff, cellB = (e.x >> 8) & 0xff;
+    const int y0 = e.z & 0xff, dx = (e.z >> 8) & 0xff, scell = (e.z >> 16) & 0xff, sh = (e.z >> 24) * 8;
+    const int q = e.w & 0xff, k = (e.w >> 8) & 0xff;
+    const bool corner = (e.w >> 31) != 0;
+    const size_t per_desc = (size_t)r.n_sr * 2 * 3 * r.OW;
+    const uint16_t* u0 = r.uv + ((size_t)q * 2 * 3 + c0) * r.OW + 4 * k;
+    const uint16_t* v0 = u0 + (size_t)3 * r.OW;
+    const uint16_t *uAp = u0 + celldesc(cellA) * per_desc, *uBp = u0 + celldesc(cellB) * per_desc;
+    const uint16_t *vAp = v0 + celldesc(cellA + r.W) * per_desc, *vBp = v0 + celldesc(cellB + r.W) * per_desc;
+    for (int cc = 0; cc < nc; ++cc) {
+        const XwU2 uA = *(const XwU2*)(uAp + cc * r.OW), uB = *(const XwU2*)(uBp + cc * r.OW);
+        const XwU2 vA = *(const XwU2*)(vAp + cc * r.OW), vB = *(const XwU2*)(vBp + cc * r.OW);
+        // packed u16 pairs: no carry between halves (U + V + 2 <= 2042)
+        const uint32_t a_lo = ((uA.x + vA.x + 0x00020002u) >> 2) & 0x00ff00ffu, a_hi = ((uA.y + vA.y + 0x00020002u) >> 2) & 0x00ff00ffu;
+        const uint32_t b_lo = ((uB.x + vB.x + 0x00020002u) >> 2) & 0x00ff00ffu, b_hi = ((uB.y + vB.y + 0x00020002u) >> 2) & 0x00ff00ffu;
+        uint32_t word = xw_prmt(xw_prmt(a_lo, a_hi, 0x6420), xw_prmt(b_lo, b_hi, 0x6420), sel);
+        if (corner) word = (word & ~(0xffu << sh)) | (xw_corner_px(r, x, celldesc, scell, c0 + cc, y0, dx) << sh);
+        fb[w0 + cc * PW] = word;
+    }
+}
+
 // ---- compose one plan item into the frame being built (fb, words) ----------------------------
 // WR_T = words per frame row when known at compile time (row offsets become immediates), 0 = use r.WR.
 // Rows go four at a time, all loads before the stores: the tables and the frame buffer may alias as
@@ -196,7 +299,8 @@ XW_HD void xw_compose_item(const XwRender& r, const XwComposeCtx& x, const XwU4 
     // plane order of this lane: (rot + i) % 3, chosen by the planner so that the lanes of a bundle stay
     // on different banks (xw_build_plan); po[i] = word offset of the i-th plane visited
     const int rot = (e.w >> 24) & 3;
-    const int po[3] = {rot * PW, (rot == 2 ? 0 : rot + 1) * PW, (rot == 0 ? 2 : rot - 1) * PW};
+    const int pl[3] = {rot, rot == 2 ? 0 : rot + 1, rot == 0 ? 2 : rot - 1};
+    const int po[3] = {pl[0] * PW, pl[1] * PW, pl[2] * PW};
     if (type == XW_ITEM_M1) {
         const XwSrc sA = xw_src_of(r, x, celldesc(cellA), fb, false);
         const uint32_t* pA = (const uint32_t*)sA.base + w0;
@@ -241,74 +345,75 @@ XW_HD void xw_compose_item(const XwRender& r, const XwComposeCtx& x, const XwU4 
     const int c0 = (e.y >> 27) & 3;
     const int y0 = e.z & 0xff, dx = (e.z >> 8) & 0xff, scell = (e.z >> 16) & 0xff, sh = (e.z >> 24) * 8;
     if (type == XW_ITEM_M3) {
+        // an M2 word whose byte `sh` comes from a pair table: (left cell, class of the right cell) or
+        // (right cell, class of the left cell); both special -> the exact version
         const uint32_t dA = celldesc(cellA), dB = celldesc(cellB);
         const XwSrc sA = xw_src_of(r, x, dA, fb, false), sB = xw_src_of(r, x, dB, fb, xw_special(r, dA));
         const uint32_t wmask = xw_prmt(sA.wmask, sB.wmask, sel);
-        const int band = (e.w >> 16) & 0xff;
-        const uint16_t* eL0 = r.ecol + ((((size_t)celldesc(scell) * 2 + 0) * 3 + c0) * r.H + band) * r.RB;
-        const uint16_t* eR0 = r.ecol + ((((size_t)celldesc(scell + 1) * 2 + 1) * 3 + c0) * r.H + band) * r.RB;
-        const int a0 = r.taps.xa0[dx], a1 = r.taps.xa1[dx];
+        const uint32_t* pA = (const uint32_t*)sA.base + w0;
+        const uint32_t* pB = (const uint32_t*)sB.base + w0;
+        uint32_t* dst = fb + w0;
+        const int band = (e.w >> 16) & 0xff, s_idx = e.w & 0xff;
+        const uint32_t dL = celldesc(scell), dR = celldesc(scell + 1);
+        const int cL = xw_cls(r, dL), cR = xw_cls(r, dR);
+        const size_t cs = xw_colpair_stride(r);
+        const uint8_t* tab = x.colL_hot;
+        if (cR < 2) tab = (cL < 2 ? x.colL_hot + (size_t)cL * 2 * cs : r.colL + (size_t)dL * 2 * cs) + (size_t)cR * cs;
+        else if (cL < 2) tab = r.colR + (size_t)dR * 2 * cs + (size_t)cL * cs;
+        const bool need_exact = cL == 2 && cR == 2;
+        tab += ((size_t)(s_idx * 3 + c0) * r.H + band) * r.RB;
+        const int pstride = r.H * r.RB;  // bytes between planes
         const uint32_t keep = ~(0xffu << sh);
-        for (int ci = 0; ci < nc; ++ci) {
-            const int cc = nc == 3 ? (rot + ci >= 3 ? rot + ci - 3 : rot + ci) : ci;
-            const uint32_t* pA = (const uint32_t*)sA.base + w0 + cc * PW;
-            const uint32_t* pB = (const uint32_t*)sB.base + w0 + cc * PW;
-            uint32_t* dst = fb + w0 + cc * PW;
-            const uint16_t* eL = eL0 + (size_t)cc * r.H * r.RB;
-            const uint16_t* eR = eR0 + (size_t)cc * r.H * r.RB;
-            const uint32_t* yb = x.yb + y0;
-            for (int i0 = 0; i0 < nrows; i0 += 4, pA += 4 * WR, pB += 4 * WR, dst += 4 * WR, eL += 4, eR += 4, yb += 4) {
-                uint32_t va[4], vb[4];
+        for (int i0 = 0; i0 < nrows; i0 += 4, pA += 4 * WR, pB += 4 * WR, dst += 4 * WR, tab += 4) {
+            uint32_t va[3][4], vb[3][4], pb[3];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) { va[j] = pA[j * WR]; vb[j] = pB[j * WR]; }
-                const XwU2 tl2 = *(const XwU2*)eL, tr2 = *(const XwU2*)eR;  // four rows of edge taps each
-                const uint32_t tl[4] = {tl2.x & 0xffffu, tl2.x >> 16, tl2.y & 0xffffu, tl2.y >> 16};
-                const uint32_t tr[4] = {tr2.x & 0xffffu, tr2.x >> 16, tr2.y & 0xffffu, tr2.y >> 16};
+            for (int cc = 0; cc < 3; ++cc)
+                if (cc < nc) {
+                    pb[cc] = *(const uint32_t*)(tab + pl[cc] * pstride);  // the straddling byte of four rows
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (i0 + j < nrows) {
-                        const uint32_t b = yb[j];
-                        const uint32_t v = xw_resize_px(tl[j] & 255, tr[j] & 255, tl[j] >> 8, tr[j] >> 8, a0, a1, b & 0xffff, b >> 16);
-                        dst[j * WR] = ((xw_prmt(va[j], vb[j], sel) | wmask) & keep) | (v << sh);
-                    }
-            }
+                    for (int j = 0; j < 4; ++j) { va[cc][j] = pA[po[cc] + j * WR]; vb[cc][j] = pB[po[cc] + j * WR]; }
+                }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (i0 + j < nrows) {
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc)
+                        if (cc < nc)
+                            dst[po[cc] + j * WR] = ((xw_prmt(va[cc][j], vb[cc][j], sel) | wmask) & keep) | (((pb[cc] >> (8 * j)) & 0xffu) << sh);
+                }
         }
+        if (need_exact) xw_item_m3_exact<WR_T>(r, x, e, celldesc, fb);
         return;
     }
-    // R: one word of straddling row q: out = (U[top cell] + V[bottom cell] + 2) >> 2
+    // R: one word of straddling row q, from the row pair tables: per cell column (top cell, class of the
+    // bottom cell) or (bottom cell, class of the top cell); both special -> the exact version
     const int q = e.w & 0xff, k = (e.w >> 8) & 0xff;
     const bool corner = (e.w >> 31) != 0;
-    const size_t per_desc = (size_t)r.n_sr * 2 * 3 * r.OW;
-    const uint16_t* u0 = r.uv + ((size_t)q * 2 * 3 + c0) * r.OW + 4 * k;
-    const uint16_t* v0 = u0 + (size_t)3 * r.OW;
-    const uint16_t *uAp = u0 + celldesc(cellA) * per_desc, *uBp = u0 + celldesc(cellB) * per_desc;
-    const uint16_t *vAp = v0 + celldesc(cellA + r.W) * per_desc, *vBp = v0 + celldesc(cellB + r.W) * per_desc;
-    XwU2 uA[3], uB[3], vA[3], vB[3];
+    const size_t rs = xw_rowpair_stride(r);
+    bool need_exact = false;
+    const uint8_t* tabs[2];
 #pragma unroll
-    for (int ci = 0; ci < 3; ++ci)
-        if (ci < nc) {
-            const int cc = nc == 3 ? (rot + ci >= 3 ? rot + ci - 3 : rot + ci) : ci;
-            uA[ci] = *(const XwU2*)(uAp + cc * r.OW); uB[ci] = *(const XwU2*)(uBp + cc * r.OW);
-            vA[ci] = *(const XwU2*)(vAp + cc * r.OW); vB[ci] = *(const XwU2*)(vBp + cc * r.OW);
-        }
+    for (int h = 0; h < 2; ++h) {
+        const int cell = h ? cellB : cellA;
+        const uint32_t dT = celldesc(cell), dBt = celldesc(cell + r.W);
+        const int cT = xw_cls(r, dT), cB = xw_cls(r, dBt);
+        const uint8_t* tab = x.rowT_hot;
+        if (cB < 2) tab = (cT < 2 ? x.rowT_hot + (size_t)cT * 2 * rs : r.rowT + (size_t)dT * 2 * rs) + (size_t)cB * rs;
+        else if (cT < 2) tab = r.rowB + (size_t)dBt * 2 * rs + (size_t)cT * rs;
+        else need_exact = true;
+        tabs[h] = tab + (size_t)(q * 3 + c0) * r.OW + 4 * k;
+    }
+    if (need_exact) { xw_item_r_exact<WR_T>(r, x, e, celldesc, fb); return; }
+    uint32_t wa[3], wb[3];
 #pragma unroll
-    for (int ci = 0; ci < 3; ++ci)
-        if (ci < nc) {
-            const int cc = nc == 3 ? (rot + ci >= 3 ? rot + ci - 3 : rot + ci) : ci;
-            // packed u16 pairs: no carry between halves (U + V + 2 <= 2042)
-            const uint32_t a_lo = ((uA[ci].x + vA[ci].x + 0x00020002u) >> 2) & 0x00ff00ffu, a_hi = ((uA[ci].y + vA[ci].y + 0x00020002u) >> 2) & 0x00ff00ffu;
-            const uint32_t b_lo = ((uB[ci].x + vB[ci].x + 0x00020002u) >> 2) & 0x00ff00ffu, b_hi = ((uB[ci].y + vB[ci].y + 0x00020002u) >> 2) & 0x00ff00ffu;
-            uint32_t word = xw_prmt(xw_prmt(a_lo, a_hi, 0x6420), xw_prmt(b_lo, b_hi, 0x6420), sel);
-            if (corner) {  // taps: (63,63) of the top-left cell, (63,0) top-right, (0,63) bottom-left, (0,0) bottom-right
-                const int c = c0 + cc;
-                const uint32_t t00 = r.corner[celldesc(scell) * 3 + c], t01 = r.corner[celldesc(scell + 1) * 3 + c];
-                const uint32_t t10 = r.corner[celldesc(scell + r.W) * 3 + c], t11 = r.corner[celldesc(scell + r.W + 1) * 3 + c];
-                const uint32_t b = x.yb[y0];
-                const uint32_t v = xw_resize_px(t00 & 255, (t01 >> 8) & 255, (t10 >> 16) & 255, t11 >> 24, r.taps.xa0[dx], r.taps.xa1[dx],
-                                                b & 0xffff, b >> 16);
-                word = (word & ~(0xffu << sh)) | (v << sh);
-            }
-            fb[w0 + cc * PW] = word;
+    for (int cc = 0; cc < 3; ++cc)
+        if (cc < nc) { wa[cc] = *(const uint32_t*)(tabs[0] + pl[cc] * r.OW); wb[cc] = *(const uint32_t*)(tabs[1] + pl[cc] * r.OW); }
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc)
+        if (cc < nc) {
+            uint32_t word = xw_prmt(wa[cc], wb[cc], sel);
+            if (corner) word = (word & ~(0xffu << sh)) | (xw_corner_px(r, x, celldesc, scell, c0 + pl[cc], y0, dx) << sh);
+            fb[w0 + po[cc]] = word;
         }
 }
 
@@ -321,20 +426,24 @@ XW_HD uint32_t xw_cell_desc(const XwDev& d, int e, int code) {
 }
 #define XW_CODE_SLOTS (XW_CELL_GOAL0 + XW_MAX_GOALS + 5)  // 16 descriptors per env
 
+
 // Dynamic shared memory layout (bytes), all sections 16-byte aligned:
 //   brick phase table (TMA bulk load, once) | G frame buffers | plan | yb | G cell arrays | mbarrier
 #define XW_CELL_STRIDE (XW_MAX_DIM * XW_MAX_DIM + 2 * XW_MAX_DIM)  // bytes: the map + the (never drawn) row below it
-struct XwRenderSmem { int hot, fb, plan, yb, cellinfo, cell, bar, total; };
+// one cell buffer: codes | descriptors per code | cell of the agent / of goal g (XW_STAGE_SLOTS bytes)
+#define XW_CELLBUF_BYTES (XW_CELL_STRIDE + XW_CODE_SLOTS * 4 + 16)
+struct XwRenderSmem { int hot, fb, plan, yb, cellinfo, pair, cell, bar, total; };
 XW_HD int xw_align16(int v) { return (v + 15) & ~15; }
 XW_HD XwRenderSmem xw_render_smem(const XwRender& r, int G) {
     XwRenderSmem s;
     int o = 0;
     s.hot = o; o += xw_align16(r.FB);
-    s.fb = o; o += G * xw_align16(r.FB);
+    s.fb = o; o += 2 * G * xw_align16(r.FB);  // two frame buffers per group
     s.plan = o; o += r.n_plan * 16;
     s.yb = o; o += xw_align16(r.OH * 4);
     s.cellinfo = o; o += XW_MAX_DIM * XW_MAX_DIM * 4;
-    s.cell = o; o += G * (XW_CELL_STRIDE + XW_CODE_SLOTS * 4 + 16);
+    s.pair = o; o += xw_align16(xw_pair_hot_bytes(r));
+    s.cell = o; o += 2 * G * XW_CELLBUF_BYTES;  // two cell buffers per group
     s.bar = o; o += 16;
     s.total = o;
     return s;
@@ -369,6 +478,30 @@ __global__ void k_build_edge_tables(XwRender r) {
             const int c = (int)(j % 3); j /= 3;
             const int role = (int)(j % 2); j /= 2;
             ((uint16_t*)r.uv)[i - n_ecol] = xw_uv_entry(r, (uint32_t)(j / r.n_sr), (int)(j % r.n_sr), role, c, dx);
+        }
+    }
+}
+
+__global__ void k_build_pair_tables(XwRender r) {
+    const size_t cs = xw_colpair_stride(r), rs = xw_rowpair_stride(r);
+    const size_t n_col = (size_t)(r.n_icons + 1) * 2 * cs, n_row = (size_t)(r.n_icons + 1) * 2 * rs;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * (n_col + n_row); i += (size_t)gridDim.x * blockDim.x) {
+        if (i < 2 * n_col) {
+            const int role = i >= n_col;
+            size_t j = i - role * n_col;
+            const int row = (int)(j % r.RB); j /= r.RB;
+            const int band = (int)(j % r.H); j /= r.H;
+            const int c = (int)(j % 3); j /= 3;
+            const int s = (int)(j % r.n_sc); j /= r.n_sc;
+            ((uint8_t*)(role ? r.colR : r.colL))[i - role * n_col] = xw_colpair_entry(r, role, (uint32_t)(j / 2), (int)(j % 2), s, c, band, row);
+        } else {
+            const size_t i2 = i - 2 * n_col;
+            const int role = i2 >= n_row;
+            size_t j = i2 - role * n_row;
+            const int dx = (int)(j % r.OW); j /= r.OW;
+            const int c = (int)(j % 3); j /= 3;
+            const int q = (int)(j % r.n_sr); j /= r.n_sr;
+            ((uint8_t*)(role ? r.rowB : r.rowT))[i2 - role * n_row] = xw_rowpair_entry(r, role, (uint32_t)(j / 2), (int)(j % 2), q, c, dx);
         }
     }
 }
@@ -415,7 +548,13 @@ __device__ __forceinline__ void group_bar(int id, int nthreads) {
 }
 
 // Persistent CTAs.  Group g of CTA b renders envs (b*G + g) + i * gridDim.x*G; the frame of env e goes
-// to frames + e*env_stride.
+// to frames + e*env_stride.  Each group owns TWO frame buffers and runs a two-stage pipeline with one
+// group barrier per env:
+//   warp 0 of the group is also the loader: while the group composes env i into buffer i&1 it stores the
+//   (register-prefetched) cells of env i+1 into the other cell buffer, prefetches env i+2, waits until
+//   the TMA store of env i-1 has drained buffer (i+1)&1 and stages env i+1's agent / goal table words
+//   into it (LDGSTS, no registers).  After the barrier thread 0 hands buffer i&1 to the TMA engine and
+//   everybody starts env i+1 at once.
 template <int WR_T, int NT_MAX>
 __global__ void __launch_bounds__(NT_MAX, 1)
 k_render(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
@@ -427,7 +566,6 @@ k_render(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
     uint32_t* s_yb = (uint32_t*)(smem + L.yb);
     uint64_t* bar = (uint64_t*)(smem + L.bar);
     const int tid = threadIdx.x, nt = blockDim.x;
-    const int HW = r.H * r.W;
 
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -438,71 +576,116 @@ k_render(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
         mbar_expect_tx(bar, (uint32_t)r.FB);
         tma_load_1d(hot, r.T + (size_t)r.brick_icon * r.FB, (uint32_t)r.FB, bar);
     }
-    {  // plan + row weights -> shared memory
+    {  // plan + row weights + cell geometry -> shared memory
         for (int i = tid; i < r.n_plan; i += nt) s_plan[i] = r.plan[i];
         for (int i = tid; i < r.H * r.W; i += nt) ((uint32_t*)(smem + L.cellinfo))[i] = r.cellinfo[i];
         for (int i = tid; i < r.OH; i += nt) s_yb[i] = (uint32_t)(uint16_t)r.taps.ya0[i] | ((uint32_t)(uint16_t)r.taps.ya1[i] << 16);
+        for (int i = tid; i < G * 2 * XW_CELLBUF_BYTES / 4; i += nt) ((uint32_t*)(smem + L.cell))[i] = 0;
+        // white / brick entries of the pair tables: [desc in {white, brick}][cls][...]
+        const int cs2 = (int)(2 * xw_colpair_stride(r)), rs2 = (int)(2 * xw_rowpair_stride(r));
+        uint8_t* pc = smem + L.pair;
+        uint8_t* pr = pc + 2 * cs2;
+        for (int i = tid; i < 2 * cs2; i += nt) pc[i] = r.colL[(size_t)(i < cs2 ? 0 : r.brick_icon + 1) * cs2 + (i < cs2 ? i : i - cs2)];
+        for (int i = tid; i < 2 * rs2; i += nt) pr[i] = r.rowT[(size_t)(i < rs2 ? 0 : r.brick_icon + 1) * rs2 + (i < rs2 ? i : i - rs2)];
     }
     mbar_wait(bar, 0);
     __syncthreads();
 
     const int g = tid / GT, gt = tid - g * GT;
     if (g >= G) return;  // spare warps (G*GT < blockDim.x)
-    uint8_t* s_code = smem + L.cell + g * (XW_CELL_STRIDE + XW_CODE_SLOTS * 4 + 16);
-    uint32_t* s_icon = (uint32_t*)(s_code + XW_CELL_STRIDE);
-    uint8_t* s_special = (uint8_t*)(s_icon + XW_CODE_SLOTS);  // [XW_STAGE_SLOTS] cell of the agent / goal g
     const uint32_t* s_cellinfo = (const uint32_t*)(smem + L.cellinfo);
-    uint32_t* fb = (uint32_t*)(smem + L.fb + (size_t)g * xw_align16(r.FB));
+    uint8_t* cellbuf = smem + L.cell + (size_t)g * 2 * XW_CELLBUF_BYTES;
+    uint8_t* fbbuf = smem + L.fb + (size_t)g * 2 * xw_align16(r.FB);
     XwComposeCtx x;
     x.hot = hot; x.yb = s_yb;
-    XwCells cells;
-    cells.code = s_code; cells.icon = s_icon;
+    x.colL_hot = smem + L.pair; x.rowT_hot = smem + L.pair + 4 * xw_colpair_stride(r);
     const int bar_id = 1 + g;
     const int n_plan = r.n_plan;
     const int gstride = gridDim.x * G;
-    int env = blockIdx.x * G + g;
+    const bool loader = gt < 32;  // warp 0 of the group
+    const int lane = gt & 31;
+    const int row_words = d.CS >> 2;  // <= 64: two words per loader lane
+    const int WR = WR_T ? WR_T : r.WR;
 
-    // register prefetch of the env's grid row (CS bytes = CS/4 words, CS/4 <= 64 <= GT) and goal icons
-    const int row_words = d.CS >> 2;
-    uint32_t nq = 0, ni = 0;
-    if (env < d.n) {
-        if (gt < row_words) nq = ((const uint32_t*)(d.grid + (size_t)env * d.CS))[gt];
-        if (gt < d.G) ni = (uint32_t)d.goal_icon[(size_t)gt * d.n + env] + 1;
-    }
-    for (int i = gt; i < XW_CELL_STRIDE / 4; i += GT) ((uint32_t*)s_code)[i] = 0;
-    if (gt < XW_CODE_SLOTS) s_icon[gt] = gt == XW_CELL_BLOCK ? (uint32_t)d.brick_icon + 1 : gt == XW_CELL_AGENT ? (uint32_t)d.agent_icon + 1 : 0;
-    for (; env < d.n; env += gstride) {
-        if (gt < row_words) {  // (every warp passed the barrier after the last compose)
-            ((uint32_t*)s_code)[gt] = nq;
+    // loader registers: the grid row + goal icons of the env after next
+    uint32_t nq0 = 0, nq1 = 0, ni = 0;
+    auto load_cells = [&](int e) {
+        if (e < d.n) {
+            const uint32_t* row = (const uint32_t*)(d.grid + (size_t)e * d.CS);
+            if (lane < row_words) nq0 = row[lane];
+            if (lane + 32 < row_words) nq1 = row[lane + 32];
+            if (lane < d.G) ni = (uint32_t)d.goal_icon[(size_t)lane * d.n + e] + 1;
+        }
+    };
+    auto store_cells = [&](int buf) {  // registers -> cell buffer `buf`: codes, descriptors, where the specials are
+        uint8_t* code = cellbuf + buf * XW_CELLBUF_BYTES;
+        uint32_t* icon = (uint32_t*)(code + XW_CELL_STRIDE);
+        uint8_t* special = (uint8_t*)(icon + XW_CODE_SLOTS);
+        if (lane == XW_CELL_BLOCK) icon[lane] = (uint32_t)d.brick_icon + 1;
+        if (lane == XW_CELL_AGENT) icon[lane] = (uint32_t)d.agent_icon + 1;
+        if (lane < d.G) icon[XW_CELL_GOAL0 + lane] = ni;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {  // where the agent and the goals are
-                const uint32_t code = (nq >> (8 * b)) & 0xff;
-                if (code >= XW_CELL_AGENT) s_special[code - XW_CELL_AGENT] = (uint8_t)(4 * gt + b);
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t q = h ? nq1 : nq0;
+            const int wi = lane + 32 * h;
+            if (wi < row_words) {
+                ((uint32_t*)code)[wi] = q;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const uint32_t c = (q >> (8 * b)) & 0xff;
+                    if (c >= XW_CELL_AGENT) special[c - XW_CELL_AGENT] = (uint8_t)(4 * wi + b);
+                }
             }
         }
-        if (gt < d.G) s_icon[XW_CELL_GOAL0 + gt] = ni;
-        if (gt == 0) tma_wait_read<0>();  // the TMA store of this group's previous frame has drained fb
-        group_bar(bar_id, GT);
-        // stage the agent's and goals' table words into the frame buffer (LDGSTS, no registers): one
-        // thread per (cell, plane, word column), one 4-byte copy per row
-        for (int i = gt; i < (1 + d.G) * XW_STAGE_COLS; i += GT) {
+        __syncwarp();
+    };
+    auto stage = [&](int buf) {  // LDGSTS the special cells' table words of cell buffer `buf` into frame buffer `buf`
+        XwCells cells;
+        cells.code = cellbuf + buf * XW_CELLBUF_BYTES;
+        cells.icon = (const uint32_t*)(cells.code + XW_CELL_STRIDE);
+        const uint8_t* special = (const uint8_t*)(cells.icon + XW_CODE_SLOTS);
+        uint32_t* fb = (uint32_t*)(fbbuf + (size_t)buf * xw_align16(r.FB));
+        for (int i = lane; i < (1 + d.G) * XW_STAGE_COLS; i += 32) {
             const int slot = i / XW_STAGE_COLS, col = i - slot * XW_STAGE_COLS, c = col / 3, wc = col - 3 * c;
             uint32_t w0; int nrows; const uint32_t* src;
-            if (xw_stage_column(r, cells, s_cellinfo, s_special[slot], c, wc, &w0, &nrows, &src)) {
-                const int WR = WR_T ? WR_T : r.WR;
+            if (xw_stage_column(r, cells, s_cellinfo, special[slot], c, wc, &w0, &nrows, &src))
                 for (int j = 0; j < nrows; ++j) cp_async_4(fb + w0 + j * WR, src + j * WR);
-            }
         }
+    };
+
+    int env = blockIdx.x * G + g;
+    if (env >= d.n) return;
+    if (loader) {  // prologue: env 0 of this group goes in directly, env 1 into the registers
+        load_cells(env);
+        store_cells(0);
+        stage(0);
+        load_cells(env + gstride);
         cp_async_wait_all();
-        group_bar(bar_id, GT);
-        {  // prefetch the next env's cells while this one is composed
-            const int en = env + gstride;
-            if (en < d.n) {
-                if (gt < row_words) nq = ((const uint32_t*)(d.grid + (size_t)en * d.CS))[gt];
-                if (gt < d.G) ni = (uint32_t)d.goal_icon[(size_t)gt * d.n + en] + 1;
+    }
+    group_bar(bar_id, GT);
+    for (int it = 0; env < d.n; env += gstride, ++it) {
+        const int buf = it & 1;
+        XwCells cells;
+        cells.code = cellbuf + buf * XW_CELLBUF_BYTES;
+        cells.icon = (const uint32_t*)(cells.code + XW_CELL_STRIDE);
+        uint32_t* fb = (uint32_t*)(fbbuf + (size_t)buf * xw_align16(r.FB));
+        const bool have_next = env + gstride < d.n;
+        if (loader && have_next) {
+            store_cells(buf ^ 1);             // env i+1's cells (every warp is past env i-1, which used this buffer)
+            load_cells(env + 2 * gstride);    // env i+2 -> registers
+        }
+        bool staged = !(loader && have_next);
+        for (int i = gt; i < n_plan; i += GT) {
+            xw_compose_item<WR_T>(r, x, s_plan[i], cells, fb);
+            if (!staged) {  // after the first bundle: by now the TMA store of env i-1 has usually drained
+                if (lane == 0) tma_wait_read<0>();
+                __syncwarp();
+                stage(buf ^ 1);
+                staged = true;
             }
         }
-        for (int i = gt; i < n_plan; i += GT) xw_compose_item<WR_T>(r, x, s_plan[i], cells, fb);
+        if (!staged) { if (lane == 0) tma_wait_read<0>(); __syncwarp(); stage(buf ^ 1); }
+        if (loader) cp_async_wait_all();
         fence_async_smem();  // generic-proxy writes -> visible to the async (TMA) proxy
         group_bar(bar_id, GT);
         if (gt == 0) {

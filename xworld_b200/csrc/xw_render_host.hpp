@@ -31,7 +31,8 @@ enum { XW_ITEM_M1 = 0, XW_ITEM_M2 = 1, XW_ITEM_M3 = 2, XW_ITEM_R = 3, XW_ITEM_TY
 //                                          first plane, number of planes (0 = padding slot)
 //   z = y0 | dx << 8 | scell << 16 | sbyte << 24    first row; M3 / R-with-corner: the straddling column,
 //                                          its left cell (the right one is scell + 1), its byte in the word
-//   w = q | k << 8 | band << 16 | rot << 24 | corner << 31     R: index of the straddling row, word column,
+//   w = q | k << 8 | band << 16 | rot << 24 | corner << 31     R: index of the straddling row (M3: of the
+//                                          straddling column), word column,
 //                                          corner flag; M3: band = cell row (edge tables are stored per
 //                                          band); rot: the item visits planes (rot + i) % 3, i = 0,1,2
 // The plan is a sequence of 32-slot bundles of one type; bundle b belongs to warp b % n_warps of a
@@ -39,7 +40,7 @@ enum { XW_ITEM_M1 = 0, XW_ITEM_M2 = 1, XW_ITEM_M3 = 2, XW_ITEM_R = 3, XW_ITEM_TY
 struct alignas(16) XwU4 { uint32_t x, y, z, w; };
 struct alignas(8) XwU2 { uint32_t x, y; };
 
-struct XwPlanItem { int cellA, cellB, sel, woff, nrows, type, y0, k, sbyte, scell, dx, q, corner, band; };
+struct XwPlanItem { int cellA, cellB, sel, woff, nrows, type, y0, k, sbyte, scell, dx, q, corner, band, sidx; };
 
 struct XwRenderTables {
     int H = 0, W = 0, OH = 0, OW = 0, WR = 0, FB = 0;
@@ -84,7 +85,8 @@ inline XwRenderTables xw_build_render_tables(int H, int W, int OH, int OW) {
         if (t.xa1[dx] != 0 && ((t.xofs[dx] + 1) >> 6) != (t.xofs[dx] >> 6)) { t.sc.push_back((int16_t)dx); is_sc[dx] = 1; }
     for (int dy = 0; dy < OH; ++dy)
         if (t.ya1[dy] != 0 && ((t.yofs[dy] + 1) >> 6) != (t.yofs[dy] >> 6)) { t.sr.push_back((int16_t)dy); is_sr[dy] = 1; }
-    bool ok = (OW % 4 == 0) && (t.FB % 16 == 0) && OH <= 255 && OW <= 252 && OH * (OW / 4) <= 65535 && t.sr.size() <= 255;
+    bool ok = (OW % 4 == 0) && (t.FB % 16 == 0) && OH <= 255 && OW <= 252 && OH * (OW / 4) <= 65535 && t.sr.size() <= 255 &&
+              t.sc.size() <= 255;
     // a straddling row is the last row of its band (yofs is monotone); two in one band (upscaling)
     // would break the plan
     for (size_t q = 0; q < t.sr.size() && ok; ++q) {
@@ -115,7 +117,10 @@ inline XwRenderTables xw_build_render_tables(int H, int W, int OH, int OW) {
                 if (tx[i] == A) it.sel |= i << (4 * i);
                 else if (tx[i] == B) it.sel |= (4 + i) << (4 * i);
                 else ok = false;  // a 4-pixel word spans 3 cells: cells narrower than 2 px
-                if (is_sc[4 * k + i]) { ++n_sc; it.sbyte = i; it.scell = ty * W + tx[i]; it.dx = 4 * k + i; }
+                if (is_sc[4 * k + i]) {
+                    ++n_sc; it.sbyte = i; it.scell = ty * W + tx[i]; it.dx = 4 * k + i;
+                    for (size_t si = 0; si < t.sc.size(); ++si) if (t.sc[si] == 4 * k + i) it.sidx = (int)si;
+                }
             }
             if (n_sc > 1) ok = false;  // two straddling columns in one word: cells narrower than 4 px
             it.cellA = ty * W + A; it.cellB = ty * W + B;
@@ -157,10 +162,10 @@ inline XwRenderTables xw_build_render_tables(int H, int W, int OH, int OW) {
 // Cost model of one item (instructions), calibrated on ncu source counters (profiles/).
 inline double xw_item_cost(const XwPlanItem& it, int nc) {
     switch (it.type) {
-        case XW_ITEM_M1: return 60 + nc * (8 + it.nrows * 5.3);
-        case XW_ITEM_M2: return 75 + nc * (8 + it.nrows * 8.0);
-        case XW_ITEM_M3: return 110 + nc * (12 + it.nrows * 30.0);
-        default: return 90 + nc * (45.0 + (it.corner ? 45.0 : 0.0));
+        case XW_ITEM_M1: return 50 + nc * (6 + it.nrows * 5.0);
+        case XW_ITEM_M2: return 80 + nc * (6 + it.nrows * 10.0);
+        case XW_ITEM_M3: return 110 + nc * (8 + it.nrows * 13.0);
+        default: return 90 + nc * (20.0 + (it.corner ? 45.0 : 0.0));
     }
 }
 
@@ -234,7 +239,8 @@ inline void xw_build_plan(XwRenderTables& t, int n_warps, bool split_m3, bool co
             e.x = (uint32_t)it.cellA | ((uint32_t)it.cellB << 8) | ((uint32_t)it.sel << 16);
             e.y = w0s[j] | ((uint32_t)it.nrows << 16) | ((uint32_t)ty << 24) | ((uint32_t)c0 << 27) | ((uint32_t)nc << 29);
             e.z = (uint32_t)it.y0 | ((uint32_t)it.dx << 8) | ((uint32_t)it.scell << 16) | ((uint32_t)it.sbyte << 24);
-            e.w = (uint32_t)it.q | ((uint32_t)it.k << 8) | ((uint32_t)it.band << 16) | ((uint32_t)best_r[j] << 24) | ((uint32_t)it.corner << 31);
+            e.w = (uint32_t)(ty == XW_ITEM_M3 ? it.sidx : it.q) | ((uint32_t)it.k << 8) | ((uint32_t)it.band << 16) | ((uint32_t)best_r[j] << 24) |
+                  ((uint32_t)it.corner << 31);
             bd.slots.push_back(e);
             const double c = xw_item_cost(it, nc);
             if (c > bd.cost) bd.cost = c;
@@ -250,6 +256,7 @@ inline void xw_build_plan(XwRenderTables& t, int n_warps, bool split_m3, bool co
     std::stable_sort(bundles.begin(), bundles.end(), [](const Bundle& a, const Bundle& b) { return a.cost > b.cost; });
     std::vector<std::vector<int>> mine(n_warps);
     std::vector<double> load(n_warps, 0.0);
+    load[0] = 250.0;  // warp 0 of a group is also the loader (cells, staging): k_render
     t.total_cost = 0;
     for (size_t b = 0; b < bundles.size(); ++b) {
         int w = 0;
