@@ -94,6 +94,7 @@ struct xw_sim {
     XwRenderTables tab;
     std::vector<void*> allocs;
     int n_sms = 148, render_grid = 0, render_smem = 0;
+    bool render_sb = false;
     void (*render_fn)(XwDev, XwRender, uint8_t*, size_t) = nullptr;  // k_render<WR> for this frame width
     int C = 3;
     // race
@@ -234,16 +235,22 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
         const bool split = es ? atoi(es) != 0 : false;
         const char* ec = getenv("XW_RENDER_CONFLICT_FREE");
         const bool cfree = ec ? atoi(ec) != 0 : false;
-        int G = eg ? atoi(eg) : XW_RENDER_MAX_GROUPS;
-        if (G > XW_RENDER_MAX_GROUPS) G = XW_RENDER_MAX_GROUPS;
+        // "sb" (default): one frame buffer per group, up to 8 groups; "pipe": two per group, up to 4 groups.
+        // Measured on B200 (profiles/r01_summary.md): sb 8x64 threads is the fastest at 84x84 frames.
+        const char* em = getenv("XW_RENDER_MODE");
+        s->render_sb = !(em && !strcmp(em, "pipe"));
+        const int max_groups = s->render_sb ? 2 * XW_RENDER_MAX_GROUPS : XW_RENDER_MAX_GROUPS;
+        int G = eg ? atoi(eg) : max_groups;
+        if (G > max_groups) G = max_groups;
         bool found = false;
         for (; G >= 1 && !found; --G) {
-            int GT = et ? atoi(et) : (768 / G) / 32 * 32;  // 768 threads/CTA: 80 registers per thread
+            // <= 512 threads/CTA keeps 124 registers per thread (no spills, 24-word load batches)
+            int GT = et ? atoi(et) : (G >= 6 ? 64 : (768 / G) / 32 * 32);
             GT = GT / 32 * 32;
             if (GT < 32 || G * GT > XW_RENDER_THREADS) { if (et) break; continue; }
             xw_build_plan(t, GT / 32, split, cfree);
             r.n_plan = (int)t.plan.size();
-            if (xw_render_smem(r, G).total > max_optin) continue;
+            if (xw_render_smem(r, s->render_sb ? (G + 1) / 2 : G).total > max_optin) continue;
             r.G = G; r.GT = GT;
             found = true;
         }
@@ -285,12 +292,15 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
     }
     CUDA_TRY(cudaGetLastError());
     if (t.fast_ok) {
-        s->render_smem = xw_render_smem(r, r.G).total;
+        s->render_smem = xw_render_smem(r, s->render_sb ? (r.G + 1) / 2 : r.G).total;
         // instantiations: compile-time row stride for the common frame widths x register budget by CTA size
         const int nt = r.G * r.GT;
 #define XW_PICK(WR_) (nt <= 512 ? k_render<WR_, 512> : nt <= 768 ? k_render<WR_, 768> : k_render<WR_, 1024>)
-        s->render_fn = r.WR == 21 ? XW_PICK(21) : r.WR == 24 ? XW_PICK(24) : r.WR == 32 ? XW_PICK(32) : XW_PICK(0);
+#define XW_PICK_SB(WR_) (nt <= 512 ? k_render_sb<WR_, 512> : nt <= 768 ? k_render_sb<WR_, 768> : k_render_sb<WR_, 1024>)
+        if (s->render_sb) s->render_fn = r.WR == 21 ? XW_PICK_SB(21) : r.WR == 24 ? XW_PICK_SB(24) : r.WR == 32 ? XW_PICK_SB(32) : XW_PICK_SB(0);
+        else s->render_fn = r.WR == 21 ? XW_PICK(21) : r.WR == 24 ? XW_PICK(24) : r.WR == 32 ? XW_PICK(32) : XW_PICK(0);
 #undef XW_PICK
+#undef XW_PICK_SB
         CUDA_TRY(cudaFuncSetAttribute(s->render_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, s->render_smem));
         s->render_grid = s->n_sms;
     }

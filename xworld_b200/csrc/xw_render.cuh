@@ -696,6 +696,112 @@ k_render(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
     if (gt == 0) tma_wait_all<0>();
 }
 
+// Single-buffer variant of k_render (XW_RENDER_MODE=sb): r.G groups with ONE frame buffer each and
+// three group barriers per env (cells visible / staged words visible / compose done).  More groups and
+// warps per SM, more synchronisation per env.  Same compose code, same shared-memory layout function
+// (called with (G+1)/2 buffer pairs).
+template <int WR_T, int NT_MAX>
+__global__ void __launch_bounds__(NT_MAX, 1)
+k_render_sb(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int G = r.G, GT = r.GT;
+    const XwRenderSmem L = xw_render_smem(r, (G + 1) / 2);
+    uint8_t* hot = smem + L.hot;
+    XwU4* s_plan = (XwU4*)(smem + L.plan);
+    uint32_t* s_yb = (uint32_t*)(smem + L.yb);
+    uint64_t* bar = (uint64_t*)(smem + L.bar);
+    const int tid = threadIdx.x, nt = blockDim.x;
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {  // stage the brick table: one TMA bulk load per CTA
+        mbar_expect_tx(bar, (uint32_t)r.FB);
+        tma_load_1d(hot, r.T + (size_t)r.brick_icon * r.FB, (uint32_t)r.FB, bar);
+    }
+    {  // plan + row weights + pair-table heads -> shared memory
+        for (int i = tid; i < r.n_plan; i += nt) s_plan[i] = r.plan[i];
+        for (int i = tid; i < r.H * r.W; i += nt) ((uint32_t*)(smem + L.cellinfo))[i] = r.cellinfo[i];
+        for (int i = tid; i < r.OH; i += nt) s_yb[i] = (uint32_t)(uint16_t)r.taps.ya0[i] | ((uint32_t)(uint16_t)r.taps.ya1[i] << 16);
+        const int cs2 = (int)(2 * xw_colpair_stride(r)), rs2 = (int)(2 * xw_rowpair_stride(r));
+        uint8_t* pc = smem + L.pair;
+        uint8_t* pr = pc + 2 * cs2;
+        for (int i = tid; i < 2 * cs2; i += nt) pc[i] = r.colL[(size_t)(i < cs2 ? 0 : r.brick_icon + 1) * cs2 + (i < cs2 ? i : i - cs2)];
+        for (int i = tid; i < 2 * rs2; i += nt) pr[i] = r.rowT[(size_t)(i < rs2 ? 0 : r.brick_icon + 1) * rs2 + (i < rs2 ? i : i - rs2)];
+    }
+    mbar_wait(bar, 0);
+    __syncthreads();
+
+    const int g = tid / GT, gt = tid - g * GT;
+    if (g >= G) return;  // spare warps (G*GT < blockDim.x)
+    uint8_t* s_code = smem + L.cell + g * XW_CELLBUF_BYTES;
+    uint32_t* s_icon = (uint32_t*)(s_code + XW_CELL_STRIDE);
+    uint8_t* s_special = (uint8_t*)(s_icon + XW_CODE_SLOTS);  // [XW_STAGE_SLOTS] cell of the agent / goal g
+    const uint32_t* s_cellinfo = (const uint32_t*)(smem + L.cellinfo);
+    uint32_t* fb = (uint32_t*)(smem + L.fb + (size_t)g * xw_align16(r.FB));
+    XwComposeCtx x;
+    x.hot = hot; x.yb = s_yb;
+    x.colL_hot = smem + L.pair; x.rowT_hot = smem + L.pair + 4 * xw_colpair_stride(r);
+    XwCells cells;
+    cells.code = s_code; cells.icon = s_icon;
+    const int bar_id = 1 + g;
+    const int n_plan = r.n_plan;
+    const int gstride = gridDim.x * G;
+    int env = blockIdx.x * G + g;
+
+    // register prefetch of the env's grid row (CS bytes = CS/4 words, CS/4 <= 64 <= GT) and goal icons
+    const int row_words = d.CS >> 2;
+    uint32_t nq = 0, ni = 0;
+    if (env < d.n) {
+        if (gt < row_words) nq = ((const uint32_t*)(d.grid + (size_t)env * d.CS))[gt];
+        if (gt < d.G) ni = (uint32_t)d.goal_icon[(size_t)gt * d.n + env] + 1;
+    }
+    for (int i = gt; i < XW_CELL_STRIDE / 4; i += GT) ((uint32_t*)s_code)[i] = 0;
+    if (gt < XW_CODE_SLOTS) s_icon[gt] = gt == XW_CELL_BLOCK ? (uint32_t)d.brick_icon + 1 : gt == XW_CELL_AGENT ? (uint32_t)d.agent_icon + 1 : 0;
+    for (; env < d.n; env += gstride) {
+        if (gt < row_words) {  // (every warp passed the barrier after the last compose)
+            ((uint32_t*)s_code)[gt] = nq;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {  // where the agent and the goals are
+                const uint32_t code = (nq >> (8 * b)) & 0xff;
+                if (code >= XW_CELL_AGENT) s_special[code - XW_CELL_AGENT] = (uint8_t)(4 * gt + b);
+            }
+        }
+        if (gt < d.G) s_icon[XW_CELL_GOAL0 + gt] = ni;
+        if (gt == 0) tma_wait_read<0>();  // the TMA store of this group's previous frame has drained fb
+        group_bar(bar_id, GT);
+        // stage the agent's and goals' table words into the frame buffer (LDGSTS, no registers): one
+        // thread per (cell, plane, word column), one 4-byte copy per row
+        for (int i = gt; i < (1 + d.G) * XW_STAGE_COLS; i += GT) {
+            const int slot = i / XW_STAGE_COLS, col = i - slot * XW_STAGE_COLS, c = col / 3, wc = col - 3 * c;
+            uint32_t w0; int nrows; const uint32_t* src;
+            if (xw_stage_column(r, cells, s_cellinfo, s_special[slot], c, wc, &w0, &nrows, &src)) {
+                const int WR = WR_T ? WR_T : r.WR;
+                for (int j = 0; j < nrows; ++j) cp_async_4(fb + w0 + j * WR, src + j * WR);
+            }
+        }
+        cp_async_wait_all();
+        group_bar(bar_id, GT);
+        {  // prefetch the next env's cells while this one is composed
+            const int en = env + gstride;
+            if (en < d.n) {
+                if (gt < row_words) nq = ((const uint32_t*)(d.grid + (size_t)en * d.CS))[gt];
+                if (gt < d.G) ni = (uint32_t)d.goal_icon[(size_t)gt * d.n + en] + 1;
+            }
+        }
+        for (int i = gt; i < n_plan; i += GT) xw_compose_item<WR_T>(r, x, s_plan[i], cells, fb);
+        fence_async_smem();  // generic-proxy writes -> visible to the async (TMA) proxy
+        group_bar(bar_id, GT);
+        if (gt == 0) {
+            tma_store_1d(frames + (size_t)env * env_stride, fb, (uint32_t)r.FB);
+            tma_commit();
+        }
+    }
+    if (gt == 0) tma_wait_all<0>();
+}
+
 // General fallback (any frame size): one thread per output byte, straight to global memory.
 __global__ void k_render_generic(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
     const size_t total = (size_t)d.n * r.FB;
