@@ -25,7 +25,7 @@ struct HostSim {
     std::vector<uint8_t> T;
     std::vector<uint16_t> ecol, uv;
     std::vector<uint32_t> corner;
-    std::vector<uint8_t> colL, colR, rowT, rowB;
+    std::vector<uint8_t> colL, colR, rowT, rowB, cwb;
     XwRaceCfg race;
 };
 
@@ -93,7 +93,7 @@ HostSim* hs_create(const xw_config* c, const xw_catalog* cat, int n) {
     r.taps.yofs = t.yofs.data(); r.taps.ya0 = t.ya0.data(); r.taps.ya1 = t.ya1.data();
     if (t.fast_ok) {  // odd map sides exercise the per-plane M3 split, even ones the 3-plane items
         xw_build_plan(t, 4 + c->height % 3, c->height % 2 != 0);
-        r.plan = t.plan.data(); r.n_plan = (int)t.plan.size(); r.G = 1; r.GT = t.n_warps * 32;
+        r.plan = t.plan.data(); r.n_plan = (int)t.plan.size(); r.n_plan1 = t.n_plan1; r.G = 1; r.GT = t.n_warps * 32;
         r.cellinfo = t.cellinfo.data();
     }
     r.n_sr = (int)t.sr.size();
@@ -144,6 +144,14 @@ HostSim* hs_create(const xw_config* c, const xw_catalog* cat, int n) {
                 }
             }
             r.colL = s->colL.data(); r.colR = s->colR.data(); r.rowT = s->rowT.data(); r.rowB = s->rowB.data();
+            s->cwb.assign((size_t)16 * r.n_sr * r.n_sc * 3 + 64, 0);
+            for (size_t i = 0; i < (size_t)16 * r.n_sr * r.n_sc * 3; ++i) {
+                size_t j = i;
+                const int cc = (int)(j % 3); j /= 3;
+                const int si = (int)(j % r.n_sc); j /= r.n_sc;
+                s->cwb[i] = xw_cornerwb_entry(r, (int)(j / r.n_sr), (int)(j % r.n_sr), si, cc);
+            }
+            r.cornerWB = s->cwb.data();
         }
     }
     r.atlas64 = cat->atlas64;
@@ -200,6 +208,7 @@ void hs_render(HostSim* s, uint8_t* frames) {
         memcpy(pair_hot.data(), r.colL, cs2); memcpy(pair_hot.data() + cs2, r.colL + (size_t)(r.brick_icon + 1) * cs2, cs2);
         memcpy(pair_hot.data() + 2 * cs2, r.rowT, rs2); memcpy(pair_hot.data() + 2 * cs2 + rs2, r.rowT + (size_t)(r.brick_icon + 1) * rs2, rs2);
         x.colL_hot = pair_hot.data(); x.rowT_hot = pair_hot.data() + 2 * cs2;
+        x.cornerWB = r.cornerWB;
     }
     XwCells cells;
     cells.code = code.data(); cells.icon = icon;

@@ -95,6 +95,9 @@ struct xw_sim {
     std::vector<void*> allocs;
     int n_sms = 148, render_grid = 0, render_smem = 0;
     bool render_sb = false;
+    uint8_t* tables = nullptr;      // phase atlas + edge / pair tables, one allocation
+    size_t tables_bytes = 0, l2_window = 0;
+    float l2_ratio = 0.f;
     void (*render_fn)(XwDev, XwRender, uint8_t*, size_t) = nullptr;  // k_render<WR> for this frame width
     int C = 3;
     // race
@@ -248,41 +251,62 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
             int GT = et ? atoi(et) : (G >= 6 ? 64 : (768 / G) / 32 * 32);
             GT = GT / 32 * 32;
             if (GT < 32 || G * GT > XW_RENDER_THREADS) { if (et) break; continue; }
-            xw_build_plan(t, GT / 32, split, cfree);
-            r.n_plan = (int)t.plan.size();
+            const char* e2 = getenv("XW_RENDER_TWO_PHASE");
+            xw_build_plan(t, GT / 32, split, cfree, !s->render_sb, e2 && atoi(e2) != 0);
+            r.n_plan = (int)t.plan.size(); r.n_plan1 = t.n_plan1;
             if (xw_render_smem(r, s->render_sb ? (G + 1) / 2 : G).total > max_optin) continue;
             r.G = G; r.GT = GT;
             found = true;
         }
         if (!found) t.fast_ok = false;
     }
-    if (t.fast_ok) {
+    // All render tables live in ONE allocation so that a single L2 access-policy window can pin them:
+    // a step streams 1.4 GB of frames through the 126 MB L2, which would otherwise evict the 8-20 MB of
+    // tables and turn every special-cell look-up into a DRAM read (seen as 61 MB of DRAM reads per launch).
+    {
         static const int16_t zero16 = 0;
-        uint16_t *ecol = nullptr, *uv = nullptr;
-        uint32_t* corner = nullptr;
-        rc |= dupload(s, &r.plan, t.plan.data(), t.plan.size());
-        rc |= dupload(s, &r.cellinfo, t.cellinfo.data(), t.cellinfo.size());
-        rc |= dupload(s, &r.sr, t.sr.empty() ? &zero16 : t.sr.data(), t.sr.empty() ? 1 : t.sr.size());
-        rc |= dalloc(s, &ecol, (size_t)(cat->n_icons + 1) * 2 * 3 * c.height * t.RB + XW_TABLE_PAD / 2, false);
-        rc |= dupload(s, &r.band_y0, t.band_y0.data(), t.band_y0.size());
-        r.RB = t.RB;
-        rc |= dalloc(s, &uv, (size_t)(cat->n_icons + 1) * r.n_sr * 2 * 3 * OW + 8, false);
-        rc |= dalloc(s, &corner, (size_t)(cat->n_icons + 1) * 3, false);
-        r.ecol = ecol; r.uv = uv; r.corner = corner;
-        static const int16_t zero16b = 0;
+        r.RB = t.fast_ok ? t.RB : 4;
         r.n_sc = (int)t.sc.size();
-        rc |= dupload(s, &r.sc, t.sc.empty() ? &zero16b : t.sc.data(), t.sc.empty() ? 1 : t.sc.size());
-        uint8_t *colL = nullptr, *colR = nullptr, *rowT = nullptr, *rowB = nullptr;
-        const size_t n_col = (size_t)(cat->n_icons + 1) * 2 * r.n_sc * 3 * c.height * t.RB, n_row = (size_t)(cat->n_icons + 1) * 2 * r.n_sr * 3 * OW;
-        rc |= dalloc(s, &colL, n_col + 64, false); rc |= dalloc(s, &colR, n_col + 64, false);
-        rc |= dalloc(s, &rowT, n_row + 64, false); rc |= dalloc(s, &rowB, n_row + 64, false);
-        r.colL = colL; r.colR = colR; r.rowT = rowT; r.rowB = rowB;
+        const size_t n_T = (size_t)cat->n_icons * r.FB + XW_TABLE_PAD;
+        const size_t n_ecol = ((size_t)(cat->n_icons + 1) * 2 * 3 * c.height * r.RB) * 2 + XW_TABLE_PAD;
+        const size_t n_uv = ((size_t)(cat->n_icons + 1) * r.n_sr * 2 * 3 * OW + 8) * 2;
+        const size_t n_corner = (size_t)(cat->n_icons + 1) * 3 * 4;
+        const size_t n_col = (size_t)(cat->n_icons + 1) * 2 * r.n_sc * 3 * c.height * r.RB + 64, n_row = (size_t)(cat->n_icons + 1) * 2 * r.n_sr * 3 * OW + 64;
+        const size_t n_cwb = (size_t)16 * r.n_sr * r.n_sc * 3 + 64;
+        auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+        const size_t total = up(n_T) + (t.fast_ok ? up(n_ecol) + up(n_uv) + up(n_corner) + 2 * up(n_col) + 2 * up(n_row) + up(n_cwb) : 0);
+        uint8_t* base = nullptr;
+        rc |= dalloc(s, &base, total, false);
+        if (rc) return rc;
+        s->tables = base; s->tables_bytes = total;
+        size_t o = 0;
+        auto take = [&](size_t n) { uint8_t* p = base + o; o += up(n); return p; };
+        r.T = take(n_T);
+        if (t.fast_ok) {
+            r.ecol = (const uint16_t*)take(n_ecol); r.uv = (const uint16_t*)take(n_uv); r.corner = (const uint32_t*)take(n_corner);
+            r.colL = take(n_col); r.colR = take(n_col); r.rowT = take(n_row); r.rowB = take(n_row); r.cornerWB = take(n_cwb);
+            rc |= dupload(s, &r.plan, t.plan.data(), t.plan.size());
+            rc |= dupload(s, &r.cellinfo, t.cellinfo.data(), t.cellinfo.size());
+            rc |= dupload(s, &r.sr, t.sr.empty() ? &zero16 : t.sr.data(), t.sr.empty() ? 1 : t.sr.size());
+            rc |= dupload(s, &r.sc, t.sc.empty() ? &zero16 : t.sc.data(), t.sc.empty() ? 1 : t.sc.size());
+            rc |= dupload(s, &r.band_y0, t.band_y0.data(), t.band_y0.size());
+        }
+        // L2 set-aside for persisting lines (best effort: not every driver / MIG slice grants it)
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, s->device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, s->device);
+        const char* ep = getenv("XW_RENDER_L2_PERSIST");
+        if ((!ep || atoi(ep) != 0) && max_persist > 0 && max_window > 0) {
+            size_t want = total + (total >> 2);
+            if (want > (size_t)max_persist) want = (size_t)max_persist;
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+                s->l2_window = total < (size_t)max_window ? total : (size_t)max_window;
+                s->l2_ratio = want >= s->l2_window ? 1.0f : (float)want / (float)s->l2_window;
+            } else cudaGetLastError();
+        }
     }
     rc |= dupload(s, &r.atlas64, cat->atlas64, (size_t)cat->n_icons * 64 * 64 * 3);
-    uint8_t* T = nullptr;
-    rc |= dalloc(s, &T, (size_t)cat->n_icons * r.FB + XW_TABLE_PAD, false);
     if (rc) return rc;
-    r.T = T;
     k_build_phase_atlas<<<s->n_sms * 8, 256, 0, s->own_stream>>>(r);
     s->launches++;
     if (t.fast_ok) {
@@ -445,7 +469,20 @@ static int launch_render(xw_sim* s, uint8_t* d_frames, cudaStream_t st) {
     if (s->tab.fast_ok) {
         const int need = (s->n + r.G - 1) / r.G;  // CTAs that get at least one env
         const int grid = s->render_grid < need ? s->render_grid : need;
-        s->render_fn<<<grid, r.G * r.GT, s->render_smem, st>>>(s->d, r, dst, env_stride);
+        cudaLaunchConfig_t lc;
+        memset(&lc, 0, sizeof lc);
+        lc.gridDim = dim3(grid); lc.blockDim = dim3(r.G * r.GT); lc.dynamicSmemBytes = s->render_smem; lc.stream = st;
+        cudaLaunchAttribute at[1];
+        if (s->l2_window) {  // keep the tables in L2 while the frames stream through it
+            at[0].id = cudaLaunchAttributeAccessPolicyWindow;
+            at[0].val.accessPolicyWindow.base_ptr = s->tables;
+            at[0].val.accessPolicyWindow.num_bytes = s->l2_window;
+            at[0].val.accessPolicyWindow.hitRatio = s->l2_ratio;
+            at[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            at[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            lc.attrs = at; lc.numAttrs = 1;
+        }
+        CUDA_TRY(cudaLaunchKernelEx(&lc, s->render_fn, s->d, r, dst, env_stride));
     } else {
         k_render_generic<<<s->n_sms * 8, 256, 0, st>>>(s->d, r, dst, env_stride);
     }

@@ -38,6 +38,7 @@ struct XwRender {
     int32_t OH, OW, WR, FB;   // frame rows, cols, words per row, bytes per frame (3*OH*OW)
     int32_t H, W;
     int32_t n_plan;           // plan slots (a multiple of GT)
+    int32_t n_plan1;          // the first n_plan1 slots (straddling rows) do not read staged words
     int32_t G, GT;            // warp groups per CTA, threads per group
     int32_t n_icons, brick_icon, agent_icon;
     int32_t n_sr;             // straddling rows
@@ -57,6 +58,8 @@ struct XwRender {
     // a brick (cls 1) -- all but a few per cent of the borders of a maze
     const uint8_t *colL, *colR;  // [n_icons+1][2][n_sc][3][H][RB]  this cell left / right of straddling column s
     const uint8_t *rowT, *rowB;  // [n_icons+1][2][n_sr][3][OW]     this cell above / below straddling row q
+    const uint8_t* cornerWB;     // [16][n_sr][n_sc][3]  corner pixel when the four cells are white / brick:
+                                 //   combo = cls(top-left) | cls(top-right) << 1 | cls(bottom-left) << 2 | cls(bottom-right) << 3
     const int16_t* sc;        // [n_sc] the straddling columns
     int32_t n_sc;
     const uint8_t* atlas64;   // [n_icons][64][64][3] BGR
@@ -138,6 +141,13 @@ XW_HD uint8_t xw_rowpair_entry(const XwRender& r, int role, uint32_t dsc, int cl
                         xw_canvas_tap(r, db, 0, sx1, c), t.xa0[dx], t.xa1[dx], t.ya0[dy], t.ya1[dy]);
 }
 
+XW_HD uint8_t xw_cornerwb_entry(const XwRender& r, int combo, int q, int s, int c) {
+    const XwTaps& t = r.taps;
+    const int dy = r.sr[q], dx = r.sc[s];
+    return xw_resize_px(xw_canvas_tap(r, xw_cls_desc(r, combo & 1), 63, 63, c), xw_canvas_tap(r, xw_cls_desc(r, (combo >> 1) & 1), 63, 0, c),
+                        xw_canvas_tap(r, xw_cls_desc(r, (combo >> 2) & 1), 0, 63, c), xw_canvas_tap(r, xw_cls_desc(r, (combo >> 3) & 1), 0, 0, c),
+                        t.xa0[dx], t.xa1[dx], t.ya0[dy], t.ya1[dy]);
+}
 XW_HD uint32_t xw_corner_entry(const XwRender& r, uint32_t dsc, int c) {
     return (uint32_t)xw_canvas_tap(r, dsc, 63, 63, c) | ((uint32_t)xw_canvas_tap(r, dsc, 63, 0, c) << 8) |
            ((uint32_t)xw_canvas_tap(r, dsc, 0, 63, c) << 16) | ((uint32_t)xw_canvas_tap(r, dsc, 0, 0, c) << 24);
@@ -172,11 +182,12 @@ struct XwComposeCtx {
     const uint8_t* hot;     // brick phase table [FB]
     const uint32_t* yb;     // [OH] ya0 | ya1 << 16
     const uint8_t *colL_hot, *rowT_hot;  // the white and brick entries of colL / rowT: [2 descs][2 cls][stride]
+    const uint8_t* cornerWB;             // copy of XwRender::cornerWB
 };
 XW_HD size_t xw_colpair_stride(const XwRender& r) { return (size_t)r.n_sc * 3 * r.H * r.RB; }  // per (desc, cls)
 XW_HD size_t xw_rowpair_stride(const XwRender& r) { return (size_t)r.n_sr * 3 * r.OW; }
 XW_HD int xw_pair_hot_bytes(const XwRender& r) {  // shared-memory copies: desc in {white, brick} x cls x ...
-    return (int)(2 * 2 * (xw_colpair_stride(r) + xw_rowpair_stride(r)));
+    return (int)(2 * 2 * (xw_colpair_stride(r) + xw_rowpair_stride(r))) + 16 * r.n_sr * r.n_sc * 3;
 }
 
 // Source of a cell's words: word w of the frame comes from *(base + 4*w) | wmask.  White cells read
@@ -284,8 +295,11 @@ XW_HD void xw_item_r_exact(const XwRender& r, const XwComposeCtx& x, const XwU4 
 // WR_T = words per frame row when known at compile time (row offsets become immediates), 0 = use r.WR.
 // Rows go four at a time, all loads before the stores: the tables and the frame buffer may alias as
 // far as the compiler knows, and a load-store-load chain would expose one memory latency per row.
-template <int WR_T>
+template <int WR_T, int SMALL = 0>
 XW_HD void xw_compose_item(const XwRender& r, const XwComposeCtx& x, const XwU4 e, const XwCells& celldesc, uint32_t* fb) {
+    // rows per load batch: every source is shared memory once the special cells are staged, so small
+    // batches (SMALL: half the registers, for CTAs of more than 512 threads) cost little
+    constexpr int R1 = SMALL ? 4 : 8, R2 = SMALL ? 2 : 4;
     const int WR = WR_T ? WR_T : r.WR;
     const int PW = r.OH * WR;  // words per plane
     const int type = (e.y >> 24) & 7, nrows = (e.y >> 16) & 0xff, nc = e.y >> 29;
@@ -305,14 +319,14 @@ XW_HD void xw_compose_item(const XwRender& r, const XwComposeCtx& x, const XwU4 
         const XwSrc sA = xw_src_of(r, x, celldesc(cellA), fb, false);
         const uint32_t* pA = (const uint32_t*)sA.base + w0;
         uint32_t* dst = fb + w0;
-        for (int i0 = 0; i0 < nrows; i0 += 8, pA += 8 * WR, dst += 8 * WR) {
-            uint32_t v[3][8];
+        for (int i0 = 0; i0 < nrows; i0 += R1, pA += R1 * WR, dst += R1 * WR) {
+            uint32_t v[3][R1];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
+            for (int j = 0; j < R1; ++j)
 #pragma unroll
                 for (int cc = 0; cc < 3; ++cc) v[cc][j] = pA[po[cc] + j * WR];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
+            for (int j = 0; j < R1; ++j)
                 if (i0 + j < nrows) {
 #pragma unroll
                     for (int cc = 0; cc < 3; ++cc) dst[po[cc] + j * WR] = v[cc][j] | sA.wmask;
@@ -327,14 +341,14 @@ XW_HD void xw_compose_item(const XwRender& r, const XwComposeCtx& x, const XwU4 
         const uint32_t* pA = (const uint32_t*)sA.base + w0;
         const uint32_t* pB = (const uint32_t*)sB.base + w0;
         uint32_t* dst = fb + w0;
-        for (int i0 = 0; i0 < nrows; i0 += 4, pA += 4 * WR, pB += 4 * WR, dst += 4 * WR) {
-            uint32_t va[3][4], vb[3][4];
+        for (int i0 = 0; i0 < nrows; i0 += R2, pA += R2 * WR, pB += R2 * WR, dst += R2 * WR) {
+            uint32_t va[3][R2], vb[3][R2];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < R2; ++j)
 #pragma unroll
                 for (int cc = 0; cc < 3; ++cc) { va[cc][j] = pA[po[cc] + j * WR]; vb[cc][j] = pB[po[cc] + j * WR]; }
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < R2; ++j)
                 if (i0 + j < nrows) {
 #pragma unroll
                     for (int cc = 0; cc < 3; ++cc) dst[po[cc] + j * WR] = xw_prmt(va[cc][j], vb[cc][j], sel) | wmask;
@@ -365,22 +379,29 @@ XW_HD void xw_compose_item(const XwRender& r, const XwComposeCtx& x, const XwU4 
         const int pstride = r.H * r.RB;  // bytes between planes
         const uint32_t keep = ~(0xffu << sh);
         for (int i0 = 0; i0 < nrows; i0 += 4, pA += 4 * WR, pB += 4 * WR, dst += 4 * WR, tab += 4) {
-            uint32_t va[3][4], vb[3][4], pb[3];
+            uint32_t pb[3];
 #pragma unroll
             for (int cc = 0; cc < 3; ++cc)
-                if (cc < nc) {
-                    pb[cc] = *(const uint32_t*)(tab + pl[cc] * pstride);  // the straddling byte of four rows
+                if (cc < nc) pb[cc] = *(const uint32_t*)(tab + pl[cc] * pstride);  // the straddling byte of four rows
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) { va[cc][j] = pA[po[cc] + j * WR]; vb[cc][j] = pB[po[cc] + j * WR]; }
-                }
+            for (int h0 = 0; h0 < 4; h0 += R2) {
+                uint32_t va[3][R2], vb[3][R2];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (i0 + j < nrows) {
+                for (int cc = 0; cc < 3; ++cc)
+                    if (cc < nc) {
 #pragma unroll
-                    for (int cc = 0; cc < 3; ++cc)
-                        if (cc < nc)
-                            dst[po[cc] + j * WR] = ((xw_prmt(va[cc][j], vb[cc][j], sel) | wmask) & keep) | (((pb[cc] >> (8 * j)) & 0xffu) << sh);
-                }
+                        for (int j = 0; j < R2; ++j) { va[cc][j] = pA[po[cc] + (h0 + j) * WR]; vb[cc][j] = pB[po[cc] + (h0 + j) * WR]; }
+                    }
+#pragma unroll
+                for (int j = 0; j < R2; ++j)
+                    if (i0 + h0 + j < nrows) {
+#pragma unroll
+                        for (int cc = 0; cc < 3; ++cc)
+                            if (cc < nc)
+                                dst[po[cc] + (h0 + j) * WR] =
+                                    ((xw_prmt(va[cc][j], vb[cc][j], sel) | wmask) & keep) | (((pb[cc] >> (8 * (h0 + j))) & 0xffu) << sh);
+                    }
+            }
         }
         if (need_exact) xw_item_m3_exact<WR_T>(r, x, e, celldesc, fb);
         return;
@@ -404,6 +425,13 @@ XW_HD void xw_compose_item(const XwRender& r, const XwComposeCtx& x, const XwU4 
         tabs[h] = tab + (size_t)(q * 3 + c0) * r.OW + 4 * k;
     }
     if (need_exact) { xw_item_r_exact<WR_T>(r, x, e, celldesc, fb); return; }
+    int corner_combo = -1;  // all four corner cells white / brick: one table byte per plane
+    const int s_idx = (e.w >> 26) & 31;
+    if (corner) {
+        const int c00 = xw_cls(r, celldesc(scell)), c01 = xw_cls(r, celldesc(scell + 1));
+        const int c10 = xw_cls(r, celldesc(scell + r.W)), c11 = xw_cls(r, celldesc(scell + r.W + 1));
+        if ((c00 | c01 | c10 | c11) < 2) corner_combo = c00 | (c01 << 1) | (c10 << 2) | (c11 << 3);
+    }
     uint32_t wa[3], wb[3];
 #pragma unroll
     for (int cc = 0; cc < 3; ++cc)
@@ -412,7 +440,11 @@ XW_HD void xw_compose_item(const XwRender& r, const XwComposeCtx& x, const XwU4 
     for (int cc = 0; cc < 3; ++cc)
         if (cc < nc) {
             uint32_t word = xw_prmt(wa[cc], wb[cc], sel);
-            if (corner) word = (word & ~(0xffu << sh)) | (xw_corner_px(r, x, celldesc, scell, c0 + pl[cc], y0, dx) << sh);
+            if (corner) {
+                const uint32_t v = corner_combo >= 0 ? x.cornerWB[((corner_combo * r.n_sr + q) * r.n_sc + s_idx) * 3 + c0 + pl[cc]]
+                                                     : xw_corner_px(r, x, celldesc, scell, c0 + pl[cc], y0, dx);
+                word = (word & ~(0xffu << sh)) | (v << sh);
+            }
             fb[w0 + po[cc]] = word;
         }
 }
@@ -485,8 +517,14 @@ __global__ void k_build_edge_tables(XwRender r) {
 __global__ void k_build_pair_tables(XwRender r) {
     const size_t cs = xw_colpair_stride(r), rs = xw_rowpair_stride(r);
     const size_t n_col = (size_t)(r.n_icons + 1) * 2 * cs, n_row = (size_t)(r.n_icons + 1) * 2 * rs;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * (n_col + n_row); i += (size_t)gridDim.x * blockDim.x) {
-        if (i < 2 * n_col) {
+    const size_t n_cwb = (size_t)16 * r.n_sr * r.n_sc * 3;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * (n_col + n_row) + n_cwb; i += (size_t)gridDim.x * blockDim.x) {
+        if (i >= 2 * (n_col + n_row)) {
+            size_t j = i - 2 * (n_col + n_row);
+            const int c = (int)(j % 3); j /= 3;
+            const int sidx = (int)(j % r.n_sc); j /= r.n_sc;
+            ((uint8_t*)r.cornerWB)[i - 2 * (n_col + n_row)] = xw_cornerwb_entry(r, (int)(j / r.n_sr), (int)(j % r.n_sr), sidx, c);
+        } else if (i < 2 * n_col) {
             const int role = i >= n_col;
             size_t j = i - role * n_col;
             const int row = (int)(j % r.RB); j /= r.RB;
@@ -527,9 +565,13 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, ui
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// frames are written once and not read by this kernel: evict-first in L2, so that the streaming
+// 1.4 GB of frame lines does not push the render tables out
 __device__ __forceinline__ void tma_store_1d(void* gdst, const void* smem_src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                 ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void tma_wait_read() {
@@ -587,6 +629,7 @@ k_render(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
         uint8_t* pr = pc + 2 * cs2;
         for (int i = tid; i < 2 * cs2; i += nt) pc[i] = r.colL[(size_t)(i < cs2 ? 0 : r.brick_icon + 1) * cs2 + (i < cs2 ? i : i - cs2)];
         for (int i = tid; i < 2 * rs2; i += nt) pr[i] = r.rowT[(size_t)(i < rs2 ? 0 : r.brick_icon + 1) * rs2 + (i < rs2 ? i : i - rs2)];
+        for (int i = tid; i < 16 * r.n_sr * r.n_sc * 3; i += nt) pr[2 * rs2 + i] = r.cornerWB[i];
     }
     mbar_wait(bar, 0);
     __syncthreads();
@@ -599,6 +642,7 @@ k_render(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
     XwComposeCtx x;
     x.hot = hot; x.yb = s_yb;
     x.colL_hot = smem + L.pair; x.rowT_hot = smem + L.pair + 4 * xw_colpair_stride(r);
+    x.cornerWB = x.rowT_hot + 4 * xw_rowpair_stride(r);
     const int bar_id = 1 + g;
     const int n_plan = r.n_plan;
     const int gstride = gridDim.x * G;
@@ -676,7 +720,7 @@ k_render(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
         }
         bool staged = !(loader && have_next);
         for (int i = gt; i < n_plan; i += GT) {
-            xw_compose_item<WR_T>(r, x, s_plan[i], cells, fb);
+            xw_compose_item<WR_T, (NT_MAX > 512)>(r, x, s_plan[i], cells, fb);
             if (!staged) {  // after the first bundle: by now the TMA store of env i-1 has usually drained
                 if (lane == 0) tma_wait_read<0>();
                 __syncwarp();
@@ -730,6 +774,7 @@ k_render_sb(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride
         uint8_t* pr = pc + 2 * cs2;
         for (int i = tid; i < 2 * cs2; i += nt) pc[i] = r.colL[(size_t)(i < cs2 ? 0 : r.brick_icon + 1) * cs2 + (i < cs2 ? i : i - cs2)];
         for (int i = tid; i < 2 * rs2; i += nt) pr[i] = r.rowT[(size_t)(i < rs2 ? 0 : r.brick_icon + 1) * rs2 + (i < rs2 ? i : i - rs2)];
+        for (int i = tid; i < 16 * r.n_sr * r.n_sc * 3; i += nt) pr[2 * rs2 + i] = r.cornerWB[i];
     }
     mbar_wait(bar, 0);
     __syncthreads();
@@ -744,6 +789,7 @@ k_render_sb(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride
     XwComposeCtx x;
     x.hot = hot; x.yb = s_yb;
     x.colL_hot = smem + L.pair; x.rowT_hot = smem + L.pair + 4 * xw_colpair_stride(r);
+    x.cornerWB = x.rowT_hot + 4 * xw_rowpair_stride(r);
     XwCells cells;
     cells.code = s_code; cells.icon = s_icon;
     const int bar_id = 1 + g;
@@ -782,8 +828,6 @@ k_render_sb(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride
                 for (int j = 0; j < nrows; ++j) cp_async_4(fb + w0 + j * WR, src + j * WR);
             }
         }
-        cp_async_wait_all();
-        group_bar(bar_id, GT);
         {  // prefetch the next env's cells while this one is composed
             const int en = env + gstride;
             if (en < d.n) {
@@ -791,7 +835,11 @@ k_render_sb(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride
                 if (gt < d.G) ni = (uint32_t)d.goal_icon[(size_t)gt * d.n + en] + 1;
             }
         }
-        for (int i = gt; i < n_plan; i += GT) xw_compose_item<WR_T>(r, x, s_plan[i], cells, fb);
+        // the straddling-row items read only tables: they run while the staging copies are in flight
+        for (int i = gt; i < r.n_plan1; i += GT) xw_compose_item<WR_T, (NT_MAX > 512)>(r, x, s_plan[i], cells, fb);
+        cp_async_wait_all();
+        group_bar(bar_id, GT);
+        for (int i = r.n_plan1 + gt; i < n_plan; i += GT) xw_compose_item<WR_T, (NT_MAX > 512)>(r, x, s_plan[i], cells, fb);
         fence_async_smem();  // generic-proxy writes -> visible to the async (TMA) proxy
         group_bar(bar_id, GT);
         if (gt == 0) {

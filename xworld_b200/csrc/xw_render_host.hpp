@@ -18,10 +18,11 @@
 //   M3  like M2, and one byte lies on a straddling column (its two tap columns are in different
 //       cells): that byte is evaluated exactly from the cells' edge-tap tables
 //   R   one word of a straddling row (tap rows in different cell rows): separable U(top)+V(bottom)
-//       rule; if the word also holds a corner (straddling row x column) that byte comes from the
-//       four cells' corner taps
+//       rule
+//   RC  an R word that also holds a corner (straddling row x column): that byte depends on four cells
+//       (kept in bundles of their own: there are n_sr*n_sc of them per plane)
 // The M items of a band exclude the band's straddling last row, so every frame word has one writer.
-enum { XW_ITEM_M1 = 0, XW_ITEM_M2 = 1, XW_ITEM_M3 = 2, XW_ITEM_R = 3, XW_ITEM_TYPES = 4 };
+enum { XW_ITEM_M1 = 0, XW_ITEM_M2 = 1, XW_ITEM_M3 = 2, XW_ITEM_R = 3, XW_ITEM_RC = 4, XW_ITEM_TYPES = 5 };
 
 // Packed plan entry (one LDS.128):
 //   x = cellA | cellB << 8 | sel << 16     cell indices ty*W + tx owning the word's first / last byte
@@ -31,7 +32,7 @@ enum { XW_ITEM_M1 = 0, XW_ITEM_M2 = 1, XW_ITEM_M3 = 2, XW_ITEM_R = 3, XW_ITEM_TY
 //                                          first plane, number of planes (0 = padding slot)
 //   z = y0 | dx << 8 | scell << 16 | sbyte << 24    first row; M3 / R-with-corner: the straddling column,
 //                                          its left cell (the right one is scell + 1), its byte in the word
-//   w = q | k << 8 | band << 16 | rot << 24 | corner << 31     R: index of the straddling row (M3: of the
+//   w = q | k << 8 | band << 16 | rot << 24 | sidx << 26 | corner << 31     R: index of the straddling row (M3: of the
 //                                          straddling column), word column,
 //                                          corner flag; M3: band = cell row (edge tables are stored per
 //                                          band); rot: the item visits planes (rot + i) % 3, i = 0,1,2
@@ -53,6 +54,7 @@ struct XwRenderTables {
     std::vector<XwPlanItem> items;       // per-plane items (planner input)
     std::vector<XwU4> plan;              // bundled plan for n_warps warps per group
     int n_warps = 0;
+    int n_plan1 = 0;                     // plan[0..n_plan1): phase 1 (R / RC bundles), the rest: phase 2
     int bank_conflicts = 0;              // lane pairs of a bundle left on one bank (0 = conflict-free plan)
     double makespan = 0, total_cost = 0; // planner's cost model (instructions per env): slowest warp, sum
 };
@@ -86,7 +88,7 @@ inline XwRenderTables xw_build_render_tables(int H, int W, int OH, int OW) {
     for (int dy = 0; dy < OH; ++dy)
         if (t.ya1[dy] != 0 && ((t.yofs[dy] + 1) >> 6) != (t.yofs[dy] >> 6)) { t.sr.push_back((int16_t)dy); is_sr[dy] = 1; }
     bool ok = (OW % 4 == 0) && (t.FB % 16 == 0) && OH <= 255 && OW <= 252 && OH * (OW / 4) <= 65535 && t.sr.size() <= 255 &&
-              t.sc.size() <= 255;
+              t.sc.size() <= 31;
     // a straddling row is the last row of its band (yofs is monotone); two in one band (upscaling)
     // would break the plan
     for (size_t q = 0; q < t.sr.size() && ok; ++q) {
@@ -133,7 +135,7 @@ inline XwRenderTables xw_build_render_tables(int H, int W, int OH, int OW) {
                 XwPlanItem r = it;
                 r.woff = (y1 - 1) * t.WR + k;
                 r.nrows = 1; r.y0 = y1 - 1; r.q = q;
-                r.type = XW_ITEM_R; r.corner = n_sc ? 1 : 0;
+                r.type = XW_ITEM_R; r.corner = n_sc ? 1 : 0;  // (XW_ITEM_RC: corner words in bundles of their own -- measured slower)
                 t.items.push_back(r);
             }
         }
@@ -142,7 +144,7 @@ inline XwRenderTables xw_build_render_tables(int H, int W, int OH, int OW) {
     t.RB = (t.RB + 3) / 4 * 4;
     t.cellinfo.assign((size_t)H * W, 0);
     for (const XwPlanItem& it : t.items) {  // per cell: first word column, number of columns, rows of the M items
-        if (it.type == XW_ITEM_R) continue;
+        if (it.type >= XW_ITEM_R) continue;
         const int cells[2] = {it.cellA, it.cellB};
         for (int q = 0; q < 2; ++q) {
             uint32_t& ci = t.cellinfo[cells[q]];
@@ -154,7 +156,7 @@ inline XwRenderTables xw_build_render_tables(int H, int W, int OH, int OW) {
         }
     }
     for (const XwPlanItem& it : t.items)  // first column shared with the left neighbour?
-        if (it.type != XW_ITEM_R && it.cellA != it.cellB) t.cellinfo[it.cellB] |= 1u << 26;
+        if (it.type < XW_ITEM_R && it.cellA != it.cellB) t.cellinfo[it.cellB] |= 1u << 26;
     t.fast_ok = ok;
     return t;
 }
@@ -165,13 +167,14 @@ inline double xw_item_cost(const XwPlanItem& it, int nc) {
         case XW_ITEM_M1: return 50 + nc * (6 + it.nrows * 5.0);
         case XW_ITEM_M2: return 80 + nc * (6 + it.nrows * 10.0);
         case XW_ITEM_M3: return 110 + nc * (8 + it.nrows * 13.0);
-        default: return 90 + nc * (20.0 + (it.corner ? 45.0 : 0.0));
+        default: return 90 + nc * (20.0 + (it.corner ? 25.0 : 0.0));
     }
 }
 
 // Bundle the items for groups of n_warps warps.  split_m3: M3 items per plane (three times the
 // items, a third of the rows each) instead of one item for the three planes.
-inline void xw_build_plan(XwRenderTables& t, int n_warps, bool split_m3, bool conflict_free = false) {
+inline void xw_build_plan(XwRenderTables& t, int n_warps, bool split_m3, bool conflict_free = false, bool warp0_loader = false,
+                          bool two_phase = false) {
     struct Bundle { std::vector<XwU4> slots; double cost; };
     std::vector<Bundle> bundles;
     t.bank_conflicts = 0;
@@ -240,7 +243,7 @@ inline void xw_build_plan(XwRenderTables& t, int n_warps, bool split_m3, bool co
             e.y = w0s[j] | ((uint32_t)it.nrows << 16) | ((uint32_t)ty << 24) | ((uint32_t)c0 << 27) | ((uint32_t)nc << 29);
             e.z = (uint32_t)it.y0 | ((uint32_t)it.dx << 8) | ((uint32_t)it.scell << 16) | ((uint32_t)it.sbyte << 24);
             e.w = (uint32_t)(ty == XW_ITEM_M3 ? it.sidx : it.q) | ((uint32_t)it.k << 8) | ((uint32_t)it.band << 16) | ((uint32_t)best_r[j] << 24) |
-                  ((uint32_t)it.corner << 31);
+                  ((uint32_t)(it.sidx & 31) << 26) | ((uint32_t)it.corner << 31);
             bd.slots.push_back(e);
             const double c = xw_item_cost(it, nc);
             if (c > bd.cost) bd.cost = c;
@@ -252,25 +255,38 @@ inline void xw_build_plan(XwRenderTables& t, int n_warps, bool split_m3, bool co
             bundles.push_back(mine[b]);
         }
     }
-    // longest-processing-time-first assignment of bundles to the warps of a group
-    std::stable_sort(bundles.begin(), bundles.end(), [](const Bundle& a, const Bundle& b) { return a.cost > b.cost; });
-    std::vector<std::vector<int>> mine(n_warps);
-    std::vector<double> load(n_warps, 0.0);
-    load[0] = 250.0;  // warp 0 of a group is also the loader (cells, staging): k_render
-    t.total_cost = 0;
-    for (size_t b = 0; b < bundles.size(); ++b) {
-        int w = 0;
-        for (int i = 1; i < n_warps; ++i) if (load[i] < load[w]) w = i;
-        mine[w].push_back((int)b);
-        load[w] += bundles[b].cost;
-        t.total_cost += bundles[b].cost;
+    // Two phases: the straddling-row bundles (R, RC) read only tables, so the single-buffer kernel runs
+    // them while the staging copies of the special cells are in flight; everything else follows.  Within
+    // a phase: longest-processing-time-first assignment of bundles to the warps of a group.
+    t.plan.clear();
+    t.total_cost = 0; t.makespan = 0;
+    for (int phase = 0; phase < 2; ++phase) {
+        std::vector<Bundle> ph;
+        for (const Bundle& b : bundles) {
+            const int ty = (int)((b.slots[0].y >> 24) & 7);
+            if ((two_phase && ty >= XW_ITEM_R) == (phase == 0)) ph.push_back(b);
+        }
+        std::stable_sort(ph.begin(), ph.end(), [](const Bundle& a, const Bundle& b) { return a.cost > b.cost; });
+        std::vector<std::vector<int>> mine(n_warps);
+        std::vector<double> load(n_warps, 0.0);
+        if (phase == 1 && warp0_loader) load[0] = 250.0;  // k_render (pipe): warp 0 also loads cells and stages
+        for (size_t b = 0; b < ph.size(); ++b) {
+            int w = 0;
+            for (int i = 1; i < n_warps; ++i) if (load[i] < load[w]) w = i;
+            mine[w].push_back((int)b);
+            load[w] += ph[b].cost;
+            t.total_cost += ph[b].cost;
+        }
+        size_t rounds = 0;
+        double mk = 0;
+        for (int w = 0; w < n_warps; ++w) { if (mine[w].size() > rounds) rounds = mine[w].size(); if (load[w] > mk) mk = load[w]; }
+        t.makespan += mk;
+        const size_t base = t.plan.size();
+        t.plan.resize(base + rounds * n_warps * 32, XwU4{0, 0, 0, 0});
+        for (int w = 0; w < n_warps; ++w)
+            for (size_t j = 0; j < mine[w].size(); ++j)
+                for (int l = 0; l < 32; ++l) t.plan[base + (j * n_warps + w) * 32 + l] = ph[mine[w][j]].slots[l];
+        if (phase == 0) t.n_plan1 = (int)t.plan.size();
     }
-    size_t rounds = 0;
-    t.makespan = 0;
-    for (int w = 0; w < n_warps; ++w) { if (mine[w].size() > rounds) rounds = mine[w].size(); if (load[w] > t.makespan) t.makespan = load[w]; }
-    t.plan.assign(rounds * n_warps * 32, XwU4{0, 0, 0, 0});
-    for (int w = 0; w < n_warps; ++w)
-        for (size_t j = 0; j < mine[w].size(); ++j)
-            for (int l = 0; l < 32; ++l) t.plan[(j * n_warps + w) * 32 + l] = bundles[mine[w][j]].slots[l];
     t.n_warps = n_warps;
 }
