@@ -242,19 +242,21 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
         // Measured on B200 (profiles/r01_summary.md): sb 8x64 threads is the fastest at 84x84 frames.
         const char* em = getenv("XW_RENDER_MODE");
         s->render_sb = !(em && !strcmp(em, "pipe"));
-        const int max_groups = s->render_sb ? 2 * XW_RENDER_MAX_GROUPS : XW_RENDER_MAX_GROUPS;
+        const int max_groups = s->render_sb ? XW_RENDER_MAX_GROUPS : XW_RENDER_MAX_GROUPS / 2;
         int G = eg ? atoi(eg) : max_groups;
         if (G > max_groups) G = max_groups;
         bool found = false;
         for (; G >= 1 && !found; --G) {
             // <= 512 threads/CTA keeps 124 registers per thread (no spills, 24-word load batches)
             int GT = et ? atoi(et) : (G >= 6 ? 64 : (768 / G) / 32 * 32);
+            // 9 groups fit at 84x84 but need > 512 threads = fewer registers per thread: measured 30 % slower
+            if (!eg && s->render_sb && G * GT > 512 && G > 8) continue;
             GT = GT / 32 * 32;
             if (GT < 32 || G * GT > XW_RENDER_THREADS) { if (et) break; continue; }
             const char* e2 = getenv("XW_RENDER_TWO_PHASE");
             xw_build_plan(t, GT / 32, split, cfree, !s->render_sb, e2 && atoi(e2) != 0);
             r.n_plan = (int)t.plan.size(); r.n_plan1 = t.n_plan1;
-            if (xw_render_smem(r, s->render_sb ? (G + 1) / 2 : G).total > max_optin) continue;
+            if (xw_render_smem(r, s->render_sb ? G : 2 * G).total > max_optin) continue;
             r.G = G; r.GT = GT;
             found = true;
         }
@@ -316,11 +318,11 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
     }
     CUDA_TRY(cudaGetLastError());
     if (t.fast_ok) {
-        s->render_smem = xw_render_smem(r, s->render_sb ? (r.G + 1) / 2 : r.G).total;
+        s->render_smem = xw_render_smem(r, s->render_sb ? r.G : 2 * r.G).total;
         // instantiations: compile-time row stride for the common frame widths x register budget by CTA size
         const int nt = r.G * r.GT;
 #define XW_PICK(WR_) (nt <= 512 ? k_render<WR_, 512> : nt <= 768 ? k_render<WR_, 768> : k_render<WR_, 1024>)
-#define XW_PICK_SB(WR_) (nt <= 512 ? k_render_sb<WR_, 512> : nt <= 768 ? k_render_sb<WR_, 768> : k_render_sb<WR_, 1024>)
+#define XW_PICK_SB(WR_) (nt <= 512 ? k_render_sb<WR_, 512> : nt <= 576 ? k_render_sb<WR_, 576> : nt <= 768 ? k_render_sb<WR_, 768> : k_render_sb<WR_, 1024>)
         if (s->render_sb) s->render_fn = r.WR == 21 ? XW_PICK_SB(21) : r.WR == 24 ? XW_PICK_SB(24) : r.WR == 32 ? XW_PICK_SB(32) : XW_PICK_SB(0);
         else s->render_fn = r.WR == 21 ? XW_PICK(21) : r.WR == 24 ? XW_PICK(24) : r.WR == 32 ? XW_PICK(32) : XW_PICK(0);
 #undef XW_PICK

@@ -29,7 +29,7 @@
 
 #define XW_MAX_OUT 252        // max frame side
 #define XW_RENDER_THREADS 1024
-#define XW_RENDER_MAX_GROUPS 4    // groups per CTA (two frame buffers each)
+#define XW_RENDER_MAX_GROUPS 12   // groups per CTA (named barriers 1..12)
 #define XW_TABLE_PAD 8192     // bytes past each table the compositor may read (and never use)
 
 struct XwTaps { const int16_t *xofs, *xa0, *xa1, *yofs, *ya0, *ya1; };  // cv::resize tables
@@ -466,16 +466,17 @@ XW_HD uint32_t xw_cell_desc(const XwDev& d, int e, int code) {
 #define XW_CELLBUF_BYTES (XW_CELL_STRIDE + XW_CODE_SLOTS * 4 + 16)
 struct XwRenderSmem { int hot, fb, plan, yb, cellinfo, pair, cell, bar, total; };
 XW_HD int xw_align16(int v) { return (v + 15) & ~15; }
-XW_HD XwRenderSmem xw_render_smem(const XwRender& r, int G) {
+// nbuf = frame buffers (and cell buffers) in the CTA: G in the single-buffer kernel, 2*G in the pipelined one
+XW_HD XwRenderSmem xw_render_smem(const XwRender& r, int nbuf) {
     XwRenderSmem s;
     int o = 0;
     s.hot = o; o += xw_align16(r.FB);
-    s.fb = o; o += 2 * G * xw_align16(r.FB);  // two frame buffers per group
+    s.fb = o; o += nbuf * xw_align16(r.FB);
     s.plan = o; o += r.n_plan * 16;
     s.yb = o; o += xw_align16(r.OH * 4);
     s.cellinfo = o; o += XW_MAX_DIM * XW_MAX_DIM * 4;
     s.pair = o; o += xw_align16(xw_pair_hot_bytes(r));
-    s.cell = o; o += 2 * G * XW_CELLBUF_BYTES;  // two cell buffers per group
+    s.cell = o; o += nbuf * XW_CELLBUF_BYTES;
     s.bar = o; o += 16;
     s.total = o;
     return s;
@@ -602,7 +603,7 @@ __global__ void __launch_bounds__(NT_MAX, 1)
 k_render(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int G = r.G, GT = r.GT;
-    const XwRenderSmem L = xw_render_smem(r, G);
+    const XwRenderSmem L = xw_render_smem(r, 2 * G);
     uint8_t* hot = smem + L.hot;
     XwU4* s_plan = (XwU4*)(smem + L.plan);
     uint32_t* s_yb = (uint32_t*)(smem + L.yb);
@@ -720,7 +721,7 @@ k_render(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
         }
         bool staged = !(loader && have_next);
         for (int i = gt; i < n_plan; i += GT) {
-            xw_compose_item<WR_T, (NT_MAX > 512)>(r, x, s_plan[i], cells, fb);
+            xw_compose_item<WR_T, (NT_MAX > 640)>(r, x, s_plan[i], cells, fb);
             if (!staged) {  // after the first bundle: by now the TMA store of env i-1 has usually drained
                 if (lane == 0) tma_wait_read<0>();
                 __syncwarp();
@@ -749,7 +750,7 @@ __global__ void __launch_bounds__(NT_MAX, 1)
 k_render_sb(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int G = r.G, GT = r.GT;
-    const XwRenderSmem L = xw_render_smem(r, (G + 1) / 2);
+    const XwRenderSmem L = xw_render_smem(r, G);
     uint8_t* hot = smem + L.hot;
     XwU4* s_plan = (XwU4*)(smem + L.plan);
     uint32_t* s_yb = (uint32_t*)(smem + L.yb);
@@ -836,10 +837,10 @@ k_render_sb(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride
             }
         }
         // the straddling-row items read only tables: they run while the staging copies are in flight
-        for (int i = gt; i < r.n_plan1; i += GT) xw_compose_item<WR_T, (NT_MAX > 512)>(r, x, s_plan[i], cells, fb);
+        for (int i = gt; i < r.n_plan1; i += GT) xw_compose_item<WR_T, (NT_MAX > 640)>(r, x, s_plan[i], cells, fb);
         cp_async_wait_all();
         group_bar(bar_id, GT);
-        for (int i = r.n_plan1 + gt; i < n_plan; i += GT) xw_compose_item<WR_T, (NT_MAX > 512)>(r, x, s_plan[i], cells, fb);
+        for (int i = r.n_plan1 + gt; i < n_plan; i += GT) xw_compose_item<WR_T, (NT_MAX > 640)>(r, x, s_plan[i], cells, fb);
         fence_async_smem();  // generic-proxy writes -> visible to the async (TMA) proxy
         group_bar(bar_id, GT);
         if (gt == 0) {
