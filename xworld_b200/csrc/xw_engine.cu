@@ -221,6 +221,7 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
     r.OH = OH; r.OW = OW; r.WR = t.WR; r.FB = t.FB; r.H = c.height; r.W = c.width;
     r.n_sr = (int)t.sr.size();
     r.n_icons = cat->n_icons; r.brick_icon = cat->brick_icon; r.agent_icon = cat->agent_icon;
+    { const char* ed = getenv("XW_RENDER_DEBUG"); r.debug = ed ? atoi(ed) : 0; }
     rc |= dupload(s, &r.taps.xofs, t.xofs.data(), t.xofs.size());
     rc |= dupload(s, &r.taps.xa0, t.xa0.data(), t.xa0.size());
     rc |= dupload(s, &r.taps.xa1, t.xa1.data(), t.xa1.size());

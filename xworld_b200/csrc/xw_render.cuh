@@ -42,6 +42,7 @@ struct XwRender {
     int32_t G, GT;            // warp groups per CTA, threads per group
     int32_t n_icons, brick_icon, agent_icon;
     int32_t n_sr;             // straddling rows
+    int32_t debug;            // tuning experiments only (XW_RENDER_DEBUG): 1 skip compose, 2 skip staging, 4 skip the frame store
     XwTaps taps;
     const int16_t* sr;        // [n_sr] the straddling rows
     const XwU4* plan;         // [n_plan] packed items (xw_render_host.hpp)
@@ -821,7 +822,7 @@ k_render_sb(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride
         group_bar(bar_id, GT);
         // stage the agent's and goals' table words into the frame buffer (LDGSTS, no registers): one
         // thread per (cell, plane, word column), one 4-byte copy per row
-        for (int i = gt; i < (1 + d.G) * XW_STAGE_COLS; i += GT) {
+        for (int i = gt; i < ((r.debug & 2) ? 0 : (1 + d.G) * XW_STAGE_COLS); i += GT) {
             const int slot = i / XW_STAGE_COLS, col = i - slot * XW_STAGE_COLS, c = col / 3, wc = col - 3 * c;
             uint32_t w0; int nrows; const uint32_t* src;
             if (xw_stage_column(r, cells, s_cellinfo, s_special[slot], c, wc, &w0, &nrows, &src)) {
@@ -840,10 +841,10 @@ k_render_sb(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride
         for (int i = gt; i < r.n_plan1; i += GT) xw_compose_item<WR_T, (NT_MAX > 640)>(r, x, s_plan[i], cells, fb);
         cp_async_wait_all();
         group_bar(bar_id, GT);
-        for (int i = r.n_plan1 + gt; i < n_plan; i += GT) xw_compose_item<WR_T, (NT_MAX > 640)>(r, x, s_plan[i], cells, fb);
+        for (int i = r.n_plan1 + gt; i < ((r.debug & 1) ? 0 : n_plan); i += GT) xw_compose_item<WR_T, (NT_MAX > 640)>(r, x, s_plan[i], cells, fb);
         fence_async_smem();  // generic-proxy writes -> visible to the async (TMA) proxy
         group_bar(bar_id, GT);
-        if (gt == 0) {
+        if (gt == 0 && !(r.debug & 4)) {
             tma_store_1d(frames + (size_t)env * env_stride, fb, (uint32_t)r.FB);
             tma_commit();
         }
