@@ -96,6 +96,11 @@ HostSim* hs_create(const xw_config* c, const xw_catalog* cat, int n) {
         r.plan = t.plan.data(); r.n_plan = (int)t.plan.size(); r.n_plan1 = t.n_plan1; r.G = 1; r.GT = t.n_warps * 32;
         r.cellinfo = t.cellinfo.data();
     }
+    xw_build_paint_tables(t);
+    if (t.sp_ok) {
+        r.cellgeo = t.cellgeo.data(); r.wcol = t.wcol.data();
+        r.nwc = t.nwc; r.slot_magic = 65536 / (3 * t.nwc) + 1;
+    }
     r.n_sr = (int)t.sr.size();
     r.sr = t.sr.data();
     r.atlas64 = cat->atlas64;
@@ -192,7 +197,12 @@ void hs_step(HostSim* s, const int32_t* actions, int act_rep, float* reward, int
 
 // Emulates one k_render warp group per env: celldesc, every item of the plan, copy out.  Configs the
 // compositor does not take go through the generic per-pixel rule (k_render_generic's arithmetic).
-void hs_render(HostSim* s, uint8_t* frames) {
+// mode 0: the plan compositor (k_render / k_render_sb); mode 1: the sparse painter (k_render_sp);
+// mode 2: the per-pixel rule on the 64-px atlas (k_render_generic's arithmetic) -- the ground truth
+int hs_sp_ok(HostSim* s) { return s->tab.sp_ok; }
+void hs_render_mode(HostSim* s, uint8_t* frames, int mode);
+void hs_render(HostSim* s, uint8_t* frames) { hs_render_mode(s, frames, s->tab.sp_ok ? 1 : 0); }
+void hs_render_mode(HostSim* s, uint8_t* frames, int mode) {
     XwRender& r = s->r;
     XwDev& d = s->d;
     std::vector<uint32_t> fb(r.FB / 4 + 4), yb(r.OH);
@@ -215,7 +225,31 @@ void hs_render(HostSim* s, uint8_t* frames) {
     for (int e = 0; e < d.n; ++e) {
         memcpy(code.data(), d.grid + (size_t)e * d.CS, d.CS);
         for (int k = 0; k < XW_CODE_SLOTS; ++k) icon[k] = k < XW_CELL_GOAL0 + d.G ? xw_cell_desc(d, e, k) : 0;
-        if (s->tab.fast_ok) {
+        if (s->tab.fast_ok && mode == 1 && s->tab.sp_ok) {
+            // k_render_sp: white pre-fill, list of the non-white cells, every slot of every listed cell
+            std::fill(fb.begin(), fb.end(), 0xffffffffu);
+            XwPaintCtx pg;
+            pg.cellgeo = r.cellgeo; pg.wcol = r.wcol;
+            std::vector<uint8_t> list;
+            for (int cell = 0; cell < d.H * d.W; ++cell) if (code[cell]) list.push_back((uint8_t)cell);
+            const int S = 3 * r.nwc, n_slots = (int)list.size() * S;
+            // slots run concurrently on the device: every word must have one writer, so the order of
+            // the slots cannot matter -- paint forwards and backwards and compare
+            std::vector<uint32_t> fb2(fb);
+            for (int pass = 0; pass < 2; ++pass) {
+                uint32_t* out = pass ? fb2.data() : fb.data();
+                for (int q = 0; q < n_slots; ++q) {
+                    const int sl = pass ? n_slots - 1 - q : q;
+                    int i, p, wc;
+                    xw_paint_decode(r, sl, &i, &p, &wc);
+                    if (i != sl / S || p != (sl % S) / r.nwc || wc != (sl % S) % r.nwc) abort();
+                    if (r.WR == 21 && (e & 1)) xw_paint_slot<21>(r, x, pg, cells, list[i], p, wc, out);
+                    else xw_paint_slot<0>(r, x, pg, cells, list[i], p, wc, out);
+                }
+            }
+            if (memcmp(fb.data(), fb2.data(), r.FB)) abort();
+            memcpy(frames + (size_t)e * r.FB, fb.data(), r.FB);
+        } else if (s->tab.fast_ok && mode != 2) {
             std::fill(fb.begin(), fb.end(), 0x5a5a5a5au);
             for (int cell = 0; cell < d.H * d.W; ++cell) {  // the kernel's staging pass (LDGSTS)
                 if (code[cell] < XW_CELL_AGENT) continue;
@@ -243,6 +277,11 @@ void hs_render(HostSim* s, uint8_t* frames) {
 void hs_set_grid(HostSim* s, const uint8_t* grid, const int32_t* goal_icons) {
     memcpy(s->d.grid, grid, (size_t)s->d.H * s->d.W);
     for (int k = 0; k < s->d.G; ++k) s->d.goal_icon[(size_t)k * s->d.n] = goal_icons[k];
+}
+
+void hs_set_grid_env(HostSim* s, int e, const uint8_t* grid, const int32_t* goal_icons) {
+    memcpy(s->d.grid + (size_t)e * s->d.CS, grid, (size_t)s->d.H * s->d.W);
+    for (int k = 0; k < s->d.G; ++k) s->d.goal_icon[(size_t)k * s->d.n + e] = goal_icons[k];
 }
 
 int hs_get_field(HostSim* s, const char* name, void* out) {

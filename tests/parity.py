@@ -58,6 +58,8 @@ class HostSim(object):
             L.hs_reset.argtypes = [C.c_void_p, C.c_void_p]
             L.hs_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
             L.hs_render.argtypes = [C.c_void_p, C.c_void_p]
+            L.hs_render_mode.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+            L.hs_sp_ok.argtypes = [C.c_void_p]
             L.hs_get_field.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
             L.hs_build_phase_atlas.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
             L.hs_fast_ok.argtypes = [C.c_void_p]
@@ -90,7 +92,9 @@ class HostSim(object):
         self.L.hs_step(self.h, a.ctypes.data, act_rep, r.ctypes.data, o.ctypes.data)
         return r, o, (self.render() if render else None)
 
-    def render(self):
+    def render(self, mode=None):
+        """mode None: what the engine would pick (sparse painter when the geometry allows); 0: the plan
+        compositor; 1: the sparse painter."""
         icons = set(self.field("goal_icon")[:, :self.cfg.n_goals].ravel().tolist())
         icons |= {self.catalog.brick_icon, self.catalog.agent_icon}
         if not icons <= self._atlas_icons:
@@ -98,7 +102,10 @@ class HostSim(object):
             arr = np.array(sorted(self._atlas_icons), np.int32)
             self.L.hs_build_phase_atlas(self.h, arr.ctypes.data, len(arr))
         out = np.zeros((self.n, 3, self.out_h, self.out_w), np.uint8)
-        self.L.hs_render(self.h, out.ctypes.data)
+        if mode is None:
+            self.L.hs_render(self.h, out.ctypes.data)
+        else:
+            self.L.hs_render_mode(self.h, out.ctypes.data, mode)
         return out
 
     def field(self, name):

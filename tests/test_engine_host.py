@@ -83,3 +83,46 @@ def test_hostsim_race_matches_oracle():
                 assert (np.array(list(st2), np.float32).view(np.uint32) == st[i].view(np.uint32)).all()
                 if ov2.value:
                     lib.xo_race_reset(C.byref(cfg), C.byref(o))
+
+
+@pytest.mark.parametrize("geom", [(11, 11, 84, 84), (7, 7, 84, 84), (15, 15, 128, 128), (8, 8, 96, 96), (16, 16, 128, 128),
+                                  (10, 10, 84, 84), (12, 12, 100, 100), (16, 16, 84, 84), (6, 6, 64, 64), (13, 13, 128, 128),
+                                  (5, 9, 60, 100), (16, 16, 252, 252), (3, 3, 20, 20), (9, 9, 84, 84), (14, 14, 112, 112)])
+def test_sparse_painter_and_plan_compositor_vs_per_pixel_rule(geom, synthetic_catalog):
+    """Both shared-memory renderers against the per-pixel rule on crowded random grids: goals and the agent
+    packed next to each other and next to bricks, so that every pair-table / exact fallback branch runs
+    (special-special borders, corners of four different cells)."""
+    H, W, OH, OW = geom
+    G = 8
+    cfg = _abi.default_config(height=H, width=W, n_goals=G, n_blocks=1, rules=_abi.XW_RULES_NAV3D, out_h=OH, out_w=OW)
+    n = 24
+    hs = parity.HostSim(cfg, synthetic_catalog, n)   # no reset: the grids are written below (maps are square
+    L = hs.L                                          # in the engine; the renderers take any H x W)
+    L.hs_set_grid_env.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    rng = np.random.RandomState(H * 1000 + OW)
+    pool = rng.permutation(synthetic_catalog.as_c().n_icons)[:10]
+    for e in range(n):
+        grid = np.zeros(H * W, np.uint8)
+        density = [0.0, 0.1, 0.3, 0.6, 1.0][e % 5]
+        grid[rng.rand(H * W) < density] = _abi.XW_CELL_BLOCK
+        # the agent and the goals in one clump (e even) or anywhere (e odd)
+        k = min(G + 1, H * W)
+        if e % 2 == 0:
+            y0, x0 = rng.randint(0, max(1, H - 2)), rng.randint(0, max(1, W - 2))
+            cand = [(y0 + dy) * W + (x0 + dx) for dy in range(3) for dx in range(3) if y0 + dy < H and x0 + dx < W]
+            cells = rng.permutation(cand)[:k]
+        else:
+            cells = rng.permutation(H * W)[:k]
+        for i, c in enumerate(cells):
+            grid[c] = _abi.XW_CELL_AGENT + i
+        icons = pool[rng.randint(0, len(pool), G)].astype(np.int32)
+        L.hs_set_grid_env(hs.h, e, np.ascontiguousarray(grid).ctypes.data, icons.ctypes.data)
+    want = hs.render(mode=2)
+    if L.hs_fast_ok(hs.h):
+        got0 = hs.render(mode=0)
+        assert (got0 == want).all(), ("plan", geom, int((got0 != want).sum()))
+    if L.hs_sp_ok(hs.h):
+        got1 = hs.render(mode=1)
+        bad = np.argwhere(got1 != want)
+        assert bad.size == 0, ("sparse", geom, len(bad), bad[:8].tolist())
+    assert L.hs_sp_ok(hs.h) == L.hs_fast_ok(hs.h)

@@ -38,6 +38,7 @@ def main():
         os.environ["XW_RENDER_CONFLICT_FREE"] = str(combo[3] if len(combo) > 3 else 0)
         os.environ["XW_RENDER_MODE"] = str(combo[4]) if len(combo) > 4 else "sb"
         os.environ["XW_RENDER_TWO_PHASE"] = str(combo[5]) if len(combo) > 5 else "0"
+        os.environ["XW_RENDER_SP_FILL"] = str(combo[6]) if len(combo) > 6 else "0"
         os.environ["XW_RENDER_GROUPS"] = str(g)
         os.environ["XW_RENDER_GROUP_THREADS"] = str(t)
         os.environ["XW_RENDER_SPLIT_M3"] = str(s)
@@ -65,7 +66,7 @@ def main():
         if ref is None:
             ref = chk
         same = bool((chk == ref).all())
-        print(json.dumps({"G": g, "GT": t, "split": s, "cfree": combo[3] if len(combo) > 3 else 0, "mode": os.environ["XW_RENDER_MODE"], "two_phase": os.environ["XW_RENDER_TWO_PHASE"], "ms": round(ms, 4), "GBs": round(n * fb / ms / 1e6, 1), "same_as_first": same}),
+        print(json.dumps({"G": g, "GT": t, "split": s, "cfree": combo[3] if len(combo) > 3 else 0, "mode": os.environ["XW_RENDER_MODE"], "two_phase": os.environ["XW_RENDER_TWO_PHASE"], "fill": os.environ["XW_RENDER_SP_FILL"], "ms": round(ms, 4), "GBs": round(n * fb / ms / 1e6, 1), "same_as_first": same}),
               flush=True)
         del sim
         torch.cuda.synchronize()

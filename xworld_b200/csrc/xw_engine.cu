@@ -94,7 +94,7 @@ struct xw_sim {
     XwRenderTables tab;
     std::vector<void*> allocs;
     int n_sms = 148, render_grid = 0, render_smem = 0;
-    bool render_sb = false;
+    bool render_sb = false, render_sp = false;
     uint8_t* tables = nullptr;      // phase atlas + edge / pair tables, one allocation
     size_t tables_bytes = 0, l2_window = 0;
     float l2_ratio = 0.f;
@@ -243,6 +243,16 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
         // Measured on B200 (profiles/r01_summary.md): sb 8x64 threads is the fastest at 84x84 frames.
         const char* em = getenv("XW_RENDER_MODE");
         s->render_sb = !(em && !strcmp(em, "pipe"));
+        // "sp" (opt-in until it beats "sb"): the sparse painter -- white pre-fill + the words of the
+        // non-white cells only; "sb" / "pipe": the dense plan compositors
+        xw_build_paint_tables(t);
+        s->render_sp = t.sp_ok && em && !strcmp(em, "sp");
+        if (s->render_sp) {
+            r.nwc = t.nwc;
+            r.slot_magic = 65536 / (3 * t.nwc) + 1;
+            const char* ef = getenv("XW_RENDER_SP_FILL");
+            r.sp_fill = ef ? atoi(ef) : 0;
+        }
         const int max_groups = s->render_sb ? XW_RENDER_MAX_GROUPS : XW_RENDER_MAX_GROUPS / 2;
         int G = eg ? atoi(eg) : max_groups;
         if (G > max_groups) G = max_groups;
@@ -251,13 +261,13 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
             // <= 512 threads/CTA keeps 124 registers per thread (no spills, 24-word load batches)
             int GT = et ? atoi(et) : (G >= 6 ? 64 : (768 / G) / 32 * 32);
             // 9 groups fit at 84x84 but need > 512 threads = fewer registers per thread: measured 30 % slower
-            if (!eg && s->render_sb && G * GT > 512 && G > 8) continue;
+            if (!eg && !s->render_sp && s->render_sb && G * GT > 512 && G > 8) continue;
             GT = GT / 32 * 32;
             if (GT < 32 || G * GT > XW_RENDER_THREADS) { if (et) break; continue; }
             const char* e2 = getenv("XW_RENDER_TWO_PHASE");
             xw_build_plan(t, GT / 32, split, cfree, !s->render_sb, e2 && atoi(e2) != 0);
             r.n_plan = (int)t.plan.size(); r.n_plan1 = t.n_plan1;
-            if (xw_render_smem(r, s->render_sb ? G : 2 * G).total > max_optin) continue;
+            if ((s->render_sp ? xw_render_sp_smem(r, G).total : xw_render_smem(r, s->render_sb ? G : 2 * G).total) > max_optin) continue;
             r.G = G; r.GT = GT;
             found = true;
         }
@@ -277,7 +287,8 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
         const size_t n_col = (size_t)(cat->n_icons + 1) * 2 * r.n_sc * 3 * c.height * r.RB + 64, n_row = (size_t)(cat->n_icons + 1) * 2 * r.n_sr * 3 * OW + 64;
         const size_t n_cwb = (size_t)16 * r.n_sr * r.n_sc * 3 + 64;
         auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
-        const size_t total = up(n_T) + (t.fast_ok ? up(n_ecol) + up(n_uv) + up(n_corner) + 2 * up(n_col) + 2 * up(n_row) + up(n_cwb) : 0);
+        const size_t n_white = s->render_sp ? (size_t)r.FB : 0;
+        const size_t total = up(n_T) + (t.fast_ok ? up(n_ecol) + up(n_uv) + up(n_corner) + 2 * up(n_col) + 2 * up(n_row) + up(n_cwb) + up(n_white) : 0);
         uint8_t* base = nullptr;
         rc |= dalloc(s, &base, total, false);
         if (rc) return rc;
@@ -288,6 +299,13 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
         if (t.fast_ok) {
             r.ecol = (const uint16_t*)take(n_ecol); r.uv = (const uint16_t*)take(n_uv); r.corner = (const uint32_t*)take(n_corner);
             r.colL = take(n_col); r.colR = take(n_col); r.rowT = take(n_row); r.rowB = take(n_row); r.cornerWB = take(n_cwb);
+            if (s->render_sp) {
+                uint8_t* w = take(n_white);
+                CUDA_TRY(cudaMemset(w, 0xff, n_white));
+                r.white = w;
+                rc |= dupload(s, &r.cellgeo, t.cellgeo.data(), t.cellgeo.size());
+                rc |= dupload(s, &r.wcol, t.wcol.data(), t.wcol.size());
+            }
             rc |= dupload(s, &r.plan, t.plan.data(), t.plan.size());
             rc |= dupload(s, &r.cellinfo, t.cellinfo.data(), t.cellinfo.size());
             rc |= dupload(s, &r.sr, t.sr.empty() ? &zero16 : t.sr.data(), t.sr.empty() ? 1 : t.sr.size());
@@ -319,15 +337,18 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
     }
     CUDA_TRY(cudaGetLastError());
     if (t.fast_ok) {
-        s->render_smem = xw_render_smem(r, s->render_sb ? r.G : 2 * r.G).total;
+        s->render_smem = s->render_sp ? xw_render_sp_smem(r, r.G).total : xw_render_smem(r, s->render_sb ? r.G : 2 * r.G).total;
         // instantiations: compile-time row stride for the common frame widths x register budget by CTA size
         const int nt = r.G * r.GT;
 #define XW_PICK(WR_) (nt <= 512 ? k_render<WR_, 512> : nt <= 768 ? k_render<WR_, 768> : k_render<WR_, 1024>)
 #define XW_PICK_SB(WR_) (nt <= 512 ? k_render_sb<WR_, 512> : nt <= 576 ? k_render_sb<WR_, 576> : nt <= 768 ? k_render_sb<WR_, 768> : k_render_sb<WR_, 1024>)
-        if (s->render_sb) s->render_fn = r.WR == 21 ? XW_PICK_SB(21) : r.WR == 24 ? XW_PICK_SB(24) : r.WR == 32 ? XW_PICK_SB(32) : XW_PICK_SB(0);
+#define XW_PICK_SP(WR_) (nt <= 512 ? k_render_sp<WR_, 512> : nt <= 768 ? k_render_sp<WR_, 768> : k_render_sp<WR_, 1024>)
+        if (s->render_sp) s->render_fn = r.WR == 21 ? XW_PICK_SP(21) : r.WR == 24 ? XW_PICK_SP(24) : r.WR == 32 ? XW_PICK_SP(32) : XW_PICK_SP(0);
+        else if (s->render_sb) s->render_fn = r.WR == 21 ? XW_PICK_SB(21) : r.WR == 24 ? XW_PICK_SB(24) : r.WR == 32 ? XW_PICK_SB(32) : XW_PICK_SB(0);
         else s->render_fn = r.WR == 21 ? XW_PICK(21) : r.WR == 24 ? XW_PICK(24) : r.WR == 32 ? XW_PICK(32) : XW_PICK(0);
 #undef XW_PICK
 #undef XW_PICK_SB
+#undef XW_PICK_SP
         CUDA_TRY(cudaFuncSetAttribute(s->render_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, s->render_smem));
         s->render_grid = s->n_sms;
     }

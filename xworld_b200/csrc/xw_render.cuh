@@ -64,6 +64,13 @@ struct XwRender {
     const int16_t* sc;        // [n_sc] the straddling columns
     int32_t n_sc;
     const uint8_t* atlas64;   // [n_icons][64][64][3] BGR
+    // sparse painter (k_render_sp): static geometry, see xw_build_paint_tables (xw_render_host.hpp)
+    const XwU4* cellgeo;      // [H*W]
+    const uint32_t* wcol;     // [WR]
+    const uint8_t* white;     // [FB] 0xff: source of the TMA pre-fill
+    int32_t nwc;              // word-column slots per cell; a cell has 3 * nwc slots (plane-major)
+    int32_t slot_magic;       // slot / (3 * nwc) == (slot * slot_magic) >> 16 for slot < 4096
+    int32_t sp_fill;          // 0: pre-fill with vector stores, 1: with a TMA bulk load of `white`
 };
 
 // ---- exact cv::resize arithmetic --------------------------------------------------------
@@ -175,6 +182,14 @@ XW_HD uint32_t xw_prmt(uint32_t a, uint32_t b, uint32_t sel) {
     uint32_t o = 0;
     for (int i = 0; i < 4; ++i) o |= (uint32_t)((v >> (8 * ((sel >> (4 * i)) & 7))) & 0xff) << (8 * i);
     return o;
+#endif
+}
+
+XW_HD int xw_popc(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
 #endif
 }
 
@@ -479,6 +494,161 @@ XW_HD XwRenderSmem xw_render_smem(const XwRender& r, int nbuf) {
     s.pair = o; o += xw_align16(xw_pair_hot_bytes(r));
     s.cell = o; o += nbuf * XW_CELLBUF_BYTES;
     s.bar = o; o += 16;
+    s.total = o;
+    return s;
+}
+
+
+// ---- sparse painter (k_render_sp) -----------------------------------------------------------------
+// The frame buffer is pre-filled with white; every non-white cell then paints the words it owns (rule in
+// xw_render_host.hpp: xw_build_paint_tables).  One slot = (cell, plane, word column of the cell): the
+// rows of the cell's band, plus the word of the straddling row below it, plus the one above it when the
+// cells above are white.  Same table arithmetic as the plan items above (pair tables, exact fallbacks),
+// but sources are read in place: brick / white from the shared-memory brick table, agent and goal words
+// straight from the L2-resident phase atlas.
+struct XwPaintCtx { const XwU4* cellgeo; const uint32_t* wcol; };  // shared-memory copies on the device
+
+XW_HD const uint32_t* xw_src_direct(const XwRender& r, const XwComposeCtx& x, uint32_t dsc) {
+    return (const uint32_t*)(xw_special(r, dsc) ? r.T + (size_t)(dsc - 1) * r.FB : x.hot);
+}
+
+// word k of straddling row q = output row dy, between cell rows ty and ty + 1, plane p
+template <int WR_T>
+XW_HD void xw_paint_rword(const XwRender& r, const XwComposeCtx& x, const XwCells& cells, uint32_t wk, int k, int ty, int q, int dy,
+                          int p, uint32_t* fb) {
+    const int WR = WR_T ? WR_T : r.WR;
+    const int lo = wk & 15, hi = (wk >> 4) & 15;
+    const uint32_t sel = (wk >> 8) & 0xffffu;
+    const int top = ty * r.W;
+    const uint32_t dTa = cells(top + lo), dBa = cells(top + r.W + lo), dTb = cells(top + hi), dBb = cells(top + r.W + hi);
+    const int cTa = xw_cls(r, dTa), cBa = xw_cls(r, dBa), cTb = xw_cls(r, dTb), cBb = xw_cls(r, dBb);
+    uint32_t word;
+    if ((cTa == 2 && cBa == 2) || (cTb == 2 && cBb == 2)) {
+        // a special cell above a special cell: separable rule (U(top) + V(bottom) + 2) >> 2 on packed u16 pairs
+        const size_t per_desc = (size_t)r.n_sr * 2 * 3 * r.OW;
+        const uint16_t* u0 = r.uv + ((size_t)q * 2 * 3 + p) * r.OW + 4 * k;
+        const uint16_t* v0 = u0 + (size_t)3 * r.OW;
+        const XwU2 uA = *(const XwU2*)(u0 + dTa * per_desc), uB = *(const XwU2*)(u0 + dTb * per_desc);
+        const XwU2 vA = *(const XwU2*)(v0 + dBa * per_desc), vB = *(const XwU2*)(v0 + dBb * per_desc);
+        const uint32_t a_lo = ((uA.x + vA.x + 0x00020002u) >> 2) & 0x00ff00ffu, a_hi = ((uA.y + vA.y + 0x00020002u) >> 2) & 0x00ff00ffu;
+        const uint32_t b_lo = ((uB.x + vB.x + 0x00020002u) >> 2) & 0x00ff00ffu, b_hi = ((uB.y + vB.y + 0x00020002u) >> 2) & 0x00ff00ffu;
+        word = xw_prmt(xw_prmt(a_lo, a_hi, 0x6420), xw_prmt(b_lo, b_hi, 0x6420), sel);
+    } else {
+        const size_t rs = xw_rowpair_stride(r);
+        const uint8_t *tA = x.rowT_hot, *tB = x.rowT_hot;
+        if (cBa < 2) tA = (cTa < 2 ? x.rowT_hot + (size_t)cTa * 2 * rs : r.rowT + (size_t)dTa * 2 * rs) + (size_t)cBa * rs;
+        else tA = r.rowB + (size_t)dBa * 2 * rs + (size_t)cTa * rs;
+        if (cBb < 2) tB = (cTb < 2 ? x.rowT_hot + (size_t)cTb * 2 * rs : r.rowT + (size_t)dTb * 2 * rs) + (size_t)cBb * rs;
+        else tB = r.rowB + (size_t)dBb * 2 * rs + (size_t)cTb * rs;
+        const size_t off = (size_t)(q * 3 + p) * r.OW + 4 * k;
+        word = xw_prmt(*(const uint32_t*)(tA + off), *(const uint32_t*)(tB + off), sel);
+    }
+    if ((wk >> 24) & 1) {  // corner byte: four cells
+        const int sh = (int)((wk >> 25) & 3) * 8, sidx = (int)(wk >> 27);
+        uint32_t v;
+        if ((cTa | cTb | cBa | cBb) < 2) v = x.cornerWB[(((cTa | (cTb << 1) | (cBa << 2) | (cBb << 3)) * r.n_sr + q) * r.n_sc + sidx) * 3 + p];
+        else v = xw_corner_px(r, x, cells, top + lo, p, dy, r.sc[sidx]);
+        word = (word & ~(0xffu << sh)) | (v << sh);
+    }
+    fb[p * (r.OH * WR) + dy * WR + k] = word;
+}
+
+template <int WR_T>
+XW_HD void xw_paint_slot(const XwRender& r, const XwComposeCtx& x, const XwPaintCtx& g, const XwCells& cells, int cell, int p, int wc,
+                         uint32_t* fb) {
+    const int WR = WR_T ? WR_T : r.WR;
+    const XwU4 cg = g.cellgeo[cell];
+    if (wc >= (int)((cg.x >> 24) & 7)) return;
+    const int k = (int)(cg.y & 0xff) + wc, ty = (int)((cg.y >> 8) & 0xff);
+    const uint32_t wk = g.wcol[k];
+    const int lo = wk & 15, hi = (wk >> 4) & 15;
+    const int row = cell - (int)((cg.z >> 8) & 0xff);  // ty * W
+    const uint32_t dA = cells(row + lo), dB = cells(row + hi);
+    if (row + lo != cell && dA != 0) return;  // the non-white left neighbour owns this word
+    const uint32_t sel = (wk >> 8) & 0xffffu;
+    const int nrows = (int)((cg.x >> 16) & 0xff), y0 = (int)(cg.z & 0xff);
+    const uint32_t w0 = (cg.x & 0xffffu) + (uint32_t)wc + (uint32_t)(p * r.OH * WR);
+    const uint32_t* pA = xw_src_direct(r, x, dA) + w0;
+    const uint32_t* pB = xw_src_direct(r, x, dB) + w0;
+    const uint32_t wmask = xw_prmt(dA == 0 ? 0xffffffffu : 0u, dB == 0 ? 0xffffffffu : 0u, sel);
+    uint32_t* dst = fb + w0;
+    if (!((wk >> 24) & 1)) {
+        // all loads of a batch before its stores (the frame buffer and the tables may alias as far as the
+        // compiler knows); rows past the band are loaded (the tables are padded) and not stored
+        {
+            uint32_t va[8], vb[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { va[j] = pA[j * WR]; vb[j] = pB[j * WR]; }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < nrows) dst[j * WR] = xw_prmt(va[j], vb[j], sel) | wmask;
+        }
+        for (int i0 = 8; i0 < nrows; i0 += 4) {
+            uint32_t va[4], vb[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { va[j] = pA[(i0 + j) * WR]; vb[j] = pB[(i0 + j) * WR]; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (i0 + j < nrows) dst[(i0 + j) * WR] = xw_prmt(va[j], vb[j], sel) | wmask;
+        }
+    } else {
+        // one byte of the word lies on a straddling column: it comes from a pair table -- (left cell, class
+        // of the right cell) or (right cell, class of the left cell); both special -> exact, from the edge taps
+        const int sh = (int)((wk >> 25) & 3) * 8, sidx = (int)(wk >> 27);
+        const int cL = xw_cls(r, dA), cR = xw_cls(r, dB);
+        const size_t cs = xw_colpair_stride(r);
+        const uint8_t* tab = x.colL_hot;
+        if (cR < 2) tab = (cL < 2 ? x.colL_hot + (size_t)cL * 2 * cs : r.colL + (size_t)dA * 2 * cs) + (size_t)cR * cs;
+        else if (cL < 2) tab = r.colR + (size_t)dB * 2 * cs + (size_t)cL * cs;
+        tab += ((size_t)(sidx * 3 + p) * r.H + ty) * r.RB;
+        const uint32_t keep = ~(0xffu << sh);
+        for (int i0 = 0; i0 < nrows; i0 += 4) {
+            const uint32_t pb = *(const uint32_t*)(tab + i0);  // the straddling byte of four rows
+            uint32_t va[4], vb[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { va[j] = pA[(i0 + j) * WR]; vb[j] = pB[(i0 + j) * WR]; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (i0 + j < nrows) dst[(i0 + j) * WR] = ((xw_prmt(va[j], vb[j], sel) | wmask) & keep) | (((pb >> (8 * j)) & 0xffu) << sh);
+        }
+        if (cL == 2 && cR == 2) {
+            const uint16_t* eL = r.ecol + ((((size_t)dA * 2 + 0) * 3 + p) * r.H + ty) * r.RB;
+            const uint16_t* eR = r.ecol + ((((size_t)dB * 2 + 1) * 3 + p) * r.H + ty) * r.RB;
+            const int dx = r.sc[sidx], a0 = r.taps.xa0[dx], a1 = r.taps.xa1[dx];
+            for (int j = 0; j < nrows; ++j) {
+                const uint32_t tl = eL[j], tr = eR[j], b = x.yb[y0 + j];
+                const uint32_t v = xw_resize_px(tl & 255, tr & 255, tl >> 8, tr >> 8, a0, a1, b & 0xffff, b >> 16);
+                dst[j * WR] = (dst[j * WR] & keep) | (v << sh);
+            }
+        }
+    }
+    const int qb = (int)((cg.y >> 16) & 0xff), qa = (int)(cg.y >> 24);
+    if (r.debug & 16) return;
+    if (qb != 0xff) xw_paint_rword<WR_T>(r, x, cells, wk, k, ty, qb, y0 + nrows, p, fb);
+    if (qa != 0xff && cells.code[row - r.W + lo] == 0 && cells.code[row - r.W + hi] == 0)
+        xw_paint_rword<WR_T>(r, x, cells, wk, k, ty - 1, qa, y0 - 1, p, fb);
+}
+
+// slot s of the cell list -> (list index, plane, word column)
+XW_HD void xw_paint_decode(const XwRender& r, int s, int* i, int* p, int* wc) {
+    *i = (int)(((uint32_t)s * (uint32_t)r.slot_magic) >> 16);
+    const int j = s - *i * 3 * r.nwc;
+    *p = (j >= r.nwc) + (j >= 2 * r.nwc);
+    *wc = j - *p * r.nwc;
+}
+#define XW_SP_LIST_BYTES (XW_MAX_DIM * XW_MAX_DIM + 16)   // non-white cell list + its length (u32 at the end)
+struct XwRenderSpSmem { int hot, fb, cellgeo, wcol, yb, pair, cell, bar, total; };
+XW_HD XwRenderSpSmem xw_render_sp_smem(const XwRender& r, int G) {
+    XwRenderSpSmem s;
+    int o = 0;
+    s.hot = o; o += xw_align16(r.FB);
+    s.fb = o; o += G * xw_align16(r.FB);
+    s.cellgeo = o; o += r.H * r.W * 16;
+    s.wcol = o; o += xw_align16(r.WR * 4);
+    s.yb = o; o += xw_align16(r.OH * 4);
+    s.pair = o; o += xw_align16(xw_pair_hot_bytes(r));
+    s.cell = o; o += G * (XW_CELLBUF_BYTES + XW_SP_LIST_BYTES);
+    s.bar = o; o += 16 + 8 * G;
     s.total = o;
     return s;
 }
@@ -842,6 +1012,152 @@ k_render_sb(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride
         cp_async_wait_all();
         group_bar(bar_id, GT);
         for (int i = r.n_plan1 + gt; i < ((r.debug & 1) ? 0 : n_plan); i += GT) xw_compose_item<WR_T, (NT_MAX > 640)>(r, x, s_plan[i], cells, fb);
+        fence_async_smem();  // generic-proxy writes -> visible to the async (TMA) proxy
+        group_bar(bar_id, GT);
+        if (gt == 0 && !(r.debug & 4)) {
+            tma_store_1d(frames + (size_t)env * env_stride, fb, (uint32_t)r.FB);
+            tma_commit();
+        }
+    }
+    if (gt == 0) tma_wait_all<0>();
+}
+
+
+// Sparse painter (the default): r.G warp groups, one frame buffer each.  Per env a group
+//   (warp 0) stores the env's cell codes, lists its non-white cells (ballot-free warp scan), waits until
+//            the TMA store of the group's previous frame has drained the buffer;
+//   pre-fills the buffer with white -- vector stores by every thread, or one TMA bulk load (r.sp_fill);
+//   paints the slots of the listed cells (xw_paint_slot): ~30 % of the words of a maze frame;
+//   hands the frame to the TMA engine (one bulk store, evict-first in L2).
+template <int WR_T, int NT_MAX>
+__global__ void __launch_bounds__(NT_MAX, 1)
+k_render_sp(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int G = r.G, GT = r.GT;
+    const XwRenderSpSmem L = xw_render_sp_smem(r, G);
+    uint8_t* hot = smem + L.hot;
+    uint32_t* s_yb = (uint32_t*)(smem + L.yb);
+    uint64_t* bar = (uint64_t*)(smem + L.bar);
+    const int tid = threadIdx.x, nt = blockDim.x;
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        for (int i = 0; i < G; ++i) mbar_init(bar + 2 + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {  // stage the brick table: one TMA bulk load per CTA
+        mbar_expect_tx(bar, (uint32_t)r.FB);
+        tma_load_1d(hot, r.T + (size_t)r.brick_icon * r.FB, (uint32_t)r.FB, bar);
+    }
+    {  // geometry + row weights + pair-table heads -> shared memory
+        for (int i = tid; i < r.H * r.W; i += nt) ((XwU4*)(smem + L.cellgeo))[i] = r.cellgeo[i];
+        for (int i = tid; i < r.WR; i += nt) ((uint32_t*)(smem + L.wcol))[i] = r.wcol[i];
+        for (int i = tid; i < r.OH; i += nt) s_yb[i] = (uint32_t)(uint16_t)r.taps.ya0[i] | ((uint32_t)(uint16_t)r.taps.ya1[i] << 16);
+        const int cs2 = (int)(2 * xw_colpair_stride(r)), rs2 = (int)(2 * xw_rowpair_stride(r));
+        uint8_t* pc = smem + L.pair;
+        uint8_t* pr = pc + 2 * cs2;
+        for (int i = tid; i < 2 * cs2; i += nt) pc[i] = r.colL[(size_t)(i < cs2 ? 0 : r.brick_icon + 1) * cs2 + (i < cs2 ? i : i - cs2)];
+        for (int i = tid; i < 2 * rs2; i += nt) pr[i] = r.rowT[(size_t)(i < rs2 ? 0 : r.brick_icon + 1) * rs2 + (i < rs2 ? i : i - rs2)];
+        for (int i = tid; i < 16 * r.n_sr * r.n_sc * 3; i += nt) pr[2 * rs2 + i] = r.cornerWB[i];
+        for (int i = tid; i < G * (XW_CELLBUF_BYTES + XW_SP_LIST_BYTES) / 4; i += nt) ((uint32_t*)(smem + L.cell))[i] = 0;
+    }
+    mbar_wait(bar, 0);
+    __syncthreads();
+
+    const int g = tid / GT, gt = tid - g * GT;
+    if (g >= G) return;  // spare warps (G*GT < blockDim.x)
+    uint8_t* s_code = smem + L.cell + g * (XW_CELLBUF_BYTES + XW_SP_LIST_BYTES);
+    uint32_t* s_icon = (uint32_t*)(s_code + XW_CELL_STRIDE);
+    uint8_t* s_list = s_code + XW_CELLBUF_BYTES;
+    volatile uint32_t* s_count = (volatile uint32_t*)(s_list + XW_MAX_DIM * XW_MAX_DIM);
+    uint32_t* fb = (uint32_t*)(smem + L.fb + (size_t)g * xw_align16(r.FB));
+    uint64_t* fillbar = bar + 2 + g;
+    XwComposeCtx x;
+    x.hot = hot; x.yb = s_yb;
+    x.colL_hot = smem + L.pair; x.rowT_hot = smem + L.pair + 4 * xw_colpair_stride(r);
+    x.cornerWB = x.rowT_hot + 4 * xw_rowpair_stride(r);
+    XwPaintCtx pg;
+    pg.cellgeo = (const XwU4*)(smem + L.cellgeo); pg.wcol = (const uint32_t*)(smem + L.wcol);
+    XwCells cells;
+    cells.code = s_code; cells.icon = s_icon;
+    const int bar_id = 1 + g;
+    const int gstride = gridDim.x * G;
+    const int lane = gt & 31;
+    const bool w0 = gt < 32;  // warp 0 of the group: cells, list
+    const int row_words = d.CS >> 2, HW = d.H * d.W;
+    const int S = 3 * r.nwc;
+    const bool tma_fill = r.sp_fill != 0;
+    int env = blockIdx.x * G + g;
+    if (env >= d.n) return;
+
+    // register prefetch of the next env's grid row (<= 64 words: two per lane of warp 0) and goal icons
+    uint32_t nq0 = 0, nq1 = 0, ni = 0;
+    auto load_cells = [&](int e) {
+        const uint32_t* rowp = (const uint32_t*)(d.grid + (size_t)e * d.CS);
+        if (lane < row_words) nq0 = rowp[lane];
+        if (lane + 32 < row_words) nq1 = rowp[lane + 32];
+        if (lane < d.G) ni = (uint32_t)d.goal_icon[(size_t)lane * d.n + e] + 1;
+    };
+    if (w0) {
+        load_cells(env);
+        if (lane == XW_CELL_BLOCK) s_icon[lane] = (uint32_t)d.brick_icon + 1;
+        if (lane == XW_CELL_AGENT) s_icon[lane] = (uint32_t)d.agent_icon + 1;
+    }
+    for (uint32_t it = 0; env < d.n; env += gstride, ++it) {
+        if (w0) {
+            if (tma_fill && lane == 0 && !(r.debug & 2)) {  // buffer drained -> white again, asynchronously
+                tma_wait_read<0>();
+                mbar_expect_tx(fillbar, (uint32_t)r.FB);
+                tma_load_1d(fb, r.white, (uint32_t)r.FB, fillbar);
+            }
+            // cells -> shared memory; list of the non-white cells (cells past the map are zero)
+            if (lane < d.G) s_icon[XW_CELL_GOAL0 + lane] = ni;
+            uint32_t m0 = 0, m1 = 0;
+            if (lane < row_words) {
+                ((uint32_t*)s_code)[lane] = nq0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) if (((nq0 >> (8 * b)) & 0xff) && 4 * lane + b < HW && !((r.debug & 8) && ((nq0 >> (8 * b)) & 0xff) >= XW_CELL_AGENT)) m0 |= 1u << b;
+            }
+            if (lane + 32 < row_words) {
+                ((uint32_t*)s_code)[lane + 32] = nq1;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) if (((nq1 >> (8 * b)) & 0xff) && 4 * (lane + 32) + b < HW) m1 |= 1u << b;
+            }
+            // inclusive scan of the per-lane counts; the second half of the row follows the first
+            const int c0 = xw_popc(m0), c1 = xw_popc(m1);
+            int s0 = c0, s1 = c1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t0 = __shfl_up_sync(0xffffffffu, s0, o), t1 = __shfl_up_sync(0xffffffffu, s1, o);
+                if (lane >= o) { s0 += t0; s1 += t1; }
+            }
+            const int tot0 = __shfl_sync(0xffffffffu, s0, 31), tot1 = __shfl_sync(0xffffffffu, s1, 31);
+            int pos = s0 - c0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) if (m0 & (1u << b)) s_list[pos++] = (uint8_t)(4 * lane + b);
+            pos = tot0 + s1 - c1;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) if (m1 & (1u << b)) s_list[pos++] = (uint8_t)(4 * (lane + 32) + b);
+            if (lane == 0) {
+                *s_count = (uint32_t)(tot0 + tot1);
+                if (!tma_fill) tma_wait_read<0>();  // the TMA store of this group's previous frame has drained fb
+            }
+        }
+        group_bar(bar_id, GT);
+        if (!tma_fill && !(r.debug & 2)) {
+            const int4 ones = make_int4(-1, -1, -1, -1);
+            for (int i = gt; i < r.FB / 16; i += GT) ((int4*)fb)[i] = ones;
+        }
+        if (w0 && env + gstride < d.n) load_cells(env + gstride);  // prefetch while this env is painted
+        if (tma_fill) { if (!(r.debug & 2)) mbar_wait(fillbar, it & 1); }
+        else group_bar(bar_id, GT);
+        const int n_slots = (r.debug & 1) ? 0 : (int)*s_count * S;
+        for (int s = gt; s < n_slots; s += GT) {
+            int i, p, wc;
+            xw_paint_decode(r, s, &i, &p, &wc);
+            xw_paint_slot<WR_T>(r, x, pg, cells, s_list[i], p, wc, fb);
+        }
         fence_async_smem();  // generic-proxy writes -> visible to the async (TMA) proxy
         group_bar(bar_id, GT);
         if (gt == 0 && !(r.debug & 4)) {

@@ -53,6 +53,11 @@ struct XwRenderTables {
     int RB = 0;                          // rows per band in the edge table, a multiple of 4
     std::vector<XwPlanItem> items;       // per-plane items (planner input)
     std::vector<XwU4> plan;              // bundled plan for n_warps warps per group
+    // sparse painter (k_render_sp): static geometry per cell / per word column, see xw_build_paint_tables
+    bool sp_ok = false;
+    int nwc = 0;                         // most word columns one cell column touches
+    std::vector<XwU4> cellgeo;           // [H*W]
+    std::vector<uint32_t> wcol;          // [WR]
     int n_warps = 0;
     int n_plan1 = 0;                     // plan[0..n_plan1): phase 1 (R / RC bundles), the rest: phase 2
     int bank_conflicts = 0;              // lane pairs of a bundle left on one bank (0 = conflict-free plan)
@@ -159,6 +164,73 @@ inline XwRenderTables xw_build_render_tables(int H, int W, int OH, int OW) {
         if (it.type < XW_ITEM_R && it.cellA != it.cellB) t.cellinfo[it.cellB] |= 1u << 26;
     t.fast_ok = ok;
     return t;
+}
+
+// ---- sparse painter geometry -------------------------------------------------------------------
+// k_render_sp pre-fills a frame with white and then paints only the words a non-white cell touches.
+// A frame word (band = cell row ty, word column k) touches at most two cell columns lo <= hi (its four
+// bytes' tap-0 cells, plus the tap-1 cell of a straddling byte); its OWNER is cell (ty,lo) unless that
+// cell is white, then (ty,hi).  The word of a straddling row between bands ty and ty+1 is owned by the
+// owner of word (ty,k) if there is one, else by the owner of word (ty+1,k).  Every non-white word thus
+// has exactly one writer and all-white words none.
+//   wcol[k]    = lo | hi << 4 | sel << 8 | has_sc << 24 | sbyte << 25 | sidx << 27
+//                sel: PRMT selector taking byte i from word(lo) or word(hi); the straddling column
+//                sc[sidx] (if any) is byte `sbyte`, its tap-0 cell column is lo and its tap-1 column hi
+//   cellgeo[c] = x: woff | nrows << 16 | nwords << 24     first word of the cell's band rows in a plane, rows of
+//                                                         the band without its straddling row, word columns
+//                y: kfirst | ty << 8 | q_below << 16 | q_above << 24   (straddling-row index, 0xff = none)
+//                z: y0 | tx << 8                          first row of the band, cell column
+inline void xw_build_paint_tables(XwRenderTables& t) {
+    t.sp_ok = false;
+    if (!t.fast_ok || t.W > 16 || t.H > 255) return;
+    const int W = t.W, H = t.H, WR = t.WR;
+    std::vector<uint8_t> is_sc(t.OW, 0), is_sr(t.OH, 0);
+    for (int16_t v : t.sc) is_sc[v] = 1;
+    for (int16_t v : t.sr) is_sr[v] = 1;
+    t.wcol.assign(WR, 0);
+    std::vector<int> kfirst(W, -1), klast(W, -1);
+    for (int k = 0; k < WR; ++k) {
+        int tx[4], lo = 1 << 30, hi = -1, nsc = 0, sbyte = 0, sidx = 0;
+        for (int i = 0; i < 4; ++i) {
+            tx[i] = t.xofs[4 * k + i] >> 6;
+            lo = std::min(lo, tx[i]); hi = std::max(hi, tx[i]);
+            if (is_sc[4 * k + i]) {
+                ++nsc; sbyte = i; hi = std::max(hi, tx[i] + 1);
+                for (size_t si = 0; si < t.sc.size(); ++si) if (t.sc[si] == 4 * k + i) sidx = (int)si;
+            }
+        }
+        if (hi - lo > 1 || nsc > 1 || hi >= W) return;
+        // the straddling byte must have its tap-0 cell = lo (then tap 1 = hi)
+        if (nsc && tx[sbyte] != lo) return;
+        uint32_t sel = 0;
+        for (int i = 0; i < 4; ++i) sel |= (uint32_t)(tx[i] == lo ? i : 4 + i) << (4 * i);
+        t.wcol[k] = (uint32_t)lo | ((uint32_t)hi << 4) | (sel << 8) | ((uint32_t)(nsc ? 1 : 0) << 24) | ((uint32_t)sbyte << 25) | ((uint32_t)sidx << 27);
+        for (int c = lo; c <= hi; ++c) { if (kfirst[c] < 0) kfirst[c] = k; klast[c] = k; }
+    }
+    t.nwc = 0;
+    for (int c = 0; c < W; ++c) {
+        if (kfirst[c] < 0) return;
+        t.nwc = std::max(t.nwc, klast[c] - kfirst[c] + 1);
+    }
+    if (t.nwc > 4) return;
+    t.cellgeo.assign((size_t)H * W, XwU4{0, 0, 0, 0});
+    std::vector<int> qb(H, 0xff);
+    for (int ty = 0; ty < H; ++ty) {
+        const int y0 = t.band_y0[ty];
+        if (y0 < 0) return;
+        int y1 = y0;
+        while (y1 < t.OH && (t.yofs[y1] >> 6) == ty) ++y1;
+        const bool srow = is_sr[y1 - 1] != 0;
+        if (srow) { for (size_t q = 0; q < t.sr.size(); ++q) if (t.sr[q] == y1 - 1) qb[ty] = (int)q; if (ty + 1 >= H) return; }
+        const int nrows = y1 - y0 - (srow ? 1 : 0);
+        for (int tx = 0; tx < W; ++tx) {
+            XwU4& g = t.cellgeo[(size_t)ty * W + tx];
+            g.x = (uint32_t)(y0 * WR + kfirst[tx]) | ((uint32_t)nrows << 16) | ((uint32_t)(klast[tx] - kfirst[tx] + 1) << 24);
+            g.y = (uint32_t)kfirst[tx] | ((uint32_t)ty << 8) | ((uint32_t)qb[ty] << 16) | ((uint32_t)(ty > 0 ? qb[ty - 1] : 0xff) << 24);
+            g.z = (uint32_t)y0 | ((uint32_t)tx << 8);
+        }
+    }
+    t.sp_ok = true;
 }
 
 // Cost model of one item (instructions), calibrated on ncu source counters (profiles/).
