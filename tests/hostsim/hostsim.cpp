@@ -26,6 +26,7 @@ struct HostSim {
     std::vector<uint16_t> ecol, uv;
     std::vector<uint32_t> corner;
     std::vector<uint8_t> colL, colR, rowT, rowB, cwb;
+    std::vector<uint32_t> ctab, cornerP;
     XwRaceCfg race;
 };
 
@@ -98,8 +99,8 @@ HostSim* hs_create(const xw_config* c, const xw_catalog* cat, int n) {
     }
     xw_build_paint_tables(t);
     if (t.sp_ok) {
-        r.cellgeo = t.cellgeo.data(); r.wcol = t.wcol.data();
-        r.nwc = t.nwc; r.slot_magic = 65536 / (3 * t.nwc) + 1;
+        r.cellgeo = t.cellgeo.data(); r.wcol = t.wcol.data(); r.wshare = t.wshare.data(); r.sr_ty = t.sr_ty.data();
+        r.nwc = t.nwc; r.ns = t.ns; r.slot_magic = 65536 / t.nwc + 1;
     }
     r.n_sr = (int)t.sr.size();
     r.sr = t.sr.data();
@@ -226,28 +227,72 @@ void hs_render_mode(HostSim* s, uint8_t* frames, int mode) {
         memcpy(code.data(), d.grid + (size_t)e * d.CS, d.CS);
         for (int k = 0; k < XW_CODE_SLOTS; ++k) icon[k] = k < XW_CELL_GOAL0 + d.G ? xw_cell_desc(d, e, k) : 0;
         if (s->tab.fast_ok && mode == 1 && s->tab.sp_ok) {
-            // k_render_sp: white pre-fill, list of the non-white cells, every slot of every listed cell
-            std::fill(fb.begin(), fb.end(), 0xffffffffu);
-            XwPaintCtx pg;
-            pg.cellgeo = r.cellgeo; pg.wcol = r.wcol;
-            std::vector<uint8_t> list;
-            for (int cell = 0; cell < d.H * d.W; ++cell) if (code[cell]) list.push_back((uint8_t)cell);
-            const int S = 3 * r.nwc, n_slots = (int)list.size() * S;
-            // slots run concurrently on the device: every word must have one writer, so the order of
-            // the slots cannot matter -- paint forwards and backwards and compare
-            std::vector<uint32_t> fb2(fb);
-            for (int pass = 0; pass < 2; ++pass) {
-                uint32_t* out = pass ? fb2.data() : fb.data();
-                for (int q = 0; q < n_slots; ++q) {
-                    const int sl = pass ? n_slots - 1 - q : q;
-                    int i, p, wc;
-                    xw_paint_decode(r, sl, &i, &p, &wc);
-                    if (i != sl / S || p != (sl % S) / r.nwc || wc != (sl % S) % r.nwc) abort();
-                    if (r.WR == 21 && (e & 1)) xw_paint_slot<21>(r, x, pg, cells, list[i], p, wc, out);
-                    else xw_paint_slot<0>(r, x, pg, cells, list[i], p, wc, out);
+            // k_render_sp: white pre-fill, special slots + straddling-row words (PRE), brick slots (POST)
+            if (s->ctab.empty()) {  // k_build_class_tables
+                s->cornerP.resize((size_t)(r.n_icons + 1) * 4);
+                for (size_t i = 0; i < s->cornerP.size(); ++i) s->cornerP[i] = xw_cornerP_entry(r, (uint32_t)(i / 4), (int)(i % 4));
+                r.cornerP = s->cornerP.data();
+                s->ctab.resize(xw_ctab_words(r) + 64, 0);
+                r.ctab = s->ctab.data();
+                const size_t per = (size_t)xw_ctab_stride(r);
+                for (size_t i = 0; i < xw_ctab_words(r); ++i) {
+                    const int col = (int)(i / per), rem = (int)(i % per), p = rem / r.OH, dy = rem % r.OH;
+                    if (p >= 3 || col >= r.WR + 2 * r.ns) continue;
+                    int variant = 0, k = col;
+                    if (col >= r.WR) {
+                        variant = col - r.WR < r.ns ? 1 : 2;
+                        const int si = col - r.WR - (variant == 2 ? r.ns : 0);
+                        for (k = 0; k < r.WR; ++k) if (r.wshare[k] == si) break;
+                    }
+                    s->ctab[i] = xw_ctab_word(r, r.wcol[k], variant, k, p, dy);
                 }
             }
-            if (memcmp(fb.data(), fb2.data(), r.FB)) abort();
+            std::fill(fb.begin(), fb.end(), 0xffffffffu);
+            std::vector<uint8_t> sr_dy(r.n_sr + 1);
+            for (int q = 0; q < r.n_sr; ++q) sr_dy[q] = (uint8_t)r.sr[q];
+            std::vector<uint32_t> sc_a(r.n_sc + 1);
+            for (int i = 0; i < r.n_sc; ++i) sc_a[i] = (uint32_t)(uint16_t)r.taps.xa0[r.sc[i]] | ((uint32_t)(uint16_t)r.taps.xa1[r.sc[i]] << 16);
+            XwPaintCtx pg;
+            pg.sc_a = sc_a.data();
+            pg.cellgeo = r.cellgeo; pg.wcol = r.wcol; pg.wshare = r.wshare; pg.ctab = r.ctab; pg.sr_ty = r.sr_ty; pg.sr_dy = sr_dy.data();
+            std::vector<uint32_t> written(r.FB / 4, 0);  // every frame word has at most one writer
+            const bool fixed = r.WR == 21 && (e & 1);    // alternate the compile-time and the run-time row stride
+            auto mark = [&](uint32_t w) { if (written[w]++) abort(); };
+            for (int cell = 0; cell < d.H * d.W; ++cell) {
+                if (code[cell] < XW_CELL_AGENT) continue;
+                for (int wc = 0; wc < r.nwc; ++wc) {
+                    for (int p = 0; p < 3; ++p) {
+                        uint32_t m[12], pb[3];
+                        memset(m, 0x5a, sizeof m); memset(pb, 0x5a, sizeof pb);
+                        const bool have = fixed ? xw_sp_special<21, 12, 0>(r, x, pg, cells, cell, wc, p, m, pb, nullptr)
+                                                : xw_sp_special<0, 12, 0>(r, x, pg, cells, cell, wc, p, m, pb, nullptr);
+                        if (!have) continue;
+                        std::vector<uint32_t> before(fb);
+                        const bool have2 = fixed ? xw_sp_special<21, 12, 1>(r, x, pg, cells, cell, wc, p, m, pb, fb.data())
+                                                 : xw_sp_special<0, 12, 1>(r, x, pg, cells, cell, wc, p, m, pb, fb.data());
+                        if (!have2) abort();
+                        for (size_t w = 0; w < (size_t)r.FB / 4; ++w) if (fb[w] != before[w]) mark((uint32_t)w);
+                    }
+                }
+            }
+            for (int idx = 0; idx < r.n_sr * r.WR; ++idx) {
+                uint32_t wa[3], wb[3], tt[4];
+                memset(wa, 0x5a, sizeof wa); memset(wb, 0x5a, sizeof wb); memset(tt, 0x5a, sizeof tt);
+                const int q = idx / r.WR, k = idx % r.WR;
+                if (fixed) { xw_sp_rword<21, 0>(r, x, pg, cells, q, k, wa, wb, tt, nullptr); xw_sp_rword<21, 1>(r, x, pg, cells, q, k, wa, wb, tt, fb.data()); }
+                else { xw_sp_rword<0, 0>(r, x, pg, cells, q, k, wa, wb, tt, nullptr); xw_sp_rword<0, 1>(r, x, pg, cells, q, k, wa, wb, tt, fb.data()); }
+                for (int p = 0; p < 3; ++p) mark(p * r.OH * r.WR + r.sr[q] * r.WR + k);
+            }
+            std::vector<uint8_t> list;
+            for (int cell = 0; cell < d.H * d.W; ++cell) if (code[cell] == XW_CELL_BLOCK) list.push_back((uint8_t)cell);
+            for (int sl = 0; sl < (int)list.size() * r.nwc; ++sl) {
+                int i, wc;
+                xw_sp_decode(r, sl, &i, &wc);
+                if (i != sl / r.nwc || wc != sl % r.nwc) abort();
+                std::vector<uint32_t> before(fb);
+                if (fixed) xw_sp_brick_slot<21, 12>(r, pg, cells, list[i], wc, fb.data()); else xw_sp_brick_slot<0, 12>(r, pg, cells, list[i], wc, fb.data());
+                for (size_t w = 0; w < (size_t)r.FB / 4; ++w) if (fb[w] != before[w]) mark((uint32_t)w);
+            }
             memcpy(frames + (size_t)e * r.FB, fb.data(), r.FB);
         } else if (s->tab.fast_ok && mode != 2) {
             std::fill(fb.begin(), fb.end(), 0x5a5a5a5au);

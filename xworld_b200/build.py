@@ -15,7 +15,7 @@ def build(force=False, verbose=False):
     if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= max(os.path.getmtime(d) for d in deps):
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    cmd = [nvcc] + NVCC_FLAGS + os.environ.get("XW_BUILD_DEFS", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
     subprocess.check_call(cmd)
     return OUT
 

@@ -222,6 +222,9 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
     r.n_sr = (int)t.sr.size();
     r.n_icons = cat->n_icons; r.brick_icon = cat->brick_icon; r.agent_icon = cat->agent_icon;
     { const char* ed = getenv("XW_RENDER_DEBUG"); r.debug = ed ? atoi(ed) : 0; }
+#if defined(XW_SP_PROF)
+    { unsigned int* pp = nullptr; rc |= dalloc(s, &pp, 16); r.prof = pp; }
+#endif
     rc |= dupload(s, &r.taps.xofs, t.xofs.data(), t.xofs.size());
     rc |= dupload(s, &r.taps.xa0, t.xa0.data(), t.xa0.size());
     rc |= dupload(s, &r.taps.xa1, t.xa1.data(), t.xa1.size());
@@ -240,16 +243,16 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
         const char* ec = getenv("XW_RENDER_CONFLICT_FREE");
         const bool cfree = ec ? atoi(ec) != 0 : false;
         // "sb" (default): one frame buffer per group, up to 8 groups; "pipe": two per group, up to 4 groups.
-        // Measured on B200 (profiles/r01_summary.md): sb 8x64 threads is the fastest at 84x84 frames.
+        // Measured on B200 (profiles/r01_summary.md): of the two, sb 8x64 threads is the faster at 84x84 frames.
         const char* em = getenv("XW_RENDER_MODE");
         s->render_sb = !(em && !strcmp(em, "pipe"));
-        // "sp" (opt-in until it beats "sb"): the sparse painter -- white pre-fill + the words of the
+        // "sp" (default when the geometry allows): the sparse painter -- white pre-fill + the words of the
         // non-white cells only; "sb" / "pipe": the dense plan compositors
         xw_build_paint_tables(t);
-        s->render_sp = t.sp_ok && em && !strcmp(em, "sp");
+        s->render_sp = t.sp_ok && !(em && (!strcmp(em, "pipe") || !strcmp(em, "sb")));
         if (s->render_sp) {
-            r.nwc = t.nwc;
-            r.slot_magic = 65536 / (3 * t.nwc) + 1;
+            r.nwc = t.nwc; r.ns = t.ns; r.n_sc = (int)t.sc.size();
+            r.slot_magic = 65536 / t.nwc + 1;
             const char* ef = getenv("XW_RENDER_SP_FILL");
             r.sp_fill = ef ? atoi(ef) : 0;
         }
@@ -259,10 +262,16 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
         bool found = false;
         for (; G >= 1 && !found; --G) {
             // <= 512 threads/CTA keeps 124 registers per thread (no spills, 24-word load batches)
-            int GT = et ? atoi(et) : (G >= 6 ? 64 : (768 / G) / 32 * 32);
+            // (k_render_sp needs its 128 registers: <= 512 threads per CTA)
+            int GT = et ? atoi(et) : (G >= 6 ? 64 : ((s->render_sp ? 512 : 768) / G) / 32 * 32);
             // 9 groups fit at 84x84 but need > 512 threads = fewer registers per thread: measured 30 % slower
             if (!eg && !s->render_sp && s->render_sb && G * GT > 512 && G > 8) continue;
             GT = GT / 32 * 32;
+            if (s->render_sp) {  // one special slot-plane per thread of a group, at least two warps (k_render_sp)
+                const int need = 3 * (1 + c.n_goals) * t.nwc;
+                if (GT < 64) GT = 64;
+                if (GT < need) GT = (need + 31) / 32 * 32;
+            }
             if (GT < 32 || G * GT > XW_RENDER_THREADS) { if (et) break; continue; }
             const char* e2 = getenv("XW_RENDER_TWO_PHASE");
             xw_build_plan(t, GT / 32, split, cfree, !s->render_sb, e2 && atoi(e2) != 0);
@@ -287,7 +296,7 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
         const size_t n_col = (size_t)(cat->n_icons + 1) * 2 * r.n_sc * 3 * c.height * r.RB + 64, n_row = (size_t)(cat->n_icons + 1) * 2 * r.n_sr * 3 * OW + 64;
         const size_t n_cwb = (size_t)16 * r.n_sr * r.n_sc * 3 + 64;
         auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
-        const size_t n_white = s->render_sp ? (size_t)r.FB : 0;
+        const size_t n_white = s->render_sp ? (size_t)r.FB + xw_ctab_words(r) * 4 + (size_t)(cat->n_icons + 1) * 16 : 0;
         const size_t total = up(n_T) + (t.fast_ok ? up(n_ecol) + up(n_uv) + up(n_corner) + 2 * up(n_col) + 2 * up(n_row) + up(n_cwb) + up(n_white) : 0);
         uint8_t* base = nullptr;
         rc |= dalloc(s, &base, total, false);
@@ -301,10 +310,15 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
             r.colL = take(n_col); r.colR = take(n_col); r.rowT = take(n_row); r.rowB = take(n_row); r.cornerWB = take(n_cwb);
             if (s->render_sp) {
                 uint8_t* w = take(n_white);
-                CUDA_TRY(cudaMemset(w, 0xff, n_white));
+                CUDA_TRY(cudaMemset(w, 0xff, (size_t)r.FB));
                 r.white = w;
+                r.ctab = (const uint32_t*)(w + r.FB);  // (FB % 16 == 0)
+                r.cornerP = r.ctab + xw_ctab_words(r);
                 rc |= dupload(s, &r.cellgeo, t.cellgeo.data(), t.cellgeo.size());
                 rc |= dupload(s, &r.wcol, t.wcol.data(), t.wcol.size());
+                rc |= dupload(s, &r.wshare, t.wshare.data(), t.wshare.size());
+                static const uint8_t zero8 = 0;
+                rc |= dupload(s, &r.sr_ty, t.sr_ty.empty() ? &zero8 : t.sr_ty.data(), t.sr_ty.empty() ? 1 : t.sr_ty.size());
             }
             rc |= dupload(s, &r.plan, t.plan.data(), t.plan.size());
             rc |= dupload(s, &r.cellinfo, t.cellinfo.data(), t.cellinfo.size());
@@ -334,15 +348,18 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
         k_build_edge_tables<<<s->n_sms * 2, 256, 0, s->own_stream>>>(r);
         k_build_pair_tables<<<s->n_sms * 4, 256, 0, s->own_stream>>>(r);
         s->launches += 2;
+        if (s->render_sp) { k_build_class_tables<<<s->n_sms * 2, 256, 0, s->own_stream>>>(r); s->launches++; }
     }
     CUDA_TRY(cudaGetLastError());
     if (t.fast_ok) {
-        s->render_smem = s->render_sp ? xw_render_sp_smem(r, r.G).total : xw_render_smem(r, s->render_sb ? r.G : 2 * r.G).total;
+        if (s->render_sp) r.sp = xw_render_sp_smem(r, r.G);
+        s->render_smem = s->render_sp ? r.sp.total : xw_render_smem(r, s->render_sb ? r.G : 2 * r.G).total;
         // instantiations: compile-time row stride for the common frame widths x register budget by CTA size
         const int nt = r.G * r.GT;
 #define XW_PICK(WR_) (nt <= 512 ? k_render<WR_, 512> : nt <= 768 ? k_render<WR_, 768> : k_render<WR_, 1024>)
 #define XW_PICK_SB(WR_) (nt <= 512 ? k_render_sb<WR_, 512> : nt <= 576 ? k_render_sb<WR_, 576> : nt <= 768 ? k_render_sb<WR_, 768> : k_render_sb<WR_, 1024>)
-#define XW_PICK_SP(WR_) (nt <= 512 ? k_render_sp<WR_, 512> : nt <= 768 ? k_render_sp<WR_, 768> : k_render_sp<WR_, 1024>)
+#define XW_PICK_SP(WR_) (t.max_band_rows <= 8 ? (nt <= 512 ? k_render_sp<WR_, 512, 8> : k_render_sp<WR_, 1024, 8>) \
+                                              : (nt <= 512 ? k_render_sp<WR_, 512, 12> : k_render_sp<WR_, 1024, 12>))
         if (s->render_sp) s->render_fn = r.WR == 21 ? XW_PICK_SP(21) : r.WR == 24 ? XW_PICK_SP(24) : r.WR == 32 ? XW_PICK_SP(32) : XW_PICK_SP(0);
         else if (s->render_sb) s->render_fn = r.WR == 21 ? XW_PICK_SB(21) : r.WR == 24 ? XW_PICK_SB(24) : r.WR == 32 ? XW_PICK_SB(32) : XW_PICK_SB(0);
         else s->render_fn = r.WR == 21 ? XW_PICK(21) : r.WR == 24 ? XW_PICK(24) : r.WR == 32 ? XW_PICK(32) : XW_PICK(0);
@@ -420,6 +437,19 @@ int xw_create(const xw_config* cfg, const xw_catalog* catalog, int32_t n_envs, i
 void xw_destroy(xw_sim* s) {
     if (!s) return;
     if (s->own_stream) cudaStreamSynchronize(s->own_stream);
+#if defined(XW_SP_PROF)
+    if (s->cfg.game == XW_GAME_XWORLD && s->r.prof && s->render_sp) {  // phase clocks summed over every render launch of the handle
+        unsigned int h[16];
+        cudaDeviceSynchronize();
+        if (cudaMemcpy(h, s->r.prof, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess) {
+            const double envs = (double)((s->n + s->render_grid * s->r.G - 1) / (s->render_grid * s->r.G)) * (double)(s->launches > 8 ? s->launches - 4 : 1);
+            fprintf(stderr, "XW_SP_PROF cycles/env (~%g envs): lane0 cells %.0f | barrier A %.0f | finish special %.0f | bricks %.0f | issue %.0f | barrier C %.0f | rest %.0f ;"
+                            " lane63 drain %.0f | fill %.0f | barrier A %.0f | finish rword %.0f | bricks %.0f | issue %.0f | barrier C %.0f | rest %.0f\n",
+                    envs, h[1] / envs, h[2] / envs, h[3] / envs, h[4] / envs, h[5] / envs, h[6] / envs, h[7] / envs,
+                    h[8] / envs, h[9] / envs, h[10] / envs, h[11] / envs, h[12] / envs, h[13] / envs, h[14] / envs, h[15] / envs);
+        }
+    }
+#endif
     for (void* p : s->allocs) cudaFree(p);
     if (s->h_act) cudaFreeHost(s->h_act);
     if (s->h_over) cudaFreeHost(s->h_over);

@@ -34,6 +34,10 @@
 
 struct XwTaps { const int16_t *xofs, *xa0, *xa1, *yofs, *ya0, *ya1; };  // cv::resize tables
 
+// shared-memory layout of k_render_sp (byte offsets; filled by the host with xw_render_sp_smem so that the kernel
+// reads them from the constant bank instead of keeping a dozen derived pointers in registers)
+struct XwRenderSpSmem { int ctab, fb, cellgeo, wcol, wshare, srq, sca, yb, pair, cell, bar, total; };
+
 struct XwRender {
     int32_t OH, OW, WR, FB;   // frame rows, cols, words per row, bytes per frame (3*OH*OW)
     int32_t H, W;
@@ -68,9 +72,17 @@ struct XwRender {
     const XwU4* cellgeo;      // [H*W]
     const uint32_t* wcol;     // [WR]
     const uint8_t* white;     // [FB] 0xff: source of the TMA pre-fill
-    int32_t nwc;              // word-column slots per cell; a cell has 3 * nwc slots (plane-major)
-    int32_t slot_magic;       // slot / (3 * nwc) == (slot * slot_magic) >> 16 for slot < 4096
-    int32_t sp_fill;          // 0: pre-fill with vector stores, 1: with a TMA bulk load of `white`
+    const uint8_t* wshare;    // [WR]
+    const uint8_t* sr_ty;     // [n_sr]
+    const uint32_t* ctab;     // class tables (xw_ctab_words), built by k_build_class_tables
+    int32_t ns;               // word columns shared by two cell columns
+    int32_t nwc;              // word-column slots per cell
+    int32_t slot_magic;       // slot / nwc == (slot * slot_magic) >> 16 for slot < 4096
+    const uint32_t* cornerP;  // [n_icons+1][4] corner tap of role (top-left cell's (63,63), top-right's (63,0), bottom-left's
+                              //   (0,63), bottom-right's (0,0)), planes 0..2 in bytes 0..2
+    XwRenderSpSmem sp;        // = xw_render_sp_smem(r, G)
+    unsigned int* prof;       // -DXW_SP_PROF builds only: per-phase clock sums of group 0 of CTA 0 (tools/sweep_render.py)
+    int32_t sp_fill;          // 0: white pre-fill with vector stores (warp 1), 1: with a TMA bulk load of `white`
 };
 
 // ---- exact cv::resize arithmetic --------------------------------------------------------
@@ -156,13 +168,19 @@ XW_HD uint8_t xw_cornerwb_entry(const XwRender& r, int combo, int q, int s, int 
                         xw_canvas_tap(r, xw_cls_desc(r, (combo >> 2) & 1), 0, 63, c), xw_canvas_tap(r, xw_cls_desc(r, (combo >> 3) & 1), 0, 0, c),
                         t.xa0[dx], t.xa1[dx], t.ya0[dy], t.ya1[dy]);
 }
+XW_HD uint32_t xw_cornerP_entry(const XwRender& r, uint32_t dsc, int role) {
+    uint32_t v = 0;
+    for (int c = 0; c < 3; ++c) v |= (uint32_t)xw_canvas_tap(r, dsc, role < 2 ? 63 : 0, (role & 1) ? 0 : 63, c) << (8 * c);
+    return v;
+}
 XW_HD uint32_t xw_corner_entry(const XwRender& r, uint32_t dsc, int c) {
     return (uint32_t)xw_canvas_tap(r, dsc, 63, 63, c) | ((uint32_t)xw_canvas_tap(r, dsc, 63, 0, c) << 8) |
            ((uint32_t)xw_canvas_tap(r, dsc, 0, 63, c) << 16) | ((uint32_t)xw_canvas_tap(r, dsc, 0, 0, c) << 24);
 }
 
 // Value of output pixel (c,dy,dx) on the real canvas, from the 64-px atlas (any four cells).
-XW_HD uint8_t xw_exact_px(const XwRender& r, const XwCells& celldesc, int c, int dy, int dx) {
+template <class CellDesc>
+XW_HD uint8_t xw_exact_px(const XwRender& r, const CellDesc& celldesc, int c, int dy, int dx) {
     const XwTaps& t = r.taps;
     int sx0 = t.xofs[dx], sy0 = t.yofs[dy];
     int a1 = t.xa1[dx], b1 = t.ya1[dy];
@@ -500,155 +518,273 @@ XW_HD XwRenderSmem xw_render_smem(const XwRender& r, int nbuf) {
 
 
 // ---- sparse painter (k_render_sp) -----------------------------------------------------------------
-// The frame buffer is pre-filled with white; every non-white cell then paints the words it owns (rule in
-// xw_render_host.hpp: xw_build_paint_tables).  One slot = (cell, plane, word column of the cell): the
-// rows of the cell's band, plus the word of the straddling row below it, plus the one above it when the
-// cells above are white.  Same table arithmetic as the plan items above (pair tables, exact fallbacks),
-// but sources are read in place: brick / white from the shared-memory brick table, agent and goal words
-// straight from the L2-resident phase atlas.
-struct XwPaintCtx { const XwU4* cellgeo; const uint32_t* wcol; };  // shared-memory copies on the device
-
-XW_HD const uint32_t* xw_src_direct(const XwRender& r, const XwComposeCtx& x, uint32_t dsc) {
-    return (const uint32_t*)(xw_special(r, dsc) ? r.T + (size_t)(dsc - 1) * r.FB : x.hot);
+// The frame buffer is pre-filled with white; only the words a non-white cell touches are then written.
+// Three kinds of work, each with its own uniform code path (geometry: xw_build_paint_tables):
+//   brick slots    (brick cell, word column of the cell): the rows of the cell's band in the three planes.
+//                  A word touches at most two cell columns lo | hi, so with only bricks and white around
+//                  there are three cases -- brick|brick (or a word inside one cell), brick|white,
+//                  white|brick -- and each has a precomputed, exact (straddling byte included) class
+//                  table in shared memory, stored column-major so that the rows of a word column are
+//                  consecutive words: one LDS + one STS per frame word, no merging.
+//   special slots  (agent / goal cell, word column): the general two-source merge (PRMT) with the
+//                  straddling byte from the pair tables or the edge taps; the cell's own words come from
+//                  the L2-resident phase atlas.  Computed into registers while the previous frame of
+//                  the group drains, stored after the pre-fill.
+//   straddling-row words: every word of every straddling row (dense, they are few), from the row pair
+//                  tables; likewise precomputed into registers.
+// Ownership: a word that touches a special cell belongs to that cell's slot (the left one if both are
+// special); otherwise to the brick on its left, else to the brick on its right.
+#define XW_SP_ROWS_MAX 12  // most rows of a band without its straddling row; a special slot keeps 3 x ROWS words in
+                           // registers, ROWS = 8 or 12 (template parameter)
+#define XW_SP_RR 2     // straddling-row words a lane of warp 0 precomputes per env; the rest are written in place
+struct XwPaintCtx {    // shared-memory copies on the device
+    const XwU4* cellgeo;
+    const uint32_t* wcol;
+    const uint8_t* wshare;
+    const uint32_t* ctab;   // class tables, column-major: full [WR][3][OH] | brick|white [ns][3][OH] | white|brick [ns][3][OH]
+    const uint8_t* sr_ty;   // [n_sr] cell row above straddling row q
+    const uint8_t* sr_dy;   // [n_sr] its output row
+    const uint32_t* sc_a;   // [n_sc] horizontal weights xa0 | xa1 << 16 of straddling column s
+};
+// words per class-table column: 3 planes x OH rows, made odd so that the columns of one band (same rows, different
+// word columns) sit on different shared-memory banks
+XW_HD int xw_ctab_stride(const XwRender& r) { return (3 * r.OH) | 1; }
+XW_HD size_t xw_ctab_words(const XwRender& r) {  // (a multiple of 4: the tables are one TMA bulk load)
+    return ((size_t)(r.WR + 2 * r.ns) * xw_ctab_stride(r) + 3) & ~(size_t)3;
 }
 
-// word k of straddling row q = output row dy, between cell rows ty and ty + 1, plane p
-template <int WR_T>
-XW_HD void xw_paint_rword(const XwRender& r, const XwComposeCtx& x, const XwCells& cells, uint32_t wk, int k, int ty, int q, int dy,
-                          int p, uint32_t* fb) {
+// cells of a class-table entry: cell column `lo` and the other one hold a brick or nothing
+struct XwClassCells {
+    int W, lo;
+    uint32_t dlo, dhi;
+    XW_HD uint32_t operator()(int cell) const { return cell % W == lo ? dlo : dhi; }
+};
+// word (k, p, dy) of class table `variant` (0 brick|brick, 1 brick|white, 2 white|brick); only the rows
+// whose taps stay inside one cell row are used
+XW_HD uint32_t xw_ctab_word(const XwRender& r, uint32_t wk, int variant, int k, int p, int dy) {
+    XwClassCells cc;
+    cc.W = r.W; cc.lo = (int)(wk & 15);
+    cc.dlo = variant == 2 ? 0u : (uint32_t)r.brick_icon + 1;
+    cc.dhi = variant == 1 ? 0u : (uint32_t)r.brick_icon + 1;
+    uint32_t w = 0;
+    for (int i = 0; i < 4; ++i) w |= (uint32_t)xw_exact_px(r, cc, p, dy, 4 * k + i) << (8 * i);
+    return w;
+}
+
+// The three planes of word k of straddling row q, in two steps like the special slots:
+//   MODE 0 (issue):  the two row-pair-table words per plane -> wa, wb and, for a corner next to a special cell,
+//                    the corner taps -> t; loads only (from L2 when a special cell is involved), no use;
+//   MODE 1 (finish): merge, insert the corner byte, store.  (Special above special: everything here, exactly.)
+template <int WR_T, int MODE>
+XW_HD void xw_sp_rword(const XwRender& r, const XwComposeCtx& x, const XwPaintCtx& g, const XwCells& cells, int q, int k,
+                       uint32_t wa[3], uint32_t wb[3], uint32_t t[4], uint32_t* fb) {
     const int WR = WR_T ? WR_T : r.WR;
+    const uint32_t wk = g.wcol[k];
     const int lo = wk & 15, hi = (wk >> 4) & 15;
     const uint32_t sel = (wk >> 8) & 0xffffu;
-    const int top = ty * r.W;
-    const uint32_t dTa = cells(top + lo), dBa = cells(top + r.W + lo), dTb = cells(top + hi), dBb = cells(top + r.W + hi);
-    const int cTa = xw_cls(r, dTa), cBa = xw_cls(r, dBa), cTb = xw_cls(r, dTb), cBb = xw_cls(r, dBb);
-    uint32_t word;
-    if ((cTa == 2 && cBa == 2) || (cTb == 2 && cBb == 2)) {
+    const int top = g.sr_ty[q] * r.W;
+    const int kTa = cells.code[top + lo], kBa = cells.code[top + r.W + lo], kTb = cells.code[top + hi], kBb = cells.code[top + r.W + hi];
+    const int cTa = kTa < 2 ? kTa : 2, cBa = kBa < 2 ? kBa : 2, cTb = kTb < 2 ? kTb : 2, cBb = kBb < 2 ? kBb : 2;  // = xw_cls
+    const bool exact = (cTa == 2 && cBa == 2) || (cTb == 2 && cBb == 2);
+    const bool corner = ((wk >> 24) & 1) != 0, wb_corner = (cTa | cTb | cBa | cBb) < 2;
+    const int sh = (int)((wk >> 25) & 3) * 8, sidx = (int)(wk >> 27);
+    if (MODE == 0) {
+        if (exact) return;
+        // per cell column: (top cell, class of the bottom cell) or (bottom cell, class of the top cell)
+        const size_t rs = xw_rowpair_stride(r);
+        const uint8_t *tA, *tB;
+        if (cBa < 2) tA = (cTa < 2 ? x.rowT_hot + (size_t)cTa * 2 * rs : r.rowT + (size_t)cells.icon[kTa] * 2 * rs) + (size_t)cBa * rs;
+        else tA = r.rowB + (size_t)cells.icon[kBa] * 2 * rs + (size_t)cTa * rs;
+        if (cBb < 2) tB = (cTb < 2 ? x.rowT_hot + (size_t)cTb * 2 * rs : r.rowT + (size_t)cells.icon[kTb] * 2 * rs) + (size_t)cBb * rs;
+        else tB = r.rowB + (size_t)cells.icon[kBb] * 2 * rs + (size_t)cTb * rs;
+        const size_t off = (size_t)q * 3 * r.OW + 4 * k;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) { wa[p] = *(const uint32_t*)(tA + off + p * r.OW); wb[p] = *(const uint32_t*)(tB + off + p * r.OW); }
+        if (corner && !wb_corner) {
+            // taps (63,63) of the top-left cell, (63,0) top-right, (0,63) bottom-left, (0,0) bottom-right
+            t[0] = r.cornerP[cells.icon[kTa] * 4 + 0]; t[1] = r.cornerP[cells.icon[kTb] * 4 + 1];
+            t[2] = r.cornerP[cells.icon[kBa] * 4 + 2]; t[3] = r.cornerP[cells.icon[kBb] * 4 + 3];
+        }
+        return;
+    }
+    uint32_t out[3];
+    if (exact) {
         // a special cell above a special cell: separable rule (U(top) + V(bottom) + 2) >> 2 on packed u16 pairs
         const size_t per_desc = (size_t)r.n_sr * 2 * 3 * r.OW;
-        const uint16_t* u0 = r.uv + ((size_t)q * 2 * 3 + p) * r.OW + 4 * k;
-        const uint16_t* v0 = u0 + (size_t)3 * r.OW;
-        const XwU2 uA = *(const XwU2*)(u0 + dTa * per_desc), uB = *(const XwU2*)(u0 + dTb * per_desc);
-        const XwU2 vA = *(const XwU2*)(v0 + dBa * per_desc), vB = *(const XwU2*)(v0 + dBb * per_desc);
-        const uint32_t a_lo = ((uA.x + vA.x + 0x00020002u) >> 2) & 0x00ff00ffu, a_hi = ((uA.y + vA.y + 0x00020002u) >> 2) & 0x00ff00ffu;
-        const uint32_t b_lo = ((uB.x + vB.x + 0x00020002u) >> 2) & 0x00ff00ffu, b_hi = ((uB.y + vB.y + 0x00020002u) >> 2) & 0x00ff00ffu;
-        word = xw_prmt(xw_prmt(a_lo, a_hi, 0x6420), xw_prmt(b_lo, b_hi, 0x6420), sel);
+        const uint32_t dTa = cells.icon[kTa], dBa = cells.icon[kBa], dTb = cells.icon[kTb], dBb = cells.icon[kBb];
+        for (int p = 0; p < 3; ++p) {
+            const uint16_t* u0 = r.uv + ((size_t)q * 2 * 3 + p) * r.OW + 4 * k;
+            const uint16_t* v0 = u0 + (size_t)3 * r.OW;
+            const XwU2 uA = *(const XwU2*)(u0 + dTa * per_desc), uB = *(const XwU2*)(u0 + dTb * per_desc);
+            const XwU2 vA = *(const XwU2*)(v0 + dBa * per_desc), vB = *(const XwU2*)(v0 + dBb * per_desc);
+            const uint32_t a_lo = ((uA.x + vA.x + 0x00020002u) >> 2) & 0x00ff00ffu, a_hi = ((uA.y + vA.y + 0x00020002u) >> 2) & 0x00ff00ffu;
+            const uint32_t b_lo = ((uB.x + vB.x + 0x00020002u) >> 2) & 0x00ff00ffu, b_hi = ((uB.y + vB.y + 0x00020002u) >> 2) & 0x00ff00ffu;
+            out[p] = xw_prmt(xw_prmt(a_lo, a_hi, 0x6420), xw_prmt(b_lo, b_hi, 0x6420), sel);
+            if (corner) out[p] = (out[p] & ~(0xffu << sh)) | ((uint32_t)xw_corner_px(r, x, cells, top + lo, p, g.sr_dy[q], r.sc[sidx]) << sh);
+        }
     } else {
-        const size_t rs = xw_rowpair_stride(r);
-        const uint8_t *tA = x.rowT_hot, *tB = x.rowT_hot;
-        if (cBa < 2) tA = (cTa < 2 ? x.rowT_hot + (size_t)cTa * 2 * rs : r.rowT + (size_t)dTa * 2 * rs) + (size_t)cBa * rs;
-        else tA = r.rowB + (size_t)dBa * 2 * rs + (size_t)cTa * rs;
-        if (cBb < 2) tB = (cTb < 2 ? x.rowT_hot + (size_t)cTb * 2 * rs : r.rowT + (size_t)dTb * 2 * rs) + (size_t)cBb * rs;
-        else tB = r.rowB + (size_t)dBb * 2 * rs + (size_t)cTb * rs;
-        const size_t off = (size_t)(q * 3 + p) * r.OW + 4 * k;
-        word = xw_prmt(*(const uint32_t*)(tA + off), *(const uint32_t*)(tB + off), sel);
+#pragma unroll
+        for (int p = 0; p < 3; ++p) out[p] = xw_prmt(wa[p], wb[p], sel);
+        if (corner) {  // corner byte: four cells
+            uint32_t v[3];
+            if (wb_corner) {
+#pragma unroll
+                for (int p = 0; p < 3; ++p) v[p] = x.cornerWB[(((cTa | (cTb << 1) | (cBa << 2) | (cBb << 3)) * r.n_sr + q) * r.n_sc + sidx) * 3 + p];
+            } else {
+                const uint32_t a = g.sc_a[sidx], b = x.yb[g.sr_dy[q]];
+#pragma unroll
+                for (int p = 0; p < 3; ++p)
+                    v[p] = xw_resize_px((t[0] >> (8 * p)) & 255, (t[1] >> (8 * p)) & 255, (t[2] >> (8 * p)) & 255, (t[3] >> (8 * p)) & 255, a & 0xffff, a >> 16,
+                                        b & 0xffff, b >> 16);
+            }
+#pragma unroll
+            for (int p = 0; p < 3; ++p) out[p] = (out[p] & ~(0xffu << sh)) | (v[p] << sh);
+        }
     }
-    if ((wk >> 24) & 1) {  // corner byte: four cells
-        const int sh = (int)((wk >> 25) & 3) * 8, sidx = (int)(wk >> 27);
-        uint32_t v;
-        if ((cTa | cTb | cBa | cBb) < 2) v = x.cornerWB[(((cTa | (cTb << 1) | (cBa << 2) | (cBb << 3)) * r.n_sr + q) * r.n_sc + sidx) * 3 + p];
-        else v = xw_corner_px(r, x, cells, top + lo, p, dy, r.sc[sidx]);
-        word = (word & ~(0xffu << sh)) | (v << sh);
-    }
-    fb[p * (r.OH * WR) + dy * WR + k] = word;
+    uint32_t* dst = fb + g.sr_dy[q] * WR + k;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) dst[p * r.OH * WR] = out[p];
 }
 
-template <int WR_T>
-XW_HD void xw_paint_slot(const XwRender& r, const XwComposeCtx& x, const XwPaintCtx& g, const XwCells& cells, int cell, int p, int wc,
-                         uint32_t* fb) {
+// Word column wc of special cell `cell` in plane p, in two steps so that the L2 latency of the first is never waited for:
+//   MODE 0 (issue):  the cell's own phase-table words of the band rows -> m[j], the straddling byte (if any) of
+//                    four rows per word -> pb[j / 4]; loads only, no use;
+//   MODE 1 (finish): merge with the other cell column of the word (PRMT), insert the straddling byte, store
+//                    to the frame buffer.  Recomputes the (shared-memory) geometry instead of carrying it.
+// False: nothing to do (the cell has fewer word columns, or the word belongs to the special cell on its left).
+template <int WR_T, int XW_SP_ROWS, int MODE>
+XW_HD bool xw_sp_special(const XwRender& r, const XwComposeCtx& x, const XwPaintCtx& g, const XwCells& cells, int cell, int wc, int p,
+                         uint32_t m[XW_SP_ROWS], uint32_t pb[XW_SP_ROWS / 4], uint32_t* fb) {
     const int WR = WR_T ? WR_T : r.WR;
     const XwU4 cg = g.cellgeo[cell];
-    if (wc >= (int)((cg.x >> 24) & 7)) return;
+    if (wc >= (int)((cg.x >> 24) & 7)) return false;
     const int k = (int)(cg.y & 0xff) + wc, ty = (int)((cg.y >> 8) & 0xff);
     const uint32_t wk = g.wcol[k];
     const int lo = wk & 15, hi = (wk >> 4) & 15;
     const int row = cell - (int)((cg.z >> 8) & 0xff);  // ty * W
-    const uint32_t dA = cells(row + lo), dB = cells(row + hi);
-    if (row + lo != cell && dA != 0) return;  // the non-white left neighbour owns this word
-    const uint32_t sel = (wk >> 8) & 0xffffu;
+    const int kA = cells.code[row + lo], kB = cells.code[row + hi];
+    if (row + lo != cell && kA >= XW_CELL_AGENT) return false;
+    const uint32_t dA = cells.icon[kA], dB = cells.icon[kB];
     const int nrows = (int)((cg.x >> 16) & 0xff), y0 = (int)(cg.z & 0xff);
-    const uint32_t w0 = (cg.x & 0xffffu) + (uint32_t)wc + (uint32_t)(p * r.OH * WR);
-    const uint32_t* pA = xw_src_direct(r, x, dA) + w0;
-    const uint32_t* pB = xw_src_direct(r, x, dB) + w0;
-    const uint32_t wmask = xw_prmt(dA == 0 ? 0xffffffffu : 0u, dB == 0 ? 0xffffffffu : 0u, sel);
-    uint32_t* dst = fb + w0;
-    if (!((wk >> 24) & 1)) {
-        // all loads of a batch before its stores (the frame buffer and the tables may alias as far as the
-        // compiler knows); rows past the band are loaded (the tables are padded) and not stored
-        {
-            uint32_t va[8], vb[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { va[j] = pA[j * WR]; vb[j] = pB[j * WR]; }
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (j < nrows) dst[j * WR] = xw_prmt(va[j], vb[j], sel) | wmask;
+    const int PW = r.OH * WR;
+    const bool meA = row + lo == cell;
+    const bool has_sc = ((wk >> 24) & 1) != 0;
+    const int sh = (int)((wk >> 25) & 3) * 8, sidx = (int)(wk >> 27);
+    const int cL = kA < 2 ? kA : 2, cR = kB < 2 ? kB : 2;
+    const bool exact = has_sc && cL == 2 && cR == 2;
+    if (MODE == 0) {
+        // this cell's own phase table (row-major, L2); the straddling byte from the pair table of the special
+        // cell and the class of the other one (special | special: exact, in the finish step)
+        const uint32_t dM = meA ? dA : dB;
+        const uint32_t* pM = (const uint32_t*)(r.T + (size_t)(dM - 1) * r.FB) + p * PW + y0 * WR + k;
+        const uint8_t* tab = (const uint8_t*)g.ctab;  // (no straddling byte: any readable address)
+        if (has_sc && !exact) {
+            const size_t cs = xw_colpair_stride(r);
+            tab = (cR < 2 ? r.colL + ((size_t)dA * 2 + cR) * cs : r.colR + ((size_t)dB * 2 + cL) * cs) + ((size_t)(sidx * 3 + p) * r.H + ty) * r.RB;
         }
-        for (int i0 = 8; i0 < nrows; i0 += 4) {
-            uint32_t va[4], vb[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { va[j] = pA[(i0 + j) * WR]; vb[j] = pB[(i0 + j) * WR]; }
+        for (int j = 0; j < XW_SP_ROWS; ++j)
+            if (j < nrows) m[j] = pM[j * WR];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (i0 + j < nrows) dst[(i0 + j) * WR] = xw_prmt(va[j], vb[j], sel) | wmask;
+        for (int j4 = 0; j4 < XW_SP_ROWS; j4 += 4)
+            if (j4 < nrows) pb[j4 / 4] = *(const uint32_t*)(tab + j4);
+        return true;
+    }
+    // the other cell column of the word: the brick class table (column-major, shared memory; white = brick |
+    // 0xffffffff) unless it is special too
+    const bool spO = lo != hi && (meA ? kB : kA) >= XW_CELL_AGENT;
+    const uint32_t dO = meA ? dB : dA;
+    const uint32_t sel = ((wk >> 8) & 0xffffu) ^ (meA ? 0u : 0x4444u);  // PRMT(mine, other)
+    const uint32_t* pO = spO ? (const uint32_t*)(r.T + (size_t)(dO - 1) * r.FB) + p * PW + y0 * WR + k
+                             : g.ctab + (size_t)k * xw_ctab_stride(r) + p * r.OH + y0;
+    const int rsO = spO ? WR : 1;
+    const uint32_t wmask = xw_prmt(0u, dO == 0 ? 0xffffffffu : 0u, sel);
+    const uint32_t keep = has_sc ? ~(0xffu << sh) : 0xffffffffu;
+    const int bsh = has_sc ? sh : 0;
+    uint32_t* dst = fb + p * PW + y0 * WR + k;
+    uint32_t o[XW_SP_ROWS];
+#pragma unroll
+    for (int j = 0; j < XW_SP_ROWS; ++j)
+        if (j < nrows) o[j] = pO[j * rsO];
+#pragma unroll
+    for (int j = 0; j < XW_SP_ROWS; ++j)
+        if (j < nrows) {
+            const uint32_t byte = has_sc ? (pb[j / 4] >> (8 * (j & 3))) & 0xffu : 0u;
+            dst[j * WR] = ((xw_prmt(m[j], o[j], sel) | wmask) & keep) | (byte << bsh);
         }
-    } else {
-        // one byte of the word lies on a straddling column: it comes from a pair table -- (left cell, class
-        // of the right cell) or (right cell, class of the left cell); both special -> exact, from the edge taps
-        const int sh = (int)((wk >> 25) & 3) * 8, sidx = (int)(wk >> 27);
-        const int cL = xw_cls(r, dA), cR = xw_cls(r, dB);
-        const size_t cs = xw_colpair_stride(r);
-        const uint8_t* tab = x.colL_hot;
-        if (cR < 2) tab = (cL < 2 ? x.colL_hot + (size_t)cL * 2 * cs : r.colL + (size_t)dA * 2 * cs) + (size_t)cR * cs;
-        else if (cL < 2) tab = r.colR + (size_t)dB * 2 * cs + (size_t)cL * cs;
-        tab += ((size_t)(sidx * 3 + p) * r.H + ty) * r.RB;
-        const uint32_t keep = ~(0xffu << sh);
-        for (int i0 = 0; i0 < nrows; i0 += 4) {
-            const uint32_t pb = *(const uint32_t*)(tab + i0);  // the straddling byte of four rows
-            uint32_t va[4], vb[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { va[j] = pA[(i0 + j) * WR]; vb[j] = pB[(i0 + j) * WR]; }
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (i0 + j < nrows) dst[(i0 + j) * WR] = ((xw_prmt(va[j], vb[j], sel) | wmask) & keep) | (((pb >> (8 * j)) & 0xffu) << sh);
-        }
-        if (cL == 2 && cR == 2) {
-            const uint16_t* eL = r.ecol + ((((size_t)dA * 2 + 0) * 3 + p) * r.H + ty) * r.RB;
-            const uint16_t* eR = r.ecol + ((((size_t)dB * 2 + 1) * 3 + p) * r.H + ty) * r.RB;
-            const int dx = r.sc[sidx], a0 = r.taps.xa0[dx], a1 = r.taps.xa1[dx];
-            for (int j = 0; j < nrows; ++j) {
-                const uint32_t tl = eL[j], tr = eR[j], b = x.yb[y0 + j];
-                const uint32_t v = xw_resize_px(tl & 255, tr & 255, tl >> 8, tr >> 8, a0, a1, b & 0xffff, b >> 16);
-                dst[j * WR] = (dst[j * WR] & keep) | (v << sh);
-            }
+    if (exact) {  // special | special across the straddling column: from the edge taps
+        const int dx = r.sc[sidx], a0 = r.taps.xa0[dx], a1 = r.taps.xa1[dx];
+        const uint16_t* eL = r.ecol + ((((size_t)dA * 2 + 0) * 3 + p) * r.H + ty) * r.RB;
+        const uint16_t* eR = r.ecol + ((((size_t)dB * 2 + 1) * 3 + p) * r.H + ty) * r.RB;
+        for (int j = 0; j < nrows; ++j) {
+            const uint32_t tl = eL[j], tr = eR[j], b = x.yb[y0 + j];
+            const uint32_t v = xw_resize_px(tl & 255, tr & 255, tl >> 8, tr >> 8, a0, a1, b & 0xffff, b >> 16);
+            dst[j * WR] = (dst[j * WR] & ~(0xffu << sh)) | (v << sh);
         }
     }
-    const int qb = (int)((cg.y >> 16) & 0xff), qa = (int)(cg.y >> 24);
-    if (r.debug & 16) return;
-    if (qb != 0xff) xw_paint_rword<WR_T>(r, x, cells, wk, k, ty, qb, y0 + nrows, p, fb);
-    if (qa != 0xff && cells.code[row - r.W + lo] == 0 && cells.code[row - r.W + hi] == 0)
-        xw_paint_rword<WR_T>(r, x, cells, wk, k, ty - 1, qa, y0 - 1, p, fb);
+    return true;
 }
 
-// slot s of the cell list -> (list index, plane, word column)
-XW_HD void xw_paint_decode(const XwRender& r, int s, int* i, int* p, int* wc) {
-    *i = (int)(((uint32_t)s * (uint32_t)r.slot_magic) >> 16);
-    const int j = s - *i * 3 * r.nwc;
-    *p = (j >= r.nwc) + (j >= 2 * r.nwc);
-    *wc = j - *p * r.nwc;
+// Word column wc of brick cell `cell`: one class-table column per plane, copied to the frame.
+template <int WR_T, int XW_SP_ROWS>
+XW_HD void xw_sp_brick_slot(const XwRender& r, const XwPaintCtx& g, const XwCells& cells, int cell, int wc, uint32_t* fb) {
+    const int WR = WR_T ? WR_T : r.WR;
+    const XwU4 cg = g.cellgeo[cell];
+    if (wc >= (int)((cg.x >> 24) & 7)) return;
+    const int k = (int)(cg.y & 0xff) + wc;
+    const uint32_t wk = g.wcol[k];
+    const int lo = wk & 15, hi = (wk >> 4) & 15;
+    int col = k;  // class-table column: brick | brick
+    if (lo != hi) {
+        const int row = cell - (int)((cg.z >> 8) & 0xff);
+        const bool left = row + lo == cell;
+        const int ko = cells.code[row + (left ? hi : lo)];  // the other cell of the word
+        if (ko >= XW_CELL_AGENT || (!left && ko == XW_CELL_BLOCK)) return;  // a special cell's, or the left brick's word
+        if (ko == XW_CELL_EMPTY) col = r.WR + (left ? 0 : r.ns) + g.wshare[k];
+    }
+    const int nrows = (int)((cg.x >> 16) & 0xff), y0 = (int)(cg.z & 0xff);
+    const uint32_t* src = g.ctab + (size_t)col * xw_ctab_stride(r) + y0;
+    uint32_t* dst = fb + y0 * WR + k;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        // (rows past the band are loaded -- the tables are followed by other shared memory -- and not stored)
+        uint32_t v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = src[p * r.OH + j];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < nrows) dst[p * r.OH * WR + j * WR] = v[j];
+        if (XW_SP_ROWS > 8 && nrows > 8) {
+            uint32_t u[XW_SP_ROWS > 8 ? XW_SP_ROWS - 8 : 1];
+#pragma unroll
+            for (int j = 8; j < XW_SP_ROWS; ++j) u[j - 8] = src[p * r.OH + j];
+#pragma unroll
+            for (int j = 8; j < XW_SP_ROWS; ++j)
+                if (j < nrows) dst[p * r.OH * WR + j * WR] = u[j - 8];
+        }
+    }
 }
-#define XW_SP_LIST_BYTES (XW_MAX_DIM * XW_MAX_DIM + 16)   // non-white cell list + its length (u32 at the end)
-struct XwRenderSpSmem { int hot, fb, cellgeo, wcol, yb, pair, cell, bar, total; };
+// brick slot s -> (list index, word column); exact for s < 4096 (xw_build_paint_tables: nwc <= 4)
+XW_HD void xw_sp_decode(const XwRender& r, int s, int* i, int* wc) {
+    *i = (int)(((uint32_t)s * (uint32_t)r.slot_magic) >> 16);
+    *wc = s - *i * r.nwc;
+}
+
+#define XW_SP_LIST_BYTES (XW_MAX_DIM * XW_MAX_DIM + 16)   // brick cell list + its length (u32 at the end)
 XW_HD XwRenderSpSmem xw_render_sp_smem(const XwRender& r, int G) {
     XwRenderSpSmem s;
     int o = 0;
-    s.hot = o; o += xw_align16(r.FB);
+    s.ctab = o; o += xw_align16((int)xw_ctab_words(r) * 4);
     s.fb = o; o += G * xw_align16(r.FB);
     s.cellgeo = o; o += r.H * r.W * 16;
     s.wcol = o; o += xw_align16(r.WR * 4);
+    s.wshare = o; o += xw_align16(r.WR);
+    s.srq = o; o += xw_align16(2 * (r.n_sr + 1));
+    s.sca = o; o += xw_align16(4 * (r.n_sc + 1));
     s.yb = o; o += xw_align16(r.OH * 4);
-    s.pair = o; o += xw_align16(xw_pair_hot_bytes(r));
-    s.cell = o; o += G * (XW_CELLBUF_BYTES + XW_SP_LIST_BYTES);
-    s.bar = o; o += 16 + 8 * G;
+    s.pair = o; o += xw_align16((int)(4 * xw_rowpair_stride(r)) + 16 * r.n_sr * r.n_sc * 3);
+    s.cell = o; o += 2 * G * (XW_CELLBUF_BYTES + XW_SP_LIST_BYTES);
+    s.bar = o; o += 16 + 16 * G;
     s.total = o;
     return s;
 }
@@ -722,6 +858,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
@@ -1023,149 +1162,262 @@ k_render_sb(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride
 }
 
 
-// Sparse painter (the default): r.G warp groups, one frame buffer each.  Per env a group
-//   (warp 0) stores the env's cell codes, lists its non-white cells (ballot-free warp scan), waits until
-//            the TMA store of the group's previous frame has drained the buffer;
-//   pre-fills the buffer with white -- vector stores by every thread, or one TMA bulk load (r.sp_fill);
-//   paints the slots of the listed cells (xw_paint_slot): ~30 % of the words of a maze frame;
-//   hands the frame to the TMA engine (one bulk store, evict-first in L2).
-template <int WR_T, int NT_MAX>
+__global__ void k_build_class_tables(XwRender r) {
+    const size_t per = (size_t)xw_ctab_stride(r), total = xw_ctab_words(r);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)(r.n_icons + 1) * 4; i += (size_t)gridDim.x * blockDim.x)
+        ((uint32_t*)r.cornerP)[i] = xw_cornerP_entry(r, (uint32_t)(i / 4), (int)(i % 4));
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int col = (int)(i / per), rem = (int)(i % per), p = rem / r.OH, dy = rem % r.OH;
+        if (p >= 3 || col >= r.WR + 2 * r.ns) { ((uint32_t*)r.ctab)[i] = 0; continue; }  // pad words
+        int variant = 0, k = col;
+        if (col >= r.WR) {  // brick|white then white|brick, shared word columns only
+            variant = col - r.WR < r.ns ? 1 : 2;
+            const int si = col - r.WR - (variant == 2 ? r.ns : 0);
+            for (k = 0; k < r.WR; ++k) if (r.wshare[k] == si) break;
+        }
+        ((uint32_t*)r.ctab)[i] = xw_ctab_word(r, r.wcol[k], variant, k, p, dy);
+    }
+}
+
+// Sparse painter: r.G warp groups of >= 2 warps, one frame buffer each.  Per env, in a group:
+//   warp 0    stores the env's cell codes, lists its brick cells, signals warp 1 (mbarrier), prefetches the next
+//             env's cells and computes the special slots into registers;
+//   warp 1    computes the straddling-row words into registers; then its last lane -- the thread that issued
+//             the group's previous TMA store -- waits until that store has read the frame buffer, and the
+//             buffer is made white again (vector stores by warp 1, or one TMA bulk load: r.sp_fill).
+//             All L2 latency of an env is in these two PRE phases, which run side by side and overlap the
+//             drain of the previous frame;
+//   everybody then stores the precomputed words and paints the brick slots (POST: shared memory only), and
+//   the TMA thread hands the frame to the TMA engine (one bulk store, evict-first in L2).
+template <int WR_T, int NT_MAX, int XW_SP_ROWS>
 __global__ void __launch_bounds__(NT_MAX, 1)
 k_render_sp(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int G = r.G, GT = r.GT;
-    const XwRenderSpSmem L = xw_render_sp_smem(r, G);
-    uint8_t* hot = smem + L.hot;
+    const XwRenderSpSmem& L = r.sp;
     uint32_t* s_yb = (uint32_t*)(smem + L.yb);
     uint64_t* bar = (uint64_t*)(smem + L.bar);
     const int tid = threadIdx.x, nt = blockDim.x;
 
     if (tid == 0) {
         mbar_init(bar, 1);
-        for (int i = 0; i < G; ++i) mbar_init(bar + 2 + i, 1);
+        for (int i = 0; i < 2 * G; ++i) mbar_init(bar + 2 + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tid == 0) {  // stage the brick table: one TMA bulk load per CTA
-        mbar_expect_tx(bar, (uint32_t)r.FB);
-        tma_load_1d(hot, r.T + (size_t)r.brick_icon * r.FB, (uint32_t)r.FB, bar);
+    const uint32_t ctab_bytes = (uint32_t)xw_ctab_words(r) * 4;
+    if (tid == 0) {  // the class tables: one TMA bulk load per CTA
+        mbar_expect_tx(bar, ctab_bytes);
+        tma_load_1d(smem + L.ctab, r.ctab, ctab_bytes, bar);
     }
-    {  // geometry + row weights + pair-table heads -> shared memory
+    {  // geometry, row weights, row pair tables of white / brick -> shared memory
         for (int i = tid; i < r.H * r.W; i += nt) ((XwU4*)(smem + L.cellgeo))[i] = r.cellgeo[i];
-        for (int i = tid; i < r.WR; i += nt) ((uint32_t*)(smem + L.wcol))[i] = r.wcol[i];
+        for (int i = tid; i < r.WR; i += nt) { ((uint32_t*)(smem + L.wcol))[i] = r.wcol[i]; (smem + L.wshare)[i] = r.wshare[i]; }
+        for (int i = tid; i < r.n_sr; i += nt) { (smem + L.srq)[i] = r.sr_ty[i]; (smem + L.srq)[r.n_sr + i] = (uint8_t)r.sr[i]; }
+        for (int i = tid; i < r.n_sc; i += nt) ((uint32_t*)(smem + L.sca))[i] = (uint32_t)(uint16_t)r.taps.xa0[r.sc[i]] | ((uint32_t)(uint16_t)r.taps.xa1[r.sc[i]] << 16);
         for (int i = tid; i < r.OH; i += nt) s_yb[i] = (uint32_t)(uint16_t)r.taps.ya0[i] | ((uint32_t)(uint16_t)r.taps.ya1[i] << 16);
-        const int cs2 = (int)(2 * xw_colpair_stride(r)), rs2 = (int)(2 * xw_rowpair_stride(r));
-        uint8_t* pc = smem + L.pair;
-        uint8_t* pr = pc + 2 * cs2;
-        for (int i = tid; i < 2 * cs2; i += nt) pc[i] = r.colL[(size_t)(i < cs2 ? 0 : r.brick_icon + 1) * cs2 + (i < cs2 ? i : i - cs2)];
+        const int rs2 = (int)(2 * xw_rowpair_stride(r));
+        uint8_t* pr = smem + L.pair;
         for (int i = tid; i < 2 * rs2; i += nt) pr[i] = r.rowT[(size_t)(i < rs2 ? 0 : r.brick_icon + 1) * rs2 + (i < rs2 ? i : i - rs2)];
         for (int i = tid; i < 16 * r.n_sr * r.n_sc * 3; i += nt) pr[2 * rs2 + i] = r.cornerWB[i];
-        for (int i = tid; i < G * (XW_CELLBUF_BYTES + XW_SP_LIST_BYTES) / 4; i += nt) ((uint32_t*)(smem + L.cell))[i] = 0;
+        for (int i = tid; i < 2 * G * (XW_CELLBUF_BYTES + XW_SP_LIST_BYTES) / 4; i += nt) ((uint32_t*)(smem + L.cell))[i] = 0;
     }
     mbar_wait(bar, 0);
     __syncthreads();
 
     const int g = tid / GT, gt = tid - g * GT;
     if (g >= G) return;  // spare warps (G*GT < blockDim.x)
-    uint8_t* s_code = smem + L.cell + g * (XW_CELLBUF_BYTES + XW_SP_LIST_BYTES);
-    uint32_t* s_icon = (uint32_t*)(s_code + XW_CELL_STRIDE);
-    uint8_t* s_list = s_code + XW_CELLBUF_BYTES;
-    volatile uint32_t* s_count = (volatile uint32_t*)(s_list + XW_MAX_DIM * XW_MAX_DIM);
+    // two cell buffers per group: codes | descriptor per code | cell of the agent / goal g (0xff: none) | brick list | count
+    uint8_t* cellbuf = smem + L.cell + g * 2 * (XW_CELLBUF_BYTES + XW_SP_LIST_BYTES);
     uint32_t* fb = (uint32_t*)(smem + L.fb + (size_t)g * xw_align16(r.FB));
-    uint64_t* fillbar = bar + 2 + g;
+    uint64_t *fillbar = bar + 2 + g, *cellsbar = bar + 2 + G + g;
     XwComposeCtx x;
-    x.hot = hot; x.yb = s_yb;
-    x.colL_hot = smem + L.pair; x.rowT_hot = smem + L.pair + 4 * xw_colpair_stride(r);
+    x.hot = nullptr; x.yb = s_yb; x.colL_hot = nullptr;
+    x.rowT_hot = smem + L.pair;
     x.cornerWB = x.rowT_hot + 4 * xw_rowpair_stride(r);
     XwPaintCtx pg;
-    pg.cellgeo = (const XwU4*)(smem + L.cellgeo); pg.wcol = (const uint32_t*)(smem + L.wcol);
-    XwCells cells;
-    cells.code = s_code; cells.icon = s_icon;
+    pg.cellgeo = (const XwU4*)(smem + L.cellgeo); pg.wcol = (const uint32_t*)(smem + L.wcol); pg.wshare = smem + L.wshare;
+    pg.ctab = (const uint32_t*)(smem + L.ctab); pg.sr_ty = smem + L.srq; pg.sr_dy = smem + L.srq + r.n_sr;
+    pg.sc_a = (const uint32_t*)(smem + L.sca);
     const int bar_id = 1 + g;
     const int gstride = gridDim.x * G;
     const int lane = gt & 31;
-    const bool w0 = gt < 32;  // warp 0 of the group: cells, list
+    const bool w0 = gt < 32, w1 = gt >= 32 && gt < 64;  // the two PRE warps of the group
+    const bool tma_thread = gt == 63, tma_fill = r.sp_fill != 0;
     const int row_words = d.CS >> 2, HW = d.H * d.W;
-    const int S = 3 * r.nwc;
-    const bool tma_fill = r.sp_fill != 0;
+    const int WR = WR_T ? WR_T : r.WR;
+    const int n_sslots = (1 + d.G) * r.nwc, n_rw = r.n_sr * WR;
     int env = blockIdx.x * G + g;
     if (env >= d.n) return;
 
-    // register prefetch of the next env's grid row (<= 64 words: two per lane of warp 0) and goal icons
+    // register prefetch of an env's grid row (<= 64 words: two per lane of warp 0) and goal icons
     uint32_t nq0 = 0, nq1 = 0, ni = 0;
     auto load_cells = [&](int e) {
         const uint32_t* rowp = (const uint32_t*)(d.grid + (size_t)e * d.CS);
         if (lane < row_words) nq0 = rowp[lane];
         if (lane + 32 < row_words) nq1 = rowp[lane + 32];
-        if (lane < d.G) ni = (uint32_t)d.goal_icon[(size_t)lane * d.n + e] + 1;
+        if (lane < d.G) ni = (uint32_t)d.goal_icon[(size_t)lane * d.n + e];  // (+1 at the use: no wait here)
     };
-    if (w0) {
-        load_cells(env);
+    auto cells_of = [&](int b) {
+        XwCells c;
+        c.code = cellbuf + b * (XW_CELLBUF_BYTES + XW_SP_LIST_BYTES);
+        c.icon = (const uint32_t*)(c.code + XW_CELL_STRIDE);
+        return c;
+    };
+    // (warp 0) registers -> cell buffer b: codes, descriptors, where the agent and the goals are, brick list
+    auto store_cells = [&](int b) {
+        uint8_t* s_code = cellbuf + b * (XW_CELLBUF_BYTES + XW_SP_LIST_BYTES);
+        uint32_t* s_icon = (uint32_t*)(s_code + XW_CELL_STRIDE);
+        uint8_t* s_special = (uint8_t*)(s_icon + XW_CODE_SLOTS);
+        uint8_t* s_list = s_code + XW_CELLBUF_BYTES;
         if (lane == XW_CELL_BLOCK) s_icon[lane] = (uint32_t)d.brick_icon + 1;
         if (lane == XW_CELL_AGENT) s_icon[lane] = (uint32_t)d.agent_icon + 1;
+        if (lane < d.G) s_icon[XW_CELL_GOAL0 + lane] = ni + 1;
+        if (lane < XW_STAGE_SLOTS) s_special[lane] = 0xff;
+        __syncwarp();
+        uint32_t m0 = 0, m1 = 0;
+        if (lane < row_words) {
+            ((uint32_t*)s_code)[lane] = nq0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t c = (nq0 >> (8 * q)) & 0xff;
+                if (c == XW_CELL_BLOCK && 4 * lane + q < HW) m0 |= 1u << q;
+                if (c >= XW_CELL_AGENT && !(r.debug & 8)) s_special[c - XW_CELL_AGENT] = (uint8_t)(4 * lane + q);
+            }
+        }
+        if (lane + 32 < row_words) {
+            ((uint32_t*)s_code)[lane + 32] = nq1;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t c = (nq1 >> (8 * q)) & 0xff;
+                if (c == XW_CELL_BLOCK && 4 * (lane + 32) + q < HW) m1 |= 1u << q;
+                if (c >= XW_CELL_AGENT && !(r.debug & 8)) s_special[c - XW_CELL_AGENT] = (uint8_t)(4 * (lane + 32) + q);
+            }
+        }
+        // brick list: exclusive prefix of the per-lane counts (4-bit masks -> one ballot per bit); the second half
+        // of the row (maps of more than 128 cells) follows the first
+        int total = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (h == 1 && row_words <= 32) break;
+            const uint32_t mk = h ? m1 : m0;
+            const uint32_t b0 = __ballot_sync(0xffffffffu, mk & 1u), b1 = __ballot_sync(0xffffffffu, mk & 2u);
+            const uint32_t b2 = __ballot_sync(0xffffffffu, mk & 4u), b3 = __ballot_sync(0xffffffffu, mk & 8u);
+            const uint32_t below = (1u << lane) - 1u;
+            int pos = total + xw_popc(b0 & below) + xw_popc(b1 & below) + xw_popc(b2 & below) + xw_popc(b3 & below);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (mk & (1u << q)) s_list[pos++] = (uint8_t)(4 * (lane + 32 * h) + q);
+            total += xw_popc(b0) + xw_popc(b1) + xw_popc(b2) + xw_popc(b3);
+        }
+        if (lane == 0) *(volatile uint32_t*)(s_list + XW_MAX_DIM * XW_MAX_DIM) = (uint32_t)total;
+        __syncwarp();
+    };
+    // Work that reads L2 (special slots, straddling-row words) is ISSUED for the next env at the end of an env's
+    // POST and FINISHED in the next env's POST: the loads have a whole env time to land and nothing on the path
+    // barrier -> paint -> barrier -> TMA store ever waits for L2 (under this kernel's write load an L2 round
+    // trip is thousands of cycles).  Every thread of the group takes one special slot-plane (threads < 3 * n_sslots)
+    // and one straddling-row word (threads < n_rw; more words than threads: the rest in place), so that both warps
+    // carry the same load: a warp issues an instruction every ~7 cycles, and the instruction count of the
+    // busiest warp is what an env costs.
+    const int n_sl3 = 3 * n_sslots;                       // special slot-planes: lane s = (ord * 3 + p) * nwc + wc
+    const bool s_lane = gt < n_sl3;
+    const int s_ord = gt / (3 * r.nwc), s_p = (gt - s_ord * 3 * r.nwc) / r.nwc, s_wc = gt - (s_ord * 3 + s_p) * r.nwc;
+    const int r_idx = GT - 1 - gt;                        // straddling-row word (three planes): from the last thread down
+    const bool r_lane = r_idx < n_rw && !(r.debug & 16);
+    const int r_q = r_lane ? r_idx / WR : 0, r_k = r_lane ? r_idx - r_q * WR : 0;
+    uint32_t sm[XW_SP_ROWS], spb[XW_SP_ROWS / 4];  // special slot-plane: raw loads
+    uint32_t rwa[3], rwb[3], rt[4];               // straddling-row word: raw loads
+    int s_cell = 0xff;
+    bool s_have = false;
+    auto issue = [&](int b) {
+        const XwCells cn = cells_of(b);
+        s_have = false;
+        if (s_lane) {
+            s_cell = ((const uint8_t*)(cn.icon + XW_CODE_SLOTS))[s_ord];
+            if (s_cell != 0xff) s_have = xw_sp_special<WR_T, XW_SP_ROWS, 0>(r, x, pg, cn, s_cell, s_wc, s_p, sm, spb, nullptr);
+        }
+        if (r_lane) xw_sp_rword<WR_T, 0>(r, x, pg, cn, r_q, r_k, rwa, rwb, rt, nullptr);
+    };
+    // ---- prologue: env 0 of the group
+    if (w0) {
+        load_cells(env);
+        store_cells(0);
+        if (env + gstride < d.n) load_cells(env + gstride);
     }
+    group_bar(bar_id, GT);
+    issue(0);
+
+#if defined(XW_SP_PROF)  // phase clocks of lane 0 (a special-slot lane) and lane 63 (the TMA thread) of group 0, CTA 0
+    const bool prof = r.prof != nullptr && blockIdx.x == 0 && g == 0 && (gt == 0 || gt == 63);
+    unsigned int t_prev = prof ? (unsigned int)clock() : 0u;
+#define XW_PROF(i) do { if (prof) { const unsigned int t_now = (unsigned int)clock(); atomicAdd(r.prof + (gt == 0 ? 0 : 8) + (i), t_now - t_prev); t_prev = t_now; } } while (0)
+#else
+#define XW_PROF(i) do { } while (0)
+#endif
     for (uint32_t it = 0; env < d.n; env += gstride, ++it) {
+        const int cur = it & 1;
+        const bool have_next = env + gstride < d.n;
+        const XwCells cells = cells_of(cur);
+        XW_PROF(7);  // (loop overhead, TMA store issue)
         if (w0) {
-            if (tma_fill && lane == 0 && !(r.debug & 2)) {  // buffer drained -> white again, asynchronously
+            if (have_next) {
+                store_cells(cur ^ 1);  // next env's cells (every warp is past the POST of env it-1, the buffer's last reader)
+            }
+        } else if (w1 && !(r.debug & 2)) {  // the previous frame has left the buffer -> white again
+            if (lane == 31) {
                 tma_wait_read<0>();
-                mbar_expect_tx(fillbar, (uint32_t)r.FB);
-                tma_load_1d(fb, r.white, (uint32_t)r.FB, fillbar);
+                XW_PROF(0);  // lane 63: drain wait
+                if (tma_fill) {
+                    mbar_expect_tx(fillbar, (uint32_t)r.FB);
+                    tma_load_1d(fb, r.white, (uint32_t)r.FB, fillbar);
+                }
             }
-            // cells -> shared memory; list of the non-white cells (cells past the map are zero)
-            if (lane < d.G) s_icon[XW_CELL_GOAL0 + lane] = ni;
-            uint32_t m0 = 0, m1 = 0;
-            if (lane < row_words) {
-                ((uint32_t*)s_code)[lane] = nq0;
-#pragma unroll
-                for (int b = 0; b < 4; ++b) if (((nq0 >> (8 * b)) & 0xff) && 4 * lane + b < HW && !((r.debug & 8) && ((nq0 >> (8 * b)) & 0xff) >= XW_CELL_AGENT)) m0 |= 1u << b;
-            }
-            if (lane + 32 < row_words) {
-                ((uint32_t*)s_code)[lane + 32] = nq1;
-#pragma unroll
-                for (int b = 0; b < 4; ++b) if (((nq1 >> (8 * b)) & 0xff) && 4 * (lane + 32) + b < HW) m1 |= 1u << b;
-            }
-            // inclusive scan of the per-lane counts; the second half of the row follows the first
-            const int c0 = xw_popc(m0), c1 = xw_popc(m1);
-            int s0 = c0, s1 = c1;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t0 = __shfl_up_sync(0xffffffffu, s0, o), t1 = __shfl_up_sync(0xffffffffu, s1, o);
-                if (lane >= o) { s0 += t0; s1 += t1; }
-            }
-            const int tot0 = __shfl_sync(0xffffffffu, s0, 31), tot1 = __shfl_sync(0xffffffffu, s1, 31);
-            int pos = s0 - c0;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) if (m0 & (1u << b)) s_list[pos++] = (uint8_t)(4 * lane + b);
-            pos = tot0 + s1 - c1;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) if (m1 & (1u << b)) s_list[pos++] = (uint8_t)(4 * (lane + 32) + b);
-            if (lane == 0) {
-                *s_count = (uint32_t)(tot0 + tot1);
-                if (!tma_fill) tma_wait_read<0>();  // the TMA store of this group's previous frame has drained fb
+            if (!tma_fill) {
+                __syncwarp();
+                const int4 ones = make_int4(-1, -1, -1, -1);
+#pragma unroll 8
+                for (int i = lane; i < r.FB / 16; i += 32) ((int4*)fb)[i] = ones;
             }
         }
-        group_bar(bar_id, GT);
-        if (!tma_fill && !(r.debug & 2)) {
-            const int4 ones = make_int4(-1, -1, -1, -1);
-            for (int i = gt; i < r.FB / 16; i += GT) ((int4*)fb)[i] = ones;
+        XW_PROF(1);  // lane 0: next env's cells -> shared memory; lane 63: fill
+        if (tma_fill && !(r.debug & 2)) mbar_wait(fillbar, it & 1);
+        group_bar(bar_id, GT);  // buffer white, next env's cells visible
+        XW_PROF(2);  // barrier A wait
+        // ---- POST of this env: finish what was issued an env ago, paint the bricks, issue for the next env
+        if (!(r.debug & 1)) {
+            const uint8_t* s_list = cells.code + XW_CELLBUF_BYTES;
+            if (r_lane) xw_sp_rword<WR_T, 1>(r, x, pg, cells, r_q, r_k, rwa, rwb, rt, fb);
+            if (s_have && !(r.debug & 32)) xw_sp_special<WR_T, XW_SP_ROWS, 1>(r, x, pg, cells, s_cell, s_wc, s_p, sm, spb, fb);
+            XW_PROF(3);  // finish (lane 0: special slot, lane 63: straddling-row word)
+            if (!(r.debug & 16))
+                for (int idx = GT + gt; idx < n_rw; idx += GT) {  // (more straddling-row words than lanes: in place)
+                    uint32_t ta[3], tb[3], tt[4];
+                    xw_sp_rword<WR_T, 0>(r, x, pg, cells, idx / WR, idx % WR, ta, tb, tt, nullptr);
+                    xw_sp_rword<WR_T, 1>(r, x, pg, cells, idx / WR, idx % WR, ta, tb, tt, fb);
+                }
+            const int n_slots = (int)*(volatile const uint32_t*)(s_list + XW_MAX_DIM * XW_MAX_DIM) * r.nwc;
+            // (the last warp first: warp 0 has the cells of the next env to store, so the odd round goes elsewhere)
+            for (int s = GT - 32 - (gt & ~31) + lane; s < n_slots; s += GT) {
+                int i, wc;
+                xw_sp_decode(r, s, &i, &wc);
+                xw_sp_brick_slot<WR_T, XW_SP_ROWS>(r, pg, cells, s_list[i], wc, fb);
+            }
         }
-        if (w0 && env + gstride < d.n) load_cells(env + gstride);  // prefetch while this env is painted
-        if (tma_fill) { if (!(r.debug & 2)) mbar_wait(fillbar, it & 1); }
-        else group_bar(bar_id, GT);
-        const int n_slots = (r.debug & 1) ? 0 : (int)*s_count * S;
-        for (int s = gt; s < n_slots; s += GT) {
-            int i, p, wc;
-            xw_paint_decode(r, s, &i, &p, &wc);
-            xw_paint_slot<WR_T>(r, x, pg, cells, s_list[i], p, wc, fb);
-        }
+        XW_PROF(4);  // brick slots
         fence_async_smem();  // generic-proxy writes -> visible to the async (TMA) proxy
+        // (after the fence, which would otherwise wait for them: L2 loads for the next env and the env after it)
+        if (have_next && !(r.debug & 65)) issue(cur ^ 1);
+        if (w0 && env + 2 * gstride < d.n) load_cells(env + 2 * gstride);
+        XW_PROF(5);  // issue for the next env
         group_bar(bar_id, GT);
-        if (gt == 0 && !(r.debug & 4)) {
+        XW_PROF(6);  // barrier C wait
+        if (tma_thread && !(r.debug & 4)) {
             tma_store_1d(frames + (size_t)env * env_stride, fb, (uint32_t)r.FB);
             tma_commit();
         }
     }
-    if (gt == 0) tma_wait_all<0>();
+#undef XW_PROF
+    if (tma_thread) tma_wait_all<0>();
 }
 
 // General fallback (any frame size): one thread per output byte, straight to global memory.

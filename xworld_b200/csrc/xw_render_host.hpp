@@ -58,6 +58,10 @@ struct XwRenderTables {
     int nwc = 0;                         // most word columns one cell column touches
     std::vector<XwU4> cellgeo;           // [H*W]
     std::vector<uint32_t> wcol;          // [WR]
+    std::vector<uint8_t> wshare;         // [WR] index of word column k among the columns shared by two cell columns (0xff: not shared)
+    int ns = 0;                          // shared word columns
+    std::vector<uint8_t> sr_ty;          // [n_sr] cell row above straddling row q
+    int max_band_rows = 0;               // most rows of a band without its straddling row
     int n_warps = 0;
     int n_plan1 = 0;                     // plan[0..n_plan1): phase 1 (R / RC bundles), the rest: phase 2
     int bank_conflicts = 0;              // lane pairs of a bundle left on one bank (0 = conflict-free plan)
@@ -182,6 +186,7 @@ inline XwRenderTables xw_build_render_tables(int H, int W, int OH, int OW) {
 //                z: y0 | tx << 8                          first row of the band, cell column
 inline void xw_build_paint_tables(XwRenderTables& t) {
     t.sp_ok = false;
+    t.max_band_rows = 0;
     if (!t.fast_ok || t.W > 16 || t.H > 255) return;
     const int W = t.W, H = t.H, WR = t.WR;
     std::vector<uint8_t> is_sc(t.OW, 0), is_sr(t.OH, 0);
@@ -207,6 +212,9 @@ inline void xw_build_paint_tables(XwRenderTables& t) {
         t.wcol[k] = (uint32_t)lo | ((uint32_t)hi << 4) | (sel << 8) | ((uint32_t)(nsc ? 1 : 0) << 24) | ((uint32_t)sbyte << 25) | ((uint32_t)sidx << 27);
         for (int c = lo; c <= hi; ++c) { if (kfirst[c] < 0) kfirst[c] = k; klast[c] = k; }
     }
+    t.wshare.assign(WR, 0xff);
+    t.ns = 0;
+    for (int k = 0; k < WR; ++k) if ((t.wcol[k] & 15) != ((t.wcol[k] >> 4) & 15)) t.wshare[k] = (uint8_t)t.ns++;
     t.nwc = 0;
     for (int c = 0; c < W; ++c) {
         if (kfirst[c] < 0) return;
@@ -223,6 +231,7 @@ inline void xw_build_paint_tables(XwRenderTables& t) {
         const bool srow = is_sr[y1 - 1] != 0;
         if (srow) { for (size_t q = 0; q < t.sr.size(); ++q) if (t.sr[q] == y1 - 1) qb[ty] = (int)q; if (ty + 1 >= H) return; }
         const int nrows = y1 - y0 - (srow ? 1 : 0);
+        t.max_band_rows = std::max(t.max_band_rows, nrows);
         for (int tx = 0; tx < W; ++tx) {
             XwU4& g = t.cellgeo[(size_t)ty * W + tx];
             g.x = (uint32_t)(y0 * WR + kfirst[tx]) | ((uint32_t)nrows << 16) | ((uint32_t)(klast[tx] - kfirst[tx] + 1) << 24);
@@ -230,6 +239,9 @@ inline void xw_build_paint_tables(XwRenderTables& t) {
             g.z = (uint32_t)y0 | ((uint32_t)tx << 8);
         }
     }
+    t.sr_ty.assign(t.sr.size(), 0);
+    for (int ty = 0; ty < H; ++ty) if (qb[ty] != 0xff) t.sr_ty[qb[ty]] = (uint8_t)ty;
+    if (t.max_band_rows > 12) return;  // XW_SP_ROWS_MAX: rows a special slot keeps in registers
     t.sp_ok = true;
 }
 
