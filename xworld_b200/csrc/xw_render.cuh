@@ -745,23 +745,30 @@ XW_HD void xw_sp_brick_slot(const XwRender& r, const XwPaintCtx& g, const XwCell
     const int nrows = (int)((cg.x >> 16) & 0xff), y0 = (int)(cg.z & 0xff);
     const uint32_t* src = g.ctab + (size_t)col * xw_ctab_stride(r) + y0;
     uint32_t* dst = fb + y0 * WR + k;
+    // all loads of the three planes before the first store: the compiler cannot tell the class tables from the
+    // frame buffer, and a load -> store -> load chain would expose one shared-memory latency per plane.
+    // (Rows past the band are loaded -- the tables are followed by other shared memory -- and not stored.)
+    uint32_t v[3][8];
 #pragma unroll
-    for (int p = 0; p < 3; ++p) {
-        // (rows past the band are loaded -- the tables are followed by other shared memory -- and not stored)
-        uint32_t v[8];
+    for (int p = 0; p < 3; ++p)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = src[p * r.OH + j];
+        for (int j = 0; j < 8; ++j) v[p][j] = src[p * r.OH + j];
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-            if (j < nrows) dst[p * r.OH * WR + j * WR] = v[j];
-        if (XW_SP_ROWS > 8 && nrows > 8) {
-            uint32_t u[XW_SP_ROWS > 8 ? XW_SP_ROWS - 8 : 1];
+            if (j < nrows) dst[p * r.OH * WR + j * WR] = v[p][j];
+    if (XW_SP_ROWS > 8 && nrows > 8) {
+        uint32_t u[3][XW_SP_ROWS > 8 ? XW_SP_ROWS - 8 : 1];
 #pragma unroll
-            for (int j = 8; j < XW_SP_ROWS; ++j) u[j - 8] = src[p * r.OH + j];
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int j = 8; j < XW_SP_ROWS; ++j) u[p][j - 8] = src[p * r.OH + j];
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
 #pragma unroll
             for (int j = 8; j < XW_SP_ROWS; ++j)
-                if (j < nrows) dst[p * r.OH * WR + j * WR] = u[j - 8];
-        }
+                if (j < nrows) dst[p * r.OH * WR + j * WR] = u[p][j - 8];
     }
 }
 // brick slot s -> (list index, word column); exact for s < 4096 (xw_build_paint_tables: nwc <= 4)
