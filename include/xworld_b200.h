@@ -181,6 +181,11 @@ int xw_set_field(xw_sim* sim, const char* name, const void* h_in, size_t bytes);
 
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t xw_launch_count(const xw_sim* sim);
+/* Which render kernel the handle uses (diagnostics, tests): 0 = generic per-byte kernel, 1 = plan compositor with
+ * one frame buffer per warp group, 2 = pipelined plan compositor, 3 = sparse painter (the default when the frame
+ * geometry allows; XW_RENDER_MODE=sb|pipe selects the others); -1 = the game has no renderer.  No reference
+ * counterpart: the reference has one OpenCV code path (xworld_simulator.cpp:278-307). */
+int32_t xw_render_kernel(const xw_sim* sim);
 /* CUDA-event timing of the render kernel alone: average ms over the launches since the last
  * call with reset != 0.  Returns <0 if timing is disabled.  xw_enable_timing(sim, 1) first. */
 int xw_enable_timing(xw_sim* sim, int32_t on);

@@ -204,3 +204,35 @@ def test_simple_race_vs_oracle_1e6(backend_cls):
             exact += int((r.view(np.uint32) == r2.view(np.uint32)).sum())
             total += n
         assert exact >= 0.999 * total, (exact, total)
+
+
+@pytest.mark.parametrize("name,n", [("c3_nav2d_11x11_84", 65536), ("c2_nav3d_7x7_84", 65536), ("c4_nav3d_15x15_128", 32768),
+                                    ("ref_nav3d_8x8_96", 16384)])
+def test_painter_equals_plan_compositor_full_size(name, n, synthetic_catalog, monkeypatch):
+    """Two independent render kernels -- the sparse painter (default) and the dense plan compositor
+    (XW_RENDER_MODE=sb) -- on the same states at the BASELINE env counts: every byte of every frame equal."""
+    import torch
+    assert torch.cuda.is_available()
+    from gpu_backend import EngineBackend
+    cfg = parity.make_cfg(name, auto_reset=1)
+    engines = {}
+    for mode in ("sp", "sb"):
+        monkeypatch.setenv("XW_RENDER_MODE", mode)
+        engines[mode] = EngineBackend(cfg, synthetic_catalog, n)
+        engines[mode].reset()
+    monkeypatch.delenv("XW_RENDER_MODE")
+    assert engines["sp"].sim.render_kernel() == 3 and engines["sb"].sim.render_kernel() == 1
+    n_act = engines["sp"].sim.get_num_actions()
+    for s in range(12):
+        a = parity.actions_for(s, n, n_act)
+        for e in engines.values():
+            e.step(a, render=False)
+    for e in engines.values():
+        sim = e.sim
+        with torch.cuda.device(sim._dev):
+            assert sim._lib.xw_render(sim._h, sim._screen.data_ptr(), sim._stream()) == 0
+    torch.cuda.synchronize()
+    a, b = engines["sp"].sim._screen, engines["sb"].sim._screen
+    assert a.shape == b.shape and bool(torch.equal(a, b)), int((a != b).sum())
+    white = float((a == 255).float().mean())
+    assert 0.3 < white < 0.95  # a maze: mostly white, never blank

@@ -92,7 +92,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libxworld_b
 SYMBOLS = [
     "xw_config_init", "xw_create", "xw_destroy", "xw_last_error", "xw_reset", "xw_step", "xw_render",
     "xw_step_host", "xw_reset_host", "xw_step_hd", "xw_num_envs", "xw_num_actions", "xw_screen_dims",
-    "xw_frame_bytes", "xw_num_steps", "xw_get_field", "xw_set_field", "xw_launch_count",
+    "xw_frame_bytes", "xw_num_steps", "xw_get_field", "xw_set_field", "xw_launch_count", "xw_render_kernel",
     "xw_enable_timing", "xw_render_ms",
 ]
 
@@ -143,6 +143,8 @@ def load():
     lib.xw_set_field.argtypes = [vp, C.c_char_p, vp, C.c_size_t]
     lib.xw_set_field.restype = C.c_int
     lib.xw_launch_count.argtypes = [vp]
+    lib.xw_render_kernel.argtypes = [vp]
+    lib.xw_render_kernel.restype = C.c_int32
     lib.xw_launch_count.restype = i64
     lib.xw_enable_timing.argtypes = [vp, i32]
     lib.xw_enable_timing.restype = C.c_int

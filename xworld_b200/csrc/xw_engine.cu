@@ -482,6 +482,11 @@ size_t xw_frame_bytes(const xw_sim* s) {
 }
 
 int64_t xw_launch_count(const xw_sim* s) { return s->launches; }
+int32_t xw_render_kernel(const xw_sim* s) {
+    if (s->cfg.game != XW_GAME_XWORLD) return -1;
+    if (!s->tab.fast_ok) return 0;
+    return s->render_sp ? 3 : (s->render_sb ? 1 : 2);
+}
 
 int xw_enable_timing(xw_sim* s, int32_t on) { s->timing = on != 0; return 0; }
 

@@ -300,3 +300,7 @@ class Simulator(object):
 
     def launch_count(self):
         return int(self._lib.xw_launch_count(self._h))
+
+    def render_kernel(self):
+        """0 generic, 1 plan compositor, 2 pipelined plan compositor, 3 sparse painter (xw_render_kernel)."""
+        return int(self._lib.xw_render_kernel(self._h))
