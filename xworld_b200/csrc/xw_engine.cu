@@ -358,8 +358,10 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
         const int nt = r.G * r.GT;
 #define XW_PICK(WR_) (nt <= 512 ? k_render<WR_, 512> : nt <= 768 ? k_render<WR_, 768> : k_render<WR_, 1024>)
 #define XW_PICK_SB(WR_) (nt <= 512 ? k_render_sb<WR_, 512> : nt <= 576 ? k_render_sb<WR_, 576> : nt <= 768 ? k_render_sb<WR_, 768> : k_render_sb<WR_, 1024>)
-#define XW_PICK_SP(WR_) (t.max_band_rows <= 8 ? (nt <= 512 ? k_render_sp<WR_, 512, 8> : nt <= 768 ? k_render_sp<WR_, 768, 8> : k_render_sp<WR_, 1024, 8>) \
-                                              : (nt <= 512 ? k_render_sp<WR_, 512, 12> : nt <= 768 ? k_render_sp<WR_, 768, 12> : k_render_sp<WR_, 1024, 12>))
+        // (768 threads = 80 registers: only with the role-disjoint register sharing, i.e. 3 warps per group at 84x84)
+        const bool disj = 3 * (1 + c.n_goals) * t.nwc + r.n_sr * r.WR <= r.GT;
+#define XW_PICK_SP(WR_) (t.max_band_rows <= 8 ? (nt <= 512 ? k_render_sp<WR_, 512, 8> : nt <= 768 && disj ? k_render_sp<WR_, 768, 8, true> : k_render_sp<WR_, 1024, 8>) \
+                                              : (nt <= 512 ? k_render_sp<WR_, 512, 12> : nt <= 768 && disj ? k_render_sp<WR_, 768, 12, true> : k_render_sp<WR_, 1024, 12>))
         if (s->render_sp) s->render_fn = r.WR == 21 ? XW_PICK_SP(21) : r.WR == 24 ? XW_PICK_SP(24) : r.WR == 32 ? XW_PICK_SP(32) : XW_PICK_SP(0);
         else if (s->render_sb) s->render_fn = r.WR == 21 ? XW_PICK_SB(21) : r.WR == 24 ? XW_PICK_SB(24) : r.WR == 32 ? XW_PICK_SB(32) : XW_PICK_SB(0);
         else s->render_fn = r.WR == 21 ? XW_PICK(21) : r.WR == 24 ? XW_PICK(24) : r.WR == 32 ? XW_PICK(32) : XW_PICK(0);

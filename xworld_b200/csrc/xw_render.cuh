@@ -682,12 +682,11 @@ XW_HD bool xw_sp_special(const XwRender& r, const XwComposeCtx& x, const XwPaint
             const size_t cs = xw_colpair_stride(r);
             tab = (cR < 2 ? r.colL + ((size_t)dA * 2 + cR) * cs : r.colR + ((size_t)dB * 2 + cL) * cs) + ((size_t)(sidx * 3 + p) * r.H + ty) * r.RB;
         }
+        // (unconditional: rows past the band are inside the padded tables and never used)
 #pragma unroll
-        for (int j = 0; j < XW_SP_ROWS; ++j)
-            if (j < nrows) m[j] = pM[j * WR];
+        for (int j = 0; j < XW_SP_ROWS; ++j) m[j] = pM[j * WR];
 #pragma unroll
-        for (int j4 = 0; j4 < XW_SP_ROWS; j4 += 4)
-            if (j4 < nrows) pb[j4 / 4] = *(const uint32_t*)(tab + j4);
+        for (int j4 = 0; j4 < XW_SP_ROWS; j4 += 4) pb[j4 / 4] = *(const uint32_t*)(tab + j4);
         return true;
     }
     // the other cell column of the word: the brick class table (column-major, shared memory; white = brick |
@@ -704,8 +703,7 @@ XW_HD bool xw_sp_special(const XwRender& r, const XwComposeCtx& x, const XwPaint
     uint32_t* dst = fb + p * PW + y0 * WR + k;
     uint32_t o[XW_SP_ROWS];
 #pragma unroll
-    for (int j = 0; j < XW_SP_ROWS; ++j)
-        if (j < nrows) o[j] = pO[j * rsO];
+    for (int j = 0; j < XW_SP_ROWS; ++j) o[j] = pO[j * rsO];  // (unconditional, as in the issue step)
 #pragma unroll
     for (int j = 0; j < XW_SP_ROWS; ++j)
         if (j < nrows) {
@@ -745,30 +743,23 @@ XW_HD void xw_sp_brick_slot(const XwRender& r, const XwPaintCtx& g, const XwCell
     const int nrows = (int)((cg.x >> 16) & 0xff), y0 = (int)(cg.z & 0xff);
     const uint32_t* src = g.ctab + (size_t)col * xw_ctab_stride(r) + y0;
     uint32_t* dst = fb + y0 * WR + k;
-    // all loads of the three planes before the first store: the compiler cannot tell the class tables from the
-    // frame buffer, and a load -> store -> load chain would expose one shared-memory latency per plane.
-    // (Rows past the band are loaded -- the tables are followed by other shared memory -- and not stored.)
-    uint32_t v[3][8];
+    // (rows past the band are loaded -- the tables are followed by other shared memory -- and not stored)
 #pragma unroll
-    for (int p = 0; p < 3; ++p)
+    for (int p = 0; p < 3; ++p) {
+        uint32_t v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[p][j] = src[p * r.OH + j];
-#pragma unroll
-    for (int p = 0; p < 3; ++p)
+        for (int j = 0; j < 8; ++j) v[j] = src[p * r.OH + j];
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-            if (j < nrows) dst[p * r.OH * WR + j * WR] = v[p][j];
-    if (XW_SP_ROWS > 8 && nrows > 8) {
-        uint32_t u[3][XW_SP_ROWS > 8 ? XW_SP_ROWS - 8 : 1];
+            if (j < nrows) dst[p * r.OH * WR + j * WR] = v[j];
+        if (XW_SP_ROWS > 8 && nrows > 8) {
+            uint32_t u[XW_SP_ROWS > 8 ? XW_SP_ROWS - 8 : 1];
 #pragma unroll
-        for (int p = 0; p < 3; ++p)
-#pragma unroll
-            for (int j = 8; j < XW_SP_ROWS; ++j) u[p][j - 8] = src[p * r.OH + j];
-#pragma unroll
-        for (int p = 0; p < 3; ++p)
+            for (int j = 8; j < XW_SP_ROWS; ++j) u[j - 8] = src[p * r.OH + j];
 #pragma unroll
             for (int j = 8; j < XW_SP_ROWS; ++j)
-                if (j < nrows) dst[p * r.OH * WR + j * WR] = u[p][j - 8];
+                if (j < nrows) dst[p * r.OH * WR + j * WR] = u[j - 8];
+        }
     }
 }
 // brick slot s -> (list index, word column); exact for s < 4096 (xw_build_paint_tables: nwc <= 4)
@@ -1196,7 +1187,7 @@ __global__ void k_build_class_tables(XwRender r) {
 //             drain of the previous frame;
 //   everybody then stores the precomputed words and paints the brick slots (POST: shared memory only), and
 //   the TMA thread hands the frame to the TMA engine (one bulk store, evict-first in L2).
-template <int WR_T, int NT_MAX, int XW_SP_ROWS>
+template <int WR_T, int NT_MAX, int XW_SP_ROWS, bool DISJ = false>
 __global__ void __launch_bounds__(NT_MAX, 1)
 k_render_sp(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -1326,14 +1317,21 @@ k_render_sp(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride
     // and one straddling-row word (threads < n_rw; more words than threads: the rest in place), so that both warps
     // carry the same load: a warp issues an instruction every ~7 cycles, and the instruction count of the
     // busiest warp is what an env costs.
-    const int n_sl3 = 3 * n_sslots;                       // special slot-planes: lane s = (ord * 3 + p) * nwc + wc
-    const bool s_lane = gt < n_sl3;
-    const int s_ord = gt / (3 * r.nwc), s_p = (gt - s_ord * 3 * r.nwc) / r.nwc, s_wc = gt - (s_ord * 3 + s_p) * r.nwc;
-    const int r_idx = GT - 1 - gt;                        // straddling-row word (three planes): from the last thread down
+    // role index of a thread: with three or more warps, warps 1 and 2 are swapped so that warp 1 -- which waits for
+    // the drain and refills the buffer -- gets straddling-row words only and the special slot-planes go to warps 0, 2
+    const int vt = (GT >= 96 && gt >= 32 && gt < 96) ? (gt < 64 ? gt + 32 : gt - 32) : gt;
+    const int n_sl3 = 3 * n_sslots;                       // special slot-planes: vt = (ord * 3 + p) * nwc + wc
+    const bool s_lane = vt < n_sl3;
+    const int s_ord = vt / (3 * r.nwc), s_p = (vt - s_ord * 3 * r.nwc) / r.nwc, s_wc = vt - (s_ord * 3 + s_p) * r.nwc;
+    const int r_idx = GT - 1 - vt;                        // straddling-row word (three planes): from the last thread down
     const bool r_lane = r_idx < n_rw && !(r.debug & 16);
     const int r_q = r_lane ? r_idx / WR : 0, r_k = r_lane ? r_idx - r_q * WR : 0;
-    uint32_t sm[XW_SP_ROWS], spb[XW_SP_ROWS / 4];  // special slot-plane: raw loads
-    uint32_t rwa[3], rwb[3], rt[4];               // straddling-row word: raw loads
+    // carried raw loads: special slot-plane (m[ROWS], pb[ROWS/4]) and straddling-row word (wa[3], wb[3], t[4]).
+    // DISJ: no thread has both roles (3 * n_sslots + n_rw <= GT), so the two share one set of registers.
+    constexpr int N_SC = XW_SP_ROWS + XW_SP_ROWS / 4;
+    uint32_t carry[N_SC < 10 ? 10 : N_SC], carry2[DISJ ? 1 : 10];
+    uint32_t *sm = carry, *spb = carry + XW_SP_ROWS;
+    uint32_t *rwa = DISJ ? carry : carry2, *rwb = rwa + 3, *rt = rwa + 6;
     int s_cell = 0xff;
     bool s_have = false;
     auto issue = [&](int b) {
