@@ -236,3 +236,16 @@ def test_painter_equals_plan_compositor_full_size(name, n, synthetic_catalog, mo
     assert a.shape == b.shape and bool(torch.equal(a, b)), int((a != b).sum())
     white = float((a == 255).float().mean())
     assert 0.3 < white < 0.95  # a maze: mostly white, never blank
+
+
+@pytest.mark.parametrize("side,out,n", [(16, 128, 37), (16, 96, 300), (3, 24, 5), (5, 40, 149), (12, 96, 1185), (13, 104, 64)])
+def test_painter_odd_shapes_vs_oracle(side, out, n, backend_cls, synthetic_catalog):
+    """Map sides and env counts off the beaten path: 16x16 maps (two grid words per lane in the painter's cell
+    loader), fewer envs than warp groups, env counts that are not a multiple of the group count."""
+    blocks = {16: 60, 3: 1, 5: 4, 12: 36, 13: 42}[side]
+    cfg = _abi.default_config(height=side, width=side, n_goals=min(4, side - 1), n_blocks=blocks, rules=_abi.XW_RULES_NAV3D,
+                              out_h=out, out_w=out, seed=77, simulator_seed=3)
+    eng = backend_cls(cfg, synthetic_catalog, n)
+    orc = oracle.Oracle(cfg, synthetic_catalog, n, threads=8)
+    stats = parity.run_parity(eng, orc, 24, render_every=6, check_state_every=6)
+    assert stats["frames"] >= 4 * n

@@ -1225,7 +1225,7 @@ k_render_sp(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride
 
     const int g = tid / GT, gt = tid - g * GT;
     if (g >= G) return;  // spare warps (G*GT < blockDim.x)
-    // two cell buffers per group: codes | descriptor per code | cell of the agent / goal g (0xff: none) | brick list | count
+    // two cell buffers per group: codes | descriptor per code | cell of the agent / goal g | brick list | count
     uint8_t* cellbuf = smem + L.cell + g * 2 * (XW_CELLBUF_BYTES + XW_SP_LIST_BYTES);
     uint32_t* fb = (uint32_t*)(smem + L.fb + (size_t)g * xw_align16(r.FB));
     uint64_t *fillbar = bar + 2 + g, *cellsbar = bar + 2 + G + g;
@@ -1271,7 +1271,7 @@ k_render_sp(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride
         if (lane == XW_CELL_BLOCK) s_icon[lane] = (uint32_t)d.brick_icon + 1;
         if (lane == XW_CELL_AGENT) s_icon[lane] = (uint32_t)d.agent_icon + 1;
         if (lane < d.G) s_icon[XW_CELL_GOAL0 + lane] = ni + 1;
-        if (lane < XW_STAGE_SLOTS) s_special[lane] = 0xff;
+        if (lane < XW_STAGE_SLOTS) s_special[lane] = 0;  // (absent: the cell's code will not match, see issue())
         __syncwarp();
         uint32_t m0 = 0, m1 = 0;
         if (lane < row_words) {
@@ -1332,14 +1332,15 @@ k_render_sp(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride
     uint32_t carry[N_SC < 10 ? 10 : N_SC], carry2[DISJ ? 1 : 10];
     uint32_t *sm = carry, *spb = carry + XW_SP_ROWS;
     uint32_t *rwa = DISJ ? carry : carry2, *rwb = rwa + 3, *rt = rwa + 6;
-    int s_cell = 0xff;
+    int s_cell = 0;
     bool s_have = false;
     auto issue = [&](int b) {
         const XwCells cn = cells_of(b);
         s_have = false;
         if (s_lane) {
             s_cell = ((const uint8_t*)(cn.icon + XW_CODE_SLOTS))[s_ord];
-            if (s_cell != 0xff) s_have = xw_sp_special<WR_T, XW_SP_ROWS, 0>(r, x, pg, cn, s_cell, s_wc, s_p, sm, spb, nullptr);
+            // (every cell index 0..255 is a valid cell of a 16x16 map: presence = the cell really holds this code)
+            if (cn.code[s_cell] == XW_CELL_AGENT + s_ord) s_have = xw_sp_special<WR_T, XW_SP_ROWS, 0>(r, x, pg, cn, s_cell, s_wc, s_p, sm, spb, nullptr);
         }
         if (r_lane) xw_sp_rword<WR_T, 0>(r, x, pg, cn, r_q, r_k, rwa, rwb, rt, nullptr);
     };
