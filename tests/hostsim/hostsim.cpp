@@ -256,7 +256,7 @@ void hs_render_mode(HostSim* s, uint8_t* frames, int mode) {
             pg.sc_a = sc_a.data();
             pg.cellgeo = r.cellgeo; pg.wcol = r.wcol; pg.wshare = r.wshare; pg.ctab = r.ctab; pg.sr_ty = r.sr_ty; pg.sr_dy = sr_dy.data();
             std::vector<uint32_t> written(r.FB / 4, 0);  // every frame word has at most one writer
-            const bool fixed = r.WR == 21 && (e & 1);    // alternate the compile-time and the run-time row stride
+            const bool fixed = r.WR == 21 && r.OH == 84 && (e & 1);    // alternate the compile-time and the run-time row stride
             auto mark = [&](uint32_t w) { if (written[w]++) abort(); };
             for (int cell = 0; cell < d.H * d.W; ++cell) {
                 if (code[cell] < XW_CELL_AGENT) continue;

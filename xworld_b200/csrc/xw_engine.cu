@@ -362,7 +362,8 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
         const bool disj = 3 * (1 + c.n_goals) * t.nwc + r.n_sr * r.WR <= r.GT;
 #define XW_PICK_SP(WR_) (t.max_band_rows <= 8 ? (nt <= 512 ? k_render_sp<WR_, 512, 8> : nt <= 768 && disj ? k_render_sp<WR_, 768, 8, true> : k_render_sp<WR_, 1024, 8>) \
                                               : (nt <= 512 ? k_render_sp<WR_, 512, 12> : nt <= 768 && disj ? k_render_sp<WR_, 768, 12, true> : k_render_sp<WR_, 1024, 12>))
-        if (s->render_sp) s->render_fn = r.WR == 21 ? XW_PICK_SP(21) : r.WR == 24 ? XW_PICK_SP(24) : r.WR == 32 ? XW_PICK_SP(32) : XW_PICK_SP(0);
+        // (the painter's compile-time row stride also fixes the frame height: square frames only)
+        if (s->render_sp) s->render_fn = r.OH != r.OW ? XW_PICK_SP(0) : r.WR == 21 ? XW_PICK_SP(21) : r.WR == 24 ? XW_PICK_SP(24) : r.WR == 32 ? XW_PICK_SP(32) : XW_PICK_SP(0);
         else if (s->render_sb) s->render_fn = r.WR == 21 ? XW_PICK_SB(21) : r.WR == 24 ? XW_PICK_SB(24) : r.WR == 32 ? XW_PICK_SB(32) : XW_PICK_SB(0);
         else s->render_fn = r.WR == 21 ? XW_PICK(21) : r.WR == 24 ? XW_PICK(24) : r.WR == 32 ? XW_PICK(32) : XW_PICK(0);
 #undef XW_PICK

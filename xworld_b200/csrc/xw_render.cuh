@@ -579,6 +579,7 @@ template <int WR_T, int MODE>
 XW_HD void xw_sp_rword(const XwRender& r, const XwComposeCtx& x, const XwPaintCtx& g, const XwCells& cells, int q, int k,
                        uint32_t wa[3], uint32_t wb[3], uint32_t t[4], uint32_t* fb) {
     const int WR = WR_T ? WR_T : r.WR;
+    const int OH = WR_T ? 4 * WR_T : r.OH;  // (a compile-time row stride is only used for square frames)
     const uint32_t wk = g.wcol[k];
     const int lo = wk & 15, hi = (wk >> 4) & 15;
     const uint32_t sel = (wk >> 8) & 0xffffu;
@@ -643,7 +644,7 @@ XW_HD void xw_sp_rword(const XwRender& r, const XwComposeCtx& x, const XwPaintCt
     }
     uint32_t* dst = fb + g.sr_dy[q] * WR + k;
 #pragma unroll
-    for (int p = 0; p < 3; ++p) dst[p * r.OH * WR] = out[p];
+    for (int p = 0; p < 3; ++p) dst[p * OH * WR] = out[p];
 }
 
 // Word column wc of special cell `cell` in plane p, in two steps so that the L2 latency of the first is never waited for:
@@ -656,6 +657,7 @@ template <int WR_T, int XW_SP_ROWS, int MODE>
 XW_HD bool xw_sp_special(const XwRender& r, const XwComposeCtx& x, const XwPaintCtx& g, const XwCells& cells, int cell, int wc, int p,
                          uint32_t m[XW_SP_ROWS], uint32_t pb[XW_SP_ROWS / 4], uint32_t* fb) {
     const int WR = WR_T ? WR_T : r.WR;
+    const int OH = WR_T ? 4 * WR_T : r.OH;  // (a compile-time row stride is only used for square frames)
     const XwU4 cg = g.cellgeo[cell];
     if (wc >= (int)((cg.x >> 24) & 7)) return false;
     const int k = (int)(cg.y & 0xff) + wc, ty = (int)((cg.y >> 8) & 0xff);
@@ -666,7 +668,7 @@ XW_HD bool xw_sp_special(const XwRender& r, const XwComposeCtx& x, const XwPaint
     if (row + lo != cell && kA >= XW_CELL_AGENT) return false;
     const uint32_t dA = cells.icon[kA], dB = cells.icon[kB];
     const int nrows = (int)((cg.x >> 16) & 0xff), y0 = (int)(cg.z & 0xff);
-    const int PW = r.OH * WR;
+    const int PW = OH * WR;
     const bool meA = row + lo == cell;
     const bool has_sc = ((wk >> 24) & 1) != 0;
     const int sh = (int)((wk >> 25) & 3) * 8, sidx = (int)(wk >> 27);
@@ -695,7 +697,7 @@ XW_HD bool xw_sp_special(const XwRender& r, const XwComposeCtx& x, const XwPaint
     const uint32_t dO = meA ? dB : dA;
     const uint32_t sel = ((wk >> 8) & 0xffffu) ^ (meA ? 0u : 0x4444u);  // PRMT(mine, other)
     const uint32_t* pO = spO ? (const uint32_t*)(r.T + (size_t)(dO - 1) * r.FB) + p * PW + y0 * WR + k
-                             : g.ctab + (size_t)k * xw_ctab_stride(r) + p * r.OH + y0;
+                             : g.ctab + (size_t)k * ((3 * OH) | 1) + p * OH + y0;
     const int rsO = spO ? WR : 1;
     const uint32_t wmask = xw_prmt(0u, dO == 0 ? 0xffffffffu : 0u, sel);
     const uint32_t keep = has_sc ? ~(0xffu << sh) : 0xffffffffu;
@@ -727,6 +729,7 @@ XW_HD bool xw_sp_special(const XwRender& r, const XwComposeCtx& x, const XwPaint
 template <int WR_T, int XW_SP_ROWS>
 XW_HD void xw_sp_brick_slot(const XwRender& r, const XwPaintCtx& g, const XwCells& cells, int cell, int wc, uint32_t* fb) {
     const int WR = WR_T ? WR_T : r.WR;
+    const int OH = WR_T ? 4 * WR_T : r.OH;  // (a compile-time row stride is only used for square frames)
     const XwU4 cg = g.cellgeo[cell];
     if (wc >= (int)((cg.x >> 24) & 7)) return;
     const int k = (int)(cg.y & 0xff) + wc;
@@ -741,24 +744,24 @@ XW_HD void xw_sp_brick_slot(const XwRender& r, const XwPaintCtx& g, const XwCell
         if (ko == XW_CELL_EMPTY) col = r.WR + (left ? 0 : r.ns) + g.wshare[k];
     }
     const int nrows = (int)((cg.x >> 16) & 0xff), y0 = (int)(cg.z & 0xff);
-    const uint32_t* src = g.ctab + (size_t)col * xw_ctab_stride(r) + y0;
+    const uint32_t* src = g.ctab + (size_t)col * ((3 * OH) | 1) + y0;
     uint32_t* dst = fb + y0 * WR + k;
     // (rows past the band are loaded -- the tables are followed by other shared memory -- and not stored)
 #pragma unroll
     for (int p = 0; p < 3; ++p) {
         uint32_t v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = src[p * r.OH + j];
+        for (int j = 0; j < 8; ++j) v[j] = src[p * OH + j];
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-            if (j < nrows) dst[p * r.OH * WR + j * WR] = v[j];
+            if (j < nrows) dst[p * OH * WR + j * WR] = v[j];
         if (XW_SP_ROWS > 8 && nrows > 8) {
             uint32_t u[XW_SP_ROWS > 8 ? XW_SP_ROWS - 8 : 1];
 #pragma unroll
-            for (int j = 8; j < XW_SP_ROWS; ++j) u[j - 8] = src[p * r.OH + j];
+            for (int j = 8; j < XW_SP_ROWS; ++j) u[j - 8] = src[p * OH + j];
 #pragma unroll
             for (int j = 8; j < XW_SP_ROWS; ++j)
-                if (j < nrows) dst[p * r.OH * WR + j * WR] = u[j - 8];
+                if (j < nrows) dst[p * OH * WR + j * WR] = u[j - 8];
         }
     }
 }
