@@ -273,6 +273,7 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
                 if (GT < need) GT = (need + 31) / 32 * 32;
             }
             if (GT < 32 || G * GT > XW_RENDER_THREADS) { if (et) break; continue; }
+            if (!eg && !et && s->render_sp && G * GT > 512) continue;  // the painter needs its 124 registers: no spills
             const char* e2 = getenv("XW_RENDER_TWO_PHASE");
             xw_build_plan(t, GT / 32, split, cfree, !s->render_sb, e2 && atoi(e2) != 0);
             r.n_plan = (int)t.plan.size(); r.n_plan1 = t.n_plan1;
