@@ -249,3 +249,30 @@ def test_painter_odd_shapes_vs_oracle(side, out, n, backend_cls, synthetic_catal
     orc = oracle.Oracle(cfg, synthetic_catalog, n, threads=8)
     stats = parity.run_parity(eng, orc, 24, render_every=6, check_state_every=6)
     assert stats["frames"] >= 4 * n
+
+
+def test_step_hd_host_buffers_equal_device_path(synthetic_catalog):
+    """xw_step_hd (host actions in, host reward / game_over out, read-back overlapped with the render kernel)
+    against xw_step on a twin engine: page-locked buffers (used in place) and pageable ones (staged)."""
+    import torch
+    from gpu_backend import EngineBackend
+    cfg = parity.make_cfg("c3_nav2d_11x11_84", auto_reset=1)
+    n = 4096
+    a_eng, b_eng = EngineBackend(cfg, synthetic_catalog, n), EngineBackend(cfg, synthetic_catalog, n)
+    a_eng.reset(); b_eng.reset()
+    sim = b_eng.sim
+    for pinned in (True, False):
+        h_act = torch.zeros(n, dtype=torch.int32)
+        h_rew, h_over = torch.zeros(n, dtype=torch.float32), torch.zeros(n, dtype=torch.int32)
+        if pinned:
+            h_act, h_rew, h_over = h_act.pin_memory(), h_rew.pin_memory(), h_over.pin_memory()
+        for s in range(30):
+            a = parity.actions_for(s + (100 if pinned else 0), n, 4)
+            r1, o1, f1 = a_eng.step(a, render=True)
+            h_act.copy_(torch.from_numpy(a))
+            with torch.cuda.device(sim._dev):
+                rc = sim._lib.xw_step_hd(sim._h, h_act.data_ptr(), 1, h_rew.data_ptr(), h_over.data_ptr(), sim._screen.data_ptr())
+            assert rc == 0, sim._lib.xw_last_error()
+            assert (h_rew.numpy().view(np.uint32) == r1.view(np.uint32)).all() and (h_over.numpy() == o1).all()
+            torch.cuda.synchronize()
+            assert (sim._screen.cpu().numpy() == f1).all()

@@ -85,7 +85,8 @@ struct SimpleGameEnv {  // games/simple_game/simple_game_simulator.cpp (host; BA
 struct xw_sim {
     xw_config cfg;
     int n = 0, device = 0;
-    cudaStream_t own_stream = nullptr;
+    cudaStream_t own_stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_step = nullptr;
     int64_t launches = 0;
     int step_parity = 0;
     // xworld
@@ -459,6 +460,7 @@ void xw_destroy(xw_sim* s) {
     if (s->h_over) cudaFreeHost(s->h_over);
     if (s->h_rew) cudaFreeHost(s->h_rew);
     for (auto ev : s->ev) cudaEventDestroy(ev);
+    if (s->copy_stream) { cudaStreamDestroy(s->copy_stream); cudaEventDestroy(s->ev_step); }
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
 }
@@ -712,21 +714,48 @@ int xw_step_host(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float* h_
     return 0;
 }
 
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// Host actions in, host reward / game_over out, frames stay on the device.  Page-locked caller buffers are used
+// in place (no staging copy); the reward / game_over read-back runs on a second stream as soon as the step and
+// reset kernels are done, i.e. under the render kernel, so the call returns when the frames are complete.
 int xw_step_hd(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float* h_reward, int32_t* h_game_over, uint8_t* d_frames) {
     if (!h_actions || !h_reward || !h_game_over) return set_err(XW_ERR_INVALID_ARG, "null buffer");
     if (s->cfg.game == XW_GAME_SIMPLE_GAME) return set_err(XW_ERR_UNSUPPORTED, "simple_game has no device frames");
     int rc = ensure_staging(s, false);
     if (rc) return rc;
     cudaStream_t st = s->own_stream;
-    memcpy(s->h_act, h_actions, sizeof(int32_t) * s->n);
-    CUDA_TRY(cudaMemcpyAsync(s->d_act, s->h_act, sizeof(int32_t) * s->n, cudaMemcpyHostToDevice, st));
-    rc = xw_step(s, s->d_act, act_rep, s->d_rew, s->d_over, d_frames, st);
+    const bool pin_a = is_pinned(h_actions), pin_r = is_pinned(h_reward), pin_o = is_pinned(h_game_over);
+    const int32_t* src_a = h_actions;
+    if (!pin_a) { memcpy(s->h_act, h_actions, sizeof(int32_t) * s->n); src_a = s->h_act; }
+    CUDA_TRY(cudaMemcpyAsync(s->d_act, src_a, sizeof(int32_t) * s->n, cudaMemcpyHostToDevice, st));
+    const bool split = s->cfg.game == XW_GAME_XWORLD && d_frames != nullptr;
+    rc = xw_step(s, s->d_act, act_rep, s->d_rew, s->d_over, split ? nullptr : d_frames, st);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(s->h_rew, s->d_rew, sizeof(float) * s->n, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(s->h_over, s->d_over, sizeof(int32_t) * s->n, cudaMemcpyDeviceToHost, st));
+    cudaStream_t cs = st;
+    if (split) {
+        if (!s->copy_stream) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&s->ev_step, cudaEventDisableTiming));
+        }
+        cs = s->copy_stream;
+        CUDA_TRY(cudaEventRecord(s->ev_step, st));
+        CUDA_TRY(cudaStreamWaitEvent(cs, s->ev_step, 0));
+    }
+    CUDA_TRY(cudaMemcpyAsync(pin_r ? h_reward : s->h_rew, s->d_rew, sizeof(float) * s->n, cudaMemcpyDeviceToHost, cs));
+    CUDA_TRY(cudaMemcpyAsync(pin_o ? h_game_over : s->h_over, s->d_over, sizeof(int32_t) * s->n, cudaMemcpyDeviceToHost, cs));
+    if (split) {
+        rc = launch_render(s, d_frames, st);
+        if (rc) return rc;
+        CUDA_TRY(cudaStreamSynchronize(cs));
+    }
     CUDA_TRY(cudaStreamSynchronize(st));
-    memcpy(h_reward, s->h_rew, sizeof(float) * s->n);
-    memcpy(h_game_over, s->h_over, sizeof(int32_t) * s->n);
+    if (!pin_r) memcpy(h_reward, s->h_rew, sizeof(float) * s->n);
+    if (!pin_o) memcpy(h_game_over, s->h_over, sizeof(int32_t) * s->n);
     return 0;
 }
 
