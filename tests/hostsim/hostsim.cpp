@@ -26,7 +26,7 @@ struct HostSim {
     std::vector<uint16_t> ecol, uv;
     std::vector<uint32_t> corner;
     std::vector<uint8_t> colL, colR, rowT, rowB, cwb;
-    std::vector<uint32_t> ctab, cornerP;
+    std::vector<uint32_t> ctab, cornerP, TC;
     XwRaceCfg race;
 };
 
@@ -101,6 +101,7 @@ HostSim* hs_create(const xw_config* c, const xw_catalog* cat, int n) {
     if (t.sp_ok) {
         r.cellgeo = t.cellgeo.data(); r.wcol = t.wcol.data(); r.wshare = t.wshare.data(); r.sr_ty = t.sr_ty.data();
         r.nwc = t.nwc; r.ns = t.ns; r.slot_magic = 65536 / t.nwc + 1;
+        r.tc_rows = 12;  // (the host build always uses the 12-row instantiation)
     }
     r.n_sr = (int)t.sr.size();
     r.sr = t.sr.data();
@@ -165,6 +166,7 @@ HostSim* hs_create(const xw_config* c, const xw_catalog* cat, int n) {
 }
 
 // Build the phase atlas only for the icons in use (the full 363-icon table takes a while on one core).
+static void hs_build_cell_tables(HostSim* s, const int32_t* icons, int n_icons);
 void hs_build_phase_atlas(HostSim* s, const int32_t* icons, int n_icons) {
     XwRender& r = s->r;
     s->T.assign((size_t)r.n_icons * r.FB + XW_TABLE_PAD, 0);
@@ -176,8 +178,19 @@ void hs_build_phase_atlas(HostSim* s, const int32_t* icons, int n_icons) {
             s->T[(size_t)icon * r.FB + i] = xw_phase_px(r, icon, c, p / r.OW, p % r.OW);
         }
     }
+    hs_build_cell_tables(s, icons, n_icons);
 }
 
+// k_build_cell_tables, for the icons whose phase tables exist
+static void hs_build_cell_tables(HostSim* s, const int32_t* icons, int n_icons) {
+    XwRender& r = s->r;
+    if (!s->tab.sp_ok) return;
+    const size_t per_icon = (size_t)r.H * r.W * 3 * r.nwc * r.tc_rows;
+    s->TC.resize((size_t)r.n_icons * per_icon + 16, 0);
+    r.TC = s->TC.data();
+    for (int q = 0; q < n_icons; ++q)
+        for (size_t i = 0; i < per_icon; ++i) s->TC[(size_t)icons[q] * per_icon + i] = xw_tc_word(r, (size_t)icons[q] * per_icon + i);
+}
 int hs_fast_ok(HostSim* s) { return s->tab.fast_ok; }
 int hs_threads(HostSim* s) { return XW_RENDER_THREADS; }
 void hs_destroy(HostSim* s) { delete s; }
@@ -264,8 +277,10 @@ void hs_render_mode(HostSim* s, uint8_t* frames, int mode) {
                     for (int p = 0; p < 3; ++p) {
                         uint32_t m[12], pb[3];
                         memset(m, 0x5a, sizeof m); memset(pb, 0x5a, sizeof pb);
-                        const bool have = fixed ? xw_sp_special<21, 12, 0>(r, x, pg, cells, cell, wc, p, m, pb, nullptr)
-                                                : xw_sp_special<0, 12, 0>(r, x, pg, cells, cell, wc, p, m, pb, nullptr);
+                        XwRender r_row = r;   // every other pair of envs: without the cell-major table (the big-map path)
+                        if (e & 2) r_row.TC = nullptr;
+                        const bool have = fixed ? xw_sp_special<21, 12, 0>(r_row, x, pg, cells, cell, wc, p, m, pb, nullptr)
+                                                : xw_sp_special<0, 12, 0>(r_row, x, pg, cells, cell, wc, p, m, pb, nullptr);
                         if (!have) continue;
                         std::vector<uint32_t> before(fb);
                         const bool have2 = fixed ? xw_sp_special<21, 12, 1>(r, x, pg, cells, cell, wc, p, m, pb, fb.data())

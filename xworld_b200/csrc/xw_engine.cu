@@ -299,7 +299,12 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
         const size_t n_cwb = (size_t)16 * r.n_sr * r.n_sc * 3 + 64;
         auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
         const size_t n_white = s->render_sp ? (size_t)r.FB + xw_ctab_words(r) * 4 + (size_t)(cat->n_icons + 1) * 16 : 0;
-        const size_t total = up(n_T) + (t.fast_ok ? up(n_ecol) + up(n_uv) + up(n_corner) + 2 * up(n_col) + 2 * up(n_row) + up(n_cwb) + up(n_white) : 0);
+        if (s->render_sp) r.tc_rows = t.max_band_rows <= 8 ? 8 : 12;
+        // cell-major copy of the phase atlas for the painter's special slots -- as long as it stays L2-resident next to
+        // the other tables (C3: 12.6 MB; C4 would be 35 MB and measured slower than reading the atlas row by row)
+        size_t n_tc = s->render_sp ? (size_t)cat->n_icons * c.height * c.width * 3 * t.nwc * r.tc_rows * 4 + 64 : 0;
+        if (n_tc > ((size_t)24 << 20)) n_tc = 0;
+        const size_t total = up(n_T) + (t.fast_ok ? up(n_ecol) + up(n_uv) + up(n_corner) + 2 * up(n_col) + 2 * up(n_row) + up(n_cwb) + up(n_white) + up(n_tc) : 0);
         uint8_t* base = nullptr;
         rc |= dalloc(s, &base, total, false);
         if (rc) return rc;
@@ -316,6 +321,7 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
                 r.white = w;
                 r.ctab = (const uint32_t*)(w + r.FB);  // (FB % 16 == 0)
                 r.cornerP = r.ctab + xw_ctab_words(r);
+                r.TC = n_tc ? (const uint32_t*)take(n_tc) : nullptr;
                 rc |= dupload(s, &r.cellgeo, t.cellgeo.data(), t.cellgeo.size());
                 rc |= dupload(s, &r.wcol, t.wcol.data(), t.wcol.size());
                 rc |= dupload(s, &r.wshare, t.wshare.data(), t.wshare.size());
@@ -350,7 +356,11 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
         k_build_edge_tables<<<s->n_sms * 2, 256, 0, s->own_stream>>>(r);
         k_build_pair_tables<<<s->n_sms * 4, 256, 0, s->own_stream>>>(r);
         s->launches += 2;
-        if (s->render_sp) { k_build_class_tables<<<s->n_sms * 2, 256, 0, s->own_stream>>>(r); s->launches++; }
+        if (s->render_sp) {
+            k_build_class_tables<<<s->n_sms * 2, 256, 0, s->own_stream>>>(r);
+            if (r.TC) k_build_cell_tables<<<s->n_sms * 8, 256, 0, s->own_stream>>>(r);  // (after k_build_phase_atlas, same stream)
+            s->launches += 2;
+        }
     }
     CUDA_TRY(cudaGetLastError());
     if (t.fast_ok) {

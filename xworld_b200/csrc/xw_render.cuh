@@ -80,6 +80,11 @@ struct XwRender {
     int32_t slot_magic;       // slot / nwc == (slot * slot_magic) >> 16 for slot < 4096
     const uint32_t* cornerP;  // [n_icons+1][4] corner tap of role (top-left cell's (63,63), top-right's (63,0), bottom-left's
                               //   (0,63), bottom-right's (0,0)), planes 0..2 in bytes 0..2
+    const uint32_t* TC;       // [n_icons][H*W][3][nwc][tc_rows] cell-major copy of the phase atlas: the words a special slot-plane
+                              //   reads (band rows of word column wc of the cell in plane p) are tc_rows consecutive words --
+                              //   one or two 32-byte sectors instead of one per row (the painter is bound by the number of L2
+                              //   requests in flight, not by their bytes)
+    int32_t tc_rows;          // 8 or 12 = the kernel's XW_SP_ROWS
     XwRenderSpSmem sp;        // = xw_render_sp_smem(r, G)
     unsigned int* prof;       // -DXW_SP_PROF builds only: per-phase clock sums of group 0 of CTA 0 (tools/sweep_render.py)
     int32_t sp_fill;          // 0: white pre-fill with vector stores (warp 1), 1: with a TMA bulk load of `white`
@@ -678,15 +683,24 @@ XW_HD bool xw_sp_special(const XwRender& r, const XwComposeCtx& x, const XwPaint
         // this cell's own phase table (row-major, L2); the straddling byte from the pair table of the special
         // cell and the class of the other one (special | special: exact, in the finish step)
         const uint32_t dM = meA ? dA : dB;
-        const uint32_t* pM = (const uint32_t*)(r.T + (size_t)(dM - 1) * r.FB) + p * PW + y0 * WR + k;
         const uint8_t* tab = (const uint8_t*)g.ctab;  // (no straddling byte: any readable address)
         if (has_sc && !exact) {
             const size_t cs = xw_colpair_stride(r);
             tab = (cR < 2 ? r.colL + ((size_t)dA * 2 + cR) * cs : r.colR + ((size_t)dB * 2 + cL) * cs) + ((size_t)(sidx * 3 + p) * r.H + ty) * r.RB;
         }
-        // (unconditional: rows past the band are inside the padded tables and never used)
+        // (unconditional loads: rows past the band are inside the padded tables and never used)
+        if (r.TC == nullptr) {  // big maps: no cell-major table (xw_create), the phase atlas row by row
+            const uint32_t* pT = (const uint32_t*)(r.T + (size_t)(dM - 1) * r.FB) + p * PW + y0 * WR + k;
 #pragma unroll
-        for (int j = 0; j < XW_SP_ROWS; ++j) m[j] = pM[j * WR];
+            for (int j = 0; j < XW_SP_ROWS; ++j) m[j] = pT[j * WR];
+        } else {  // 16-byte loads (the blocks are 32- or 48-byte aligned)
+            const uint32_t* pM = r.TC + ((((size_t)(dM - 1) * (r.H * r.W) + cell) * 3 + p) * r.nwc + wc) * XW_SP_ROWS;
+#pragma unroll
+            for (int j4 = 0; j4 < XW_SP_ROWS; j4 += 4) {
+                const XwU4 q4 = *(const XwU4*)(pM + j4);
+                m[j4] = q4.x; m[j4 + 1] = q4.y; m[j4 + 2] = q4.z; m[j4 + 3] = q4.w;
+            }
+        }
 #pragma unroll
         for (int j4 = 0; j4 < XW_SP_ROWS; j4 += 4) pb[j4 / 4] = *(const uint32_t*)(tab + j4);
         return true;
@@ -771,6 +785,17 @@ XW_HD void xw_sp_decode(const XwRender& r, int s, int* i, int* wc) {
     *wc = s - *i * r.nwc;
 }
 
+// TC[icon][cell][p][wc][j] = T[icon][p][y0(cell) + j][kfirst(cell) + wc]  (0 past the frame / the cell's columns)
+XW_HD uint32_t xw_tc_word(const XwRender& r, size_t i) {
+    const int j = (int)(i % r.tc_rows); i /= r.tc_rows;
+    const int wc = (int)(i % r.nwc); i /= r.nwc;
+    const int p = (int)(i % 3); i /= 3;
+    const int cell = (int)(i % (r.H * r.W)); const size_t icon = i / (r.H * r.W);
+    const XwU4 cg = r.cellgeo[cell];
+    const int k = (int)(cg.y & 0xff) + wc, dy = (int)(cg.z & 0xff) + j;
+    if (wc >= (int)((cg.x >> 24) & 7) || dy >= r.OH) return 0;
+    return ((const uint32_t*)(r.T + icon * r.FB))[(p * r.OH + dy) * r.WR + k];
+}
 #define XW_SP_LIST_BYTES (XW_MAX_DIM * XW_MAX_DIM + 16)   // brick cell list + its length (u32 at the end)
 XW_HD XwRenderSpSmem xw_render_sp_smem(const XwRender& r, int G) {
     XwRenderSpSmem s;
@@ -1163,6 +1188,11 @@ k_render_sb(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride
 }
 
 
+__global__ void k_build_cell_tables(XwRender r) {
+    const size_t total = (size_t)r.n_icons * r.H * r.W * 3 * r.nwc * r.tc_rows;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+        ((uint32_t*)r.TC)[i] = xw_tc_word(r, i);
+}
 __global__ void k_build_class_tables(XwRender r) {
     const size_t per = (size_t)xw_ctab_stride(r), total = xw_ctab_words(r);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)(r.n_icons + 1) * 4; i += (size_t)gridDim.x * blockDim.x)
