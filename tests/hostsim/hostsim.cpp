@@ -26,7 +26,7 @@ struct HostSim {
     std::vector<uint16_t> ecol, uv;
     std::vector<uint32_t> corner;
     std::vector<uint8_t> colL, colR, rowT, rowB, cwb;
-    std::vector<uint32_t> ctab, cornerP, TC;
+    std::vector<uint32_t> ctab, cornerP, TC, rowT2, rowB2;
     XwRaceCfg race;
 };
 
@@ -265,7 +265,17 @@ void hs_render_mode(HostSim* s, uint8_t* frames, int mode) {
             for (int q = 0; q < r.n_sr; ++q) sr_dy[q] = (uint8_t)r.sr[q];
             std::vector<uint32_t> sc_a(r.n_sc + 1);
             for (int i = 0; i < r.n_sc; ++i) sc_a[i] = (uint32_t)(uint16_t)r.taps.xa0[r.sc[i]] | ((uint32_t)(uint16_t)r.taps.xa1[r.sc[i]] << 16);
+            if (s->rowT2.empty()) {  // k_build_row2_tables
+                const size_t tot = (size_t)(r.n_icons + 1) * 2 * r.n_sr * r.WR * 3;
+                s->rowT2.resize(tot + 16); s->rowB2.resize(tot + 16);
+                for (size_t i = 0; i < tot; ++i) { s->rowT2[i] = xw_row2_word(r, r.rowT, i); s->rowB2[i] = xw_row2_word(r, r.rowB, i); }
+                r.rowT2 = s->rowT2.data(); r.rowB2 = s->rowB2.data();
+            }
+            const size_t rs2w = (size_t)2 * r.n_sr * r.WR * 3;
+            std::vector<uint32_t> row2_hot(2 * rs2w + 16);
+            for (size_t i = 0; i < rs2w; ++i) { row2_hot[i] = r.rowT2[i]; row2_hot[rs2w + i] = r.rowT2[(size_t)(r.brick_icon + 1) * rs2w + i]; }
             XwPaintCtx pg;
+            pg.row2_hot = row2_hot.data();
             pg.sc_a = sc_a.data();
             pg.cellgeo = r.cellgeo; pg.wcol = r.wcol; pg.wshare = r.wshare; pg.ctab = r.ctab; pg.sr_ty = r.sr_ty; pg.sr_dy = sr_dy.data();
             std::vector<uint32_t> written(r.FB / 4, 0);  // every frame word has at most one writer

@@ -304,7 +304,8 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
         // the other tables (C3: 12.6 MB; C4 would be 35 MB and measured slower than reading the atlas row by row)
         size_t n_tc = s->render_sp ? (size_t)cat->n_icons * c.height * c.width * 3 * t.nwc * r.tc_rows * 4 + 64 : 0;
         if (n_tc > ((size_t)24 << 20)) n_tc = 0;
-        const size_t total = up(n_T) + (t.fast_ok ? up(n_ecol) + up(n_uv) + up(n_corner) + 2 * up(n_col) + 2 * up(n_row) + up(n_cwb) + up(n_white) + up(n_tc) : 0);
+        const size_t n_row2 = s->render_sp ? (size_t)(cat->n_icons + 1) * 2 * r.n_sr * r.WR * 3 * 4 + 64 : 0;
+        const size_t total = up(n_T) + (t.fast_ok ? up(n_ecol) + up(n_uv) + up(n_corner) + 2 * up(n_col) + 2 * up(n_row) + up(n_cwb) + up(n_white) + up(n_tc) + 2 * up(n_row2) : 0);
         uint8_t* base = nullptr;
         rc |= dalloc(s, &base, total, false);
         if (rc) return rc;
@@ -322,6 +323,7 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
                 r.ctab = (const uint32_t*)(w + r.FB);  // (FB % 16 == 0)
                 r.cornerP = r.ctab + xw_ctab_words(r);
                 r.TC = n_tc ? (const uint32_t*)take(n_tc) : nullptr;
+                r.rowT2 = (const uint32_t*)take(n_row2); r.rowB2 = (const uint32_t*)take(n_row2);
                 rc |= dupload(s, &r.cellgeo, t.cellgeo.data(), t.cellgeo.size());
                 rc |= dupload(s, &r.wcol, t.wcol.data(), t.wcol.size());
                 rc |= dupload(s, &r.wshare, t.wshare.data(), t.wshare.size());
@@ -359,7 +361,8 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
         if (s->render_sp) {
             k_build_class_tables<<<s->n_sms * 2, 256, 0, s->own_stream>>>(r);
             if (r.TC) k_build_cell_tables<<<s->n_sms * 8, 256, 0, s->own_stream>>>(r);  // (after k_build_phase_atlas, same stream)
-            s->launches += 2;
+            k_build_row2_tables<<<s->n_sms, 256, 0, s->own_stream>>>(r);                  // (after k_build_pair_tables)
+            s->launches += 3;
         }
     }
     CUDA_TRY(cudaGetLastError());

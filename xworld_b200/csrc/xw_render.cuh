@@ -80,6 +80,8 @@ struct XwRender {
     int32_t slot_magic;       // slot / nwc == (slot * slot_magic) >> 16 for slot < 4096
     const uint32_t* cornerP;  // [n_icons+1][4] corner tap of role (top-left cell's (63,63), top-right's (63,0), bottom-left's
                               //   (0,63), bottom-right's (0,0)), planes 0..2 in bytes 0..2
+    const uint32_t *rowT2, *rowB2;  // [n_icons+1][2][n_sr][WR][3] the painter's copy of rowT / rowB: the three planes of a word are
+                              //   adjacent (one L2 sector per cell column of a straddling-row word instead of three)
     const uint32_t* TC;       // [n_icons][H*W][3][nwc][tc_rows] cell-major copy of the phase atlas: the words a special slot-plane
                               //   reads (band rows of word column wc of the cell in plane p) are tc_rows consecutive words --
                               //   one or two 32-byte sectors instead of one per row (the painter is bound by the number of L2
@@ -550,6 +552,7 @@ struct XwPaintCtx {    // shared-memory copies on the device
     const uint8_t* sr_ty;   // [n_sr] cell row above straddling row q
     const uint8_t* sr_dy;   // [n_sr] its output row
     const uint32_t* sc_a;   // [n_sc] horizontal weights xa0 | xa1 << 16 of straddling column s
+    const uint32_t* row2_hot;  // the white and brick entries of rowT2: [2 descs][2 cls][n_sr][WR][3]
 };
 // words per class-table column: 3 planes x OH rows, made odd so that the columns of one band (same rows, different
 // word columns) sit on different shared-memory banks
@@ -597,15 +600,14 @@ XW_HD void xw_sp_rword(const XwRender& r, const XwComposeCtx& x, const XwPaintCt
     if (MODE == 0) {
         if (exact) return;
         // per cell column: (top cell, class of the bottom cell) or (bottom cell, class of the top cell)
-        const size_t rs = xw_rowpair_stride(r);
-        const uint8_t *tA, *tB;
-        if (cBa < 2) tA = (cTa < 2 ? x.rowT_hot + (size_t)cTa * 2 * rs : r.rowT + (size_t)cells.icon[kTa] * 2 * rs) + (size_t)cBa * rs;
-        else tA = r.rowB + (size_t)cells.icon[kBa] * 2 * rs + (size_t)cTa * rs;
-        if (cBb < 2) tB = (cTb < 2 ? x.rowT_hot + (size_t)cTb * 2 * rs : r.rowT + (size_t)cells.icon[kTb] * 2 * rs) + (size_t)cBb * rs;
-        else tB = r.rowB + (size_t)cells.icon[kBb] * 2 * rs + (size_t)cTb * rs;
-        const size_t off = (size_t)q * 3 * r.OW + 4 * k;
+        const uint32_t rs = (uint32_t)(r.n_sr * WR * 3), off = (uint32_t)((q * WR + k) * 3);  // words per (desc, class); this word
+        const uint32_t *tA, *tB;
+        if (cBa < 2) tA = (cTa < 2 ? g.row2_hot + cTa * 2 * rs : r.rowT2 + cells.icon[kTa] * 2 * rs) + cBa * rs;
+        else tA = r.rowB2 + cells.icon[kBa] * 2 * rs + cTa * rs;
+        if (cBb < 2) tB = (cTb < 2 ? g.row2_hot + cTb * 2 * rs : r.rowT2 + cells.icon[kTb] * 2 * rs) + cBb * rs;
+        else tB = r.rowB2 + cells.icon[kBb] * 2 * rs + cTb * rs;
 #pragma unroll
-        for (int p = 0; p < 3; ++p) { wa[p] = *(const uint32_t*)(tA + off + p * r.OW); wb[p] = *(const uint32_t*)(tB + off + p * r.OW); }
+        for (int p = 0; p < 3; ++p) { wa[p] = tA[off + p]; wb[p] = tB[off + p]; }
         if (corner && !wb_corner) {
             // taps (63,63) of the top-left cell, (63,0) top-right, (0,63) bottom-left, (0,0) bottom-right
             t[0] = r.cornerP[cells.icon[kTa] * 4 + 0]; t[1] = r.cornerP[cells.icon[kTb] * 4 + 1];
@@ -796,6 +798,13 @@ XW_HD uint32_t xw_tc_word(const XwRender& r, size_t i) {
     if (wc >= (int)((cg.x >> 24) & 7) || dy >= r.OH) return 0;
     return ((const uint32_t*)(r.T + icon * r.FB))[(p * r.OH + dy) * r.WR + k];
 }
+// rowT2 / rowB2 [desc][cls][q][k][p] <- rowT / rowB [desc][cls][q][p][OW bytes]
+XW_HD uint32_t xw_row2_word(const XwRender& r, const uint8_t* src, size_t i) {
+    const int p = (int)(i % 3); i /= 3;
+    const int k = (int)(i % r.WR); i /= r.WR;
+    const int q = (int)(i % r.n_sr); i /= r.n_sr;  // i = desc * 2 + cls
+    return *(const uint32_t*)(src + i * xw_rowpair_stride(r) + (size_t)(q * 3 + p) * r.OW + 4 * k);
+}
 #define XW_SP_LIST_BYTES (XW_MAX_DIM * XW_MAX_DIM + 16)   // brick cell list + its length (u32 at the end)
 XW_HD XwRenderSpSmem xw_render_sp_smem(const XwRender& r, int G) {
     XwRenderSpSmem s;
@@ -808,7 +817,7 @@ XW_HD XwRenderSpSmem xw_render_sp_smem(const XwRender& r, int G) {
     s.srq = o; o += xw_align16(2 * (r.n_sr + 1));
     s.sca = o; o += xw_align16(4 * (r.n_sc + 1));
     s.yb = o; o += xw_align16(r.OH * 4);
-    s.pair = o; o += xw_align16((int)(4 * xw_rowpair_stride(r)) + 16 * r.n_sr * r.n_sc * 3);
+    s.pair = o; o += xw_align16(4 * r.n_sr * r.WR * 3 * 4) + xw_align16(16 * r.n_sr * r.n_sc * 3);
     s.cell = o; o += 2 * G * (XW_CELLBUF_BYTES + XW_SP_LIST_BYTES);
     s.bar = o; o += 16 + 16 * G;
     s.total = o;
@@ -1188,6 +1197,13 @@ k_render_sb(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride
 }
 
 
+__global__ void k_build_row2_tables(XwRender r) {
+    const size_t total = (size_t)(r.n_icons + 1) * 2 * r.n_sr * r.WR * 3;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        ((uint32_t*)r.rowT2)[i] = xw_row2_word(r, r.rowT, i);
+        ((uint32_t*)r.rowB2)[i] = xw_row2_word(r, r.rowB, i);
+    }
+}
 __global__ void k_build_cell_tables(XwRender r) {
     const size_t total = (size_t)r.n_icons * r.H * r.W * 3 * r.nwc * r.tc_rows;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
@@ -1247,10 +1263,11 @@ k_render_sp(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride
         for (int i = tid; i < r.n_sr; i += nt) { (smem + L.srq)[i] = r.sr_ty[i]; (smem + L.srq)[r.n_sr + i] = (uint8_t)r.sr[i]; }
         for (int i = tid; i < r.n_sc; i += nt) ((uint32_t*)(smem + L.sca))[i] = (uint32_t)(uint16_t)r.taps.xa0[r.sc[i]] | ((uint32_t)(uint16_t)r.taps.xa1[r.sc[i]] << 16);
         for (int i = tid; i < r.OH; i += nt) s_yb[i] = (uint32_t)(uint16_t)r.taps.ya0[i] | ((uint32_t)(uint16_t)r.taps.ya1[i] << 16);
-        const int rs2 = (int)(2 * xw_rowpair_stride(r));
-        uint8_t* pr = smem + L.pair;
-        for (int i = tid; i < 2 * rs2; i += nt) pr[i] = r.rowT[(size_t)(i < rs2 ? 0 : r.brick_icon + 1) * rs2 + (i < rs2 ? i : i - rs2)];
-        for (int i = tid; i < 16 * r.n_sr * r.n_sc * 3; i += nt) pr[2 * rs2 + i] = r.cornerWB[i];
+        const int rs2 = 2 * r.n_sr * r.WR * 3;  // words of one descriptor in rowT2
+        uint32_t* pr = (uint32_t*)(smem + L.pair);
+        for (int i = tid; i < 2 * rs2; i += nt) pr[i] = r.rowT2[(size_t)(i < rs2 ? 0 : r.brick_icon + 1) * rs2 + (i < rs2 ? i : i - rs2)];
+        uint8_t* pcw = smem + L.pair + xw_align16(2 * rs2 * 4);
+        for (int i = tid; i < 16 * r.n_sr * r.n_sc * 3; i += nt) pcw[i] = r.cornerWB[i];
         for (int i = tid; i < 2 * G * (XW_CELLBUF_BYTES + XW_SP_LIST_BYTES) / 4; i += nt) ((uint32_t*)(smem + L.cell))[i] = 0;
     }
     mbar_wait(bar, 0);
@@ -1264,9 +1281,10 @@ k_render_sp(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride
     uint64_t *fillbar = bar + 2 + g, *cellsbar = bar + 2 + G + g;
     XwComposeCtx x;
     x.hot = nullptr; x.yb = s_yb; x.colL_hot = nullptr;
-    x.rowT_hot = smem + L.pair;
-    x.cornerWB = x.rowT_hot + 4 * xw_rowpair_stride(r);
+    x.rowT_hot = nullptr;
+    x.cornerWB = smem + L.pair + xw_align16(4 * r.n_sr * r.WR * 3 * 4);
     XwPaintCtx pg;
+    pg.row2_hot = (const uint32_t*)(smem + L.pair);
     pg.cellgeo = (const XwU4*)(smem + L.cellgeo); pg.wcol = (const uint32_t*)(smem + L.wcol); pg.wshare = smem + L.wshare;
     pg.ctab = (const uint32_t*)(smem + L.ctab); pg.sr_ty = smem + L.srq; pg.sr_dy = smem + L.srq + r.n_sr;
     pg.sc_a = (const uint32_t*)(smem + L.sca);
