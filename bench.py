@@ -30,11 +30,35 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 ENVS_PER_GPU = 65536
-WORKLOAD = dict(height=11, width=11, n_goals=4, n_blocks=30, rules=1, out_h=84, out_w=84, max_steps=242,
-                auto_reset=1, seed=1234, simulator_seed=1)
-WORKLOAD_NAME = "XWorld2D walls.json rules, 11x11 maze, 84x84x3 u8 obs, 65536 envs/GPU (BASELINE configs[2])"
+# The default ("c3") is the configuration BASELINE.json's metric is quoted on (64k envs, 11x11 maze, 84x84 frames);
+# --workload c2 / c4 time the other two XWorld2D configurations of BASELINE.json with the same contract.
+WORKLOADS = {
+    "c3": dict(cfg=dict(height=11, width=11, n_goals=4, n_blocks=30, rules=1, out_h=84, out_w=84, max_steps=242,
+                        auto_reset=1, seed=1234, simulator_seed=1),
+               name="XWorld2D walls.json rules, 11x11 maze, 84x84x3 u8 obs, 65536 envs/GPU (BASELINE configs[2])",
+               map="11x11", side=84, rules="walls.json", max_steps=242, envs=65536),
+    "c2": dict(cfg=dict(height=7, width=7, n_goals=4, n_blocks=12, rules=0, out_h=84, out_w=84, auto_reset=1, seed=1234,
+                        simulator_seed=1),
+               name="XWorld2D navigation2d.json rules, 7x7 map, 84x84x3 u8 obs (BASELINE configs[1] at bench scale)",
+               map="7x7", side=84, rules="navigation2d.json", max_steps=0, envs=65536),
+    "c4": dict(cfg=dict(height=15, width=15, n_goals=4, n_blocks=56, rules=0, out_h=128, out_w=128, auto_reset=1, seed=1234,
+                        simulator_seed=1),
+               name="XWorld2D navigation2d.json rules, 15x15 map, 128x128x3 u8 obs, 32768 envs/GPU (BASELINE configs[3])",
+               map="15x15", side=128, rules="navigation2d.json", max_steps=0, envs=32768),
+}
+WORKLOAD = WORKLOADS["c3"]["cfg"]
+WORKLOAD_NAME = WORKLOADS["c3"]["name"]
 # 3*84*84 frame write + 121 grid bytes + 28 bytes of action/reward/game_over/agent state
 BYTES_PER_ENV_STEP = 3 * 84 * 84 + 11 * 11 + 28
+SIDE = 84
+
+
+def select_workload(key):
+    global WORKLOAD, WORKLOAD_NAME, BYTES_PER_ENV_STEP, SIDE
+    w = WORKLOADS[key]
+    WORKLOAD, WORKLOAD_NAME, SIDE = w["cfg"], w["name"], w["side"]
+    BYTES_PER_ENV_STEP = 3 * SIDE * SIDE + w["cfg"]["height"] * w["cfg"]["width"] + 28
+    return w
 
 
 def hbm_peak():
@@ -115,7 +139,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--envs-per-gpu", type=int, default=0, help="default: the workload's (65536; c4: 32768)")
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -123,9 +148,13 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     threads = os.cpu_count() or 1
-    config = {"workload": WORKLOAD_NAME, "map": "11x11", "obs": "84x84x3 u8 (B,G,R planes)", "rules": "walls.json",
-              "envs_per_gpu": args.envs_per_gpu, "auto_reset": True, "max_steps": 242, "actions": "iid uniform{0..3}",
-              "l2": "each step writes 1.39 GB of frames per GPU (>> 126 MB L2), so no L2 flush is needed",
+    wl = select_workload(args.workload)
+    if args.envs_per_gpu <= 0:
+        args.envs_per_gpu = wl["envs"]
+    config = {"workload": WORKLOAD_NAME, "map": wl["map"], "obs": "%dx%dx3 u8 (B,G,R planes)" % (SIDE, SIDE), "rules": wl["rules"],
+              "envs_per_gpu": args.envs_per_gpu, "auto_reset": True, "max_steps": wl["max_steps"], "actions": "iid uniform{0..3}",
+              "l2": "each step writes %.2f GB of frames per GPU (>> 126 MB L2), so no L2 flush is needed" % (
+                  args.envs_per_gpu * 3 * SIDE * SIDE / 1e9),
               "bytes_per_env_step": BYTES_PER_ENV_STEP}
 
     if args.impl == "reference":
@@ -235,7 +264,7 @@ def main():
                "what": "xw_step_hd: pinned host actions -> H2D, step+reset+render kernels, reward+game_over D2H, "
                        "stream sync; frames stay in HBM (consumer = co-located learner)"}
         if rank == 0 and world == 1:  # frames to the host too (PCIe-bound), reported beside it
-            hf = torch.empty((n, 3, 84, 84), dtype=torch.uint8).pin_memory()
+            hf = torch.empty((n, 3, SIDE, SIDE), dtype=torch.uint8).pin_memory()
             for i in range(2):
                 lib.xw_step_host(h, h_act[0].data_ptr(), 1, h_rew.data_ptr(), h_over.data_ptr(), hf.data_ptr())
             t0 = time.perf_counter()
@@ -244,7 +273,7 @@ def main():
                 lib.xw_step_host(h, h_act[i % 4].data_ptr(), 1, h_rew.data_ptr(), h_over.data_ptr(), hf.data_ptr())
             dt = time.perf_counter() - t0
             e2e["with_frames_to_host"] = {"value": n * k3 / dt, "unit": "env-steps/s",
-                                          "d2h_bytes_per_step": 8 * n + n * 3 * 84 * 84}
+                                          "d2h_bytes_per_step": 8 * n + n * 3 * SIDE * SIDE}
             del hf
 
     if rank != 0:
@@ -258,12 +287,13 @@ def main():
     tp = os.path.join(ROOT, "profiles", "render_traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            traffic = json.load(f).get("dram_bytes_per_launch") if (args.workload == "c3" and n == 65536) else None
     line = {
         "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
-        "roofline": {"bound": "hbm", "kernel": "k_render", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": {3: "k_render_sp", 1: "k_render_sb", 2: "k_render", 0: "k_render_generic"}.get(
+                         sim.render_kernel(), "k_render"), "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                      "kernel_ms": render_ms, "kernel_share_of_step": (render_ms / (ms / args.steps)) if render_ms else None,
                      "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n},

@@ -33,13 +33,22 @@ static int set_err(int code, const char* fmt, ...) {
     } while (0)
 
 // ------------------------------------------------------------------------------------ kernels
-// mode: list != NULL -> envs list[0..*count); else every env (optionally filtered by mask)
+// mode: list != NULL -> envs list[0..*count); else every env (optionally filtered by mask).
+// List mode (the per-step auto-reset queue: a few per cent of the envs) gives every env a WARP of its own and
+// runs it on lane 0: a reset is one long data-dependent instruction stream (maze DFS, rejection loops), and 32
+// of them in one warp serialise -- measured 490 us per step at C2 with one lane per env, against the
+// single-stream latency of a reset with one env per warp.  The lanes of a warp are not worth more than that here:
+// the stream has no 32-wide step.
 __global__ void __launch_bounds__(128) k_reset(XwDev d, const uint8_t* mask, const int32_t* list, const int32_t* count) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int e;
-    if (list) { if (i >= *count) return; e = list[i]; }
-    else { if (i >= d.n) return; e = i; if (mask && !mask[e]) return; }
-    xw_reset_env(d, e);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (list) {
+        const int n_warps = (gridDim.x * blockDim.x) >> 5, cnt = *count;
+        for (int w = i >> 5; w < cnt; w += n_warps)
+            if ((threadIdx.x & 31) == 0) xw_reset_env(d, list[w]);
+        return;
+    }
+    if (i >= d.n || (mask && !mask[i])) return;
+    xw_reset_env(d, i);
 }
 
 __global__ void __launch_bounds__(256) k_step(XwDev d, const int32_t* __restrict__ actions, int act_rep,
@@ -600,7 +609,8 @@ int xw_step(xw_sim* s, const int32_t* d_actions, int32_t act_rep, float* d_rewar
         k_step<<<(s->n + 255) / 256, 256, 0, st>>>(s->d, d_actions, act_rep, d_reward, d_game_over, s->step_parity);
         s->launches++;
         if (s->cfg.auto_reset) {
-            k_reset<<<(s->n + 127) / 128, 128, 0, st>>>(s->d, nullptr, s->d.reset_list, s->d.reset_count + s->step_parity);
+            const int want = (s->n + 3) / 4, cap = s->n_sms * 16;  // CTAs of 4 warps: one warp per queued env, grid-stride past the cap
+            k_reset<<<want < cap ? want : cap, 128, 0, st>>>(s->d, nullptr, s->d.reset_list, s->d.reset_count + s->step_parity);
             s->launches++;
         }
         s->step_parity ^= 1;
