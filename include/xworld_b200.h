@@ -179,6 +179,30 @@ int xw_num_steps(xw_sim* sim, int64_t* h_num_steps /* [n_envs] host */);
 int xw_get_field(xw_sim* sim, const char* name, void* h_out, size_t bytes);
 int xw_set_field(xw_sim* sim, const char* name, const void* h_in, size_t bytes);
 
+/* ---- teacher language channel, host side ------------------------------------------------------
+ * Replaces CFG.generate (python/context_free_grammar.py:166-188) over the grammars of the nine navigation tasks
+ * (games/xworld3d/tasks/XWorld3DNavTarget*.py, games/xworld/tasks/XWorldNav*.py: _define_grammar + the _bind calls
+ * of idle()).  The reference draws productions from Python's unseeded `random`; here draw i of a sentence is
+ * Philox(seed, env_id, episode, salt, i), so a sentence is a pure function of the query.  No device access: the
+ * caller reads the slots from the env's state ("task", "aux0", "aux1", "goal_name", "episode"; Simulator.sentences()
+ * in xworld_b200/simulator.py does it for a whole batch).  Returns the sentence length (0 = no sentence for this
+ * query) or a negative status. */
+enum { XW_SENT_START = 0, XW_SENT_CORRECT = 1, XW_SENT_WRONG = 2, XW_SENT_TIMEUP = 3 };
+typedef struct xw_sentence_query {
+    int32_t rules;      /* XW_RULES_NAV3D | XW_RULES_NAV2D */
+    int32_t task;       /* XW_T3_* | XW_T2_* */
+    int32_t kind;       /* XW_SENT_*: `S -> start | correct/finish | wrong | timeup` */
+    int32_t direction;  /* XW_T3_DIRECTION: 1 front, 2 behind, 3 left, 4 right (the engine's "aux1") */
+    const char* name1;  /* G / G1 / O: goal class name */
+    const char* name2;  /* G2 / T (Between tasks) */
+    const char* color;  /* C (XW_T2_COLOR_TARGET) */
+    uint64_t seed;      /* xw_config.seed */
+    int64_t env_id;     /* global env id (env_id_offset + index) */
+    uint32_t episode;   /* the env's "episode" field */
+    uint32_t salt;      /* 0, or the env's step count when an episode issues several commands (walls.json tasks) */
+} xw_sentence_query;
+int xw_sentence_compose(const xw_sentence_query* q, char* buf, size_t cap);
+
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t xw_launch_count(const xw_sim* sim);
 /* Which render kernel the handle uses (diagnostics, tests): 0 = generic per-byte kernel, 1 = plan compositor with

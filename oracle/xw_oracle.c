@@ -500,7 +500,7 @@ static int idle3d(const xw_config* cfg, xo_env* e, uint32_t ep, uint32_t att) {
         int nf = flood_fill(e, cell_of(e, mx, my), filled);
         if (nf == 0) { rc = 1; goto done; }
         place_agent(e, filled[xo_randbelow(xo_draw(seed, gid, ep, att, XO_SITE_TASK_AGENT, 0), (uint32_t)nf)]);
-        e->aux0 = g1; e->aux1 = mx; e->aux2 = my;
+        e->aux0 = g1 | (g2 << 4); e->aux1 = mx; e->aux2 = my; /* g1, g2: the bindings of G1, G2 (:59-62) */
     } else { /* XW_T3_DIRECTION, XWorld3DNavTargetDirection.py:29-76 */
         int nt = l_tiles(e, tiles);
         if (nt == 0) { rc = 1; goto done; }

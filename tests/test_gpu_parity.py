@@ -276,3 +276,48 @@ def test_step_hd_host_buffers_equal_device_path(synthetic_catalog):
             assert (h_rew.numpy().view(np.uint32) == r1.view(np.uint32)).all() and (h_over.numpy() == o1).all()
             torch.cuda.synchronize()
             assert (sim._screen.cpu().numpy() == f1).all()
+
+
+@pytest.mark.parametrize("name", ["c2_nav3d_7x7_84", "c3_nav2d_11x11_84"])
+def test_sentences_follow_the_task_state(name, backend_cls, synthetic_catalog):
+    """Simulator.sentences(): the teacher's sentence of every env agrees with the env's task state -- the bound goal
+    names / direction / colour are in it (navigation2d.json tasks: while the episode runs; walls.json: in the step
+    that issued the command), "Well done !" exactly where the step reached the goal."""
+    cfg = parity.make_cfg(name, auto_reset=1)
+    n = 2048
+    eng = backend_cls(cfg, synthetic_catalog, n)
+    eng.reset()
+    cat, sim = synthetic_catalog, eng.sim
+    seen = set()
+    for s in range(12):
+        if s:
+            eng.step(parity.actions_for(s, n, sim.get_num_actions()))
+        sent = sim.sentences()
+        f = {k: sim.get_field(k) for k in ("task", "stage", "event", "aux0", "aux1", "goal_name", "goal_icon", "steps_in_task")}
+        assert len(sent) == n
+        for e in range(0, n, 7):
+            t, a0 = int(f["task"][e]), int(f["aux0"][e])
+            nm = lambda g: cat.names[int(f["goal_name"][e][g])]
+            if cfg.rules == _abi.XW_RULES_NAV3D:
+                if f["stage"][e] == _abi.XW_STAGE_NAVIGATION:
+                    assert sent[e], e
+                    if t == 2:
+                        assert "between %s and %s" % (nm(a0 & 15), nm(a0 >> 4)) in sent[e]
+                    else:
+                        assert nm(a0) in sent[e].split() or nm(a0) in sent[e]
+                    if t == 3:
+                        assert {1: "front", 2: "behind", 3: "left", 4: "right"}[int(f["aux1"][e])] in sent[e]
+                    seen.add(t)
+            else:
+                if f["event"][e] == _abi.XW_EVENT_CORRECT_GOAL:
+                    assert sent[e] == "Well done !"
+                elif f["stage"][e] == _abi.XW_STAGE_NAVIGATION and f["steps_in_task"][e] == 0:
+                    assert nm(a0) in sent[e]
+                    if t == 2:
+                        assert cat.icon_meta[int(f["goal_icon"][e][a0])]["color"] in sent[e]
+                    seen.add(t)
+                else:
+                    assert sent[e] == ""
+    assert seen >= ({0, 1, 2, 3, 4} if cfg.rules == _abi.XW_RULES_NAV3D else {0, 2})
+    one = sim.sentences([5])
+    assert one == [sim.sentences()[5]]

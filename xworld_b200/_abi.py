@@ -88,11 +88,20 @@ def default_config(**kw):
 _LIB = None
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libxworld_b200.so")
 
+XW_SENT_START, XW_SENT_CORRECT, XW_SENT_WRONG, XW_SENT_TIMEUP = 0, 1, 2, 3
+
+
+class XwSentenceQuery(C.Structure):
+    _fields_ = [("rules", C.c_int32), ("task", C.c_int32), ("kind", C.c_int32), ("direction", C.c_int32),
+                ("name1", C.c_char_p), ("name2", C.c_char_p), ("color", C.c_char_p),
+                ("seed", C.c_uint64), ("env_id", C.c_int64), ("episode", C.c_uint32), ("salt", C.c_uint32)]
+
+
 # every symbol include/xworld_b200.h declares
 SYMBOLS = [
     "xw_config_init", "xw_create", "xw_destroy", "xw_last_error", "xw_reset", "xw_step", "xw_render",
     "xw_step_host", "xw_reset_host", "xw_step_hd", "xw_num_envs", "xw_num_actions", "xw_screen_dims",
-    "xw_frame_bytes", "xw_num_steps", "xw_get_field", "xw_set_field", "xw_launch_count", "xw_render_kernel",
+    "xw_frame_bytes", "xw_num_steps", "xw_get_field", "xw_set_field", "xw_launch_count", "xw_render_kernel", "xw_sentence_compose",
     "xw_enable_timing", "xw_render_ms",
 ]
 
@@ -143,6 +152,8 @@ def load():
     lib.xw_set_field.argtypes = [vp, C.c_char_p, vp, C.c_size_t]
     lib.xw_set_field.restype = C.c_int
     lib.xw_launch_count.argtypes = [vp]
+    lib.xw_sentence_compose.argtypes = [C.POINTER(XwSentenceQuery), C.c_char_p, C.c_size_t]
+    lib.xw_sentence_compose.restype = C.c_int
     lib.xw_render_kernel.argtypes = [vp]
     lib.xw_render_kernel.restype = C.c_int32
     lib.xw_launch_count.restype = i64

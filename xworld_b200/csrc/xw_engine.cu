@@ -14,6 +14,7 @@
 #include "xw_race.cuh"
 #include "xw_render.cuh"
 #include "xw_render_host.hpp"
+#include "xw_sentence.hpp"
 #include "xw_reset.cuh"
 #include "xw_step.cuh"
 
@@ -507,6 +508,39 @@ size_t xw_frame_bytes(const xw_sim* s) {
     int32_t h, w, c, k;
     xw_screen_dims(s, &h, &w, &c, &k);
     return (size_t)h * w * c * k * (s->cfg.game == XW_GAME_SIMPLE_RACE ? sizeof(float) : 1);
+}
+
+int xw_sentence_compose(const xw_sentence_query* q, char* buf, size_t cap) {
+    if (!q || !buf || cap == 0) return set_err(XW_ERR_INVALID_ARG, "null buffer");
+    if (q->rules != XW_RULES_NAV3D && q->rules != XW_RULES_NAV2D) return set_err(XW_ERR_INVALID_ARG, "unknown rules");
+    const bool nav3d = q->rules == XW_RULES_NAV3D;
+    if (q->task < 0 || q->task > (nav3d ? 4 : 3)) return set_err(XW_ERR_INVALID_ARG, "unknown task");
+    using namespace xw_sentence;
+    // (the tasks of walls.json that never leave idle in the reference commit have no command: DESIGN.md §4)
+    if (!nav3d && q->kind == XW_SENT_START && (q->task == XW_T2_NEAR || q->task == XW_T2_BETWEEN)) { buf[0] = 0; return 0; }
+    if (!nav3d && q->kind == XW_SENT_WRONG) { buf[0] = 0; return 0; }
+    Grammar g = task_grammar(q->rules, q->task, quoted(q->name1), quoted(q->color), "'east'");
+    if (nav3d && q->task == XW_T3_BETWEEN) g.add("G2", quoted(q->name2));
+    if (!nav3d && q->task == XW_T2_BETWEEN) g.add("T", quoted(q->name2));
+    const char* kinds3[4] = {"start", "correct", "wrong", "timeup"};
+    const char* kinds2[4] = {"start", "finish", "finish", "timeup"};
+    if (q->kind < 0 || q->kind > 3 || !g.bind("S", nav3d ? kinds3[q->kind] : kinds2[q->kind])) return set_err(XW_ERR_INVALID_ARG, "unknown sentence kind");
+    if (q->kind == XW_SENT_START) {
+        if (!q->name1 || !q->name1[0]) return set_err(XW_ERR_INVALID_ARG, "start sentence needs a goal name");
+        if (nav3d && q->task == XW_T3_DIRECTION) {
+            const char* dirs[5] = {nullptr, "FRONT", "BEHIND", "LEFT", "RIGHT"};
+            if (q->direction < 1 || q->direction > 4 || !g.bind("P", dirs[q->direction])) return set_err(XW_ERR_INVALID_ARG, "direction must be 1..4");
+        }
+        if (((nav3d && q->task == XW_T3_BETWEEN)) && (!q->name2 || !q->name2[0])) return set_err(XW_ERR_INVALID_ARG, "Between needs two goal names");
+        if (!nav3d && q->task == XW_T2_COLOR_TARGET && (!q->color || !q->color[0])) return set_err(XW_ERR_INVALID_ARG, "ColorTarget needs a colour");
+    }
+    uint32_t i = 0;
+    auto draw = [&]() { return xw_draw(q->seed, q->env_id, q->episode, 0, XW_SITE_SENTENCE, ((q->salt & 0x3fffu) << 4) + (i++ & 15u)); };
+    std::string out;
+    if (!generate(g, "S", draw, &out)) return set_err(XW_ERR_INVALID_ARG, "ungrounded nonterminal");
+    if (out.size() + 1 > cap) return set_err(XW_ERR_INVALID_ARG, "sentence buffer too small (%zu bytes needed)", out.size() + 1);
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return (int)out.size();
 }
 
 int64_t xw_launch_count(const xw_sim* s) { return s->launches; }

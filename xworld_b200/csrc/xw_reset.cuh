@@ -327,7 +327,7 @@ XW_HD bool xw_idle3d(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, int
         int nf = xw_bfs(c, obst, mid, mid, -1, order);
         if (nf == 0) return false;
         c.agent = order[xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_TASK_AGENT, 0), (uint32_t)nf)];
-        o.aux0 = g1; o.aux1 = mx; o.aux2 = my;
+        o.aux0 = g1 | (g2 << 4); o.aux1 = mx; o.aux2 = my;  // (g2: only the sentence channel needs it, xw_sentence.hpp)
     } else {
         int target = g1, referent = g2;
         int tx = a % W, ty = a / W;
