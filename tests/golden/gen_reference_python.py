@@ -9,13 +9,13 @@ What is executed unmodified (loaded from /root/reference, never copied):
     python/maze2d.py, python/py_util.py                maze DFS, bfs, flood_fill
     games/xworld3d/tasks/xworld3d_task.py + XWorld3DNav{Target,TargetNear,TargetBetween,
         TargetDirection,TargetAvoid}.py                navigation2d.json task set
+    python/context_free_grammar.py                     CFG: the teacher's sentences
     games/xworld/tasks/xworld_task.py + XWorldNav{Target,Near,ColorTarget,Between}.py   walls.json
 
 What the harness supplies instead of the C++ host (and cites):
     * Python-2 -> 3 source fix-ups at load time: integer `/` on three lines (maze2d.py:89,
       xworld_env.py:129-130), dict.iteritems(), dict.keys() used as a list (xworld_env.py:292).
     * py_gflags.get_flag (python/py_init.cpp:37-58) -> a dict of the flags.
-    * context_free_grammar.CFG -> inert stub (sentences are out of scope).
     * the `random` module -> ReplayRandom: every call site the reference draws from is mapped onto the
       oracle's Philox substream of the same name (oracle/xw_oracle.h XO_SITE_*), with the sequence
       put in a canonical order first wherever the reference's order is a CPython set/dict order.
@@ -44,7 +44,12 @@ FLAGS = {"visible_radius": 0, "curriculum": 0, "task_mode": "lang_acquisition", 
 
 
 # ----------------------------------------------------------------------------- ReplayRandom
+SITE_SENTENCE = 11  # xworld_b200/csrc/xw_sentence.hpp
+
+
 class Ctx(object):
+    sent_i = 0
+    sent_salt = 0
     seed = 0
     env_gid = 0
     episode = 0
@@ -117,6 +122,12 @@ class ReplayRandom(types.ModuleType):
             v = seq[oracle.randbelow(self._u(oracle.SITE_GOAL_ASSET, Ctx.goal_no), len(seq))]
             Ctx.goal_no += 1
             return v
+        if caller == "value":  # RHS.value (context_free_grammar.py:41-49): the i-th production draw of this sentence
+            i = Ctx.sent_i
+            Ctx.sent_i += 1
+            assert i < 16
+            u = oracle.draw(Ctx.seed, Ctx.env_gid, Ctx.episode, 0, SITE_SENTENCE, ((Ctx.sent_salt & 0x3fff) << 4) + i)
+            return seq[oracle.randbelow(u, len(seq))]
         if caller == "idle":
             cls = f1.f_locals["self"].__class__.__name__
             Ctx.idle_calls += 1
@@ -164,21 +175,11 @@ def load_reference_python(dim, n_goals, n_blocks):
     gf = types.ModuleType("py_gflags")
     gf.get_flag = lambda k: FLAGS[k]
     sys.modules["py_gflags"] = gf
-    cfgm = types.ModuleType("context_free_grammar")
-
-    class CFG(object):
-        def __init__(self, *a, **k): pass
-        def bind(self, *a): pass
-        def generate(self, *a): return ""
-        def generate_all(self, *a): return []
-        def set_production_rule(self, *a): pass
-        def total_possible_sentences(self): return 0
-        def show(self): pass
-    cfgm.CFG = CFG
-    sys.modules["context_free_grammar"] = cfgm
     saved = sys.modules.get("random")
     sys.modules["random"] = rnd
     try:
+        # the reference's own CFG class (RHS.value draws through ReplayRandom.choice, site SENTENCE)
+        mk("context_free_grammar", "python/context_free_grammar.py", [(r"\.iteritems\(\)", ".items()")])
         mk("py_util", "python/py_util.py")
         mk("maze2d", "python/maze2d.py", [(r"\(X \+ 1\) / 2, \(Y \+ 1\) / 2", "(X + 1) // 2, (Y + 1) // 2")])
         mk("xworld_env", "games/xworld/maps/xworld_env.py", [
@@ -263,11 +264,14 @@ class Host(object):
         env.update_agent_action_success_from_cpp(success)
         env.update_game_event_from_cpp(game_event)
         Ctx.idle_calls = 0
+        Ctx.sent_i = 0
+        Ctx.sent_salt = 0 if self.rules == 0 else Ctx.step_no  # walls.json tasks issue several commands per episode
         ret = getattr(task, stage)()
         if env.env_changed():
             self.pull_entities()  # XWorldSimulator::update_environment -> XWorld::reset(false)
         event = task.get_event()
         assert len(ret) == 3
+        self.last_sentence = ret[2]
         return ret[0], float(ret[1]), event
 
     def snapshot(self):
@@ -353,6 +357,8 @@ def run_case(mods, cat, rules, dim, n_goals, n_blocks, seed, simulator_seed, env
         rec["task"] = t
         rec["reset"] = host.snapshot()
         if rules == 0:
+            rec["reset_sentence"] = host.last_sentence
+        if rules == 0:
             rec.update(host.task_record(t, task))
         steps = []
         num_steps = 0
@@ -374,6 +380,7 @@ def run_case(mods, cat, rules, dim, n_goals, n_blocks, seed, simulator_seed, env
             r, ev = teach2d(False, "")
             rec["reset_stage"] = stage
             rec["reset_task"] = t
+            rec["reset_sentence"] = host.last_sentence
         for s in range(n_steps):
             a = int(arng.randint(0, 4))
             num_steps += 1
@@ -385,7 +392,7 @@ def run_case(mods, cat, rules, dim, n_goals, n_blocks, seed, simulator_seed, env
             else:
                 r, ev = teach2d(ok, game_event)
             ag = host.agent()
-            steps.append({"a": a, "ok": int(ok), "r": r, "ev": ev, "stage": stage, "task": t,
+            steps.append({"a": a, "ok": int(ok), "r": r, "ev": ev, "stage": stage, "task": t, "sent": host.last_sentence,
                           "agent": [int(ag["loc"][0]), int(ag["loc"][1])]})
             if rules == 0 and stage == "terminal" and s + 3 < n_steps and len(steps) > 2 and steps[-2]["stage"] == "terminal" \
                     and steps[-3]["stage"] == "terminal":

@@ -66,3 +66,48 @@ def test_sentence_is_a_pure_function_of_the_query_and_errors_are_statuses():
     assert compose(lib, buf, rules=_abi.XW_RULES_NAV3D, task=9, kind=_abi.XW_SENT_START, name1="apple")[0] < 0
     small = C.create_string_buffer(4)
     assert compose(lib, small, **kw)[0] < 0
+
+
+def test_sentences_match_the_reference_python_sentence_by_sentence(synthetic_catalog):
+    """The reference's own task code and CFG class, run with its `random` replayed from the same Philox substreams
+    (tests/golden/gen_reference_python.py), against sentence_for_state over the oracle's state: the same sentence at
+    reset and after every step -- which sentence is due (command / "Well done !" / nothing), its slots and its
+    productions."""
+    import ctypes as C
+    import numpy as np
+    import oracle
+    from xworld_b200.simulator import sentence_for_state
+    lib = _abi.load()
+    olib = oracle.lib()
+    with gzip.open(os.path.join(HERE, "golden", "refpy_traces.json.gz")) as f:
+        tr = json.loads(f.read().decode())
+    n_cmp = n_nonempty = 0
+    kinds = set()
+    for case in tr["cases"]:
+        D, G = case["dim"], case["n_goals"]
+        cfg = _abi.default_config(height=D, width=D, n_goals=G, n_blocks=case["n_blocks"], rules=case["rules"],
+                                  seed=case["seed"], simulator_seed=case["simulator_seed"])
+        for env in case["envs"]:
+            cfg.env_id_offset = env["env_gid"]
+            o = oracle.Oracle(cfg, synthetic_catalog, 1)
+            e = o.envs[0]
+
+            def current():
+                st = dict(task=e.task, stage=e.stage, event=e.event, aux0=e.aux0, aux1=e.aux1, goal_name=list(e.goal_name),
+                          goal_icon=list(e.goal_icon), episode=e.episode, steps_in_task=e.steps_in_task, num_steps=e.num_steps)
+                return sentence_for_state(lib, cfg, synthetic_catalog, env["env_gid"], st)
+
+            for ep in env["episodes"]:
+                o.reset()
+                where = (case["tag"], env["env_gid"], ep["episode"])
+                assert current() == ep["reset_sentence"], (where, current(), ep["reset_sentence"])
+                for i, s in enumerate(ep["steps"]):
+                    r, ov = C.c_float(), C.c_int32()
+                    assert olib.xo_step(C.byref(cfg), C.byref(o.cat_c), C.byref(e), s["a"], 1, C.byref(r), C.byref(ov)) == 0
+                    got = current()
+                    # (after the episode has ended the reference's terminal stage says nothing)
+                    assert got == s["sent"], (where, i, got, s["sent"], s["stage"], s["ev"])
+                    n_cmp += 1
+                    n_nonempty += bool(s["sent"])
+                    kinds.add((case["rules"], s["task"], s["sent"][:4]))
+    assert n_cmp > 9000 and n_nonempty > 5000 and len(kinds) > 40

@@ -51,6 +51,43 @@ def rules_from_conf(conf):
     raise RuntimeError("conf has no navigation task group this engine implements: %s" % sorted(groups))
 
 
+SENTENCE_FIELDS = ("task", "stage", "event", "aux0", "aux1", "goal_name", "goal_icon", "episode", "steps_in_task", "num_steps")
+
+
+def sentence_for_state(lib, cfg, catalog, env_id, st):
+    """The teacher's sentence of one env from its state fields (SENTENCE_FIELDS): which sentence the last teach()
+    produced (see Simulator.sentences) and its slots -- goal names, direction, colour -- then xw_sentence_compose."""
+    q = _abi.XwSentenceQuery(rules=cfg.rules, task=int(st["task"]), kind=_abi.XW_SENT_START, direction=0, name1=None, name2=None,
+                             color=None, seed=cfg.seed, env_id=env_id, episode=int(st["episode"]) & 0xffffffff, salt=0)
+    stage, event, a0 = int(st["stage"]), int(st["event"]), int(st["aux0"])
+    name = lambda g: catalog.names[int(st["goal_name"][g])].encode()
+    if cfg.rules == _abi.XW_RULES_NAV3D:
+        if stage == _abi.XW_STAGE_IDLE or (stage == _abi.XW_STAGE_TERMINAL and event == _abi.XW_EVENT_NONE):
+            return ""
+        if stage == _abi.XW_STAGE_TERMINAL:  # the step that ended the episode (xworld3d_task.py:456-482)
+            q.kind = {_abi.XW_EVENT_CORRECT_GOAL: _abi.XW_SENT_CORRECT, _abi.XW_EVENT_WRONG_GOAL: _abi.XW_SENT_WRONG,
+                      _abi.XW_EVENT_TIME_UP: _abi.XW_SENT_TIMEUP}[event]
+        elif q.task == 2:    # XW_T3_BETWEEN: G1, G2
+            q.name1, q.name2 = name(a0 & 15), name(a0 >> 4)
+        else:                # Target / Near / Direction / Avoid: G (Direction: the referent, P = "aux1")
+            q.name1 = name(a0)
+            q.direction = int(st["aux1"]) if q.task == 3 else 0
+    else:
+        if event == _abi.XW_EVENT_CORRECT_GOAL:
+            q.kind = _abi.XW_SENT_CORRECT
+        elif stage == _abi.XW_STAGE_NAVIGATION and int(st["steps_in_task"]) == 0:
+            q.name1 = name(a0)
+            q.color = catalog.icon_meta[int(st["goal_icon"][a0])]["color"].encode()
+            q.salt = int(st["num_steps"]) & 0x3fff
+        else:
+            return ""
+    buf = C.create_string_buffer(256)
+    rc = lib.xw_sentence_compose(C.byref(q), buf, len(buf))
+    if rc < 0:
+        raise RuntimeError("xworld_b200 error %d: %s" % (rc, lib.xw_last_error().decode()))
+    return buf.value.decode()
+
+
 class Simulator(object):
     def __init__(self, name, cfg, catalog, n_envs, device):
         self._lib = _abi.load()
@@ -277,47 +314,17 @@ class Simulator(object):
         """The sentence the teacher's last teach() call produced, per env (XWorldSimulator::define_state_specs,
         xworld_simulator.cpp:486-493; CFG.generate over the task grammars, see include/xworld_b200.h):
           navigation2d.json tasks: the command while the episode runs (XWorld3DNavTarget*.py return self.sentence
-            from idle() and from every navigation_reward()), "" after it has ended;
+            from idle() and from every navigation_reward()), "Well done !" / "Wrong !" / "Time up ." in the step that
+            ends it (xworld3d_task.py:456-482), "" afterwards;
           walls.json tasks: the command in the step whose teach() ran idle() (XWorldNav*.py), "Well done !" in the
             step that reached the goal (xworld_task.py:215-221), "" otherwise.
         One read-back of the small state fields for the whole batch; strings are built on the host."""
         if self.cfg.game != _abi.XW_GAME_XWORLD:
             raise RuntimeError("sentences(): xworld only")
-        f = {k: self.get_field(k) for k in ("task", "stage", "event", "aux0", "aux1", "goal_name", "goal_icon", "episode",
-                                            "steps_in_task", "num_steps")}
-        nav3d = self.cfg.rules == _abi.XW_RULES_NAV3D
-        buf = C.create_string_buffer(256)
-        out = []
-        for e in (range(self.n_envs) if envs is None else envs):
-            q = _abi.XwSentenceQuery(rules=self.cfg.rules, task=int(f["task"][e]), kind=_abi.XW_SENT_START, direction=0,
-                                     name1=None, name2=None, color=None, seed=self.cfg.seed,
-                                     env_id=self.cfg.env_id_offset + e, episode=int(f["episode"][e]) & 0xffffffff, salt=0)
-            stage, event, a0 = int(f["stage"][e]), int(f["event"][e]), int(f["aux0"][e])
-            name = lambda g: self.catalog.names[int(f["goal_name"][e][g])].encode()
-            if nav3d:
-                if stage == _abi.XW_STAGE_IDLE or (stage == _abi.XW_STAGE_TERMINAL and event == _abi.XW_EVENT_NONE):
-                    out.append("")
-                    continue
-                if q.task == 2:      # XW_T3_BETWEEN: G1, G2
-                    q.name1, q.name2 = name(a0 & 15), name(a0 >> 4)
-                else:                # Target / Near / Direction / Avoid: G (Direction: the referent, P = "aux1")
-                    q.name1 = name(a0)
-                    q.direction = int(f["aux1"][e]) if q.task == 3 else 0
-            else:
-                if event == _abi.XW_EVENT_CORRECT_GOAL:
-                    q.kind = _abi.XW_SENT_CORRECT
-                elif stage == _abi.XW_STAGE_NAVIGATION and int(f["steps_in_task"][e]) == 0:
-                    q.name1 = name(a0)
-                    q.color = self.catalog.icon_meta[int(f["goal_icon"][e][a0])]["color"].encode()
-                    q.salt = int(f["num_steps"][e]) & 0x3fff
-                else:
-                    out.append("")
-                    continue
-            rc = self._lib.xw_sentence_compose(C.byref(q), buf, len(buf))
-            if rc < 0:
-                raise RuntimeError("xworld_b200 error %d: %s" % (rc, self._lib.xw_last_error().decode()))
-            out.append(buf.value.decode())
-        return out
+        f = {k: self.get_field(k) for k in SENTENCE_FIELDS}
+        return [sentence_for_state(self._lib, self.cfg, self.catalog, self.cfg.env_id_offset + e,
+                                   {k: f[k][e] for k in SENTENCE_FIELDS})
+                for e in (range(self.n_envs) if envs is None else envs)]
 
     # ------------------------------------------------------------------ state access
     def get_field(self, name):
