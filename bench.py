@@ -246,8 +246,8 @@ def main():
         h_act = [torch.randint(0, 4, (n,), dtype=torch.int32).pin_memory() for _ in range(4)]
         h_rew = torch.zeros(n, dtype=torch.float32).pin_memory()
         h_over = torch.zeros(n, dtype=torch.int32).pin_memory()
-        k2 = max(10, args.steps // 4)
-        for i in range(3):
+        k2 = max(10, args.steps)  # the same K steps as the device-resident measurement
+        for i in range(5):
             lib.xw_step_hd(h, h_act[i % 4].data_ptr(), 1, h_rew.data_ptr(), h_over.data_ptr(), frames.data_ptr())
         barrier()
         t0 = time.perf_counter()

@@ -96,7 +96,7 @@ struct xw_sim {
     xw_config cfg;
     int n = 0, device = 0;
     cudaStream_t own_stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t ev_step = nullptr;
+    cudaEvent_t ev_step = nullptr, ev_copy = nullptr;
     int64_t launches = 0;
     int step_parity = 0;
     // xworld
@@ -483,7 +483,7 @@ void xw_destroy(xw_sim* s) {
     if (s->h_over) cudaFreeHost(s->h_over);
     if (s->h_rew) cudaFreeHost(s->h_rew);
     for (auto ev : s->ev) cudaEventDestroy(ev);
-    if (s->copy_stream) { cudaStreamDestroy(s->copy_stream); cudaEventDestroy(s->ev_step); }
+    if (s->copy_stream) { cudaStreamDestroy(s->copy_stream); cudaEventDestroy(s->ev_step); cudaEventDestroy(s->ev_copy); }
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
 }
@@ -772,9 +772,14 @@ int xw_step_host(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float* h_
 }
 
 static bool is_pinned(const void* p) {
+    static thread_local const void* seen[4] = {nullptr, nullptr, nullptr, nullptr};  // (a trainer passes the same buffers every step)
+    for (const void* q : seen) if (q == p) return true;
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return a.type == cudaMemoryTypeHost;
+    if (a.type != cudaMemoryTypeHost) return false;
+    static thread_local int next = 0;
+    seen[next++ & 3] = p;
+    return true;
 }
 
 // Host actions in, host reward / game_over out, frames stay on the device.  Page-locked caller buffers are used
@@ -798,6 +803,7 @@ int xw_step_hd(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float* h_re
         if (!s->copy_stream) {
             CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
             CUDA_TRY(cudaEventCreateWithFlags(&s->ev_step, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&s->ev_copy, cudaEventDisableTiming));
         }
         cs = s->copy_stream;
         CUDA_TRY(cudaEventRecord(s->ev_step, st));
@@ -808,7 +814,8 @@ int xw_step_hd(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float* h_re
     if (split) {
         rc = launch_render(s, d_frames, st);
         if (rc) return rc;
-        CUDA_TRY(cudaStreamSynchronize(cs));
+        CUDA_TRY(cudaEventRecord(s->ev_copy, cs));  // one host wait for both streams
+        CUDA_TRY(cudaStreamWaitEvent(st, s->ev_copy, 0));
     }
     CUDA_TRY(cudaStreamSynchronize(st));
     if (!pin_r) memcpy(h_reward, s->h_rew, sizeof(float) * s->n);
