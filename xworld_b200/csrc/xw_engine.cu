@@ -35,17 +35,15 @@ static int set_err(int code, const char* fmt, ...) {
 
 // ------------------------------------------------------------------------------------ kernels
 // mode: list != NULL -> envs list[0..*count); else every env (optionally filtered by mask).
-// List mode (the per-step auto-reset queue: a few per cent of the envs) gives every env a WARP of its own and
-// runs it on lane 0: a reset is one long data-dependent instruction stream (maze DFS, rejection loops), and 32
-// of them in one warp serialise -- measured 490 us per step at C2 with one lane per env, against the
-// single-stream latency of a reset with one env per warp.  The lanes of a warp are not worth more than that here:
-// the stream has no 32-wide step.
+// List mode (the per-step auto-reset queue: a few per cent of the envs) gives every env a WARP of its own: a
+// reset is one long data-dependent instruction stream (maze DFS, rejection loops), and 32 different ones in one
+// warp serialise -- measured 490 us per step at C2 with one lane per env.  The lanes of the warp evaluate the
+// episode's attempts side by side (xw_reset_env_warp).
 __global__ void __launch_bounds__(128) k_reset(XwDev d, const uint8_t* mask, const int32_t* list, const int32_t* count) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (list) {
         const int n_warps = (gridDim.x * blockDim.x) >> 5, cnt = *count;
-        for (int w = i >> 5; w < cnt; w += n_warps)
-            if ((threadIdx.x & 31) == 0) xw_reset_env(d, list[w]);
+        for (int w = i >> 5; w < cnt; w += n_warps) xw_reset_env_warp(d, list[w]);
         return;
     }
     if (i >= d.n || (mask && !mask[i])) return;
