@@ -118,7 +118,15 @@ typedef struct {
     int32_t race_random;      /* only 0 implemented */
     int32_t difficulty;       /* 0 easy, 1 hard */
     float reward_scale;
-    int32_t reserved[8];
+    /* ---- xworld curriculum (XWorldNav.py:36-56, xworld_env.py:103-110) ---- */
+    float curriculum;         /* --curriculum (teacher.cpp:25; read as a float, py_simulator.cpp:127): 0 = off = the
+                                 last level's map every episode; > 0 = per-env level schedule: a (3+level)-sided
+                                 world with num_goals_seq / num_blocks_seq[level] entities inside the 8x8 map, padded
+                                 with bricks, one level up when the lowest per-task success rate over the last 200
+                                 results reaches this threshold.  navigation2d.json rules, 8x8 map only */
+    int32_t curriculum_check_period; /* XWorldEnv.curriculum_check_period (xworld_env.py:58); 0 = the reference's 100 */
+    int32_t start_level;      /* XWorldNav(start_level=...) (XWorldNav.py:8), 0..5 */
+    int32_t reserved[5];
 } xw_config;
 
 typedef struct xw_sim xw_sim; /* opaque handle: one batch of n_envs environments on one GPU */
@@ -175,6 +183,8 @@ int xw_num_steps(xw_sim* sim, int64_t* h_num_steps /* [n_envs] host */);
  * "target_mask","aux0","aux1","aux2" u8[n]; "goal_x","goal_y" u8[n][XW_MAX_GOALS];
  * "goal_icon" i32[n][XW_MAX_GOALS]; "steps_in_task","num_steps","episode","n_success",
  * "n_failure","success_steps","minstd","error" i32[n].
+ * Curriculum (only when cfg.curriculum > 0): "level" u8[n] (XWorldEnv.dump_curriculum_progress, xworld_env.py:62-63),
+ * "check_counter" i32[n], "win_len","win_sum" u8[n][5] (length / successes of each task class's result window).
  * Race: "pos_x","pos_y","angle" f32[n], "steps" i32[n], "state" f32[n][4]. */
 int xw_get_field(xw_sim* sim, const char* name, void* h_out, size_t bytes);
 int xw_set_field(xw_sim* sim, const char* name, const void* h_in, size_t bytes);

@@ -43,6 +43,9 @@ class XoEnv(C.Structure):
         ("minstd", C.c_uint32),
         ("error", C.c_int32),
         ("env_gid", C.c_int64),
+        ("level", C.c_int32), ("dim", C.c_int32), ("check_counter", C.c_int32),
+        ("seq_len", C.c_int32 * 5),
+        ("seq", (C.c_uint8 * 200) * 5),
     ]
 
 
@@ -177,6 +180,14 @@ class Oracle(object):
             return np.array([list(e.goal_icon) for e in self.envs], np.int32)
         if name == "facing":
             return np.full(n, 1, np.uint8)
+        if name == "level":
+            return np.array([e.level for e in self.envs], np.uint8)
+        if name == "check_counter":
+            return np.array([e.check_counter for e in self.envs], np.int32)
+        if name == "win_len":
+            return np.array([list(e.seq_len) for e in self.envs], np.uint8)
+        if name == "win_sum":
+            return np.array([[sum(e.seq[t][:e.seq_len[t]]) for t in range(5)] for e in self.envs], np.uint8)
         if name in U8_FIELDS:
             return np.array([getattr(e, name) for e in self.envs], np.uint8)
         if name in I32_FIELDS:

@@ -183,15 +183,22 @@ static int count_free(const xo_env* e) {
 static int gen_map(const xw_config* cfg, const xw_catalog* cat, xo_env* e, uint32_t ep, uint32_t att) {
     const uint64_t seed = cfg->seed;
     const int64_t gid = e->env_gid;
-    const int D = cfg->height;
-    e->H = cfg->height; e->W = cfg->width; e->n_goals = cfg->n_goals;
+    /* XWorldNav.py:36-58: curriculum == 0 -> the last level's numbers (cfg); else compute(current_level) */
+    static const int num_goals_seq[6] = {2, 2, 2, 4, 4, 4}, num_blocks_seq[6] = {0, 3, 6, 9, 12, 16};
+    const int curr = cfg->curriculum != 0;
+    const int D = curr ? 3 + e->level : cfg->height;                 /* min_dim + current_level */
+    const int n_goals = curr ? num_goals_seq[e->level] : cfg->n_goals;
+    const int n_blocks = curr ? num_blocks_seq[e->level] : cfg->n_blocks;
+    e->H = D; e->W = D; e->n_goals = n_goals; e->dim = D;            /* set_dims(current_dim, current_dim) */
     if (cfg->height != cfg->width) return XW_ERR_INVALID_ARG; /* "only support square maps" maze2d.py:78 */
+    memset(e->goal_x, 0, sizeof e->goal_x); memset(e->goal_y, 0, sizeof e->goal_y);
+    memset(e->goal_icon, 0, sizeof e->goal_icon); memset(e->goal_name, 0, sizeof e->goal_name);
     /* goal names: random.shuffle(goal_names); set_entity(name=goal_names.pop()) XWorldNav.py:60-62 */
     int n = cat->n_names;
-    if (n < cfg->n_goals) return XW_ERR_INVALID_ARG;
+    if (n < n_goals) return XW_ERR_INVALID_ARG;
     int* names = (int*)malloc(sizeof(int) * (size_t)n);
     for (int i = 0; i < n; ++i) names[i] = i;
-    for (int k = 0; k < cfg->n_goals; ++k) {
+    for (int k = 0; k < n_goals; ++k) {
         int i = n - 1 - k;
         if (i >= 1) {
             uint32_t j = xo_randbelow(xo_draw(seed, gid, ep, att, XO_SITE_NAMES, (uint32_t)k), (uint32_t)i + 1);
@@ -207,12 +214,12 @@ static int gen_map(const xw_config* cfg, const xw_catalog* cat, xo_env* e, uint3
     for (int y = 0; y < D; ++y)
         for (int x = 0; x < D; ++x)
             if (maze[y * D + x] == '#') blocks[nb++] = y * D + x;
-    if (nb < cfg->n_blocks) return XW_ERR_INVALID_ARG; /* "too many blocks for a valid maze" :443 */
+    if (nb < n_blocks) return XW_ERR_INVALID_ARG; /* "too many blocks for a valid maze" :443 */
     /* "first remove all maze blocks from the available set" :427-431 : mark them temporarily */
     memset(e->grid, XW_CELL_EMPTY, sizeof e->grid);
     for (int i = 0; i < nb; ++i) e->grid[blocks[i]] = 0xff;
     /* entities in creation order: goals, blocks, agent (XWorldNav.py:61-67) */
-    for (int k = 0; k < cfg->n_goals; ++k) { /* set_property -> loc, asset_path  xworld_env.py:187-199 */
+    for (int k = 0; k < n_goals; ++k) { /* set_property -> loc, asset_path  xworld_env.py:187-199 */
         int nf = count_free(e);
         if (nf == 0) return XW_ERR_INVALID_ARG;
         int c = nth_free(e, (int)xo_randbelow(xo_draw(seed, gid, ep, att, XO_SITE_GOAL_LOC, (uint32_t)k), (uint32_t)nf));
@@ -223,7 +230,7 @@ static int gen_map(const xw_config* cfg, const xw_catalog* cat, xo_env* e, uint3
     }
     /* blocks: random.shuffle(blocks); e.loc = blocks.pop()  :424,444 */
     int block_cells[XW_MAX_DIM * XW_MAX_DIM];
-    for (int k = 0; k < cfg->n_blocks; ++k) {
+    for (int k = 0; k < n_blocks; ++k) {
         int i = nb - 1 - k;
         if (i >= 1) {
             uint32_t j = xo_randbelow(xo_draw(seed, gid, ep, att, XO_SITE_BLOCKS, (uint32_t)k), (uint32_t)i + 1);
@@ -240,7 +247,7 @@ static int gen_map(const xw_config* cfg, const xw_catalog* cat, xo_env* e, uint3
     }
     /* "add back the unused grids" :450 */
     for (int i = 0; i < nb; ++i) e->grid[blocks[i]] = XW_CELL_EMPTY;
-    for (int k = 0; k < cfg->n_blocks; ++k) e->grid[block_cells[k]] = XW_CELL_BLOCK;
+    for (int k = 0; k < n_blocks; ++k) e->grid[block_cells[k]] = XW_CELL_BLOCK;
     e->agent_yaw = 1.5707963; /* Entity default yaw, xworld_env.py:42 (not randomised when visible_radius==0) */
     return 0;
 }
@@ -557,6 +564,58 @@ static void idle2d(const xw_config* cfg, const xw_catalog* cat, xo_env* e) {
 /* Teacher::teach for one env                                                                 */
 /* ------------------------------------------------------------------------------------------ */
 
+/* XWorld3DTask.__record_result (xworld3d_task.py:129-133) -> XWorldEnv.record_environment_usage (xworld_env.py:60-67):
+ * the env keeps a reference to the task's list, so the list itself is the usage record. */
+static void record_result(const xw_config* cfg, xo_env* e, int res) {
+    if (cfg->curriculum == 0) return; /* nothing reads the record then */
+    uint8_t* seq = e->seq[e->task];
+    int n = e->seq_len[e->task];
+    /* success_seq.append(res); if len > performance_window_size: pop(0) -- the oldest entry leaves first here,
+     * because the array holds exactly 200 */
+    if (n == 200) { memmove(seq, seq + 1, 199); n = 199; }
+    seq[n++] = (uint8_t)res;
+    e->seq_len[e->task] = n;
+}
+
+/* XWorldEnv.get_current_usage (xworld_env.py:103-110) */
+static double current_usage(const xw_config* cfg, xo_env* e) {
+    const int period = cfg->curriculum_check_period > 0 ? cfg->curriculum_check_period : 100;
+    e->check_counter += 1;
+    int any = 0;
+    for (int t = 0; t < 5; ++t) any |= e->seq_len[t] > 0;
+    if (e->check_counter < period || !any) return 0;
+    double usage = 0; int first = 1;
+    for (int t = 0; t < 5; ++t) {
+        if (e->seq_len[t] == 0) continue;
+        int sum = 0;
+        for (int i = 0; i < e->seq_len[t]; ++i) sum += e->seq[t][i];
+        double u = sum / (double)e->seq_len[t];             /* sum(l) / float(len(l)) */
+        if (first || u < usage) usage = u;
+        first = 0;
+    }
+    e->check_counter = 0;
+    return usage;
+}
+
+/* cpp_get_entities (xworld_env.py:352-366): entity locations move by (offset_w, offset_h) = ((max - dim) / 2, same)
+ * and __padding_walls (:454-473) fills the rest of the max_height x max_width map with bricks. */
+static void embed_world(const xw_config* cfg, xo_env* e) {
+    const int D = e->dim, M = cfg->height, off = (M - D) / 2;
+    if (D == M) return;
+    uint8_t inner[XW_MAX_DIM * XW_MAX_DIM];
+    memcpy(inner, e->grid, sizeof inner);
+    memset(e->grid, XW_CELL_EMPTY, sizeof e->grid);
+    for (int y = 0; y < M; ++y)
+        for (int x = 0; x < M; ++x) {
+            int ix = x - off, iy = y - off;
+            e->grid[y * M + x] = (ix >= 0 && ix < D && iy >= 0 && iy < D) ? inner[iy * D + ix] : XW_CELL_BLOCK;
+        }
+    e->H = e->W = M;
+    e->agent_x += off; e->agent_y += off;
+    for (int g = 0; g < e->n_goals; ++g) { e->goal_x[g] += off; e->goal_y[g] += off; }
+    if (e->task == XW_T3_BETWEEN) { e->aux1 += off; e->aux2 += off; } /* the middle cell is kept in map coordinates */
+}
+
 /* One teach() after the agent's move(s).  collided = cell code of the blocking item (0 = none).
  * Returns the teacher reward as the double the reference accumulates (simulator.h:322). */
 int xo_teach(const xw_config* cfg, const xw_catalog* cat, xo_env* e, int32_t collided, double* reward_out) {
@@ -587,7 +646,10 @@ int xo_teach(const xw_config* cfg, const xw_catalog* cat, xo_env* e, int32_t col
     /* _time_reward, xworld3d_task.py:472-482 */
     double r = -0.01;
     e->steps_in_task += 1;
-    if (e->steps_in_task >= e->H * e->W * cfg->max_steps_factor) {
+    /* h, w = self.env.get_dims(): the world the Python side sees, not the padded C++ map */
+    const int side = cfg->curriculum != 0 ? e->dim : e->H;
+    if (e->steps_in_task >= side * side * cfg->max_steps_factor) {
+        record_result(cfg, e, 0);
         e->n_failure += 1;
         e->event = XW_EVENT_TIME_UP;
         e->stage = XW_STAGE_TERMINAL;
@@ -613,20 +675,30 @@ int xo_teach(const xw_config* cfg, const xw_catalog* cat, xo_env* e, int32_t col
         }
     } else { /* XWorld3DNavTargetDirection.py:78-96 */
         int ref = e->aux0, any = 0, ok = 0;
+        /* self.target holds the referent's Entity OBJECT from the idle stage.  cpp_get_entities (xworld_env.py:359-361)
+         * adds (offset_w, offset_h) to the loc of the env's entity objects IN PLACE when the C++ side fetches the map
+         * after that stage, and update_entities_from_cpp then replaces the env's list with fresh objects in the
+         * Python side's coordinates: from there on referent.loc is off by the padding offset against every g.loc.
+         * With curriculum levels 0-3 (offset 2, 2, 1, 1) the test below therefore runs on a displaced referent: never
+         * "close" at offset 2, close for two of the four true arrangements at offset 1.  Reproduced, not fixed. */
+        const int off = cfg->curriculum != 0 ? (cfg->height - e->dim) / 2 : 0;
+        const int ref_x = e->goal_x[ref] + off, ref_y = e->goal_y[ref] + off;
         for (int g = 0; g < e->n_goals; ++g)
             if (reach_mask & (1 << g)) {
                 any = 1;
-                int d = triple_direction(e->goal_x[g], e->goal_y[g], e->goal_x[ref], e->goal_y[ref], e->agent_yaw);
-                double dx = e->goal_x[g] - e->goal_x[ref], dy = e->goal_y[g] - e->goal_y[ref];
+                int d = triple_direction(e->goal_x[g], e->goal_y[g], ref_x, ref_y, e->agent_yaw);
+                double dx = e->goal_x[g] - ref_x, dy = e->goal_y[g] - ref_y;
                 int close = sqrt(dx * dx + dy * dy) < 1.0 + 1e-3;
                 if (d == e->aux1 && d != DIR_FALSE && close) ok = 1;
             }
         if (ok) correct = 1; else if (any) wrong = 1;
     }
     if (correct) { /* _successful_goal :456-462 */
+        record_result(cfg, e, 1);
         e->n_success += 1; e->success_steps += e->steps_in_task;
         e->event = XW_EVENT_CORRECT_GOAL; r += 1.0; e->stage = XW_STAGE_TERMINAL;
     } else if (wrong) { /* _failed_goal :464-470 */
+        record_result(cfg, e, 0);
         e->n_failure += 1;
         e->event = XW_EVENT_WRONG_GOAL; r += -1.0; e->stage = XW_STAGE_TERMINAL;
     }
@@ -638,6 +710,7 @@ void xo_env_init(const xw_config* cfg, xo_env* e, int64_t env_gid) {
     memset(e, 0, sizeof *e);
     e->env_gid = env_gid;
     e->H = cfg->height; e->W = cfg->width; e->n_goals = cfg->n_goals;
+    e->level = cfg->start_level; e->dim = cfg->height;
     /* env i plays the role of the reference's i-th simulator thread (1-based) */
     e->minstd = xo_minstd_seed_for_thread(cfg->simulator_seed, (int32_t)(env_gid + 1));
 }
@@ -654,6 +727,9 @@ int xo_reset(const xw_config* cfg, const xw_catalog* cat, xo_env* e) {
     if (cfg->rules == XW_RULES_NAV3D) {
         /* teacher_->teach(): TaskGroup::run_stage samples the task with the seeded C++ engine */
         e->task = xo_get_rand_ind(&e->minstd, 5);
+        if (cfg->curriculum != 0) { /* XWorldNav._configure, XWorldNav.py:40-56; once per episode */
+            if (current_usage(cfg, e) >= (double)cfg->curriculum && e->level < 6 - 1) e->level += 1;
+        }
         int ok = 0;
         for (uint32_t att = 0; att < 64 && !ok; ++att) {
             int rc = gen_map(cfg, cat, e, ep, att);
@@ -661,6 +737,7 @@ int xo_reset(const xw_config* cfg, const xw_catalog* cat, xo_env* e) {
             if (idle3d(cfg, e, ep, att) == 0) ok = 1;
         }
         if (!ok) { e->error = 1; return XW_ERR_INVALID_ARG; }
+        if (cfg->curriculum != 0) embed_world(cfg, e);
         e->stage = XW_STAGE_NAVIGATION;
     } else {
         int rc = gen_map(cfg, cat, e, ep, 0);

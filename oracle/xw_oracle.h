@@ -45,6 +45,11 @@ typedef struct {
     uint32_t minstd;
     int32_t error;
     int64_t env_gid;
+    /* curriculum (cfg->curriculum > 0): XWorldEnv.current_level / curriculum_check_counter, the world's side
+     * (XWorldEnv.height == width) and each task class's success_seq (xworld3d_task.py:67,129-133) */
+    int32_t level, dim, check_counter;
+    int32_t seq_len[5];
+    uint8_t seq[5][200];
 } xo_env;
 
 /* ---- RNG ---- */

@@ -2,7 +2,10 @@
 """Golden-vector generator: runs the REFERENCE's own Python (map generator + teacher tasks) and
 records what it does, so the C oracle (oracle/xw_oracle.c) can be pinned against it.
 
-Runs only in the build container (needs /root/reference).  Output: tests/golden/refpy_traces.json.gz.
+Runs only in the build container (needs /root/reference).  Output: tests/golden/refpy_traces.json.gz;
+`gen_reference_python.py curriculum` writes tests/golden/refpy_curriculum.json.gz instead: XWorldNav with
+--curriculum > 0 run unmodified at its own 8x8 / level tables, XWorldEnv.curriculum_check_period set
+to a few resets so that the levels move within a short trace, plus one env at the reference's own period of 100.
 
 What is executed unmodified (loaded from /root/reference, never copied):
     games/xworld/maps/xworld_env.py, XWorldNav.py      map/entity schema + generator
@@ -214,10 +217,11 @@ DIRS = {"front": 1, "behind": 2, "left": 3, "right": 4}
 # ----------------------------------------------------------------------------- host emulation
 class Host(object):
     """What XWorldSimulator/XWorld/XMap/Teacher do around the Python (C++ side), for one env."""
+    start_level = 0
 
     def __init__(self, mods, cat, rules, dim):
         self.mods, self.cat, self.rules, self.dim = mods, cat, rules, dim
-        self.env = mods["XWorldNav"].XWorldNav(ITEM_PATH)
+        self.env = mods["XWorldNav"].XWorldNav(ITEM_PATH, start_level=self.start_level)
         names = T3 if rules == 0 else T2
         self.tasks = [getattr(mods[n], n)(self.env) for n in names]  # Task::init_py_task
         self.path2icon = {os.path.join(ITEM_PATH, m["path"]): i for i, m in enumerate(cat.icon_meta)}
@@ -295,6 +299,33 @@ class Host(object):
             "goal_icon": [self.path2icon[g["asset_path"]] for g in goals],
         }
 
+    def approach_from_above(self, goal):
+        """First move of a shortest path to the cell above `goal`, MOVE_DOWN once there (the only scoring move: the
+        heading is +y); None when there is no path.  Harness-side action policy only."""
+        occ = {(int(e["loc"][0]), int(e["loc"][1])) for e in self.entities}
+        a = self.agent()
+        start = (int(a["loc"][0]), int(a["loc"][1]))
+        dest = (int(goal["loc"][0]), int(goal["loc"][1]) - 1)
+        if start == dest:
+            return 1
+        if dest in occ or dest[1] < 0:
+            return None
+        prev = {start: None}
+        queue = [start]
+        moves = [(0, -1, 0), (0, 1, 1), (-1, 0, 2), (1, 0, 3)]
+        while queue:
+            cur = queue.pop(0)
+            if cur == dest:
+                while prev[cur][0] != start:
+                    cur = prev[cur][0]
+                return prev[cur][1]
+            for dx, dy, act in moves:
+                q = (cur[0] + dx, cur[1] + dy)
+                if 0 <= q[0] < self.dim and 0 <= q[1] < self.dim and q not in occ and q not in prev:
+                    prev[q] = (cur, act)
+                    queue.append(q)
+        return None
+
     def goal_index(self, ent):
         return int(ent.id.split("_")[-1])
 
@@ -306,8 +337,8 @@ class Host(object):
             if name in ("XWorld3DNavTarget", "XWorld3DNavTargetAvoid", "XWorld3DNavTargetNear"):
                 rec["target_mask"] = sum(1 << self.goal_index(g) for g in task.target)
             elif name == "XWorld3DNavTargetBetween":
-                o1, o2 = task.target
-                rec["mid"] = [int((o1[0] + o2[0]) // 2), int((o1[1] + o2[1]) // 2)]
+                o1, o2 = task.target  # the Python side's coordinates; the trace keeps map coordinates (cpp_get_entities)
+                rec["mid"] = [int((o1[0] + o2[0]) // 2) + self.env.offset_w, int((o1[1] + o2[1]) // 2) + self.env.offset_h]
             else:
                 referent, direction = task.target
                 rec["referent"] = self.goal_index(referent)
@@ -315,7 +346,8 @@ class Host(object):
         return rec
 
 
-def run_case(mods, cat, rules, dim, n_goals, n_blocks, seed, simulator_seed, env_gid, n_episodes, n_steps, act_seed):
+def run_case(mods, cat, rules, dim, n_goals, n_blocks, seed, simulator_seed, env_gid, n_episodes, n_steps, act_seed,
+             curriculum=False):
     """One env, several episodes; returns the trace the oracle must reproduce."""
     L = oracle.lib()
     import ctypes as C
@@ -335,7 +367,10 @@ def run_case(mods, cat, rules, dim, n_goals, n_blocks, seed, simulator_seed, env
             ok = False
             for att in range(64):
                 Ctx.attempt, Ctx.maze_visits, Ctx.goal_no, Ctx.step_no = att, 0, 0, 0
+                if att > 0:  # a re-drawn map is the same reset: the curriculum check ran with attempt 0
+                    host.env.get_current_usage = lambda: 0
                 host.env.reset()
+                host.env.__dict__.pop("get_current_usage", None)
                 assert host.env.env_changed()
                 host.pull_entities()
                 task.reset()
@@ -356,6 +391,11 @@ def run_case(mods, cat, rules, dim, n_goals, n_blocks, seed, simulator_seed, env
             stage, task, t = "idle", None, -1
         rec["task"] = t
         rec["reset"] = host.snapshot()
+        if curriculum:
+            rec["level"] = host.env.current_level
+            rec["dims"] = list(host.env.get_dims())
+            rec["check_counter"] = host.env.curriculum_check_counter
+            rec["usage"] = {k: [len(v), sum(v)] for k, v in host.env.current_usage.items()}
         if rules == 0:
             rec["reset_sentence"] = host.last_sentence
         if rules == 0:
@@ -383,6 +423,20 @@ def run_case(mods, cat, rules, dim, n_goals, n_blocks, seed, simulator_seed, env
             rec["reset_sentence"] = host.last_sentence
         for s in range(n_steps):
             a = int(arng.randint(0, 4))
+            if curriculum and arng.rand() < 0.4:
+                a = 1  # MOVE_DOWN is the only move that can score (the heading is +y): lets the success rates rise
+            if curriculum and T3[t] == "XWorld3DNavTargetDirection" and arng.rand() < 0.7:
+                # walk to the goal next to the referent and bump it from above, so that the displaced-referent test
+                # of the padded levels (oracle/xw_oracle.c xo_teach) sees goals reached in every arrangement
+                ref_id = task.target[0].id
+                goals = [e for e in host.entities if e["type"] == "goal"]
+                ref = [e for e in goals if e["id"] == ref_id][0]
+                near = [e for e in goals if e["id"] != ref_id and
+                        abs(e["loc"][0] - ref["loc"][0]) + abs(e["loc"][1] - ref["loc"][1]) == 1]
+                if near:
+                    b = host.approach_from_above(near[0])
+                    if b is not None:
+                        a = b
             num_steps += 1
             Ctx.step_no = num_steps
             ok, contacts = host.move(a)
@@ -392,8 +446,13 @@ def run_case(mods, cat, rules, dim, n_goals, n_blocks, seed, simulator_seed, env
             else:
                 r, ev = teach2d(ok, game_event)
             ag = host.agent()
-            steps.append({"a": a, "ok": int(ok), "r": r, "ev": ev, "stage": stage, "task": t, "sent": host.last_sentence,
-                          "agent": [int(ag["loc"][0]), int(ag["loc"][1])]})
+            if curriculum:
+                steps.append({"a": a, "ok": int(ok), "r": r, "ev": ev, "agent": [int(ag["loc"][0]), int(ag["loc"][1])]})
+            else:
+                steps.append({"a": a, "ok": int(ok), "r": r, "ev": ev, "stage": stage, "task": t, "sent": host.last_sentence,
+                              "agent": [int(ag["loc"][0]), int(ag["loc"][1])]})
+            if curriculum and stage == "terminal":
+                break  # the trainer resets a finished game (test_xworld.py:46-49)
             if rules == 0 and stage == "terminal" and s + 3 < n_steps and len(steps) > 2 and steps[-2]["stage"] == "terminal" \
                     and steps[-3]["stage"] == "terminal":
                 break  # a few terminal-stage steps are enough
@@ -401,6 +460,36 @@ def run_case(mods, cat, rules, dim, n_goals, n_blocks, seed, simulator_seed, env
         rec["minstd"] = minstd.value
         episodes.append(rec)
     return episodes
+
+
+def main_curriculum():
+    """XWorldNav.py:36-58 + xworld_env.py:103-110,118-134,352-366,454-473 + the task classes' success windows."""
+    import gzip
+    import numpy as np
+    cat = Catalog.from_item_path(ITEM_PATH)
+    thr = float(np.float32(0.05))  # FLAGS_curriculum = the option read as a float (py_simulator.cpp:127)
+    FLAGS["curriculum"] = thr
+    out = {"generator": "tests/golden/gen_reference_python.py curriculum", "curriculum": thr, "cases": []}
+    cases = [("period5", 5, 24, 30, 60, 3, 0), ("period100_reference", 100, 1, 330, 12, 1, 0)]
+    cases += [("start_level%d" % k, 4, 6 if k in (2, 3) else 4, 24 if k in (2, 3) else 14, 60, 1, k) for k in range(1, 6)]  # XWorldNav(item_path, start_level=k)
+    for tag, period, n_envs, n_ep, n_st, msf, start_level in cases:
+        FLAGS["max_steps_factor"] = msf
+        Host.start_level = start_level
+        mods = load_reference_python(8, 4, 16)  # XWorldNav.py as it is
+        mods["xworld_env"].XWorldEnv.curriculum_check_period = period  # a class attribute (xworld_env.py:58)
+        envs = []
+        for gid in range(n_envs):
+            envs.append({"env_gid": gid,
+                         "episodes": run_case(mods, cat, 0, 8, 4, 16, seed=4321, simulator_seed=3, env_gid=gid,
+                                              n_episodes=n_ep, n_steps=n_st, act_seed=2000 + gid, curriculum=True)})
+        levels = [ep["level"] for e in envs for ep in e["episodes"]]
+        print(tag, "levels reached:", sorted(set(levels)))
+        out["cases"].append({"tag": tag, "rules": 0, "dim": 8, "n_goals": 4, "n_blocks": 16, "seed": 4321, "simulator_seed": 3,
+                             "check_period": period, "max_steps_factor": msf, "start_level": start_level, "envs": envs})
+    path = os.path.join(HERE, "refpy_curriculum.json.gz")
+    with gzip.GzipFile(path, "wb", mtime=0) as f:
+        f.write(json.dumps(out, separators=(",", ":")).encode())
+    print("wrote", path, os.path.getsize(path))
 
 
 def main():
@@ -433,4 +522,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["curriculum"]:
+        main_curriculum()
+    else:
+        main()

@@ -80,6 +80,13 @@ HostSim* hs_create(const xw_config* c, const xw_catalog* cat, int n) {
     for (auto p : i32s) *p = halloc<int32_t>(s, n);
     d.minstd = halloc<uint32_t>(s, n);
     d.reset_count = halloc<int32_t>(s, 2); d.reset_list = halloc<int32_t>(s, n);
+    if (c->curriculum != 0) {
+        d.curriculum = (double)c->curriculum; d.check_period = c->curriculum_check_period > 0 ? c->curriculum_check_period : 100;
+        d.level = halloc<uint8_t>(s, n); d.check_counter = halloc<int32_t>(s, n);
+        d.win_len = halloc<uint8_t>(s, (size_t)n * XW_N_T3); d.win_pos = halloc<uint8_t>(s, (size_t)n * XW_N_T3);
+        d.win_sum = halloc<uint8_t>(s, (size_t)n * XW_N_T3); d.win_bits = halloc<uint32_t>(s, (size_t)n * XW_N_T3 * XW_WIN_WORDS);
+        for (int i = 0; i < n; ++i) d.level[i] = (uint8_t)c->start_level;
+    }
     for (int i = 0; i < n; ++i) d.minstd[i] = minstd_seed(c->simulator_seed, c->env_id_offset + i + 1);
     d.n_names = cat->n_names; d.brick_icon = cat->brick_icon; d.agent_icon = cat->agent_icon;
     d.name_first = cat->name_first; d.name_icons = cat->name_icons; d.icon_colored = cat->icon_colored;
@@ -373,6 +380,12 @@ int hs_get_field(HostSim* s, const char* name, void* out) {
     struct { const char* nm; void* p; } i32t[] = {{"steps_in_task", d.steps_in_task}, {"num_steps", d.num_steps}, {"episode", d.episode},
         {"n_success", d.n_success}, {"n_failure", d.n_failure}, {"success_steps", d.success_steps}, {"minstd", d.minstd}, {"error", d.error}};
     for (auto& t : i32t) if (k == t.nm) { memcpy(out, t.p, 4 * n); return 0; }
+    if (d.curriculum != 0) {
+        if (k == "level") { memcpy(out, d.level, n); return 0; }
+        if (k == "check_counter") { memcpy(out, d.check_counter, 4 * n); return 0; }
+        if (k == "win_len") { memcpy(out, d.win_len, n * XW_N_T3); return 0; }
+        if (k == "win_sum") { memcpy(out, d.win_sum, n * XW_N_T3); return 0; }
+    }
     if (k == "goal_x" || k == "goal_y") {
         uint8_t* src = k == "goal_x" ? d.goal_x : d.goal_y;
         for (size_t g = 0; g < XW_MAX_GOALS; ++g) for (size_t e = 0; e < n; ++e) ((uint8_t*)out)[e * XW_MAX_GOALS + g] = src[g * n + e];

@@ -21,6 +21,9 @@ CONFIGS = {
                               max_steps=242),
     "c4_nav3d_15x15_128": dict(height=15, width=15, n_goals=4, n_blocks=56, rules=_abi.XW_RULES_NAV3D, out_h=128, out_w=128),
     "ref_nav3d_8x8_96": dict(height=8, width=8, n_goals=4, n_blocks=16, rules=_abi.XW_RULES_NAV3D),
+    # XWorldNav's level schedule (the check period is shortened so that levels change within a test)
+    "curriculum_nav3d_8x8_96": dict(height=8, width=8, n_goals=4, n_blocks=16, rules=_abi.XW_RULES_NAV3D, curriculum=0.1,
+                                    curriculum_check_period=5),
     "ref_nav2d_8x8_96": dict(height=8, width=8, n_goals=4, n_blocks=16, rules=_abi.XW_RULES_NAV2D, max_steps=64),
 }
 
@@ -116,7 +119,9 @@ class HostSim(object):
             out = np.zeros((n, _abi.XW_MAX_GOALS), np.uint8)
         elif name in ("goal_icon", "goal_name"):
             out = np.zeros((n, _abi.XW_MAX_GOALS), np.int32)
-        elif name in U8:
+        elif name in ("win_len", "win_sum"):
+            out = np.zeros((n, 5), np.uint8)
+        elif name in U8 or name == "level":
             out = np.zeros(n, np.uint8)
         elif name == "state":
             out = np.zeros((n, 4), np.float32)
@@ -141,6 +146,10 @@ def compare_state(backend, orc, tag=""):
     for f in ["goal_x", "goal_y", "goal_icon"]:
         a, b = backend.field(f)[:, :G], orc.field(f)[:, :G]
         assert (a == b).all(), "%s field %s differs" % (tag, f)
+    if orc.cfg.curriculum != 0:
+        for f in ["level", "check_counter", "win_len", "win_sum"]:
+            a, b = backend.field(f), orc.field(f)
+            assert (a == b).all(), "%s curriculum field %s differs: got %s want %s" % (tag, f, a[:4], b[:4])
 
 
 def run_parity(backend, orc, n_steps, render_every=0, act_rep=1, check_state_every=1, auto_reset=False, seed=99):

@@ -22,6 +22,29 @@ def test_hostsim_matches_oracle(name, synthetic_catalog):
     assert stats["frames"] >= 4 * n
 
 
+@pytest.mark.parametrize("kw,n,steps", [
+    (dict(curriculum=0.9, max_steps_factor=1), 8, 9000),                          # level 0 for ever: the 200-result windows fill and roll
+    (dict(curriculum=0.02, start_level=2, curriculum_check_period=3), 16, 1500),  # offset-1 levels (displaced referent)
+    (dict(curriculum=0.02, start_level=4, curriculum_check_period=2), 16, 1500),  # 7x7 world in the 8x8 map, then the last level
+    (dict(curriculum=0.5, start_level=5), 16, 300),                               # last level = the curriculum-0 map
+    (dict(curriculum=0.1, curriculum_check_period=4, auto_reset=1, max_steps=40), 48, 600),
+])
+def test_hostsim_curriculum(kw, n, steps, synthetic_catalog):
+    """per-env level schedule, padded worlds, result windows -- engine code vs the oracle."""
+    cfg = parity.make_cfg("curriculum_nav3d_8x8_96", **kw)
+    hs = parity.HostSim(cfg, synthetic_catalog, n)
+    orc = oracle.Oracle(cfg, synthetic_catalog, n, threads=2)
+    parity.run_parity(hs, orc, steps, render_every=steps // 3, check_state_every=53, auto_reset=bool(kw.get("auto_reset")))
+    lv = hs.field("level")
+    assert lv.min() >= kw.get("start_level", 0)
+    if kw.get("max_steps_factor") == 1:
+        assert (hs.field("win_len") == 200).all()
+    if kw.get("start_level") == 4:
+        assert lv.max() == 5
+    if kw.get("auto_reset"):
+        assert lv.max() >= 1
+
+
 def test_hostsim_act_rep_and_global_ids(synthetic_catalog):
     cfg = parity.make_cfg("c2_nav3d_7x7_84", env_id_offset=1000, seed=42, simulator_seed=7)
     hs = parity.HostSim(cfg, synthetic_catalog, 32)

@@ -53,6 +53,30 @@ def test_auto_reset_and_act_rep(backend_cls, synthetic_catalog):
     parity.run_parity(eng, orc, 300, render_every=100, auto_reset=True, act_rep=2, check_state_every=50)
 
 
+@pytest.mark.parametrize("kw,n,steps", [
+    (dict(curriculum=0.1, curriculum_check_period=4, auto_reset=1, max_steps=40), 2048, 400),  # warp-per-env k_reset
+    (dict(curriculum=0.02, start_level=2, curriculum_check_period=3), 1024, 300),              # offset-1 levels
+    (dict(curriculum=0.02, start_level=4, curriculum_check_period=2, auto_reset=1), 1024, 300),
+    (dict(curriculum=0.9, max_steps_factor=1, auto_reset=1), 64, 4000),                        # windows fill and roll
+])
+def test_curriculum_levels(kw, n, steps, backend_cls, synthetic_catalog):
+    """SURVEY 8f-3 (XWorldNav.py:36-58): per-env levels, padded worlds, result windows, the displaced-referent
+    rule of the padded levels -- state, rewards, game_over and frames bit-exact against the oracle."""
+    cfg = parity.make_cfg("curriculum_nav3d_8x8_96", **kw)
+    eng = backend_cls(cfg, synthetic_catalog, n)
+    orc = oracle.Oracle(cfg, synthetic_catalog, n, threads=8)
+    parity.run_parity(eng, orc, steps, render_every=steps // 4, check_state_every=steps // 8,
+                      auto_reset=bool(kw.get("auto_reset")))
+    lv = eng.field("level")
+    assert lv.min() >= kw.get("start_level", 0)
+    if kw.get("max_steps_factor") == 1:
+        assert eng.field("win_len").min() >= 150
+    elif "start_level" not in kw:
+        assert lv.max() >= 1
+    if kw.get("start_level") == 4:
+        assert lv.max() == 5
+
+
 def test_golden_frames_from_real_opencv(backend_cls):
     """The GPU compositor vs frames the real OpenCV produced from the reference call sequence."""
     n = 0

@@ -100,6 +100,64 @@ def test_against_reference_python_traces(oracle_lib, synthetic_catalog):
     assert n_steps > 9000 and n_resets > 80
 
 
+def test_curriculum_against_reference_python(oracle_lib, synthetic_catalog):
+    """XWorldNav with --curriculum > 0, run by the reference's own Python (XWorldNav.py:36-58,
+    xworld_env.py:103-110,118-134,352-366,454-473; the task classes' 200-result windows, xworld3d_task.py:129-146):
+    the level of every episode, the padded 8x8 map, the counters and windows at every reset, and every step."""
+    with gzip.open(os.path.join(HERE, "golden", "refpy_curriculum.json.gz")) as f:
+        tr = json.loads(f.read().decode())
+    T3 = ["XWorld3DNavTarget", "XWorld3DNavTargetNear", "XWorld3DNavTargetBetween", "XWorld3DNavTargetDirection",
+          "XWorld3DNavTargetAvoid"]
+    n_steps = n_resets = 0
+    levels, ups = set(), 0
+    for case in tr["cases"]:
+        cfg = _abi.default_config(height=8, width=8, n_goals=4, n_blocks=16, rules=0, seed=case["seed"],
+                                  simulator_seed=case["simulator_seed"], curriculum=tr["curriculum"],
+                                  curriculum_check_period=case["check_period"], max_steps_factor=case["max_steps_factor"],
+                                  start_level=case["start_level"])
+        for env in case["envs"]:
+            cfg.env_id_offset = env["env_gid"]
+            o = oracle.Oracle(cfg, synthetic_catalog, 1)
+            e = o.envs[0]
+            prev = case["start_level"]
+            for ep in env["episodes"]:
+                o.reset()
+                n_resets += 1
+                rs = ep["reset"]
+                where = (case["tag"], env["env_gid"], ep["episode"])
+                assert e.level == ep["level"] and [e.dim, e.dim] == ep["dims"], where
+                levels.add(e.level)
+                ups += e.level != prev
+                prev = e.level
+                assert e.check_counter == ep["check_counter"], where
+                for t, name in enumerate(T3):
+                    ln, sm = ep["usage"].get(name, [0, 0])
+                    assert e.seq_len[t] == ln and sum(e.seq[t][:ln]) == sm, (where, name)
+                G = len(rs["goal_x"])
+                assert e.n_goals == G == (2 if e.level < 3 else 4), where
+                assert list(e.grid)[:64] == rs["grid"], where
+                assert [e.agent_x, e.agent_y] == rs["agent"], where
+                assert list(e.goal_x)[:G] == rs["goal_x"] and list(e.goal_y)[:G] == rs["goal_y"], where
+                assert list(e.goal_name)[:G] == rs["goal_name"] and list(e.goal_icon)[:G] == rs["goal_icon"], where
+                assert e.task == ep["task"], where
+                if "target_mask" in ep:
+                    assert e.target_mask == ep["target_mask"], where
+                if "mid" in ep:
+                    assert [e.aux1, e.aux2] == ep["mid"], where
+                if "referent" in ep:
+                    assert (e.aux0, e.aux1) == (ep["referent"], ep["direction"]), where
+                for i, s in enumerate(ep["steps"]):
+                    r, ov = C.c_float(), C.c_int32()
+                    rc = oracle_lib.xo_step(C.byref(cfg), C.byref(o.cat_c), C.byref(e), s["a"], 1, C.byref(r), C.byref(ov))
+                    assert rc == 0
+                    n_steps += 1
+                    assert np.float32(r.value).view(np.uint32) == np.float32(s["r"]).view(np.uint32), (where, i)
+                    assert [e.agent_x, e.agent_y] == s["agent"] and e.action_success == s["ok"], (where, i)
+                    assert e.event == EVMAP[s["ev"]], (where, i)
+                assert e.minstd == ep["minstd"], where
+    assert levels == {0, 1, 2, 3, 4, 5} and ups >= 2 and n_resets > 1300 and n_steps > 10000, (levels, ups, n_resets, n_steps)
+
+
 def test_reward_bit_patterns(oracle_lib, synthetic_catalog):
     """the float32 images of the reference's double sums."""
     want3 = {0xbc23d70a, 0x3f7d70a4, 0xbf8147ae, 0x00000000}

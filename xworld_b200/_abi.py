@@ -59,7 +59,10 @@ class XwConfig(C.Structure):
         ("race_random", C.c_int32),
         ("difficulty", C.c_int32),
         ("reward_scale", C.c_float),
-        ("reserved", C.c_int32 * 8),
+        ("curriculum", C.c_float),
+        ("curriculum_check_period", C.c_int32),
+        ("start_level", C.c_int32),
+        ("reserved", C.c_int32 * 5),
     ]
 
 

@@ -25,6 +25,17 @@ enum {
 // directions relative to a heading (XWorld3DNavTargetDirection.__compute_triple_direction)
 enum { XW_DIR_FALSE = 0, XW_DIR_FRONT = 1, XW_DIR_BEHIND = 2, XW_DIR_LEFT = 3, XW_DIR_RIGHT = 4 };
 
+// XWorldNav._configure (XWorldNav.py:24-35): level l = a (3+l)-sided world inside the 8x8 map, padded with bricks
+#define XW_N_T3 5
+#define XW_WIN_SIZE 200
+#define XW_WIN_WORDS 7
+#define XW_N_LEVELS 6
+XW_HD void xw_level_dims(int level, int& D, int& n_goals, int& n_blocks) {
+    D = 3 + level;
+    n_goals = level < 3 ? 2 : 4;                                   // num_goals_seq  = [2, 2, 2, 4, 4, 4]
+    n_blocks = level < 5 ? 3 * level : 16;                          // num_blocks_seq = [0, 3, 6, 9, 12, 16]
+}
+
 struct XwDev {
     int32_t n;                 // envs on this device
     int32_t H, W, CS;          // map size, grid row stride (bytes)
@@ -39,6 +50,13 @@ struct XwDev {
     int32_t* goal_name;        // [XW_MAX_GOALS][n]
     int32_t *steps_in_task, *num_steps, *episode, *n_success, *n_failure, *success_steps, *error;
     uint32_t* minstd;
+    // ---- curriculum (XWorldNav._configure with --curriculum > 0; all NULL / 0 when it is off) ----
+    double curriculum;         // FLAGS_curriculum: (double)(float) of the option, py_simulator.cpp:127
+    int32_t check_period;      // XWorldEnv.curriculum_check_period (xworld_env.py:58)
+    uint8_t* level;            // [n] XWorldEnv.current_level
+    int32_t* check_counter;    // [n] XWorldEnv.curriculum_check_counter
+    uint8_t *win_len, *win_pos, *win_sum;  // [n][XW_N_T3]: XWorld3DTask.success_seq of each task class as a
+    uint32_t* win_bits;        // [n][XW_N_T3][XW_WIN_WORDS] 200-entry ring of bits (xworld3d_task.py:47,129-133)
     // ---- catalog ----
     int32_t n_names, brick_icon, agent_icon;
     const int32_t *name_first, *name_icons;

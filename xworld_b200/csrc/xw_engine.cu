@@ -183,6 +183,14 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
     if (c.visible_radius != 0) return set_err(XW_ERR_UNSUPPORTED, "visible_radius > 0 (first-person view) is not implemented");
     if (c.context < 1 || c.context > 16) return set_err(XW_ERR_INVALID_ARG, "context must be in [1,16]");
     if (c.rules != XW_RULES_NAV3D && c.rules != XW_RULES_NAV2D) return set_err(XW_ERR_INVALID_ARG, "unknown rules");
+    if (c.curriculum != 0) {  // XWorldNav's level schedule is written for its own 8x8 map (XWorldNav.py:10-11,27-33)
+        if (!(c.curriculum > 0)) return set_err(XW_ERR_INVALID_ARG, "curriculum must be >= 0");
+        if (c.rules != XW_RULES_NAV3D) return set_err(XW_ERR_UNSUPPORTED, "curriculum > 0 is implemented for the navigation2d.json rules only");
+        if (c.height != 8 || c.n_goals != 4 || c.n_blocks != 16)
+            return set_err(XW_ERR_INVALID_ARG, "curriculum > 0 needs XWorldNav's own map: 8x8, 4 goals, 16 blocks");
+        if (c.start_level < 0 || c.start_level >= XW_N_LEVELS) return set_err(XW_ERR_INVALID_ARG, "start_level must be in [0,%d]", XW_N_LEVELS - 1);
+        if (c.curriculum_check_period < 0) return set_err(XW_ERR_INVALID_ARG, "curriculum_check_period must be >= 0");
+    }
     {  // the maze must offer n_blocks wall cells ("too many blocks for a valid maze", xworld_env.py:443)
         int D = c.height, X = (D % 2 == 0) ? D - 1 : D, nx = (X + 1) / 2;
         int walls = X * X - nx * nx - (nx * nx - 1) + ((D % 2 == 0) ? (X / 2) + (D / 2) : 0);
@@ -208,6 +216,17 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
     rc |= dalloc(s, &d.minstd, (size_t)n);
     rc |= dalloc(s, &d.reset_count, 2);
     rc |= dalloc(s, &d.reset_list, (size_t)n);
+    if (c.curriculum != 0) {
+        d.curriculum = (double)c.curriculum;
+        d.check_period = c.curriculum_check_period > 0 ? c.curriculum_check_period : 100;
+        rc |= dalloc(s, &d.level, (size_t)n);
+        rc |= dalloc(s, &d.check_counter, (size_t)n);
+        rc |= dalloc(s, &d.win_len, (size_t)n * XW_N_T3);
+        rc |= dalloc(s, &d.win_pos, (size_t)n * XW_N_T3);
+        rc |= dalloc(s, &d.win_sum, (size_t)n * XW_N_T3);
+        rc |= dalloc(s, &d.win_bits, (size_t)n * XW_N_T3 * XW_WIN_WORDS);
+        if (!rc && c.start_level) CUDA_TRY(cudaMemset(d.level, c.start_level, (size_t)n));
+    }
     if (rc) return rc;
     {
         std::vector<uint32_t> seeds(n);
@@ -848,8 +867,10 @@ static bool find_field(xw_sim* s, const char* name, FieldRef* f) {
             {"steps_in_task", d.steps_in_task, 4, 1, false}, {"num_steps", d.num_steps, 4, 1, false},
             {"episode", d.episode, 4, 1, false}, {"n_success", d.n_success, 4, 1, false},
             {"n_failure", d.n_failure, 4, 1, false}, {"success_steps", d.success_steps, 4, 1, false},
-            {"minstd", d.minstd, 4, 1, false}, {"error", d.error, 4, 1, false}};
-        for (auto& t : tbl) if (k == t.n) { *f = {t.p, t.elem, t.per, t.gm}; return true; }
+            {"minstd", d.minstd, 4, 1, false}, {"error", d.error, 4, 1, false},
+            {"level", d.level, 1, 1, false}, {"check_counter", d.check_counter, 4, 1, false},
+            {"win_len", d.win_len, 1, XW_N_T3, false}, {"win_sum", d.win_sum, 1, XW_N_T3, false}};
+        for (auto& t : tbl) if (k == t.n && t.p) { *f = {t.p, t.elem, t.per, t.gm}; return true; }
     } else if (s->cfg.game == XW_GAME_SIMPLE_RACE) {
         XwRaceCfg& r = s->race;
         struct { const char* n; void* p; size_t elem, per; } tbl[] = {

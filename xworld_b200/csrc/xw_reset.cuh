@@ -3,7 +3,7 @@
 // Replaces, per env (reference file:line):
 //   XWorld::reset                       games/xworld/xworld/xworld.cpp:109-151
 //   XWorldEnv.reset/__instantiate_entities   games/xworld/maps/xworld_env.py:95-101,412-452
-//   XWorldNav._configure (curriculum 0)  games/xworld/maps/XWorldNav.py:16-67
+//   XWorldNav._configure (curriculum 0 and > 0: levels, padded worlds)  games/xworld/maps/XWorldNav.py:16-67
 //   spanning_tree_maze_generator, bfs, flood_fill   python/maze2d.py:21-114
 //   Teacher::reset_after_game_reset + teach -> TaskGroup::run_stage  teacher.cpp:207-237, teaching_task.cpp:204-222
 //   the idle() stages of games/xworld3d/tasks/XWorld3DNav*.py and games/xworld/tasks/XWorldNav*.py
@@ -46,7 +46,8 @@ XW_HD int m_nth(const XwMask& m, int k) {
 }
 
 struct XwMapCtx {
-    int H, W;
+    int H, W;        // the world the Python side sees: the whole map, or the level's inner world (curriculum)
+    int nG, nB;      // goals / blocks of this episode
     XwMask inrange;  // cells of the map
     XwMask block;    // wall bricks
     XwMask goal;     // goal cells
@@ -64,9 +65,10 @@ XW_HD bool ctx_free(const XwMapCtx& c, int x, int y) {  // (x,y,0) in env.availa
 
 // -------------------------------------------------------------------------- maze + entities
 // Returns 0 on success.  `wall` receives the maze's '#' cells.
-XW_HD int xw_gen_map(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, XwMapCtx& c) {
-    const int D = d.H;
-    c.H = d.H; c.W = d.W;
+XW_HD int xw_gen_map(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, int level, XwMapCtx& c) {
+    int D = d.H, nG = d.G, nB = d.n_blocks;
+    if (d.curriculum != 0) xw_level_dims(level, D, nG, nB);  // set_dims(current_dim, current_dim), XWorldNav.py:58
+    c.H = D; c.W = D; c.nG = nG; c.nB = nB;
     m_zero(c.inrange); m_zero(c.block); m_zero(c.goal);
     for (int i = 0; i < D * D; ++i) m_set(c.inrange, i);
     // ---- goal names: shuffle(goal_names) then pop() per goal == partial Fisher-Yates from the end;
@@ -74,7 +76,7 @@ XW_HD int xw_gen_map(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, XwM
     {
         int keys[2 * XW_MAX_GOALS], vals[2 * XW_MAX_GOALS], cnt = 0;
         const int n = d.n_names;
-        for (int k = 0; k < d.G; ++k) {
+        for (int k = 0; k < nG; ++k) {
             int i = n - 1 - k, vi = i;
             for (int q = 0; q < cnt; ++q) if (keys[q] == i) vi = vals[q];
             if (i >= 1) {
@@ -133,11 +135,11 @@ XW_HD int xw_gen_map(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, XwM
         for (int i = 0; i < D; ++i) if (i & 1) m_set(wall, i * D + X);
     }
     const int nb = m_count(wall);
-    if (nb < d.n_blocks) return 1;
+    if (nb < nB) return 1;
     // ---- goals (loc + icon variant), in creation order
     XwMask avail;
     for (int i = 0; i < 4; ++i) avail.w[i] = c.inrange.w[i] & ~wall.w[i];
-    for (int k = 0; k < d.G; ++k) {
+    for (int k = 0; k < nG; ++k) {
         int nf = m_count(avail);
         if (nf == 0) return 1;
         int cell = m_nth(avail, (int)xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_GOAL_LOC, (uint32_t)k), (uint32_t)nf));
@@ -151,7 +153,7 @@ XW_HD int xw_gen_map(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, XwM
         uint8_t bl[XW_MAX_DIM * XW_MAX_DIM / 2 + 8];
         int n = 0;
         for (int i = 0; i < D * D; ++i) if (m_get(wall, i)) bl[n++] = (uint8_t)i;
-        for (int k = 0; k < d.n_blocks; ++k) {
+        for (int k = 0; k < nB; ++k) {
             int i = nb - 1 - k;
             if (i >= 1) {
                 int j = (int)xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_BLOCKS, (uint32_t)k), (uint32_t)i + 1);
@@ -265,7 +267,7 @@ struct XwTaskOut { int tmask, aux0, aux1, aux2; };
 XW_HD bool xw_idle3d(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, int task, XwMapCtx& c, XwTaskOut& o) {
     uint8_t order[XW_MAX_DIM * XW_MAX_DIM];
     o.tmask = o.aux0 = o.aux1 = o.aux2 = 0;
-    const int G = d.G;
+    const int G = c.nG;
     XwMask obst;
     for (int i = 0; i < 4; ++i) obst.w[i] = c.block.w[i] | c.goal.w[i];
     if (task == XW_T3_TARGET || task == XW_T3_AVOID) {
@@ -380,9 +382,9 @@ XW_HD void xw_idle2d(const XwDev& d, int64_t gid, uint32_t ep, uint32_t step_no,
 // One attempt at a new episode: map + (navigation2d.json) the task's idle() stage.  A pure function of
 // (env id, episode, attempt): 1 = done, 0 = the reference's `assert ..., "map too crowded?"` -> next attempt,
 // 2 = the map itself cannot be built (configuration error).
-XW_HD int xw_reset_attempt(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, int task, XwMapCtx& c, XwTaskOut& o) {
+XW_HD int xw_reset_attempt(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, int task, int level, XwMapCtx& c, XwTaskOut& o) {
     o.tmask = o.aux0 = o.aux1 = o.aux2 = 0;
-    if (xw_gen_map(d, gid, ep, att, c)) return 2;
+    if (xw_gen_map(d, gid, ep, att, level, c)) return 2;
     if (d.rules != XW_RULES_NAV3D) return 1;
     return xw_idle3d(d, gid, ep, att, task, c, o) ? 1 : 0;
 }
@@ -393,18 +395,29 @@ XW_HD void xw_reset_commit(const XwDev& d, int e, uint32_t ep, uint32_t minstd, 
     const int64_t gid = d.gid0 + e;
     int stage = d.rules == XW_RULES_NAV3D ? XW_STAGE_NAVIGATION : XW_STAGE_IDLE;
     uint8_t* g = d.grid + (size_t)e * d.CS;
+    // cpp_get_entities (xworld_env.py:352-366): the world sits at (offset_w, offset_h) = ((max - dim) / 2, same) of
+    // the map, everything around it is brick (__padding_walls, :454-473); no offset when the world is the map
+    const int D = c.W, off = (d.W - D) / 2;
     for (int i = 0; i < d.CS; ++i) g[i] = XW_CELL_EMPTY;
-    for (int i = 0; i < d.H * d.W; ++i) if (m_get(c.block, i)) g[i] = XW_CELL_BLOCK;
+    if (D != d.W)
+        for (int y = 0; y < d.H; ++y)
+            for (int x = 0; x < d.W; ++x)
+                if (x < off || x >= off + D || y < off || y >= off + D) g[y * d.W + x] = XW_CELL_BLOCK;
+    for (int i = 0; i < D * D; ++i) if (m_get(c.block, i)) g[(i / D + off) * d.W + i % D + off] = XW_CELL_BLOCK;
     for (int k = 0; k < d.G; ++k) {
-        g[c.gcell[k]] = (uint8_t)(XW_CELL_GOAL0 + k);
-        d.goal_x[(size_t)k * n + e] = (uint8_t)(c.gcell[k] % d.W);
-        d.goal_y[(size_t)k * n + e] = (uint8_t)(c.gcell[k] / d.W);
-        d.goal_icon[(size_t)k * n + e] = c.gicon[k];
-        d.goal_name[(size_t)k * n + e] = c.gname[k];
+        const bool on = k < c.nG;  // levels 0-2 hold two goals (XWorldNav.py:31): the other slots read 0
+        const int gx = on ? c.gcell[k] % D + off : 0, gy = on ? c.gcell[k] / D + off : 0;
+        if (on) g[gy * d.W + gx] = (uint8_t)(XW_CELL_GOAL0 + k);
+        d.goal_x[(size_t)k * n + e] = (uint8_t)gx;
+        d.goal_y[(size_t)k * n + e] = (uint8_t)gy;
+        d.goal_icon[(size_t)k * n + e] = on ? c.gicon[k] : 0;
+        d.goal_name[(size_t)k * n + e] = on ? c.gname[k] : 0;
     }
-    g[c.agent] = XW_CELL_AGENT;
-    d.agent_x[e] = (uint8_t)(c.agent % d.W);
-    d.agent_y[e] = (uint8_t)(c.agent / d.W);
+    const int agx = c.agent % D + off, agy = c.agent / D + off;
+    g[agy * d.W + agx] = XW_CELL_AGENT;
+    d.agent_x[e] = (uint8_t)agx;
+    d.agent_y[e] = (uint8_t)agy;
+    if (task == XW_T3_BETWEEN && d.rules == XW_RULES_NAV3D) { o.aux1 += off; o.aux2 += off; }  // the middle cell, in map coordinates
     d.facing[e] = 1;  // yaw 1.5707963 == "down" (xworld_env.py:42, xitem.cpp:65-78)
     int32_t steps_in_task = 0;
     if (d.rules == XW_RULES_NAV2D) {
@@ -428,6 +441,45 @@ XW_HD void xw_reset_commit(const XwDev& d, int e, uint32_t ep, uint32_t minstd, 
     d.minstd[e] = minstd;
 }
 
+// XWorldNav._configure, curriculum != 0 (XWorldNav.py:40-56) + XWorldEnv.get_current_usage (xworld_env.py:103-110):
+// every reset counts; once `check_period` resets have passed and some task class has a record, usage = the lowest
+// success rate over the task classes' windows, and the level moves up when it reaches the threshold.  Runs once
+// per episode (a re-drawn "too crowded" map keeps the level).  Returns the level of the new episode.
+XW_HD int xw_curriculum_level(const XwDev& d, int e) {
+    if (d.curriculum == 0) return 0;
+    int level = d.level[e];
+    int cnt = d.check_counter[e] + 1;
+    double usage = 0;
+    if (cnt >= d.check_period) {
+        bool any = false;
+        for (int t = 0; t < XW_N_T3; ++t) {
+            const int len = d.win_len[(size_t)e * XW_N_T3 + t];
+            if (len == 0) continue;  // current_usage only holds the classes that recorded a result
+            const double u = (double)d.win_sum[(size_t)e * XW_N_T3 + t] / (double)len;
+            if (!any || u < usage) usage = u;
+            any = true;
+        }
+        if (any) cnt = 0; else usage = 0;
+    }
+    d.check_counter[e] = cnt;
+    if (usage >= d.curriculum && level < XW_N_LEVELS - 1) d.level[e] = (uint8_t)++level;
+    return level;
+}
+
+// XWorld3DTask.__record_result (xworld3d_task.py:129-133): append to the task class's success_seq, keep the last 200.
+XW_HD void xw_record_result(const XwDev& d, int e, int task, int res) {
+    if (d.curriculum == 0) return;  // the windows feed nothing but the curriculum
+    const size_t k = (size_t)e * XW_N_T3 + task;
+    int len = d.win_len[k], pos = d.win_pos[k], sum = d.win_sum[k];
+    uint32_t* w = d.win_bits + k * XW_WIN_WORDS;
+    uint32_t word = w[pos >> 5];
+    if (len == XW_WIN_SIZE) sum -= (int)((word >> (pos & 31)) & 1u); else ++len;
+    w[pos >> 5] = (word & ~(1u << (pos & 31))) | ((uint32_t)res << (pos & 31));
+    sum += res;
+    pos = pos + 1 == XW_WIN_SIZE ? 0 : pos + 1;
+    d.win_len[k] = (uint8_t)len; d.win_pos[k] = (uint8_t)pos; d.win_sum[k] = (uint8_t)sum;
+}
+
 // SimulatorInterface::reset_game for env `e` (simulator_interface.cpp:95-105), one thread: attempts in order.
 XW_HD void xw_reset_env(const XwDev& d, int e) {
     const int64_t gid = d.gid0 + e;
@@ -436,10 +488,11 @@ XW_HD void xw_reset_env(const XwDev& d, int e) {
     uint32_t minstd = d.minstd[e];
     const bool nav3d = d.rules == XW_RULES_NAV3D;
     const int task = nav3d ? xw_get_rand_ind(minstd, 5) : 0;  // TaskGroup::run_stage, schedule "random"
+    const int level = xw_curriculum_level(d, e);
     XwMapCtx c;
     XwTaskOut o;
     int st = 0;
-    for (uint32_t att = 0; att < (nav3d ? 64u : 1u) && st == 0; ++att) st = xw_reset_attempt(d, gid, ep, att, task, c, o);
+    for (uint32_t att = 0; att < (nav3d ? 64u : 1u) && st == 0; ++att) st = xw_reset_attempt(d, gid, ep, att, task, level, c, o);
     if (st != 1) { d.error[e] = XW_ERR_INVALID_ARG; return; }
     xw_reset_commit(d, e, ep, minstd, task, c, o);
 }
@@ -460,10 +513,13 @@ __device__ __forceinline__ void xw_reset_env_warp(const XwDev& d, int e) {
     if (lane == 0) d.episode[e] = (int32_t)ep;
     const bool nav3d = d.rules == XW_RULES_NAV3D;
     const int task = nav3d ? xw_get_rand_ind(minstd, 5) : 0;
+    int level = 0;
+    if (lane == 0) level = xw_curriculum_level(d, e);
+    level = __shfl_sync(0xffffffffu, level, 0);
     XwMapCtx c;
     XwTaskOut o;
     int st = 0;
-    if (lane == 0) st = xw_reset_attempt(d, gid, ep, 0, task, c, o);
+    if (lane == 0) st = xw_reset_attempt(d, gid, ep, 0, task, level, c, o);
     st = __shfl_sync(0xffffffffu, st, 0);
     if (st != 0 || !nav3d) {
         if (lane == 0) {
@@ -474,7 +530,7 @@ __device__ __forceinline__ void xw_reset_env_warp(const XwDev& d, int e) {
     }
     for (uint32_t base = 1; base < 64; base += 32) {
         const uint32_t att = base + lane;
-        st = att < 64 ? xw_reset_attempt(d, gid, ep, att, task, c, o) : 0;
+        st = att < 64 ? xw_reset_attempt(d, gid, ep, att, task, level, c, o) : 0;
         const unsigned done = __ballot_sync(0xffffffffu, st != 0);
         if (done) {
             if (lane == __ffs(done) - 1) {

@@ -74,7 +74,10 @@ XW_HD bool xw_step_env(const XwDev& d, int e, int action, int act_rep, float* re
         reward = XW_R3_STEP;
         int sit = d.steps_in_task[e] + 1;
         d.steps_in_task[e] = sit;
-        if (sit >= d.H * d.W * d.max_steps_factor) {
+        // h, w = self.env.get_dims(): the level's world, not the padded map (xworld3d_task.py:475-476)
+        const int side = d.curriculum != 0 ? 3 + d.level[e] : d.H;
+        if (sit >= side * side * d.max_steps_factor) {
+            xw_record_result(d, e, d.task[e], 0);
             d.n_failure[e] += 1;
             event = XW_EVENT_TIME_UP;
             stage = XW_STAGE_TERMINAL;
@@ -90,8 +93,12 @@ XW_HD bool xw_step_env(const XwDev& d, int e, int action, int act_rep, float* re
             } else if (task == XW_T3_DIRECTION) {
                 if (gr >= 0) {
                     const int ref = d.aux0[e];
-                    const int rdx = (int)d.goal_x[(size_t)ref * n + e] - (int)d.goal_x[(size_t)gr * n + e];
-                    const int rdy = (int)d.goal_y[(size_t)ref * n + e] - (int)d.goal_y[(size_t)gr * n + e];
+                    // the reference's referent is a stale Entity object whose loc cpp_get_entities shifted by the padding
+                    // offset in place (xworld_env.py:359-361): at curriculum levels 0-3 the test sees it displaced by
+                    // (off, off) -- reproduced, not fixed (oracle/xw_oracle.c xo_teach has the call sequence)
+                    const int off = (d.W - side) >> 1;
+                    const int rdx = (int)d.goal_x[(size_t)ref * n + e] - (int)d.goal_x[(size_t)gr * n + e] + off;
+                    const int rdy = (int)d.goal_y[(size_t)ref * n + e] - (int)d.goal_y[(size_t)gr * n + e] + off;
                     const int fx = facing == 0 ? 1 : facing == 2 ? -1 : 0, fy = facing == 1 ? 1 : facing == 3 ? -1 : 0;
                     const bool close = (rdx * rdx + rdy * rdy) <= 1;  // dist < 1 + 1e-3
                     correct = close && (rdx | rdy) != 0 && xw_axis_direction(fx, fy, rdx, rdy) == d.aux1[e];
@@ -101,9 +108,11 @@ XW_HD bool xw_step_env(const XwDev& d, int e, int action, int act_rep, float* re
                 if (gr >= 0) { correct = (d.tmask[e] >> gr) & 1; wrong = !correct; }
             }
             if (correct) {
+                xw_record_result(d, e, task, 1);
                 d.n_success[e] += 1; d.success_steps[e] += sit;
                 event = XW_EVENT_CORRECT_GOAL; reward = XW_R3_CORRECT; stage = XW_STAGE_TERMINAL;
             } else if (wrong) {
+                xw_record_result(d, e, task, 0);
                 d.n_failure[e] += 1;
                 event = XW_EVENT_WRONG_GOAL; reward = XW_R3_WRONG; stage = XW_STAGE_TERMINAL;
             }

@@ -150,8 +150,7 @@ class Simulator(object):
                 raise RuntimeError("task_mode '%s' is not implemented (lang_acquisition only)" % task_mode)
             if not _opt(opts, "color", False, False):
                 raise RuntimeError("color=False (grayscale) is not implemented; pass {'color': True}")
-            if float(_opt(opts, "curriculum", False, 0)) != 0:
-                raise RuntimeError("curriculum > 0 is not implemented")
+            curriculum = float(_opt(opts, "curriculum", False, 0))  # py_simulator.cpp:127
             catalog = opts.get("catalog")
             if catalog is None:
                 item_path = opts.get("item_path")
@@ -172,7 +171,9 @@ class Simulator(object):
                 n_goals=int(opts.get("n_goals", 4)), n_blocks=int(opts.get("n_blocks", default_blocks)),
                 rules=rules_from_conf(conf), out_h=int(opts.get("out_h", 0)), out_w=int(opts.get("out_w", 0)),
                 context=int(_opt(opts, "context", False, 1)), visible_radius=int(_opt(opts, "visible_radius", False, 0)),
-                max_steps=int(opts.get("max_steps", 0)), max_steps_factor=int(opts.get("max_steps_factor", 10)))
+                max_steps=int(opts.get("max_steps", 0)), max_steps_factor=int(opts.get("max_steps_factor", 10)),
+                curriculum=curriculum, curriculum_check_period=int(opts.get("curriculum_check_period", 0)),
+                start_level=int(opts.get("start_level", 0)))
         else:
             raise RuntimeError("Unrecognized game type: " + name)
         cfg.auto_reset = int(bool(opts.get("auto_reset", False)))
@@ -336,8 +337,10 @@ class Simulator(object):
         elif name in ("goal_icon", "goal_name"):
             out = np.zeros((n, _abi.XW_MAX_GOALS), np.int32)
         elif name in ("agent_x", "agent_y", "facing", "task", "stage", "event", "action_success", "target_mask",
-                      "aux0", "aux1", "aux2"):
+                      "aux0", "aux1", "aux2", "level"):
             out = np.zeros(n, np.uint8)
+        elif name in ("win_len", "win_sum"):
+            out = np.zeros((n, 5), np.uint8)
         elif name == "state":
             out = np.zeros((n, 4), np.float32)
         elif name in ("pos_x", "pos_y", "angle"):
