@@ -31,7 +31,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 ENVS_PER_GPU = 65536
 # The default ("c3") is the configuration BASELINE.json's metric is quoted on (64k envs, 11x11 maze, 84x84 frames);
-# --workload c2 / c4 time the other two XWorld2D configurations of BASELINE.json with the same contract.
+# --workload c2 / c4 time the other two XWorld2D configurations of BASELINE.json with the same contract;
+# --workload c5 the SimpleRace step kernel at 1,048,576 envs (BASELINE configs[4], render off).
 WORKLOADS = {
     "c3": dict(cfg=dict(height=11, width=11, n_goals=4, n_blocks=30, rules=1, out_h=84, out_w=84, max_steps=242,
                         auto_reset=1, seed=1234, simulator_seed=1),
@@ -133,6 +134,145 @@ def cpu_reference_arm(steps, warmup, sample_envs, threads):
     return sample_envs * steps / dt, dt
 
 
+RACE_BYTES_PER_ENV_STEP = 60  # pos_x, pos_y, angle, steps read + written (32) + action 4 + reward 4 + game_over 4 + state 16
+RACE_NAME = "SimpleRace straight track, easy, 2 actions, fp32 step kernel, 1,048,576 envs/GPU, render off (BASELINE configs[4])"
+
+
+def race_cpu_arm(sample_envs, steps):
+    """The C port of simple_race_simulator.cpp (bit-equal to the compiled reference, tests/test_oracle_pins.py), one thread."""
+    import numpy as np
+    import oracle
+    from xworld_b200 import _abi
+    L = oracle.lib()
+    cfg = _abi.default_config(game=_abi.XW_GAME_SIMPLE_RACE)
+    envs = (oracle.XoRace * sample_envs)()
+    for o in envs:
+        L.xo_race_reset(C.byref(cfg), C.byref(o))
+    rng = np.random.RandomState(0)
+    acts = np.ascontiguousarray(rng.randint(0, 2, (steps, sample_envs)), np.int32)
+    L.xo_race_batch.restype = C.c_double
+    L.xo_race_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    t0 = time.perf_counter()
+    L.xo_race_batch(C.byref(cfg), envs, sample_envs, acts.ctypes.data, steps)
+    dt = time.perf_counter() - t0
+    return sample_envs * steps / dt, dt
+
+
+def bench_race(args, rank, world, local_rank):
+    """--workload c5: BASELINE configs[4].  One k_race_step launch per step; the kernel is the whole step."""
+    config = {"workload": RACE_NAME, "envs_per_gpu": args.envs_per_gpu, "auto_reset": True, "actions": "iid uniform{0,1}",
+              "l2": "per step the kernel touches 60 B x 1,048,576 envs = 63 MB of state (< 126 MB L2): state stays L2-resident "
+                    "between steps by design -- the roofline figure is against HBM and is an upper bound on DRAM traffic",
+              "bytes_per_env_step": RACE_BYTES_PER_ENV_STEP}
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        v, dt = race_cpu_arm(65536, max(1, min(args.steps, 200)))
+        print(json.dumps({"impl": "reference", "metric": "env_steps_per_sec", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
+                          "steps": min(args.steps, 200), "warmup": 0, "ms_per_step": None, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port",
+                                           "sample": "65536 envs x %d steps, C port, one thread" % min(args.steps, 200)},
+                          "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+    import torch
+    from xworld_b200 import _abi
+    from xworld_b200.sharding import gather_throughput
+    from xworld_b200.simulator import Simulator
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.envs_per_gpu
+    cfg = _abi.default_config(game=_abi.XW_GAME_SIMPLE_RACE, auto_reset=1)
+    sim = Simulator("simple_race", cfg, None, n, local_rank)
+    lib, h = sim._lib, sim._h
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(7 + rank)
+    acts = [torch.randint(0, 2, (n,), dtype=torch.int32, device=dev, generator=gen) for _ in range(8)]
+    reward = torch.zeros(n, dtype=torch.float32, device=dev)
+    over = torch.zeros(n, dtype=torch.int32, device=dev)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    sim.reset_game()
+
+    def step(i):
+        rc = lib.xw_step(h, acts[i % 8].data_ptr(), 1, reward.data_ptr(), over.data_ptr(), None, stream)
+        if rc:
+            raise RuntimeError(lib.xw_last_error().decode())
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = sim.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = sim.launch_count() - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    total_steps, _, per_rank = gather_throughput(n * args.steps, int(ms * 1e6), device=dev)
+    h_act = [torch.randint(0, 2, (n,), dtype=torch.int32).pin_memory() for _ in range(4)]
+    h_rew = torch.zeros(n, dtype=torch.float32).pin_memory()
+    h_over = torch.zeros(n, dtype=torch.int32).pin_memory()
+    for i in range(5):
+        lib.xw_step_hd(h, h_act[i % 4].data_ptr(), 1, h_rew.data_ptr(), h_over.data_ptr(), None)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        assert lib.xw_step_hd(h, h_act[i % 4].data_ptr(), 1, h_rew.data_ptr(), h_over.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+    peak, peak_src = hbm_peak()
+    kernel_ms = ms / args.steps  # the step is this one kernel
+    achieved = RACE_BYTES_PER_ENV_STEP * n / (kernel_ms * 1e-3) / 1e9
+    line = {"metric": "env_steps_per_sec", "value": total_steps / (ms_max / 1e3), "unit": "env-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "roofline": {"bound": "hbm", "kernel": "k_race_step", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": kernel_ms,
+                         "kernel_share_of_step": 1.0, "algorithmic_bytes_per_launch": RACE_BYTES_PER_ENV_STEP * n,
+                         "note": "one launch per step (the agent's actions arrive per step): launch + tail latency, not "
+                                 "bandwidth, sets the time at this size"},
+            "gpu_launches": launches, "clocks": clocks, "per_rank": per_rank,
+            "e2e": {"value": n * world * args.steps / float(tt.item()), "unit": "env-steps/s", "h2d_bytes_per_step": 4 * n,
+                    "d2h_bytes_per_step": 8 * n, "steps": args.steps,
+                    "what": "xw_step_hd: pinned host actions -> H2D, k_race_step, reward + game_over D2H, stream sync"}}
+    if world == 1 and not args.no_cpu_baseline:
+        v, dt = race_cpu_arm(65536, 200)
+        line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port",
+                                "sample": "65536 envs x 200 steps (%.1f s), the C port (bit-equal to the compiled reference), one thread" % dt}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -140,7 +280,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=0, help="default: the workload's (65536; c4: 32768)")
-    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -148,6 +288,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     threads = os.cpu_count() or 1
+    if args.workload == "c5":
+        if args.envs_per_gpu <= 0:
+            args.envs_per_gpu = 1 << 20
+        return bench_race(args, rank, world, local_rank)
     wl = select_workload(args.workload)
     if args.envs_per_gpu <= 0:
         args.envs_per_gpu = wl["envs"]

@@ -1076,3 +1076,15 @@ float xo_race_act(const xw_config* cfg, xo_race* r, int action_index, float stat
     *game_over = code;
     return reward;
 }
+
+double xo_race_batch(const xw_config* cfg, xo_race* envs, int n, const int32_t* actions, int steps) {
+    double sum = 0;
+    float st[4];
+    int32_t over;
+    for (int s = 0; s < steps; ++s)
+        for (int i = 0; i < n; ++i) {
+            sum += xo_race_act(cfg, &envs[i], actions[(size_t)s * n + i], st, &over);
+            if (over) xo_race_reset(cfg, &envs[i]);
+        }
+    return sum;
+}

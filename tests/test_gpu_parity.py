@@ -231,6 +231,40 @@ def test_simple_race_vs_oracle_1e6(backend_cls):
         assert exact >= 0.999 * total, (exact, total)
 
 
+def test_simple_race_full_size_c5(backend_cls):
+    """BASELINE config 5 at its full size: 1,048,576 envs.  Envs start in the same state (random=false), so envs fed
+    the same action stream must stay bit-identical; 64 streams, each checked against the oracle (tol 1e-6)."""
+    lib = oracle.lib()
+    n, groups, steps = 1 << 20, 64, 120
+    for tt, full in [(0, 0), (1, 1)]:
+        cfg = _abi.default_config(game=_abi.XW_GAME_SIMPLE_RACE, track_type=tt, race_full_manouver=full, auto_reset=1)
+        eng = backend_cls(cfg, None, n)
+        eng.reset()
+        orcs = (oracle.XoRace * groups)()
+        for o in orcs:
+            lib.xo_race_reset(C.byref(cfg), C.byref(o))
+        rng = np.random.RandomState(3 + tt)
+        gid = np.arange(n) % groups
+        n_over = 0
+        for s in range(steps):
+            ga = rng.randint(0, 9 if full else 2, groups).astype(np.int32)
+            r, ov, _ = eng.step(ga[gid])
+            st = eng.field("state")
+            r2, st2, ov2 = np.zeros(groups, np.float32), np.zeros((groups, 4), np.float32), np.zeros(groups, np.int32)
+            for g in range(groups):
+                buf, o2 = (C.c_float * 4)(), C.c_int32()
+                r2[g] = lib.xo_race_act(C.byref(cfg), C.byref(orcs[g]), int(ga[g]), buf, C.byref(o2))
+                st2[g], ov2[g] = list(buf), o2.value
+                if o2.value:
+                    lib.xo_race_reset(C.byref(cfg), C.byref(orcs[g]))
+            # every env equals the first env of its group, bit for bit
+            assert (r.view(np.uint32) == r.view(np.uint32)[:groups][gid]).all(), s
+            assert (st.view(np.uint32) == st.view(np.uint32)[:groups][gid]).all() and (ov == ov[:groups][gid]).all(), s
+            assert np.abs(r[:groups] - r2).max() <= 1e-6 and np.abs(st[:groups] - st2).max() <= 1e-6 and (ov[:groups] == ov2).all(), s
+            n_over += int((ov2 != 0).sum())
+        assert n_over > 0 or tt == 0
+
+
 @pytest.mark.parametrize("name,n", [("c3_nav2d_11x11_84", 65536), ("c2_nav3d_7x7_84", 65536), ("c4_nav3d_15x15_128", 32768),
                                     ("ref_nav3d_8x8_96", 16384)])
 def test_painter_equals_plan_compositor_full_size(name, n, synthetic_catalog, monkeypatch):
