@@ -72,6 +72,11 @@ enum {
     XW_T2_TARGET = 0, XW_T2_NEAR = 1, XW_T2_COLOR_TARGET = 2, XW_T2_BETWEEN = 3
 };
 
+/* An action id that makes xw_step / xw_step_host / xw_step_hd leave that env alone: no move, no teacher call, no step
+ * count, and its reward / game_over output slots are not written.  The reference has no such thing (one process per
+ * env: an env that is not stepped is simply not called); a batch needs it to serve callers that step envs one at a
+ * time (xworld_b200/wire.py).  The frame of such an env is re-rendered unchanged. */
+#define XW_ACTION_NONE (-1)
 /* Grid cell codes (one item per cell in navigation maps; XMap::item_ptr_cube_, xmap.h:95). */
 enum { XW_CELL_EMPTY = 0, XW_CELL_BLOCK = 1, XW_CELL_AGENT = 2, XW_CELL_GOAL0 = 3 };
 
@@ -213,6 +218,48 @@ typedef struct xw_sentence_query {
 } xw_sentence_query;
 int xw_sentence_compose(const xw_sentence_query* q, char* buf, size_t cap);
 
+/* ---- SimulatorServer / SimulatorClient wire format, host side, no sockets ------------------------------
+ * The reference runs one simulator process per env; the trainer's SimulatorServer (simulator_interface.cpp:165-320)
+ * sends each a length-prefixed util::BinaryBuffer message (simulator_communication.h:34-76,222-240; memory_util.h:83-115)
+ * whose packets are StatePacket::encode (data_packet.h:315-333, data_packet.cpp:137-174), and SimulatorClient::
+ * simulation_loop (simulator_interface.cpp:361-435) answers.  These functions parse those requests and build those
+ * replies byte for byte, so that N such connections can be served from the N envs of one batch (xworld_b200/wire.py).
+ * Encoders return the number of bytes the message takes and write it only if it fits in `cap` (out may be NULL to
+ * size a buffer); replies and requests are FRAMED: 8-byte body size, then the body. */
+#define XW_WIRE_MAX_FIELDS 8
+typedef struct xw_wire_field {     /* one StatePacket entry = key + StateBuffer; a NULL pointer = that part is absent */
+    const char* key;
+    const float* reals;   uint64_t n_reals;   /* std::vector<float>   (flag bit 1) */
+    const uint8_t* pixels; uint64_t n_pixels; /* std::vector<uint8_t> (flag bit 2) */
+    const int32_t* ids;   uint64_t n_ids;     /* std::vector<int>     (flag bit 4) */
+    const char* str;                          /* std::string          (flag bit 8) */
+} xw_wire_field;
+typedef struct xw_wire_request {
+    const char* cmd;        /* "reset" | "take_actions" | "get_state" | "report_perf" | "get_extra_info" | "stop" */
+    int32_t act_rep;        /* take_actions */
+    int32_t show_screen;    /* take_actions */
+    float reward;           /* get_state */
+    int32_t n_fields;       /* take_actions: the action packet ("action" ids, "pred_sentence" str) */
+    xw_wire_field fields[XW_WIRE_MAX_FIELDS];
+} xw_wire_request;
+/* StatePacket::encode / decode.  Decoded pointers point INTO `in` (keys and strings are NUL-terminated on the wire);
+ * float / int arrays may be unaligned there: memcpy them out. */
+int64_t xw_wire_encode_packet(const xw_wire_field* fields, int32_t n_fields, uint8_t* out, size_t cap);
+int xw_wire_decode_packet(const uint8_t* in, size_t len, xw_wire_field* fields, int32_t max_fields, int32_t* n_fields,
+                          size_t* consumed);
+/* A request body (after the 8-byte size), as CommServer::call_remote_func composes it. */
+int xw_wire_parse_request(const uint8_t* body, size_t len, xw_wire_request* req);
+/* The server side of the same, for tests and for trainers written against this library. */
+int64_t xw_wire_compose_request(const char* cmd, const xw_wire_field* fields, int32_t n_fields, int32_t act_rep, int32_t show_screen,
+                        float reward, uint8_t* out, size_t cap);
+/* SimulatorClient::reset_game / take_actions / get_state / get_extra_info replies (simulator_interface.cpp:385-435);
+ * xw_wire_reply_text(cmd, NULL) is the echo that answers "report_perf". */
+int64_t xw_wire_reply_reset(int32_t num_actions, int32_t game_over, int32_t lives, uint64_t height, uint64_t width,
+                            uint64_t channels, double X, double Y, double Z, uint8_t* out, size_t cap);
+int64_t xw_wire_reply_take_actions(float reward, int64_t num_steps, int32_t game_over, int32_t lives, int32_t action_success,
+                                   const char* last_action, uint8_t* out, size_t cap);
+int64_t xw_wire_reply_get_state(const xw_wire_field* fields, int32_t n_fields, uint8_t* out, size_t cap);
+int64_t xw_wire_reply_text(const char* cmd, const char* text, uint8_t* out, size_t cap);
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t xw_launch_count(const xw_sim* sim);
 /* Which render kernel the handle uses (diagnostics, tests): 0 = generic per-byte kernel, 1 = plan compositor with

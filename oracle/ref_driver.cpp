@@ -3,7 +3,9 @@
 //
 // Exposes: SimpleGame (games/simple_game), SimpleRaceGame physics (games/simple_race), XMap/XAgent
 // step logic (games/xworld/xworld/xmap.cpp, xitem.cpp) and util::get_rand_ind (simulator_util.cpp).
+#include <algorithm>
 #include <cstring>
+#include <string>
 #include <memory>
 #include <thread>
 #include <vector>
@@ -12,6 +14,8 @@
 #include "games/simple_race/simple_race_simulator.h"
 #include "games/xworld/xworld/xmap.h"
 #include "simulator_util.h"
+#include "memory_util.h"
+#include "data_packet.h"
 
 DECLARE_int32(array_size);
 DECLARE_int32(simulator_seed);
@@ -108,6 +112,102 @@ int ref_map_act(void* p, int action, int* ax, int* ay, double* yaw, int* contact
     return ok ? 1 : 0;
 }
 int ref_map_num_actions(void* p) { return ((RefMap*)p)->agent->get_num_actions(); }
+
+// ---- wire format: the reference's own util::BinaryBuffer (memory_util.h) and StatePacket::encode/decode
+// (data_packet.h:315-333, data_packet.cpp:137-174).  The message bodies are composed with the same append sequence
+// as CommServer::call_remote_func / Communicator::compose_msg (simulator_communication.h:160-176,222-240) and the
+// SimulatorClient replies (simulator_interface.cpp:385-435); deliver_msg's header insert is simulator_communication.cpp:31-38
+// (that TU needs boost::asio and is not compiled here).
+struct RefField { const char* key; const float* reals; uint64_t n_reals; const uint8_t* pixels; uint64_t n_pixels;
+                  const int* ids; uint64_t n_ids; const char* str; };
+static void ref_fill_packet(StatePacket& p, const RefField* f, int n) {
+    for (int i = 0; i < n; ++i) {
+        p.add_key(f[i].key);
+        auto b = p.get_buffer(f[i].key);
+        if (f[i].reals) b->set_value(f[i].reals, f[i].reals + f[i].n_reals);
+        if (f[i].pixels) b->set_value(f[i].pixels, f[i].pixels + f[i].n_pixels);
+        if (f[i].ids) b->set_id(f[i].ids, f[i].ids + f[i].n_ids);
+        if (f[i].str) b->set_str(f[i].str);
+    }
+}
+static long ref_emit(util::BinaryBuffer& buf, bool framed, uint8_t* out, long cap) {
+    if (framed) buf.insert(0, (size_t)buf.size());  // MessageHeader::insert_into_msg
+    if ((long)buf.size() <= cap) std::memcpy(out, buf.data(), buf.size());
+    return (long)buf.size();
+}
+long ref_wire_encode_packet(const RefField* f, int n, uint8_t* out, long cap) {
+    StatePacket p; ref_fill_packet(p, f, n);
+    util::BinaryBuffer buf; p.encode(buf);
+    return ref_emit(buf, false, out, cap);
+}
+// decodes with the reference's code and writes a canonical text dump (keys sorted) for comparison
+long ref_wire_decode_dump(const uint8_t* in, long len, char* out, long cap) {
+    util::BinaryBuffer buf(in, (size_t)len);
+    buf.rewind();
+    StatePacket p; p.decode(buf);
+    auto keys = p.get_keys();
+    std::sort(keys.begin(), keys.end());
+    std::string s;
+    for (auto& k : keys) {
+        auto b = p.get_buffer(k);
+        s += k + "|";
+        util::BinaryBuffer one; b->encode(one);   // flags + present parts, the reference's own layout
+        static const char* hex = "0123456789abcdef";
+        for (size_t i = 0; i < one.size(); ++i) { s += hex[one.data()[i] >> 4]; s += hex[one.data()[i] & 15]; }
+        s += "\n";
+    }
+    if ((long)s.size() + 1 <= cap) std::memcpy(out, s.c_str(), s.size() + 1);
+    return (long)s.size() + 1;
+}
+long ref_wire_request(const char* cmd, const RefField* f, int n, int act_rep, int show_screen, float reward, uint8_t* out, long cap) {
+    util::BinaryBuffer buf;
+    std::string name(cmd);
+    buf.append(name);
+    if (name == "take_actions") {   // compose_msg(*sim_data, func_name, act_rep, show_screen): args first, packet last
+        buf.append(act_rep); buf.append((bool)show_screen);
+        StatePacket p; ref_fill_packet(p, f, n); p.encode(buf);
+    } else if (name == "get_state") {
+        buf.append(reward);
+    }
+    return ref_emit(buf, true, out, cap);
+}
+long ref_wire_reply_reset(int num_actions, int game_over, int lives, size_t h, size_t w, size_t c, double X, double Y, double Z,
+                          uint8_t* out, long cap) {
+    util::BinaryBuffer buf;
+    buf.append(std::string("reset")); buf.append(num_actions); buf.append(game_over); buf.append(lives);
+    buf.append(h); buf.append(w); buf.append(c); buf.append(X); buf.append(Y); buf.append(Z);
+    return ref_emit(buf, true, out, cap);
+}
+long ref_wire_reply_take_actions(float reward, int64_t num_steps, int game_over, int lives, int success, const char* last_action,
+                                 uint8_t* out, long cap) {
+    util::BinaryBuffer buf;
+    buf.append(std::string("take_actions")); buf.append(reward); buf.append(num_steps); buf.append(game_over); buf.append(lives);
+    buf.append((bool)success); buf.append(std::string(last_action));
+    return ref_emit(buf, true, out, cap);
+}
+long ref_wire_reply_get_state(const RefField* f, int n, uint8_t* out, long cap) {
+    util::BinaryBuffer buf;
+    buf.append(std::string("get_state"));
+    StatePacket p; ref_fill_packet(p, f, n); p.encode(buf);
+    return ref_emit(buf, true, out, cap);
+}
+long ref_wire_reply_text(const char* cmd, const char* text, uint8_t* out, long cap) {
+    util::BinaryBuffer buf;
+    buf.append(std::string(cmd));
+    if (text) buf.append(std::string(text));
+    return ref_emit(buf, true, out, cap);
+}
+// reads a take_actions reply the way SimulatorServer::take_actions does (simulator_interface.cpp:279-282)
+int ref_wire_read_take_actions_reply(const uint8_t* body, long len, float* r, int64_t* num_steps, int* game_over, int* lives,
+                                     int* success, char* last_action, long cap) {
+    util::BinaryBuffer buf(body, (size_t)len);
+    buf.rewind();
+    std::string reply, la; bool ok;
+    buf.read(reply); buf.read(*r); buf.read(*num_steps); buf.read(*game_over); buf.read(*lives); buf.read(ok); buf.read(la);
+    *success = ok;
+    if ((long)la.size() + 1 <= cap) std::memcpy(last_action, la.c_str(), la.size() + 1);
+    return reply == "take_actions" && buf.eof() ? 0 : -1;
+}
 
 // ---- util::get_rand_ind on fresh threads (tests/test_simulator_seed.cpp) ----
 void ref_rand_ind_threads(int simulator_seed, int n_threads, int size, int* out) {

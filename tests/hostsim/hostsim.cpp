@@ -213,7 +213,7 @@ void hs_step(HostSim* s, const int32_t* actions, int act_rep, float* reward, int
         return;
     }
     for (int e = 0; e < s->d.n; ++e)
-        if (xw_step_env(s->d, e, actions[e], act_rep, &reward[e], &over[e])) xw_reset_env(s->d, e);
+        if (actions[e] != XW_ACTION_NONE && xw_step_env(s->d, e, actions[e], act_rep, &reward[e], &over[e])) xw_reset_env(s->d, e);
 }
 
 // Emulates one k_render warp group per env: celldesc, every item of the plan, copy out.  Configs the

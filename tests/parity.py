@@ -187,3 +187,36 @@ def run_parity(backend, orc, n_steps, render_every=0, act_rep=1, check_state_eve
             stats["frames"] += n
     compare_state(backend, orc, "final")
     return stats
+
+
+def run_partial_parity(backend, orc, n_steps, p_step=0.6, render_every=0, seed=5):
+    """XW_ACTION_NONE: every step a random subset of the envs acts, the others sit it out.  The oracle steps only
+    the subset (the reference: an env that is not stepped is simply not called); state of ALL envs, and the reward /
+    game_over of the subset, must agree; finished games of the subset are reset by the caller."""
+    import ctypes as C
+    n = orc.n
+    backend.reset()
+    orc.reset()
+    rng = np.random.RandomState(seed)
+    stepped = 0
+    for s in range(n_steps):
+        m = rng.rand(n) < p_step
+        a = actions_for(s, n, 4, seed)
+        a_eng = np.where(m, a, _abi.XW_ACTION_NONE).astype(np.int32)
+        r1, o1, f1 = backend.step(a_eng, 1, render=bool(render_every) and s % render_every == 0)
+        done = np.zeros(n, np.uint8)
+        for i in np.nonzero(m)[0]:
+            r, ov = C.c_float(), C.c_int32()
+            rc = orc.L.xo_step(C.byref(orc.cfg), C.byref(orc.cat_c), C.byref(orc.envs[i]), int(a[i]), 1, C.byref(r), C.byref(ov))
+            assert rc == 0
+            assert np.float32(r.value).view(np.uint32) == r1[i].view(np.uint32) and ov.value == o1[i], (s, i)
+            done[i] = ov.value != 0
+        stepped += int(m.sum())
+        if f1 is not None:
+            f2 = orc.render()
+            assert (f1 == f2).all(), "step %d: frames differ" % s
+        if done.any():
+            backend.reset(done)
+            orc.reset(done)
+        compare_state(backend, orc, "partial step %d" % s)
+    return stepped

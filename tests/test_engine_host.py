@@ -45,6 +45,15 @@ def test_hostsim_curriculum(kw, n, steps, synthetic_catalog):
         assert lv.max() >= 1
 
 
+def test_hostsim_action_none(synthetic_catalog):
+    """XW_ACTION_NONE (include/xworld_b200.h): envs that sit a step out are untouched."""
+    for name in ("c2_nav3d_7x7_84", "c3_nav2d_11x11_84"):
+        cfg = parity.make_cfg(name)
+        hs = parity.HostSim(cfg, synthetic_catalog, 24)
+        orc = oracle.Oracle(cfg, synthetic_catalog, 24, threads=1)
+        assert parity.run_partial_parity(hs, orc, 80, render_every=40) > 500
+
+
 def test_hostsim_act_rep_and_global_ids(synthetic_catalog):
     cfg = parity.make_cfg("c2_nav3d_7x7_84", env_id_offset=1000, seed=42, simulator_seed=7)
     hs = parity.HostSim(cfg, synthetic_catalog, 32)

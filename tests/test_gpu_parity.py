@@ -231,6 +231,89 @@ def test_simple_race_vs_oracle_1e6(backend_cls):
         assert exact >= 0.999 * total, (exact, total)
 
 
+def test_action_none_and_batch_client(backend_cls, synthetic_catalog):
+    """XW_ACTION_NONE through the C ABI (envs that sit a step out are untouched, their output slots keep their last
+    values), then the same engine behind the reference's TCP protocol: wire.BatchClient with one connection per env."""
+    import socket
+    import struct
+    import threading
+    from xworld_b200 import wire
+    for name in ("c2_nav3d_7x7_84", "c3_nav2d_11x11_84"):
+        cfg = parity.make_cfg(name)
+        eng = backend_cls(cfg, synthetic_catalog, 512)
+        orc = oracle.Oracle(cfg, synthetic_catalog, 512, threads=8)
+        assert parity.run_partial_parity(eng, orc, 60, render_every=20) > 10000
+    # ---- the wire protocol in front of a GPU batch
+    n = 8
+    cfg = parity.make_cfg("c2_nav3d_7x7_84")
+    eng = backend_cls(cfg, synthetic_catalog, n)
+    orc = oracle.Oracle(cfg, synthetic_catalog, n, threads=1)
+    lsocks = []
+    for _ in range(n):
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        s.listen(1)
+        lsocks.append(s)
+    box = {}
+
+    def run():
+        box["c"] = wire.BatchClient(eng.sim, [s.getsockname()[1] for s in lsocks])
+        box["c"].serve()
+
+    th = threading.Thread(target=run, daemon=True)
+    th.start()
+    conns = [s.accept()[0] for s in lsocks]
+
+    def read_msg(c):
+        b = b""
+        while len(b) < 8:
+            b += c.recv(8 - len(b))
+        size = struct.unpack("<Q", b)[0]
+        body = b""
+        while len(body) < size:
+            body += c.recv(size - len(body))
+        return body
+
+    for c in conns:
+        c.sendall(wire.compose_request("reset"))
+    for c in conns:
+        body = read_msg(c)
+        assert body[8:13] == b"reset" and struct.unpack("<iii", body[14:26]) == (4, 0, 1)
+        assert struct.unpack("<QQQddd", body[26:74]) == (84, 84, 3, 7.0, 7.0, 0.0)
+    orc.reset()
+    rng = np.random.RandomState(1)
+    for it in range(40):
+        who = [i for i in range(n) if rng.rand() < 0.6] or [3]
+        acts = {i: int(rng.randint(0, 4)) for i in who}
+        for i in who:
+            conns[i].sendall(wire.compose_request("take_actions", {"action": acts[i], "pred_sentence": ""}))
+        for i in who:
+            body = read_msg(conns[i])
+            assert body[8:20] == b"take_actions"
+            r, num_steps, over, lives, ok = struct.unpack("<fqiiB", body[21:42])
+            r2, o2 = C.c_float(), C.c_int32()
+            assert orc.L.xo_step(C.byref(orc.cfg), C.byref(orc.cat_c), C.byref(orc.envs[i]), acts[i], 1, C.byref(r2), C.byref(o2)) == 0
+            e = orc.envs[i]
+            assert (np.float32(r), num_steps, over, lives, ok) == (np.float32(r2.value), e.num_steps, o2.value, 0 if o2.value else 1,
+                                                                   e.action_success), (it, i)
+            if over:
+                conns[i].sendall(wire.compose_request("reset"))
+                read_msg(conns[i])
+                m = np.zeros(n, np.uint8)
+                m[i] = 1
+                orc.reset(m)
+    conns[2].sendall(wire.compose_request("get_state", reward=0.0))
+    st = wire.decode_packet(read_msg(conns[2])[8 + 10:])
+    assert (st["screen"].reshape(3, 84, 84) == orc.render([2])[0]).all() and isinstance(st["sentence"], str)
+    conns[5].sendall(wire.compose_request("get_extra_info"))
+    assert b"height:7,width:7" in read_msg(conns[5])
+    for c in conns:
+        c.sendall(wire.compose_request("stop"))
+    th.join(timeout=20)
+    assert not th.is_alive() and box["c"].batches < box["c"].steps_served
+    parity.compare_state(eng, orc, "after the wire session")
+
+
 def test_simple_race_full_size_c5(backend_cls):
     """BASELINE config 5 at its full size: 1,048,576 envs.  Envs start in the same state (random=false), so envs fed
     the same action stream must stay bit-identical; 64 streams, each checked against the oracle (tol 1e-6)."""

@@ -7,6 +7,8 @@ import os
 
 XW_ABI_VERSION = 1
 XW_MAX_GOALS = 8
+XW_ACTION_NONE = -1
+XW_WIRE_MAX_FIELDS = 8
 XW_MAX_DIM = 16
 XW_ICON_SIZE = 64
 
@@ -100,12 +102,25 @@ class XwSentenceQuery(C.Structure):
                 ("seed", C.c_uint64), ("env_id", C.c_int64), ("episode", C.c_uint32), ("salt", C.c_uint32)]
 
 
+class XwWireField(C.Structure):
+    _fields_ = [("key", C.c_char_p), ("reals", C.POINTER(C.c_float)), ("n_reals", C.c_uint64),
+                ("pixels", C.POINTER(C.c_uint8)), ("n_pixels", C.c_uint64), ("ids", C.POINTER(C.c_int32)), ("n_ids", C.c_uint64),
+                ("str", C.c_char_p)]
+
+
+class XwWireRequest(C.Structure):
+    _fields_ = [("cmd", C.c_char_p), ("act_rep", C.c_int32), ("show_screen", C.c_int32), ("reward", C.c_float),
+                ("n_fields", C.c_int32), ("fields", XwWireField * XW_WIRE_MAX_FIELDS)]
+
+
 # every symbol include/xworld_b200.h declares
 SYMBOLS = [
     "xw_config_init", "xw_create", "xw_destroy", "xw_last_error", "xw_reset", "xw_step", "xw_render",
     "xw_step_host", "xw_reset_host", "xw_step_hd", "xw_num_envs", "xw_num_actions", "xw_screen_dims",
     "xw_frame_bytes", "xw_num_steps", "xw_get_field", "xw_set_field", "xw_launch_count", "xw_render_kernel", "xw_sentence_compose",
     "xw_enable_timing", "xw_render_ms",
+    "xw_wire_encode_packet", "xw_wire_decode_packet", "xw_wire_parse_request", "xw_wire_compose_request", "xw_wire_reply_reset",
+    "xw_wire_reply_take_actions", "xw_wire_reply_get_state", "xw_wire_reply_text",
 ]
 
 
@@ -164,5 +179,22 @@ def load():
     lib.xw_enable_timing.restype = C.c_int
     lib.xw_render_ms.argtypes = [vp, i32]
     lib.xw_render_ms.restype = C.c_double
+    u8p, sz, wf = C.POINTER(C.c_uint8), C.c_size_t, C.POINTER(XwWireField)
+    lib.xw_wire_encode_packet.argtypes = [wf, i32, u8p, sz]
+    lib.xw_wire_encode_packet.restype = i64
+    lib.xw_wire_decode_packet.argtypes = [u8p, sz, wf, i32, C.POINTER(i32), C.POINTER(sz)]
+    lib.xw_wire_decode_packet.restype = C.c_int
+    lib.xw_wire_parse_request.argtypes = [u8p, sz, C.POINTER(XwWireRequest)]
+    lib.xw_wire_parse_request.restype = C.c_int
+    lib.xw_wire_compose_request.argtypes = [C.c_char_p, wf, i32, i32, i32, C.c_float, u8p, sz]
+    lib.xw_wire_compose_request.restype = i64
+    lib.xw_wire_reply_reset.argtypes = [i32, i32, i32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_double, C.c_double, u8p, sz]
+    lib.xw_wire_reply_reset.restype = i64
+    lib.xw_wire_reply_take_actions.argtypes = [C.c_float, i64, i32, i32, i32, C.c_char_p, u8p, sz]
+    lib.xw_wire_reply_take_actions.restype = i64
+    lib.xw_wire_reply_get_state.argtypes = [wf, i32, u8p, sz]
+    lib.xw_wire_reply_get_state.restype = i64
+    lib.xw_wire_reply_text.argtypes = [C.c_char_p, C.c_char_p, u8p, sz]
+    lib.xw_wire_reply_text.restype = i64
     _LIB = lib
     return lib

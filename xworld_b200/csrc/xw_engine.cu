@@ -12,6 +12,7 @@
 
 #include "xw_common.cuh"
 #include "xw_race.cuh"
+#include "xw_wire.hpp"
 #include "xw_render.cuh"
 #include "xw_render_host.hpp"
 #include "xw_sentence.hpp"
@@ -55,8 +56,10 @@ __global__ void __launch_bounds__(256) k_step(XwDev d, const int32_t* __restrict
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e == 0) d.reset_count[parity ^ 1] = 0;  // consumed by the previous step's reset launch
     if (e >= d.n) return;
+    const int32_t a = actions[e];
+    if (a == XW_ACTION_NONE) return;  // this env sits the step out: state and its reward / game_over slots untouched
     float r; int32_t o;
-    bool need = xw_step_env(d, e, actions[e], act_rep, &r, &o);
+    bool need = xw_step_env(d, e, a, act_rep, &r, &o);
     reward[e] = r; over[e] = o;
     if (need) {  // warp-aggregated append to the auto-reset queue
         unsigned m = __activemask();
@@ -78,6 +81,7 @@ __global__ void __launch_bounds__(256) k_race_step(XwRaceCfg r, const int32_t* _
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= r.n) return;
     int a = actions[e];
+    if (a == XW_ACTION_NONE) return;
     if (a < 0 || a >= n_actions) { error[e] = XW_ERR_INVALID_ACTION; reward[e] = 0.f; over[e] = 0; return; }
     float rw; int32_t o;
     bool need = xw_race_step_env(r, e, a, &rw, &o);
@@ -759,6 +763,7 @@ int xw_step_host(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float* h_
     if (s->cfg.game == XW_GAME_SIMPLE_GAME) {
         for (int i = 0; i < s->n; ++i) {
             SimpleGameEnv& g = s->sg[i];
+            if (h_actions[i] == XW_ACTION_NONE) continue;
             if (h_actions[i] < 0 || h_actions[i] >= 2) return set_err(XW_ERR_INVALID_ACTION, "undefined action_id: %d", h_actions[i]);
             float r = 0;
             g.num_steps++;

@@ -265,8 +265,8 @@ class Simulator(object):
             a = np.ascontiguousarray(actions, np.int32).reshape(-1)
             if a.size != self.n_envs:
                 raise RuntimeError("expected %d actions" % self.n_envs)
-        r = np.zeros(self.n_envs, np.float32)
-        o = np.zeros(self.n_envs, np.int32)
+        r = np.array(self._last_reward, np.float32)  # envs given XW_ACTION_NONE keep their last reward / game_over
+        o = np.array(self._last_over, np.int32)
         if not self._on_gpu:
             self._check(self._lib.xw_step_host(self._h, a.ctypes.data, int(act_rep), r.ctypes.data, o.ctypes.data,
                                                self._screen.ctypes.data))
