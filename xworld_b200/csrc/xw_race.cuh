@@ -58,7 +58,12 @@ XW_HD bool xw_race_step_env(const XwRaceCfg& r, int e, int action_index, float* 
     float ang = XW_FA(r.angle[e], d_turn);
     if ((double)ang > 2 * XW_RACE_PI) ang = (float)((double)ang - 2 * XW_RACE_PI);
     else if (ang < 0) ang = (float)((double)ang + 2 * XW_RACE_PI);
+#if defined(__CUDA_ARCH__)
+    double ca, sa;
+    sincos((double)ang, &sa, &ca);  // one argument reduction for both (same polynomials as cos() / sin())
+#else
     const double ca = cos((double)ang), sa = sin((double)ang);
+#endif
     const float cx = (float)ca, sx = (float)sa;
     const float px = XW_FA(r.pos_x[e], XW_FM(d_forward, cx));
     const float py = XW_FA(r.pos_y[e], XW_FM(d_forward, sx));
