@@ -203,6 +203,53 @@ XW_HD bool xw_reachable(const XwMapCtx& c, const XwMask& obst, int start, int en
     return xw_bfs(c, obst, start, end, end, scratch) == -2;
 }
 
+// Set of cells reachable from `seed` through cells outside `obst` (4-neighbourhood), seed included: the same set
+// maze2d.flood_fill / bfs discover (python/maze2d.py:21-63), grown a whole frontier at a time with 256-bit shifts
+// instead of a queue.  Used where only membership matters (which goals can be reached), not discovery order.
+XW_HD XwMask xw_flood(const XwMapCtx& c, const XwMask& obst, int seed) {
+    const int D = c.W, n = c.H * c.W;
+    XwMask free_, not_first, not_last, reach;  // not_first / not_last: cells with x != 0 / x != W-1
+    m_zero(not_first); m_zero(not_last); m_zero(reach);
+    for (int i = 0; i < 4; ++i) free_.w[i] = c.inrange.w[i] & ~obst.w[i];
+    for (int y = 0; y < c.H; ++y) {
+        // a row is at most 16 bits: OR it into the (at most two) words it touches
+        const uint64_t row_nf = ((1ull << D) - 1) & ~1ull, row_nl = ((1ull << (D - 1)) - 1);
+        const int b = y * D, w = b >> 6, s = b & 63;
+        not_first.w[w] |= row_nf << s; not_last.w[w] |= row_nl << s;
+        if (s + D > 64 && w < 3) { not_first.w[w + 1] |= row_nf >> (64 - s); not_last.w[w + 1] |= row_nl >> (64 - s); }
+    }
+    (void)n;
+    m_set(reach, seed);
+    m_set(free_, seed);
+    while (true) {
+        XwMask nx;
+        uint64_t changed = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint64_t lo = i > 0 ? reach.w[i - 1] : 0, hi = i < 3 ? reach.w[i + 1] : 0, me = reach.w[i];
+            const uint64_t right = ((me << 1) | (lo >> 63)) & not_first.w[i];          // x + 1
+            const uint64_t left = ((me >> 1) | (hi << 63)) & not_last.w[i];            // x - 1
+            const uint64_t down = (me << D) | (lo >> (64 - D));                         // y + 1
+            const uint64_t up = (me >> D) | (hi << (64 - D));                           // y - 1
+            nx.w[i] = (me | right | left | down | up) & free_.w[i];
+            changed |= nx.w[i] ^ me;
+        }
+        if (!changed) break;
+        reach = nx;
+    }
+    return reach;
+}
+// is any 4-neighbour of `cell` (or the cell itself) in `set`?  == "a walk that ends by entering `cell` exists"
+XW_HD bool xw_touches(const XwMapCtx& c, const XwMask& set, int cell) {
+    const int x = cell % c.W, y = cell / c.W;
+    if (m_get(set, cell)) return true;
+    if (x > 0 && m_get(set, cell - 1)) return true;
+    if (x + 1 < c.W && m_get(set, cell + 1)) return true;
+    if (y > 0 && m_get(set, cell - c.W)) return true;
+    if (y + 1 < c.H && m_get(set, cell + c.W)) return true;
+    return false;
+}
+
 // -------------------------------------------------------------------------- tiles
 // Enumerates the reference's p/t/l tiles in its own order; returns the count and, when
 // pick >= 0, the pick-th pair in (a, b).  Two passes (count, then pick) avoid materialising lists.
@@ -271,9 +318,12 @@ XW_HD bool xw_idle3d(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, int
     XwMask obst;
     for (int i = 0; i < 4; ++i) obst.w[i] = c.block.w[i] | c.goal.w[i];
     if (task == XW_T3_TARGET || task == XW_T3_AVOID) {
+        // _reachable(agent.loc, g.loc) per goal (XWorld3DNavTarget.py:31): goals and blocks are obstacles, the end cell
+        // is enterable -> one flood from the agent, then "does the flood touch the goal"
         int cand = 0, nc = 0;
+        const XwMask reach = xw_flood(c, obst, c.agent);
         for (int g = 0; g < G; ++g)
-            if (xw_reachable(c, obst, c.agent, c.gcell[g], order)) { cand |= 1 << g; ++nc; }
+            if (xw_touches(c, reach, c.gcell[g])) { cand |= 1 << g; ++nc; }
         if (nc == 0) return false;
         int k = (int)xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_TASK_A, 0), (uint32_t)nc);
         int sel = 0;
@@ -423,10 +473,10 @@ XW_HD void xw_reset_commit(const XwDev& d, int e, uint32_t ep, uint32_t minstd, 
     if (d.rules == XW_RULES_NAV2D) {
         // per-episode constants for the 2-D idle stages: goals reachable through non-block cells,
         // goals whose icon has a colour (properties.txt)
-        uint8_t order[XW_MAX_DIM * XW_MAX_DIM];
         int reach = 0, colored = 0;
+        const XwMask rset = xw_flood(c, c.block, c.agent);  // only blocks are obstacles here: goals are walked over
         for (int k = 0; k < d.G; ++k) {
-            if (xw_reachable(c, c.block, c.agent, c.gcell[k], order)) reach |= 1 << k;
+            if (m_get(rset, c.gcell[k])) reach |= 1 << k;
             if (d.icon_colored[c.gicon[k]]) colored |= 1 << k;
         }
         o.aux1 = reach; o.aux2 = colored;
