@@ -97,6 +97,7 @@ XW_HD int xw_gen_map(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, int
         for (int x = 0; x < X; ++x)
             if ((x | y) & 1) m_set(wall, y * D + x);
     {
+        XwDrawSeq mz = xw_draw_seq(d.seed, gid, ep, att, XW_SITE_MAZE);
         uint8_t sx[64], sy[64], snext[64], sorder[64];
         uint64_t visited = 0;
         int sp = 0;
@@ -108,7 +109,7 @@ XW_HD int xw_gen_map(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, int
                 uint32_t o0 = 0, o1 = 1, o2 = 2, o3 = 3;  // moves (-1,0),(1,0),(0,1),(0,-1)
                 uint32_t ord[4] = {o0, o1, o2, o3};
                 for (int i = 3; i >= 1; --i) {
-                    uint32_t j = xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_MAZE, visit_no * 3 + (uint32_t)(3 - i)), (uint32_t)i + 1);
+                    uint32_t j = xw_randbelow(xw_draw_next(mz, visit_no * 3 + (uint32_t)(3 - i)), (uint32_t)i + 1);
                     uint32_t t = ord[i]; ord[i] = ord[j]; ord[j] = t;
                 }
                 sx[sp] = (uint8_t)px; sy[sp] = (uint8_t)py; snext[sp] = 0;
@@ -150,13 +151,14 @@ XW_HD int xw_gen_map(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, int
     }
     // ---- blocks: shuffle(blocks) + pop() per block entity == partial Fisher-Yates over the wall list
     {
+        XwDrawSeq bq = xw_draw_seq(d.seed, gid, ep, att, XW_SITE_BLOCKS);
         uint8_t bl[XW_MAX_DIM * XW_MAX_DIM / 2 + 8];
         int n = 0;
         for (int i = 0; i < D * D; ++i) if (m_get(wall, i)) bl[n++] = (uint8_t)i;
         for (int k = 0; k < nB; ++k) {
             int i = nb - 1 - k;
             if (i >= 1) {
-                int j = (int)xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_BLOCKS, (uint32_t)k), (uint32_t)i + 1);
+                int j = (int)xw_randbelow(xw_draw_next(bq, (uint32_t)k), (uint32_t)i + 1);
                 uint8_t t = bl[i]; bl[i] = bl[j]; bl[j] = t;
             }
             m_set(c.block, bl[i]);
@@ -203,22 +205,49 @@ XW_HD bool xw_reachable(const XwMapCtx& c, const XwMask& obst, int start, int en
     return xw_bfs(c, obst, start, end, end, scratch) == -2;
 }
 
+// 256-bit mask helpers: value of `m` at the neighbour cell.  nf / nl = cells with x != 0 / x != W-1.
+struct XwCols { XwMask nf, nl; };
+XW_HD XwCols xw_cols(const XwMapCtx& c) {
+    XwCols k; m_zero(k.nf); m_zero(k.nl);
+    const int D = c.W;
+    const uint64_t row_nf = ((1ull << D) - 1) & ~1ull, row_nl = (1ull << (D - 1)) - 1;  // a row is at most 16 bits
+    for (int y = 0; y < c.H; ++y) {
+        const int b = y * D, w = b >> 6, sft = b & 63;
+        k.nf.w[w] |= row_nf << sft; k.nl.w[w] |= row_nl << sft;
+        if (sft + D > 64 && w < 3) { k.nf.w[w + 1] |= row_nf >> (64 - sft); k.nl.w[w + 1] |= row_nl >> (64 - sft); }
+    }
+    return k;
+}
+XW_HD XwMask m_shr(const XwMask& m, int s) {  // result(c) = m(c + s), 0 < s < 64
+    XwMask r;
+    r.w[0] = (m.w[0] >> s) | (m.w[1] << (64 - s)); r.w[1] = (m.w[1] >> s) | (m.w[2] << (64 - s));
+    r.w[2] = (m.w[2] >> s) | (m.w[3] << (64 - s)); r.w[3] = m.w[3] >> s;
+    return r;
+}
+XW_HD XwMask m_shl(const XwMask& m, int s) {  // result(c) = m(c - s)
+    XwMask r;
+    r.w[3] = (m.w[3] << s) | (m.w[2] >> (64 - s)); r.w[2] = (m.w[2] << s) | (m.w[1] >> (64 - s));
+    r.w[1] = (m.w[1] << s) | (m.w[0] >> (64 - s)); r.w[0] = m.w[0] << s;
+    return r;
+}
+XW_HD XwMask m_and(const XwMask& a, const XwMask& b) { XwMask r; for (int i = 0; i < 4; ++i) r.w[i] = a.w[i] & b.w[i]; return r; }
+XW_HD XwMask m_or(const XwMask& a, const XwMask& b) { XwMask r; for (int i = 0; i < 4; ++i) r.w[i] = a.w[i] | b.w[i]; return r; }
+XW_HD XwMask m_right(const XwMask& m, const XwCols& k) { return m_and(m_shr(m, 1), k.nl); }            // m at (x+1, y)
+XW_HD XwMask m_left(const XwMask& m, const XwCols& k) { return m_and(m_shl(m, 1), k.nf); }             // m at (x-1, y)
+XW_HD XwMask m_below(const XwMask& m, int W) { return m_shr(m, W); }                                    // m at (x, y+1)
+XW_HD XwMask m_above(const XwMask& m, int W) { return m_shl(m, W); }                                    // m at (x, y-1)
+
 // Set of cells reachable from `seed` through cells outside `obst` (4-neighbourhood), seed included: the same set
 // maze2d.flood_fill / bfs discover (python/maze2d.py:21-63), grown a whole frontier at a time with 256-bit shifts
 // instead of a queue.  Used where only membership matters (which goals can be reached), not discovery order.
 XW_HD XwMask xw_flood(const XwMapCtx& c, const XwMask& obst, int seed) {
-    const int D = c.W, n = c.H * c.W;
-    XwMask free_, not_first, not_last, reach;  // not_first / not_last: cells with x != 0 / x != W-1
-    m_zero(not_first); m_zero(not_last); m_zero(reach);
+    const int D = c.W;
+    XwMask free_, reach;
+    m_zero(reach);
     for (int i = 0; i < 4; ++i) free_.w[i] = c.inrange.w[i] & ~obst.w[i];
-    for (int y = 0; y < c.H; ++y) {
-        // a row is at most 16 bits: OR it into the (at most two) words it touches
-        const uint64_t row_nf = ((1ull << D) - 1) & ~1ull, row_nl = ((1ull << (D - 1)) - 1);
-        const int b = y * D, w = b >> 6, s = b & 63;
-        not_first.w[w] |= row_nf << s; not_last.w[w] |= row_nl << s;
-        if (s + D > 64 && w < 3) { not_first.w[w + 1] |= row_nf >> (64 - s); not_last.w[w + 1] |= row_nl >> (64 - s); }
-    }
-    (void)n;
+    const XwCols k = xw_cols(c);
+    const XwMask& not_first = k.nf;
+    const XwMask& not_last = k.nl;
     m_set(reach, seed);
     m_set(free_, seed);
     while (true) {
@@ -251,8 +280,6 @@ XW_HD bool xw_touches(const XwMapCtx& c, const XwMask& set, int cell) {
 }
 
 // -------------------------------------------------------------------------- tiles
-// Enumerates the reference's p/t/l tiles in its own order; returns the count and, when
-// pick >= 0, the pick-th pair in (a, b).  Two passes (count, then pick) avoid materialising lists.
 XW_HD int n_free4(const XwMapCtx& c, int x, int y, int excl) {
     int n = 0;
     if (ctx_free(c, x, y - 1) && (y - 1) * c.W + x != excl) ++n;
@@ -261,42 +288,65 @@ XW_HD int n_free4(const XwMapCtx& c, int x, int y, int excl) {
     if (ctx_free(c, x, y + 1) && (y + 1) * c.W + x != excl) ++n;
     return n;
 }
-#define XW_EMIT(A, B) do { if (n == pick) { a = (A); b = (B); } ++n; } while (0)
+
+// The reference's p / t / l tiles (xworld3d_task.py:226-251, 253-276, 302-322) in its own order: cells row-major, and
+// inside a cell the order of the Python's appends.  Each append kind ("slot") is a 256-bit mask of the cells where
+// it happens, built from the free-cell mask with shifts, so counting is popcounts and the pick-th pair is found by
+// walking only the cells that emit -- the scalar enumeration was two passes of ~15 free-cell tests per cell, the
+// longest stretch of a reset.  Returns the count; pick >= 0 also returns the pick-th pair in (a, b).
 XW_HD int xw_tiles(const XwMapCtx& c, int kind, int pick, int& a, int& b) {
-    int n = 0;
     const int W = c.W;
-    for (int y = 0; y < c.H; ++y)
-        for (int x = 0; x < c.W; ++x) {
-            if (kind == XW_T3_NEAR) {  // _get_p_tiles, xworld3d_task.py:226-251
-                for (int k = 0; k < 3; ++k) {
-                    int x2 = x + (k != 1), y2 = y + (k != 0);
-                    if (ctx_free(c, x, y) && ctx_free(c, x2, y2)) {
-                        int p1 = y * W + x, p2 = y2 * W + x2;
-                        if (n_free4(c, x2, y2, p1) > 0) XW_EMIT(p1, p2);
-                        if (n_free4(c, x, y, p2) > 0) XW_EMIT(p2, p1);
-                    }
+    const XwCols k = xw_cols(c);
+    XwMask F;
+    for (int i = 0; i < 4; ++i) F.w[i] = c.inrange.w[i] & ~c.block.w[i] & ~c.goal.w[i];
+    if (c.agent >= 0) m_clr(F, c.agent);
+    const XwMask fR = m_right(F, k), fL = m_left(F, k), fD = m_below(F, W), fU = m_above(F, W);
+    XwMask slot[6];
+    int da[6], db[6], ns;  // the pair a slot emits at cell q: (q + da, q + db)
+    if (kind == XW_T3_NEAR) {  // for k in ((x+1,y), (x,y+1), (x+1,y+1)): (p1,p2) if p2 has another free side, then (p2,p1)
+        const XwMask any4 = m_or(m_or(fU, fD), m_or(fL, fR));
+        const XwMask b0 = m_and(F, fR), b1 = m_and(F, fD), b2 = m_and(F, m_right(fD, k));
+        slot[0] = m_and(b0, m_right(m_or(m_or(fU, fD), fR), k)); slot[1] = m_and(b0, m_or(m_or(fU, fD), fL));
+        slot[2] = m_and(b1, m_below(m_or(m_or(fL, fR), fD), W)); slot[3] = m_and(b1, m_or(m_or(fL, fR), fU));
+        slot[4] = m_and(b2, m_right(m_below(any4, W), k));       slot[5] = m_and(b2, any4);
+        da[0] = 0; db[0] = 1;      da[1] = 1; db[1] = 0;
+        da[2] = 0; db[2] = W;      da[3] = W; db[3] = 0;
+        da[4] = 0; db[4] = W + 1;  da[5] = W + 1; db[5] = 0;
+        ns = 6;
+    } else if (kind == XW_T3_BETWEEN) {  // the free cell between two free cells, with a free cell on one of the other sides
+        slot[0] = m_and(m_and(F, m_and(fL, fR)), m_or(fU, fD)); da[0] = -1; db[0] = 1;
+        slot[1] = m_and(m_and(F, m_and(fU, fD)), m_or(fL, fR)); da[1] = -W; db[1] = W;
+        ns = 2;
+    } else {  // three free cells in a column, then in a row: both adjacent pairs of each
+        const XwMask v = m_and(m_and(F, fD), m_below(fD, W)), h = m_and(m_and(F, fR), m_right(fR, k));
+        slot[0] = v; da[0] = 0; db[0] = W;  slot[1] = v; da[1] = W; db[1] = 2 * W;
+        slot[2] = h; da[2] = 0; db[2] = 1;  slot[3] = h; da[3] = 1; db[3] = 2;
+        ns = 4;
+    }
+    int total = 0;
+    for (int j = 0; j < ns; ++j) total += m_count(slot[j]);
+    if (pick < 0 || pick >= total) return total;
+    for (int w = 0; w < 4; ++w) {
+        int cw = 0;
+        uint64_t any = 0;
+        for (int j = 0; j < ns; ++j) { cw += xw_popc64(slot[j].w[w]); any |= slot[j].w[w]; }
+        if (pick >= cw) { pick -= cw; continue; }
+        while (any) {
+#if defined(__CUDA_ARCH__)
+            const int bit = __ffsll((long long)any) - 1;
+#else
+            const int bit = __builtin_ctzll(any);
+#endif
+            any &= any - 1;
+            for (int j = 0; j < ns; ++j)
+                if ((slot[j].w[w] >> bit) & 1ull) {
+                    if (pick == 0) { const int q = w * 64 + bit; a = q + da[j]; b = q + db[j]; return total; }
+                    --pick;
                 }
-            } else if (kind == XW_T3_BETWEEN) {  // _get_t_tiles, :253-276
-                if (ctx_free(c, x, y)) {
-                    if (ctx_free(c, x - 1, y) && ctx_free(c, x + 1, y) && (ctx_free(c, x, y - 1) || ctx_free(c, x, y + 1)))
-                        XW_EMIT(y * W + x - 1, y * W + x + 1);
-                    if (ctx_free(c, x, y - 1) && ctx_free(c, x, y + 1) && (ctx_free(c, x - 1, y) || ctx_free(c, x + 1, y)))
-                        XW_EMIT((y - 1) * W + x, (y + 1) * W + x);
-                }
-            } else {  // _get_l_tiles, :302-322
-                if (ctx_free(c, x, y) && ctx_free(c, x, y + 1) && ctx_free(c, x, y + 2)) {
-                    XW_EMIT(y * W + x, (y + 1) * W + x);
-                    XW_EMIT((y + 1) * W + x, (y + 2) * W + x);
-                }
-                if (ctx_free(c, x, y) && ctx_free(c, x + 1, y) && ctx_free(c, x + 2, y)) {
-                    XW_EMIT(y * W + x, y * W + x + 1);
-                    XW_EMIT(y * W + x + 1, y * W + x + 2);
-                }
-            }
         }
-    return n;
+    }
+    return total;
 }
-#undef XW_EMIT
 
 // direction of `r` seen from `t` when looking along the unit axis vector (vx,vy):
 // XWorld3DNavTargetDirection.__compute_triple_direction (:98-126) collapsed to integers for
