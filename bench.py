@@ -77,28 +77,52 @@ class ClockSampler(object):
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.rows, self.stamps, self.proc, self.gpu = [], [], None, gpu_index
+        self.t0 = self.t1 = None
 
     def start(self):
+        """Starts nvidia-smi (20 ms period) and waits for its first row, so that it is already sampling when the timed
+        region begins (the region of the default run is ~60 ms: shorter than nvidia-smi's start-up)."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            end = time.perf_counter() + 3.0
+            while not self.rows and time.perf_counter() < end:
+                time.sleep(0.01)
         except OSError:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
+            self.stamps.append(time.perf_counter())
             self.rows.append([c.strip() for c in line.split(",")])
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         self.t.join(timeout=2)
+        rows, where = self.rows, "whole run"
+        if self.t0 is not None and self.t1 is not None:
+            # a row printed at time t describes the ~20 ms before it: rows stamped inside [t0, t1 + one period]
+            inside = [r for r, t in zip(self.rows, self.stamps) if self.t0 <= t <= self.t1 + 0.03]
+            if inside:
+                rows, where = inside, "timed region"
+            elif self.rows:  # region shorter than a period: the rows on either side of it
+                k = min(range(len(self.rows)), key=lambda i: abs(self.stamps[i] - self.t1))
+                rows, where = self.rows[max(0, k - 1):k + 2], "rows adjacent to the timed region"
+        self.rows = rows
+        self.where = where
         sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
@@ -109,7 +133,7 @@ class ClockSampler(object):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": getattr(self, "where", "whole run")}
 
 
 def cpu_reference_arm(steps, warmup, sample_envs, threads):
@@ -208,19 +232,21 @@ def bench_race(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        step(i)
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()  # before the warm-up: nothing but the warm-up may sit between it and the timed region
+    for i in range(args.warmup):
+        step(i)
     launches0 = sim.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     e0.record()
     for i in range(args.steps):
         step(i)
     e1.record()
     barrier()
+    sampler.mark_end()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     launches = sim.launch_count() - launches0
@@ -356,22 +382,24 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # before the warm-up: nothing but the warm-up may sit between it and the timed region
     for i in range(args.warmup):
         step(i)
     barrier()
     lib.xw_enable_timing(h, 1)
     lib.xw_render_ms(h, 1)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = sim.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     e0.record()
     for i in range(args.steps):
         step(i)
     e1.record()
     barrier()
+    sampler.mark_end()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     launches = sim.launch_count() - launches0

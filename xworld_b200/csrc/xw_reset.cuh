@@ -45,6 +45,20 @@ XW_HD int m_nth(const XwMask& m, int k) {
     return -1;
 }
 
+XW_HD int xw_ctz64(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)v) - 1;
+#else
+    return __builtin_ctzll(v);
+#endif
+}
+// OR a row of at most 16 bits into the mask at bit offset `b` (it touches at most two words)
+XW_HD void m_or_bits(XwMask& m, int b, uint64_t bits) {
+    const int w = b >> 6, s = b & 63;
+    m.w[w] |= bits << s;
+    if (s > 48 && w < 3) m.w[w + 1] |= bits >> (64 - s);
+}
+
 struct XwMapCtx {
     int H, W;        // the world the Python side sees: the whole map, or the level's inner world (curriculum)
     int nG, nB;      // goals / blocks of this episode
@@ -93,9 +107,10 @@ XW_HD int xw_gen_map(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, int
     // ---- maze: walls as a bit mask, carved by an explicit-stack DFS with 3 draws per visited node
     XwMask wall; m_zero(wall);
     const int pad = (D % 2 == 0), X = pad ? D - 1 : D, nx = (X + 1) / 2;
-    for (int y = 0; y < X; ++y)
-        for (int x = 0; x < X; ++x)
-            if ((x | y) & 1) m_set(wall, y * D + x);
+    {   // odd rows are all wall, even rows have wall at odd x (python/maze2d.py:80-86), a row at a time
+        const uint64_t full = (1ull << X) - 1, odd = 0xAAAAull & full;
+        for (int y = 0; y < X; ++y) m_or_bits(wall, y * D, (y & 1) ? full : odd);
+    }
     {
         XwDrawSeq mz = xw_draw_seq(d.seed, gid, ep, att, XW_SITE_MAZE);
         uint8_t sx[64], sy[64], snext[64], sorder[64];
@@ -154,7 +169,8 @@ XW_HD int xw_gen_map(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, int
         XwDrawSeq bq = xw_draw_seq(d.seed, gid, ep, att, XW_SITE_BLOCKS);
         uint8_t bl[XW_MAX_DIM * XW_MAX_DIM / 2 + 8];
         int n = 0;
-        for (int i = 0; i < D * D; ++i) if (m_get(wall, i)) bl[n++] = (uint8_t)i;
+        for (int w = 0; w < 4; ++w)
+            for (uint64_t v = wall.w[w]; v; v &= v - 1) bl[n++] = (uint8_t)(w * 64 + xw_ctz64(v));
         for (int k = 0; k < nB; ++k) {
             int i = nb - 1 - k;
             if (i >= 1) {
@@ -177,32 +193,31 @@ XW_HD int xw_gen_map(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, int
 // Breadth-first discovery from `seed`; obstacles = `obst` (the cell `pass`, if >= 0, is always
 // enterable).  order[] receives the discovered cells (seed excluded) in maze2d.flood_fill order
 // (moves (-1,0),(1,0),(0,-1),(0,1)).  Returns their count; stops early when `stop_at` is found (-2).
+// order[] entries are packed (y << 4 | x) (no division per dequeued cell); xw_bfs_cell turns one into a cell index.
+XW_HD int xw_bfs_cell(const XwMapCtx& c, uint8_t packed) { return (packed >> 4) * c.W + (packed & 15); }
 XW_HD int xw_bfs(const XwMapCtx& c, const XwMask& obst, int seed, int pass, int stop_at, uint8_t* order) {
-    XwMask vis; m_zero(vis);
-    m_set(vis, seed);
+    XwMask closed;  // visited or not enterable
+    for (int i = 0; i < 4; ++i) closed.w[i] = obst.w[i] | ~c.inrange.w[i];
+    if (pass >= 0) m_clr(closed, pass);
+    m_set(closed, seed);
+    const int sx = seed % c.W, sy = seed / c.W;
     int head = -1, n = 0;  // queue = seed, order[0..n)
     while (head < n) {
-        int cur = head < 0 ? seed : order[head];
+        const int cx = head < 0 ? sx : (order[head] & 15), cy = head < 0 ? sy : (order[head] >> 4);
         ++head;
+        const int cur = cy * c.W + cx;
         if (cur == stop_at) return -2;
-        int cx = cur % c.W, cy = cur / c.W;
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-            int x = cx + (m == 0 ? -1 : m == 1 ? 1 : 0), y = cy + (m == 2 ? -1 : m == 3 ? 1 : 0);
+            const int x = cx + (m == 0 ? -1 : m == 1 ? 1 : 0), y = cy + (m == 2 ? -1 : m == 3 ? 1 : 0);
             if (x < 0 || y < 0 || x >= c.W || y >= c.H) continue;
-            int q = y * c.W + x;
-            if (m_get(vis, q)) continue;
-            if (q != pass && m_get(obst, q)) continue;
-            m_set(vis, q);
-            order[n++] = (uint8_t)q;
+            const int q = y * c.W + x;
+            if (m_get(closed, q)) continue;
+            m_set(closed, q);
+            order[n++] = (uint8_t)((y << 4) | x);
         }
     }
     return n;
-}
-
-XW_HD bool xw_reachable(const XwMapCtx& c, const XwMask& obst, int start, int end, uint8_t* scratch) {
-    if (start == end) return true;
-    return xw_bfs(c, obst, start, end, end, scratch) == -2;
 }
 
 // 256-bit mask helpers: value of `m` at the neighbour cell.  nf / nl = cells with x != 0 / x != W-1.
@@ -416,7 +431,7 @@ XW_HD bool xw_idle3d(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, int
     if (task == XW_T3_NEAR) {
         int nf = xw_bfs(c, obst, b, b, -1, order);
         if (nf == 0) return false;
-        c.agent = order[xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_TASK_AGENT, 0), (uint32_t)nf)];
+        c.agent = xw_bfs_cell(c, order[xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_TASK_AGENT, 0), (uint32_t)nf)]);
         // goals within 1.5 (+1e-3) of g1, g1 itself excluded: the 8-neighbourhood
         for (int g = 0; g < G; ++g) {
             int dx = c.gcell[g] % W - a % W, dy = c.gcell[g] / W - a / W;
@@ -428,7 +443,7 @@ XW_HD bool xw_idle3d(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, int
         int mid = my * W + mx;
         int nf = xw_bfs(c, obst, mid, mid, -1, order);
         if (nf == 0) return false;
-        c.agent = order[xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_TASK_AGENT, 0), (uint32_t)nf)];
+        c.agent = xw_bfs_cell(c, order[xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_TASK_AGENT, 0), (uint32_t)nf)]);
         o.aux0 = g1 | (g2 << 4); o.aux1 = mx; o.aux2 = my;  // (g2: only the sentence channel needs it, xw_sentence.hpp)
     } else {
         int target = g1, referent = g2;
@@ -451,7 +466,7 @@ XW_HD bool xw_idle3d(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, int
         int ecell = ey * W + ex;
         int nf = 1 + xw_bfs(c, obst, ecell, ecell, -1, order);  // inclusive: seed first
         int pick = (int)xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_TASK_AGENT, 0), (uint32_t)nf);
-        c.agent = pick == 0 ? ecell : order[pick - 1];
+        c.agent = pick == 0 ? ecell : xw_bfs_cell(c, order[pick - 1]);
         o.aux0 = referent; o.aux1 = dir; o.aux2 = target;
     }
     return true;
@@ -498,12 +513,19 @@ XW_HD void xw_reset_commit(const XwDev& d, int e, uint32_t ep, uint32_t minstd, 
     // cpp_get_entities (xworld_env.py:352-366): the world sits at (offset_w, offset_h) = ((max - dim) / 2, same) of
     // the map, everything around it is brick (__padding_walls, :454-473); no offset when the world is the map
     const int D = c.W, off = (d.W - D) / 2;
-    for (int i = 0; i < d.CS; ++i) g[i] = XW_CELL_EMPTY;
+    {   // rows are 16-byte multiples (CS), 16-byte aligned: clear with 8-byte stores
+        uint64_t* g8 = (uint64_t*)g;
+        for (int i = 0; i < (d.CS >> 3); ++i) g8[i] = 0;  // XW_CELL_EMPTY == 0
+    }
     if (D != d.W)
         for (int y = 0; y < d.H; ++y)
             for (int x = 0; x < d.W; ++x)
                 if (x < off || x >= off + D || y < off || y >= off + D) g[y * d.W + x] = XW_CELL_BLOCK;
-    for (int i = 0; i < D * D; ++i) if (m_get(c.block, i)) g[(i / D + off) * d.W + i % D + off] = XW_CELL_BLOCK;
+    for (int w = 0; w < 4; ++w)
+        for (uint64_t v = c.block.w[w]; v; v &= v - 1) {
+            const int i = w * 64 + xw_ctz64(v);
+            g[D == d.W ? i : (i / D + off) * d.W + i % D + off] = XW_CELL_BLOCK;
+        }
     for (int k = 0; k < d.G; ++k) {
         const bool on = k < c.nG;  // levels 0-2 hold two goals (XWorldNav.py:31): the other slots read 0
         const int gx = on ? c.gcell[k] % D + off : 0, gy = on ? c.gcell[k] / D + off : 0;
