@@ -40,6 +40,7 @@ struct XwDev {
     int32_t n;                 // envs on this device
     int32_t H, W, CS;          // map size, grid row stride (bytes)
     int32_t G, n_blocks, rules, max_steps, max_steps_factor, auto_reset;
+    int32_t retry_width;       // attempts the warp of a queued env evaluates side by side in its first retry round
     uint64_t seed;
     int64_t gid0;              // global id of env 0
     // ---- per-env state (SoA) ----

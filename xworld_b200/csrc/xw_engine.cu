@@ -207,6 +207,7 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
     d.G = c.n_goals; d.n_blocks = c.n_blocks; d.rules = c.rules; d.max_steps = c.max_steps;
     d.max_steps_factor = c.max_steps_factor; d.auto_reset = c.auto_reset;
     d.seed = c.seed; d.gid0 = c.env_id_offset;
+    { const char* ew = getenv("XW_RESET_RETRY_WIDTH"); int w = ew ? atoi(ew) : 32; d.retry_width = w < 1 ? 1 : (w > 32 ? 32 : w); }
     int rc = 0;
     rc |= dalloc(s, &d.grid, (size_t)n * d.CS);
     uint8_t** u8s[] = {&d.agent_x, &d.agent_y, &d.facing, &d.task, &d.stage, &d.event, &d.succ, &d.tmask, &d.aux0, &d.aux1, &d.aux2};

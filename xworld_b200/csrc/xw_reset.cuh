@@ -650,9 +650,12 @@ __device__ __forceinline__ void xw_reset_env_warp(const XwDev& d, int e) {
         }
         return;
     }
-    for (uint32_t base = 1; base < 64; base += 32) {
+    // rounds of `retry_width` attempts, then 32 at a time (a round costs up to its width in divergent lanes; most
+    // retries succeed within the first few attempts, the rare hopeless map / task pair wants them all at once)
+    uint32_t width = (uint32_t)d.retry_width;
+    for (uint32_t base = 1; base < 64; base += width, width = 32) {
         const uint32_t att = base + lane;
-        st = att < 64 ? xw_reset_attempt(d, gid, ep, att, task, level, c, o) : 0;
+        st = ((uint32_t)lane < width && att < 64) ? xw_reset_attempt(d, gid, ep, att, task, level, c, o) : 0;
         const unsigned done = __ballot_sync(0xffffffffu, st != 0);
         if (done) {
             if (lane == __ffs(done) - 1) {
