@@ -795,13 +795,13 @@ int xw_step_host(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float* h_
 }
 
 static bool is_pinned(const void* p) {
-    static thread_local const void* seen[4] = {nullptr, nullptr, nullptr, nullptr};  // (a trainer passes the same buffers every step)
+    static thread_local const void* seen[16] = {};  // (a trainer passes the same few buffers every step)
     for (const void* q : seen) if (q == p) return true;
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
     if (a.type != cudaMemoryTypeHost) return false;
     static thread_local int next = 0;
-    seen[next++ & 3] = p;
+    seen[next++ & 15] = p;
     return true;
 }
 
@@ -817,9 +817,15 @@ int xw_step_hd(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float* h_re
     const bool pin_a = is_pinned(h_actions), pin_r = is_pinned(h_reward), pin_o = is_pinned(h_game_over);
     const int32_t* src_a = h_actions;
     if (!pin_a) { memcpy(s->h_act, h_actions, sizeof(int32_t) * s->n); src_a = s->h_act; }
-    CUDA_TRY(cudaMemcpyAsync(s->d_act, src_a, sizeof(int32_t) * s->n, cudaMemcpyHostToDevice, st));
+    // The step kernel reads a page-locked action buffer over PCIe itself: no copy operation in front of it
+    // (e2e +0.9 %, profiles/r01_summary.md; XW_E2E_ZEROCOPY=0 goes back to the H2D copy)
+    static const bool zero_copy = [] { const char* e = getenv("XW_E2E_ZEROCOPY"); return !e || atoi(e) != 0; }();
+    const int32_t* dev_a = s->d_act;
+    void* mapped = nullptr;
+    if (zero_copy && pin_a && cudaHostGetDevicePointer(&mapped, (void*)src_a, 0) == cudaSuccess && mapped) dev_a = (const int32_t*)mapped;
+    else { cudaGetLastError(); CUDA_TRY(cudaMemcpyAsync(s->d_act, src_a, sizeof(int32_t) * s->n, cudaMemcpyHostToDevice, st)); }
     const bool split = s->cfg.game == XW_GAME_XWORLD && d_frames != nullptr;
-    rc = xw_step(s, s->d_act, act_rep, s->d_rew, s->d_over, split ? nullptr : d_frames, st);
+    rc = xw_step(s, dev_a, act_rep, s->d_rew, s->d_over, split ? nullptr : d_frames, st);
     if (rc) return rc;
     cudaStream_t cs = st;
     if (split) {
@@ -830,13 +836,13 @@ int xw_step_hd(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float* h_re
         }
         cs = s->copy_stream;
         CUDA_TRY(cudaEventRecord(s->ev_step, st));
+        rc = launch_render(s, d_frames, st);  // first: the render launch must be queued before the step kernels end
+        if (rc) return rc;
         CUDA_TRY(cudaStreamWaitEvent(cs, s->ev_step, 0));
     }
     CUDA_TRY(cudaMemcpyAsync(pin_r ? h_reward : s->h_rew, s->d_rew, sizeof(float) * s->n, cudaMemcpyDeviceToHost, cs));
     CUDA_TRY(cudaMemcpyAsync(pin_o ? h_game_over : s->h_over, s->d_over, sizeof(int32_t) * s->n, cudaMemcpyDeviceToHost, cs));
     if (split) {
-        rc = launch_render(s, d_frames, st);
-        if (rc) return rc;
         CUDA_TRY(cudaEventRecord(s->ev_copy, cs));  // one host wait for both streams
         CUDA_TRY(cudaStreamWaitEvent(st, s->ev_copy, 0));
     }
