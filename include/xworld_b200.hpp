@@ -101,7 +101,8 @@ public:
         if (show_screen) throw std::runtime_error("show_screen is not supported (no GUI)");
         if ((int)actions.size() != n_) throw std::runtime_error("expected one action per env");
         check(xw_step_host(sim_, actions.data(), act_rep, reward_.data(), over_.data(), screen_.data()));
-        for (int i = 0; i < n_; ++i) acc_reward_[i] += reward_[i];
+        for (int i = 0; i < n_; ++i)
+            if (actions[i] != XW_ACTION_NONE) acc_reward_[i] += reward_[i];  // an env that sat the step out keeps its totals
         return reward_;
     }
     // the reference's scalar shape (n_envs == 1)
