@@ -435,6 +435,29 @@ def main():
                "d2h_bytes_per_step": 8 * n, "steps": k2,
                "what": "xw_step_hd: pinned host actions -> H2D, step+reset+render kernels, reward+game_over D2H, "
                        "stream sync; frames stay in HBM (consumer = co-located learner)"}
+        # the pipelined form of the same call (xw_step_hd_async): the host still waits for every step's reward / game_over
+        # before it issues the next step, but not for the frames, which a co-located learner consumes in stream order
+        # (two frame buffers, alternating); everything is complete (xw_sync) inside the timed region
+        frames2 = torch.empty_like(frames)
+        fb = [frames, frames2]
+        for i in range(5):
+            lib.xw_step_hd_async(h, h_act[i % 4].data_ptr(), 1, h_rew.data_ptr(), h_over.data_ptr(), fb[i & 1].data_ptr())
+        lib.xw_sync(h)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(k2):
+            rc = lib.xw_step_hd_async(h, h_act[i % 4].data_ptr(), 1, h_rew.data_ptr(), h_over.data_ptr(), fb[i & 1].data_ptr())
+            assert rc == 0
+        lib.xw_sync(h)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e["pipelined"] = {"value": n * world * k2 / float(tt.item()), "unit": "env-steps/s", "steps": k2,
+                            "what": "xw_step_hd_async: the same copies and the same host wait for reward + game_over every step; "
+                                    "the frames of step t are complete in stream order (xw_wait_frames), not waited for by the host"}
+        del frames2, fb
         if rank == 0 and world == 1:  # frames to the host too (PCIe-bound), reported beside it
             hf = torch.empty((n, 3, SIDE, SIDE), dtype=torch.uint8).pin_memory()
             for i in range(2):

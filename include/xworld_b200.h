@@ -175,6 +175,16 @@ int xw_reset_host(xw_sim* sim, const uint8_t* h_mask, uint8_t* h_frames);
 int xw_step_hd(xw_sim* sim, const int32_t* h_actions, int32_t act_rep, float* h_reward,
                int32_t* h_game_over, uint8_t* d_frames);
 
+/* xw_step_hd without the wait for the frames: returns as soon as reward / game_over are on the host, while the render
+ * kernel of the step may still be running on the handle's stream (the next call's step kernel queues behind it, so the
+ * GPU never waits for the host between steps).  Anything that reads d_frames must be ordered after the render:
+ * xw_wait_frames makes `stream` wait for it (event), xw_sync the host.  A caller that lets a consumer on another stream
+ * read the frames of step t while step t+1 is issued should alternate between two d_frames buffers.  No reference
+ * counterpart (the reference renders on the CPU inside take_actions). */
+int xw_step_hd_async(xw_sim* sim, const int32_t* h_actions, int32_t act_rep, float* h_reward,
+                     int32_t* h_game_over, uint8_t* d_frames);
+int xw_wait_frames(xw_sim* sim, void* stream);
+int xw_sync(xw_sim* sim);
 /* get_num_actions / get_screen_out_dimensions / get_num_steps / get_lives
  * (simulator_interface.h:52-63). */
 int32_t xw_num_envs(const xw_sim* sim);

@@ -418,6 +418,25 @@ def test_step_hd_host_buffers_equal_device_path(synthetic_catalog):
             assert (h_rew.numpy().view(np.uint32) == r1.view(np.uint32)).all() and (h_over.numpy() == o1).all()
             torch.cuda.synchronize()
             assert (sim._screen.cpu().numpy() == f1).all()
+    # the pipelined form: reward / game_over on return, frames after xw_wait_frames / xw_sync; two frame buffers
+    h_act, h_rew, h_over = (torch.zeros(n, dtype=torch.int32).pin_memory(), torch.zeros(n, dtype=torch.float32).pin_memory(),
+                            torch.zeros(n, dtype=torch.int32).pin_memory())
+    bufs = [torch.empty_like(sim._screen), torch.empty_like(sim._screen)]
+    prev = None
+    for s in range(40):
+        a = parity.actions_for(s + 500, n, 4)
+        r1, o1, f1 = a_eng.step(a, render=True)
+        h_act.copy_(torch.from_numpy(a))
+        with torch.cuda.device(sim._dev):
+            rc = sim._lib.xw_step_hd_async(sim._h, h_act.data_ptr(), 1, h_rew.data_ptr(), h_over.data_ptr(), bufs[s & 1].data_ptr())
+            assert rc == 0, sim._lib.xw_last_error()
+            assert (h_rew.numpy().view(np.uint32) == r1.view(np.uint32)).all() and (h_over.numpy() == o1).all()
+            if prev is not None:  # the previous step's frames, read by a consumer stream while this step renders
+                assert (bufs[(s - 1) & 1].cpu().numpy() == prev).all()
+            assert sim._lib.xw_wait_frames(sim._h, C.c_void_p(torch.cuda.current_stream().cuda_stream)) == 0
+        prev = f1
+    assert sim._lib.xw_sync(sim._h) == 0
+    assert (bufs[39 & 1].cpu().numpy() == prev).all()
 
 
 @pytest.mark.parametrize("name", ["c2_nav3d_7x7_84", "c3_nav2d_11x11_84"])

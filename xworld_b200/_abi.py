@@ -116,7 +116,7 @@ class XwWireRequest(C.Structure):
 # every symbol include/xworld_b200.h declares
 SYMBOLS = [
     "xw_config_init", "xw_create", "xw_destroy", "xw_last_error", "xw_reset", "xw_step", "xw_render",
-    "xw_step_host", "xw_reset_host", "xw_step_hd", "xw_num_envs", "xw_num_actions", "xw_screen_dims",
+    "xw_step_host", "xw_reset_host", "xw_step_hd", "xw_step_hd_async", "xw_wait_frames", "xw_sync", "xw_num_envs", "xw_num_actions", "xw_screen_dims",
     "xw_frame_bytes", "xw_num_steps", "xw_get_field", "xw_set_field", "xw_launch_count", "xw_render_kernel", "xw_sentence_compose",
     "xw_enable_timing", "xw_render_ms",
     "xw_wire_encode_packet", "xw_wire_decode_packet", "xw_wire_parse_request", "xw_wire_compose_request", "xw_wire_reply_reset",
@@ -153,6 +153,12 @@ def load():
     lib.xw_step_host.restype = C.c_int
     lib.xw_step_hd.argtypes = [vp, vp, i32, vp, vp, vp]
     lib.xw_step_hd.restype = C.c_int
+    lib.xw_step_hd_async.argtypes = [vp, vp, i32, vp, vp, vp]
+    lib.xw_step_hd_async.restype = C.c_int
+    lib.xw_wait_frames.argtypes = [vp, vp]
+    lib.xw_wait_frames.restype = C.c_int
+    lib.xw_sync.argtypes = [vp]
+    lib.xw_sync.restype = C.c_int
     lib.xw_reset_host.argtypes = [vp, vp, vp]
     lib.xw_reset_host.restype = C.c_int
     lib.xw_num_envs.argtypes = [vp]

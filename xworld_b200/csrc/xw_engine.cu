@@ -98,7 +98,7 @@ struct xw_sim {
     xw_config cfg;
     int n = 0, device = 0;
     cudaStream_t own_stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t ev_step = nullptr, ev_copy = nullptr;
+    cudaEvent_t ev_step = nullptr, ev_copy = nullptr, ev_frames = nullptr, ev_h2d = nullptr;
     int64_t launches = 0;
     int step_parity = 0;
     // xworld
@@ -505,7 +505,8 @@ void xw_destroy(xw_sim* s) {
     if (s->h_over) cudaFreeHost(s->h_over);
     if (s->h_rew) cudaFreeHost(s->h_rew);
     for (auto ev : s->ev) cudaEventDestroy(ev);
-    if (s->copy_stream) { cudaStreamDestroy(s->copy_stream); cudaEventDestroy(s->ev_step); cudaEventDestroy(s->ev_copy); }
+    if (s->copy_stream) { cudaStreamDestroy(s->copy_stream); cudaEventDestroy(s->ev_step); cudaEventDestroy(s->ev_copy); cudaEventDestroy(s->ev_h2d); }
+    if (s->ev_frames) cudaEventDestroy(s->ev_frames);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
 }
@@ -808,7 +809,31 @@ static bool is_pinned(const void* p) {
 // Host actions in, host reward / game_over out, frames stay on the device.  Page-locked caller buffers are used
 // in place (no staging copy); the reward / game_over read-back runs on a second stream as soon as the step and
 // reset kernels are done, i.e. under the render kernel, so the call returns when the frames are complete.
+static int step_hd(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float* h_reward, int32_t* h_game_over, uint8_t* d_frames,
+                   bool wait_frames);
 int xw_step_hd(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float* h_reward, int32_t* h_game_over, uint8_t* d_frames) {
+    return step_hd(s, h_actions, act_rep, h_reward, h_game_over, d_frames, true);
+}
+// The pipelined form: returns when reward / game_over are on the host; the render kernel of this step may still be
+// running on the handle's stream.  Whatever reads the frames must be ordered after it: xw_wait_frames(sim, stream)
+// makes a consumer stream wait, xw_sync(sim) the host.  The next call's step kernel is stream-ordered behind the
+// render, so the GPU goes from one step into the next without waiting for the host.
+int xw_step_hd_async(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float* h_reward, int32_t* h_game_over, uint8_t* d_frames) {
+    return step_hd(s, h_actions, act_rep, h_reward, h_game_over, d_frames, false);
+}
+int xw_wait_frames(xw_sim* s, void* stream) {
+    if (!s->ev_frames) CUDA_TRY(cudaEventCreateWithFlags(&s->ev_frames, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(s->ev_frames, s->own_stream));
+    CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, s->ev_frames, 0));
+    return 0;
+}
+int xw_sync(xw_sim* s) {
+    if (s->own_stream) CUDA_TRY(cudaStreamSynchronize(s->own_stream));
+    if (s->copy_stream) CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
+    return 0;
+}
+static int step_hd(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float* h_reward, int32_t* h_game_over, uint8_t* d_frames,
+                   bool wait_frames) {
     if (!h_actions || !h_reward || !h_game_over) return set_err(XW_ERR_INVALID_ARG, "null buffer");
     if (s->cfg.game == XW_GAME_SIMPLE_GAME) return set_err(XW_ERR_UNSUPPORTED, "simple_game has no device frames");
     int rc = ensure_staging(s, false);
@@ -822,18 +847,29 @@ int xw_step_hd(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float* h_re
     static const bool zero_copy = [] { const char* e = getenv("XW_E2E_ZEROCOPY"); return !e || atoi(e) != 0; }();
     const int32_t* dev_a = s->d_act;
     void* mapped = nullptr;
-    if (zero_copy && pin_a && cudaHostGetDevicePointer(&mapped, (void*)src_a, 0) == cudaSuccess && mapped) dev_a = (const int32_t*)mapped;
-    else { cudaGetLastError(); CUDA_TRY(cudaMemcpyAsync(s->d_act, src_a, sizeof(int32_t) * s->n, cudaMemcpyHostToDevice, st)); }
     const bool split = s->cfg.game == XW_GAME_XWORLD && d_frames != nullptr;
+    if (split && !s->copy_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&s->ev_step, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&s->ev_copy, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&s->ev_h2d, cudaEventDisableTiming));
+    }
+    if (split && !wait_frames) {
+        // pipelined: the previous step's render kernel is probably still running on `st`; the actions go up on the copy
+        // stream under it, and the step kernel (queued behind the render) finds them in HBM
+        CUDA_TRY(cudaMemcpyAsync(s->d_act, src_a, sizeof(int32_t) * s->n, cudaMemcpyHostToDevice, s->copy_stream));
+        CUDA_TRY(cudaEventRecord(s->ev_h2d, s->copy_stream));
+        CUDA_TRY(cudaStreamWaitEvent(st, s->ev_h2d, 0));
+    } else if (zero_copy && pin_a && cudaHostGetDevicePointer(&mapped, (void*)src_a, 0) == cudaSuccess && mapped) {
+        dev_a = (const int32_t*)mapped;
+    } else {
+        cudaGetLastError();
+        CUDA_TRY(cudaMemcpyAsync(s->d_act, src_a, sizeof(int32_t) * s->n, cudaMemcpyHostToDevice, st));
+    }
     rc = xw_step(s, dev_a, act_rep, s->d_rew, s->d_over, split ? nullptr : d_frames, st);
     if (rc) return rc;
     cudaStream_t cs = st;
     if (split) {
-        if (!s->copy_stream) {
-            CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
-            CUDA_TRY(cudaEventCreateWithFlags(&s->ev_step, cudaEventDisableTiming));
-            CUDA_TRY(cudaEventCreateWithFlags(&s->ev_copy, cudaEventDisableTiming));
-        }
         cs = s->copy_stream;
         CUDA_TRY(cudaEventRecord(s->ev_step, st));
         rc = launch_render(s, d_frames, st);  // first: the render launch must be queued before the step kernels end
@@ -843,10 +879,12 @@ int xw_step_hd(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float* h_re
     CUDA_TRY(cudaMemcpyAsync(pin_r ? h_reward : s->h_rew, s->d_rew, sizeof(float) * s->n, cudaMemcpyDeviceToHost, cs));
     CUDA_TRY(cudaMemcpyAsync(pin_o ? h_game_over : s->h_over, s->d_over, sizeof(int32_t) * s->n, cudaMemcpyDeviceToHost, cs));
     if (split) {
-        CUDA_TRY(cudaEventRecord(s->ev_copy, cs));  // one host wait for both streams
-        CUDA_TRY(cudaStreamWaitEvent(st, s->ev_copy, 0));
+        if (wait_frames) {
+            CUDA_TRY(cudaEventRecord(s->ev_copy, cs));  // one host wait for both streams
+            CUDA_TRY(cudaStreamWaitEvent(st, s->ev_copy, 0));
+        }
     }
-    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaStreamSynchronize(split && !wait_frames ? cs : st));
     if (!pin_r) memcpy(h_reward, s->h_rew, sizeof(float) * s->n);
     if (!pin_o) memcpy(h_game_over, s->h_over, sizeof(int32_t) * s->n);
     return 0;
