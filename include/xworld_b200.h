@@ -199,7 +199,8 @@ int xw_num_steps(xw_sim* sim, int64_t* h_num_steps /* [n_envs] host */);
  * "goal_icon" i32[n][XW_MAX_GOALS]; "steps_in_task","num_steps","episode","n_success",
  * "n_failure","success_steps","minstd","error" i32[n].
  * Curriculum (only when cfg.curriculum > 0): "level" u8[n] (XWorldEnv.dump_curriculum_progress, xworld_env.py:62-63),
- * "check_counter" i32[n], "win_len","win_sum" u8[n][5] (length / successes of each task class's result window).
+ * "check_counter" i32[n], "win_len","win_sum" u8[n][5] (length / successes of each task class's result window),
+ * "win_pos" u8[n][5] and "win_bits" u32[n][5][7] (the windows themselves: with these a checkpoint restores everything).
  * Race: "pos_x","pos_y","angle" f32[n], "steps" i32[n], "state" f32[n][4]. */
 int xw_get_field(xw_sim* sim, const char* name, void* h_out, size_t bytes);
 int xw_set_field(xw_sim* sim, const char* name, const void* h_in, size_t bytes);

@@ -314,6 +314,30 @@ def test_action_none_and_batch_client(backend_cls, synthetic_catalog):
     parity.compare_state(eng, orc, "after the wire session")
 
 
+def test_checkpoint_resume_is_bit_exact(backend_cls, synthetic_catalog):
+    """Simulator.state_dict / load_state_dict: a fresh handle loaded with a snapshot continues exactly like the
+    original (state, rewards, game_over, frames), including the curriculum windows and auto-reset episodes."""
+    for name, kw in (("curriculum_nav3d_8x8_96", dict(auto_reset=1, curriculum_check_period=3)), ("c3_nav2d_11x11_84", dict(auto_reset=1))):
+        cfg = parity.make_cfg(name, **kw)
+        a = backend_cls(cfg, synthetic_catalog, 512)
+        a.reset()
+        for s in range(150):
+            a.step(parity.actions_for(s, 512, 4))
+        snap = a.sim.state_dict()
+        b = backend_cls(cfg, synthetic_catalog, 512)
+        b.sim.load_state_dict(snap)
+        for s in range(150, 260):
+            act = parity.actions_for(s, 512, 4)
+            r1, o1, f1 = a.step(act, render=(s % 50 == 0))
+            r2, o2, f2 = b.step(act, render=(s % 50 == 0))
+            assert (r1.view(np.uint32) == r2.view(np.uint32)).all() and (o1 == o2).all(), (name, s)
+            if f1 is not None:
+                assert (f1 == f2).all(), (name, s)
+        s1, s2 = a.sim.state_dict(), b.sim.state_dict()
+        for k in s1:
+            assert (np.asarray(s1[k]) == np.asarray(s2[k])).all(), (name, k)
+
+
 def test_simple_race_full_size_c5(backend_cls):
     """BASELINE config 5 at its full size: 1,048,576 envs.  Envs start in the same state (random=false), so envs fed
     the same action stream must stay bit-identical; 64 streams, each checked against the oracle (tol 1e-6)."""

@@ -919,7 +919,8 @@ static bool find_field(xw_sim* s, const char* name, FieldRef* f) {
             {"n_failure", d.n_failure, 4, 1, false}, {"success_steps", d.success_steps, 4, 1, false},
             {"minstd", d.minstd, 4, 1, false}, {"error", d.error, 4, 1, false},
             {"level", d.level, 1, 1, false}, {"check_counter", d.check_counter, 4, 1, false},
-            {"win_len", d.win_len, 1, XW_N_T3, false}, {"win_sum", d.win_sum, 1, XW_N_T3, false}};
+            {"win_len", d.win_len, 1, XW_N_T3, false}, {"win_sum", d.win_sum, 1, XW_N_T3, false},
+            {"win_pos", d.win_pos, 1, XW_N_T3, false}, {"win_bits", d.win_bits, 4, XW_N_T3 * XW_WIN_WORDS, false}};
         for (auto& t : tbl) if (k == t.n && t.p) { *f = {t.p, t.elem, t.per, t.gm}; return true; }
     } else if (s->cfg.game == XW_GAME_SIMPLE_RACE) {
         XwRaceCfg& r = s->race;

@@ -339,8 +339,10 @@ class Simulator(object):
         elif name in ("agent_x", "agent_y", "facing", "task", "stage", "event", "action_success", "target_mask",
                       "aux0", "aux1", "aux2", "level"):
             out = np.zeros(n, np.uint8)
-        elif name in ("win_len", "win_sum"):
+        elif name in ("win_len", "win_sum", "win_pos"):
             out = np.zeros((n, 5), np.uint8)
+        elif name == "win_bits":
+            out = np.zeros((n, 5, 7), np.uint32)
         elif name == "state":
             out = np.zeros((n, 4), np.float32)
         elif name in ("pos_x", "pos_y", "angle"):
@@ -354,6 +356,32 @@ class Simulator(object):
         cur = self.get_field(name)
         v = np.ascontiguousarray(value, cur.dtype).reshape(cur.shape)
         self._check(self._lib.xw_set_field(self._h, name.encode(), v.ctypes.data, v.nbytes))
+
+    # ------------------------------------------------------------------ checkpoint / resume
+    _XWORLD_STATE = ("grid", "agent_x", "agent_y", "facing", "task", "stage", "event", "action_success", "target_mask", "aux0",
+                     "aux1", "aux2", "goal_x", "goal_y", "goal_icon", "goal_name", "steps_in_task", "num_steps", "episode",
+                     "n_success", "n_failure", "success_steps", "minstd", "error")
+    _CURRICULUM_STATE = ("level", "check_counter", "win_len", "win_sum", "win_pos", "win_bits")
+    _RACE_STATE = ("pos_x", "pos_y", "angle", "steps", "state")
+
+    def state_dict(self):
+        """Everything a batch needs to continue bit for bit: the SoA state of every env (the episode counter and the
+        minstd word are the RNG state: the Philox draws are counter-based), copied to the host.  The reference has no
+        counterpart beyond --curriculum_stamp (xworld.cpp:92-135); SURVEY lists checkpoint/resume as an aux subsystem."""
+        if self.cfg.game == _abi.XW_GAME_SIMPLE_GAME:
+            raise RuntimeError("state_dict(): not available for simple_game")
+        names = self._RACE_STATE if self.cfg.game == _abi.XW_GAME_SIMPLE_RACE else self._XWORLD_STATE + (
+            self._CURRICULUM_STATE if self.cfg.curriculum != 0 else ())
+        sd = {k: self.get_field(k) for k in names}
+        sd["_last_over"], sd["_last_reward"] = self._last_over.copy(), np.array(self._last_reward, np.float32)
+        return sd
+
+    def load_state_dict(self, sd):
+        for k, v in sd.items():
+            if not k.startswith("_"):
+                self.set_field(k, v)
+        self._last_over = np.array(sd["_last_over"], np.int32)
+        self._last_reward = np.array(sd["_last_reward"], np.float32)
 
     def launch_count(self):
         return int(self._lib.xw_launch_count(self._h))
