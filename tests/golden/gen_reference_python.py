@@ -472,13 +472,16 @@ def main_curriculum():
     out = {"generator": "tests/golden/gen_reference_python.py curriculum", "curriculum": thr, "cases": []}
     cases = [("period5", 5, 24, 30, 60, 3, 0), ("period100_reference", 100, 1, 330, 12, 1, 0)]
     cases += [("start_level%d" % k, 4, 6 if k in (2, 3) else 4, 24 if k in (2, 3) else 14, 60, 1, k) for k in range(1, 6)]  # XWorldNav(item_path, start_level=k)
+    # Envs in which the displaced-referent rule of the padded levels lets a Direction episode SUCCEED: found
+    # by running this same action policy against the oracle (gids 0..1500), then replayed here by the reference itself.
+    cases += [("level2_direction_success", 4, [405, 249], 10, 60, 1, 2), ("level3_direction_success", 4, [68, 206], 4, 60, 1, 3)]
     for tag, period, n_envs, n_ep, n_st, msf, start_level in cases:
         FLAGS["max_steps_factor"] = msf
         Host.start_level = start_level
         mods = load_reference_python(8, 4, 16)  # XWorldNav.py as it is
         mods["xworld_env"].XWorldEnv.curriculum_check_period = period  # a class attribute (xworld_env.py:58)
         envs = []
-        for gid in range(n_envs):
+        for gid in (range(n_envs) if isinstance(n_envs, int) else n_envs):
             envs.append({"env_gid": gid,
                          "episodes": run_case(mods, cat, 0, 8, 4, 16, seed=4321, simulator_seed=3, env_gid=gid,
                                               n_episodes=n_ep, n_steps=n_st, act_seed=2000 + gid, curriculum=True)})

@@ -110,6 +110,7 @@ def test_curriculum_against_reference_python(oracle_lib, synthetic_catalog):
           "XWorld3DNavTargetAvoid"]
     n_steps = n_resets = 0
     levels, ups = set(), 0
+    displaced_ok = 0  # Direction episodes answered correctly at a padded level with offset 1
     for case in tr["cases"]:
         cfg = _abi.default_config(height=8, width=8, n_goals=4, n_blocks=16, rules=0, seed=case["seed"],
                                   simulator_seed=case["simulator_seed"], curriculum=tr["curriculum"],
@@ -155,6 +156,8 @@ def test_curriculum_against_reference_python(oracle_lib, synthetic_catalog):
                     assert [e.agent_x, e.agent_y] == s["agent"] and e.action_success == s["ok"], (where, i)
                     assert e.event == EVMAP[s["ev"]], (where, i)
                 assert e.minstd == ep["minstd"], where
+                displaced_ok += ep["task"] == 3 and ep["level"] in (2, 3) and ep["steps"][-1]["ev"] == "correct_goal"
+    assert displaced_ok >= 4
     assert levels == {0, 1, 2, 3, 4, 5} and ups >= 2 and n_resets > 1300 and n_steps > 10000, (levels, ups, n_resets, n_steps)
 
 
