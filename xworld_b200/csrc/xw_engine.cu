@@ -76,6 +76,8 @@ __global__ void __launch_bounds__(256) k_race_reset(XwRaceCfg r, const uint8_t* 
     if (e >= r.n || (mask && !mask[e])) return;
     xw_race_reset_env(r, e);
 }
+// 46 registers (5 CTAs / SM).  Forcing 6 or 8 CTAs per SM (40 / 32 registers, spills) is slower: 18.4 / 21.1 us
+// against 18.2 us per step at 1,048,576 envs (profiles/r01_summary.md).
 __global__ void __launch_bounds__(256) k_race_step(XwRaceCfg r, const int32_t* __restrict__ actions, int n_actions,
                                                    float* __restrict__ reward, int32_t* __restrict__ over, int32_t* error) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
