@@ -93,6 +93,35 @@ def test_packets_against_the_reference_encoder(R):
         assert wire.encode_packet(wire.decode_packet(mine)) == mine
 
 
+def test_the_reference_serialization_test_vector(R):
+    """tests/test_statepacket.cpp:77-104 (StatePacket, serialization): "screen" = pixels {1,2,3,4} + ids {10,11},
+    "internal_state" = reals {1.5..6.5} + str "abc"; encode, decode, compare -- here through the C ABI on one side
+    and the reference's own StatePacket on the other."""
+    lib = _abi.load()
+    px = (C.c_uint8 * 4)(1, 2, 3, 4)
+    ids = (C.c_int32 * 2)(10, 11)
+    re = (C.c_float * 6)(1.5, 2.5, 3.5, 4.5, 5.5, 6.5)
+    f = (_abi.XwWireField * 2)()
+    f[0].key, f[0].pixels, f[0].n_pixels, f[0].ids, f[0].n_ids = b"screen", px, 4, ids, 2
+    f[1].key, f[1].reals, f[1].n_reals, f[1].str = b"internal_state", re, 6, b"abc"
+    n = lib.xw_wire_encode_packet(f, 2, None, 0)
+    buf = (C.c_uint8 * n)()
+    assert lib.xw_wire_encode_packet(f, 2, buf, n) == n
+    mine = bytes(buf)
+    theirs = ref_call(R.ref_wire_encode_packet, C.cast(f, C.c_void_p), 2)
+    assert len(mine) == len(theirs) and ref_dump(R, mine) == ref_dump(R, theirs)
+    assert "screen|06" in ref_dump(R, mine) and "internal_state|09" in ref_dump(R, mine)  # flag bytes: pixels|id, reals|str
+    out = (_abi.XwWireField * 8)()
+    k, used = C.c_int32(), C.c_size_t()
+    tb = (C.c_uint8 * len(theirs)).from_buffer_copy(theirs)
+    assert lib.xw_wire_decode_packet(tb, len(theirs), out, 8, C.byref(k), C.byref(used)) == 0
+    assert k.value == 2 and used.value == len(theirs)  # EXPECT_TRUE(buf.eof())
+    got = {out[i].key: out[i] for i in range(2)}
+    s, i = got[b"screen"], got[b"internal_state"]
+    assert C.string_at(s.pixels, 4) == bytes(px) and s.n_ids == 2 and C.string_at(s.ids, 8) == bytes(ids) and not s.reals and s.str is None
+    assert i.n_reals == 6 and C.string_at(i.reals, 24) == bytes(re) and i.str == b"abc" and not i.pixels and not i.ids
+
+
 def test_requests_and_replies_byte_for_byte(R):
     # requests, as SimulatorServer sends them
     for act in ({"action": 1}, {"pred_sentence": "what"}):
