@@ -156,6 +156,17 @@ def test_requests_and_replies_byte_for_byte(R):
     assert wire.reply_text("report_perf") == ref_call(R.ref_wire_reply_text, b"report_perf", None)
 
 
+def test_empty_vectors_round_trip():
+    """tests/test_binary_buffer.cpp:160-175: an empty vector travels as a count of 0 and reads back empty (the
+    reference's StateBuffer::set_value CHECKs on an empty range, so only the codec itself is exercised here)."""
+    for d in ({"reward": np.zeros(0, np.float32)}, {"action": np.zeros(0, np.int32)}, {"screen": np.zeros(0, np.uint8)}):
+        data = wire.encode_packet(d)
+        k = next(iter(d))
+        assert len(data) == 8 + (8 + len(k) + 1) + 1 + 8
+        back = wire.decode_packet(data)
+        assert list(back) == [k] and len(back[k]) == 0 and back[k].dtype == d[k].dtype
+
+
 def test_malformed_input_is_an_error_not_a_crash():
     good = wire.compose_request("take_actions", {"action": 1})[8:]
     for cut in range(len(good)):
