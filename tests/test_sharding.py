@@ -69,3 +69,36 @@ def test_sharded_batch_equals_single_batch(synthetic_catalog):
             assert (r.view(np.uint32) == r_full[lo:hi].view(np.uint32)).all() and (ov == o_full[lo:hi]).all()
     for lo, hi, o in shards:
         assert (o.field("grid") == full.field("grid")[lo:hi]).all()
+
+
+def test_bench_clock_sampler_picks_rows_of_the_timed_region():
+    """bench.py's ClockSampler: rows stamped inside [begin, end + one period] are the ones reported; a region shorter
+    than a period falls back to the rows next to it; no nvidia-smi (this container) is reported as such."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(__file__), "..", "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class FakeProc(object):
+        def terminate(self):
+            pass
+
+    class FakeThread(object):
+        def join(self, timeout=None):
+            pass
+
+    def sampler(stamps, clocks, t0, t1):
+        s = bench.ClockSampler(0)
+        s.proc, s.t = FakeProc(), FakeThread()
+        s.stamps = list(stamps)
+        s.rows = [["0", str(c), "1965", "300", "0x0", "Not Active", "Not Active", "Not Active", "Not Active"] for c in clocks]
+        s.t0, s.t1 = t0, t1
+        return s.stop()
+
+    out = sampler([0.00, 0.02, 0.04, 0.06, 0.08, 0.50], [300, 1965, 1950, 1965, 1200, 210], 0.015, 0.065)
+    assert out["window"] == "timed region" and out["samples"] == 4 and out["sm_mhz"] == 1957.5 and out["reasons"] == []
+    out = sampler([0.00, 0.10, 0.20], [300, 1965, 400], 0.11, 0.12)
+    assert out["window"].startswith("rows adjacent") and out["samples"] >= 2
+    s = bench.ClockSampler(0)
+    assert s.stop()["reasons"] == ["nvidia-smi unavailable"]
