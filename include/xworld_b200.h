@@ -128,7 +128,8 @@ typedef struct {
                                  last level's map every episode; > 0 = per-env level schedule: a (3+level)-sided
                                  world with num_goals_seq / num_blocks_seq[level] entities inside the 8x8 map, padded
                                  with bricks, one level up when the lowest per-task success rate over the last 200
-                                 results reaches this threshold.  navigation2d.json rules, 8x8 map only */
+                                 results reaches this threshold.  8x8 map only.  With the walls.json rules no task
+                                 class ever records a result in lang_acquisition mode, so an env keeps its start level */
     int32_t curriculum_check_period; /* XWorldEnv.curriculum_check_period (xworld_env.py:58); 0 = the reference's 100 */
     int32_t start_level;      /* XWorldNav(start_level=...) (XWorldNav.py:8), 0..5 */
     int32_t reserved[5];

@@ -740,6 +740,9 @@ int xo_reset(const xw_config* cfg, const xw_catalog* cat, xo_env* e) {
         if (cfg->curriculum != 0) embed_world(cfg, e);
         e->stage = XW_STAGE_NAVIGATION;
     } else {
+        if (cfg->curriculum != 0) { /* the same check; with these rules no task class ever records (xworld_task.py:205-214) */
+            if (current_usage(cfg, e) >= (double)cfg->curriculum && e->level < 6 - 1) e->level += 1;
+        }
         int rc = gen_map(cfg, cat, e, ep, 0);
         if (rc) return rc;
         double r;
@@ -751,6 +754,7 @@ int xo_reset(const xw_config* cfg, const xw_catalog* cat, xo_env* e) {
             if (reachable(e, cell_of(e, e->agent_x, e->agent_y), cell_of(e, e->goal_x[g], e->goal_y[g]), 0)) e->aux1 |= 1 << g;
             if (cat->icon_colored[e->goal_icon[g]]) e->aux2 |= 1 << g;
         }
+        if (cfg->curriculum != 0) { int t = e->task; e->task = -1; embed_world(cfg, e); e->task = t; } /* (no middle cell here) */
     }
     return 0;
 }

@@ -425,7 +425,7 @@ def run_case(mods, cat, rules, dim, n_goals, n_blocks, seed, simulator_seed, env
             a = int(arng.randint(0, 4))
             if curriculum and arng.rand() < 0.4:
                 a = 1  # MOVE_DOWN is the only move that can score (the heading is +y): lets the success rates rise
-            if curriculum and T3[t] == "XWorld3DNavTargetDirection" and arng.rand() < 0.7:
+            if curriculum and rules == 0 and T3[t] == "XWorld3DNavTargetDirection" and arng.rand() < 0.7:
                 # walk to the goal next to the referent and bump it from above, so that the displaced-referent test
                 # of the padded levels (oracle/xw_oracle.c xo_teach) sees goals reached in every arrangement
                 ref_id = task.target[0].id
@@ -475,7 +475,12 @@ def main_curriculum():
     # Envs in which the displaced-referent rule of the padded levels lets a Direction episode SUCCEED: found
     # by running this same action policy against the oracle (gids 0..1500), then replayed here by the reference itself.
     cases += [("level2_direction_success", 4, [405, 249], 10, 60, 1, 2), ("level3_direction_success", 4, [68, 206], 4, 60, 1, 3)]
-    for tag, period, n_envs, n_ep, n_st, msf, start_level in cases:
+    cases = [c + (0,) for c in cases]
+    # walls.json rules (test_xworld.py:31-40 runs them with curriculum 0.1): in lang_acquisition mode no task class ever
+    # records a result (xworld_task.py:205-214: time-up is one_channel only, a goal cell is never entered; the
+    # XWorldRec* tasks stay in idle), so usage stays empty and the env keeps its start level: a padded world for ever
+    cases += [("nav2d_level0", 4, 3, 8, 30, 10, 0, 1), ("nav2d_start_level3", 4, 3, 6, 40, 10, 3, 1)]
+    for tag, period, n_envs, n_ep, n_st, msf, start_level, rules in cases:
         FLAGS["max_steps_factor"] = msf
         Host.start_level = start_level
         mods = load_reference_python(8, 4, 16)  # XWorldNav.py as it is
@@ -483,11 +488,11 @@ def main_curriculum():
         envs = []
         for gid in (range(n_envs) if isinstance(n_envs, int) else n_envs):
             envs.append({"env_gid": gid,
-                         "episodes": run_case(mods, cat, 0, 8, 4, 16, seed=4321, simulator_seed=3, env_gid=gid,
+                         "episodes": run_case(mods, cat, rules, 8, 4, 16, seed=4321, simulator_seed=3, env_gid=gid,
                                               n_episodes=n_ep, n_steps=n_st, act_seed=2000 + gid, curriculum=True)})
         levels = [ep["level"] for e in envs for ep in e["episodes"]]
         print(tag, "levels reached:", sorted(set(levels)))
-        out["cases"].append({"tag": tag, "rules": 0, "dim": 8, "n_goals": 4, "n_blocks": 16, "seed": 4321, "simulator_seed": 3,
+        out["cases"].append({"tag": tag, "rules": rules, "dim": 8, "n_goals": 4, "n_blocks": 16, "seed": 4321, "simulator_seed": 3,
                              "check_period": period, "max_steps_factor": msf, "start_level": start_level, "envs": envs})
     path = os.path.join(HERE, "refpy_curriculum.json.gz")
     with gzip.GzipFile(path, "wb", mtime=0) as f:

@@ -24,6 +24,8 @@ CONFIGS = {
     # XWorldNav's level schedule (the check period is shortened so that levels change within a test)
     "curriculum_nav3d_8x8_96": dict(height=8, width=8, n_goals=4, n_blocks=16, rules=_abi.XW_RULES_NAV3D, curriculum=0.1,
                                     curriculum_check_period=5),
+    "curriculum_nav2d_8x8_96": dict(height=8, width=8, n_goals=4, n_blocks=16, rules=_abi.XW_RULES_NAV2D, curriculum=0.1,
+                                    start_level=2, max_steps=40),
     "ref_nav2d_8x8_96": dict(height=8, width=8, n_goals=4, n_blocks=16, rules=_abi.XW_RULES_NAV2D, max_steps=64),
 }
 

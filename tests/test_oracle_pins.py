@@ -112,7 +112,7 @@ def test_curriculum_against_reference_python(oracle_lib, synthetic_catalog):
     levels, ups = set(), 0
     displaced_ok = 0  # Direction episodes answered correctly at a padded level with offset 1
     for case in tr["cases"]:
-        cfg = _abi.default_config(height=8, width=8, n_goals=4, n_blocks=16, rules=0, seed=case["seed"],
+        cfg = _abi.default_config(height=8, width=8, n_goals=4, n_blocks=16, rules=case["rules"], seed=case["seed"],
                                   simulator_seed=case["simulator_seed"], curriculum=tr["curriculum"],
                                   curriculum_check_period=case["check_period"], max_steps_factor=case["max_steps_factor"],
                                   start_level=case["start_level"])
@@ -131,6 +131,9 @@ def test_curriculum_against_reference_python(oracle_lib, synthetic_catalog):
                 ups += e.level != prev
                 prev = e.level
                 assert e.check_counter == ep["check_counter"], where
+                if case["rules"] == 1:  # walls.json rules: nothing is ever recorded, the level stays
+                    assert ep["usage"] == {} and e.level == case["start_level"] and ep["check_counter"] == ep["episode"], where
+                    assert list(e.seq_len) == [0] * 5, where
                 for t, name in enumerate(T3):
                     ln, sm = ep["usage"].get(name, [0, 0])
                     assert e.seq_len[t] == ln and sum(e.seq[t][:ln]) == sm, (where, name)
@@ -140,7 +143,10 @@ def test_curriculum_against_reference_python(oracle_lib, synthetic_catalog):
                 assert [e.agent_x, e.agent_y] == rs["agent"], where
                 assert list(e.goal_x)[:G] == rs["goal_x"] and list(e.goal_y)[:G] == rs["goal_y"], where
                 assert list(e.goal_name)[:G] == rs["goal_name"] and list(e.goal_icon)[:G] == rs["goal_icon"], where
-                assert e.task == ep["task"], where
+                if case["rules"] == 1:
+                    assert e.task == ep["reset_task"] and (e.stage != 0) == (ep["reset_stage"] != "idle"), where
+                else:
+                    assert e.task == ep["task"], where
                 if "target_mask" in ep:
                     assert e.target_mask == ep["target_mask"], where
                 if "mid" in ep:
@@ -156,7 +162,8 @@ def test_curriculum_against_reference_python(oracle_lib, synthetic_catalog):
                     assert [e.agent_x, e.agent_y] == s["agent"] and e.action_success == s["ok"], (where, i)
                     assert e.event == EVMAP[s["ev"]], (where, i)
                 assert e.minstd == ep["minstd"], where
-                displaced_ok += ep["task"] == 3 and ep["level"] in (2, 3) and ep["steps"][-1]["ev"] == "correct_goal"
+                displaced_ok += (case["rules"] == 0 and ep["task"] == 3 and ep["level"] in (2, 3) and
+                                 ep["steps"][-1]["ev"] == "correct_goal")
     assert displaced_ok >= 4
     assert levels == {0, 1, 2, 3, 4, 5} and ups >= 2 and n_resets > 1300 and n_steps > 10000, (levels, ups, n_resets, n_steps)
 

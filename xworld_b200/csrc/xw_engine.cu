@@ -191,7 +191,6 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
     if (c.rules != XW_RULES_NAV3D && c.rules != XW_RULES_NAV2D) return set_err(XW_ERR_INVALID_ARG, "unknown rules");
     if (c.curriculum != 0) {  // XWorldNav's level schedule is written for its own 8x8 map (XWorldNav.py:10-11,27-33)
         if (!(c.curriculum > 0)) return set_err(XW_ERR_INVALID_ARG, "curriculum must be >= 0");
-        if (c.rules != XW_RULES_NAV3D) return set_err(XW_ERR_UNSUPPORTED, "curriculum > 0 is implemented for the navigation2d.json rules only");
         if (c.height != 8 || c.n_goals != 4 || c.n_blocks != 16)
             return set_err(XW_ERR_INVALID_ARG, "curriculum > 0 needs XWorldNav's own map: 8x8, 4 goals, 16 blocks");
         if (c.start_level < 0 || c.start_level >= XW_N_LEVELS) return set_err(XW_ERR_INVALID_ARG, "start_level must be in [0,%d]", XW_N_LEVELS - 1);

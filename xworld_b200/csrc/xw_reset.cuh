@@ -547,7 +547,7 @@ XW_HD void xw_reset_commit(const XwDev& d, int e, uint32_t ep, uint32_t minstd, 
         // goals whose icon has a colour (properties.txt)
         int reach = 0, colored = 0;
         const XwMask rset = xw_flood(c, c.block, c.agent);  // only blocks are obstacles here: goals are walked over
-        for (int k = 0; k < d.G; ++k) {
+        for (int k = 0; k < c.nG; ++k) {
             if (m_get(rset, c.gcell[k])) reach |= 1 << k;
             if (d.icon_colored[c.gicon[k]]) colored |= 1 << k;
         }
