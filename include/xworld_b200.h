@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define XW_ABI_VERSION 1
+#define XW_ABI_VERSION 2
 #define XW_MAX_GOALS 8   /* goals per map (XWorldNav uses 2..4, XWorldNav.py:31-32) */
 #define XW_MAX_DIM 16    /* map side in cells (reference hard-codes 8, XWorldNav.py:10-11) */
 #define XW_ICON_SIZE 64  /* XItem::item_size_, xitem.h:151 */
@@ -48,6 +48,12 @@ typedef enum {
     XW_GAME_SIMPLE_GAME = 1, /* "simple_game" -> host (BASELINE config 1: CPU plumbing) */
     XW_GAME_SIMPLE_RACE = 2  /* "simple_race" -> CUDA, fp32 */
 } xw_game;
+
+/* --task_mode (xworld_simulator.cpp:34-37).  lang_acquisition: a teacher event ends the episode (game_over =
+ * SUCCESS / DEAD / MAX_STEP, xworld_simulator.cpp:165-177).  one_channel: "each session has all tasks until the max
+ * steps" (:192-193): game_over reports only --max_steps; the walls.json navigation tasks get their time-up rule
+ * (xworld_task.py:205-210).  "interactive" (language-only sessions) is out of scope. */
+typedef enum { XW_TASK_LANG_ACQUISITION = 0, XW_TASK_ONE_CHANNEL = 1 } xw_task_mode;
 
 /* Teacher rule set = the task group of the conf json (teacher.cpp:70-99). */
 typedef enum {
@@ -107,7 +113,11 @@ typedef struct {
     int32_t context;          /* --context (frames stacked, simulator.cpp:21) */
     int32_t max_steps;        /* --max_steps, 0 = off (simulator.h:68-74) */
     int32_t max_steps_factor; /* --max_steps_factor (xworld3d_task.py:38), default 10 */
-    int32_t visible_radius;   /* --visible_radius; only 0 (fully observed) is implemented */
+    int32_t visible_radius;   /* --visible_radius (xworld_simulator.cpp:26): 0 = fully observed; an odd vr > 0 = the
+                                 first-person view (xmap.cpp:148-200): a vr x vr cell window ahead of the agent, wall
+                                 shadows, rotated to the agent's heading, frames of vr*(84/vr) pixels a side
+                                 (xworld_simulator.cpp:62-68), six actions (xitem.cpp:82-86).  Clamped to the map side
+                                 like the reference; an even value is an error (CHECK_EQ(vr % 2, 1), xmap.cpp:277) */
     int32_t auto_reset;       /* 0 = reference behaviour (caller resets) */
     int32_t simulator_seed;   /* --simulator_seed: env i seeds minstd_rand0 like the reference's
                                  i-th thread (simulator_util.cpp:38-55) */
@@ -132,7 +142,15 @@ typedef struct {
                                  class ever records a result in lang_acquisition mode, so an env keeps its start level */
     int32_t curriculum_check_period; /* XWorldEnv.curriculum_check_period (xworld_env.py:58); 0 = the reference's 100 */
     int32_t start_level;      /* XWorldNav(start_level=...) (XWorldNav.py:8), 0..5 */
-    int32_t reserved[5];
+    /* ---- flags the reference reads per process (xworld_simulator.cpp:34-37, simulator.cpp:25) ---- */
+    int32_t task_mode;        /* xw_task_mode: --task_mode.  The C++ flag default is "lang_acquisition" (= 0 here); the
+                                 reference's PYTHON default is "one_channel" (py_simulator.cpp:128-130), which
+                                 xworld_b200.Simulator.create mirrors */
+    int32_t gray;             /* 1 = --color=false (the reference default, simulator.cpp:25): one-channel frames,
+                                 cv::cvtColor(BGR2GRAY) after the resize (xworld_simulator.cpp:529-531) with the
+                                 coefficients of the OpenCV 3.2.0 the reference pins (cmake/opencv.cmake:5-6):
+                                 (B*1868 + G*9617 + R*4899 + 8192) >> 14.  0 = --color=true: planes B, G, R */
+    int32_t reserved[3];
 } xw_config;
 
 typedef struct xw_sim xw_sim; /* opaque handle: one batch of n_envs environments on one GPU */

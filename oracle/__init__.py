@@ -23,6 +23,8 @@ MAXG, MAXD = _abi.XW_MAX_GOALS, _abi.XW_MAX_DIM
 
 (SITE_NAMES, SITE_MAZE, SITE_BLOCKS, SITE_GOAL_LOC, SITE_GOAL_ASSET, SITE_AGENT_LOC, SITE_TASK_A,
  SITE_TASK_B, SITE_TASK_SHUF, SITE_TASK_AGENT) = range(1, 11)
+SITE_AGENT_YAW, SITE_GOAL_POSE = 12, 13
+YAW_STEPS = 4096
 
 
 class XoEnv(C.Structure):
@@ -46,6 +48,7 @@ class XoEnv(C.Structure):
         ("level", C.c_int32), ("dim", C.c_int32), ("check_counter", C.c_int32),
         ("seq_len", C.c_int32 * 5),
         ("seq", (C.c_uint8 * 200) * 5),
+        ("goal_yaw", C.c_double * MAXG), ("goal_scale", C.c_double * MAXG), ("goal_offset", C.c_double * MAXG),
     ]
 
 
@@ -60,8 +63,9 @@ class XoSimpleGame(C.Structure):
 
 def build(force=False):
     """Compile xw_oracle.c (and oracle/_ref when /root/reference is present)."""
-    if force or not os.path.exists(LIB) or \
-            os.path.getmtime(LIB) < os.path.getmtime(os.path.join(_HERE, "xw_oracle.c")):
+    srcs = [os.path.join(_HERE, f) for f in ("xw_oracle.c", "xw_oracle_fpv.c", "xw_oracle.h", "Makefile")]
+    srcs.append(os.path.join(_HERE, "..", "include", "xworld_b200.h"))
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "libxw_oracle.so"], stdout=subprocess.DEVNULL)
     if os.path.isdir("/root/reference"):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
@@ -98,6 +102,15 @@ def lib():
         L.xo_resize_linear_8uc3.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int]
         L.xo_render.argtypes = [cfgp, catp, envp, vp]
         L.xo_frame_dims.argtypes = [cfgp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        dbl = C.c_double
+        L.xo_rotation_matrix.argtypes = [C.c_float, C.c_float, dbl, dbl, C.POINTER(dbl)]
+        L.xo_warp_affine_8uc3.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.POINTER(dbl), vp]
+        L.xo_item_image.argtypes = [vp, dbl, dbl, dbl, vp]
+        L.xo_facing_dir.argtypes = [dbl]
+        L.xo_image_masking.argtypes = [envp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), vp]
+        L.xo_visible_radius.argtypes = [cfgp]
+        L.xo_goal_pose.argtypes = [u64, i64, u32, u32, C.c_int, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(dbl)]
+        L.xo_render_fpv.argtypes = [cfgp, catp, envp, vp]
         L.xo_batch_reset.argtypes = [cfgp, catp, envp, C.c_int, C.c_int]
         L.xo_batch_step.argtypes = [cfgp, catp, envp, C.c_int, vp, C.c_int, vp, vp, vp, C.c_int]
         L.xo_sizeof_env.restype = C.c_int
@@ -140,6 +153,7 @@ class Oracle(object):
         oh, ow = C.c_int(), C.c_int()
         self.L.xo_frame_dims(C.byref(cfg), C.byref(oh), C.byref(ow))
         self.out_h, self.out_w = oh.value, ow.value
+        self.channels = 1 if cfg.gray else 3
 
     def reset(self, mask=None):
         if mask is None:
@@ -155,7 +169,7 @@ class Oracle(object):
         actions = np.ascontiguousarray(actions, dtype=np.int32)
         reward = np.zeros(self.n, np.float32)
         over = np.zeros(self.n, np.int32)
-        frames = np.zeros((self.n, 3, self.out_h, self.out_w), np.uint8) if render else None
+        frames = np.zeros((self.n, self.channels, self.out_h, self.out_w), np.uint8) if render else None
         rc = self.L.xo_batch_step(
             C.byref(self.cfg), C.byref(self.cat_c), self.envs, self.n, actions.ctypes.data, act_rep,
             reward.ctypes.data, over.ctypes.data, frames.ctypes.data if render else None, self.threads)
@@ -164,7 +178,7 @@ class Oracle(object):
 
     def render(self, idx=None):
         idx = range(self.n) if idx is None else idx
-        out = np.zeros((len(idx), 3, self.out_h, self.out_w), np.uint8)
+        out = np.zeros((len(idx), self.channels, self.out_h, self.out_w), np.uint8)
         for k, i in enumerate(idx):
             self.L.xo_render(C.byref(self.cfg), C.byref(self.cat_c), C.byref(self.envs[i]), out[k].ctypes.data)
         return out
@@ -178,8 +192,12 @@ class Oracle(object):
             return np.array([list(getattr(e, name)) for e in self.envs], np.uint8)
         if name == "goal_icon":
             return np.array([list(e.goal_icon) for e in self.envs], np.int32)
-        if name == "facing":
-            return np.full(n, 1, np.uint8)
+        if name == "facing":  # XItem::get_item_facing_dir of the agent's yaw: 0 right, 1 down, 2 left, 3 up
+            return np.array([self.L.xo_facing_dir(e.agent_yaw) for e in self.envs], np.uint8)
+        if name in ("goal_scale", "goal_offset", "goal_yaw"):
+            return np.array([list(getattr(e, name)) for e in self.envs], np.float64)
+        if name == "goal_yaw_idx":  # yaw = 4 * PI_2 * idx / 4096 (xo_goal_pose); defaults (fully observed) read 1024
+            return np.array([[int(round(y / (1.5707963 * 4) * YAW_STEPS)) for y in e.goal_yaw] for e in self.envs], np.uint16)
         if name == "level":
             return np.array([e.level for e in self.envs], np.uint8)
         if name == "check_counter":

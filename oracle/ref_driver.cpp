@@ -111,6 +111,15 @@ int ref_map_act(void* p, int action, int* ax, int* ay, double* yaw, int* contact
     *contact = contacts.empty() ? -1 : std::stoi(contacts[0].substr(1));
     return ok ? 1 : 0;
 }
+// XMap::image_masking (xmap.cpp:273-362) at the agent's location and yaw: rect4 = {x, y, width, height} in cells of the
+// padded map, shadow = vr*vr flags
+void ref_map_masking(void* p, int vr, int* rect4, uint8_t* shadow) {
+    RefMap* m = (RefMap*)p;
+    std::vector<bool> sh;
+    cv::Rect r = m->map.image_masking(m->agent->get_item_location(), m->agent->get_item_yaw(), vr, sh);
+    rect4[0] = r.x; rect4[1] = r.y; rect4[2] = r.width; rect4[3] = r.height;
+    for (size_t i = 0; i < sh.size(); ++i) shadow[i] = sh[i] ? 1 : 0;
+}
 int ref_map_num_actions(void* p) { return ((RefMap*)p)->agent->get_num_actions(); }
 
 // ---- wire format: the reference's own util::BinaryBuffer (memory_util.h) and StatePacket::encode/decode

@@ -249,6 +249,13 @@ static int gen_map(const xw_config* cfg, const xw_catalog* cat, xo_env* e, uint3
     for (int i = 0; i < nb; ++i) e->grid[blocks[i]] = XW_CELL_EMPTY;
     for (int k = 0; k < n_blocks; ++k) e->grid[block_cells[k]] = XW_CELL_BLOCK;
     e->agent_yaw = 1.5707963; /* Entity default yaw, xworld_env.py:42 (not randomised when visible_radius==0) */
+    for (int k = 0; k < XW_MAX_GOALS; ++k) { e->goal_yaw[k] = 1.5707963; e->goal_scale[k] = 1.0; e->goal_offset[k] = 0.0; }
+    if (cfg->visible_radius > 0) { /* set_property, xworld_env.py:207-223: "if partially observed, perturb the objects" */
+        static const int yaw_range[4] = {-1, 0, 1, 2}; /* range(-1, 3) */
+        e->agent_yaw = yaw_range[xo_randbelow(xo_draw(seed, gid, ep, att, XO_SITE_AGENT_YAW, 0), 4)] * 1.5707963;
+        for (int k = 0; k < n_goals; ++k)
+            xo_goal_pose(seed, gid, ep, att, k, &e->goal_yaw[k], &e->goal_scale[k], &e->goal_offset[k]);
+    }
     return 0;
 }
 
@@ -629,6 +636,13 @@ int xo_teach(const xw_config* cfg, const xw_catalog* cat, xo_env* e, int32_t col
             double r = -0.1;                          /* time_penalty */
             if (!e->action_success) r += -0.2;        /* failed_action_penalty */
             e->steps_in_task += 1;
+            /* one_channel only: `self.steps_in_cur_task >= h*w / 2` with h, w = get_max_dims() and Python-2 integer
+             * division: time up -> _record_failure, back to idle, no event (xworld_task.py:203-210) */
+            if (cfg->task_mode == XW_TASK_ONE_CHANNEL && e->steps_in_task >= cfg->height * cfg->width / 2) {
+                e->steps_in_task = 0;
+                e->n_failure += 1;
+                e->stage = XW_STAGE_IDLE;
+            }
             /* agent.loc == self.target: the target is a goal cell, goals block => never.
              * agent.loc in goal_locs: never, same reason. */
             reward += r;
@@ -711,6 +725,8 @@ void xo_env_init(const xw_config* cfg, xo_env* e, int64_t env_gid) {
     e->env_gid = env_gid;
     e->H = cfg->height; e->W = cfg->width; e->n_goals = cfg->n_goals;
     e->level = cfg->start_level; e->dim = cfg->height;
+    e->agent_yaw = 1.5707963;
+    for (int k = 0; k < XW_MAX_GOALS; ++k) { e->goal_yaw[k] = 1.5707963; e->goal_scale[k] = 1.0; e->goal_offset[k] = 0.0; }
     /* env i plays the role of the reference's i-th simulator thread (1-based) */
     e->minstd = xo_minstd_seed_for_thread(cfg->simulator_seed, (int32_t)(env_gid + 1));
 }
@@ -763,14 +779,40 @@ int xo_reset(const xw_config* cfg, const xw_catalog* cat, xo_env* e) {
 int xo_step(const xw_config* cfg, const xw_catalog* cat, xo_env* e, int32_t action, int32_t act_rep,
             float* reward_out, int32_t* game_over) {
     static const int DX[4] = {0, 0, -1, 1}, DY[4] = {-1, 1, 0, 0}; /* XAgent::act, xitem.cpp:94-98 */
-    if (action < 0 || action >= 4) { e->error = XW_ERR_INVALID_ACTION; return XW_ERR_INVALID_ACTION; }
+    const int fpv = cfg->visible_radius > 0;
+    if (action < 0 || action >= (fpv ? 6 : 4)) { e->error = XW_ERR_INVALID_ACTION; return XW_ERR_INVALID_ACTION; }
     float r = 0;
     e->num_steps += 1; /* GameSimulator::take_actions counts calls, not repeats (simulator.cpp:100) */
     int collided = 0;
     for (int rep = 0; rep < act_rep; ++rep) {
         /* XWorldSimulator::take_action (xworld_simulator.cpp:200-265) -> XMap::move_item (xmap.cpp:76-101) */
-        int tx = e->agent_x + DX[action], ty = e->agent_y + DY[action];
-        if (!in_bounds(e, tx, ty)) {
+        int tx, ty;
+        if (!fpv) { tx = e->agent_x + DX[action]; ty = e->agent_y + DY[action]; }
+        else { /* legal_actions_ = {MOVE_FORWARD, MOVE_BACKWARD, MOVE_LEFT_FPV, MOVE_RIGHT_FPV, TURN_LEFT, TURN_RIGHT} (xitem.cpp:84-86) */
+            static const int FX[4] = {1, 0, -1, 0}, FY[4] = {0, 1, 0, -1}; /* right, down, left, up */
+            const int dir = xo_facing_dir(e->agent_yaw);
+            const int fx = FX[dir], fy = FY[dir];
+            tx = e->agent_x; ty = e->agent_y;
+            switch (action) {
+                case 0: tx += fx; ty += fy; break;   /* MOVE_FORWARD   xitem.cpp:100-109 */
+                case 1: tx -= fx; ty -= fy; break;   /* MOVE_BACKWARD  :110-119 */
+                case 2: tx += fy; ty -= fx; break;   /* MOVE_LEFT_FPV  :120-129: right -> (x, y-1), down -> (x+1, y), left -> (x, y+1), up -> (x-1, y) */
+                case 3: tx -= fy; ty += fx; break;   /* MOVE_RIGHT_FPV :130-139 */
+                case 4: /* TURN_LEFT :146-151 */
+                    e->agent_yaw -= M_PI / 2;
+                    if (e->agent_yaw < -M_PI / 2 - 1e-4) e->agent_yaw += 2 * M_PI;
+                    break;
+                default: /* TURN_RIGHT :140-145 */
+                    e->agent_yaw += M_PI / 2;
+                    if (e->agent_yaw > M_PI + 1e-4) e->agent_yaw -= 2 * M_PI;
+                    break;
+            }
+        }
+        if (fpv && action >= 4) {
+            /* the target is the agent's own cell: move_item finds the agent itself there, which is not reachable and
+             * is not a contact (same id) -> returns false (xmap.cpp:76-101): a turn is a "failed" action */
+            e->action_success = 0;
+        } else if (!in_bounds(e, tx, ty)) {
             e->action_success = 0;
         } else if (e->grid[cell_of(e, tx, ty)] != XW_CELL_EMPTY) {
             e->action_success = 0;
@@ -790,9 +832,11 @@ int xo_step(const xw_config* cfg, const xw_catalog* cat, xo_env* e, int32_t acti
     /* AgentSpecificSimulator::game_over (simulator.cpp:158-161) */
     int code = 0;
     if (cfg->max_steps > 0 && e->num_steps >= cfg->max_steps) code |= XW_MAX_STEP;
-    if (e->event == XW_EVENT_CORRECT_GOAL) code |= XW_SUCCESS;    /* xworld_simulator.cpp:170-177 */
-    else if (e->event == XW_EVENT_WRONG_GOAL) code |= XW_DEAD;
-    else if (e->event == XW_EVENT_TIME_UP) code |= XW_MAX_STEP;
+    if (cfg->task_mode == XW_TASK_LANG_ACQUISITION) {             /* one_channel: "all tasks until the max steps" :192-193 */
+        if (e->event == XW_EVENT_CORRECT_GOAL) code |= XW_SUCCESS;    /* xworld_simulator.cpp:170-177 */
+        else if (e->event == XW_EVENT_WRONG_GOAL) code |= XW_DEAD;
+        else if (e->event == XW_EVENT_TIME_UP) code |= XW_MAX_STEP;
+    }
     *game_over = code;
     return 0;
 }
@@ -818,7 +862,12 @@ void xo_resize_tables(int src, int dst, int32_t* ofs, int16_t* a0, int16_t* a1) 
     }
 }
 
-/* src HWC 3 channels -> dst HWC.  HResizeLinear + VResizeLinear<uchar,int,short,FixedPtCast<..,22>> */
+/* src HWC 3 channels -> dst HWC.  HResizeLinear + VResizeLinear<uchar,int,short,FixedPtCast<..,22>>.
+ * Columns: index and weight clamped as in xo_resize_tables (resize.cpp: `if (sx < 0) fx = 0, sx = 0`, same at the right
+ * edge).  Rows are different: the weights keep the raw fraction and only the two row INDICES are clipped to the
+ * image (resizeGeneric_Invoker: `sy = clip(sy0 - ksize2 + 1 + k, 0, ssize.height)`), so above the first / below the
+ * last source row both taps read the same row with weights (1 - fy, fy) -- which the truncating V pass does not
+ * collapse to a copy.  Only upscaling reaches those rows (the first-person view's resize to the map size). */
 void xo_resize_linear_8uc3(const uint8_t* src, int sh, int sw, uint8_t* dst, int dh, int dw) {
     if (sh == dh && sw == dw) { memcpy(dst, src, (size_t)sh * sw * 3); return; } /* resize(): src.copyTo(dst) */
     int32_t* xofs = (int32_t*)malloc(sizeof(int32_t) * (size_t)(dw + dh));
@@ -826,24 +875,30 @@ void xo_resize_linear_8uc3(const uint8_t* src, int sh, int sw, uint8_t* dst, int
     int16_t* xa0 = (int16_t*)malloc(sizeof(int16_t) * 2 * (size_t)(dw + dh));
     int16_t *xa1 = xa0 + dw, *ya0 = xa1 + dw, *ya1 = ya0 + dh;
     xo_resize_tables(sw, dw, xofs, xa0, xa1);
-    xo_resize_tables(sh, dh, yofs, ya0, ya1);
+    {
+        double scale = 1. / ((double)dh / (double)sh);
+        for (int d = 0; d < dh; ++d) {
+            float f = (float)((d + 0.5) * scale - 0.5);
+            int sy = (int)floorf(f);
+            f -= (float)sy;
+            yofs[d] = sy;
+            ya0[d] = (int16_t)lrintf((1.f - f) * 2048.f);
+            ya1[d] = (int16_t)lrintf(f * 2048.f);
+        }
+    }
     int32_t* rows = (int32_t*)malloc(sizeof(int32_t) * 2 * (size_t)dw * 3);
     int32_t* row[2] = {rows, rows + (size_t)dw * 3};
-    int have[2] = {-1, -1};
     for (int dy = 0; dy < dh; ++dy) {
-        int sy[2] = {yofs[dy], yofs[dy] + 1 < sh ? yofs[dy] + 1 : sh - 1};
-        /* reuse the previous second row as this first row when possible (as OpenCV does) */
-        if (have[1] == sy[0]) { int32_t* t = row[0]; row[0] = row[1]; row[1] = t; have[0] = have[1]; have[1] = -1; }
         for (int k = 0; k < 2; ++k) {
-            if (have[k] == sy[k]) continue;
-            const uint8_t* S = src + (size_t)sy[k] * sw * 3;
+            int sy = yofs[dy] + k;
+            sy = sy < 0 ? 0 : (sy > sh - 1 ? sh - 1 : sy);
+            const uint8_t* S = src + (size_t)sy * sw * 3;
             int32_t* D = row[k];
             for (int dx = 0; dx < dw; ++dx) {
                 int sx = xofs[dx], sx1 = sx + 1 < sw ? sx + 1 : sw - 1;
                 for (int c = 0; c < 3; ++c)
                     D[dx * 3 + c] = S[sx * 3 + c] * xa0[dx] + S[sx1 * 3 + c] * xa1[dx];
             }
-            have[k] = sy[k];
         }
         int b0 = ya0[dy], b1 = ya1[dy];
         uint8_t* O = dst + (size_t)dy * dw * 3;
@@ -854,9 +909,12 @@ void xo_resize_linear_8uc3(const uint8_t* src, int sh, int sw, uint8_t* dst, int
 }
 
 void xo_frame_dims(const xw_config* cfg, int* oh, int* ow) {
-    /* XWorldSimulator::init (xworld_simulator.cpp:48-61): block_size 12 when fully observed */
-    *oh = cfg->out_h > 0 ? cfg->out_h : cfg->height * 12;
-    *ow = cfg->out_w > 0 ? cfg->out_w : cfg->width * 12;
+    /* XWorldSimulator::init (xworld_simulator.cpp:48-68): block_size 12 when fully observed, 84 / visible_radius
+     * otherwise (the frame is visible_radius blocks a side) */
+    int bh = cfg->height * 12, bw = cfg->width * 12;
+    if (cfg->visible_radius > 0) { int vr = xo_visible_radius(cfg); bh = bw = vr * (84 / vr); }
+    *oh = cfg->out_h > 0 ? cfg->out_h : bh;
+    *ow = cfg->out_w > 0 ? cfg->out_w : bw;
 }
 
 static int icon_of_cell(const xw_catalog* cat, const xo_env* e, int code) {
@@ -869,7 +927,24 @@ static int icon_of_cell(const xw_catalog* cat, const xo_env* e, int code) {
 /* XWorldSimulator::get_screen (xworld_simulator.cpp:278-285) for visible_radius == 0, color == true.
  * XItem::get_item_image's warpAffine is the identity for yaw 1.5707963/scale 1/offset 0
  * (byte-identical for all 363 icons) and is not re-evaluated here. */
+/* down_sample_image's tail (xworld_simulator.cpp:524-544): optional cv::cvtColor(BGR2GRAY), then HWC -> planar.
+ * BGR2GRAY on 8-bit data in the OpenCV 3.2.0 the reference pins (cmake/opencv.cmake:5-6; imgproc/src/color.cpp, RGB2Gray<uchar>:
+ * yuv_shift = 14, B2Y = 1868, G2Y = 9617, R2Y = 4899): (B*1868 + G*9617 + R*4899 + (1 << 13)) >> 14.  OpenCV 4.x changed the
+ * constants (3735, 19235, 9798, shift 15): tests/test_oracle_fpv.py checks this formula's structure against cv2 with those. */
+void xo_gray_or_planes(const xw_config* cfg, const uint8_t* img_out, int oh, int ow, uint8_t* out) {
+    if (cfg->gray) {
+        for (int i = 0; i < oh * ow; ++i)
+            out[i] = (uint8_t)((img_out[i * 3] * 1868 + img_out[i * 3 + 1] * 9617 + img_out[i * 3 + 2] * 4899 + (1 << 13)) >> 14);
+        return;
+    }
+    for (int h = 0; h < oh; ++h)
+        for (int w = 0; w < ow; ++w)
+            for (int c = 0; c < 3; ++c)
+                out[(size_t)c * ow * oh + (size_t)h * ow + w] = img_out[((size_t)h * ow + w) * 3 + c];
+}
+
 void xo_render(const xw_config* cfg, const xw_catalog* cat, const xo_env* e, uint8_t* out) {
+    if (cfg->visible_radius > 0) { xo_render_fpv(cfg, cat, e, out); return; }
     const int G = XW_ICON_SIZE;
     int ch = e->H * G, cw = e->W * G;
     int oh, ow;
@@ -906,10 +981,7 @@ void xo_render(const xw_config* cfg, const xw_catalog* cat, const xo_env* e, uin
             p[2] = planar[2 * (size_t)cw * ch + (size_t)h * cw + w];
         }
     xo_resize_linear_8uc3(img, ch, cw, img_out, oh, ow);
-    for (int h = 0; h < oh; ++h)
-        for (int w = 0; w < ow; ++w)
-            for (int c = 0; c < 3; ++c)
-                out[(size_t)c * ow * oh + (size_t)h * ow + w] = img_out[((size_t)h * ow + w) * 3 + c];
+    xo_gray_or_planes(cfg, img_out, oh, ow, out);
     free(world);
 }
 
@@ -936,7 +1008,7 @@ int xo_batch_step(const xw_config* cfg, const xw_catalog* cat, xo_env* envs, int
                   int act_rep, float* reward, int32_t* game_over, uint8_t* frames, int threads) {
     int oh, ow;
     xo_frame_dims(cfg, &oh, &ow);
-    size_t fb = (size_t)3 * oh * ow;
+    size_t fb = (size_t)(cfg->gray ? 1 : 3) * oh * ow;
     int err = 0;
     if (threads < 1) threads = 1;
 #pragma omp parallel for num_threads(threads) schedule(static)

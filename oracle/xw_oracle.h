@@ -26,8 +26,13 @@ enum {
     XO_SITE_TASK_A = 7,    /* task idle: first choice (sel_goal / tile)                    XWorld3DNav*.py idle */
     XO_SITE_TASK_B = 8,    /* task idle: second choice (referent / empty grid e)           */
     XO_SITE_TASK_SHUF = 9, /* task idle: random.shuffle(goals); g1, g2 = goals[:2]         */
-    XO_SITE_TASK_AGENT = 10/* task idle: agent.loc = choice(new_a)                         */
+    XO_SITE_TASK_AGENT = 10,/* task idle: agent.loc = choice(new_a)                         */
+    /* 11 = the sentence channel (xworld_b200/csrc/xw_sentence.hpp) */
+    XO_SITE_AGENT_YAW = 12,/* set_property, --visible_radius > 0: agent yaw = choice(range(-1,3)) * PI_2   xworld_env.py:208-210 */
+    XO_SITE_GOAL_POSE = 13 /* set_property, --visible_radius > 0: goal yaw / scale / offset = uniform(...)  xworld_env.py:211-223;
+                              index = 4 * goal# + {0 yaw, 1 scale, 2 offset} */
 };
+#define XO_YAW_STEPS 4096 /* goal yaws are drawn on a 4096-point grid of [0, 4 * PI_2): see xo_goal_pose */
 
 typedef struct {
     int32_t H, W;
@@ -50,6 +55,9 @@ typedef struct {
     int32_t level, dim, check_counter;
     int32_t seq_len[5];
     uint8_t seq[5][200];
+    /* --visible_radius > 0: Entity.yaw / scale / offset of each goal (xworld_env.py:211-223); agent_yaw above is the
+     * agent's.  Defaults (fully observed): yaw 1.5707963, scale 1, offset 0 (xworld_env.py:41-42). */
+    double goal_yaw[XW_MAX_GOALS], goal_scale[XW_MAX_GOALS], goal_offset[XW_MAX_GOALS];
 } xo_env;
 
 /* ---- RNG ---- */
@@ -72,6 +80,25 @@ int xo_step(const xw_config* cfg, const xw_catalog* cat, xo_env* e, int32_t acti
 /* teacher stage run once on an explicit state (used to pin rules against the reference python) */
 int xo_teach(const xw_config* cfg, const xw_catalog* cat, xo_env* e, int32_t collided_cell_code,
              double* reward);
+
+/* ---- first-person view (xw_oracle_fpv.c) ---- */
+/* cv::getRotationMatrix2D (OpenCV imgproc/imgwarp.cpp), center given as Point2f */
+void xo_rotation_matrix(float cx, float cy, double angle_deg, double scale, double M[6]);
+/* cv::warpAffine, INTER_LINEAR, BORDER_CONSTANT, 8UC3, forward matrix M (inverted inside, as OpenCV does) */
+void xo_warp_affine_8uc3(const uint8_t* src, int sh, int sw, uint8_t* dst, int dh, int dw, const double M[6],
+                         const uint8_t border[3]);
+/* XItem::get_item_image's transform of one 64x64 icon (xitem.cpp:47-60) */
+void xo_item_image(const uint8_t* icon64, double yaw, double scale, double offset, uint8_t* out64);
+/* XItem::get_item_facing_dir (xitem.cpp:65-78): 0 right, 1 down, 2 left, 3 up */
+int xo_facing_dir(double yaw);
+/* XMap::image_masking (xmap.cpp:273-362): ROI (in cells of the padded map) and the vr*vr shadow flags */
+void xo_image_masking(const xo_env* e, int vr, int* x_st, int* y_st, uint8_t* shadow);
+/* min(--visible_radius, max(h, w)) (xworld_simulator.cpp:63-64) */
+int xo_visible_radius(const xw_config* cfg);
+/* yaw / scale / offset of goal k as set_property draws them (xworld_env.py:211-223) */
+void xo_goal_pose(uint64_t seed, int64_t env_gid, uint32_t episode, uint32_t attempt, int k, double* yaw, double* scale,
+                  double* offset);
+void xo_render_fpv(const xw_config* cfg, const xw_catalog* cat, const xo_env* e, uint8_t* frame_out);
 
 /* ---- render ---- */
 void xo_resize_tables(int src, int dst, int32_t* ofs, int16_t* a0, int16_t* a1);

@@ -6,6 +6,11 @@ Runs only in the build container (needs /root/reference).  Output: tests/golden/
 `gen_reference_python.py curriculum` writes tests/golden/refpy_curriculum.json.gz instead: XWorldNav with
 --curriculum > 0 run unmodified at its own 8x8 / level tables, XWorldEnv.curriculum_check_period set
 to a few resets so that the levels move within a short trace, plus one env at the reference's own period of 100.
+`gen_reference_python.py fpv` writes tests/golden/refpy_fpv.json.gz: the same code with --visible_radius > 0:
+set_property's agent yaw / goal yaw, scale, offset draws (xworld_env.py:207-223), the six first-person actions, and the
+teacher's reach test with a heading that turns; and with --task_mode=one_channel (py_simulator.cpp:128-130, the reference's
+Python default): the navigation2d.json tasks past their terminal stage, the walls.json tasks' time-up rule
+(xworld_task.py:203-210; navigation group only -- the XWorldRec question tasks are outside the path).
 
 What is executed unmodified (loaded from /root/reference, never copied):
     games/xworld/maps/xworld_env.py, XWorldNav.py      map/entity schema + generator
@@ -16,8 +21,8 @@ What is executed unmodified (loaded from /root/reference, never copied):
     games/xworld/tasks/xworld_task.py + XWorldNav{Target,Near,ColorTarget,Between}.py   walls.json
 
 What the harness supplies instead of the C++ host (and cites):
-    * Python-2 -> 3 source fix-ups at load time: integer `/` on three lines (maze2d.py:89,
-      xworld_env.py:129-130), dict.iteritems(), dict.keys() used as a list (xworld_env.py:292).
+    * Python-2 -> 3 source fix-ups at load time: integer `/` on four lines (maze2d.py:89,
+      xworld_env.py:129-130, xworld_task.py:206), dict.iteritems(), dict.keys() used as a list (xworld_env.py:292).
     * py_gflags.get_flag (python/py_init.cpp:37-58) -> a dict of the flags.
     * the `random` module -> ReplayRandom: every call site the reference draws from is mapped onto the
       oracle's Philox substream of the same name (oracle/xw_oracle.h XO_SITE_*), with the sequence
@@ -61,6 +66,7 @@ class Ctx(object):
     goal_no = 0
     step_no = 0
     idle_calls = 0
+    pose_calls = {}
 
 
 def cell_key(p):  # canonical row-major (y, x)
@@ -118,6 +124,9 @@ class ReplayRandom(types.ModuleType):
                     assert ent.type == "agent"
                     u = self._u(oracle.SITE_AGENT_LOC, 0)
                 return seq[oracle.randbelow(u, len(seq))]
+            if isinstance(seq[0], int):  # yaw = choice(range(-1, 3)) * PI_2 (xworld_env.py:208-210)
+                assert ent.type == "agent" and seq == [-1, 0, 1, 2]
+                return seq[oracle.randbelow(self._u(oracle.SITE_AGENT_YAW, 0), 4)]
             seq.sort()
             if len(seq) == 1:
                 return seq[0]
@@ -148,7 +157,20 @@ class ReplayRandom(types.ModuleType):
         raise RuntimeError("unmapped choice call site: " + caller)
 
     def uniform(self, a, b):
-        raise RuntimeError("unmapped uniform()")
+        """random.uniform(a, b) = a + (b - a) * random() (CPython random.py).  Only set_property draws continuous values:
+        a goal's yaw, scale, offset, in that order (xworld_env.py:211-223) -> oracle site GOAL_POSE, index 4 * goal + k;
+        random() = draw * 2^-32, and (draw >> 20) / 4096 for the yaw (oracle/xw_oracle_fpv.c xo_goal_pose)."""
+        f1 = sys._getframe(1)
+        assert f1.f_code.co_name == "check_or_get_value"
+        ent = f1.f_back.f_locals["entity"]
+        assert ent.type == "goal"
+        g = int(ent.id.split("_")[-1])
+        k = Ctx.pose_calls.get(g, 0)
+        Ctx.pose_calls[g] = k + 1
+        assert k < 3
+        u = self._u(oracle.SITE_GOAL_POSE, 4 * g + k)
+        r = (u >> 20) / 4096.0 if k == 0 else u * (1.0 / 4294967296.0)
+        return a + (b - a) * r
 
     def randint(self, a, b):
         raise RuntimeError("unmapped randint()")
@@ -199,7 +221,7 @@ def load_reference_python(dim, n_goals, n_blocks):
         for t in ("XWorld3DNavTarget", "XWorld3DNavTargetNear", "XWorld3DNavTargetBetween",
                   "XWorld3DNavTargetDirection", "XWorld3DNavTargetAvoid"):
             mk(t, "games/xworld3d/tasks/%s.py" % t)
-        mk("xworld_task", "games/xworld/tasks/xworld_task.py", [(r"iteritems", "items")])
+        mk("xworld_task", "games/xworld/tasks/xworld_task.py", [(r"iteritems", "items"), (r"h\*w / 2", "h*w // 2")])
         for t in ("XWorldNavTarget", "XWorldNavNear", "XWorldNavColorTarget", "XWorldNavBetween"):
             mk(t, "games/xworld/tasks/%s.py" % t)
     finally:
@@ -244,10 +266,30 @@ class Host(object):
     def agent(self):
         return [e for e in self.entities if e["type"] == "agent"][0]
 
+    @staticmethod
+    def facing(yaw):  # XItem::get_item_facing_dir (xitem.cpp:65-78): 0 right, 1 down, 2 left, 3 up
+        import math
+        return 0 if abs(yaw) < 1e-4 else 1 if abs(yaw - math.pi / 2) < 1e-4 else 2 if abs(yaw - math.pi) < 1e-4 else 3
+
     # XAgent::act + XMap::move_item
     def move(self, action):
+        import math
         a = self.agent()
-        dx, dy = [(0, -1), (0, 1), (-1, 0), (1, 0)][action]
+        if FLAGS["visible_radius"]:  # xitem.cpp:100-151; the compiled XAgent is checked against the oracle in tests/test_oracle_fpv.py
+            fx, fy = [(1, 0), (0, 1), (-1, 0), (0, -1)][self.facing(a["yaw"])]
+            if action >= 4:
+                if action == 4:
+                    a["yaw"] -= math.pi / 2
+                    if a["yaw"] < -math.pi / 2 - 1e-4:
+                        a["yaw"] += 2 * math.pi
+                else:
+                    a["yaw"] += math.pi / 2
+                    if a["yaw"] > math.pi + 1e-4:
+                        a["yaw"] -= 2 * math.pi
+                return False, []  # move_item onto the agent's own cell: not reachable, no contact (xmap.cpp:76-101)
+            dx, dy = [(fx, fy), (-fx, -fy), (fy, -fx), (-fy, fx)][action]
+        else:
+            dx, dy = [(0, -1), (0, 1), (-1, 0), (1, 0)][action]
         tx, ty = int(a["loc"][0]) + dx, int(a["loc"][1]) + dy
         contacts = []
         ok = False
@@ -297,6 +339,8 @@ class Host(object):
             "goal_x": [int(g["loc"][0]) for g in goals], "goal_y": [int(g["loc"][1]) for g in goals],
             "goal_name": [self.cat.names.index(g["name"]) for g in goals],
             "goal_icon": [self.path2icon[g["asset_path"]] for g in goals],
+            "agent_yaw": a["yaw"],
+            "goal_pose": [[g["yaw"], g["scale"], g["offset"]] for g in goals],
         }
 
     def approach_from_above(self, goal):
@@ -367,6 +411,7 @@ def run_case(mods, cat, rules, dim, n_goals, n_blocks, seed, simulator_seed, env
             ok = False
             for att in range(64):
                 Ctx.attempt, Ctx.maze_visits, Ctx.goal_no, Ctx.step_no = att, 0, 0, 0
+                Ctx.pose_calls = {}
                 if att > 0:  # a re-drawn map is the same reset: the curriculum check ran with attempt 0
                     host.env.get_current_usage = lambda: 0
                 host.env.reset()
@@ -386,6 +431,7 @@ def run_case(mods, cat, rules, dim, n_goals, n_blocks, seed, simulator_seed, env
             assert stage == "navigation_reward" and r0 == 0.0
         else:
             Ctx.attempt, Ctx.maze_visits, Ctx.goal_no, Ctx.step_no = 0, 0, 0, 0
+            Ctx.pose_calls = {}
             host.env.reset()
             host.pull_entities()
             stage, task, t = "idle", None, -1
@@ -422,7 +468,9 @@ def run_case(mods, cat, rules, dim, n_goals, n_blocks, seed, simulator_seed, env
             rec["reset_task"] = t
             rec["reset_sentence"] = host.last_sentence
         for s in range(n_steps):
-            a = int(arng.randint(0, 4))
+            a = int(arng.randint(0, 6 if FLAGS["visible_radius"] else 4))
+            if FLAGS["visible_radius"] and arng.rand() < 0.35:
+                a = 0  # MOVE_FORWARD is the only move that can score: lets episodes end by reaching goals
             if curriculum and arng.rand() < 0.4:
                 a = 1  # MOVE_DOWN is the only move that can score (the heading is +y): lets the success rates rise
             if curriculum and rules == 0 and T3[t] == "XWorld3DNavTargetDirection" and arng.rand() < 0.7:
@@ -450,11 +498,11 @@ def run_case(mods, cat, rules, dim, n_goals, n_blocks, seed, simulator_seed, env
                 steps.append({"a": a, "ok": int(ok), "r": r, "ev": ev, "agent": [int(ag["loc"][0]), int(ag["loc"][1])]})
             else:
                 steps.append({"a": a, "ok": int(ok), "r": r, "ev": ev, "stage": stage, "task": t, "sent": host.last_sentence,
-                              "agent": [int(ag["loc"][0]), int(ag["loc"][1])]})
+                              "agent": [int(ag["loc"][0]), int(ag["loc"][1])], "yaw": ag["yaw"]})
             if curriculum and stage == "terminal":
                 break  # the trainer resets a finished game (test_xworld.py:46-49)
             if rules == 0 and stage == "terminal" and s + 3 < n_steps and len(steps) > 2 and steps[-2]["stage"] == "terminal" \
-                    and steps[-3]["stage"] == "terminal":
+                    and steps[-3]["stage"] == "terminal" and (FLAGS["task_mode"] != "one_channel" or len(steps) > 12):
                 break  # a few terminal-stage steps are enough
         rec["steps"] = steps
         rec["minstd"] = minstd.value
@@ -500,6 +548,43 @@ def main_curriculum():
     print("wrote", path, os.path.getsize(path))
 
 
+def main_fpv():
+    """--visible_radius > 0 and --task_mode=one_channel traces -> refpy_fpv.json.gz."""
+    import gzip
+    cat = Catalog.from_item_path(ITEM_PATH)
+    cases = [  # (tag, rules, dim, goals, blocks, visible_radius, task_mode, n_envs, episodes, steps)
+        ("fpv_nav3d_8x8_vr3", 0, 8, 4, 16, 3, "lang_acquisition", 8, 6, 90),
+        ("fpv_nav3d_7x7_vr7", 0, 7, 4, 12, 7, "lang_acquisition", 8, 6, 90),
+        ("fpv_nav3d_8x8_vr5_one_channel", 0, 8, 4, 16, 5, "one_channel", 4, 4, 60),
+        ("fpv_nav2d_11x11_vr7", 1, 11, 4, 30, 7, "lang_acquisition", 6, 3, 70),
+        ("nav3d_8x8_one_channel", 0, 8, 4, 16, 0, "one_channel", 6, 4, 60),
+        ("nav2d_11x11_one_channel_nav_group", 1, 11, 4, 30, 0, "one_channel", 4, 2, 150),
+        ("nav2d_8x8_one_channel_nav_group", 1, 8, 4, 16, 0, "one_channel", 4, 2, 100),
+    ]
+    out = {"generator": "tests/golden/gen_reference_python.py fpv", "cases": []}
+    for tag, rules, dim, G, B, vr, mode, n_envs, n_ep, n_st in cases:
+        FLAGS["visible_radius"], FLAGS["task_mode"] = vr, mode
+        mods = load_reference_python(dim, G, B)
+        envs = []
+        for gid in range(n_envs):
+            envs.append({"env_gid": gid,
+                         "episodes": run_case(mods, cat, rules, dim, G, B, seed=777, simulator_seed=5,
+                                              env_gid=gid, n_episodes=n_ep, n_steps=n_st, act_seed=3000 + gid)})
+        evs = {}
+        for e in envs:
+            for ep in e["episodes"]:
+                for st in ep["steps"]:
+                    evs[st["ev"]] = evs.get(st["ev"], 0) + 1
+        print(tag, "events:", evs)
+        out["cases"].append({"tag": tag, "rules": rules, "dim": dim, "n_goals": G, "n_blocks": B, "seed": 777,
+                             "simulator_seed": 5, "visible_radius": vr, "task_mode": mode, "envs": envs})
+    FLAGS["visible_radius"], FLAGS["task_mode"] = 0, "lang_acquisition"
+    path = os.path.join(HERE, "refpy_fpv.json.gz")
+    with gzip.GzipFile(path, "wb", mtime=0) as f:
+        f.write(json.dumps(out, separators=(",", ":")).encode())
+    print("wrote", path, os.path.getsize(path))
+
+
 def main():
     cat = Catalog.from_item_path(ITEM_PATH)
     meta_names = Catalog(Catalog.metadata(), __import__("numpy").zeros((363, 64, 64, 3), "uint8")).names
@@ -532,5 +617,7 @@ def main():
 if __name__ == "__main__":
     if sys.argv[1:] == ["curriculum"]:
         main_curriculum()
+    elif sys.argv[1:] == ["fpv"]:
+        main_fpv()
     else:
         main()

@@ -96,6 +96,9 @@ def test_against_reference_python_traces(oracle_lib, synthetic_catalog):
                     assert np.float32(r.value).view(np.uint32) == np.float32(s["r"]).view(np.uint32), (where, i)
                     assert [e.agent_x, e.agent_y] == s["agent"] and e.action_success == s["ok"], (where, i)
                     assert e.event == EVMAP[s["ev"]], (where, i)
+                    # XWorldSimulator::game_over, lang_acquisition (xworld_simulator.cpp:165-177); --max_steps is off here
+                    assert ov.value == {"": 0, "correct_goal": _abi.XW_SUCCESS, "wrong_goal": _abi.XW_DEAD,
+                                        "time_up": _abi.XW_MAX_STEP}[s["ev"]], (where, i)
                 assert e.minstd == ep["minstd"], where
     assert n_steps > 9000 and n_resets > 80
 

@@ -5,7 +5,7 @@ The product path has no CPU fallback: if libxworld_b200.so is missing, `load()` 
 import ctypes as C
 import os
 
-XW_ABI_VERSION = 1
+XW_ABI_VERSION = 2
 XW_MAX_GOALS = 8
 XW_ACTION_NONE = -1
 XW_WIRE_MAX_FIELDS = 8
@@ -14,6 +14,7 @@ XW_ICON_SIZE = 64
 
 XW_GAME_XWORLD, XW_GAME_SIMPLE_GAME, XW_GAME_SIMPLE_RACE = 0, 1, 2
 XW_RULES_NAV3D, XW_RULES_NAV2D = 0, 1
+XW_TASK_LANG_ACQUISITION, XW_TASK_ONE_CHANNEL = 0, 1
 XW_ALIVE, XW_MAX_STEP, XW_DEAD, XW_SUCCESS, XW_LOST_LIFE = 0, 1, 2, 4, 8
 XW_EVENT_NONE, XW_EVENT_CORRECT_GOAL, XW_EVENT_WRONG_GOAL, XW_EVENT_TIME_UP = 0, 1, 2, 3
 XW_STAGE_IDLE, XW_STAGE_NAVIGATION, XW_STAGE_TERMINAL = 0, 1, 2
@@ -64,7 +65,9 @@ class XwConfig(C.Structure):
         ("curriculum", C.c_float),
         ("curriculum_check_period", C.c_int32),
         ("start_level", C.c_int32),
-        ("reserved", C.c_int32 * 5),
+        ("task_mode", C.c_int32),
+        ("gray", C.c_int32),
+        ("reserved", C.c_int32 * 3),
     ]
 
 
