@@ -46,6 +46,12 @@ WORKLOADS = {
                         simulator_seed=1),
                name="XWorld2D navigation2d.json rules, 15x15 map, 128x128x3 u8 obs, 32768 envs/GPU (BASELINE configs[3])",
                map="15x15", side=128, rules="navigation2d.json", max_steps=0, envs=32768),
+    # BASELINE configs[2]'s map in the only 84x84 view the reference itself produces for it: the first-person
+    # view with --visible_radius 7 (xworld_simulator.cpp:62-68), six actions
+    "fpv": dict(cfg=dict(height=11, width=11, n_goals=4, n_blocks=30, rules=1, visible_radius=7, max_steps=242, auto_reset=1,
+                         seed=1234, simulator_seed=1),
+                name="XWorld2D walls.json rules, 11x11 maze, first-person view visible_radius=7 -> 84x84x3 u8 obs, 65536 envs/GPU",
+                map="11x11", side=84, rules="walls.json", max_steps=242, envs=65536),
 }
 WORKLOAD = WORKLOADS["c3"]["cfg"]
 WORKLOAD_NAME = WORKLOADS["c3"]["name"]
@@ -148,7 +154,7 @@ def cpu_reference_arm(steps, warmup, sample_envs, threads):
     orc = oracle.Oracle(cfg, cat, sample_envs, threads=threads)
     orc.reset()
     rng = np.random.RandomState(0)
-    acts = [rng.randint(0, 4, sample_envs).astype(np.int32) for _ in range(8)]
+    acts = [rng.randint(0, 6 if cfg.visible_radius > 0 else 4, sample_envs).astype(np.int32) for _ in range(8)]
     for s in range(warmup):
         orc.step(acts[s % 8], render=True)
     t0 = time.perf_counter()
@@ -322,7 +328,7 @@ def main():
     if args.envs_per_gpu <= 0:
         args.envs_per_gpu = wl["envs"]
     config = {"workload": WORKLOAD_NAME, "map": wl["map"], "obs": "%dx%dx3 u8 (B,G,R planes)" % (SIDE, SIDE), "rules": wl["rules"],
-              "envs_per_gpu": args.envs_per_gpu, "auto_reset": True, "max_steps": wl["max_steps"], "actions": "iid uniform{0..3}",
+              "envs_per_gpu": args.envs_per_gpu, "auto_reset": True, "max_steps": wl["max_steps"], "actions": "iid uniform{0..%d}" % (5 if wl["cfg"].get("visible_radius") else 3),
               "l2": "each step writes %.2f GB of frames per GPU (>> 126 MB L2), so no L2 flush is needed" % (
                   args.envs_per_gpu * 3 * SIDE * SIDE / 1e9),
               "bytes_per_env_step": BYTES_PER_ENV_STEP}
@@ -365,7 +371,8 @@ def main():
     lib, h = sim._lib, sim._h
     gen = torch.Generator(device=dev)
     gen.manual_seed(99 + rank)
-    acts = [torch.randint(0, 4, (n,), dtype=torch.int32, device=dev, generator=gen) for _ in range(8)]
+    n_act = sim.get_num_actions()
+    acts = [torch.randint(0, n_act, (n,), dtype=torch.int32, device=dev, generator=gen) for _ in range(8)]
     frames = sim.screen()
     reward = torch.zeros(n, dtype=torch.float32, device=dev)
     over = torch.zeros(n, dtype=torch.int32, device=dev)
@@ -415,7 +422,7 @@ def main():
     # ---- end to end through the host-buffer C ABI (pinned host actions in, host reward/over out)
     e2e = None
     if not args.no_e2e:
-        h_act = [torch.randint(0, 4, (n,), dtype=torch.int32).pin_memory() for _ in range(4)]
+        h_act = [torch.randint(0, n_act, (n,), dtype=torch.int32).pin_memory() for _ in range(4)]
         h_rew = torch.zeros(n, dtype=torch.float32).pin_memory()
         h_over = torch.zeros(n, dtype=torch.int32).pin_memory()
         k2 = max(10, args.steps)  # the same K steps as the device-resident measurement
@@ -487,7 +494,8 @@ def main():
         "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
-        "roofline": {"bound": "hbm", "kernel": {3: "k_render_sp", 1: "k_render_sb", 2: "k_render", 0: "k_render_generic"}.get(
+        "roofline": {"bound": "hbm", "kernel": {3: "k_render_sp", 1: "k_render_sb", 2: "k_render", 0: "k_render_generic",
+                                                 4: "k_render_fpv_generic", 5: "k_render_fpv"}.get(
                          sim.render_kernel(), "k_render"), "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                      "kernel_ms": render_ms, "kernel_share_of_step": (render_ms / (ms / args.steps)) if render_ms else None,

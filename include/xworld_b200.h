@@ -176,7 +176,10 @@ int xw_reset(xw_sim* sim, const uint8_t* d_mask, void* stream);
  *   d_reward    f32[n_envs]   return value of take_actions
  *   d_game_over i32[n_envs]   SimulatorInterface::game_over() right after the step
  *   d_frames    u8[n_envs][context*C][out_h][out_w] or NULL (get_state()["screen"] bytes)
- * An invalid action marks the env in the error flags (xw_error_flags) and leaves it untouched. */
+ * An action outside [0, xw_num_actions) leaves the env untouched (reward 0, game_over 0) and sets its error flag
+ * (xw_error_flags); the reference CHECK-aborts the process (xworld_simulator.cpp:254).  This call is asynchronous and
+ * cannot report it; the calls that hand results to the host (xw_step_host, xw_step_hd, xw_step_hd_async) return
+ * XW_ERR_INVALID_ACTION when an env of that step was flagged -- the other envs were stepped normally. */
 int xw_step(xw_sim* sim, const int32_t* d_actions, int32_t act_rep, float* d_reward,
             int32_t* d_game_over, uint8_t* d_frames, void* stream);
 
@@ -217,11 +220,17 @@ int xw_num_steps(xw_sim* sim, int64_t* h_num_steps /* [n_envs] host */);
  * "target_mask","aux0","aux1","aux2" u8[n]; "goal_x","goal_y" u8[n][XW_MAX_GOALS];
  * "goal_icon" i32[n][XW_MAX_GOALS]; "steps_in_task","num_steps","episode","n_success",
  * "n_failure","success_steps","minstd","error" i32[n].
+ * First-person view (cfg.visible_radius > 0): "goal_yaw" u16[n][XW_MAX_GOALS] (yaw = 4 * 1.5707963 * idx / 4096),
+ * "goal_scale","goal_offset" f64[n][XW_MAX_GOALS] (Entity.yaw / scale / offset, xworld_env.py:211-223); setting any "goal_*"
+ * field re-warps the cached goal icons.  "facing" is the agent's heading: 0 right, 1 down, 2 left, 3 up.
  * Curriculum (only when cfg.curriculum > 0): "level" u8[n] (XWorldEnv.dump_curriculum_progress, xworld_env.py:62-63),
  * "check_counter" i32[n], "win_len","win_sum" u8[n][5] (length / successes of each task class's result window),
  * "win_pos" u8[n][5] and "win_bits" u32[n][5][7] (the windows themselves: with these a checkpoint restores everything).
  * Race: "pos_x","pos_y","angle" f32[n], "steps" i32[n], "state" f32[n][4]. */
 int xw_get_field(xw_sim* sim, const char* name, void* h_out, size_t bytes);
+/* Per-env error flags: 0, or XW_ERR_INVALID_ACTION since the env's last reset.  Copies them to h_flags[n_envs] (may be
+ * NULL) and returns how many envs are flagged (< 0: a CUDA error).  Synchronises the device. */
+int32_t xw_error_flags(xw_sim* sim, int32_t* h_flags);
 int xw_set_field(xw_sim* sim, const char* name, const void* h_in, size_t bytes);
 
 /* ---- teacher language channel, host side ------------------------------------------------------
@@ -294,7 +303,8 @@ int64_t xw_wire_reply_text(const char* cmd, const char* text, uint8_t* out, size
 int64_t xw_launch_count(const xw_sim* sim);
 /* Which render kernel the handle uses (diagnostics, tests): 0 = generic per-byte kernel, 1 = plan compositor with
  * one frame buffer per warp group, 2 = pipelined plan compositor, 3 = sparse painter (the default when the frame
- * geometry allows; XW_RENDER_MODE=sb|pipe selects the others); -1 = the game has no renderer.  No reference
+ * geometry allows; XW_RENDER_MODE=sb|pipe selects the others); first-person view: 4 = per-pixel kernel (any frame size),
+ * 5 = shared-memory frame kernel (frame width % 4 == 0 and frame bytes % 16 == 0); -1 = the game has no renderer.  No reference
  * counterpart: the reference has one OpenCV code path (xworld_simulator.cpp:278-307). */
 int32_t xw_render_kernel(const xw_sim* sim);
 /* CUDA-event timing of the render kernel alone: average ms over the launches since the last

@@ -15,6 +15,8 @@
 #include "../../xworld_b200/csrc/xw_render_host.hpp"
 #include "../../xworld_b200/csrc/xw_reset.cuh"
 #include "../../xworld_b200/csrc/xw_step.cuh"
+#include "../../xworld_b200/csrc/xw_fpv.cuh"
+#include "../../xworld_b200/csrc/xw_fpv_host.hpp"
 
 struct HostSim {
     xw_config cfg;
@@ -28,6 +30,13 @@ struct HostSim {
     std::vector<uint8_t> colL, colR, rowT, rowB, cwb;
     std::vector<uint32_t> ctab, cornerP, TC, rowT2, rowB2;
     XwRaceCfg race;
+    // first-person view
+    XwFpv fpv;
+    std::vector<int16_t> ft[12];
+    std::vector<uint8_t> agent4, gcache, pmap, Tb, Ta;
+    std::vector<int16_t> itab;
+    std::vector<double> yaw_cs;
+    int32_t n_invalid = 0;
 };
 
 template <typename T>
@@ -71,6 +80,14 @@ HostSim* hs_create(const xw_config* c, const xw_catalog* cat, int n) {
     d.n = n; d.H = c->height; d.W = c->width; d.CS = (c->height * c->width + 15) & ~15;
     d.G = c->n_goals; d.n_blocks = c->n_blocks; d.rules = c->rules; d.max_steps = c->max_steps;
     d.max_steps_factor = c->max_steps_factor; d.auto_reset = c->auto_reset; d.seed = c->seed; d.gid0 = c->env_id_offset;
+    d.vr = c->visible_radius < c->height ? c->visible_radius : c->height; d.task_mode = c->task_mode;
+    d.n_invalid = &s->n_invalid;
+    if (d.vr > 0) {
+        d.goal_yaw = halloc<uint16_t>(s, (size_t)n * XW_MAX_GOALS);
+        d.goal_scale = halloc<double>(s, (size_t)n * XW_MAX_GOALS); d.goal_offset = halloc<double>(s, (size_t)n * XW_MAX_GOALS);
+        s->yaw_cs = xw_fpv_yaw_table();
+        d.yaw_cs = s->yaw_cs.data();
+    }
     d.grid = halloc<uint8_t>(s, (size_t)n * d.CS);
     uint8_t** u8s[] = {&d.agent_x, &d.agent_y, &d.facing, &d.task, &d.stage, &d.event, &d.succ, &d.tmask, &d.aux0, &d.aux1, &d.aux2};
     for (auto p : u8s) *p = halloc<uint8_t>(s, n);
@@ -91,6 +108,36 @@ HostSim* hs_create(const xw_config* c, const xw_catalog* cat, int n) {
     d.n_names = cat->n_names; d.brick_icon = cat->brick_icon; d.agent_icon = cat->agent_icon;
     d.name_first = cat->name_first; d.name_icons = cat->name_icons; d.icon_colored = cat->icon_colored;
     int OH = c->out_h > 0 ? c->out_h : c->height * 12, OW = c->out_w > 0 ? c->out_w : c->width * 12;
+    if (d.vr > 0) {  // create_fpv (xw_engine.cu)
+        if (c->out_h <= 0) OH = d.vr * (84 / d.vr);
+        if (c->out_w <= 0) OW = d.vr * (84 / d.vr);
+        XwFpv& F = s->fpv;
+        memset(&F, 0, sizeof F);
+        F.vr = d.vr; F.N = d.vr * 64; F.CH = c->height * 64; F.OH = OH; F.OW = OW; F.FB = 3 * OH * OW;
+        F.ident1 = F.N == F.CH; F.ident2 = F.CH == OH && F.CH == OW;
+        F.G = c->n_goals; F.brick_icon = cat->brick_icon; F.agent_icon = cat->agent_icon;
+        xw_fpv_resize_tables(F.N, F.CH, false, s->ft[0], s->ft[1], s->ft[2]);
+        xw_fpv_resize_tables(F.N, F.CH, true, s->ft[3], s->ft[4], s->ft[5]);
+        xw_fpv_resize_tables(F.CH, OW, false, s->ft[6], s->ft[7], s->ft[8]);
+        xw_fpv_resize_tables(F.CH, OH, true, s->ft[9], s->ft[10], s->ft[11]);
+        F.x1ofs = s->ft[0].data(); F.x1a0 = s->ft[1].data(); F.x1a1 = s->ft[2].data();
+        F.y1ofs = s->ft[3].data(); F.y1a0 = s->ft[4].data(); F.y1a1 = s->ft[5].data();
+        F.x2ofs = s->ft[6].data(); F.x2a0 = s->ft[7].data(); F.x2a1 = s->ft[8].data();
+        F.y2ofs = s->ft[9].data(); F.y2a0 = s->ft[10].data(); F.y2a1 = s->ft[11].data();
+        F.atlas64 = cat->atlas64;
+        s->agent4 = xw_fpv_agent_icons(cat->atlas64 + (size_t)cat->agent_icon * 12288);
+        F.agent4 = s->agent4.data();
+        s->itab.resize(32 * 32 * 4);
+        xw_fpv_build_itab(s->itab.data());
+        F.itab = s->itab.data();
+        s->gcache.assign((size_t)n * F.G * 12288, 0);
+        F.gcache = s->gcache.data();
+        s->pmap.assign((size_t)4 * OH * OW, 0); s->Tb.assign((size_t)12 * OH * OW, 0); s->Ta.assign((size_t)12 * OH * OW, 0);
+        for (size_t i = 0; i < (size_t)4 * OH * OW; ++i) xw_fpv_table_entry(F, i, s->pmap.data(), s->Tb.data(), s->Ta.data());
+        F.pmap = s->pmap.data(); F.Tb = s->Tb.data(); F.Ta = s->Ta.data();
+        s->r.OH = OH; s->r.OW = OW; s->r.FB = F.FB;
+        return s;
+    }
     s->tab = xw_build_render_tables(c->height, c->width, OH, OW);
     XwRenderTables& t = s->tab;
     XwRender& r = s->r;
@@ -202,9 +249,29 @@ int hs_fast_ok(HostSim* s) { return s->tab.fast_ok; }
 int hs_threads(HostSim* s) { return XW_RENDER_THREADS; }
 void hs_destroy(HostSim* s) { delete s; }
 
+// k_fpv_warp_goals for one env
+static void hs_warp_goals(HostSim* s, int e) {
+    XwDev& d = s->d;
+    XwFpv& F = s->fpv;
+    if (d.vr == 0) return;
+    for (int g = 0; g < F.G; ++g) {
+        const size_t k = (size_t)g * d.n + e;
+        int co[4][64];
+        for (int i = 0; i < 64; ++i)
+            xw_fpv_warp_coeffs(d.yaw_cs, d.goal_yaw[k], d.goal_scale[k], d.goal_offset[k], i, &co[0][i], &co[1][i], &co[2][i], &co[3][i]);
+        const uint8_t* icon = F.atlas64 + (size_t)d.goal_icon[k] * 12288;
+        uint8_t* dst = F.gcache + ((size_t)e * F.G + g) * 12288;
+        for (int p = 0; p < 4096; ++p) {
+            const uint32_t v = xw_fpv_warp_px(icon, F.itab, (co[2][p >> 6] + co[0][p & 63]) >> 5, (co[3][p >> 6] + co[1][p & 63]) >> 5);
+            dst[p * 3] = (uint8_t)v; dst[p * 3 + 1] = (uint8_t)(v >> 8); dst[p * 3 + 2] = (uint8_t)(v >> 16);
+        }
+    }
+}
+static void hs_reset_one(HostSim* s, int e) { xw_reset_env(s->d, e); hs_warp_goals(s, e); }
+
 void hs_reset(HostSim* s, const uint8_t* mask) {
     if (s->cfg.game == XW_GAME_SIMPLE_RACE) { for (int e = 0; e < s->race.n; ++e) if (!mask || mask[e]) xw_race_reset_env(s->race, e); return; }
-    for (int e = 0; e < s->d.n; ++e) if (!mask || mask[e]) xw_reset_env(s->d, e);
+    for (int e = 0; e < s->d.n; ++e) if (!mask || mask[e]) hs_reset_one(s, e);
 }
 
 void hs_step(HostSim* s, const int32_t* actions, int act_rep, float* reward, int32_t* over) {
@@ -213,7 +280,7 @@ void hs_step(HostSim* s, const int32_t* actions, int act_rep, float* reward, int
         return;
     }
     for (int e = 0; e < s->d.n; ++e)
-        if (actions[e] != XW_ACTION_NONE && xw_step_env(s->d, e, actions[e], act_rep, &reward[e], &over[e])) xw_reset_env(s->d, e);
+        if (actions[e] != XW_ACTION_NONE && xw_step_env(s->d, e, actions[e], act_rep, &reward[e], &over[e])) hs_reset_one(s, e);
 }
 
 // Emulates one k_render warp group per env: celldesc, every item of the plan, copy out.  Configs the
@@ -222,8 +289,36 @@ void hs_step(HostSim* s, const int32_t* actions, int act_rep, float* reward, int
 // mode 2: the per-pixel rule on the 64-px atlas (k_render_generic's arithmetic) -- the ground truth
 int hs_sp_ok(HostSim* s) { return s->tab.sp_ok; }
 void hs_render_mode(HostSim* s, uint8_t* frames, int mode);
-void hs_render(HostSim* s, uint8_t* frames) { hs_render_mode(s, frames, s->tab.sp_ok ? 1 : 0); }
+void hs_render(HostSim* s, uint8_t* frames) { hs_render_mode(s, frames, s->d.vr > 0 || s->tab.sp_ok ? 1 : 0); }
+// k_render_fpv (mode != 2: the table pass + the exact pass) / k_render_fpv_generic (mode 2: every pixel tap by tap)
+static void hs_render_fpv(HostSim* s, uint8_t* frames, int mode) {
+    XwDev& d = s->d;
+    XwFpv& F = s->fpv;
+    const int plane = F.OH * F.OW;
+    uint8_t ccode[XW_MAX_DIM * XW_MAX_DIM];
+    for (int e = 0; e < d.n; ++e) {
+        for (int k = 0; k < F.vr; ++k) xw_fpv_cells_line(d, e, k, ccode);
+        XwFpvEnvFetch fe;
+        fe.F = &F; fe.ccode = ccode; fe.gc = F.gcache + (size_t)e * F.G * 12288; fe.facing = d.facing[e];
+        uint8_t* out = frames + (size_t)e * F.FB;
+        const int f = d.facing[e];
+        for (int p = 0; p < plane; ++p) {
+            const int id = F.pmap[(size_t)f * plane + p];
+            const int code = id == 255 ? -1 : ccode[id];
+            uint32_t v;
+            if (mode != 2 && code == XW_CELL_EMPTY) v = 0xffffffu;
+            else if (mode != 2 && code == XW_FPV_BLACK) v = 0;
+            else if (mode != 2 && (code == XW_CELL_BLOCK || code == XW_CELL_AGENT)) {
+                const uint8_t* t = (code == XW_CELL_BLOCK ? F.Tb : F.Ta) + (size_t)f * 3 * plane + p;
+                v = (uint32_t)t[0] | ((uint32_t)t[plane] << 8) | ((uint32_t)t[2 * (size_t)plane] << 16);
+            } else v = xw_fpv_px(F, p / F.OW, p % F.OW, fe);
+            out[p] = (uint8_t)v; out[plane + p] = (uint8_t)(v >> 8); out[2 * plane + p] = (uint8_t)(v >> 16);
+        }
+    }
+}
+
 void hs_render_mode(HostSim* s, uint8_t* frames, int mode) {
+    if (s->d.vr > 0) { hs_render_fpv(s, frames, mode); return; }
     XwRender& r = s->r;
     XwDev& d = s->d;
     std::vector<uint32_t> fb(r.FB / 4 + 4), yb(r.OH);
@@ -361,6 +456,20 @@ void hs_set_grid_env(HostSim* s, int e, const uint8_t* grid, const int32_t* goal
     for (int k = 0; k < s->d.G; ++k) s->d.goal_icon[(size_t)k * s->d.n + e] = goal_icons[k];
 }
 
+// test-only: overwrite one env's whole first-person scene (golden-frame tests)
+void hs_set_fpv_env(HostSim* s, int e, const uint8_t* grid, const int32_t* goal_icons, const uint16_t* yaw_idx, const double* scale,
+                    const double* offset, int facing) {
+    XwDev& d = s->d;
+    memcpy(d.grid + (size_t)e * d.CS, grid, (size_t)d.H * d.W);
+    for (int c = 0; c < d.H * d.W; ++c) if (grid[c] == XW_CELL_AGENT) { d.agent_x[e] = (uint8_t)(c % d.W); d.agent_y[e] = (uint8_t)(c / d.W); }
+    for (int k = 0; k < d.G; ++k) {
+        const size_t i = (size_t)k * d.n + e;
+        d.goal_icon[i] = goal_icons[k]; d.goal_yaw[i] = yaw_idx[k]; d.goal_scale[i] = scale[k]; d.goal_offset[i] = offset[k];
+    }
+    d.facing[e] = (uint8_t)facing;
+    hs_warp_goals(s, e);
+}
+
 int hs_get_field(HostSim* s, const char* name, void* out) {
     XwDev& d = s->d;
     std::string k(name);
@@ -389,6 +498,15 @@ int hs_get_field(HostSim* s, const char* name, void* out) {
     if (k == "goal_x" || k == "goal_y") {
         uint8_t* src = k == "goal_x" ? d.goal_x : d.goal_y;
         for (size_t g = 0; g < XW_MAX_GOALS; ++g) for (size_t e = 0; e < n; ++e) ((uint8_t*)out)[e * XW_MAX_GOALS + g] = src[g * n + e];
+        return 0;
+    }
+    if (d.vr > 0 && k == "goal_yaw") {
+        for (size_t g = 0; g < XW_MAX_GOALS; ++g) for (size_t e = 0; e < n; ++e) ((uint16_t*)out)[e * XW_MAX_GOALS + g] = d.goal_yaw[g * n + e];
+        return 0;
+    }
+    if (d.vr > 0 && (k == "goal_scale" || k == "goal_offset")) {
+        double* src = k == "goal_scale" ? d.goal_scale : d.goal_offset;
+        for (size_t g = 0; g < XW_MAX_GOALS; ++g) for (size_t e = 0; e < n; ++e) ((double*)out)[e * XW_MAX_GOALS + g] = src[g * n + e];
         return 0;
     }
     if (k == "goal_icon" || k == "goal_name") {

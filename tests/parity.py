@@ -27,6 +27,18 @@ CONFIGS = {
     "curriculum_nav2d_8x8_96": dict(height=8, width=8, n_goals=4, n_blocks=16, rules=_abi.XW_RULES_NAV2D, curriculum=0.1,
                                     start_level=2, max_steps=40),
     "ref_nav2d_8x8_96": dict(height=8, width=8, n_goals=4, n_blocks=16, rules=_abi.XW_RULES_NAV2D, max_steps=64),
+    # the first-person view.  11x11 with visible_radius 7 is the reference-native 84x84 frame of BASELINE config 3's map
+    "fpv_nav2d_11x11_vr7_84": dict(height=11, width=11, n_goals=4, n_blocks=30, rules=_abi.XW_RULES_NAV2D, visible_radius=7, max_steps=242),
+    "fpv_nav3d_8x8_vr3_84": dict(height=8, width=8, n_goals=4, n_blocks=16, rules=_abi.XW_RULES_NAV3D, visible_radius=3),
+    "fpv_nav3d_7x7_vr7_84": dict(height=7, width=7, n_goals=4, n_blocks=12, rules=_abi.XW_RULES_NAV3D, visible_radius=7),
+    "fpv_nav3d_8x8_vr5_80": dict(height=8, width=8, n_goals=4, n_blocks=16, rules=_abi.XW_RULES_NAV3D, visible_radius=5),
+    "fpv_nav3d_15x15_vr9_81": dict(height=15, width=15, n_goals=4, n_blocks=56, rules=_abi.XW_RULES_NAV3D, visible_radius=9),
+    "fpv_nav3d_7x7_vr1_84": dict(height=7, width=7, n_goals=4, n_blocks=12, rules=_abi.XW_RULES_NAV3D, visible_radius=1),
+    # --task_mode=one_channel (the reference's Python default, py_simulator.cpp:128-130)
+    "one_channel_nav3d_8x8_96": dict(height=8, width=8, n_goals=4, n_blocks=16, rules=_abi.XW_RULES_NAV3D, max_steps=60,
+                                     task_mode=_abi.XW_TASK_ONE_CHANNEL),
+    "one_channel_nav2d_8x8_96": dict(height=8, width=8, n_goals=4, n_blocks=16, rules=_abi.XW_RULES_NAV2D, max_steps=90,
+                                     task_mode=_abi.XW_TASK_ONE_CHANNEL),
 }
 
 
@@ -36,6 +48,19 @@ def make_cfg(name, **over):
     kw.setdefault("simulator_seed", 1)
     kw.update(over)
     return _abi.default_config(**kw)
+
+
+def frame_dims(cfg):
+    """XWorldSimulator::init (xworld_simulator.cpp:48-68)."""
+    h, w = cfg.height * 12, cfg.width * 12
+    if cfg.visible_radius > 0:
+        vr = min(cfg.visible_radius, cfg.height)
+        h = w = vr * (84 // vr)
+    return cfg.out_h or h, cfg.out_w or w
+
+
+def n_actions_of(cfg):
+    return 6 if cfg.visible_radius > 0 else 4
 
 
 def actions_for(step, n, n_actions, seed=99):
@@ -55,7 +80,7 @@ class HostSim(object):
             deps = [src] + [os.path.join(HERE, "..", "xworld_b200", "csrc", f)
                             for f in os.listdir(os.path.join(HERE, "..", "xworld_b200", "csrc"))]
             if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
-                subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src])
+                subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, src])
             L = C.CDLL(so)
             L.hs_create.restype = C.c_void_p
             L.hs_create.argtypes = [C.POINTER(_abi.XwConfig), C.POINTER(_abi.XwCatalog), C.c_int]
@@ -69,6 +94,7 @@ class HostSim(object):
             L.hs_build_phase_atlas.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
             L.hs_fast_ok.argtypes = [C.c_void_p]
             L.hs_threads.argtypes = [C.c_void_p]
+            L.hs_set_fpv_env.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
             cls._lib = L
         return cls._lib
 
@@ -77,8 +103,7 @@ class HostSim(object):
         self.cfg, self.catalog, self.n = cfg, catalog, n
         self.cat_c = catalog.as_c() if catalog is not None else None
         self.h = self.L.hs_create(C.byref(cfg), C.byref(self.cat_c) if catalog is not None else None, n)
-        self.out_h = cfg.out_h or cfg.height * 12
-        self.out_w = cfg.out_w or cfg.width * 12
+        self.out_h, self.out_w = frame_dims(cfg)
         self._atlas_icons = set()
 
     def __del__(self):
@@ -102,6 +127,8 @@ class HostSim(object):
         compositor; 1: the sparse painter."""
         icons = set(self.field("goal_icon")[:, :self.cfg.n_goals].ravel().tolist())
         icons |= {self.catalog.brick_icon, self.catalog.agent_icon}
+        if self.cfg.visible_radius > 0:
+            icons = set()  # the first-person view has no phase atlas
         if not icons <= self._atlas_icons:
             self._atlas_icons |= icons
             arr = np.array(sorted(self._atlas_icons), np.int32)
@@ -121,6 +148,10 @@ class HostSim(object):
             out = np.zeros((n, _abi.XW_MAX_GOALS), np.uint8)
         elif name in ("goal_icon", "goal_name"):
             out = np.zeros((n, _abi.XW_MAX_GOALS), np.int32)
+        elif name == "goal_yaw":
+            out = np.zeros((n, _abi.XW_MAX_GOALS), np.uint16)
+        elif name in ("goal_scale", "goal_offset"):
+            out = np.zeros((n, _abi.XW_MAX_GOALS), np.float64)
         elif name in ("win_len", "win_sum"):
             out = np.zeros((n, 5), np.uint8)
         elif name in U8 or name == "level":
@@ -148,6 +179,11 @@ def compare_state(backend, orc, tag=""):
     for f in ["goal_x", "goal_y", "goal_icon"]:
         a, b = backend.field(f)[:, :G], orc.field(f)[:, :G]
         assert (a == b).all(), "%s field %s differs" % (tag, f)
+    if orc.cfg.visible_radius > 0:  # the goals' poses: the yaw's grid index, scale and offset as bit-equal doubles
+        assert (backend.field("goal_yaw")[:, :G] == orc.field("goal_yaw_idx")[:, :G]).all(), "%s goal_yaw differs" % tag
+        for f in ["goal_scale", "goal_offset"]:
+            a, b = backend.field(f)[:, :G], orc.field(f)[:, :G]
+            assert (a.view(np.uint64) == b.view(np.uint64)).all(), "%s field %s differs" % (tag, f)
     if orc.cfg.curriculum != 0:
         for f in ["level", "check_counter", "win_len", "win_sum"]:
             a, b = backend.field(f), orc.field(f)
@@ -166,7 +202,7 @@ def run_parity(backend, orc, n_steps, render_every=0, act_rep=1, check_state_eve
         assert (fa == fb).all(), "first frame differs: %d px" % (fa != fb).sum()
         stats["frames"] += n
     for s in range(n_steps):
-        a = actions_for(s, n, 4, seed)
+        a = actions_for(s, n, n_actions_of(orc.cfg), seed)
         do_render = bool(render_every) and (s % render_every == 0)
         r1, o1, f1 = backend.step(a, act_rep, render=do_render)
         r2, o2, f2 = orc.step(a, act_rep, render=do_render)
@@ -203,7 +239,7 @@ def run_partial_parity(backend, orc, n_steps, p_step=0.6, render_every=0, seed=5
     stepped = 0
     for s in range(n_steps):
         m = rng.rand(n) < p_step
-        a = actions_for(s, n, 4, seed)
+        a = actions_for(s, n, n_actions_of(orc.cfg), seed)
         a_eng = np.where(m, a, _abi.XW_ACTION_NONE).astype(np.int32)
         r1, o1, f1 = backend.step(a_eng, 1, render=bool(render_every) and s % render_every == 0)
         done = np.zeros(n, np.uint8)

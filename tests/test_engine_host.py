@@ -158,3 +158,23 @@ def test_sparse_painter_and_plan_compositor_vs_per_pixel_rule(geom, synthetic_ca
         bad = np.argwhere(got1 != want)
         assert bad.size == 0, ("sparse", geom, len(bad), bad[:8].tolist())
     assert L.hs_sp_ok(hs.h) == L.hs_fast_ok(hs.h)
+
+
+def test_hostsim_fpv_golden_frames_from_real_opencv():
+    """The engine's first-person code (goal icon warp, crop-cell classes, table pass + exact pass) vs frames the real OpenCV
+    produced from the reference call sequence (tests/golden/fpv_golden.npz)."""
+    from test_oracle_fpv import fpv_golden_cases
+    n = 0
+    for tag, cfg, cat, grid, gi, pose, agent_yaw, want in fpv_golden_cases():
+        hs = parity.HostSim(cfg, cat, 1)
+        yaw_idx = np.array([int(round(p[0] / (1.5707963 * 4) * 4096)) for p in pose], np.uint16)
+        scale = np.ascontiguousarray([p[1] for p in pose], np.float64)
+        offset = np.ascontiguousarray([p[2] for p in pose], np.float64)
+        facing = oracle.lib().xo_facing_dir(agent_yaw)
+        hs.L.hs_set_fpv_env(hs.h, 0, np.ascontiguousarray(grid, np.uint8).ctypes.data, np.ascontiguousarray(gi, np.int32).ctypes.data,
+                            yaw_idx.ctypes.data, scale.ctypes.data, offset.ctypes.data, facing)
+        for mode in (1, 2):
+            got = hs.render(mode=mode)[0]
+            assert (got == want).all(), (tag, n, mode, int((got != want).sum()))
+        n += 1
+    assert n == 42

@@ -169,8 +169,14 @@ def test_python_api_single_env(synthetic_catalog, tmp_path):
         if sim.game_over() != "alive":
             break
     assert sim.get_num_steps() == s + 1
-    with pytest.raises(RuntimeError):
-        Simulator.create("xworld", dict(opts, task_mode="one_channel"))
+    # the reference's own defaults (py_simulator.cpp:124-136): task_mode one_channel, color false -> one gray plane
+    dflt = Simulator.create("xworld", {"xwd_conf_path": str(conf), "catalog": synthetic_catalog})
+    assert dflt.cfg.task_mode == _abi.XW_TASK_ONE_CHANNEL and dflt.get_screen_out_dimensions() == [96, 96, 1, 1]
+    dflt.reset_game()
+    assert len(dflt.get_state()["screen"]) == 96 * 96
+    for s2 in range(12):
+        dflt.take_actions({"action": s2 % 4, "pred_sentence": ""}, 1, False)
+        assert dflt.game_over() == "alive"   # one_channel: only --max_steps ends a session (xworld_simulator.cpp:192-193)
     # invalid action: flagged, never aborts (the reference CHECK-fails, xworld_simulator.cpp:254)
     sim.take_actions({"action": 7})
     assert sim.get_field("error")[0] == -4
@@ -506,3 +512,136 @@ def test_sentences_follow_the_task_state(name, backend_cls, synthetic_catalog):
     assert seen >= ({0, 1, 2, 3, 4} if cfg.rules == _abi.XW_RULES_NAV3D else {0, 2})
     one = sim.sentences([5])
     assert one == [sim.sentences()[5]]
+
+
+def _fpv_scene(eng, grid, gi, pose, agent_yaw, W):
+    """Write one first-person scene into env 0 of `eng` through xw_set_field."""
+    sim = eng.sim
+    g = np.asarray(grid, np.uint8)
+    sim.set_field("grid", g[None, :])
+    c = int(np.nonzero(g == _abi.XW_CELL_AGENT)[0][0])
+    sim.set_field("agent_x", [c % W])
+    sim.set_field("agent_y", [c // W])
+    sim.set_field("facing", [oracle.lib().xo_facing_dir(agent_yaw)])
+    pad = lambda v, dt: np.concatenate([np.asarray(v, dt), np.zeros(_abi.XW_MAX_GOALS - len(v), dt)])[None, :]
+    sim.set_field("goal_icon", pad(gi, np.int32))
+    sim.set_field("goal_yaw", pad([int(round(p[0] / (1.5707963 * 4) * 4096)) for p in pose], np.uint16))
+    sim.set_field("goal_scale", pad([p[1] for p in pose], np.float64))
+    sim.set_field("goal_offset", pad([p[2] for p in pose], np.float64))
+
+
+def test_fpv_golden_frames_from_real_opencv(backend_cls):
+    """the first-person kernels (k_fpv_warp_goals + k_render_fpv / k_render_fpv_generic) vs frames the real
+    OpenCV produced from the reference call sequence, incl. the reference-native 84x84 view of an 11x11 map."""
+    from test_oracle_fpv import fpv_golden_cases
+    n = 0
+    kernels = set()
+    for tag, cfg, cat, grid, gi, pose, agent_yaw, want in fpv_golden_cases():
+        eng = backend_cls(cfg, cat, 1)
+        eng.reset()
+        _fpv_scene(eng, grid, gi, pose, agent_yaw, cfg.width)
+        got = eng.render()[0]
+        assert (got == want).all(), (tag, n, int((got != want).sum()))
+        kernels.add(eng.sim.render_kernel())
+        n += 1
+    assert n == 42 and kernels == {4, 5}   # both the shared-memory kernel and the any-size one ran
+
+
+def test_fpv_auto_reset_and_context(backend_cls, synthetic_catalog):
+    """Auto-reset in the first-person view: the goal icons of re-started episodes are warped by the list-mode launch."""
+    cfg = parity.make_cfg("fpv_nav3d_8x8_vr3_84", auto_reset=1, max_steps=30)
+    eng = backend_cls(cfg, synthetic_catalog, 2048)
+    orc = oracle.Oracle(cfg, synthetic_catalog, 2048, threads=8)
+    st = parity.run_parity(eng, orc, 120, render_every=30, auto_reset=True, check_state_every=15)
+    assert st["events"].get(_abi.XW_MAX_STEP, 0) > 0 and st["events"].get(_abi.XW_SUCCESS, 0) > 0
+    cfg = parity.make_cfg("fpv_nav2d_11x11_vr7_84", auto_reset=1, max_steps=40, context=2)
+    eng = backend_cls(cfg, synthetic_catalog, 256)
+    one = backend_cls(parity.make_cfg("fpv_nav2d_11x11_vr7_84", auto_reset=1, max_steps=40), synthetic_catalog, 256)
+    eng.reset()
+    one.reset()
+    prev = one.render().copy()
+    for s in range(50):
+        a = parity.actions_for(s, 256, 6)
+        eng.step(a, render=True)
+        _, _, f = one.step(a, render=True)
+        scr = eng.sim.screen().cpu().numpy()
+        assert (scr[:, 0:3] == prev).all() and (scr[:, 3:6] == f).all(), s
+        prev = f.copy()
+
+
+def test_fpv_full_size_properties(backend_cls, synthetic_catalog):
+    """BASELINE config 3's map in its reference-native 84x84 first-person view (11x11, visible_radius 7) at 65,536 envs:
+    re-rendering is idempotent; 64 envs sampled at random are pixel-exact against the oracle rendering the same state."""
+    cfg = parity.make_cfg("fpv_nav2d_11x11_vr7_84", auto_reset=1)
+    n = 65536
+    eng = backend_cls(cfg, synthetic_catalog, n)
+    eng.reset()
+    for s in range(30):
+        eng.step(parity.actions_for(s, n, 6), render=False)
+    f1 = eng.render()
+    f2 = eng.render()
+    assert (f1 == f2).all()
+    F = {k: eng.field(k) for k in ("grid", "goal_icon", "goal_yaw", "goal_scale", "goal_offset", "agent_x", "agent_y", "facing")}
+    assert set(np.unique(F["facing"])) == {0, 1, 2, 3}
+    lib = oracle.lib()
+    rng = np.random.RandomState(0)
+    yaw_of = {0: 0.0, 1: 1.5707963, 2: 2 * 1.5707963, 3: -1.5707963}
+    for i in rng.choice(n, 64, replace=False):
+        e = oracle.XoEnv()
+        lib.xo_env_init(C.byref(cfg), C.byref(e), 0)
+        for c, v in enumerate(F["grid"][i]):
+            e.grid[c] = int(v)
+        e.agent_x, e.agent_y, e.agent_yaw = int(F["agent_x"][i]), int(F["agent_y"][i]), yaw_of[int(F["facing"][i])]
+        for k in range(4):
+            e.goal_icon[k] = int(F["goal_icon"][i, k])
+            e.goal_yaw[k] = 0 + (1.5707963 * 4 - 0) * (int(F["goal_yaw"][i, k]) / 4096.0)
+            e.goal_scale[k], e.goal_offset[k] = float(F["goal_scale"][i, k]), float(F["goal_offset"][i, k])
+        want = np.zeros((3, 84, 84), np.uint8)
+        lib.xo_render(C.byref(cfg), C.byref(synthetic_catalog.as_c()), C.byref(e), want.ctypes.data)
+        assert (f1[i] == want).all(), i
+
+
+def test_gray_frames(backend_cls, synthetic_catalog):
+    """--color=false (the reference default): one plane, OpenCV 3.2.0's BGR2GRAY of the colour frame -- fully observed and
+    first person, against the oracle."""
+    for name in ("c3_nav2d_11x11_84", "fpv_nav3d_8x8_vr3_84", "c4_nav3d_15x15_128"):
+        cfg = parity.make_cfg(name, gray=1)
+        eng = backend_cls(cfg, synthetic_catalog, 256)
+        orc = oracle.Oracle(cfg, synthetic_catalog, 256, threads=8)
+        assert eng.sim.get_screen_out_dimensions()[2] == 1
+        parity.run_parity(eng, orc, 24, render_every=6)
+
+
+def test_invalid_action_status(backend_cls, synthetic_catalog):
+    """an invalid action sets the env's error flag AND the call's status (the reference CHECK-aborts)."""
+    import torch
+    for name, n_act in (("c2_nav3d_7x7_84", 4), ("fpv_nav3d_8x8_vr3_84", 6)):
+        cfg = parity.make_cfg(name)
+        eng = backend_cls(cfg, synthetic_catalog, 64)
+        eng.reset()
+        sim = eng.sim
+        assert sim.get_num_actions() == n_act
+        a = torch.zeros(64, dtype=torch.int32, device="cuda")
+        a[5] = n_act
+        before = {k: eng.field(k) for k in ("grid", "agent_x", "agent_y", "num_steps")}
+        sim._lib.xw_error_flags.argtypes = [C.c_void_p, C.c_void_p]
+        rc = sim._lib.xw_step(sim._h, a.data_ptr(), 1, sim._d_reward.data_ptr(), sim._d_over.data_ptr(), None, sim._stream())
+        torch.cuda.synchronize()
+        assert sim._lib.xw_error_flags(sim._h, None) == 1
+        flags = np.zeros(64, np.int32)
+        assert sim._lib.xw_error_flags(sim._h, flags.ctypes.data) == 1 and flags[5] == _abi.XW_ERR_INVALID_ACTION and (np.delete(flags, 5) == 0).all()
+        assert rc == 0   # the device-pointer call cannot know yet; the host-buffer calls return the status:
+        for k in ("agent_x", "agent_y", "num_steps"):
+            assert eng.field(k)[5] == before[k][5]   # the env was left untouched
+        assert (eng.field("grid")[5] == before["grid"][5]).all()
+        h_a = np.zeros(64, np.int32)
+        h_a[7] = -3
+        r, o = np.zeros(64, np.float32), np.zeros(64, np.int32)
+        rc = sim._lib.xw_step_host(sim._h, h_a.ctypes.data, 1, r.ctypes.data, o.ctypes.data, None)
+        assert rc == _abi.XW_ERR_INVALID_ACTION and b"invalid action" in sim._lib.xw_last_error()
+        assert eng.field("num_steps")[5] == 1 and eng.field("num_steps")[7] == 1 and eng.field("num_steps")[0] == 2
+        assert sim._lib.xw_error_flags(sim._h, None) == 2
+        m = np.zeros(64, np.uint8)
+        m[5] = 1
+        eng.reset(m)   # a reset clears the env's flag
+        assert sim._lib.xw_error_flags(sim._h, None) == 1

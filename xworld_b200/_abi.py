@@ -7,6 +7,7 @@ import os
 
 XW_ABI_VERSION = 2
 XW_MAX_GOALS = 8
+XW_ERR_INVALID_ARG, XW_ERR_CUDA, XW_ERR_NO_DEVICE, XW_ERR_INVALID_ACTION, XW_ERR_UNSUPPORTED = -1, -2, -3, -4, -5
 XW_ACTION_NONE = -1
 XW_WIRE_MAX_FIELDS = 8
 XW_MAX_DIM = 16
@@ -120,7 +121,7 @@ class XwWireRequest(C.Structure):
 SYMBOLS = [
     "xw_config_init", "xw_create", "xw_destroy", "xw_last_error", "xw_reset", "xw_step", "xw_render",
     "xw_step_host", "xw_reset_host", "xw_step_hd", "xw_step_hd_async", "xw_wait_frames", "xw_sync", "xw_num_envs", "xw_num_actions", "xw_screen_dims",
-    "xw_frame_bytes", "xw_num_steps", "xw_get_field", "xw_set_field", "xw_launch_count", "xw_render_kernel", "xw_sentence_compose",
+    "xw_frame_bytes", "xw_num_steps", "xw_get_field", "xw_set_field", "xw_error_flags", "xw_launch_count", "xw_render_kernel", "xw_sentence_compose",
     "xw_enable_timing", "xw_render_ms",
     "xw_wire_encode_packet", "xw_wire_decode_packet", "xw_wire_parse_request", "xw_wire_compose_request", "xw_wire_reply_reset",
     "xw_wire_reply_take_actions", "xw_wire_reply_get_state", "xw_wire_reply_text",
@@ -178,6 +179,8 @@ def load():
     lib.xw_get_field.restype = C.c_int
     lib.xw_set_field.argtypes = [vp, C.c_char_p, vp, C.c_size_t]
     lib.xw_set_field.restype = C.c_int
+    lib.xw_error_flags.argtypes = [vp, vp]
+    lib.xw_error_flags.restype = i32
     lib.xw_launch_count.argtypes = [vp]
     lib.xw_sentence_compose.argtypes = [C.POINTER(XwSentenceQuery), C.c_char_p, C.c_size_t]
     lib.xw_sentence_compose.restype = C.c_int

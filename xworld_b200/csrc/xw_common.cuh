@@ -19,8 +19,15 @@
 // (the reference file:line of each site is listed in DESIGN.md §RNG).
 enum {
     XW_SITE_NAMES = 1, XW_SITE_MAZE = 2, XW_SITE_BLOCKS = 3, XW_SITE_GOAL_LOC = 4, XW_SITE_GOAL_ASSET = 5,
-    XW_SITE_AGENT_LOC = 6, XW_SITE_TASK_A = 7, XW_SITE_TASK_B = 8, XW_SITE_TASK_SHUF = 9, XW_SITE_TASK_AGENT = 10
+    XW_SITE_AGENT_LOC = 6, XW_SITE_TASK_A = 7, XW_SITE_TASK_B = 8, XW_SITE_TASK_SHUF = 9, XW_SITE_TASK_AGENT = 10,
+    // 11 = XW_SITE_SENTENCE (xw_sentence.hpp)
+    XW_SITE_AGENT_YAW = 12,  // set_property, --visible_radius > 0: agent yaw = choice(range(-1, 3)) * PI_2 (xworld_env.py:208-210)
+    XW_SITE_GOAL_POSE = 13   // goal yaw / scale / offset = uniform(...) (xworld_env.py:211-223): index 4 * goal + {0, 1, 2}
 };
+// Goal yaws are drawn on a grid of XW_YAW_STEPS points of [0, 4 * PI_2): cos / sin of the rotation angle feed lrint() in
+// cv::warpAffine's fixed-point set-up, and device libm does not agree with the host's to the last bit -- the host evaluates the
+// 4096 possible angles once per handle (XwDev::yaw_cs) and the device only multiplies and adds (IEEE-exact).
+#define XW_YAW_STEPS 4096
 
 // directions relative to a heading (XWorld3DNavTargetDirection.__compute_triple_direction)
 enum { XW_DIR_FALSE = 0, XW_DIR_FRONT = 1, XW_DIR_BEHIND = 2, XW_DIR_LEFT = 3, XW_DIR_RIGHT = 4 };
@@ -41,6 +48,9 @@ struct XwDev {
     int32_t H, W, CS;          // map size, grid row stride (bytes)
     int32_t G, n_blocks, rules, max_steps, max_steps_factor, auto_reset;
     int32_t retry_width;       // attempts the warp of a queued env evaluates side by side in its first retry round
+    int32_t vr;                // --visible_radius after the clamp to the map side; 0 = fully observed
+    int32_t task_mode;         // xw_task_mode
+    int32_t* n_invalid;        // [1] envs that were handed an invalid action since the last xw_step* call returned (or NULL)
     uint64_t seed;
     int64_t gid0;              // global id of env 0
     // ---- per-env state (SoA) ----
@@ -49,6 +59,10 @@ struct XwDev {
     uint8_t *goal_x, *goal_y;  // [XW_MAX_GOALS][n]
     int32_t* goal_icon;        // [XW_MAX_GOALS][n]
     int32_t* goal_name;        // [XW_MAX_GOALS][n]
+    // ---- first-person view (vr > 0): Entity.yaw / scale / offset of the goals (xworld_env.py:211-223); NULL otherwise ----
+    uint16_t* goal_yaw;        // [XW_MAX_GOALS][n] index on the yaw grid: yaw = 4 * PI_2 * idx / XW_YAW_STEPS
+    double *goal_scale, *goal_offset;  // [XW_MAX_GOALS][n]
+    const double* yaw_cs;      // [XW_YAW_STEPS][2] cos, sin of (90 - yaw * 180 / pi) degrees, evaluated by the host's libm
     int32_t *steps_in_task, *num_steps, *episode, *n_success, *n_failure, *success_steps, *error;
     uint32_t* minstd;
     // ---- curriculum (XWorldNav._configure with --curriculum > 0; all NULL / 0 when it is off) ----

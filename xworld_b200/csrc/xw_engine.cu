@@ -18,6 +18,10 @@
 #include "xw_sentence.hpp"
 #include "xw_reset.cuh"
 #include "xw_step.cuh"
+#include "xw_fpv.cuh"
+#include "xw_fpv_host.hpp"
+
+#include <cmath>
 
 // ------------------------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
@@ -114,7 +118,12 @@ struct xw_sim {
     size_t tables_bytes = 0, l2_window = 0;
     float l2_ratio = 0.f;
     void (*render_fn)(XwDev, XwRender, uint8_t*, size_t) = nullptr;  // k_render<WR> for this frame width
-    int C = 3;
+    int C = 3;                      // frame channels: 3 (planes B, G, R) or 1 (--color=false)
+    // first-person view
+    XwFpv fpv;
+    bool fpv_fast = false;
+    int fpv_smem = 0, fpv_grid = 0;
+    uint8_t* d_bgr = nullptr;       // --color=false: the colour frames the gray pass reads
     // race
     XwRaceCfg race;
     int32_t* race_error = nullptr;
@@ -122,6 +131,8 @@ struct xw_sim {
     std::vector<SimpleGameEnv> sg;
     // host staging (pinned)
     int32_t *h_act = nullptr, *h_over = nullptr, *d_act = nullptr, *d_over = nullptr;
+    int32_t* h_invalid = nullptr;   // pinned: running count of invalid actions (XwDev::n_invalid), read back by the host-buffer calls
+    int32_t invalid_seen = 0;
     float *h_rew = nullptr, *d_rew = nullptr;
     uint8_t *d_mask = nullptr, *d_frames = nullptr;
     // timing
@@ -178,6 +189,65 @@ void xw_config_init(xw_config* c) {
     c->reward_scale = 1.f;
 }
 
+// First-person view: tables + the per-env goal icon cache (xw_fpv.cuh).
+static int create_fpv(xw_sim* s, const xw_catalog* cat, int OH, int OW) {
+    const xw_config& c = s->cfg;
+    XwDev& d = s->d;
+    XwFpv& F = s->fpv;
+    memset(&F, 0, sizeof F);
+    F.vr = d.vr; F.N = d.vr * 64; F.CH = c.height * 64; F.OH = OH; F.OW = OW; F.FB = 3 * OH * OW;
+    F.ident1 = F.N == F.CH; F.ident2 = F.CH == OH && F.CH == OW;
+    F.G = c.n_goals; F.brick_icon = cat->brick_icon; F.agent_icon = cat->agent_icon;
+    XwRender& r = s->r;  // (dimensions only: xw_screen_dims and the context shift read them)
+    memset(&r, 0, sizeof r);
+    r.OH = OH; r.OW = OW; r.FB = F.FB; r.H = c.height; r.W = c.width; r.n_icons = cat->n_icons;
+    int rc = 0;
+    std::vector<int16_t> o, a0, a1;
+    xw_fpv_resize_tables(F.N, F.CH, false, o, a0, a1);
+    rc |= dupload(s, &F.x1ofs, o.data(), o.size()); rc |= dupload(s, &F.x1a0, a0.data(), a0.size()); rc |= dupload(s, &F.x1a1, a1.data(), a1.size());
+    xw_fpv_resize_tables(F.N, F.CH, true, o, a0, a1);
+    rc |= dupload(s, &F.y1ofs, o.data(), o.size()); rc |= dupload(s, &F.y1a0, a0.data(), a0.size()); rc |= dupload(s, &F.y1a1, a1.data(), a1.size());
+    xw_fpv_resize_tables(F.CH, OW, false, o, a0, a1);
+    rc |= dupload(s, &F.x2ofs, o.data(), o.size()); rc |= dupload(s, &F.x2a0, a0.data(), a0.size()); rc |= dupload(s, &F.x2a1, a1.data(), a1.size());
+    xw_fpv_resize_tables(F.CH, OH, true, o, a0, a1);
+    rc |= dupload(s, &F.y2ofs, o.data(), o.size()); rc |= dupload(s, &F.y2a0, a0.data(), a0.size()); rc |= dupload(s, &F.y2a1, a1.data(), a1.size());
+    rc |= dupload(s, &F.atlas64, cat->atlas64, (size_t)cat->n_icons * 12288);
+    {
+        std::vector<uint8_t> a4 = xw_fpv_agent_icons(cat->atlas64 + (size_t)cat->agent_icon * 12288);
+        rc |= dupload(s, &F.agent4, a4.data(), a4.size());
+        std::vector<int16_t> itab(32 * 32 * 4);
+        xw_fpv_build_itab(itab.data());
+        rc |= dupload(s, &F.itab, itab.data(), itab.size());
+        std::vector<double> cs = xw_fpv_yaw_table();
+        rc |= dupload(s, &d.yaw_cs, cs.data(), cs.size());
+    }
+    rc |= dalloc(s, &F.gcache, (size_t)s->n * F.G * 12288, false);
+    uint8_t *pmap = nullptr, *Tb = nullptr, *Ta = nullptr;
+    rc |= dalloc(s, &pmap, (size_t)4 * OH * OW);
+    rc |= dalloc(s, &Tb, (size_t)4 * 3 * OH * OW);
+    rc |= dalloc(s, &Ta, (size_t)4 * 3 * OH * OW);
+    if (rc) return rc;
+    F.pmap = pmap; F.Tb = Tb; F.Ta = Ta;
+    k_fpv_build_tables<<<s->n_sms * 4, 256, 0, s->own_stream>>>(F, pmap, Tb, Ta);
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    s->fpv_fast = OW % 4 == 0 && F.FB % 16 == 0;
+    if (s->fpv_fast) {
+        s->fpv_smem = F.FB + 2 * OH * OW + 256;
+        int max_optin = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
+        if (s->fpv_smem > max_optin) s->fpv_fast = false;
+        else {
+            CUDA_TRY(cudaFuncSetAttribute(k_render_fpv<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->fpv_smem));
+            int per_sm = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_render_fpv<256>, 256, s->fpv_smem));
+            s->fpv_grid = s->n_sms * (per_sm > 0 ? per_sm : 1);
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(s->own_stream));
+    return 0;
+}
+
 static int create_xworld(xw_sim* s, const xw_catalog* cat) {
     const xw_config& c = s->cfg;
     const int n = s->n;
@@ -186,7 +256,13 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
     if (c.height < 3 || c.height > XW_MAX_DIM) return set_err(XW_ERR_INVALID_ARG, "map side must be in [3,%d]", XW_MAX_DIM);
     if (c.n_goals < 1 || c.n_goals > XW_MAX_GOALS) return set_err(XW_ERR_INVALID_ARG, "n_goals must be in [1,%d]", XW_MAX_GOALS);
     if (cat->n_names < c.n_goals) return set_err(XW_ERR_INVALID_ARG, "catalog has fewer goal names than n_goals");
-    if (c.visible_radius != 0) return set_err(XW_ERR_UNSUPPORTED, "visible_radius > 0 (first-person view) is not implemented");
+    if (c.visible_radius < 0) return set_err(XW_ERR_INVALID_ARG, "visible_radius must be >= 0");
+    const int vr = c.visible_radius < c.height ? c.visible_radius : c.height;  // xworld_simulator.cpp:63-64
+    if (vr > 0 && vr % 2 == 0) return set_err(XW_ERR_INVALID_ARG, "visible_radius %d: must be an odd int (xmap.cpp:277)", vr);
+    if (c.task_mode != XW_TASK_LANG_ACQUISITION && c.task_mode != XW_TASK_ONE_CHANNEL) return set_err(XW_ERR_INVALID_ARG, "unknown task_mode");
+    if (c.task_mode == XW_TASK_ONE_CHANNEL && c.rules == XW_RULES_NAV2D && c.curriculum != 0)
+        return set_err(XW_ERR_UNSUPPORTED, "one_channel + walls.json rules + curriculum: the task classes' usage records then depend on the "
+                                           "XWorldRec question tasks, which are outside this engine");
     if (c.context < 1 || c.context > 16) return set_err(XW_ERR_INVALID_ARG, "context must be in [1,16]");
     if (c.rules != XW_RULES_NAV3D && c.rules != XW_RULES_NAV2D) return set_err(XW_ERR_INVALID_ARG, "unknown rules");
     if (c.curriculum != 0) {  // XWorldNav's level schedule is written for its own 8x8 map (XWorldNav.py:10-11,27-33)
@@ -208,6 +284,8 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
     d.G = c.n_goals; d.n_blocks = c.n_blocks; d.rules = c.rules; d.max_steps = c.max_steps;
     d.max_steps_factor = c.max_steps_factor; d.auto_reset = c.auto_reset;
     d.seed = c.seed; d.gid0 = c.env_id_offset;
+    d.vr = vr; d.task_mode = c.task_mode;
+    s->C = c.gray ? 1 : 3;
     { const char* ew = getenv("XW_RESET_RETRY_WIDTH"); int w = ew ? atoi(ew) : 32; d.retry_width = w < 1 ? 1 : (w > 32 ? 32 : w); }
     int rc = 0;
     rc |= dalloc(s, &d.grid, (size_t)n * d.CS);
@@ -222,6 +300,12 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
     rc |= dalloc(s, &d.minstd, (size_t)n);
     rc |= dalloc(s, &d.reset_count, 2);
     rc |= dalloc(s, &d.reset_list, (size_t)n);
+    rc |= dalloc(s, &d.n_invalid, 1);
+    if (vr > 0) {
+        rc |= dalloc(s, &d.goal_yaw, (size_t)n * XW_MAX_GOALS);
+        rc |= dalloc(s, &d.goal_scale, (size_t)n * XW_MAX_GOALS);
+        rc |= dalloc(s, &d.goal_offset, (size_t)n * XW_MAX_GOALS);
+    }
     if (c.curriculum != 0) {
         d.curriculum = (double)c.curriculum;
         d.check_period = c.curriculum_check_period > 0 ? c.curriculum_check_period : 100;
@@ -247,7 +331,14 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
     if (rc) return rc;
     // renderer
     int OH = c.out_h > 0 ? c.out_h : c.height * 12, OW = c.out_w > 0 ? c.out_w : c.width * 12;  // xworld_simulator.cpp:52-61
+    if (vr > 0) {  // block_size = 84 / visible_radius, visible_radius blocks a side (xworld_simulator.cpp:62-68)
+        if (c.out_h <= 0) OH = vr * (84 / vr);
+        if (c.out_w <= 0) OW = vr * (84 / vr);
+    }
     if (OH > XW_MAX_OUT || OW > XW_MAX_OUT) return set_err(XW_ERR_INVALID_ARG, "frame side must be <= %d", XW_MAX_OUT);
+    if (c.gray) rc |= dalloc(s, &s->d_bgr, (size_t)n * 3 * OH * OW, false);
+    if (rc) return rc;
+    if (vr > 0) return create_fpv(s, cat, OH, OW);
     s->tab = xw_build_render_tables(c.height, c.width, OH, OW);
     XwRenderTables& t = s->tab;
     XwRender& r = s->r;
@@ -505,6 +596,7 @@ void xw_destroy(xw_sim* s) {
     if (s->h_act) cudaFreeHost(s->h_act);
     if (s->h_over) cudaFreeHost(s->h_over);
     if (s->h_rew) cudaFreeHost(s->h_rew);
+    if (s->h_invalid) cudaFreeHost(s->h_invalid);
     for (auto ev : s->ev) cudaEventDestroy(ev);
     if (s->copy_stream) { cudaStreamDestroy(s->copy_stream); cudaEventDestroy(s->ev_step); cudaEventDestroy(s->ev_copy); cudaEventDestroy(s->ev_h2d); }
     if (s->ev_frames) cudaEventDestroy(s->ev_frames);
@@ -515,13 +607,13 @@ void xw_destroy(xw_sim* s) {
 int32_t xw_num_envs(const xw_sim* s) { return s->n; }
 
 int32_t xw_num_actions(const xw_sim* s) {
-    if (s->cfg.game == XW_GAME_XWORLD) return s->cfg.visible_radius == 0 ? 4 : 6;  // xitem.cpp:82-86
+    if (s->cfg.game == XW_GAME_XWORLD) return s->d.vr == 0 ? 4 : 6;  // xitem.cpp:82-86
     if (s->cfg.game == XW_GAME_SIMPLE_GAME) return 2;
     return s->cfg.race_full_manouver ? 9 : 2;  // simple_race_simulator.cpp:432-440
 }
 
 int xw_screen_dims(const xw_sim* s, int32_t* h, int32_t* w, int32_t* c, int32_t* context) {
-    if (s->cfg.game == XW_GAME_XWORLD) { *h = s->r.OH; *w = s->r.OW; *c = 3; }
+    if (s->cfg.game == XW_GAME_XWORLD) { *h = s->r.OH; *w = s->r.OW; *c = s->C; }
     else if (s->cfg.game == XW_GAME_SIMPLE_GAME) { *h = 1; *w = s->cfg.array_size; *c = 1; }  // simple_game_simulator.cpp:101-107
     else { *h = 1; *w = 4; *c = 1; }
     *context = s->cfg.context;
@@ -570,6 +662,7 @@ int xw_sentence_compose(const xw_sentence_query* q, char* buf, size_t cap) {
 int64_t xw_launch_count(const xw_sim* s) { return s->launches; }
 int32_t xw_render_kernel(const xw_sim* s) {
     if (s->cfg.game != XW_GAME_XWORLD) return -1;
+    if (s->d.vr > 0) return s->fpv_fast ? 5 : 4;
     if (!s->tab.fast_ok) return 0;
     return s->render_sp ? 3 : (s->render_sb ? 1 : 2);
 }
@@ -595,13 +688,17 @@ double xw_render_ms(xw_sim* s, int32_t reset) {
 static int launch_render(xw_sim* s, uint8_t* d_frames, cudaStream_t st) {
     XwRender& r = s->r;
     const int K = s->cfg.context;
-    const size_t env_stride = (size_t)K * r.FB;
+    const int FBo = s->C * r.OH * r.OW;  // bytes of one frame as the caller sees it
+    const size_t env_stride = (size_t)K * FBo;
     if (K > 1) {  // GameSimulator::shift_context (simulator.cpp:51-60)
-        if (r.FB % 16) return set_err(XW_ERR_UNSUPPORTED, "context > 1 needs a frame size divisible by 16");
-        k_shift_context<<<s->n_sms * 4, 256, 0, st>>>(d_frames, s->n, K, r.FB);
+        if (FBo % 16) return set_err(XW_ERR_UNSUPPORTED, "context > 1 needs a frame size divisible by 16");
+        k_shift_context<<<s->n_sms * 4, 256, 0, st>>>(d_frames, s->n, K, FBo);
         s->launches++;
     }
-    uint8_t* dst = d_frames + (size_t)(K - 1) * r.FB;  // newest frame last
+    uint8_t* out = d_frames + (size_t)(K - 1) * FBo;  // newest frame last
+    // --color=false: the colour frame goes to a scratch buffer, k_gray writes the caller's (xworld_simulator.cpp:529-531)
+    uint8_t* dst = s->cfg.gray ? s->d_bgr : out;
+    const size_t dst_stride = s->cfg.gray ? (size_t)r.FB : env_stride;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (s->timing) {
         if (s->ev_used + 2 > s->ev.size()) {
@@ -611,7 +708,14 @@ static int launch_render(xw_sim* s, uint8_t* d_frames, cudaStream_t st) {
         s->ev_used += 2;
         CUDA_TRY(cudaEventRecord(e0, st));
     }
-    if (s->tab.fast_ok) {
+    if (s->d.vr > 0) {
+        if (s->fpv_fast && dst_stride % 16 == 0) {
+            const int grid = s->fpv_grid < s->n ? s->fpv_grid : s->n;
+            k_render_fpv<256><<<grid, 256, s->fpv_smem, st>>>(s->d, s->fpv, dst, dst_stride);
+        } else {
+            k_render_fpv_generic<<<s->n_sms * 8 < s->n ? s->n_sms * 8 : s->n, 256, 0, st>>>(s->d, s->fpv, dst, dst_stride);
+        }
+    } else if (s->tab.fast_ok) {
         const int need = (s->n + r.G - 1) / r.G;  // CTAs that get at least one env
         const int grid = s->render_grid < need ? s->render_grid : need;
         cudaLaunchConfig_t lc;
@@ -627,11 +731,15 @@ static int launch_render(xw_sim* s, uint8_t* d_frames, cudaStream_t st) {
             at[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
             lc.attrs = at; lc.numAttrs = 1;
         }
-        CUDA_TRY(cudaLaunchKernelEx(&lc, s->render_fn, s->d, r, dst, env_stride));
+        CUDA_TRY(cudaLaunchKernelEx(&lc, s->render_fn, s->d, r, dst, dst_stride));
     } else {
-        k_render_generic<<<s->n_sms * 8, 256, 0, st>>>(s->d, r, dst, env_stride);
+        k_render_generic<<<s->n_sms * 8, 256, 0, st>>>(s->d, r, dst, dst_stride);
     }
     s->launches++;
+    if (s->cfg.gray) {
+        k_gray<<<s->n_sms * 8, 256, 0, st>>>(s->d_bgr, out, s->n, r.OH * r.OW, (size_t)r.FB, env_stride);
+        s->launches++;
+    }
     if (s->timing) CUDA_TRY(cudaEventRecord(e1, st));
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -648,6 +756,10 @@ int xw_reset(xw_sim* s, const uint8_t* d_mask, void* stream) {
     if (s->cfg.game == XW_GAME_XWORLD) {
         k_reset<<<(s->n + 127) / 128, 128, 0, st>>>(s->d, d_mask, nullptr, nullptr);
         s->launches++;
+        if (s->d.vr > 0) {  // the new episodes' goal icons, warped once (xitem.cpp:47-60)
+            k_fpv_warp_goals<<<s->n_sms * 8 < s->n ? s->n_sms * 8 : s->n, 256, 0, st>>>(s->d, s->fpv, d_mask, nullptr, nullptr);
+            s->launches++;
+        }
     } else if (s->cfg.game == XW_GAME_SIMPLE_RACE) {
         k_race_reset<<<(s->n + 255) / 256, 256, 0, st>>>(s->race, d_mask);
         s->launches++;
@@ -670,6 +782,11 @@ int xw_step(xw_sim* s, const int32_t* d_actions, int32_t act_rep, float* d_rewar
             const int want = (s->n + 3) / 4, cap = s->n_sms * 16;  // CTAs of 4 warps: one warp per queued env, grid-stride past the cap
             k_reset<<<want < cap ? want : cap, 128, 0, st>>>(s->d, nullptr, s->d.reset_list, s->d.reset_count + s->step_parity);
             s->launches++;
+            if (s->d.vr > 0) {
+                k_fpv_warp_goals<<<s->n_sms * 8 < s->n ? s->n_sms * 8 : s->n, 256, 0, st>>>(s->d, s->fpv, nullptr, s->d.reset_list,
+                                                                                           s->d.reset_count + s->step_parity);
+                s->launches++;
+            }
         }
         s->step_parity ^= 1;
         CUDA_TRY(cudaGetLastError());
@@ -690,11 +807,14 @@ int xw_step(xw_sim* s, const int32_t* d_actions, int32_t act_rep, float* d_rewar
     return set_err(XW_ERR_UNSUPPORTED, "simple_game runs on the host: use xw_step_host");
 }
 
+static int invalid_status(xw_sim* s);
 static int ensure_staging(xw_sim* s, bool frames) {
     if (!s->h_act) {
         CUDA_TRY(cudaMallocHost((void**)&s->h_act, sizeof(int32_t) * s->n));
         CUDA_TRY(cudaMallocHost((void**)&s->h_over, sizeof(int32_t) * s->n));
         CUDA_TRY(cudaMallocHost((void**)&s->h_rew, sizeof(float) * s->n));
+        CUDA_TRY(cudaMallocHost((void**)&s->h_invalid, sizeof(int32_t)));
+        *s->h_invalid = 0;
         int rc = dalloc(s, &s->d_act, (size_t)s->n) | dalloc(s, &s->d_over, (size_t)s->n) | dalloc(s, &s->d_rew, (size_t)s->n) |
                  dalloc(s, &s->d_mask, (size_t)s->n);
         if (rc) return rc;
@@ -789,11 +909,21 @@ int xw_step_host(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float* h_
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(s->h_rew, s->d_rew, sizeof(float) * s->n, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(s->h_over, s->d_over, sizeof(int32_t) * s->n, cudaMemcpyDeviceToHost, st));
+    if (s->cfg.game == XW_GAME_XWORLD) CUDA_TRY(cudaMemcpyAsync(s->h_invalid, s->d.n_invalid, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     if (h_frames) CUDA_TRY(cudaMemcpyAsync(h_frames, s->d_frames, (size_t)s->n * xw_frame_bytes(s), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     memcpy(h_reward, s->h_rew, sizeof(float) * s->n);
     memcpy(h_game_over, s->h_over, sizeof(int32_t) * s->n);
-    return 0;
+    return invalid_status(s);
+}
+
+// SURVEY §8b "per-env flag + status": the calls that hand results to the host also report whether any env of this
+// step was given an action outside [0, num_actions) (the reference CHECK-aborts, xworld_simulator.cpp:254)
+static int invalid_status(xw_sim* s) {
+    if (s->cfg.game != XW_GAME_XWORLD || !s->h_invalid) return 0;
+    const int32_t total = *s->h_invalid, fresh = total - s->invalid_seen;
+    s->invalid_seen = total;
+    return fresh > 0 ? set_err(XW_ERR_INVALID_ACTION, "invalid action for %d env(s): left untouched and flagged (xw_error_flags)", fresh) : 0;
 }
 
 static bool is_pinned(const void* p) {
@@ -879,6 +1009,7 @@ static int step_hd(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float* 
     }
     CUDA_TRY(cudaMemcpyAsync(pin_r ? h_reward : s->h_rew, s->d_rew, sizeof(float) * s->n, cudaMemcpyDeviceToHost, cs));
     CUDA_TRY(cudaMemcpyAsync(pin_o ? h_game_over : s->h_over, s->d_over, sizeof(int32_t) * s->n, cudaMemcpyDeviceToHost, cs));
+    if (s->cfg.game == XW_GAME_XWORLD) CUDA_TRY(cudaMemcpyAsync(s->h_invalid, s->d.n_invalid, sizeof(int32_t), cudaMemcpyDeviceToHost, cs));
     if (split) {
         if (wait_frames) {
             CUDA_TRY(cudaEventRecord(s->ev_copy, cs));  // one host wait for both streams
@@ -888,7 +1019,7 @@ static int step_hd(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float* 
     CUDA_TRY(cudaStreamSynchronize(split && !wait_frames ? cs : st));
     if (!pin_r) memcpy(h_reward, s->h_rew, sizeof(float) * s->n);
     if (!pin_o) memcpy(h_game_over, s->h_over, sizeof(int32_t) * s->n);
-    return 0;
+    return invalid_status(s);
 }
 
 int xw_num_steps(xw_sim* s, int64_t* h) {
@@ -915,6 +1046,8 @@ static bool find_field(xw_sim* s, const char* name, FieldRef* f) {
             {"aux0", d.aux0, 1, 1, false}, {"aux1", d.aux1, 1, 1, false}, {"aux2", d.aux2, 1, 1, false},
             {"goal_x", d.goal_x, 1, XW_MAX_GOALS, true}, {"goal_y", d.goal_y, 1, XW_MAX_GOALS, true},
             {"goal_icon", d.goal_icon, 4, XW_MAX_GOALS, true}, {"goal_name", d.goal_name, 4, XW_MAX_GOALS, true},
+            {"goal_yaw", d.goal_yaw, 2, XW_MAX_GOALS, true}, {"goal_scale", d.goal_scale, 8, XW_MAX_GOALS, true},
+            {"goal_offset", d.goal_offset, 8, XW_MAX_GOALS, true},
             {"steps_in_task", d.steps_in_task, 4, 1, false}, {"num_steps", d.num_steps, 4, 1, false},
             {"episode", d.episode, 4, 1, false}, {"n_success", d.n_success, 4, 1, false},
             {"n_failure", d.n_failure, 4, 1, false}, {"success_steps", d.success_steps, 4, 1, false},
@@ -967,6 +1100,26 @@ static int field_io(xw_sim* s, const char* name, void* h, size_t bytes, bool get
 }
 
 int xw_get_field(xw_sim* s, const char* name, void* h_out, size_t bytes) { return field_io(s, name, h_out, bytes, true); }
-int xw_set_field(xw_sim* s, const char* name, const void* h_in, size_t bytes) { return field_io(s, name, (void*)h_in, bytes, false); }
+
+int32_t xw_error_flags(xw_sim* s, int32_t* h_flags) {
+    if (s->cfg.game == XW_GAME_SIMPLE_GAME) { if (h_flags) memset(h_flags, 0, sizeof(int32_t) * s->n); return 0; }
+    std::vector<int32_t> tmp(s->n);
+    if (field_io(s, "error", tmp.data(), sizeof(int32_t) * s->n, true)) return -1;
+    int32_t cnt = 0;
+    for (int i = 0; i < s->n; ++i) cnt += tmp[i] != 0;
+    if (h_flags) memcpy(h_flags, tmp.data(), sizeof(int32_t) * s->n);
+    return cnt;
+}
+int xw_set_field(xw_sim* s, const char* name, const void* h_in, size_t bytes) {
+    int rc = field_io(s, name, (void*)h_in, bytes, false);
+    if (rc == 0 && s->cfg.game == XW_GAME_XWORLD && s->d.vr > 0 && !strncmp(name, "goal_", 5)) {
+        // the cached goal icons are a function of (icon, yaw, scale, offset): warp them again
+        k_fpv_warp_goals<<<s->n_sms * 8 < s->n ? s->n_sms * 8 : s->n, 256, 0, s->own_stream>>>(s->d, s->fpv, nullptr, nullptr, nullptr);
+        s->launches++;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(s->own_stream));
+    }
+    return rc;
+}
 
 }  // extern "C"

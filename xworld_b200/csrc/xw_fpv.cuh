@@ -1,0 +1,388 @@
+// xw_fpv.cuh -- the first-person view (--visible_radius > 0): XWorldSimulator::get_screen for every env when the agent
+// sees a vr x vr window of cells ahead of it.
+//
+// Replaces (reference file:line):
+//   XMap::to_image, visible_radius_unit > 0   games/xworld/xworld/xmap.cpp:125-200  (canvas, black border, crop, shadow cells,
+//                                                                                   rotation by 90 + yaw)
+//   XMap::image_masking                       xmap.cpp:273-362                      (ROI + wall shadows)
+//   XItem::get_item_image                     games/xworld/xworld/xitem.cpp:33-63   (per-item warpAffine: yaw, scale, offset)
+//   XWorldSimulator::get_screen_rgb           games/xworld/xworld_simulator.cpp:287-307  (cv::resize view -> map size)
+//   XWorldSimulator::down_sample_image        xworld_simulator.cpp:508-545               (cv::resize -> frame)
+//
+// None of the reference's images exists here.  An output pixel is resize2(resize1(view)) evaluated backwards: its 2x2 taps in
+// the map-sized intermediate image, each of which is 2x2 taps in the rotated view; a view pixel is a pure function of
+//   (heading, crop cell code, pixel in the cell):  the view rotation is an exact pixel permutation for the four headings
+//   (a quarter turn about the pixel corner (N/2, N/2): index i -> N - i, one black row / column; tests/test_oracle_fpv.py),
+//   a crop cell is white / black (outside the map or in a wall's shadow) / brick / the agent (its icon turned by the same
+//   kind of permutation) / goal g (its icon warped with the goal's own yaw, scale and offset).
+// Goal icons are warped ONCE per episode (k_fpv_warp_goals, after the reset kernel) into a per-env cache in HBM with
+// cv::warpAffine's fixed-point arithmetic; the matrix set-up runs in IEEE doubles on the device, with cos / sin taken from a
+// host-evaluated table (xw_common.cuh XW_YAW_STEPS).
+//
+// Frame kernel (k_render_fpv): one CTA per env at a time, frame composed in shared memory, one TMA bulk store per frame.
+// Pixels whose whole footprint lies inside one crop cell of a uniform class come from per-heading tables built once per
+// handle (pmap: which crop cell; Tb / Ta: the finished pixel if that cell is a brick / the agent; white and black are
+// constants); the rest (footprints that straddle cells, goal cells) are queued and evaluated exactly, tap by tap.
+#pragma once
+#include "xw_common.cuh"
+#include "xw_render.cuh"
+#include "xw_reset.cuh"
+
+// crop-cell classes (the grid's cell codes + black)
+#define XW_FPV_BLACK 0x80
+
+struct XwFpv {
+    int32_t vr, N;            // window side in cells / pixels (N = 64 * vr)
+    int32_t CH;               // side of the intermediate image = map side * 64 (xworld_simulator.cpp:293)
+    int32_t OH, OW, FB;       // frame: rows, columns, bytes (3 * OH * OW)
+    int32_t ident1, ident2;   // resize 1 / 2 is a copy (cv::resize with equal sizes)
+    int32_t G;                // goal slots per env
+    // cv::resize tables (INTER_LINEAR, 11-bit weights): columns clamp index and weight, rows keep the raw weight and
+    // clip the two row indices (oracle/xw_oracle.c xo_resize_linear_8uc3 has the derivation)
+    const int16_t *x1ofs, *x1a0, *x1a1, *y1ofs, *y1a0, *y1a1;  // [CH]  view -> intermediate
+    const int16_t *x2ofs, *x2a0, *x2a1, *y2ofs, *y2a0, *y2a1;  // [OW] / [OH]  intermediate -> frame
+    const uint8_t* atlas64;   // [n_icons][64][64][3] BGR
+    int32_t brick_icon, agent_icon;
+    const uint8_t* agent4;    // [4][64][64][3] the agent's icon for headings right, down, left, up
+    uint8_t* gcache;          // [n][G][64][64][3] warped goal icons of the current episode
+    const int16_t* itab;      // [32][32][4] cv::warpAffine's bilinear weights (sum 32768)
+    const uint8_t* pmap;      // [4][OH][OW] crop cell (cy * vr + cx) that holds the whole footprint of the pixel, 0xff = none
+    const uint8_t* Tb;        // [4][3][OH][OW] the pixel if that cell is a brick
+    const uint8_t* Ta;        // [4][3][OH][OW] the pixel if that cell is the agent
+};
+
+// ---------------------------------------------------------------------------------------- geometry
+// View rotation (xmap.cpp:196-200), inverted: pixel (vy, vx) of the rotated view is pixel (cy, cx) of the crop;
+// false = the black row / column the quarter turn about (N/2, N/2) leaves.
+XW_HD bool xw_fpv_unrotate(int N, int facing, int vy, int vx, int* cy, int* cx) {
+    int y, x;
+    if (facing == 3) { y = vy; x = vx; }
+    else if (facing == 0) { y = vx; x = N - vy; }
+    else if (facing == 1) { y = N - vy; x = N - vx; }
+    else { y = N - vx; x = vy; }
+    *cy = y; *cx = x;
+    return y < N && x < N;
+}
+// The agent's icon (xitem.cpp:47-60 with the agent's yaw): pixel (y, x) of the turned icon is pixel (sy, sx) of the file's;
+// false = the white row / column.
+XW_HD bool xw_fpv_agent_src(int facing, int y, int x, int* sy, int* sx) {
+    int a, b;
+    if (facing == 1) { a = y; b = x; }
+    else if (facing == 0) { a = x; b = 64 - y; }
+    else if (facing == 2) { a = 64 - x; b = y; }
+    else { a = 64 - y; b = 64 - x; }
+    *sy = a; *sx = b;
+    return a < 64 && b < 64;
+}
+
+// XMap::image_masking (xmap.cpp:273-362) + the crop: class of every cell of the vr x vr window, ccode[cy * vr + cx].
+// One call computes the major line `k` (a column of the window when the agent looks up / down, a row otherwise): the
+// lines are independent, so vr lanes do them side by side.
+XW_HD void xw_fpv_cells_line(const XwDev& d, int e, int k, uint8_t* ccode) {
+    const int vr = d.vr, h = vr / 2;
+    const uint8_t* g = d.grid + (size_t)e * d.CS;
+    const int ax = d.agent_x[e], ay = d.agent_y[e], facing = d.facing[e];
+    // window origin in map cells: x_st - vr, y_st - vr of the reference (the padded canvas is shifted by vr)
+    int ox = ax - h, oy = ay - h;
+    int major_x = 0, major_y = 0, minor_x = 0, minor_y = 0, scan_x = 0, scan_y = 0;
+    if (facing == 0) { ox += h; major_y = 1; minor_x = 1; }
+    else if (facing == 3) { oy -= h; major_x = 1; minor_y = -1; scan_y = vr - 1; }
+    else if (facing == 2) { ox -= h; major_y = 1; minor_x = -1; scan_x = vr - 1; }
+    else { oy += h; major_x = 1; minor_y = 1; }
+    // "which grids the agent's ray can start going forward": line k starts blocked iff a brick sits between the agent and it
+    bool block = false;
+    {
+        const int o = k < h ? -1 : 1, steps = k < h ? h - k : k - h;
+        int rx = ax, ry = ay;
+        for (int j = 1; j < steps; ++j) {
+            rx += o * major_x; ry += o * major_y;
+            if (rx >= 0 && rx < d.W && ry >= 0 && ry < d.H && g[ry * d.W + rx] == XW_CELL_BLOCK) block = true;
+        }
+    }
+    int cx = scan_x + k * major_x, cy = scan_y + k * major_y;
+    for (int j = 0; j < vr; ++j) {
+        const int gx = ox + cx, gy = oy + cy;
+        const bool in = gx >= 0 && gx < d.W && gy >= 0 && gy < d.H;
+        const int code = in ? g[gy * d.W + gx] : XW_FPV_BLACK;        // copyMakeBorder(..., Scalar(0, 0, 0))
+        ccode[cy * vr + cx] = (uint8_t)(block ? XW_FPV_BLACK : code);  // shadow cells are painted black (xmap.cpp:170-185)
+        if (code == XW_CELL_BLOCK) block = true;
+        cx += minor_x; cy += minor_y;  // (never wraps: vr steps from one edge of the window to the other)
+    }
+}
+
+// ---------------------------------------------------------------------------------------- pixels
+XW_HD uint32_t xw_px3(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16); }
+
+// A view pixel of one env (B | G << 8 | R << 16).
+struct XwFpvEnvFetch {
+    const XwFpv* F; const uint8_t* ccode; const uint8_t* gc; int facing;
+    XW_HD uint32_t operator()(int vy, int vx) const {
+        int cy, cx;
+        if (!xw_fpv_unrotate(F->N, facing, vy, vx, &cy, &cx)) return 0u;
+        const int code = ccode[(cy >> 6) * F->vr + (cx >> 6)];
+        if (code == XW_CELL_EMPTY) return 0xffffffu;
+        if (code == XW_FPV_BLACK) return 0u;
+        const int off = (((cy & 63) << 6) + (cx & 63)) * 3;
+        if (code == XW_CELL_BLOCK) return xw_px3(F->atlas64 + (size_t)F->brick_icon * 12288 + off);
+        if (code == XW_CELL_AGENT) return xw_px3(F->agent4 + facing * 12288 + off);
+        return xw_px3(gc + (size_t)(code - XW_CELL_GOAL0) * 12288 + off);
+    }
+};
+// Table building: every cell holds `src` (a 64x64x3 icon); records which crop cells the taps touch.
+struct XwFpvProbeFetch {
+    const XwFpv* F; const uint8_t* src; int facing;
+    mutable int cell, mixed;
+    XW_HD uint32_t operator()(int vy, int vx) const {
+        int cy, cx;
+        if (!xw_fpv_unrotate(F->N, facing, vy, vx, &cy, &cx)) { mixed = 1; return 0u; }
+        const int c = (cy >> 6) * F->vr + (cx >> 6);
+        if (cell < 0) cell = c; else if (cell != c) mixed = 1;
+        return xw_px3(src + (((cy & 63) << 6) + (cx & 63)) * 3);
+    }
+};
+
+XW_HD int xw_clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+XW_HD uint32_t xw_resize_px3(uint32_t p00, uint32_t p01, uint32_t p10, uint32_t p11, int a0, int a1, int b0, int b1) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int s = 8 * c;
+        o |= (uint32_t)xw_resize_px((p00 >> s) & 255, (p01 >> s) & 255, (p10 >> s) & 255, (p11 >> s) & 255, a0, a1, b0, b1) << s;
+    }
+    return o;
+}
+// pixel (jy, jx) of the intermediate image: cv::resize(view -> CH x CH)
+template <class Fetch>
+XW_HD uint32_t xw_fpv_mid(const XwFpv& F, int jy, int jx, const Fetch& fetch) {
+    if (F.ident1) return fetch(jy, jx);
+    const int sx0 = F.x1ofs[jx], sx1 = sx0 + 1 < F.N ? sx0 + 1 : F.N - 1;
+    const int sy = F.y1ofs[jy], sy0 = xw_clampi(sy, 0, F.N - 1), sy1 = xw_clampi(sy + 1, 0, F.N - 1);
+    return xw_resize_px3(fetch(sy0, sx0), fetch(sy0, sx1), fetch(sy1, sx0), fetch(sy1, sx1), F.x1a0[jx], F.x1a1[jx], F.y1a0[jy], F.y1a1[jy]);
+}
+// frame pixel (oy, ox), three channels: cv::resize(intermediate -> OH x OW)
+template <class Fetch>
+XW_HD uint32_t xw_fpv_px(const XwFpv& F, int oy, int ox, const Fetch& fetch) {
+    if (F.ident2) return xw_fpv_mid(F, oy, ox, fetch);
+    const int jx0 = F.x2ofs[ox], jx1 = jx0 + 1 < F.CH ? jx0 + 1 : F.CH - 1;
+    const int jy = F.y2ofs[oy], jy0 = xw_clampi(jy, 0, F.CH - 1), jy1 = xw_clampi(jy + 1, 0, F.CH - 1);
+    return xw_resize_px3(xw_fpv_mid(F, jy0, jx0, fetch), xw_fpv_mid(F, jy0, jx1, fetch), xw_fpv_mid(F, jy1, jx0, fetch),
+                         xw_fpv_mid(F, jy1, jx1, fetch), F.x2a0[ox], F.x2a1[ox], F.y2a0[oy], F.y2a1[oy]);
+}
+
+// One entry of the per-heading tables: i = ((f * OH) + oy) * OW + ox.
+XW_HD void xw_fpv_table_entry(const XwFpv& F, size_t i, uint8_t* pmap, uint8_t* Tb, uint8_t* Ta) {
+    const int ox = (int)(i % F.OW), oy = (int)((i / F.OW) % F.OH), f = (int)(i / ((size_t)F.OW * F.OH));
+    const size_t plane = (size_t)F.OH * F.OW;
+    XwFpvProbeFetch pb;
+    pb.F = &F; pb.facing = f; pb.cell = -1; pb.mixed = 0;
+    pb.src = F.atlas64 + (size_t)F.brick_icon * 12288;
+    const uint32_t vb = xw_fpv_px(F, oy, ox, pb);
+    pmap[i] = (uint8_t)(pb.mixed || pb.cell < 0 ? 0xff : pb.cell);
+    pb.src = F.agent4 + f * 12288;
+    const uint32_t va = xw_fpv_px(F, oy, ox, pb);
+    for (int c = 0; c < 3; ++c) {
+        Tb[((size_t)f * 3 + c) * plane + (size_t)oy * F.OW + ox] = (uint8_t)(vb >> (8 * c));
+        Ta[((size_t)f * 3 + c) * plane + (size_t)oy * F.OW + ox] = (uint8_t)(va >> (8 * c));
+    }
+}
+
+// ---------------------------------------------------------------------------------------- goal icons (cv::warpAffine)
+// Fixed-point set-up of cv::warpAffine for XItem::get_item_image's matrix (xitem.cpp:47-60; OpenCV imgproc/imgwarp.cpp):
+// getRotationMatrix2D(centre (32, 32), 90 - yaw * 180 / pi, scale), the offset shift, the inversion, then for index i
+//   adelta = rint(M0 * i * 1024), bdelta = rint(M3 * i * 1024), X0 = rint((M1 * i + M2) * 1024) + 16, Y0 = rint((M4 * i + M5) * 1024) + 16.
+// Every product / sum is a separately rounded IEEE double, as in the generic C++ OpenCV is built from.
+XW_HD int xw_d2i(double v) {
+#if defined(__CUDA_ARCH__)
+    return __double2int_rn(v);
+#else
+    return (int)__builtin_lrint(v);
+#endif
+}
+XW_HD void xw_fpv_warp_coeffs(const double* yaw_cs, int yaw_idx, double scale, double offset, int i, int* ad, int* bd, int* X0, int* Y0) {
+    const double alpha = xw_dmul(yaw_cs[2 * yaw_idx], scale), beta = xw_dmul(yaw_cs[2 * yaw_idx + 1], scale);
+    const double c = 32.0;
+    const double t = xw_dmul(xw_dadd(xw_dadd(offset, xw_dmul(scale, 0.5)), -0.5), 64.0);  // (offset + scale / 2 - 0.5) * icon.cols
+    double m0 = alpha, m1 = beta, m2 = xw_dadd(xw_dadd(xw_dmul(xw_dadd(1.0, -alpha), c), -xw_dmul(beta, c)), t);
+    double m3 = -beta, m4 = alpha, m5 = xw_dadd(xw_dadd(xw_dmul(beta, c), xw_dmul(xw_dadd(1.0, -alpha), c)), t);
+    double D = xw_dadd(xw_dmul(m0, m4), -xw_dmul(m1, m3));
+#if defined(__CUDA_ARCH__)
+    D = D != 0 ? __ddiv_rn(1.0, D) : 0;
+#else
+    D = D != 0 ? 1. / D : 0;
+#endif
+    const double A11 = xw_dmul(m4, D), A22 = xw_dmul(m0, D);
+    m0 = A11; m1 = xw_dmul(m1, -D); m3 = xw_dmul(m3, -D); m4 = A22;
+    const double b1 = xw_dadd(xw_dmul(-m0, m2), -xw_dmul(m1, m5)), b2 = xw_dadd(xw_dmul(-m3, m2), -xw_dmul(m4, m5));
+    m2 = b1; m5 = b2;
+    const double di = (double)i;
+    *ad = xw_d2i(xw_dmul(xw_dmul(m0, di), 1024.0));
+    *bd = xw_d2i(xw_dmul(xw_dmul(m3, di), 1024.0));
+    *X0 = xw_d2i(xw_dmul(xw_dadd(xw_dmul(m1, di), m2), 1024.0)) + 16;
+    *Y0 = xw_d2i(xw_dmul(xw_dadd(xw_dmul(m4, di), m5), 1024.0)) + 16;
+}
+// remap, INTER_LINEAR, BORDER_CONSTANT white: destination pixel with fixed-point source coordinates X, Y (5 fractional bits)
+XW_HD uint32_t xw_fpv_warp_px(const uint8_t* icon, const int16_t* itab, int X, int Y) {
+    const int sx = X >> 5, sy = Y >> 5;
+    const int16_t* w = itab + (((Y & 31) << 5) + (X & 31)) * 4;
+    uint32_t o = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        int acc = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int yy = sy + (k >> 1), xx = sx + (k & 1);
+            const int p = (yy >= 0 && yy < 64 && xx >= 0 && xx < 64) ? icon[((yy << 6) + xx) * 3 + c] : 255;
+            acc += p * w[k];
+        }
+        o |= (uint32_t)(uint8_t)((acc + (1 << 14)) >> 15) << (8 * c);
+    }
+    return o;
+}
+
+// initInterTab2D(INTER_LINEAR, fixpt) (imgwarp.cpp): float weights * 32768 rounded to short; the only cell whose weights do
+// not add up to 32768 is (0, 0) (32768 saturates to 32767), and the correction lands on its last entry: (32767, 0, 0, 1)
+// (oracle/xw_oracle_fpv.c build_inter_tab emulates the original loop, including where it reads; the tests compare the two)
+static inline void xw_fpv_build_itab(int16_t* itab) {
+    for (int i = 0; i < 32; ++i)
+        for (int j = 0; j < 32; ++j) {
+            const float y1 = (float)i * (1.f / 32), x1 = (float)j * (1.f / 32);
+            const float wy[2] = {1.f - y1, y1}, wx[2] = {1.f - x1, x1};
+            int sum = 0;
+            for (int k = 0; k < 4; ++k) {
+                long v = __builtin_lrintf(wy[k >> 1] * wx[k & 1] * 32768.f);
+                if (v > 32767) v = 32767;
+                itab[(i * 32 + j) * 4 + k] = (int16_t)v;
+                sum += (int)v;
+            }
+            if (sum != 32768) itab[(i * 32 + j) * 4 + 3] = (int16_t)(itab[(i * 32 + j) * 4 + 3] - (sum - 32768));
+        }
+}
+
+#if defined(__CUDACC__)
+__global__ void k_fpv_build_tables(XwFpv F, uint8_t* pmap, uint8_t* Tb, uint8_t* Ta) {
+    const size_t total = (size_t)4 * F.OH * F.OW;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+        xw_fpv_table_entry(F, i, pmap, Tb, Ta);
+}
+
+// Warps the goal icons of the envs that were just reset (list mode: the step's auto-reset queue; else every env,
+// optionally filtered by mask).  One CTA per env at a time.
+__global__ void __launch_bounds__(256) k_fpv_warp_goals(XwDev d, XwFpv F, const uint8_t* mask, const int32_t* list, const int32_t* count) {
+    __shared__ int co[4][64];
+    const int cnt = list ? *count : d.n;
+    for (int i = blockIdx.x; i < cnt; i += gridDim.x) {
+        const int e = list ? list[i] : i;
+        if (!list && mask && !mask[e]) continue;
+        for (int g = 0; g < F.G; ++g) {
+            const size_t k = (size_t)g * d.n + e;
+            __syncthreads();
+            if (threadIdx.x < 64)
+                xw_fpv_warp_coeffs(d.yaw_cs, d.goal_yaw[k], d.goal_scale[k], d.goal_offset[k], threadIdx.x, &co[0][threadIdx.x],
+                                   &co[1][threadIdx.x], &co[2][threadIdx.x], &co[3][threadIdx.x]);
+            __syncthreads();
+            const uint8_t* icon = F.atlas64 + (size_t)d.goal_icon[k] * 12288;
+            uint8_t* dst = F.gcache + ((size_t)e * F.G + g) * 12288;
+            for (int p = threadIdx.x; p < 4096; p += blockDim.x) {
+                const int y = p >> 6, x = p & 63;
+                const uint32_t v = xw_fpv_warp_px(icon, F.itab, (co[2][y] + co[0][x]) >> 5, (co[3][y] + co[1][x]) >> 5);
+                dst[p * 3] = (uint8_t)v; dst[p * 3 + 1] = (uint8_t)(v >> 8); dst[p * 3 + 2] = (uint8_t)(v >> 16);
+            }
+        }
+    }
+}
+
+// Any frame size: one thread per frame pixel, straight to global memory.
+__global__ void __launch_bounds__(256) k_render_fpv_generic(XwDev d, XwFpv F, uint8_t* __restrict__ frames, size_t env_stride) {
+    __shared__ uint8_t ccode[XW_MAX_DIM * XW_MAX_DIM];
+    const int plane = F.OH * F.OW;
+    for (int e = blockIdx.x; e < d.n; e += gridDim.x) {
+        __syncthreads();
+        if ((int)threadIdx.x < F.vr) xw_fpv_cells_line(d, e, threadIdx.x, ccode);
+        __syncthreads();
+        XwFpvEnvFetch fe;
+        fe.F = &F; fe.ccode = ccode; fe.gc = F.gcache + (size_t)e * F.G * 12288; fe.facing = d.facing[e];
+        uint8_t* out = frames + (size_t)e * env_stride;
+        for (int p = threadIdx.x; p < plane; p += blockDim.x) {
+            const uint32_t v = xw_fpv_px(F, p / F.OW, p % F.OW, fe);
+            out[p] = (uint8_t)v; out[plane + p] = (uint8_t)(v >> 8); out[2 * plane + p] = (uint8_t)(v >> 16);
+        }
+    }
+}
+
+// Frame kernel for OW % 4 == 0, FB % 16 == 0.  Dynamic shared memory: frame buffer [FB] | slow list u16[OH * OW] | ccode[256].
+template <int NT>
+__global__ void __launch_bounds__(NT) k_render_fpv(XwDev d, XwFpv F, uint8_t* __restrict__ frames, size_t env_stride) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t* fb = (uint32_t*)smem;
+    uint16_t* slow = (uint16_t*)(smem + F.FB);
+    uint8_t* ccode = smem + F.FB + 2 * F.OH * F.OW;
+    __shared__ int n_slow;
+    const int WR = F.OW >> 2, plane_w = F.OH * WR, plane = F.OH * F.OW;
+    const int tid = threadIdx.x;
+    for (int e = blockIdx.x; e < d.n; e += gridDim.x) {
+        if (tid == 0) { tma_wait_read<0>(); n_slow = 0; }   // the previous frame has left the buffer
+        if (tid < F.vr) xw_fpv_cells_line(d, e, tid, ccode);
+        __syncthreads();
+        const int facing = d.facing[e];
+        const uint32_t* pm = (const uint32_t*)(F.pmap + (size_t)facing * plane);
+        const uint32_t* tb = (const uint32_t*)(F.Tb + (size_t)facing * 3 * plane);
+        const uint32_t* ta = (const uint32_t*)(F.Ta + (size_t)facing * 3 * plane);
+        // pass 1: the words of uniform cells; everything else goes on the list (one entry per pixel)
+        for (int w = tid; w < plane_w; w += NT) {
+            const uint32_t cells = pm[w];
+            uint32_t sel_w = 0, sel_b = 0, sel_a = 0, todo = 0;  // byte masks: white, brick, agent; pixels for pass 2
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const uint32_t id = (cells >> (8 * b)) & 255u;
+                const int code = id == 255u ? -1 : ccode[id];
+                const uint32_t m = 0xffu << (8 * b);
+                if (code == XW_CELL_EMPTY) sel_w |= m;
+                else if (code == XW_CELL_BLOCK) sel_b |= m;
+                else if (code == XW_CELL_AGENT) sel_a |= m;
+                else if (code != XW_FPV_BLACK) todo |= 1u << b;
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                uint32_t v = sel_w;
+                if (sel_b) v |= tb[c * plane_w + w] & sel_b;
+                if (sel_a) v |= ta[c * plane_w + w] & sel_a;
+                fb[c * plane_w + w] = v;
+            }
+            if (todo) {
+                const int k = atomicAdd(&n_slow, __popc(todo));
+                int j = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (todo & (1u << b)) slow[k + j++] = (uint16_t)(w * 4 + b);
+            }
+        }
+        __syncthreads();
+        // pass 2: exact evaluation, tap by tap
+        {
+            XwFpvEnvFetch fe;
+            fe.F = &F; fe.ccode = ccode; fe.gc = F.gcache + (size_t)e * F.G * 12288; fe.facing = facing;
+            uint8_t* fb8 = (uint8_t*)fb;
+            const int ns = n_slow;
+            for (int i = tid; i < ns; i += NT) {
+                const int p = slow[i];
+                const uint32_t v = xw_fpv_px(F, p / F.OW, p % F.OW, fe);
+                fb8[p] = (uint8_t)v; fb8[plane + p] = (uint8_t)(v >> 8); fb8[2 * plane + p] = (uint8_t)(v >> 16);
+            }
+        }
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) { tma_store_1d(frames + (size_t)e * env_stride, fb, (uint32_t)F.FB); tma_commit(); }
+    }
+    if (tid == 0) tma_wait_all<0>();
+}
+
+// --color=false: cv::cvtColor(BGR2GRAY) of the finished frame, OpenCV 3.2.0's coefficients (include/xworld_b200.h xw_config.gray)
+__global__ void k_gray(const uint8_t* __restrict__ bgr, uint8_t* __restrict__ out, int n, int plane, size_t in_stride, size_t out_stride) {
+    const size_t total = (size_t)n * plane;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t e = i / plane, p = i % plane;
+        const uint8_t* s = bgr + e * in_stride + p;
+        out[e * out_stride + p] = (uint8_t)((s[0] * 1868 + s[plane] * 9617 + s[2 * (size_t)plane] * 4899 + (1 << 13)) >> 14);
+    }
+}
+#endif  // __CUDACC__

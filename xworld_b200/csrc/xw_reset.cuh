@@ -69,7 +69,27 @@ struct XwMapCtx {
     int gcell[XW_MAX_GOALS];
     int gname[XW_MAX_GOALS];
     int gicon[XW_MAX_GOALS];
+    // first-person view only: the agent's heading and the goals' poses (set_property, xworld_env.py:207-223)
+    int facing;
+    int gyaw[XW_MAX_GOALS];
+    double gscale[XW_MAX_GOALS], goffset[XW_MAX_GOALS];
 };
+
+// IEEE double products / sums that must not be contracted into FMAs (the oracle, like OpenCV, rounds each one)
+XW_HD double xw_dmul(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+XW_HD double xw_dadd(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
 
 XW_HD bool ctx_free(const XwMapCtx& c, int x, int y) {  // (x,y,0) in env.available_grids
     if (x < 0 || y < 0 || x >= c.W || y >= c.H) return false;
@@ -185,6 +205,19 @@ XW_HD int xw_gen_map(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, int
         int nf = m_count(avail);
         if (nf == 0) return 1;
         c.agent = m_nth(avail, (int)xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_AGENT_LOC, 0), (uint32_t)nf));
+    }
+    c.facing = 1;  // Entity default yaw 1.5707963 == "down" (xworld_env.py:42, xitem.cpp:65-78)
+    if (d.vr > 0) {  // "if partially observed, perturb the objects" (xworld_env.py:207-223)
+        // agent: yaw = choice(range(-1, 3)) * PI_2: -PI_2 up, 0 right, PI_2 down, 2 PI_2 left
+        c.facing = ((int)xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_AGENT_YAW, 0), 4u) + 3) & 3;
+        for (int k = 0; k < nG; ++k) {
+            // random.uniform(a, b) = a + (b - a) * random(); random() = draw * 2^-32 (yaw: on the XW_YAW_STEPS grid)
+            const XwDraw4 u = xw_draw_block(d.seed, gid, ep, att, XW_SITE_GOAL_POSE, (uint32_t)k);
+            c.gyaw[k] = (int)(u.v0 >> 20);
+            const double scale = xw_dadd(0.5, xw_dmul(0.5, (double)u.v1 * (1.0 / 4294967296.0)));
+            c.gscale[k] = scale;
+            c.goffset[k] = xw_dmul(1.0 - scale, (double)u.v2 * (1.0 / 4294967296.0));
+        }
     }
     return 0;
 }
@@ -534,13 +567,18 @@ XW_HD void xw_reset_commit(const XwDev& d, int e, uint32_t ep, uint32_t minstd, 
         d.goal_y[(size_t)k * n + e] = (uint8_t)gy;
         d.goal_icon[(size_t)k * n + e] = on ? c.gicon[k] : 0;
         d.goal_name[(size_t)k * n + e] = on ? c.gname[k] : 0;
+        if (d.vr > 0) {
+            d.goal_yaw[(size_t)k * n + e] = (uint16_t)(on ? c.gyaw[k] : XW_YAW_STEPS / 4);
+            d.goal_scale[(size_t)k * n + e] = on ? c.gscale[k] : 1.0;
+            d.goal_offset[(size_t)k * n + e] = on ? c.goffset[k] : 0.0;
+        }
     }
     const int agx = c.agent % D + off, agy = c.agent / D + off;
     g[agy * d.W + agx] = XW_CELL_AGENT;
     d.agent_x[e] = (uint8_t)agx;
     d.agent_y[e] = (uint8_t)agy;
     if (task == XW_T3_BETWEEN && d.rules == XW_RULES_NAV3D) { o.aux1 += off; o.aux2 += off; }  // the middle cell, in map coordinates
-    d.facing[e] = 1;  // yaw 1.5707963 == "down" (xworld_env.py:42, xitem.cpp:65-78)
+    d.facing[e] = (uint8_t)c.facing;
     int32_t steps_in_task = 0;
     if (d.rules == XW_RULES_NAV2D) {
         // per-episode constants for the 2-D idle stages: goals reachable through non-block cells,
@@ -561,6 +599,7 @@ XW_HD void xw_reset_commit(const XwDev& d, int e, uint32_t ep, uint32_t minstd, 
     d.steps_in_task[e] = steps_in_task;
     d.num_steps[e] = 0;
     d.minstd[e] = minstd;
+    d.error[e] = 0;  // a new game: the invalid-action flag of the old one is gone
 }
 
 // XWorldNav._configure, curriculum != 0 (XWorldNav.py:40-56) + XWorldEnv.get_current_usage (xworld_env.py:103-110):

@@ -27,22 +27,47 @@
 // Returns true when the env must be reset (auto_reset and the episode ended).
 XW_HD bool xw_step_env(const XwDev& d, int e, int action, int act_rep, float* reward_out, int32_t* over_out) {
     const int n = d.n;
-    if (action < 0 || action >= 4) {  // CHECK_LT(action_idx, get_num_actions()) aborts in the reference
+    if (action < 0 || action >= (d.vr > 0 ? 6 : 4)) {  // CHECK_LT(action_idx, get_num_actions()) aborts in the reference
         d.error[e] = XW_ERR_INVALID_ACTION;
+        if (d.n_invalid) {
+#if defined(__CUDA_ARCH__)
+            atomicAdd(d.n_invalid, 1);
+#else
+            ++*d.n_invalid;
+#endif
+        }
         *reward_out = 0.f;
         *over_out = 0;
         return false;
     }
     uint8_t* g = d.grid + (size_t)e * d.CS;
     int ax = d.agent_x[e], ay = d.agent_y[e];
-    const int facing = d.facing[e];
-    // MOVE_UP(0,-1) MOVE_DOWN(0,+1) MOVE_LEFT(-1,0) MOVE_RIGHT(+1,0); heading codes 0 right 1 down 2 left 3 up
-    const int dx = action == 2 ? -1 : action == 3 ? 1 : 0;
-    const int dy = action == 0 ? -1 : action == 1 ? 1 : 0;
-    const int move_dir = action == 0 ? 3 : action == 1 ? 1 : action == 2 ? 2 : 0;
+    int facing = d.facing[e];  // heading codes 0 right 1 down 2 left 3 up (XItem::get_item_facing_dir, xitem.cpp:65-78)
+    int dx, dy, move_dir;
+    bool turn = false;
+    if (d.vr == 0) {
+        // MOVE_UP(0,-1) MOVE_DOWN(0,+1) MOVE_LEFT(-1,0) MOVE_RIGHT(+1,0)
+        dx = action == 2 ? -1 : action == 3 ? 1 : 0;
+        dy = action == 0 ? -1 : action == 1 ? 1 : 0;
+        move_dir = action == 0 ? 3 : action == 1 ? 1 : action == 2 ? 2 : 0;
+    } else {
+        // first-person actions (xitem.cpp:84-86,100-151): MOVE_FORWARD, MOVE_BACKWARD, MOVE_LEFT_FPV, MOVE_RIGHT_FPV relative to
+        // the heading; TURN_LEFT / TURN_RIGHT change the yaw by -/+ pi/2 and target the agent's own cell, where
+        // XMap::move_item finds the agent itself: not reachable, no contact, returns false (xmap.cpp:76-101) -- a turn is a
+        // "failed" action.  The yaw itself is a drifting double in the reference; only its facing class is ever read
+        // (get_item_facing_dir's eps 1e-4 against a drift of 1e-16 per turn), so two bits carry it here.
+        turn = action >= 4;
+        if (turn) {
+            for (int rep = 0; rep < act_rep; ++rep) facing = (facing + (action == 4 ? 3 : 1)) & 3;
+            d.facing[e] = (uint8_t)facing;
+        }
+        move_dir = action == 0 ? facing : action == 1 ? (facing + 2) & 3 : action == 2 ? (facing + 3) & 3 : (facing + 1) & 3;
+        dx = move_dir == 0 ? 1 : move_dir == 2 ? -1 : 0;
+        dy = move_dir == 1 ? 1 : move_dir == 3 ? -1 : 0;
+    }
     int num_steps = d.num_steps[e] + 1;
     int collided = XW_CELL_EMPTY, success = 0;
-    for (int rep = 0; rep < act_rep; ++rep) {
+    for (int rep = 0; rep < act_rep && !turn; ++rep) {
         int tx = ax + dx, ty = ay + dy;
         if (tx < 0 || ty < 0 || tx >= d.W || ty >= d.H) { success = 0; break; }  // blocked for all repeats
         int code = g[ty * d.W + tx];
@@ -66,7 +91,16 @@ XW_HD bool xw_step_env(const XwDev& d, int e, int action, int act_rep, float* re
             d.steps_in_task[e] = sit;
         } else {
             reward = success ? XW_R2_STEP : XW_R2_STEP_FAILED;
-            d.steps_in_task[e] += 1;
+            const int sit = d.steps_in_task[e] + 1;
+            // one_channel only (xworld_task.py:203-210): `steps_in_cur_task >= h*w / 2` (get_max_dims, Python-2 integer
+            // division): time up -> _record_failure, back to idle; no event
+            if (d.task_mode == XW_TASK_ONE_CHANNEL && sit >= d.H * d.W / 2) {
+                d.steps_in_task[e] = 0;
+                d.n_failure[e] += 1;
+                stage = XW_STAGE_IDLE;
+            } else {
+                d.steps_in_task[e] = sit;
+            }
         }
         xw_minstd_next(minstd);  // XWorldRec group's weighted task sampling: one engine draw per teach
         d.minstd[e] = minstd;
@@ -120,9 +154,11 @@ XW_HD bool xw_step_env(const XwDev& d, int e, int action, int act_rep, float* re
     }  // XW_STAGE_TERMINAL: ["terminal", 0, ""]
     int over = 0;
     if (d.max_steps > 0 && num_steps >= d.max_steps) over |= XW_MAX_STEP;
-    if (event == XW_EVENT_CORRECT_GOAL) over |= XW_SUCCESS;
-    else if (event == XW_EVENT_WRONG_GOAL) over |= XW_DEAD;
-    else if (event == XW_EVENT_TIME_UP) over |= XW_MAX_STEP;
+    if (d.task_mode == XW_TASK_LANG_ACQUISITION) {  // one_channel: "all tasks until the max steps" (xworld_simulator.cpp:192-193)
+        if (event == XW_EVENT_CORRECT_GOAL) over |= XW_SUCCESS;
+        else if (event == XW_EVENT_WRONG_GOAL) over |= XW_DEAD;
+        else if (event == XW_EVENT_TIME_UP) over |= XW_MAX_STEP;
+    }
     d.agent_x[e] = (uint8_t)ax; d.agent_y[e] = (uint8_t)ay;
     d.num_steps[e] = num_steps;
     d.stage[e] = (uint8_t)stage; d.event[e] = (uint8_t)event; d.succ[e] = (uint8_t)success;

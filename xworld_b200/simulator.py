@@ -145,11 +145,10 @@ class Simulator(object):
                 conf = json.load(f)
             if conf.get("map") != "XWorldNav":
                 raise RuntimeError("map '%s' is not implemented (XWorldNav only)" % conf.get("map"))
-            task_mode = _opt(opts, "task_mode", False, "one_channel")  # py default, py_simulator.cpp:129
-            if task_mode != "lang_acquisition":
-                raise RuntimeError("task_mode '%s' is not implemented (lang_acquisition only)" % task_mode)
-            if not _opt(opts, "color", False, False):
-                raise RuntimeError("color=False (grayscale) is not implemented; pass {'color': True}")
+            task_mode = _opt(opts, "task_mode", False, "one_channel")  # py default, py_simulator.cpp:128-130
+            if task_mode not in ("lang_acquisition", "one_channel"):
+                raise RuntimeError("task_mode '%s' is not implemented (lang_acquisition | one_channel)" % task_mode)
+            color = bool(_opt(opts, "color", False, False))            # py default, py_simulator.cpp:135
             curriculum = float(_opt(opts, "curriculum", False, 0))  # py_simulator.cpp:127
             catalog = opts.get("catalog")
             if catalog is None:
@@ -173,7 +172,9 @@ class Simulator(object):
                 context=int(_opt(opts, "context", False, 1)), visible_radius=int(_opt(opts, "visible_radius", False, 0)),
                 max_steps=int(opts.get("max_steps", 0)), max_steps_factor=int(opts.get("max_steps_factor", 10)),
                 curriculum=curriculum, curriculum_check_period=int(opts.get("curriculum_check_period", 0)),
-                start_level=int(opts.get("start_level", 0)))
+                start_level=int(opts.get("start_level", 0)),
+                task_mode=_abi.XW_TASK_ONE_CHANNEL if task_mode == "one_channel" else _abi.XW_TASK_LANG_ACQUISITION,
+                gray=0 if color else 1)
         else:
             raise RuntimeError("Unrecognized game type: " + name)
         cfg.auto_reset = int(bool(opts.get("auto_reset", False)))
@@ -336,6 +337,10 @@ class Simulator(object):
             out = np.zeros((n, _abi.XW_MAX_GOALS), np.uint8)
         elif name in ("goal_icon", "goal_name"):
             out = np.zeros((n, _abi.XW_MAX_GOALS), np.int32)
+        elif name == "goal_yaw":
+            out = np.zeros((n, _abi.XW_MAX_GOALS), np.uint16)
+        elif name in ("goal_scale", "goal_offset"):
+            out = np.zeros((n, _abi.XW_MAX_GOALS), np.float64)
         elif name in ("agent_x", "agent_y", "facing", "task", "stage", "event", "action_success", "target_mask",
                       "aux0", "aux1", "aux2", "level"):
             out = np.zeros(n, np.uint8)
@@ -362,6 +367,7 @@ class Simulator(object):
                      "aux1", "aux2", "goal_x", "goal_y", "goal_icon", "goal_name", "steps_in_task", "num_steps", "episode",
                      "n_success", "n_failure", "success_steps", "minstd", "error")
     _CURRICULUM_STATE = ("level", "check_counter", "win_len", "win_sum", "win_pos", "win_bits")
+    _FPV_STATE = ("goal_yaw", "goal_scale", "goal_offset")
     _RACE_STATE = ("pos_x", "pos_y", "angle", "steps", "state")
 
     def state_dict(self):
@@ -371,7 +377,8 @@ class Simulator(object):
         if self.cfg.game == _abi.XW_GAME_SIMPLE_GAME:
             raise RuntimeError("state_dict(): not available for simple_game")
         names = self._RACE_STATE if self.cfg.game == _abi.XW_GAME_SIMPLE_RACE else self._XWORLD_STATE + (
-            self._CURRICULUM_STATE if self.cfg.curriculum != 0 else ())
+            self._CURRICULUM_STATE if self.cfg.curriculum != 0 else ()) + (
+            self._FPV_STATE if self.cfg.visible_radius > 0 else ())
         sd = {k: self.get_field(k) for k in names}
         sd["_last_over"], sd["_last_reward"] = self._last_over.copy(), np.array(self._last_reward, np.float32)
         return sd
