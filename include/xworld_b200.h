@@ -228,6 +228,27 @@ int xw_num_steps(xw_sim* sim, int64_t* h_num_steps /* [n_envs] host */);
  * "win_pos" u8[n][5] and "win_bits" u32[n][5][7] (the windows themselves: with these a checkpoint restores everything).
  * Race: "pos_x","pos_y","angle" f32[n], "steps" i32[n], "state" f32[n][4]. */
 int xw_get_field(xw_sim* sim, const char* name, void* h_out, size_t bytes);
+/* The same for several fields with one device synchronisation (e.g. the ten fields a sentence is composed from). */
+int xw_get_fields(xw_sim* sim, int32_t n_fields, const char* const* names, void* const* h_out, const size_t* bytes);
+
+/* SimulatorInterface::get_world_dimensions (simulator_interface.cpp:163-167 -> xworld_simulator.cpp:100-104): X = width,
+ * Y = height, Z = 0 for xworld; the values are left untouched for the other games, as in the reference. */
+int xw_world_dimensions(const xw_sim* sim, double* X, double* Y, double* Z);
+
+/* XWorldSimulator::get_extra_info (xworld_simulator.cpp:495-504) for one env:
+ *   "<id>|task:<teacher sentence type>,event:<event>,height:<h>,width:<w>"
+ * the string py_simulator's get_state() splits into its "task" / "event" / "height" / "width" keys (py_simulator.cpp:276-283).
+ * <id> is the env's global id where the reference prints its process id; <h>, <w> are the world's own side (the level's,
+ * under --curriculum).  Returns the length, or a negative status.  Empty for the other games, as in the reference. */
+int xw_extra_info(xw_sim* sim, int32_t env, char* buf, size_t cap);
+
+/* SimulatorInterface::teacher_report_task_performance (simulator_interface.cpp:149-153 -> Teacher::report_task_performance,
+ * teacher.cpp:175-200): successes, failures and the steps spent in successful episodes per task class, summed over the batch
+ * since the handle was created.  Arrays of `cap` >= 5 entries; names (may be NULL) receives static strings.  Returns the number
+ * of task classes.  (Formatting the "=== S(S)/F(F) -> rate@steps" lines is the caller's: include/xworld_b200.hpp does it.) */
+int xw_task_performance(xw_sim* sim, int64_t* successes, int64_t* failures, int64_t* success_steps, int32_t cap,
+                        const char** names);
+
 /* Per-env error flags: 0, or XW_ERR_INVALID_ACTION since the env's last reset.  Copies them to h_flags[n_envs] (may be
  * NULL) and returns how many envs are flagged (< 0: a CUDA error).  Synchronises the device. */
 int32_t xw_error_flags(xw_sim* sim, int32_t* h_flags);

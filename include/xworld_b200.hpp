@@ -8,6 +8,7 @@
 //     take_actions / take_action             simulator_interface.cpp:126-137, simulator_interface.h:66-68
 //     get_state                              simulator_interface.cpp:139-143 (screen + reward of StatePacket)
 //     get_num_actions / get_lives / get_num_steps / get_screen_out_dimensions / last_action_success
+//     get_extra_info / teacher_report_task_performance / last_action / get_world_dimensions   simulator_interface.h:72-80
 // with the same argument meaning and, where the reference aborts (CHECK / LOG(FATAL)), a
 // std::runtime_error instead.  The reference class owns ONE environment; this one owns a batch of
 // n_envs (n_envs = 1 reproduces the reference's call shapes through the scalar overloads).
@@ -15,6 +16,7 @@
 #ifndef XWORLD_B200_HPP_
 #define XWORLD_B200_HPP_
 
+#include <cstdio>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -100,9 +102,17 @@ public:
                                                    bool show_screen = false) {
         if (show_screen) throw std::runtime_error("show_screen is not supported (no GUI)");
         if ((int)actions.size() != n_) throw std::runtime_error("expected one action per env");
-        check(xw_step_host(sim_, actions.data(), act_rep, reward_.data(), over_.data(), screen_.data()));
+        std::vector<float> r(n_);
+        std::vector<int32_t> o(n_);
+        const int rc = xw_step_host(sim_, actions.data(), act_rep, r.data(), o.data(), screen_.data());
+        if (rc != XW_OK && rc != XW_ERR_INVALID_ACTION) check(rc);
+        last_action_.resize(n_);
         for (int i = 0; i < n_; ++i)
-            if (actions[i] != XW_ACTION_NONE) acc_reward_[i] += reward_[i];  // an env that sat the step out keeps its totals
+            if (actions[i] != XW_ACTION_NONE) {  // an env that sat the step out keeps its totals, reward and game_over
+                reward_[i] = r[i]; over_[i] = o[i]; acc_reward_[i] += r[i];
+                last_action_[i] = std::to_string(actions[i]);  // XWorldSimulator::take_action: last_action_ (xworld_simulator.cpp:203,258)
+            }
+        if (rc == XW_ERR_INVALID_ACTION) check(rc);  // the valid envs were stepped; the reference CHECK-aborts here
         return reward_;
     }
     // the reference's scalar shape (n_envs == 1)
@@ -126,6 +136,34 @@ public:
         check(xw_get_field(sim_, "action_success", v.data(), v.size()));
         return v.at(env) != 0;
     }
+    // GameSimulator::last_action (the action id as text; xworld_simulator.cpp:203,258)
+    virtual std::string last_action(int env = 0) const { return env < (int)last_action_.size() ? last_action_[env] : std::string(); }
+    // XWorldSimulator::get_extra_info (xworld_simulator.cpp:495-504): "<id>|task:..,event:..,height:..,width:.."; "" for other games
+    virtual void get_extra_info(std::string& info, int env = 0) {
+        char buf[256];
+        const int rc = xw_extra_info(sim_, env, buf, sizeof buf);
+        if (rc < 0) check(rc);
+        info.assign(buf);
+    }
+    // SimulatorInterface::get_world_dimensions (simulator_interface.cpp:163-167): untouched unless the game is a teaching environment
+    virtual void get_world_dimensions(double& X, double& Y, double& Z) const { check(xw_world_dimensions(sim_, &X, &Y, &Z)); }
+    // Teacher::report_task_performance (teacher.cpp:175-200): the lines the reference logs, summed over the batch
+    virtual std::vector<std::string> teacher_report_task_performance() {
+        int64_t s[8], f[8], st[8];
+        const char* names[8];
+        const int nt = xw_task_performance(sim_, s, f, st, 8, names);
+        if (nt < 0) check(nt);
+        std::vector<std::string> lines;
+        for (int t = 0; t < nt; ++t) {
+            lines.push_back(std::string("=== ") + names[t] + " ===");
+            if (s[t] + f[t] == 0) continue;  // "skip task that did not occur"
+            char buf[160];
+            const double per = s[t] > 0 ? (double)st[t] / (double)s[t] : -1;
+            snprintf(buf, sizeof buf, "=== %lld(S)/%lld(F) -> %g@%g", (long long)s[t], (long long)f[t], (double)s[t] / (double)(s[t] + f[t]), per);
+            lines.push_back(buf);
+        }
+        return lines;
+    }
     float acc_reward(int env = 0) const { return acc_reward_.at(env); }
     xw_sim* handle() { return sim_; }  // for the device-pointer entry points (xw_step / xw_render)
 
@@ -141,6 +179,7 @@ protected:
     std::vector<uint8_t> screen_;
     std::vector<int32_t> over_;
     std::vector<float> reward_, acc_reward_;
+    std::vector<std::string> last_action_;
 };
 
 }  // namespace xworld_b200

@@ -218,6 +218,16 @@ int ref_wire_read_take_actions_reply(const uint8_t* body, long len, float* r, in
     return reply == "take_actions" && buf.eof() ? 0 : -1;
 }
 
+// ---- util::simple_importance_sampling (simulator_util.cpp:75-86) on a fresh thread: `n_draws` consecutive samples over the
+// accumulated weights, and the engine's raw output that each sample consumed (the thread's engine is re-seeded the same way on
+// a second fresh thread and stepped alongside)
+void ref_importance_sampling(int simulator_seed, const double* acc_weights, int n_weights, int n_draws, int* out_idx) {
+    FLAGS_simulator_seed = simulator_seed;
+    std::vector<double> acc(acc_weights, acc_weights + n_weights);
+    std::thread th([&]() { for (int i = 0; i < n_draws; ++i) out_idx[i] = util::simple_importance_sampling(acc); });
+    th.join();
+}
+
 // ---- util::get_rand_ind on fresh threads (tests/test_simulator_seed.cpp) ----
 void ref_rand_ind_threads(int simulator_seed, int n_threads, int size, int* out) {
     FLAGS_simulator_seed = simulator_seed;

@@ -17,6 +17,7 @@
 #include "../../xworld_b200/csrc/xw_step.cuh"
 #include "../../xworld_b200/csrc/xw_fpv.cuh"
 #include "../../xworld_b200/csrc/xw_fpv_host.hpp"
+#include "../../xworld_b200/csrc/xw_teacher_names.hpp"
 
 struct HostSim {
     xw_config cfg;
@@ -469,6 +470,8 @@ void hs_set_fpv_env(HostSim* s, int e, const uint8_t* grid, const int32_t* goal_
     d.facing[e] = (uint8_t)facing;
     hs_warp_goals(s, e);
 }
+
+int hs_rec_task_of_draw(uint32_t x) { return rec_task_of_draw(x); }
 
 int hs_get_field(HostSim* s, const char* name, void* out) {
     XwDev& d = s->d;

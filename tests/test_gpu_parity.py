@@ -645,3 +645,23 @@ def test_invalid_action_status(backend_cls, synthetic_catalog):
         m[5] = 1
         eng.reset(m)   # a reset clears the env's flag
         assert sim._lib.xw_error_flags(sim._h, None) == 1
+
+
+def test_debug_switches_are_compile_time_only(synthetic_catalog):
+    """XW_RENDER_DEBUG used to switch parts of k_render_sp off at run time; the shipped build must ignore it (the switches
+    exist only under -DXW_SP_DEBUG): frames stay oracle-exact with the variable set."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import oracle, parity\n"
+            "from gpu_backend import EngineBackend\n"
+            "from xworld_b200.catalog import Catalog\n"
+            "cat = Catalog.synthetic(seed=0)\n"
+            "cfg = parity.make_cfg('c3_nav2d_11x11_84')\n"
+            "eng = EngineBackend(cfg, cat, 256); orc = oracle.Oracle(cfg, cat, 256, threads=4)\n"
+            "assert eng.sim.render_kernel() == 3\n"
+            "st = parity.run_parity(eng, orc, 12, render_every=4)\n"
+            "print('frames', st['frames'])\n") % (parity.HERE + "/..", parity.HERE)
+    env = dict(__import__("os").environ, XW_RENDER_DEBUG="29")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    assert out.returncode == 0 and "frames 1024" in out.stdout, out.stdout + out.stderr

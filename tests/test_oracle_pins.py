@@ -311,3 +311,35 @@ def test_step_rules_vs_compiled_xmap(oracle_lib, synthetic_catalog):
             if nc.value:
                 assert grid[cells[ct.value]] == want_contact
         R.ref_map_destroy(m)
+
+
+def test_rec_group_task_sampling_vs_compiled_reference(oracle_lib):
+    """get_extra_info's "task:" field under walls.json needs which XWorldRec task the teacher sampled
+    (xworld_b200/csrc/xw_teacher_names.hpp rec_task_of_draw): util::simple_importance_sampling compiled from the reference
+    (simulator_util.cpp:56-86) against the restated libstdc++ arithmetic, draw by draw."""
+    import parity
+    R = _ref()
+    H = parity.HostSim.lib()
+    H.hs_rec_task_of_draw.argtypes = [C.c_uint32]
+    # which thread number will the reference's next fresh thread get?  (its counter is process-wide, simulator_util.cpp:36-47)
+    out = (C.c_int * 1)()
+    R.ref_rand_ind_threads(5, 1, 1000000, out)
+    cur = None
+    for t in range(1, 4096):
+        st = C.c_uint32(oracle_lib.xo_minstd_seed_for_thread(5, t))
+        if oracle_lib.xo_get_rand_ind(C.byref(st), 1000000) == out[0]:
+            cur = t
+            break
+    assert cur is not None
+    acc = (C.c_double * 12)(1, 2, 3, 4, 5, 6, 8, 10, 11, 12, 13, 14)
+    n = 20000
+    idx = (C.c_int * n)()
+    R.ref_importance_sampling.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    R.ref_importance_sampling(5, acc, 12, n, idx)
+    x = oracle_lib.xo_minstd_seed_for_thread(5, cur + 1)
+    seen = set()
+    for i in range(n):
+        x = (x * 16807) % 2147483647
+        assert H.hs_rec_task_of_draw(x) == idx[i], i
+        seen.add(idx[i])
+    assert seen == set(range(12))

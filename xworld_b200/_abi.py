@@ -121,7 +121,8 @@ class XwWireRequest(C.Structure):
 SYMBOLS = [
     "xw_config_init", "xw_create", "xw_destroy", "xw_last_error", "xw_reset", "xw_step", "xw_render",
     "xw_step_host", "xw_reset_host", "xw_step_hd", "xw_step_hd_async", "xw_wait_frames", "xw_sync", "xw_num_envs", "xw_num_actions", "xw_screen_dims",
-    "xw_frame_bytes", "xw_num_steps", "xw_get_field", "xw_set_field", "xw_error_flags", "xw_launch_count", "xw_render_kernel", "xw_sentence_compose",
+    "xw_frame_bytes", "xw_num_steps", "xw_get_field", "xw_set_field", "xw_error_flags", "xw_get_fields",
+    "xw_world_dimensions", "xw_extra_info", "xw_task_performance", "xw_launch_count", "xw_render_kernel", "xw_sentence_compose",
     "xw_enable_timing", "xw_render_ms",
     "xw_wire_encode_packet", "xw_wire_decode_packet", "xw_wire_parse_request", "xw_wire_compose_request", "xw_wire_reply_reset",
     "xw_wire_reply_take_actions", "xw_wire_reply_get_state", "xw_wire_reply_text",
@@ -179,6 +180,14 @@ def load():
     lib.xw_get_field.restype = C.c_int
     lib.xw_set_field.argtypes = [vp, C.c_char_p, vp, C.c_size_t]
     lib.xw_set_field.restype = C.c_int
+    lib.xw_get_fields.argtypes = [vp, i32, C.POINTER(C.c_char_p), C.POINTER(vp), C.POINTER(C.c_size_t)]
+    lib.xw_get_fields.restype = C.c_int
+    lib.xw_world_dimensions.argtypes = [vp] + [C.POINTER(C.c_double)] * 3
+    lib.xw_world_dimensions.restype = C.c_int
+    lib.xw_extra_info.argtypes = [vp, i32, C.c_char_p, C.c_size_t]
+    lib.xw_extra_info.restype = C.c_int
+    lib.xw_task_performance.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), i32, C.POINTER(C.c_char_p)]
+    lib.xw_task_performance.restype = C.c_int
     lib.xw_error_flags.argtypes = [vp, vp]
     lib.xw_error_flags.restype = i32
     lib.xw_launch_count.argtypes = [vp]

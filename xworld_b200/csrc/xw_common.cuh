@@ -65,6 +65,11 @@ struct XwDev {
     const double* yaw_cs;      // [XW_YAW_STEPS][2] cos, sin of (90 - yaw * 180 / pi) degrees, evaluated by the host's libm
     int32_t *steps_in_task, *num_steps, *episode, *n_success, *n_failure, *success_steps, *error;
     uint32_t* minstd;
+    unsigned long long* task_perf;  // [XW_N_T3][3] successes, failures, success steps per task class, summed over the batch
+                                    // (Task::obtain_performance -> Teacher::report_task_performance, teacher.cpp:175-200)
+    float* stage_rew;          // [n] the handle's own reward / game_over staging arrays (the host-buffer entry points), or NULL:
+    int32_t* stage_over;       //     a reset clears the env's slots, so that an env that then sits a step out reads "alive", 0
+    uint8_t* ctx_flag;         // [n] --context > 1 only: 1 = the env was stepped since its last render, 2 = it was reset
     // ---- curriculum (XWorldNav._configure with --curriculum > 0; all NULL / 0 when it is off) ----
     double curriculum;         // FLAGS_curriculum: (double)(float) of the option, py_simulator.cpp:127
     int32_t check_period;      // XWorldEnv.curriculum_check_period (xworld_env.py:58)

@@ -20,6 +20,7 @@
 #include "xw_step.cuh"
 #include "xw_fpv.cuh"
 #include "xw_fpv_host.hpp"
+#include "xw_teacher_names.hpp"
 
 #include <cmath>
 
@@ -139,6 +140,18 @@ struct xw_sim {
     bool timing = false;
     std::vector<cudaEvent_t> ev;
     size_t ev_used = 0;
+};
+
+// Every entry point that takes a handle runs on the handle's device and leaves the caller's current device as it found it
+// (two handles on different GPUs in one process, or a caller that switches devices between calls).
+struct DevGuard {
+    int prev = -1;
+    explicit DevGuard(const xw_sim* s) {
+        if (!s || s->cfg.game == XW_GAME_SIMPLE_GAME) return;
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != s->device) { prev = cur; cudaSetDevice(s->device); }
+    }
+    ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
 template <typename T>
@@ -301,6 +314,8 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
     rc |= dalloc(s, &d.reset_count, 2);
     rc |= dalloc(s, &d.reset_list, (size_t)n);
     rc |= dalloc(s, &d.n_invalid, 1);
+    rc |= dalloc(s, &d.task_perf, (size_t)XW_N_T3 * 3);
+    if (c.context > 1) rc |= dalloc(s, &d.ctx_flag, (size_t)n);
     if (vr > 0) {
         rc |= dalloc(s, &d.goal_yaw, (size_t)n * XW_MAX_GOALS);
         rc |= dalloc(s, &d.goal_scale, (size_t)n * XW_MAX_GOALS);
@@ -346,7 +361,9 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
     r.OH = OH; r.OW = OW; r.WR = t.WR; r.FB = t.FB; r.H = c.height; r.W = c.width;
     r.n_sr = (int)t.sr.size();
     r.n_icons = cat->n_icons; r.brick_icon = cat->brick_icon; r.agent_icon = cat->agent_icon;
+#if defined(XW_SP_DEBUG)
     { const char* ed = getenv("XW_RENDER_DEBUG"); r.debug = ed ? atoi(ed) : 0; }
+#endif
 #if defined(XW_SP_PROF)
     { unsigned int* pp = nullptr; rc |= dalloc(s, &pp, 16); r.prof = pp; }
 #endif
@@ -562,8 +579,11 @@ int xw_create(const xw_config* cfg, const xw_catalog* catalog, int32_t n_envs, i
         delete s;
         return set_err(XW_ERR_NO_DEVICE, "no CUDA device: the xworld / simple_race paths have no CPU fallback");
     }
-    if (device < 0) cudaGetDevice(&device);
+    int caller_device = -1;
+    cudaGetDevice(&caller_device);
+    if (device < 0) device = caller_device;
     s->device = device;
+    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{caller_device};  // the caller's current device is left as found
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->n_sms, cudaDevAttrMultiProcessorCount, device);
@@ -578,6 +598,7 @@ int xw_create(const xw_config* cfg, const xw_catalog* catalog, int32_t n_envs, i
 
 void xw_destroy(xw_sim* s) {
     if (!s) return;
+    DevGuard dev_guard(s);
     if (s->own_stream) cudaStreamSynchronize(s->own_stream);
 #if defined(XW_SP_PROF)
     if (s->cfg.game == XW_GAME_XWORLD && s->r.prof && s->render_sp) {  // phase clocks summed over every render launch of the handle
@@ -670,6 +691,7 @@ int32_t xw_render_kernel(const xw_sim* s) {
 int xw_enable_timing(xw_sim* s, int32_t on) { s->timing = on != 0; return 0; }
 
 double xw_render_ms(xw_sim* s, int32_t reset) {
+    DevGuard dev_guard(s);
     if (!s->timing && s->ev_used == 0) return -1.0;
     if (s->own_stream) cudaStreamSynchronize(s->own_stream);
     cudaDeviceSynchronize();
@@ -692,7 +714,7 @@ static int launch_render(xw_sim* s, uint8_t* d_frames, cudaStream_t st) {
     const size_t env_stride = (size_t)K * FBo;
     if (K > 1) {  // GameSimulator::shift_context (simulator.cpp:51-60)
         if (FBo % 16) return set_err(XW_ERR_UNSUPPORTED, "context > 1 needs a frame size divisible by 16");
-        k_shift_context<<<s->n_sms * 4, 256, 0, st>>>(d_frames, s->n, K, FBo);
+        k_shift_context<<<s->n_sms * 4, 256, 0, st>>>(d_frames, s->n, K, FBo, s->d.ctx_flag);
         s->launches++;
     }
     uint8_t* out = d_frames + (size_t)(K - 1) * FBo;  // newest frame last
@@ -746,12 +768,14 @@ static int launch_render(xw_sim* s, uint8_t* d_frames, cudaStream_t st) {
 }
 
 int xw_render(xw_sim* s, uint8_t* d_frames, void* stream) {
+    DevGuard dev_guard(s);
     if (s->cfg.game != XW_GAME_XWORLD) return set_err(XW_ERR_UNSUPPORTED, "xw_render: xworld only");
     if (!d_frames) return set_err(XW_ERR_INVALID_ARG, "null frames");
     return launch_render(s, d_frames, pick_stream(s, stream));
 }
 
 int xw_reset(xw_sim* s, const uint8_t* d_mask, void* stream) {
+    DevGuard dev_guard(s);
     cudaStream_t st = pick_stream(s, stream);
     if (s->cfg.game == XW_GAME_XWORLD) {
         k_reset<<<(s->n + 127) / 128, 128, 0, st>>>(s->d, d_mask, nullptr, nullptr);
@@ -772,6 +796,7 @@ int xw_reset(xw_sim* s, const uint8_t* d_mask, void* stream) {
 
 int xw_step(xw_sim* s, const int32_t* d_actions, int32_t act_rep, float* d_reward, int32_t* d_game_over,
             uint8_t* d_frames, void* stream) {
+    DevGuard dev_guard(s);
     if (!d_actions || !d_reward || !d_game_over) return set_err(XW_ERR_INVALID_ARG, "null buffer");
     if (act_rep < 1) return set_err(XW_ERR_INVALID_ARG, "act_rep must be >= 1");
     cudaStream_t st = pick_stream(s, stream);
@@ -818,6 +843,7 @@ static int ensure_staging(xw_sim* s, bool frames) {
         int rc = dalloc(s, &s->d_act, (size_t)s->n) | dalloc(s, &s->d_over, (size_t)s->n) | dalloc(s, &s->d_rew, (size_t)s->n) |
                  dalloc(s, &s->d_mask, (size_t)s->n);
         if (rc) return rc;
+        if (s->cfg.game == XW_GAME_XWORLD) { s->d.stage_rew = s->d_rew; s->d.stage_over = s->d_over; }
     }
     if (frames && !s->d_frames) return dalloc(s, &s->d_frames, (size_t)s->n * xw_frame_bytes(s));
     return 0;
@@ -851,6 +877,7 @@ static float sg_act(SimpleGameEnv& g, int a) {
 }
 
 int xw_reset_host(xw_sim* s, const uint8_t* h_mask, uint8_t* h_frames) {
+    DevGuard dev_guard(s);
     if (s->cfg.game == XW_GAME_SIMPLE_GAME) {
         for (int i = 0; i < s->n; ++i) {
             if (h_mask && !h_mask[i]) continue;
@@ -882,6 +909,7 @@ int xw_reset_host(xw_sim* s, const uint8_t* h_mask, uint8_t* h_frames) {
 }
 
 int xw_step_host(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float* h_reward, int32_t* h_game_over, uint8_t* h_frames) {
+    DevGuard dev_guard(s);
     if (!h_actions || !h_reward || !h_game_over) return set_err(XW_ERR_INVALID_ARG, "null buffer");
     if (s->cfg.game == XW_GAME_SIMPLE_GAME) {
         for (int i = 0; i < s->n; ++i) {
@@ -912,7 +940,7 @@ int xw_step_host(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float* h_
     if (s->cfg.game == XW_GAME_XWORLD) CUDA_TRY(cudaMemcpyAsync(s->h_invalid, s->d.n_invalid, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     if (h_frames) CUDA_TRY(cudaMemcpyAsync(h_frames, s->d_frames, (size_t)s->n * xw_frame_bytes(s), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    memcpy(h_reward, s->h_rew, sizeof(float) * s->n);
+    memcpy(h_reward, s->h_rew, sizeof(float) * s->n);   // (slots of XW_ACTION_NONE envs: their last values; 0 / alive after a reset)
     memcpy(h_game_over, s->h_over, sizeof(int32_t) * s->n);
     return invalid_status(s);
 }
@@ -953,18 +981,21 @@ int xw_step_hd_async(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float
     return step_hd(s, h_actions, act_rep, h_reward, h_game_over, d_frames, false);
 }
 int xw_wait_frames(xw_sim* s, void* stream) {
+    DevGuard dev_guard(s);
     if (!s->ev_frames) CUDA_TRY(cudaEventCreateWithFlags(&s->ev_frames, cudaEventDisableTiming));
     CUDA_TRY(cudaEventRecord(s->ev_frames, s->own_stream));
     CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, s->ev_frames, 0));
     return 0;
 }
 int xw_sync(xw_sim* s) {
+    DevGuard dev_guard(s);
     if (s->own_stream) CUDA_TRY(cudaStreamSynchronize(s->own_stream));
     if (s->copy_stream) CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
     return 0;
 }
 static int step_hd(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float* h_reward, int32_t* h_game_over, uint8_t* d_frames,
                    bool wait_frames) {
+    DevGuard dev_guard(s);
     if (!h_actions || !h_reward || !h_game_over) return set_err(XW_ERR_INVALID_ARG, "null buffer");
     if (s->cfg.game == XW_GAME_SIMPLE_GAME) return set_err(XW_ERR_UNSUPPORTED, "simple_game has no device frames");
     int rc = ensure_staging(s, false);
@@ -1023,6 +1054,7 @@ static int step_hd(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float* 
 }
 
 int xw_num_steps(xw_sim* s, int64_t* h) {
+    DevGuard dev_guard(s);
     if (s->cfg.game == XW_GAME_SIMPLE_GAME) { for (int i = 0; i < s->n; ++i) h[i] = s->sg[i].num_steps; return 0; }
     std::vector<int32_t> tmp(s->n);
     const int32_t* src = s->cfg.game == XW_GAME_XWORLD ? s->d.num_steps : s->race.steps;
@@ -1067,6 +1099,7 @@ static bool find_field(xw_sim* s, const char* name, FieldRef* f) {
 }
 
 static int field_io(xw_sim* s, const char* name, void* h, size_t bytes, bool get) {
+    DevGuard dev_guard(s);
     FieldRef f;
     if (!find_field(s, name, &f)) return set_err(XW_ERR_INVALID_ARG, "unknown field '%s'", name);
     const size_t n = s->n;
@@ -1101,6 +1134,68 @@ static int field_io(xw_sim* s, const char* name, void* h, size_t bytes, bool get
 
 int xw_get_field(xw_sim* s, const char* name, void* h_out, size_t bytes) { return field_io(s, name, h_out, bytes, true); }
 
+int xw_get_fields(xw_sim* s, int32_t n_fields, const char* const* names, void* const* h_out, const size_t* bytes) {
+    for (int i = 0; i < n_fields; ++i) {  // (field_io synchronises once: the later calls find an idle device)
+        int rc = field_io(s, names[i], h_out[i], bytes[i], true);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int xw_world_dimensions(const xw_sim* s, double* X, double* Y, double* Z) {
+    // XWorldSimulator::get_world_dimensions (xworld_simulator.cpp:100-104); other games leave the values alone
+    // (SimulatorInterface::get_world_dimensions only forwards for teaching environments, simulator_interface.cpp:163-167)
+    if (s->cfg.game == XW_GAME_XWORLD) { *X = s->cfg.width; *Y = s->cfg.height; *Z = 0; }
+    return 0;
+}
+
+int xw_extra_info(xw_sim* s, int32_t env, char* buf, size_t cap) {
+    if (!buf || cap == 0 || env < 0 || env >= s->n) return set_err(XW_ERR_INVALID_ARG, "xw_extra_info: bad argument");
+    if (s->cfg.game != XW_GAME_XWORLD) { buf[0] = 0; return 0; }  // GameSimulator::get_extra_info leaves the string empty
+    DevGuard dev_guard(s);
+    XwDev& d = s->d;
+    CUDA_TRY(cudaDeviceSynchronize());
+    uint8_t task = 0, stage = 0, event = 0, level = 0;
+    int32_t sit = 0;
+    uint32_t minstd = 0;
+    CUDA_TRY(cudaMemcpy(&task, d.task + env, 1, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&stage, d.stage + env, 1, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&event, d.event + env, 1, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&sit, d.steps_in_task + env, 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&minstd, d.minstd + env, 4, cudaMemcpyDeviceToHost));
+    if (d.level) CUDA_TRY(cudaMemcpy(&level, d.level + env, 1, cudaMemcpyDeviceToHost));
+    // the teacher sentence type = the name of the task whose sentence went into the buffer (teaching_task.cpp:118-122): a task
+    // records its name whenever no sentence has been recorded yet in this teach -- with walls.json the XWorldRec group comes
+    // second and takes the slot unless the navigation task spoke
+    const char* type;
+    if (d.rules == XW_RULES_NAV3D) type = kT3Names[task < 5 ? task : 0];
+    else {
+        const bool nav_spoke = (stage == XW_STAGE_NAVIGATION && sit == 0) || event == XW_EVENT_CORRECT_GOAL;
+        type = nav_spoke ? kT2Names[task < 4 ? task : 0] : kRecNames[rec_task_of_draw(minstd)];
+    }
+    static const char* const ev[4] = {"", "correct_goal", "wrong_goal", "time_up"};
+    const int side = d.curriculum != 0 ? 3 + level : d.H;  // xworld_.actual_height() = XWorldEnv.get_dims()
+    // the reference prints ::getpid() (one process per env); here the env's global id stands in for it
+    const int nchar = snprintf(buf, cap, "%lld|task:%s,event:%s,height:%d,width:%d", (long long)(d.gid0 + env), type, ev[event & 3], side, side);
+    if (nchar < 0 || (size_t)nchar >= cap) return set_err(XW_ERR_INVALID_ARG, "xw_extra_info: buffer too small");
+    return nchar;
+}
+
+int xw_task_performance(xw_sim* s, int64_t* successes, int64_t* failures, int64_t* success_steps, int32_t cap, const char** names) {
+    if (s->cfg.game != XW_GAME_XWORLD) return 0;
+    DevGuard dev_guard(s);
+    const int nt = s->d.rules == XW_RULES_NAV3D ? 5 : 4;
+    if (cap < nt) return set_err(XW_ERR_INVALID_ARG, "xw_task_performance: room for %d task classes needed", nt);
+    unsigned long long h[XW_N_T3 * 3];
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(h, s->d.task_perf, sizeof h, cudaMemcpyDeviceToHost));
+    for (int t = 0; t < nt; ++t) {
+        successes[t] = (int64_t)h[t * 3]; failures[t] = (int64_t)h[t * 3 + 1]; success_steps[t] = (int64_t)h[t * 3 + 2];
+        if (names) names[t] = s->d.rules == XW_RULES_NAV3D ? kT3Names[t] : kT2Names[t];
+    }
+    return nt;
+}
+
 int32_t xw_error_flags(xw_sim* s, int32_t* h_flags) {
     if (s->cfg.game == XW_GAME_SIMPLE_GAME) { if (h_flags) memset(h_flags, 0, sizeof(int32_t) * s->n); return 0; }
     std::vector<int32_t> tmp(s->n);
@@ -1111,6 +1206,7 @@ int32_t xw_error_flags(xw_sim* s, int32_t* h_flags) {
     return cnt;
 }
 int xw_set_field(xw_sim* s, const char* name, const void* h_in, size_t bytes) {
+    DevGuard dev_guard(s);
     int rc = field_io(s, name, (void*)h_in, bytes, false);
     if (rc == 0 && s->cfg.game == XW_GAME_XWORLD && s->d.vr > 0 && !strncmp(name, "goal_", 5)) {
         // the cached goal icons are a function of (icon, yaw, scale, offset): warp them again

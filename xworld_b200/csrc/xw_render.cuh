@@ -32,6 +32,12 @@
 #define XW_RENDER_MAX_GROUPS 12   // groups per CTA (named barriers 1..12)
 #define XW_TABLE_PAD 8192     // bytes past each table the compositor may read (and never use)
 
+#if defined(XW_SP_DEBUG)
+#define XW_DBG(mask) (r.debug & (mask))
+#else
+#define XW_DBG(mask) 0
+#endif
+
 struct XwTaps { const int16_t *xofs, *xa0, *xa1, *yofs, *ya0, *ya1; };  // cv::resize tables
 
 // shared-memory layout of k_render_sp (byte offsets; filled by the host with xw_render_sp_smem so that the kernel
@@ -46,7 +52,10 @@ struct XwRender {
     int32_t G, GT;            // warp groups per CTA, threads per group
     int32_t n_icons, brick_icon, agent_icon;
     int32_t n_sr;             // straddling rows
-    int32_t debug;            // tuning experiments only (XW_RENDER_DEBUG): 1 skip compose, 2 skip staging, 4 skip the frame store
+    int32_t debug;            // -DXW_SP_DEBUG builds only (tuning experiments, env XW_RENDER_DEBUG): 1 skip compose, 2 skip staging /
+                              // the white fill, 4 skip the frame store, 8 no special cells, 16 no straddling-row words, 32 no special
+                              // finish, 64 no issue.  The shipped build compiles every test of it away (XW_DBG == 0): an environment
+                              // variable can never switch parts of the frame off.
     XwTaps taps;
     const int16_t* sr;        // [n_sr] the straddling rows
     const XwU4* plan;         // [n_plan] packed items (xw_render_host.hpp)
@@ -1166,7 +1175,7 @@ k_render_sb(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride
         group_bar(bar_id, GT);
         // stage the agent's and goals' table words into the frame buffer (LDGSTS, no registers): one
         // thread per (cell, plane, word column), one 4-byte copy per row
-        for (int i = gt; i < ((r.debug & 2) ? 0 : (1 + d.G) * XW_STAGE_COLS); i += GT) {
+        for (int i = gt; i < ((XW_DBG(2)) ? 0 : (1 + d.G) * XW_STAGE_COLS); i += GT) {
             const int slot = i / XW_STAGE_COLS, col = i - slot * XW_STAGE_COLS, c = col / 3, wc = col - 3 * c;
             uint32_t w0; int nrows; const uint32_t* src;
             if (xw_stage_column(r, cells, s_cellinfo, s_special[slot], c, wc, &w0, &nrows, &src)) {
@@ -1185,10 +1194,10 @@ k_render_sb(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride
         for (int i = gt; i < r.n_plan1; i += GT) xw_compose_item<WR_T, (NT_MAX > 640)>(r, x, s_plan[i], cells, fb);
         cp_async_wait_all();
         group_bar(bar_id, GT);
-        for (int i = r.n_plan1 + gt; i < ((r.debug & 1) ? 0 : n_plan); i += GT) xw_compose_item<WR_T, (NT_MAX > 640)>(r, x, s_plan[i], cells, fb);
+        for (int i = r.n_plan1 + gt; i < ((XW_DBG(1)) ? 0 : n_plan); i += GT) xw_compose_item<WR_T, (NT_MAX > 640)>(r, x, s_plan[i], cells, fb);
         fence_async_smem();  // generic-proxy writes -> visible to the async (TMA) proxy
         group_bar(bar_id, GT);
-        if (gt == 0 && !(r.debug & 4)) {
+        if (gt == 0 && !(XW_DBG(4))) {
             tma_store_1d(frames + (size_t)env * env_stride, fb, (uint32_t)r.FB);
             tma_commit();
         }
@@ -1331,7 +1340,7 @@ k_render_sp(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride
             for (int q = 0; q < 4; ++q) {
                 const uint32_t c = (nq0 >> (8 * q)) & 0xff;
                 if (c == XW_CELL_BLOCK && 4 * lane + q < HW) m0 |= 1u << q;
-                if (c >= XW_CELL_AGENT && !(r.debug & 8)) s_special[c - XW_CELL_AGENT] = (uint8_t)(4 * lane + q);
+                if (c >= XW_CELL_AGENT && !(XW_DBG(8))) s_special[c - XW_CELL_AGENT] = (uint8_t)(4 * lane + q);
             }
         }
         if (lane + 32 < row_words) {
@@ -1340,7 +1349,7 @@ k_render_sp(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride
             for (int q = 0; q < 4; ++q) {
                 const uint32_t c = (nq1 >> (8 * q)) & 0xff;
                 if (c == XW_CELL_BLOCK && 4 * (lane + 32) + q < HW) m1 |= 1u << q;
-                if (c >= XW_CELL_AGENT && !(r.debug & 8)) s_special[c - XW_CELL_AGENT] = (uint8_t)(4 * (lane + 32) + q);
+                if (c >= XW_CELL_AGENT && !(XW_DBG(8))) s_special[c - XW_CELL_AGENT] = (uint8_t)(4 * (lane + 32) + q);
             }
         }
         // brick list: exclusive prefix of the per-lane counts (4-bit masks -> one ballot per bit); the second half
@@ -1375,7 +1384,7 @@ k_render_sp(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride
     const bool s_lane = vt < n_sl3;
     const int s_ord = vt / (3 * r.nwc), s_p = (vt - s_ord * 3 * r.nwc) / r.nwc, s_wc = vt - (s_ord * 3 + s_p) * r.nwc;
     const int r_idx = GT - 1 - vt;                        // straddling-row word (three planes): from the last thread down
-    const bool r_lane = r_idx < n_rw && !(r.debug & 16);
+    const bool r_lane = r_idx < n_rw && !(XW_DBG(16));
     const int r_q = r_lane ? r_idx / WR : 0, r_k = r_lane ? r_idx - r_q * WR : 0;
     // carried raw loads: special slot-plane (m[ROWS], pb[ROWS/4]) and straddling-row word (wa[3], wb[3], t[4]).
     // DISJ: no thread has both roles (3 * n_sslots + n_rw <= GT), so the two share one set of registers.
@@ -1420,7 +1429,7 @@ k_render_sp(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride
             if (have_next) {
                 store_cells(cur ^ 1);  // next env's cells (every warp is past the POST of env it-1, the buffer's last reader)
             }
-        } else if (w1 && !(r.debug & 2)) {  // the previous frame has left the buffer -> white again
+        } else if (w1 && !(XW_DBG(2))) {  // the previous frame has left the buffer -> white again
             if (lane == 31) {
                 tma_wait_read<0>();
                 XW_PROF(0);  // lane 63: drain wait
@@ -1437,16 +1446,16 @@ k_render_sp(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride
             }
         }
         XW_PROF(1);  // lane 0: next env's cells -> shared memory; lane 63: fill
-        if (tma_fill && !(r.debug & 2)) mbar_wait(fillbar, it & 1);
+        if (tma_fill && !(XW_DBG(2))) mbar_wait(fillbar, it & 1);
         group_bar(bar_id, GT);  // buffer white, next env's cells visible
         XW_PROF(2);  // barrier A wait
         // ---- POST of this env: finish what was issued an env ago, paint the bricks, issue for the next env
-        if (!(r.debug & 1)) {
+        if (!(XW_DBG(1))) {
             const uint8_t* s_list = cells.code + XW_CELLBUF_BYTES;
             if (r_lane) xw_sp_rword<WR_T, 1>(r, x, pg, cells, r_q, r_k, rwa, rwb, rt, fb);
-            if (s_have && !(r.debug & 32)) xw_sp_special<WR_T, XW_SP_ROWS, 1>(r, x, pg, cells, s_cell, s_wc, s_p, sm, spb, fb);
+            if (s_have && !(XW_DBG(32))) xw_sp_special<WR_T, XW_SP_ROWS, 1>(r, x, pg, cells, s_cell, s_wc, s_p, sm, spb, fb);
             XW_PROF(3);  // finish (lane 0: special slot, lane 63: straddling-row word)
-            if (!(r.debug & 16))
+            if (!(XW_DBG(16)))
                 for (int idx = GT + gt; idx < n_rw; idx += GT) {  // (more straddling-row words than lanes: in place)
                     uint32_t ta[3], tb[3], tt[4];
                     xw_sp_rword<WR_T, 0>(r, x, pg, cells, idx / WR, idx % WR, ta, tb, tt, nullptr);
@@ -1463,12 +1472,12 @@ k_render_sp(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride
         XW_PROF(4);  // brick slots
         fence_async_smem();  // generic-proxy writes -> visible to the async (TMA) proxy
         // (after the fence, which would otherwise wait for them: L2 loads for the next env and the env after it)
-        if (have_next && !(r.debug & 65)) issue(cur ^ 1);
+        if (have_next && !(XW_DBG(65))) issue(cur ^ 1);
         if (w0 && env + 2 * gstride < d.n) load_cells(env + 2 * gstride);
         XW_PROF(5);  // issue for the next env
         group_bar(bar_id, GT);
         XW_PROF(6);  // barrier C wait
-        if (tma_thread && !(r.debug & 4)) {
+        if (tma_thread && !(XW_DBG(4))) {
             tma_store_1d(frames + (size_t)env * env_stride, fb, (uint32_t)r.FB);
             tma_commit();
         }
@@ -1503,11 +1512,22 @@ __global__ void k_render_generic(XwDev d, XwRender r, uint8_t* __restrict__ fram
     }
 }
 
-// --context > 1 (GameSimulator::shift_context, simulator.cpp:51-60): slots 1..K-1 -> 0..K-2.
-__global__ void k_shift_context(uint8_t* frames, int n, int K, int FB) {
+// --context > 1 (GameSimulator::shift_context, simulator.cpp:51-60): slots 1..K-1 -> 0..K-2, for the envs that were stepped
+// since their last render (flag 1).  An env that sat the step out (flag 0, XW_ACTION_NONE / not in a reset mask) keeps its
+// history; an env that was reset (flag 2) starts with a zero-filled context (init_screen, simulator.cpp:110-113).
+// The flags are consumed here.
+__global__ void k_shift_context(uint8_t* frames, int n, int K, int FB, uint8_t* flag) {
     const int words = FB / 16;  // FB % 16 == 0 checked by the host
     for (int e = blockIdx.x; e < n; e += gridDim.x) {
+        const int f = flag ? flag[e] : 1;
+        __syncthreads();
+        if (threadIdx.x == 0 && flag) flag[e] = 0;
+        if (f == 0) continue;
         int4* base = (int4*)(frames + (size_t)e * K * FB);
+        if (f == 2) {
+            for (int i = threadIdx.x; i < (K - 1) * words; i += blockDim.x) base[i] = make_int4(0, 0, 0, 0);
+            continue;
+        }
         for (int s = 0; s + 1 < K; ++s) {
             for (int i = threadIdx.x; i < words; i += blockDim.x) base[(size_t)s * words + i] = base[(size_t)(s + 1) * words + i];
             __syncthreads();

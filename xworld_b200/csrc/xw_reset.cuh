@@ -600,6 +600,8 @@ XW_HD void xw_reset_commit(const XwDev& d, int e, uint32_t ep, uint32_t minstd, 
     d.num_steps[e] = 0;
     d.minstd[e] = minstd;
     d.error[e] = 0;  // a new game: the invalid-action flag of the old one is gone
+    if (d.stage_over) { d.stage_over[e] = 0; d.stage_rew[e] = 0.f; }
+    if (d.ctx_flag) d.ctx_flag[e] = 2;  // init_screen: the context of a new game starts zero-filled (simulator.cpp:110-113)
 }
 
 // XWorldNav._configure, curriculum != 0 (XWorldNav.py:40-56) + XWorldEnv.get_current_usage (xworld_env.py:103-110):

@@ -24,6 +24,16 @@
 #define XW_R2_STEP ((float)(-0.1))
 #define XW_R2_STEP_FAILED ((float)(-0.1 + -0.2))
 
+// Batch-wide per-task counters (report only; no state depends on them).
+XW_HD void xw_perf_add(const XwDev& d, int task, int which, int v) {
+    if (!d.task_perf) return;
+#if defined(__CUDA_ARCH__)
+    atomicAdd(d.task_perf + task * 3 + which, (unsigned long long)v);
+#else
+    d.task_perf[task * 3 + which] += (unsigned long long)v;
+#endif
+}
+
 // Returns true when the env must be reset (auto_reset and the episode ended).
 XW_HD bool xw_step_env(const XwDev& d, int e, int action, int act_rep, float* reward_out, int32_t* over_out) {
     const int n = d.n;
@@ -97,6 +107,7 @@ XW_HD bool xw_step_env(const XwDev& d, int e, int action, int act_rep, float* re
             if (d.task_mode == XW_TASK_ONE_CHANNEL && sit >= d.H * d.W / 2) {
                 d.steps_in_task[e] = 0;
                 d.n_failure[e] += 1;
+                xw_perf_add(d, d.task[e], 1, 1);
                 stage = XW_STAGE_IDLE;
             } else {
                 d.steps_in_task[e] = sit;
@@ -113,6 +124,7 @@ XW_HD bool xw_step_env(const XwDev& d, int e, int action, int act_rep, float* re
         if (sit >= side * side * d.max_steps_factor) {
             xw_record_result(d, e, d.task[e], 0);
             d.n_failure[e] += 1;
+            xw_perf_add(d, d.task[e], 1, 1);
             event = XW_EVENT_TIME_UP;
             stage = XW_STAGE_TERMINAL;
         } else {
@@ -144,10 +156,12 @@ XW_HD bool xw_step_env(const XwDev& d, int e, int action, int act_rep, float* re
             if (correct) {
                 xw_record_result(d, e, task, 1);
                 d.n_success[e] += 1; d.success_steps[e] += sit;
+                xw_perf_add(d, task, 0, 1); xw_perf_add(d, task, 2, sit);
                 event = XW_EVENT_CORRECT_GOAL; reward = XW_R3_CORRECT; stage = XW_STAGE_TERMINAL;
             } else if (wrong) {
                 xw_record_result(d, e, task, 0);
                 d.n_failure[e] += 1;
+                xw_perf_add(d, task, 1, 1);
                 event = XW_EVENT_WRONG_GOAL; reward = XW_R3_WRONG; stage = XW_STAGE_TERMINAL;
             }
         }
@@ -162,6 +176,7 @@ XW_HD bool xw_step_env(const XwDev& d, int e, int action, int act_rep, float* re
     d.agent_x[e] = (uint8_t)ax; d.agent_y[e] = (uint8_t)ay;
     d.num_steps[e] = num_steps;
     d.stage[e] = (uint8_t)stage; d.event[e] = (uint8_t)event; d.succ[e] = (uint8_t)success;
+    if (d.ctx_flag) d.ctx_flag[e] = 1;
     *reward_out = reward;
     *over_out = over;
     return d.auto_reset && over != 0;

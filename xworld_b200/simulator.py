@@ -104,6 +104,7 @@ class Simulator(object):
         self._on_gpu = cfg.game != _abi.XW_GAME_SIMPLE_GAME
         self._last_over = np.zeros(n_envs, np.int32)
         self._last_reward = np.zeros(n_envs, np.float32)
+        self._stale = False
         self._screen = None  # device tensor (gpu games) or numpy (simple_game)
         self._torch = None
         if self._on_gpu:
@@ -214,15 +215,33 @@ class Simulator(object):
                 self._check(self._lib.xw_reset(self._h, None if dm is None else dm.data_ptr(), self._stream()))
                 if self.cfg.game == _abi.XW_GAME_XWORLD:
                     self._check(self._lib.xw_render(self._h, self._screen.data_ptr(), self._stream()))
-        self._last_over[:] = 0
+                if dm is None:
+                    self._d_over.zero_()
+                    self._d_reward.zero_()
+                else:  # only the envs that were reset are "alive" again
+                    self._d_over.masked_fill_(dm.bool(), 0)
+                    self._d_reward.masked_fill_(dm.bool(), 0)
+        if mask is None:
+            self._last_over[:] = 0
+        else:
+            self._last_over[np.asarray(mask).astype(bool)] = 0
+
+    def _refresh(self):
+        """After device-side steps (take_actions with a CUDA tensor) the host copies of reward / game_over are stale."""
+        if self._stale:
+            self._last_over = self._d_over.cpu().numpy()
+            self._last_reward = self._d_reward.cpu().numpy()
+            self._stale = False
 
     def game_over(self):
         """'alive' | 'max_step' | 'dead' | 'success' | 'lost_life' (|-joined); a list when n_envs > 1."""
+        self._refresh()
         if self.n_envs == 1:
             return decode_game_over_code(int(self._last_over[0]))
         return [decode_game_over_code(int(c)) for c in self._last_over]
 
     def game_over_codes(self):
+        self._refresh()
         return self._last_over.copy()
 
     def get_num_actions(self):
@@ -230,6 +249,7 @@ class Simulator(object):
 
     def get_lives(self):
         """XWorldSimulator::get_lives: game_over() ? 0 : 1 (xworld_simulator.cpp:506)."""
+        self._refresh()
         lives = (self._last_over == 0).astype(np.int32)
         return int(lives[0]) if self.n_envs == 1 else lives
 
@@ -257,6 +277,7 @@ class Simulator(object):
             with t.cuda.device(self._dev):
                 self._check(self._lib.xw_step(self._h, a.data_ptr(), int(act_rep), self._d_reward.data_ptr(),
                                               self._d_over.data_ptr(), self._screen.data_ptr(), self._stream()))
+            self._stale = True
             return self._d_reward, self._d_over
         if isinstance(actions, dict):
             if len(actions) == 0:
@@ -266,6 +287,7 @@ class Simulator(object):
             a = np.ascontiguousarray(actions, np.int32).reshape(-1)
             if a.size != self.n_envs:
                 raise RuntimeError("expected %d actions" % self.n_envs)
+        self._refresh()
         r = np.array(self._last_reward, np.float32)  # envs given XW_ACTION_NONE keep their last reward / game_over
         o = np.array(self._last_over, np.int32)
         if not self._on_gpu:
@@ -276,8 +298,9 @@ class Simulator(object):
             with t.cuda.device(self._dev):
                 self._check(self._lib.xw_step(self._h, da.data_ptr(), int(act_rep), self._d_reward.data_ptr(),
                                               self._d_over.data_ptr(), self._screen.data_ptr(), self._stream()))
-            r = self._d_reward.cpu().numpy()
-            o = self._d_over.cpu().numpy()
+            stepped = a != _abi.XW_ACTION_NONE   # the kernel leaves the slots of the others untouched: keep the host's values
+            r = np.where(stepped, self._d_reward.cpu().numpy(), r)
+            o = np.where(stepped, self._d_over.cpu().numpy(), o)
         self._last_reward, self._last_over = r, o
         return float(r[0]) if self.n_envs == 1 else r
 
@@ -305,11 +328,46 @@ class Simulator(object):
             d["screen"] = [float(np.float32(x) * scale) for x in scr]
         if self.cfg.game == _abi.XW_GAME_XWORLD:
             d["sentence"] = self.sentences([0])[0]  # the teacher's sentence of the last teach()
-            ev = int(self.get_field("event")[0])
-            d["task"] = ""
-            d["event"] = ["", "correct_goal", "wrong_goal", "time_up"][ev]
-            d["height"], d["width"] = str(self.cfg.height), str(self.cfg.width)
+            # parse_extra_sim_info (py_simulator.cpp:222-244): "<pid>|k:v,k:v,..." -> the k:v pairs, as strings
+            for kv in self.get_extra_info(0).split("|", 1)[1].split(","):
+                k, v = kv.split(":", 1)
+                d[k] = v
         return d
+
+    def get_extra_info(self, env=0):
+        """XWorldSimulator::get_extra_info (xworld_simulator.cpp:495-504): "<id>|task:..,event:..,height:..,width:..";
+        the env's global id stands where the reference prints its process id."""
+        buf = C.create_string_buffer(256)
+        rc = self._lib.xw_extra_info(self._h, int(env), buf, len(buf))
+        if rc < 0:
+            self._check(rc)
+        return buf.value.decode()
+
+    def get_world_dimensions(self):
+        """SimulatorInterface::get_world_dimensions (simulator_interface.cpp:163-167)."""
+        X, Y, Z = C.c_double(0), C.c_double(0), C.c_double(0)
+        self._check(self._lib.xw_world_dimensions(self._h, C.byref(X), C.byref(Y), C.byref(Z)))
+        return X.value, Y.value, Z.value
+
+    def teacher_report_task_performance(self):
+        """Teacher::report_task_performance (teacher.cpp:175-200): the lines the reference logs, returned (and the raw
+        counters): "=== <task> ===" / "=== <S>(S)/<F>(F) -> <rate>@<steps per success>" for every task class that occurred."""
+        i64 = C.c_int64 * 8
+        s_, f_, st_ = i64(), i64(), i64()
+        names = (C.c_char_p * 8)()
+        nt = self._lib.xw_task_performance(self._h, s_, f_, st_, 8, names)
+        if nt < 0:
+            self._check(nt)
+        lines, raw = [], {}
+        for t in range(nt):
+            name = names[t].decode()
+            raw[name] = (int(s_[t]), int(f_[t]), int(st_[t]))
+            lines.append("=== %s ===" % name)
+            if s_[t] + f_[t] == 0:
+                continue
+            per = float(st_[t]) / s_[t] if s_[t] > 0 else -1
+            lines.append("=== %d(S)/%d(F) -> %g@%g" % (s_[t], f_[t], float(s_[t]) / (s_[t] + f_[t]), per))
+        return lines, raw
 
     # ------------------------------------------------------------------ teacher language channel
     def sentences(self, envs=None):
@@ -323,13 +381,18 @@ class Simulator(object):
         One read-back of the small state fields for the whole batch; strings are built on the host."""
         if self.cfg.game != _abi.XW_GAME_XWORLD:
             raise RuntimeError("sentences(): xworld only")
-        f = {k: self.get_field(k) for k in SENTENCE_FIELDS}
+        f = self.get_fields(SENTENCE_FIELDS)
         return [sentence_for_state(self._lib, self.cfg, self.catalog, self.cfg.env_id_offset + e,
                                    {k: f[k][e] for k in SENTENCE_FIELDS})
                 for e in (range(self.n_envs) if envs is None else envs)]
 
     # ------------------------------------------------------------------ state access
     def get_field(self, name):
+        out = self._field_buffer(name)
+        self._check(self._lib.xw_get_field(self._h, name.encode(), out.ctypes.data, out.nbytes))
+        return out
+
+    def _field_buffer(self, name):
         n = self.n_envs
         if name == "grid":
             out = np.zeros((n, self.cfg.height * self.cfg.width), np.uint8)
@@ -354,8 +417,19 @@ class Simulator(object):
             out = np.zeros(n, np.float32)
         else:
             out = np.zeros(n, np.int32)
-        self._check(self._lib.xw_get_field(self._h, name.encode(), out.ctypes.data, out.nbytes))
         return out
+
+    def get_fields(self, names):
+        """Several fields with one device synchronisation (xw_get_fields)."""
+        outs = {}
+        for k in names:
+            outs[k] = self._field_buffer(k)
+        n = len(names)
+        c_names = (C.c_char_p * n)(*[k.encode() for k in names])
+        c_ptrs = (C.c_void_p * n)(*[outs[k].ctypes.data for k in names])
+        c_bytes = (C.c_size_t * n)(*[outs[k].nbytes for k in names])
+        self._check(self._lib.xw_get_fields(self._h, n, c_names, c_ptrs, c_bytes))
+        return outs
 
     def set_field(self, name, value):
         cur = self.get_field(name)

@@ -156,6 +156,7 @@ class BatchClient(object):
             self.socks.append(s)
         self.bufs = [b"" for _ in ports]
         self.open = [True] * len(ports)
+        self.errors = []  # (env, reason) of connections that were dropped for a malformed / invalid request
         n = sim.n_envs
         self.reward = np.zeros(n, np.float32)
         self.over = np.zeros(n, np.int32)
@@ -165,11 +166,15 @@ class BatchClient(object):
         self.batches = 0
 
     # one complete message of connection i, or None
+    MAX_FRAME = 1 << 24  # a request is a command word, two scalars and a small action packet; the peer's 64-bit size is not trusted
+
     def _pop(self, i):
         b = self.bufs[i]
         if len(b) < 8:
             return None
         (size,) = struct.unpack("<Q", b[:8])
+        if size > self.MAX_FRAME:
+            raise RuntimeError("frame of %d bytes" % size)
         if len(b) < 8 + size:
             return None
         self.bufs[i] = b[8 + size:]
@@ -192,8 +197,7 @@ class BatchClient(object):
         sim = self.sim
         if sim.cfg.game != _abi.XW_GAME_XWORLD:
             return ""
-        ev = ["", "correct_goal", "wrong_goal", "time_up"][int(sim.get_field("event")[e])]
-        return "%d|task:,event:%s,height:%d,width:%d" % (sim.cfg.env_id_offset + e, ev, sim.cfg.height, sim.cfg.width)
+        return sim.get_extra_info(e)
 
     def serve(self):
         """SimulatorClient::simulation_loop for every connection, until each has been told to "stop" (or closed)."""
@@ -204,21 +208,58 @@ class BatchClient(object):
         h, w, c, _ctx = sim.get_screen_out_dimensions()
         if sim.cfg.game == _abi.XW_GAME_SIMPLE_GAME:
             h, c = 1, 1
-        while any(self.open):
-            for key, _ in sel.select():
-                i = key.data
-                data = self.socks[i].recv(1 << 20)
-                if not data:
-                    self.open[i] = False
-                    sel.unregister(self.socks[i])
-                    continue
-                self.bufs[i] += data
+        n_act = sim.get_num_actions()
+
+        def drop(i, why):
+            """One misbehaving connection is closed; the other envs keep being served."""
+            self.errors.append((i, why))
+            self.open[i] = False
+            try:
+                sel.unregister(self.socks[i])
+            except (KeyError, ValueError):
+                pass
+            self.socks[i].close()
+
+        def pending():
+            """One complete, valid request per open connection, if its buffer already holds one."""
             reqs = {}
             for i in range(n):
-                if self.open[i] and i not in reqs:
+                if not self.open[i]:
+                    continue
+                try:
                     body = self._pop(i)
-                    if body is not None:
-                        reqs[i] = (parse_request(body), body)
+                    if body is None:
+                        continue
+                    r = parse_request(body)
+                    if r["cmd"] == "take_actions":
+                        acts = r["actions"].get("action")
+                        if acts is None or len(acts) < 1:
+                            raise RuntimeError("take_actions without an 'action'")
+                        if r["act_rep"] < 1:
+                            raise RuntimeError("act_rep %d" % r["act_rep"])
+                        if not 0 <= int(acts[0]) < n_act:
+                            raise RuntimeError("action %d outside [0, %d)" % (int(acts[0]), n_act))
+                    reqs[i] = (r, body)
+                except Exception as ex:  # malformed / oversized / invalid: this connection only
+                    drop(i, str(ex))
+            return reqs
+
+        while any(self.open):
+            reqs = pending()  # requests already buffered (e.g. "stop" sent right behind another message) come first
+            if not reqs:
+                for key, _ in sel.select():
+                    i = key.data
+                    try:
+                        data = self.socks[i].recv(1 << 20)
+                    except OSError as ex:
+                        drop(i, str(ex))
+                        continue
+                    if not data:
+                        self.open[i] = False
+                        sel.unregister(self.socks[i])
+                        continue
+                    self.bufs[i] += data
+                reqs = pending()
             if not reqs:
                 continue
             # ---- one masked reset for every "reset"
@@ -271,5 +312,8 @@ class BatchClient(object):
                     continue
                 else:  # "report_perf" and anything unknown: deliver_msg sends the received body back
                     out = struct.pack("<Q", len(body)) + body
-                self.socks[i].sendall(out)
+                try:
+                    self.socks[i].sendall(out)
+                except OSError as ex:
+                    drop(i, str(ex))
         sel.close()
