@@ -305,66 +305,129 @@ def bench_race(args, rank, world, local_rank):
     return 0
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--envs-per-gpu", type=int, default=0, help="default: the workload's (65536; c4: 32768)")
-    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["c5"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
-    args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    threads = os.cpu_count() or 1
-    if args.workload == "c5":
-        if args.envs_per_gpu <= 0:
-            args.envs_per_gpu = 1 << 20
-        return bench_race(args, rank, world, local_rank)
-    wl = select_workload(args.workload)
-    if args.envs_per_gpu <= 0:
-        args.envs_per_gpu = wl["envs"]
-    config = {"workload": WORKLOAD_NAME, "map": wl["map"], "obs": "%dx%dx3 u8 (B,G,R planes)" % (SIDE, SIDE), "rules": wl["rules"],
-              "envs_per_gpu": args.envs_per_gpu, "auto_reset": True, "max_steps": wl["max_steps"], "actions": "iid uniform{0..%d}" % (5 if wl["cfg"].get("visible_radius") else 3),
-              "l2": "each step writes %.2f GB of frames per GPU (>> 126 MB L2), so no L2 flush is needed" % (
-                  args.envs_per_gpu * 3 * SIDE * SIDE / 1e9),
-              "bytes_per_env_step": BYTES_PER_ENV_STEP}
+def cv2_faithful_arm(sample_envs, steps):
+    """BASELINE.md §4's "faithful call sequence" leg: the reference's render pipeline with the real OpenCV, one thread --
+    per frame a white canvas, per ITEM cv::warpAffine + copyTo (xitem.cpp:47-60, xmap.cpp:129-146: every wall brick, every
+    frame), the identity cv::resize + HWC->CHW repack (xworld_simulator.cpp:287-307), the CHW->HWC repack + cv::resize +
+    HWC->CHW repack (:508-545); the step / teacher comes from the oracle port.  None when cv2 is not importable."""
+    try:
+        import cv2
+    except ImportError:
+        return None
+    import math
+    import numpy as np
+    import oracle
+    from xworld_b200 import _abi
+    from xworld_b200.catalog import Catalog
+    cv2.setNumThreads(1)
+    cfg = _abi.default_config(**WORKLOAD)
+    cat = Catalog.synthetic(seed=0)
+    orc = oracle.Oracle(cfg, cat, sample_envs, threads=1)
+    orc.reset()
+    H, W = cfg.height, cfg.width
+    oh, ow = orc.out_h, orc.out_w
+    rng = np.random.RandomState(0)
+    n_act = 6 if cfg.visible_radius > 0 else 4
+    rot = cv2.getRotationMatrix2D((32.0, 32.0), 90 - 1.5707963 * 180 / math.pi, 1.0)
 
-    if args.impl == "reference":
-        if rank != 0:
-            return 0
-        sample = 1024
-        steps = max(1, args.steps)
-        steps = min(steps, 40)  # bounded: ~2-3k frames/s on 8 cores
-        v, dt = cpu_reference_arm(steps, min(args.warmup, 3), sample, threads)
-        line = {"impl": "reference", "metric": "env_steps_per_sec", "value": v, "unit": "env-steps/s",
-                "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": dt / steps * 1e3,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": dict(config, sample="%d envs per step (bounded sample of the 65536-env workload)" % sample),
-                "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port",
-                                 "sample": "%d envs x %d steps, OpenMP over envs" % (sample, steps)},
-                "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
-        return 0
+    def frame(e):
+        world = np.full((H * 64, W * 64, 3), 255, np.uint8)
+        for i in range(H):
+            for j in range(W):
+                code = e.grid[i * W + j]
+                if code == 0:
+                    continue
+                icon = cat.brick_icon if code == 1 else cat.agent_icon if code == 2 else e.goal_icon[code - 3]
+                img = cv2.warpAffine(cat.atlas64[icon].copy(), rot, (64, 64), flags=cv2.INTER_LINEAR,
+                                     borderMode=cv2.BORDER_CONSTANT, borderValue=(255, 255, 255))
+                world[i * 64:(i + 1) * 64, j * 64:(j + 1) * 64] = img
+        screen = cv2.resize(world, (W * 64, H * 64), interpolation=cv2.INTER_LINEAR)
+        planar = np.ascontiguousarray(screen.transpose(2, 0, 1))
+        img = np.ascontiguousarray(planar.transpose(1, 2, 0))
+        out = cv2.resize(img, (ow, oh), interpolation=cv2.INTER_LINEAR)
+        return np.ascontiguousarray(out.transpose(2, 0, 1))
 
+    t0 = time.perf_counter()
+    for s in range(steps):
+        orc.step(rng.randint(0, n_act, sample_envs).astype(np.int32), render=False)
+        for e in orc.envs:
+            frame(e)
+    dt = time.perf_counter() - t0
+    return sample_envs * steps / dt, dt
+
+
+def cpu_legs(threads):
+    """cpu_baseline: the all-core oracle port (the figure), plus the legs BASELINE.md §4 asks for."""
+    import numpy as np
+    import oracle
+    from xworld_b200 import _abi
+    from xworld_b200.catalog import Catalog
+    sample, ksteps = 1024, 20
+    v, dt = cpu_reference_arm(ksteps, 2, sample, threads)
+    out = {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port",
+           "sample": "%d envs x %d steps of the same workload (%.1f s), oracle C port (integer restatement of the reference's "
+                     "OpenCV pipeline), OpenMP over envs on all host threads" % (sample, ksteps, dt)}
+    v1, dt1 = cpu_reference_arm(6, 1, 128, 1)
+    out["one_core"] = {"value": v1, "unit": "env-steps/s", "cores": 1, "sample": "128 envs x 6 steps (%.1f s), the same C port, one thread" % dt1}
+    cfg = _abi.default_config(**WORKLOAD)
+    orc = oracle.Oracle(cfg, Catalog.synthetic(seed=0), 4096, threads=1)
+    orc.reset()
+    rng = np.random.RandomState(0)
+    n_act = 6 if cfg.visible_radius > 0 else 4
+    acts = [rng.randint(0, n_act, 4096).astype(np.int32) for _ in range(4)]
+    t0 = time.perf_counter()
+    for i in range(50):
+        orc.step(acts[i % 4], render=False)
+    dt2 = time.perf_counter() - t0
+    out["step_teacher_only"] = {"value": 4096 * 50 / dt2, "unit": "env-steps/s", "cores": 1,
+                                "sample": "4096 envs x 50 steps, no render: move + collision + the teacher's rules as fixed C "
+                                          "(the reference runs them in embedded CPython through Boost.Python, which cannot run "
+                                          "on this box: no Python 2.7 / Boost; SURVEY §6 estimates 10^2-10^3 steps/s/core for it)"}
+    cv = cv2_faithful_arm(16, 2)
+    out["cv2_faithful"] = None if cv is None else {
+        "value": cv[0], "unit": "env-steps/s", "cores": 1,
+        "sample": "16 envs x 2 steps (%.1f s): real OpenCV (cv2), the reference's call sequence incl. one warpAffine per item "
+                  "per frame and the repacks (vectorised), one thread" % cv[1]}
+    return out
+
+
+def lib_sha256():
+    import hashlib
+    from xworld_b200 import _abi
+    with open(_abi.LIB_PATH, "rb") as f:
+        return hashlib.sha256(f.read()).hexdigest()
+
+
+def traffic_for(key, n):
+    """roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of the render kernel from the ncu --set full capture
+    recorded in profiles/render_traffic.json -- only if it was taken on THIS binary (sha256 of libxworld_b200.so) at this size."""
+    tp = os.path.join(ROOT, "profiles", "render_traffic.json")
+    if not os.path.exists(tp):
+        return None, "no capture on record"
+    with open(tp) as f:
+        rec = json.load(f)
+    ent = rec.get("workloads", {}).get(key)
+    if not ent or ent.get("envs") != n:
+        return None, "no capture of this workload / size on record"
+    if rec.get("lib_sha256") != lib_sha256():
+        return None, "the capture on record (%s) was taken on another build of libxworld_b200.so" % rec.get("capture")
+    return ent["dram_bytes_per_launch"], rec.get("capture")
+
+
+KERNEL_NAMES = {3: "k_render_sp", 1: "k_render_sb", 2: "k_render", 0: "k_render_generic", 4: "k_render_fpv_generic", 5: "k_render_fpv"}
+
+
+def run_xworld(key, n, steps, warmup, rank, world, local_rank, dist, dev, sampler=None, e2e_mode="full"):
+    """One XWorld2D workload on this rank's GPU: K timed steps with inputs in HBM (CUDA events, barrier on both sides, max
+    over ranks), the render / step+reset kernel times from the library's own events, and the end-to-end loop through the
+    host-buffer C ABI.  Returns the fields of the JSON line (rank 0) or None."""
     import numpy as np
     import torch
     from xworld_b200 import _abi
     from xworld_b200.catalog import Catalog
     from xworld_b200.sharding import gather_throughput
     from xworld_b200.simulator import Simulator
-
-    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-    n = args.envs_per_gpu
+    wl = select_workload(key)
     cfg = _abi.default_config(**WORKLOAD)
     cfg.env_id_offset = rank * n  # contiguous global env ids: the union of ranks is one logical batch
     sim = Simulator("xworld", cfg, Catalog.synthetic(seed=0), n, local_rank)
@@ -378,6 +441,15 @@ def main():
     over = torch.zeros(n, dtype=torch.int32, device=dev)
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     sim.reset_game()
+    dephased = None
+    if wl["max_steps"] > 0:
+        # Episodes of the walls.json rules end by --max_steps only: started together, all 65,536 envs would reset in the same
+        # step once every 242 and never inside a short timed region.  Start them out of phase instead (env i has already
+        # played (i * 97) mod 242 steps), so that every step re-generates n / 242 maps: the steady state of a long run.
+        ns = ((np.arange(n, dtype=np.int64) + rank * n) * 97 % wl["max_steps"]).astype(np.int32)
+        sim.set_field("num_steps", ns)
+        dephased = "num_steps of env i starts at (i * 97) mod %d: ~%d of the %d envs end an episode and are re-generated in every step" % (
+            wl["max_steps"], n // wl["max_steps"], n)
 
     def step(i):
         rc = lib.xw_step(h, acts[i % 8].data_ptr(), 1, reward.data_ptr(), over.data_ptr(), frames.data_ptr(), stream)
@@ -389,43 +461,45 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()  # before the warm-up: nothing but the warm-up may sit between it and the timed region
-    for i in range(args.warmup):
+    for i in range(warmup):
         step(i)
     barrier()
+    ep0 = int(sim.get_field("episode").astype(np.int64).sum())
     lib.xw_enable_timing(h, 1)
     lib.xw_render_ms(h, 1)
+    lib.xw_step_reset_ms(h, 1)
     launches0 = sim.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    sampler.mark_begin()
+    if sampler:
+        sampler.mark_begin()
     e0.record()
-    for i in range(args.steps):
+    for i in range(steps):
         step(i)
     e1.record()
     barrier()
-    sampler.mark_end()
+    if sampler:
+        sampler.mark_end()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
     launches = sim.launch_count() - launches0
     render_ms = lib.xw_render_ms(h, 1)
+    step_reset_ms = lib.xw_step_reset_ms(h, 1)
     lib.xw_enable_timing(h, 0)
+    resets = int(sim.get_field("episode").astype(np.int64).sum()) - ep0
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    total_steps, _, per_rank = gather_throughput(n * args.steps, int(ms * 1e6), device=dev)
+    total_steps, _, per_rank = gather_throughput(n * steps, int(ms * 1e6), device=dev)
     value = total_steps / (ms_max / 1e3)
 
     # ---- end to end through the host-buffer C ABI (pinned host actions in, host reward/over out)
     e2e = None
-    if not args.no_e2e:
+    if e2e_mode != "none":
         h_act = [torch.randint(0, n_act, (n,), dtype=torch.int32).pin_memory() for _ in range(4)]
         h_rew = torch.zeros(n, dtype=torch.float32).pin_memory()
         h_over = torch.zeros(n, dtype=torch.int32).pin_memory()
-        k2 = max(10, args.steps)  # the same K steps as the device-resident measurement
+        k2 = max(10, steps)  # the same K steps as the device-resident measurement
         for i in range(5):
             lib.xw_step_hd(h, h_act[i % 4].data_ptr(), 1, h_rew.data_ptr(), h_over.data_ptr(), frames.data_ptr())
         barrier()
@@ -439,9 +513,10 @@ def main():
         if dist is not None:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": n * world * k2 / float(tt.item()), "unit": "env-steps/s", "h2d_bytes_per_step": 4 * n,
-               "d2h_bytes_per_step": 8 * n, "steps": k2,
-               "what": "xw_step_hd: pinned host actions -> H2D, step+reset+render kernels, reward+game_over D2H, "
-                       "stream sync; frames stay in HBM (consumer = co-located learner)"}
+               "d2h_bytes_per_step": 8 * n + 4, "steps": k2,
+               "what": "xw_step_hd: pinned host actions -> H2D, step+reset+render kernels, reward+game_over (+ the invalid-action "
+                       "count) D2H, stream sync; frames stay in HBM (consumer = co-located learner)"}
+    if e2e_mode == "full":
         # the pipelined form of the same call (xw_step_hd_async): the host still waits for every step's reward / game_over
         # before it issues the next step, but not for the frames, which a co-located learner consumes in stream order
         # (two frame buffers, alternating); everything is complete (xw_sync) inside the timed region
@@ -477,39 +552,118 @@ def main():
             e2e["with_frames_to_host"] = {"value": n * k3 / dt, "unit": "env-steps/s",
                                           "d2h_bytes_per_step": 8 * n + n * 3 * SIDE * SIDE}
             del hf
+    kernel = KERNEL_NAMES.get(sim.render_kernel(), "k_render")
+    del sim
+    if rank != 0:
+        return None
+    peak, peak_src = hbm_peak()
+    achieved = BYTES_PER_ENV_STEP * n / (render_ms * 1e-3) / 1e9 if render_ms and render_ms > 0 else None
+    traffic, traffic_src = traffic_for(key, n)
+    return {
+        "value": value, "ms_per_step": ms_max / steps, "steps": steps, "warmup": warmup,
+        "config": {"workload": WORKLOAD_NAME, "map": wl["map"], "obs": "%dx%dx3 u8 (B,G,R planes)" % (SIDE, SIDE), "rules": wl["rules"],
+                   "envs_per_gpu": n, "auto_reset": True, "max_steps": wl["max_steps"],
+                   "actions": "iid uniform{0..%d}" % (n_act - 1), "dephased": dephased,
+                   "l2": "each step writes %.2f GB of frames per GPU (>> 126 MB L2), so no L2 flush is needed" % (n * 3 * SIDE * SIDE / 1e9),
+                   "bytes_per_env_step": BYTES_PER_ENV_STEP},
+        "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": peak_src, "kernel_ms": render_ms, "step_reset_ms": step_reset_ms,
+                     "resets_per_step": resets / float(steps),
+                     "kernel_share_of_step": (render_ms / (ms / steps)) if render_ms else None,
+                     "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n},
+        "gpu_launches": launches, "per_rank": per_rank, "e2e": e2e,
+    }
 
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=0, help="default: the workload's (65536; c4: 32768)")
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["c5"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short runs of the other BASELINE configs in the default line")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    threads = os.cpu_count() or 1
+    if args.workload == "c5":
+        if args.envs_per_gpu <= 0:
+            args.envs_per_gpu = 1 << 20
+        return bench_race(args, rank, world, local_rank)
+    wl = select_workload(args.workload)
+    if args.envs_per_gpu <= 0:
+        args.envs_per_gpu = wl["envs"]
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        sample = 1024
+        steps = max(1, args.steps)
+        steps = min(steps, 40)  # bounded: ~2-3k frames/s on 8 cores
+        v, dt = cpu_reference_arm(steps, min(args.warmup, 3), sample, threads)
+        config = {"workload": WORKLOAD_NAME, "map": wl["map"], "obs": "%dx%dx3 u8 (B,G,R planes)" % (SIDE, SIDE), "rules": wl["rules"],
+                  "envs_per_gpu": args.envs_per_gpu, "auto_reset": True, "max_steps": wl["max_steps"],
+                  "bytes_per_env_step": BYTES_PER_ENV_STEP,
+                  "sample": "%d envs per step (bounded sample of the %d-env workload)" % (sample, args.envs_per_gpu)}
+        line = {"impl": "reference", "metric": "env_steps_per_sec", "value": v, "unit": "env-steps/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": dt / steps * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port",
+                                 "sample": "%d envs x %d steps, OpenMP over envs" % (sample, steps)},
+                "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # before the warm-up: nothing but the warm-up may sit between it and the timed region
+    res = run_xworld(args.workload, args.envs_per_gpu, args.steps, args.warmup, rank, world, local_rank, dist, dev,
+                     sampler=sampler if rank == 0 else None, e2e_mode="none" if args.no_e2e else "full")
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- the other BASELINE configurations, a few steps each, in the same line (configs[1], configs[3] at 32,768 envs per GPU
+    #      = 262,144 over 8 GPUs, the first-person view of configs[2]'s map, configs[4]); every rank runs them, rank 0 reports
+    others = {}
+    if args.workload == "c3" and not args.no_configs:
+        for key in ("c2", "c4", "fpv"):
+            r = run_xworld(key, WORKLOADS[key]["envs"], 40, 8, rank, world, local_rank, dist, dev,
+                           e2e_mode="none" if args.no_e2e else "short")
+            if rank == 0:
+                others[key] = {"value": r["value"], "unit": "env-steps/s", "ms_per_step": r["ms_per_step"], "steps": r["steps"],
+                               "workload": r["config"]["workload"], "envs_per_gpu": r["config"]["envs_per_gpu"],
+                               "roofline": r["roofline"], "e2e": r["e2e"], "gpu_launches": r["gpu_launches"]}
+        select_workload(args.workload)
     if rank != 0:
         if dist is not None:
             dist.barrier()
             dist.destroy_process_group()
         return 0
-    peak, peak_src = hbm_peak()
-    achieved = BYTES_PER_ENV_STEP * n / (render_ms * 1e-3) / 1e9 if render_ms and render_ms > 0 else None
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "render_traffic.json")
-    if os.path.exists(tp):
-        with open(tp) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch") if (args.workload == "c3" and n == 65536) else None
     line = {
-        "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
-        "roofline": {"bound": "hbm", "kernel": {3: "k_render_sp", 1: "k_render_sb", 2: "k_render", 0: "k_render_generic",
-                                                 4: "k_render_fpv_generic", 5: "k_render_fpv"}.get(
-                         sim.render_kernel(), "k_render"), "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
-                     "kernel_ms": render_ms, "kernel_share_of_step": (render_ms / (ms / args.steps)) if render_ms else None,
-                     "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n},
-        "gpu_launches": launches, "clocks": clocks, "per_rank": per_rank,
+        "metric": "env_steps_per_sec", "value": res["value"], "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": res["config"], "roofline": res["roofline"],
+        "gpu_launches": res["gpu_launches"], "clocks": clocks, "per_rank": res["per_rank"],
     }
-    if e2e:
-        line["e2e"] = e2e
+    if res["e2e"]:
+        line["e2e"] = res["e2e"]
+    if others:
+        line["configs"] = others
     if world == 1 and not args.no_cpu_baseline:
-        sample, ksteps = 1024, 20
-        v, dt = cpu_reference_arm(ksteps, 2, sample, threads)
-        line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port",
-                                "sample": "%d envs x %d steps of the same workload (%.1f s), oracle C port, OpenMP" % (
-                                    sample, ksteps, dt)}
+        line["cpu_baseline"] = cpu_legs(threads)
     print(json.dumps(line))
     if dist is not None:
         dist.barrier()

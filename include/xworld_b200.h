@@ -332,6 +332,8 @@ int32_t xw_render_kernel(const xw_sim* sim);
  * call with reset != 0.  Returns <0 if timing is disabled.  xw_enable_timing(sim, 1) first. */
 int xw_enable_timing(xw_sim* sim, int32_t on);
 double xw_render_ms(xw_sim* sim, int32_t reset);
+/* The same for the launches in front of the render kernel: k_step + the auto-reset launch (+ the first-person goal warp). */
+double xw_step_reset_ms(xw_sim* sim, int32_t reset);
 
 #ifdef __cplusplus
 }

@@ -665,3 +665,51 @@ def test_debug_switches_are_compile_time_only(synthetic_catalog):
     env = dict(__import__("os").environ, XW_RENDER_DEBUG="29")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
     assert out.returncode == 0 and "frames 1024" in out.stdout, out.stdout + out.stderr
+
+
+def test_partial_batches_bookkeeping_and_context_history(synthetic_catalog):
+    """game_over / lives of envs outside a reset mask stay what they were; an env that was reset and then sits a
+    step out reads "alive"; the device-tensor path refreshes the host's view; with --context > 1 an env that sits a step out
+    keeps its frame history and a masked / auto reset starts from a zero-filled context (simulator.cpp:110-113)."""
+    import torch
+    n = 64
+    cfg = parity.make_cfg("c2_nav3d_7x7_84", max_steps=3, context=3)
+    sim = Simulator("xworld", cfg, synthetic_catalog, n, -1)
+    sim.reset_game()
+    for s in range(3):
+        sim.take_actions(np.full(n, s % 4, np.int32))
+    assert all("max_step" in g for g in sim.game_over())
+    mask = np.zeros(n, np.uint8)
+    mask[::2] = 1
+    before = sim.screen().cpu().numpy().reshape(n, 3, 3, 84, 84).copy()
+    sim.reset_game(mask)
+    go = sim.game_over()
+    assert all(g == "alive" for g in go[::2]) and all("max_step" in g for g in go[1::2])
+    assert (sim.get_lives()[::2] == 1).all() and (sim.get_lives()[1::2] == 0).all()
+    scr = sim.screen().cpu().numpy().reshape(n, 3, 3, 84, 84)
+    assert (scr[::2, :2] == 0).all() and (scr[::2, 2] != 0).any()        # reset envs: zero-filled history + the new frame
+    assert (scr[1::2] == before[1::2]).all()                             # the others: history untouched by the re-render
+    # the reset envs sit a step out, the others step: reset envs still read "alive" and keep their (zero) history
+    a = np.where(mask == 1, _abi.XW_ACTION_NONE, 1).astype(np.int32)
+    sim.take_actions(a)
+    go = sim.game_over()
+    assert all(g == "alive" for g in go[::2])
+    scr2 = sim.screen().cpu().numpy().reshape(n, 3, 3, 84, 84)
+    assert (scr2[::2] == scr[::2]).all()
+    assert (scr2[1::2, 0] == scr[1::2, 1]).all() and (scr2[1::2, 1] == scr[1::2, 2]).all()   # stepped envs shifted by one
+    # device-tensor path: game_over() follows the device-side step
+    sim.reset_game()
+    for s in range(3):
+        sim.take_actions(torch.full((n,), s % 4, dtype=torch.int32, device="cuda"))
+    assert all("max_step" in g for g in sim.game_over()) and (sim.get_lives() == 0).all()
+    # get_state()'s extra keys (py_simulator.cpp:276-283) and the report
+    one = Simulator("xworld", parity.make_cfg("ref_nav3d_8x8_96"), synthetic_catalog, 1, -1)
+    one.reset_game()
+    st = one.get_state()
+    assert st["task"].startswith("XWorld3DNav") and st["event"] == "" and (st["height"], st["width"]) == ("8", "8")
+    assert one.get_world_dimensions() == (8.0, 8.0, 0.0)
+    lines, raw = one.teacher_report_task_performance()
+    assert len(raw) == 5 and lines[0] == "=== XWorld3DNavTarget ==="
+    w = Simulator("xworld", parity.make_cfg("ref_nav2d_8x8_96"), synthetic_catalog, 8, -1)
+    w.reset_game()
+    assert all(w.get_extra_info(e).split("task:")[1].startswith(("XWorldNav", "XWorldRec")) for e in range(8))

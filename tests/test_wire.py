@@ -265,3 +265,56 @@ def test_batch_client_serves_simple_game_over_tcp(R):
     th.join(timeout=10)
     assert not th.is_alive() and client["c"].steps_served == served
     assert client["c"].batches <= served
+
+
+def test_batch_client_survives_a_misbehaving_connection():
+    """One connection sending garbage, an oversized frame, a take_actions without an action or an out-of-range action is
+    closed; the other envs keep being served, and a message already buffered behind another one is not left waiting."""
+    import socket
+    n = 5
+    sim = Simulator.create("simple_game", {"array_size": 8, "n_envs": n})
+    lsocks = []
+    for _ in range(n):
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        s.listen(1)
+        lsocks.append(s)
+    box = {}
+
+    def run():
+        box["c"] = wire.BatchClient(sim, [s.getsockname()[1] for s in lsocks])
+        box["c"].serve()
+
+    th = threading.Thread(target=run, daemon=True)
+    th.start()
+    conns = [s.accept()[0] for s in lsocks]
+
+    def read_msg(c):
+        b = b""
+        while len(b) < 8:
+            d = c.recv(8 - len(b))
+            assert d
+            b += d
+        size = struct.unpack("<Q", b)[0]
+        body = b""
+        while len(body) < size:
+            body += c.recv(size - len(body))
+        return body
+
+    conns[0].sendall(wire.compose_request("reset"))
+    assert read_msg(conns[0])[8:13] == b"reset"
+    conns[1].sendall(struct.pack("<Q", 5) + b"\xff\xfe\xfd\xfc\xfb")                  # not a message
+    conns[2].sendall(struct.pack("<Q", 1 << 40))                                       # absurd frame size
+    conns[3].sendall(wire.compose_request("take_actions", {"pred_sentence": "hi"}))    # no "action"
+    conns[4].sendall(wire.compose_request("take_actions", {"action": 7}))              # simple_game has 2 actions
+    for c in conns[1:]:
+        c.settimeout(5)
+        assert c.recv(16) == b""                                                       # closed by the client
+    # env 0 is still served; two messages sent back to back are both answered without further traffic
+    conns[0].sendall(wire.compose_request("take_actions", {"action": 1}) + wire.compose_request("take_actions", {"action": 1}))
+    assert read_msg(conns[0])[8:20] == b"take_actions" and read_msg(conns[0])[8:20] == b"take_actions"
+    conns[0].sendall(wire.compose_request("take_actions", {"action": 1}) + wire.compose_request("stop"))
+    assert read_msg(conns[0])[8:20] == b"take_actions"
+    th.join(timeout=10)
+    assert not th.is_alive()
+    assert sorted(i for i, _ in box["c"].errors) == [1, 2, 3, 4] and box["c"].steps_served == 3

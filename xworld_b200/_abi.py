@@ -123,7 +123,7 @@ SYMBOLS = [
     "xw_step_host", "xw_reset_host", "xw_step_hd", "xw_step_hd_async", "xw_wait_frames", "xw_sync", "xw_num_envs", "xw_num_actions", "xw_screen_dims",
     "xw_frame_bytes", "xw_num_steps", "xw_get_field", "xw_set_field", "xw_error_flags", "xw_get_fields",
     "xw_world_dimensions", "xw_extra_info", "xw_task_performance", "xw_launch_count", "xw_render_kernel", "xw_sentence_compose",
-    "xw_enable_timing", "xw_render_ms",
+    "xw_enable_timing", "xw_render_ms", "xw_step_reset_ms",
     "xw_wire_encode_packet", "xw_wire_decode_packet", "xw_wire_parse_request", "xw_wire_compose_request", "xw_wire_reply_reset",
     "xw_wire_reply_take_actions", "xw_wire_reply_get_state", "xw_wire_reply_text",
 ]
@@ -200,6 +200,8 @@ def load():
     lib.xw_enable_timing.restype = C.c_int
     lib.xw_render_ms.argtypes = [vp, i32]
     lib.xw_render_ms.restype = C.c_double
+    lib.xw_step_reset_ms.argtypes = [vp, i32]
+    lib.xw_step_reset_ms.restype = C.c_double
     u8p, sz, wf = C.POINTER(C.c_uint8), C.c_size_t, C.POINTER(XwWireField)
     lib.xw_wire_encode_packet.argtypes = [wf, i32, u8p, sz]
     lib.xw_wire_encode_packet.restype = i64

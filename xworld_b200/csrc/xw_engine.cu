@@ -138,8 +138,10 @@ struct xw_sim {
     uint8_t *d_mask = nullptr, *d_frames = nullptr;
     // timing
     bool timing = false;
-    std::vector<cudaEvent_t> ev;
+    std::vector<cudaEvent_t> ev;      // pairs around the render launches
     size_t ev_used = 0;
+    std::vector<cudaEvent_t> ev2;     // pairs around the step + reset (+ goal warp) launches
+    size_t ev2_used = 0;
 };
 
 // Every entry point that takes a handle runs on the handle's device and leaves the caller's current device as it found it
@@ -619,6 +621,7 @@ void xw_destroy(xw_sim* s) {
     if (s->h_rew) cudaFreeHost(s->h_rew);
     if (s->h_invalid) cudaFreeHost(s->h_invalid);
     for (auto ev : s->ev) cudaEventDestroy(ev);
+    for (auto ev : s->ev2) cudaEventDestroy(ev);
     if (s->copy_stream) { cudaStreamDestroy(s->copy_stream); cudaEventDestroy(s->ev_step); cudaEventDestroy(s->ev_copy); cudaEventDestroy(s->ev_h2d); }
     if (s->ev_frames) cudaEventDestroy(s->ev_frames);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
@@ -690,21 +693,28 @@ int32_t xw_render_kernel(const xw_sim* s) {
 
 int xw_enable_timing(xw_sim* s, int32_t on) { s->timing = on != 0; return 0; }
 
-double xw_render_ms(xw_sim* s, int32_t reset) {
-    DevGuard dev_guard(s);
-    if (!s->timing && s->ev_used == 0) return -1.0;
+static double avg_event_ms(xw_sim* s, std::vector<cudaEvent_t>& ev, size_t& used, int32_t reset) {
+    if (!s->timing && used == 0) return -1.0;
     if (s->own_stream) cudaStreamSynchronize(s->own_stream);
     cudaDeviceSynchronize();
     double total = 0;
-    size_t pairs = s->ev_used / 2;
+    size_t pairs = used / 2;
     for (size_t i = 0; i < pairs; ++i) {
         float ms = 0;
-        cudaEventElapsedTime(&ms, s->ev[2 * i], s->ev[2 * i + 1]);
+        cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]);
         total += ms;
     }
     double avg = pairs ? total / pairs : -1.0;
-    if (reset) s->ev_used = 0;
+    if (reset) used = 0;
     return avg;
+}
+double xw_render_ms(xw_sim* s, int32_t reset) {
+    DevGuard dev_guard(s);
+    return avg_event_ms(s, s->ev, s->ev_used, reset);
+}
+double xw_step_reset_ms(xw_sim* s, int32_t reset) {
+    DevGuard dev_guard(s);
+    return avg_event_ms(s, s->ev2, s->ev2_used, reset);
 }
 
 static int launch_render(xw_sim* s, uint8_t* d_frames, cudaStream_t st) {
@@ -801,6 +811,14 @@ int xw_step(xw_sim* s, const int32_t* d_actions, int32_t act_rep, float* d_rewar
     if (act_rep < 1) return set_err(XW_ERR_INVALID_ARG, "act_rep must be >= 1");
     cudaStream_t st = pick_stream(s, stream);
     if (s->cfg.game == XW_GAME_XWORLD) {
+        cudaEvent_t t0 = nullptr, t1 = nullptr;
+        if (s->timing) {
+            if (s->ev2_used + 2 > s->ev2.size())
+                for (int i = 0; i < 2; ++i) { cudaEvent_t ev; CUDA_TRY(cudaEventCreate(&ev)); s->ev2.push_back(ev); }
+            t0 = s->ev2[s->ev2_used]; t1 = s->ev2[s->ev2_used + 1];
+            s->ev2_used += 2;
+            CUDA_TRY(cudaEventRecord(t0, st));
+        }
         k_step<<<(s->n + 255) / 256, 256, 0, st>>>(s->d, d_actions, act_rep, d_reward, d_game_over, s->step_parity);
         s->launches++;
         if (s->cfg.auto_reset) {
@@ -814,6 +832,7 @@ int xw_step(xw_sim* s, const int32_t* d_actions, int32_t act_rep, float* d_rewar
             }
         }
         s->step_parity ^= 1;
+        if (t1) CUDA_TRY(cudaEventRecord(t1, st));
         CUDA_TRY(cudaGetLastError());
         if (d_frames) return launch_render(s, d_frames, st);
         return 0;
