@@ -429,6 +429,16 @@ static int l_tiles(const xo_env* e, tile_pair* out) {
     return n;
 }
 
+/* `agent.loc = random.choice(new_a)` (XWorld3DNavTargetNear.py:52 and siblings): uniform over the cells _propagate_agent
+ * found.  The reference's list is in BFS discovery order and its draw is Python's unseeded random(); the contract is the
+ * SET and the uniform choice, so the draw is mapped onto the set in canonical row-major order (as for every other site
+ * whose order is an artefact: gen_reference_python.py sorts the same list before indexing it). */
+static int cmp_int(const void* a, const void* b) { return *(const int*)a - *(const int*)b; }
+static int pick_canonical(int* cells, int n, uint32_t u) {
+    qsort(cells, (size_t)n, sizeof(int), cmp_int);
+    return cells[xo_randbelow(u, (uint32_t)n)];
+}
+
 static void place_goal(xo_env* e, int g, int cell) {
     e->goal_x[g] = cell % e->W; e->goal_y[g] = cell / e->W;
     e->grid[cell] = (uint8_t)(XW_CELL_GOAL0 + g);
@@ -497,7 +507,7 @@ static int idle3d(const xw_config* cfg, xo_env* e, uint32_t ep, uint32_t att) {
         place_goal(e, g1, t.a); place_goal(e, g2, t.b);
         int nf = flood_fill(e, t.b, filled);
         if (nf == 0) { rc = 1; goto done; }
-        place_agent(e, filled[xo_randbelow(xo_draw(seed, gid, ep, att, XO_SITE_TASK_AGENT, 0), (uint32_t)nf)]);
+        place_agent(e, pick_canonical(filled, nf, xo_draw(seed, gid, ep, att, XO_SITE_TASK_AGENT, 0)));
         /* _get_surrounding_goals(refer=g1.loc), threshold 1.5 (+1e-3)  xworld3d_task.py:189-206 */
         for (int g = 0; g < G; ++g) {
             if (e->goal_x[g] == e->goal_x[g1] && e->goal_y[g] == e->goal_y[g1]) continue;
@@ -513,7 +523,7 @@ static int idle3d(const xw_config* cfg, xo_env* e, uint32_t ep, uint32_t att) {
         int mx = (e->goal_x[g1] + e->goal_x[g2]) / 2, my = (e->goal_y[g1] + e->goal_y[g2]) / 2; /* _middle_loc :324 */
         int nf = flood_fill(e, cell_of(e, mx, my), filled);
         if (nf == 0) { rc = 1; goto done; }
-        place_agent(e, filled[xo_randbelow(xo_draw(seed, gid, ep, att, XO_SITE_TASK_AGENT, 0), (uint32_t)nf)]);
+        place_agent(e, pick_canonical(filled, nf, xo_draw(seed, gid, ep, att, XO_SITE_TASK_AGENT, 0)));
         e->aux0 = g1 | (g2 << 4); e->aux1 = mx; e->aux2 = my; /* g1, g2: the bindings of G1, G2 (:59-62) */
     } else { /* XW_T3_DIRECTION, XWorld3DNavTargetDirection.py:29-76 */
         int nt = l_tiles(e, tiles);
@@ -536,7 +546,7 @@ static int idle3d(const xw_config* cfg, xo_env* e, uint32_t ep, uint32_t att) {
         /* _propagate_agent([e], inclusive=True): seed first, then BFS order  xworld3d_task.py:344-355 */
         filled[0] = ecell;
         int nf = 1 + flood_fill(e, ecell, filled + 1);
-        place_agent(e, filled[xo_randbelow(xo_draw(seed, gid, ep, att, XO_SITE_TASK_AGENT, 0), (uint32_t)nf)]);
+        place_agent(e, pick_canonical(filled, nf, xo_draw(seed, gid, ep, att, XO_SITE_TASK_AGENT, 0)));
         e->aux0 = referent; e->aux1 = dir; e->aux2 = target;
     }
 done:

@@ -146,6 +146,7 @@ class ReplayRandom(types.ModuleType):
             if cls.startswith("XWorldNav"):  # 2-D tasks: one choice per idle stage, keyed by step
                 return seq[oracle.randbelow(self._u(oracle.SITE_TASK_A, Ctx.step_no), len(seq))]
             if isinstance(seq[0], tuple) and isinstance(seq[0][0], tuple):  # choice(new_a): ((x,y,0), step)
+                seq.sort(key=lambda t: cell_key(t[0]))  # BFS discovery order -> canonical row-major (the set is the contract)
                 return seq[oracle.randbelow(self._u(oracle.SITE_TASK_AGENT, 0), len(seq))]
             if isinstance(seq[0], tuple):  # choice(empty_grids)
                 seq.sort(key=cell_key)

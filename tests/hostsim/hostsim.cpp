@@ -471,6 +471,7 @@ void hs_set_fpv_env(HostSim* s, int e, const uint8_t* grid, const int32_t* goal_
     hs_warp_goals(s, e);
 }
 
+const uint8_t* hs_fpv_pmap(HostSim* s) { return s->pmap.data(); }
 int hs_rec_task_of_draw(uint32_t x) { return rec_task_of_draw(x); }
 
 int hs_get_field(HostSim* s, const char* name, void* out) {

@@ -560,13 +560,18 @@ def test_fpv_auto_reset_and_context(backend_cls, synthetic_catalog):
     eng.reset()
     one.reset()
     prev = one.render().copy()
+    n_new = 0
     for s in range(50):
         a = parity.actions_for(s, 256, 6)
+        ep0 = eng.field("episode").copy()
         eng.step(a, render=True)
         _, _, f = one.step(a, render=True)
         scr = eng.sim.screen().cpu().numpy()
-        assert (scr[:, 0:3] == prev).all() and (scr[:, 3:6] == f).all(), s
+        new = eng.field("episode") != ep0   # auto-reset in this step: the context of a new game starts zero-filled
+        n_new += int(new.sum())
+        assert (scr[~new, 0:3] == prev[~new]).all() and (scr[new, 0:3] == 0).all() and (scr[:, 3:6] == f).all(), s
         prev = f.copy()
+    assert n_new >= 256
 
 
 def test_fpv_full_size_properties(backend_cls, synthetic_catalog):

@@ -32,10 +32,14 @@
 #define XW_RENDER_MAX_GROUPS 12   // groups per CTA (named barriers 1..12)
 #define XW_TABLE_PAD 8192     // bytes past each table the compositor may read (and never use)
 
-#if defined(XW_SP_DEBUG)
-#define XW_DBG(mask) (r.debug & (mask))
-#else
+// The painter's experiment switches.  XwRender::debug can only become non-zero in a -DXW_SP_DEBUG build (xw_engine.cu reads
+// XW_RENDER_DEBUG there and nowhere else); a shipped build always passes 0.  The tests of the (always zero) field stay in
+// the kernel on purpose: compiling them away (-DXW_SP_NODEBUG) changes ptxas's schedule of k_render_sp (123 -> 116
+// registers, +6 % executed instructions) and costs 14 % of the kernel's time (profiles/r02_summary.md, r02c vs r02d).
+#if defined(XW_SP_NODEBUG)
 #define XW_DBG(mask) 0
+#else
+#define XW_DBG(mask) (r.debug & (mask))
 #endif
 
 struct XwTaps { const int16_t *xofs, *xa0, *xa1, *yofs, *ya0, *ya1; };  // cv::resize tables

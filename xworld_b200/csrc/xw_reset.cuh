@@ -410,7 +410,6 @@ struct XwTaskOut { int tmask, aux0, aux1, aux2; };
 
 // idle() of the five XWorld3DNav* tasks.  false = the reference's `assert ..., "map too crowded?"`.
 XW_HD bool xw_idle3d(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, int task, XwMapCtx& c, XwTaskOut& o) {
-    uint8_t order[XW_MAX_DIM * XW_MAX_DIM];
     o.tmask = o.aux0 = o.aux1 = o.aux2 = 0;
     const int G = c.nG;
     XwMask obst;
@@ -461,10 +460,15 @@ XW_HD bool xw_idle3d(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, int
     m_set(c.goal, a); m_set(c.goal, b);
     for (int i = 0; i < 4; ++i) obst.w[i] = c.block.w[i] | c.goal.w[i];
     const int W = c.W;
+    // `agent.loc = random.choice(new_a)`: uniform over the cells _propagate_agent finds (xworld3d_task.py:344-355).  The draw
+    // indexes that SET in row-major order (the reference's list order, BFS discovery, is an artefact its unseeded draw makes
+    // unobservable): one mask flood + the k-th set bit instead of a queue BFS.
     if (task == XW_T3_NEAR) {
-        int nf = xw_bfs(c, obst, b, b, -1, order);
+        XwMask reach = xw_flood(c, obst, b);
+        m_clr(reach, b);  // flood_fill excludes its seed
+        const int nf = m_count(reach);
         if (nf == 0) return false;
-        c.agent = xw_bfs_cell(c, order[xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_TASK_AGENT, 0), (uint32_t)nf)]);
+        c.agent = m_nth(reach, (int)xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_TASK_AGENT, 0), (uint32_t)nf));
         // goals within 1.5 (+1e-3) of g1, g1 itself excluded: the 8-neighbourhood
         for (int g = 0; g < G; ++g) {
             int dx = c.gcell[g] % W - a % W, dy = c.gcell[g] / W - a / W;
@@ -474,9 +478,11 @@ XW_HD bool xw_idle3d(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, int
     } else if (task == XW_T3_BETWEEN) {
         int mx = (a % W + b % W) / 2, my = (a / W + b / W) / 2;
         int mid = my * W + mx;
-        int nf = xw_bfs(c, obst, mid, mid, -1, order);
+        XwMask reach = xw_flood(c, obst, mid);
+        m_clr(reach, mid);
+        const int nf = m_count(reach);
         if (nf == 0) return false;
-        c.agent = xw_bfs_cell(c, order[xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_TASK_AGENT, 0), (uint32_t)nf)]);
+        c.agent = m_nth(reach, (int)xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_TASK_AGENT, 0), (uint32_t)nf));
         o.aux0 = g1 | (g2 << 4); o.aux1 = mx; o.aux2 = my;  // (g2: only the sentence channel needs it, xw_sentence.hpp)
     } else {
         int target = g1, referent = g2;
@@ -497,9 +503,9 @@ XW_HD bool xw_idle3d(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, int
         int rcell = c.gcell[referent];
         int dir = xw_axis_direction(tx - ex, ty - ey, rcell % W - tx, rcell / W - ty);
         int ecell = ey * W + ex;
-        int nf = 1 + xw_bfs(c, obst, ecell, ecell, -1, order);  // inclusive: seed first
-        int pick = (int)xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_TASK_AGENT, 0), (uint32_t)nf);
-        c.agent = pick == 0 ? ecell : xw_bfs_cell(c, order[pick - 1]);
+        const XwMask reach = xw_flood(c, obst, ecell);  // _propagate_agent([e], inclusive=True): the seed counts
+        const int nf = m_count(reach);
+        c.agent = m_nth(reach, (int)xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_TASK_AGENT, 0), (uint32_t)nf));
         o.aux0 = referent; o.aux1 = dir; o.aux2 = target;
     }
     return true;
