@@ -3,6 +3,7 @@
 // the CUDA games: every entry point either launches kernels or returns an error.
 #include <cuda_runtime.h>
 #include <stdarg.h>
+#include <time.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -23,6 +24,7 @@
 #include "xw_teacher_names.hpp"
 
 #include <cmath>
+#include <functional>
 
 // ------------------------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
@@ -45,15 +47,19 @@ static int set_err(int code, const char* fmt, ...) {
 // reset is one long data-dependent instruction stream (maze DFS, rejection loops), and 32 different ones in one
 // warp serialise -- measured 490 us per step at C2 with one lane per env.  The lanes of the warp evaluate the
 // episode's attempts side by side (xw_reset_env_warp).
-__global__ void __launch_bounds__(128) k_reset(XwDev d, const uint8_t* mask, const int32_t* list, const int32_t* count) {
+__global__ void __launch_bounds__(128) k_reset(XwDev d, const uint8_t* mask) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (list) {
-        const int n_warps = (gridDim.x * blockDim.x) >> 5, cnt = *count;
-        for (int w = i >> 5; w < cnt; w += n_warps) xw_reset_env_warp(d, list[w]);
-        return;
-    }
     if (i >= d.n || (mask && !mask[i])) return;
     xw_reset_env(d, i);
+    // an explicit reset (not the auto-reset of a step, whose game_over code is still to be read): the env is "alive", reward 0
+    if (d.stage_over) { d.stage_over[i] = 0; d.stage_rew[i] = 0.f; }
+}
+__global__ void __launch_bounds__(128) k_reset_list(XwDev d, const int32_t* list, const int32_t* count) {
+    __shared__ uint32_t s_stack[4][XW_RESET_STACK_WORDS];
+    __shared__ uint32_t s_draws[4][XW_RESET_DRAW_WORDS];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5, cnt = *count, wi = threadIdx.x >> 5;
+    for (int w = i >> 5; w < cnt; w += n_warps) xw_reset_env_warp(d, list[w], s_stack[wi], s_draws[wi]);
 }
 
 __global__ void __launch_bounds__(256) k_step(XwDev d, const int32_t* __restrict__ actions, int act_rep,
@@ -105,6 +111,20 @@ struct xw_sim {
     xw_config cfg;
     int n = 0, device = 0;
     cudaStream_t own_stream = nullptr, copy_stream = nullptr;
+    // auto-reset beside the painter (step_xworld): the reset launch runs on its own stream on `reserve` SMs the painter leaves free
+    cudaStream_t reset_stream = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    int32_t* h_reset_cnt = nullptr;   // pinned [2]: the queue lengths of the last steps (read back without a wait: sizes `reserve`)
+    float reset_avg = 128.f;
+    int reset_ctas_per_sm = 0;
+    bool overlap_reset = false;
+    // XW_TRACE=1 (diagnostics): timestamps of one overlapped step, printed by xw_sync: k_step start / end, painter end, reset
+    // end, re-paint end -- relative to the step's start
+    bool trace = false;
+    cudaEvent_t tr[6] = {};
+    int trace_steps = 0;
+    double host_enq_us = 0, host_sync_us = 0;   // step_hd: host time spent queueing the step / waiting for it (trace)
+    int host_n = 0;
     cudaEvent_t ev_step = nullptr, ev_copy = nullptr, ev_frames = nullptr, ev_h2d = nullptr;
     int64_t launches = 0;
     int step_parity = 0;
@@ -119,6 +139,7 @@ struct xw_sim {
     size_t tables_bytes = 0, l2_window = 0;
     float l2_ratio = 0.f;
     void (*render_fn)(XwDev, XwRender, uint8_t*, size_t) = nullptr;  // k_render<WR> for this frame width
+    void (*render_list_fn)(XwDev, XwRender, uint8_t*, size_t) = nullptr;  // the painter's list mode (same instantiation, LIST = true)
     int C = 3;                      // frame channels: 3 (planes B, G, R) or 1 (--color=false)
     // first-person view
     XwFpv fpv;
@@ -301,7 +322,9 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
     d.seed = c.seed; d.gid0 = c.env_id_offset;
     d.vr = vr; d.task_mode = c.task_mode;
     s->C = c.gray ? 1 : 3;
-    { const char* ew = getenv("XW_RESET_RETRY_WIDTH"); int w = ew ? atoi(ew) : 32; d.retry_width = w < 1 ? 1 : (w > 32 ? 32 : w); }
+    { const char* eo = getenv("XW_RESET_OVERLAP"); s->overlap_reset = !eo || atoi(eo) != 0; }
+    { const char* et = getenv("XW_TRACE"); s->trace = et && atoi(et) != 0; }
+    { const char* ew = getenv("XW_RESET_RETRY_WIDTH"); int w = ew ? atoi(ew) : 8; d.retry_width = w < 1 ? 1 : (w > 32 ? 32 : w); }
     int rc = 0;
     rc |= dalloc(s, &d.grid, (size_t)n * d.CS);
     uint8_t** u8s[] = {&d.agent_x, &d.agent_y, &d.facing, &d.task, &d.stage, &d.event, &d.succ, &d.tmask, &d.aux0, &d.aux1, &d.aux2};
@@ -356,6 +379,7 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
     if (c.gray) rc |= dalloc(s, &s->d_bgr, (size_t)n * 3 * OH * OW, false);
     if (rc) return rc;
     if (vr > 0) return create_fpv(s, cat, OH, OW);
+    if (OH > c.height * 64 || OW > c.width * 64) return set_err(XW_ERR_UNSUPPORTED, "fully observed frames larger than the %d-px canvas (upscaling)", c.height * 64);
     s->tab = xw_build_render_tables(c.height, c.width, OH, OW);
     XwRenderTables& t = s->tab;
     XwRender& r = s->r;
@@ -521,6 +545,13 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
 #define XW_PICK_SP(WR_) (t.max_band_rows <= 8 ? (nt <= 512 ? k_render_sp<WR_, 512, 8> : nt <= 768 && disj ? k_render_sp<WR_, 768, 8, true> : k_render_sp<WR_, 1024, 8>) \
                                               : (nt <= 512 ? k_render_sp<WR_, 512, 12> : nt <= 768 && disj ? k_render_sp<WR_, 768, 12, true> : k_render_sp<WR_, 1024, 12>))
         // (the painter's compile-time row stride also fixes the frame height: square frames only)
+#define XW_PICK_SPL(WR_) (t.max_band_rows <= 8 ? (nt <= 512 ? k_render_sp<WR_, 512, 8, false, true> : nt <= 768 && disj ? k_render_sp<WR_, 768, 8, true, true> : k_render_sp<WR_, 1024, 8, false, true>) \
+                                               : (nt <= 512 ? k_render_sp<WR_, 512, 12, false, true> : nt <= 768 && disj ? k_render_sp<WR_, 768, 12, true, true> : k_render_sp<WR_, 1024, 12, false, true>))
+        if (s->render_sp) {
+            s->render_list_fn = r.OH != r.OW ? XW_PICK_SPL(0) : r.WR == 21 ? XW_PICK_SPL(21) : r.WR == 24 ? XW_PICK_SPL(24) : r.WR == 32 ? XW_PICK_SPL(32) : XW_PICK_SPL(0);
+            CUDA_TRY(cudaFuncSetAttribute(s->render_list_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, s->render_smem));
+        }
+#undef XW_PICK_SPL
         if (s->render_sp) s->render_fn = r.OH != r.OW ? XW_PICK_SP(0) : r.WR == 21 ? XW_PICK_SP(21) : r.WR == 24 ? XW_PICK_SP(24) : r.WR == 32 ? XW_PICK_SP(32) : XW_PICK_SP(0);
         else if (s->render_sb) s->render_fn = r.WR == 21 ? XW_PICK_SB(21) : r.WR == 24 ? XW_PICK_SB(24) : r.WR == 32 ? XW_PICK_SB(32) : XW_PICK_SB(0);
         else s->render_fn = r.WR == 21 ? XW_PICK(21) : r.WR == 24 ? XW_PICK(24) : r.WR == 32 ? XW_PICK(32) : XW_PICK(0);
@@ -620,6 +651,8 @@ void xw_destroy(xw_sim* s) {
     if (s->h_over) cudaFreeHost(s->h_over);
     if (s->h_rew) cudaFreeHost(s->h_rew);
     if (s->h_invalid) cudaFreeHost(s->h_invalid);
+    if (s->h_reset_cnt) cudaFreeHost(s->h_reset_cnt);
+    if (s->reset_stream) { cudaStreamSynchronize(s->reset_stream); cudaStreamDestroy(s->reset_stream); cudaEventDestroy(s->ev_a); cudaEventDestroy(s->ev_b); }
     for (auto ev : s->ev) cudaEventDestroy(ev);
     for (auto ev : s->ev2) cudaEventDestroy(ev);
     if (s->copy_stream) { cudaStreamDestroy(s->copy_stream); cudaEventDestroy(s->ev_step); cudaEventDestroy(s->ev_copy); cudaEventDestroy(s->ev_h2d); }
@@ -717,7 +750,10 @@ double xw_step_reset_ms(xw_sim* s, int32_t reset) {
     return avg_event_ms(s, s->ev2, s->ev2_used, reset);
 }
 
-static int launch_render(xw_sim* s, uint8_t* d_frames, cudaStream_t st) {
+// fix != NULL: the painter leaves `fix->reserve` SMs free, and once `fix->done` has fired the frames of the envs in the
+// step's auto-reset queue are painted again (the painter in list mode) -- see step_xworld.
+struct RenderFix { int reserve; cudaEvent_t done; const int32_t* list; const int32_t* count; int est; std::function<int()> after_painter; };
+static int launch_render(xw_sim* s, uint8_t* d_frames, cudaStream_t st, const RenderFix* fix = nullptr) {
     XwRender& r = s->r;
     const int K = s->cfg.context;
     const int FBo = s->C * r.OH * r.OW;  // bytes of one frame as the caller sees it
@@ -749,7 +785,9 @@ static int launch_render(xw_sim* s, uint8_t* d_frames, cudaStream_t st) {
         }
     } else if (s->tab.fast_ok) {
         const int need = (s->n + r.G - 1) / r.G;  // CTAs that get at least one env
-        const int grid = s->render_grid < need ? s->render_grid : need;
+        int grid = s->render_grid - (fix ? fix->reserve : 0);
+        if (grid < 1) grid = 1;
+        if (grid > need) grid = need;
         cudaLaunchConfig_t lc;
         memset(&lc, 0, sizeof lc);
         lc.gridDim = dim3(grid); lc.blockDim = dim3(r.G * r.GT); lc.dynamicSmemBytes = s->render_smem; lc.stream = st;
@@ -768,11 +806,23 @@ static int launch_render(xw_sim* s, uint8_t* d_frames, cudaStream_t st) {
         k_render_generic<<<s->n_sms * 8, 256, 0, st>>>(s->d, r, dst, dst_stride);
     }
     s->launches++;
+    if (s->timing) CUDA_TRY(cudaEventRecord(e1, st));  // (the frame kernel alone: not the re-paint of the reset queue, not the gray pass)
+    if (fix) {
+        const int rc2 = fix->after_painter();  // (the painter is queued: now the reset launch on its own stream, then `done`)
+        if (rc2) return rc2;
+        CUDA_TRY(cudaStreamWaitEvent(st, fix->done, 0));
+        // the painter again, in list mode: about one env per warp group at the expected queue length
+        int blocks = (fix->est + r.G - 1) / r.G;
+        if (blocks > s->render_grid) blocks = s->render_grid;
+        XwRender rl = r;
+        rl.env_list = fix->list; rl.env_count = fix->count;
+        s->render_list_fn<<<blocks, r.G * r.GT, s->render_smem, st>>>(s->d, rl, dst, dst_stride);
+        s->launches++;
+    }
     if (s->cfg.gray) {
         k_gray<<<s->n_sms * 8, 256, 0, st>>>(s->d_bgr, out, s->n, r.OH * r.OW, (size_t)r.FB, env_stride);
         s->launches++;
     }
-    if (s->timing) CUDA_TRY(cudaEventRecord(e1, st));
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -788,7 +838,7 @@ int xw_reset(xw_sim* s, const uint8_t* d_mask, void* stream) {
     DevGuard dev_guard(s);
     cudaStream_t st = pick_stream(s, stream);
     if (s->cfg.game == XW_GAME_XWORLD) {
-        k_reset<<<(s->n + 127) / 128, 128, 0, st>>>(s->d, d_mask, nullptr, nullptr);
+        k_reset<<<(s->n + 127) / 128, 128, 0, st>>>(s->d, d_mask);
         s->launches++;
         if (s->d.vr > 0) {  // the new episodes' goal icons, warped once (xitem.cpp:47-60)
             k_fpv_warp_goals<<<s->n_sms * 8 < s->n ? s->n_sms * 8 : s->n, 256, 0, st>>>(s->d, s->fpv, d_mask, nullptr, nullptr);
@@ -804,39 +854,105 @@ int xw_reset(xw_sim* s, const uint8_t* d_mask, void* stream) {
     return 0;
 }
 
+// One SimulatorInterface::take_actions of the xworld batch on stream st: k_step, the auto-reset launch, the frames.
+// ev_step (may be NULL) is recorded when reward / game_over / the invalid-action count are final, i.e. after k_step.
+//
+// Reset beside the painter.  The auto-reset launch is latency, not work: a few hundred envs per step, one warp each, 80-190 us
+// of one long dependent instruction stream per env, during which 99 % of the GPU idles and the painter waits.  The frames of the
+// envs that do NOT reset depend on k_step only, so (fully observed view, context 1, shared-memory painter):
+//   st:            k_step -> painter on (SMs - reserve) CTAs, all envs -> [wait] -> the painter in list mode: the queue's envs again
+//   reset_stream:  [k_step done] -> k_reset_list on the SMs the painter left free -> [done]
+// The painter reads the queued envs' old (possibly half-rewritten: always valid cell codes) state; those frames are overwritten
+// by the second, tiny launch.  `reserve` follows the queue lengths of the last steps (a pinned counter, read without waiting).
+static int step_xworld(xw_sim* s, const int32_t* d_actions, int act_rep, float* d_reward, int32_t* d_game_over, uint8_t* d_frames,
+                       cudaStream_t st, cudaEvent_t ev_step) {
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (s->timing) {
+        if (s->ev2_used + 2 > s->ev2.size())
+            for (int i = 0; i < 2; ++i) { cudaEvent_t ev; CUDA_TRY(cudaEventCreate(&ev)); s->ev2.push_back(ev); }
+        t0 = s->ev2[s->ev2_used]; t1 = s->ev2[s->ev2_used + 1];
+        s->ev2_used += 2;
+        CUDA_TRY(cudaEventRecord(t0, st));
+    }
+    if (s->trace) {
+        if (!s->tr[0]) for (auto& e : s->tr) CUDA_TRY(cudaEventCreate(&e));
+        if (s->trace_steps > 0 && s->trace_steps % 16 == 8 && s->reset_stream) {  // report an earlier step (complete by now)
+            cudaEventSynchronize(s->tr[4]); cudaEventSynchronize(s->tr[3]);
+            float a = 0, b = 0, c2 = 0, d2 = 0;
+            cudaEventElapsedTime(&a, s->tr[0], s->tr[1]); cudaEventElapsedTime(&b, s->tr[0], s->tr[2]);
+            cudaEventElapsedTime(&c2, s->tr[0], s->tr[3]); cudaEventElapsedTime(&d2, s->tr[0], s->tr[4]);
+            fprintf(stderr, "XW_TRACE step %d: k_step end %.1f us | painter end %.1f | reset end %.1f | re-paint end %.1f (reset_avg %.0f)\n",
+                    s->trace_steps, a * 1e3, b * 1e3, c2 * 1e3, d2 * 1e3, s->reset_avg);
+        }
+    }
+    const bool tracing = s->trace && (s->trace_steps++ % 16 == 7);
+    if (tracing) CUDA_TRY(cudaEventRecord(s->tr[0], st));
+    k_step<<<(s->n + 255) / 256, 256, 0, st>>>(s->d, d_actions, act_rep, d_reward, d_game_over, s->step_parity);
+    s->launches++;
+    if (tracing) CUDA_TRY(cudaEventRecord(s->tr[1], st));
+    if (ev_step) CUDA_TRY(cudaEventRecord(ev_step, st));
+    const int32_t* q_list = s->d.reset_list;
+    const int32_t* q_count = s->d.reset_count + s->step_parity;
+    const int parity = s->step_parity;
+    s->step_parity ^= 1;
+    const bool overlap = s->overlap_reset && s->cfg.auto_reset && d_frames && s->cfg.context == 1 && s->d.vr == 0 && s->tab.fast_ok && s->render_list_fn;
+    if (overlap) {
+        if (!s->reset_stream) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&s->reset_stream, cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&s->ev_a, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&s->ev_b, cudaEventDisableTiming));
+            CUDA_TRY(cudaMallocHost((void**)&s->h_reset_cnt, 2 * sizeof(int32_t)));
+            s->h_reset_cnt[0] = s->h_reset_cnt[1] = -1;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->reset_ctas_per_sm, k_reset_list, 128, 0));
+            if (s->reset_ctas_per_sm < 1) s->reset_ctas_per_sm = 1;
+        }
+        const int32_t seen = s->h_reset_cnt[parity ^ 1];  // the previous step's queue length, if its copy has landed
+        if (seen >= 0) s->reset_avg = 0.75f * s->reset_avg + 0.25f * (float)seen;
+        // one warp per queued env, reset_ctas_per_sm CTAs of 4 warps per reserved SM, about three rounds inside a render
+        int reserve = (int)(s->reset_avg / (float)(s->reset_ctas_per_sm * 4 * 3)) + 1;
+        if (reserve > s->n_sms / 8) reserve = s->n_sms / 8;
+        if (t1) CUDA_TRY(cudaEventRecord(t1, st));
+        CUDA_TRY(cudaEventRecord(s->ev_a, st));
+        CUDA_TRY(cudaStreamWaitEvent(s->reset_stream, s->ev_a, 0));
+        RenderFix fix = {reserve, s->ev_b, q_list, q_count, (int)(s->reset_avg * 1.5f) + 16, nullptr};
+        // (the painter first: its CTAs take their SMs before the reset launch, which waits for an event, can be placed)
+        fix.after_painter = [s, reserve, q_list, q_count, parity, tracing, st]() -> int {
+            if (tracing) CUDA_TRY(cudaEventRecord(s->tr[2], st));
+            k_reset_list<<<reserve * s->reset_ctas_per_sm, 128, 0, s->reset_stream>>>(s->d, q_list, q_count);
+            s->launches++;
+            if (tracing) CUDA_TRY(cudaEventRecord(s->tr[3], s->reset_stream));
+            CUDA_TRY(cudaEventRecord(s->ev_b, s->reset_stream));
+            static const bool nocnt = [] { const char* e = getenv("XW_OVERLAP_NOCNT"); return e && atoi(e) != 0; }();
+            if (!nocnt) CUDA_TRY(cudaMemcpyAsync(s->h_reset_cnt + parity, q_count, sizeof(int32_t), cudaMemcpyDeviceToHost, s->reset_stream));
+            CUDA_TRY(cudaGetLastError());
+            return 0;
+        };
+        const int rc3 = launch_render(s, d_frames, st, &fix);
+        if (tracing) CUDA_TRY(cudaEventRecord(s->tr[4], st));
+        return rc3;
+    }
+    if (s->cfg.auto_reset) {
+        const int want = (s->n + 3) / 4, cap = s->n_sms * 16;  // CTAs of 4 warps: one warp per queued env, grid-stride past the cap
+        k_reset_list<<<want < cap ? want : cap, 128, 0, st>>>(s->d, q_list, q_count);
+        s->launches++;
+        if (s->d.vr > 0) {
+            k_fpv_warp_goals<<<s->n_sms * 8 < s->n ? s->n_sms * 8 : s->n, 256, 0, st>>>(s->d, s->fpv, nullptr, q_list, q_count);
+            s->launches++;
+        }
+    }
+    if (t1) CUDA_TRY(cudaEventRecord(t1, st));
+    CUDA_TRY(cudaGetLastError());
+    if (d_frames) return launch_render(s, d_frames, st);
+    return 0;
+}
+
 int xw_step(xw_sim* s, const int32_t* d_actions, int32_t act_rep, float* d_reward, int32_t* d_game_over,
             uint8_t* d_frames, void* stream) {
     DevGuard dev_guard(s);
     if (!d_actions || !d_reward || !d_game_over) return set_err(XW_ERR_INVALID_ARG, "null buffer");
     if (act_rep < 1) return set_err(XW_ERR_INVALID_ARG, "act_rep must be >= 1");
     cudaStream_t st = pick_stream(s, stream);
-    if (s->cfg.game == XW_GAME_XWORLD) {
-        cudaEvent_t t0 = nullptr, t1 = nullptr;
-        if (s->timing) {
-            if (s->ev2_used + 2 > s->ev2.size())
-                for (int i = 0; i < 2; ++i) { cudaEvent_t ev; CUDA_TRY(cudaEventCreate(&ev)); s->ev2.push_back(ev); }
-            t0 = s->ev2[s->ev2_used]; t1 = s->ev2[s->ev2_used + 1];
-            s->ev2_used += 2;
-            CUDA_TRY(cudaEventRecord(t0, st));
-        }
-        k_step<<<(s->n + 255) / 256, 256, 0, st>>>(s->d, d_actions, act_rep, d_reward, d_game_over, s->step_parity);
-        s->launches++;
-        if (s->cfg.auto_reset) {
-            const int want = (s->n + 3) / 4, cap = s->n_sms * 16;  // CTAs of 4 warps: one warp per queued env, grid-stride past the cap
-            k_reset<<<want < cap ? want : cap, 128, 0, st>>>(s->d, nullptr, s->d.reset_list, s->d.reset_count + s->step_parity);
-            s->launches++;
-            if (s->d.vr > 0) {
-                k_fpv_warp_goals<<<s->n_sms * 8 < s->n ? s->n_sms * 8 : s->n, 256, 0, st>>>(s->d, s->fpv, nullptr, s->d.reset_list,
-                                                                                           s->d.reset_count + s->step_parity);
-                s->launches++;
-            }
-        }
-        s->step_parity ^= 1;
-        if (t1) CUDA_TRY(cudaEventRecord(t1, st));
-        CUDA_TRY(cudaGetLastError());
-        if (d_frames) return launch_render(s, d_frames, st);
-        return 0;
-    }
+    if (s->cfg.game == XW_GAME_XWORLD) return step_xworld(s, d_actions, act_rep, d_reward, d_game_over, d_frames, st, nullptr);
     if (s->cfg.game == XW_GAME_SIMPLE_RACE) {
         for (int rep = 0; rep < act_rep; ++rep) {  // GameSimulator::take_actions repeats the action
             if (rep > 0) return set_err(XW_ERR_UNSUPPORTED, "simple_race: act_rep > 1 not implemented");
@@ -1010,6 +1126,7 @@ int xw_sync(xw_sim* s) {
     DevGuard dev_guard(s);
     if (s->own_stream) CUDA_TRY(cudaStreamSynchronize(s->own_stream));
     if (s->copy_stream) CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
+    if (s->reset_stream) CUDA_TRY(cudaStreamSynchronize(s->reset_stream));
     return 0;
 }
 static int step_hd(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float* h_reward, int32_t* h_game_over, uint8_t* d_frames,
@@ -1020,12 +1137,15 @@ static int step_hd(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float* 
     int rc = ensure_staging(s, false);
     if (rc) return rc;
     cudaStream_t st = s->own_stream;
+    struct timespec ts0, ts1, ts2;
+    if (s->trace) clock_gettime(CLOCK_MONOTONIC, &ts0);
     const bool pin_a = is_pinned(h_actions), pin_r = is_pinned(h_reward), pin_o = is_pinned(h_game_over);
     const int32_t* src_a = h_actions;
     if (!pin_a) { memcpy(s->h_act, h_actions, sizeof(int32_t) * s->n); src_a = s->h_act; }
-    // The step kernel reads a page-locked action buffer over PCIe itself: no copy operation in front of it
-    // (e2e +0.9 %, profiles/r01_summary.md; XW_E2E_ZEROCOPY=0 goes back to the H2D copy)
-    static const bool zero_copy = [] { const char* e = getenv("XW_E2E_ZEROCOPY"); return !e || atoi(e) != 0; }();
+    // XW_E2E_ZEROCOPY=1: the step kernel reads a page-locked action buffer over PCIe itself, no copy operation in front of it.
+    // Round 1 measured +0.9 % with it; with the reset launch running beside the painter it costs 20 % of the synchronous
+    // end-to-end rate (profiles/r02_summary.md, r02j: 141 M vs 177 M env-steps/s), so the H2D copy is the default again.
+    static const bool zero_copy = [] { const char* e = getenv("XW_E2E_ZEROCOPY"); return e && atoi(e) != 0; }();
     const int32_t* dev_a = s->d_act;
     void* mapped = nullptr;
     const bool split = s->cfg.game == XW_GAME_XWORLD && d_frames != nullptr;
@@ -1047,15 +1167,16 @@ static int step_hd(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float* 
         cudaGetLastError();
         CUDA_TRY(cudaMemcpyAsync(s->d_act, src_a, sizeof(int32_t) * s->n, cudaMemcpyHostToDevice, st));
     }
-    rc = xw_step(s, dev_a, act_rep, s->d_rew, s->d_over, split ? nullptr : d_frames, st);
-    if (rc) return rc;
     cudaStream_t cs = st;
-    if (split) {
+    if (split) {  // reward / game_over go back on the copy stream as soon as k_step is done, under the reset and render kernels
+        if (act_rep < 1) return set_err(XW_ERR_INVALID_ARG, "act_rep must be >= 1");
         cs = s->copy_stream;
-        CUDA_TRY(cudaEventRecord(s->ev_step, st));
-        rc = launch_render(s, d_frames, st);  // first: the render launch must be queued before the step kernels end
+        rc = step_xworld(s, dev_a, act_rep, s->d_rew, s->d_over, d_frames, st, s->ev_step);
         if (rc) return rc;
         CUDA_TRY(cudaStreamWaitEvent(cs, s->ev_step, 0));
+    } else {
+        rc = xw_step(s, dev_a, act_rep, s->d_rew, s->d_over, d_frames, st);
+        if (rc) return rc;
     }
     CUDA_TRY(cudaMemcpyAsync(pin_r ? h_reward : s->h_rew, s->d_rew, sizeof(float) * s->n, cudaMemcpyDeviceToHost, cs));
     CUDA_TRY(cudaMemcpyAsync(pin_o ? h_game_over : s->h_over, s->d_over, sizeof(int32_t) * s->n, cudaMemcpyDeviceToHost, cs));
@@ -1066,7 +1187,17 @@ static int step_hd(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float* 
             CUDA_TRY(cudaStreamWaitEvent(st, s->ev_copy, 0));
         }
     }
+    if (s->trace) clock_gettime(CLOCK_MONOTONIC, &ts1);
     CUDA_TRY(cudaStreamSynchronize(split && !wait_frames ? cs : st));
+    if (s->trace) {
+        clock_gettime(CLOCK_MONOTONIC, &ts2);
+        s->host_enq_us += (ts1.tv_sec - ts0.tv_sec) * 1e6 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-3;
+        s->host_sync_us += (ts2.tv_sec - ts1.tv_sec) * 1e6 + (ts2.tv_nsec - ts1.tv_nsec) * 1e-3;
+        if (++s->host_n % 32 == 0) {
+            fprintf(stderr, "XW_TRACE step_hd: host enqueue %.1f us, wait %.1f us per call (last 32)\n", s->host_enq_us / 32, s->host_sync_us / 32);
+            s->host_enq_us = s->host_sync_us = 0;
+        }
+    }
     if (!pin_r) memcpy(h_reward, s->h_rew, sizeof(float) * s->n);
     if (!pin_o) memcpy(h_game_over, s->h_over, sizeof(int32_t) * s->n);
     return invalid_status(s);

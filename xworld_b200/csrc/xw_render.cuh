@@ -103,6 +103,10 @@ struct XwRender {
     XwRenderSpSmem sp;        // = xw_render_sp_smem(r, G)
     unsigned int* prof;       // -DXW_SP_PROF builds only: per-phase clock sums of group 0 of CTA 0 (tools/sweep_render.py)
     int32_t sp_fill;          // 0: white pre-fill with vector stores (warp 1), 1: with a TMA bulk load of `white`
+    // list mode of the painter (k_render_sp<..., LIST = true>): the envs env_list[0 .. *env_count) instead of all of them --
+    // the frames of the step's auto-reset queue, painted after the reset launch that ran beside the painter (xw_engine.cu step_xworld)
+    const int32_t* env_list;
+    const int32_t* env_count;
 };
 
 // ---- exact cv::resize arithmetic --------------------------------------------------------
@@ -1249,7 +1253,7 @@ __global__ void k_build_class_tables(XwRender r) {
 //             drain of the previous frame;
 //   everybody then stores the precomputed words and paints the brick slots (POST: shared memory only), and
 //   the TMA thread hands the frame to the TMA engine (one bulk store, evict-first in L2).
-template <int WR_T, int NT_MAX, int XW_SP_ROWS, bool DISJ = false>
+template <int WR_T, int NT_MAX, int XW_SP_ROWS, bool DISJ = false, bool LIST = false>
 __global__ void __launch_bounds__(NT_MAX, 1)
 k_render_sp(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -1309,8 +1313,12 @@ k_render_sp(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride
     const int row_words = d.CS >> 2, HW = d.H * d.W;
     const int WR = WR_T ? WR_T : r.WR;
     const int n_sslots = (1 + d.G) * r.nwc, n_rw = r.n_sr * WR;
+    // `env` counts the kernel's work items: the envs themselves, or (LIST) positions of the env list
+#define XW_N_ITEMS (LIST ? n_list : d.n)
+#define XW_ENV_ID(i) (LIST ? r.env_list[(i)] : (i))
+    const int n_list = LIST ? *r.env_count : 0;
     int env = blockIdx.x * G + g;
-    if (env >= d.n) return;
+    if (env >= XW_N_ITEMS) return;
 
     // register prefetch of an env's grid row (<= 64 words: two per lane of warp 0) and goal icons
     uint32_t nq0 = 0, nq1 = 0, ni = 0;
@@ -1410,9 +1418,9 @@ k_render_sp(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride
     };
     // ---- prologue: env 0 of the group
     if (w0) {
-        load_cells(env);
+        load_cells(XW_ENV_ID(env));
         store_cells(0);
-        if (env + gstride < d.n) load_cells(env + gstride);
+        if (env + gstride < XW_N_ITEMS) load_cells(XW_ENV_ID(env + gstride));
     }
     group_bar(bar_id, GT);
     issue(0);
@@ -1424,9 +1432,9 @@ k_render_sp(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride
 #else
 #define XW_PROF(i) do { } while (0)
 #endif
-    for (uint32_t it = 0; env < d.n; env += gstride, ++it) {
+    for (uint32_t it = 0; env < XW_N_ITEMS; env += gstride, ++it) {
         const int cur = it & 1;
-        const bool have_next = env + gstride < d.n;
+        const bool have_next = env + gstride < XW_N_ITEMS;
         const XwCells cells = cells_of(cur);
         XW_PROF(7);  // (loop overhead, TMA store issue)
         if (w0) {
@@ -1477,45 +1485,44 @@ k_render_sp(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride
         fence_async_smem();  // generic-proxy writes -> visible to the async (TMA) proxy
         // (after the fence, which would otherwise wait for them: L2 loads for the next env and the env after it)
         if (have_next && !(XW_DBG(65))) issue(cur ^ 1);
-        if (w0 && env + 2 * gstride < d.n) load_cells(env + 2 * gstride);
+        if (w0 && env + 2 * gstride < XW_N_ITEMS) load_cells(XW_ENV_ID(env + 2 * gstride));
         XW_PROF(5);  // issue for the next env
         group_bar(bar_id, GT);
         XW_PROF(6);  // barrier C wait
         if (tma_thread && !(XW_DBG(4))) {
-            tma_store_1d(frames + (size_t)env * env_stride, fb, (uint32_t)r.FB);
+            tma_store_1d(frames + (size_t)XW_ENV_ID(env) * env_stride, fb, (uint32_t)r.FB);
             tma_commit();
         }
     }
 #undef XW_PROF
+#undef XW_N_ITEMS
+#undef XW_ENV_ID
     if (tma_thread) tma_wait_all<0>();
 }
 
 // General fallback (any frame size): one thread per output byte, straight to global memory.
+__device__ __forceinline__ uint8_t xw_generic_byte(const XwDev& d, const XwRender& r, int e, int rem) {
+    const XwTaps& t = r.taps;
+    const int c = rem / (r.OH * r.OW), p = rem % (r.OH * r.OW), dy = p / r.OW, dx = p % r.OW;
+    const int sx0 = t.xofs[dx], sy0 = t.yofs[dy];
+    const int sx1 = t.xa1[dx] ? sx0 + 1 : sx0, sy1 = t.ya1[dy] ? sy0 + 1 : sy0;
+    const uint8_t* g = d.grid + (size_t)e * d.CS;
+    uint32_t dd[4];
+    const int cy[2] = {sy0 >> 6, sy1 >> 6}, cx[2] = {sx0 >> 6, sx1 >> 6};
+    for (int q = 0; q < 4; ++q) dd[q] = xw_cell_desc(d, e, g[cy[q >> 1] * r.W + cx[q & 1]]);
+    if (dd[0] == dd[1] && dd[0] == dd[2] && dd[0] == dd[3]) return dd[0] == 0 ? 255 : r.T[(size_t)(dd[0] - 1) * r.FB + rem];
+    const int sy[2] = {sy0, sy1}, sx[2] = {sx0, sx1};
+    int px[4];
+    for (int q = 0; q < 4; ++q) px[q] = xw_canvas_tap(r, dd[q], sy[q >> 1], sx[q & 1], c);
+    return xw_resize_px(px[0], px[1], px[2], px[3], t.xa0[dx], t.xa1[dx], t.ya0[dy], t.ya1[dy]);
+}
 __global__ void k_render_generic(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
     const size_t total = (size_t)d.n * r.FB;
-    const XwTaps& t = r.taps;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int e = (int)(i / r.FB), rem = (int)(i % r.FB);
-        const int c = rem / (r.OH * r.OW), p = rem % (r.OH * r.OW), dy = p / r.OW, dx = p % r.OW;
-        const int sx0 = t.xofs[dx], sy0 = t.yofs[dy];
-        const int sx1 = t.xa1[dx] ? sx0 + 1 : sx0, sy1 = t.ya1[dy] ? sy0 + 1 : sy0;
-        const uint8_t* g = d.grid + (size_t)e * d.CS;
-        uint32_t dd[4];
-        const int cy[2] = {sy0 >> 6, sy1 >> 6}, cx[2] = {sx0 >> 6, sx1 >> 6};
-        for (int q = 0; q < 4; ++q) dd[q] = xw_cell_desc(d, e, g[cy[q >> 1] * r.W + cx[q & 1]]);
-        uint8_t v;
-        if (dd[0] == dd[1] && dd[0] == dd[2] && dd[0] == dd[3]) {
-            v = dd[0] == 0 ? 255 : r.T[(size_t)(dd[0] - 1) * r.FB + rem];
-        } else {
-            const int sy[2] = {sy0, sy1}, sx[2] = {sx0, sx1};
-            int px[4];
-            for (int q = 0; q < 4; ++q) px[q] = xw_canvas_tap(r, dd[q], sy[q >> 1], sx[q & 1], c);
-            v = xw_resize_px(px[0], px[1], px[2], px[3], t.xa0[dx], t.xa1[dx], t.ya0[dy], t.ya1[dy]);
-        }
-        frames[(size_t)e * env_stride + rem] = v;
+        frames[(size_t)e * env_stride + rem] = xw_generic_byte(d, r, e, rem);
     }
 }
-
 // --context > 1 (GameSimulator::shift_context, simulator.cpp:51-60): slots 1..K-1 -> 0..K-2, for the envs that were stepped
 // since their last render (flag 1).  An env that sat the step out (flag 0, XW_ACTION_NONE / not in a reset mask) keeps its
 // history; an env that was reset (flag 2) starts with a zero-filled context (init_screen, simulator.cpp:110-113).

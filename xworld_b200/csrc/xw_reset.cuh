@@ -32,17 +32,28 @@ XW_HD int m_nth(const XwMask& m, int k) {
     for (int i = 0; i < 4; ++i) {
         int c = xw_popc64(m.w[i]);
         if (k < c) {
+#if defined(__CUDA_ARCH__)
+            uint32_t w = (uint32_t)m.w[i];
+            int base = i * 64;
+            const int cl = __popc(w);
+            if (k >= cl) { k -= cl; w = (uint32_t)(m.w[i] >> 32); base += 32; }
+            return base + (int)__fns(w, 0, k + 1);  // position of the (k+1)-th set bit
+#else
             uint64_t v = m.w[i];
             for (int j = 0; j < k; ++j) v &= v - 1;  // drop k lowest set bits
-#if defined(__CUDA_ARCH__)
-            return i * 64 + (__ffsll((long long)v) - 1);
-#else
             return i * 64 + __builtin_ctzll(v);
 #endif
         }
         k -= c;
     }
     return -1;
+}
+// the cells 0 .. n-1
+XW_HD void m_first(XwMask& m, int n) {
+    for (int i = 0; i < 4; ++i) {
+        const int r = n - 64 * i;
+        m.w[i] = r >= 64 ? ~0ull : (r <= 0 ? 0ull : ((1ull << r) - 1));
+    }
 }
 
 XW_HD int xw_ctz64(uint64_t v) {
@@ -98,23 +109,96 @@ XW_HD bool ctx_free(const XwMapCtx& c, int x, int y) {  // (x,y,0) in env.availa
 }
 
 // -------------------------------------------------------------------------- maze + entities
-// Returns 0 on success.  `wall` receives the maze's '#' cells.
-XW_HD int xw_gen_map(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, int level, XwMapCtx& c) {
+// Where the maze DFS keeps its stack and where its draws come from are policies: the one-thread-per-env paths (host build,
+// full / masked reset) use a local array and evaluate Philox as they go; the per-step auto-reset launch (one warp per env)
+// keeps the stack in shared memory, and for attempt 0 the warp's lanes evaluate all of the maze's Philox blocks side by
+// side before lane 0 walks the maze (the draws are a pure function of the visit number, so only the walk is sequential).
+struct XwStackLocal {
+    uint32_t s[64];
+    XW_HD uint32_t get(int i) const { return s[i]; }
+    XW_HD void set(int i, uint32_t v) { s[i] = v; }
+};
+struct XwStackStrided {  // entry i of this lane's stack at p[i * 32] (lanes interleaved: no bank conflicts between lanes)
+    uint32_t* p;
+    XW_HD uint32_t get(int i) const { return p[i * 32]; }
+    XW_HD void set(int i, uint32_t v) { p[i * 32] = v; }
+};
+struct XwMazeDrawsLazy {
+    XwDrawSeq q;
+    XW_HD uint32_t operator()(uint32_t i) { return xw_draw_next(q, i); }
+};
+struct XwMazeDrawsTable {  // t != NULL: the draws were evaluated up front (attempt 0 of the warp path); else as they come
+    const uint32_t* t;
+    XwDrawSeq q;
+    XW_HD uint32_t operator()(uint32_t i) { return t ? t[i] : xw_draw_next(q, i); }
+};
+XW_HD int xw_maze_blocks(int D) {  // Philox blocks a D-sided maze consumes: 3 draws per node of its (nx x nx) graph
+    const int X = (D % 2 == 0) ? D - 1 : D, nx = (X + 1) / 2;
+    return (3 * nx * nx + 3) / 4;
+}
+
+// spanning_tree_maze_generator (python/maze2d.py:74-114): walls of a D x D maze as a bit mask, carved by an explicit-stack
+// DFS with 3 draws per visited node (random.shuffle of its 4 moves).  A stack entry packs x | y << 4 | next << 8 | order << 12.
+template <class Stack, class Draws>
+XW_HD void xw_maze_walls(int D, Stack& st, Draws& draw, XwMask& wall) {
+    m_zero(wall);
+    const int pad = (D % 2 == 0), X = pad ? D - 1 : D, nx = (X + 1) / 2;
+    {   // odd rows are all wall, even rows have wall at odd x (python/maze2d.py:80-86), a row at a time
+        const uint64_t full = (1ull << X) - 1, odd = 0xAAAAull & full;
+        for (int y = 0; y < X; ++y) m_or_bits(wall, y * D, (y & 1) ? full : odd);
+    }
+    uint64_t visited = 1ull;
+    uint32_t visit_no = 0;
+    int sp = 0;
+    auto push = [&](int px, int py) {
+        uint32_t ord = 0xE4u;  // moves 0 (-1,0), 1 (1,0), 2 (0,1), 3 (0,-1) in two-bit fields: identity order
+        for (int i = 3; i >= 1; --i) {  // random.shuffle: Fisher-Yates from the end
+            const uint32_t j = xw_randbelow(draw(visit_no * 3 + (uint32_t)(3 - i)), (uint32_t)i + 1);
+            const uint32_t a = (ord >> (2 * i)) & 3u, b = (ord >> (2 * j)) & 3u;
+            ord = (ord & ~((3u << (2 * i)) | (3u << (2 * j)))) | (b << (2 * i)) | (a << (2 * j));
+        }
+        st.set(sp, (uint32_t)px | ((uint32_t)py << 4) | (ord << 12));
+        ++visit_no; ++sp;
+    };
+    push(0, 0);
+    while (sp > 0) {
+        const uint32_t top = st.get(sp - 1);
+        const uint32_t next = (top >> 8) & 7u;
+        if (next == 4u) { --sp; continue; }
+        st.set(sp - 1, top + 0x100u);
+        const uint32_t m = (top >> (12 + 2 * next)) & 3u;
+        const int cx = (int)(top & 15u), cy = (int)((top >> 4) & 15u);
+        const int qx = cx + (int)((0x1120u >> (4 * m)) & 3u) - 1, qy = cy + (int)((0x0211u >> (4 * m)) & 3u) - 1;
+        if ((unsigned)qx < (unsigned)nx && (unsigned)qy < (unsigned)nx && !((visited >> (qy * nx + qx)) & 1ull)) {
+            m_clr(wall, (cy + qy) * D + (cx + qx));  // the edge's mid-point (maze2d.py:105-108)
+            visited |= 1ull << (qy * nx + qx);
+            push(qx, qy);
+        }
+    }
+    if (pad) {
+        for (int i = 0; i < X; ++i) if (i & 1) m_set(wall, X * D + i);
+        for (int i = 0; i < D; ++i) if (i & 1) m_set(wall, i * D + X);
+    }
+}
+
+// Returns 0 on success.
+template <class Stack, class Draws>
+XW_HD int xw_gen_map_t(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, int level, XwMapCtx& c, Stack& st, Draws& mz) {
     int D = d.H, nG = d.G, nB = d.n_blocks;
     if (d.curriculum != 0) xw_level_dims(level, D, nG, nB);  // set_dims(current_dim, current_dim), XWorldNav.py:58
     c.H = D; c.W = D; c.nG = nG; c.nB = nB;
-    m_zero(c.inrange); m_zero(c.block); m_zero(c.goal);
-    for (int i = 0; i < D * D; ++i) m_set(c.inrange, i);
+    m_first(c.inrange, D * D); m_zero(c.block); m_zero(c.goal);
     // ---- goal names: shuffle(goal_names) then pop() per goal == partial Fisher-Yates from the end;
     //      the touched positions are kept in a tiny sparse map instead of an n_names array
     {
         int keys[2 * XW_MAX_GOALS], vals[2 * XW_MAX_GOALS], cnt = 0;
         const int n = d.n_names;
+        XwDrawSeq nq = xw_draw_seq(d.seed, gid, ep, att, XW_SITE_NAMES);
         for (int k = 0; k < nG; ++k) {
             int i = n - 1 - k, vi = i;
             for (int q = 0; q < cnt; ++q) if (keys[q] == i) vi = vals[q];
             if (i >= 1) {
-                int j = (int)xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_NAMES, (uint32_t)k), (uint32_t)i + 1);
+                int j = (int)xw_randbelow(xw_draw_next(nq, (uint32_t)k), (uint32_t)i + 1);
                 int vj = j, qj = -1;
                 for (int q = 0; q < cnt; ++q) if (keys[q] == j) { vj = vals[q]; qj = q; }
                 // a[i] <-> a[j]; position i is final, only a[j] needs remembering
@@ -124,65 +208,23 @@ XW_HD int xw_gen_map(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, int
             c.gname[k] = vi;
         }
     }
-    // ---- maze: walls as a bit mask, carved by an explicit-stack DFS with 3 draws per visited node
-    XwMask wall; m_zero(wall);
-    const int pad = (D % 2 == 0), X = pad ? D - 1 : D, nx = (X + 1) / 2;
-    {   // odd rows are all wall, even rows have wall at odd x (python/maze2d.py:80-86), a row at a time
-        const uint64_t full = (1ull << X) - 1, odd = 0xAAAAull & full;
-        for (int y = 0; y < X; ++y) m_or_bits(wall, y * D, (y & 1) ? full : odd);
-    }
-    {
-        XwDrawSeq mz = xw_draw_seq(d.seed, gid, ep, att, XW_SITE_MAZE);
-        uint8_t sx[64], sy[64], snext[64], sorder[64];
-        uint64_t visited = 0;
-        int sp = 0;
-        uint32_t visit_no = 0;
-        int px = 0, py = 0;
-        bool push = true;
-        while (true) {
-            if (push) {
-                uint32_t o0 = 0, o1 = 1, o2 = 2, o3 = 3;  // moves (-1,0),(1,0),(0,1),(0,-1)
-                uint32_t ord[4] = {o0, o1, o2, o3};
-                for (int i = 3; i >= 1; --i) {
-                    uint32_t j = xw_randbelow(xw_draw_next(mz, visit_no * 3 + (uint32_t)(3 - i)), (uint32_t)i + 1);
-                    uint32_t t = ord[i]; ord[i] = ord[j]; ord[j] = t;
-                }
-                sx[sp] = (uint8_t)px; sy[sp] = (uint8_t)py; snext[sp] = 0;
-                sorder[sp] = (uint8_t)(ord[0] | (ord[1] << 2) | (ord[2] << 4) | (ord[3] << 6));
-                visited |= 1ull << (py * nx + px);
-                ++visit_no; ++sp;
-                push = false;
-            }
-            if (sp == 0) break;
-            int top = sp - 1;
-            if (snext[top] == 4) { --sp; continue; }
-            int m = (sorder[top] >> (2 * snext[top])) & 3;
-            ++snext[top];
-            int qx = sx[top] + (m == 0 ? -1 : m == 1 ? 1 : 0);
-            int qy = sy[top] + (m == 2 ? 1 : m == 3 ? -1 : 0);
-            if (qx >= 0 && qx < nx && qy >= 0 && qy < nx && !((visited >> (qy * nx + qx)) & 1ull)) {
-                m_clr(wall, (sy[top] + qy) * D + (sx[top] + qx));
-                px = qx; py = qy; push = true;
-            }
-        }
-    }
-    if (pad) {
-        for (int i = 0; i < X; ++i) if (i & 1) m_set(wall, X * D + i);
-        for (int i = 0; i < D; ++i) if (i & 1) m_set(wall, i * D + X);
-    }
+    // ---- maze
+    XwMask wall;
+    xw_maze_walls(D, st, mz, wall);
     const int nb = m_count(wall);
     if (nb < nB) return 1;
     // ---- goals (loc + icon variant), in creation order
     XwMask avail;
     for (int i = 0; i < 4; ++i) avail.w[i] = c.inrange.w[i] & ~wall.w[i];
+    XwDrawSeq lq = xw_draw_seq(d.seed, gid, ep, att, XW_SITE_GOAL_LOC), aq = xw_draw_seq(d.seed, gid, ep, att, XW_SITE_GOAL_ASSET);
     for (int k = 0; k < nG; ++k) {
         int nf = m_count(avail);
         if (nf == 0) return 1;
-        int cell = m_nth(avail, (int)xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_GOAL_LOC, (uint32_t)k), (uint32_t)nf));
+        int cell = m_nth(avail, (int)xw_randbelow(xw_draw_next(lq, (uint32_t)k), (uint32_t)nf));
         m_clr(avail, cell); m_set(c.goal, cell);
         c.gcell[k] = cell;
         int f = d.name_first[c.gname[k]], nv = d.name_first[c.gname[k] + 1] - f;
-        c.gicon[k] = d.name_icons[f + (int)xw_randbelow(xw_draw(d.seed, gid, ep, att, XW_SITE_GOAL_ASSET, (uint32_t)k), (uint32_t)nv)];
+        c.gicon[k] = d.name_icons[f + (int)xw_randbelow(xw_draw_next(aq, (uint32_t)k), (uint32_t)nv)];
     }
     // ---- blocks: shuffle(blocks) + pop() per block entity == partial Fisher-Yates over the wall list
     {
@@ -220,6 +262,13 @@ XW_HD int xw_gen_map(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, int
         }
     }
     return 0;
+}
+
+XW_HD int xw_gen_map(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, int level, XwMapCtx& c) {
+    XwStackLocal st;
+    XwMazeDrawsLazy mz;
+    mz.q = xw_draw_seq(d.seed, gid, ep, att, XW_SITE_MAZE);
+    return xw_gen_map_t(d, gid, ep, att, level, c, st, mz);
 }
 
 // -------------------------------------------------------------------------- BFS
@@ -542,6 +591,14 @@ XW_HD int xw_reset_attempt(const XwDev& d, int64_t gid, uint32_t ep, uint32_t at
     if (d.rules != XW_RULES_NAV3D) return 1;
     return xw_idle3d(d, gid, ep, att, task, c, o) ? 1 : 0;
 }
+template <class Stack, class Draws>
+XW_HD int xw_reset_attempt_t(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, int task, int level, XwMapCtx& c, XwTaskOut& o,
+                             Stack& st, Draws& mz) {
+    o.tmask = o.aux0 = o.aux1 = o.aux2 = 0;
+    if (xw_gen_map_t(d, gid, ep, att, level, c, st, mz)) return 2;
+    if (d.rules != XW_RULES_NAV3D) return 1;
+    return xw_idle3d(d, gid, ep, att, task, c, o) ? 1 : 0;
+}
 
 // Write the episode a successful attempt produced into the env's state.
 XW_HD void xw_reset_commit(const XwDev& d, int e, uint32_t ep, uint32_t minstd, int task, XwMapCtx& c, XwTaskOut o) {
@@ -606,7 +663,6 @@ XW_HD void xw_reset_commit(const XwDev& d, int e, uint32_t ep, uint32_t minstd, 
     d.num_steps[e] = 0;
     d.minstd[e] = minstd;
     d.error[e] = 0;  // a new game: the invalid-action flag of the old one is gone
-    if (d.stage_over) { d.stage_over[e] = 0; d.stage_rew[e] = 0.f; }
     if (d.ctx_flag) d.ctx_flag[e] = 2;  // init_screen: the context of a new game starts zero-filled (simulator.cpp:110-113)
 }
 
@@ -673,7 +729,16 @@ XW_HD void xw_reset_env(const XwDev& d, int e) {
 // independent pure functions of (env, episode, attempt), so taking the lowest-numbered lane that did not ask for a
 // retry is exactly the sequential rule -- and the rare env that needs dozens of attempts no longer sets the duration
 // of the whole per-step reset launch (SMs were 14 % busy at C4).
-__device__ __forceinline__ void xw_reset_env_warp(const XwDev& d, int e) {
+// one copy of an attempt's code for both call sites of the warp path
+__device__ __noinline__ int xw_reset_attempt_w(const XwDev& d, int64_t gid, uint32_t ep, uint32_t att, int task, int level, XwMapCtx& c,
+                                               XwTaskOut& o, XwStackStrided& st, XwMazeDrawsTable& mz) {
+    return xw_reset_attempt_t(d, gid, ep, att, task, level, c, o, st, mz);
+}
+
+// Shared memory of one warp of the auto-reset launch: the DFS stacks of its 32 lanes (interleaved) and attempt 0's maze draws.
+#define XW_RESET_STACK_WORDS (64 * 32)
+#define XW_RESET_DRAW_WORDS 192
+__device__ __forceinline__ void xw_reset_env_warp(const XwDev& d, int e, uint32_t* s_stack, uint32_t* s_draws) {
     const int lane = threadIdx.x & 31;
     const int64_t gid = d.gid0 + e;
     const uint32_t ep = (uint32_t)(d.episode[e] + 1);
@@ -687,14 +752,29 @@ __device__ __forceinline__ void xw_reset_env_warp(const XwDev& d, int e) {
     level = __shfl_sync(0xffffffffu, level, 0);
     XwMapCtx c;
     XwTaskOut o;
+    XwStackStrided stk;
+    stk.p = s_stack + lane;
+    {   // attempt 0's maze draws: Philox block b on lane b % 32 (the walk itself is sequential, its random numbers are not)
+        const int D = d.curriculum != 0 ? 3 + level : d.H, nblk = xw_maze_blocks(D);
+        for (int b = lane; b < nblk; b += 32) {
+            const XwDraw4 v = xw_draw_block(d.seed, gid, ep, 0, XW_SITE_MAZE, (uint32_t)b);
+            s_draws[4 * b] = v.v0; s_draws[4 * b + 1] = v.v1; s_draws[4 * b + 2] = v.v2; s_draws[4 * b + 3] = v.v3;
+        }
+        __syncwarp();
+    }
     int st = 0;
-    if (lane == 0) st = xw_reset_attempt(d, gid, ep, 0, task, level, c, o);
+    XwMazeDrawsTable mz;
+    if (lane == 0) {
+        mz.t = s_draws;
+        st = xw_reset_attempt_w(d, gid, ep, 0, task, level, c, o, stk, mz);
+    }
     st = __shfl_sync(0xffffffffu, st, 0);
     if (st != 0 || !nav3d) {
         if (lane == 0) {
             if (st == 1) xw_reset_commit(d, e, ep, minstd, task, c, o);
             else d.error[e] = XW_ERR_INVALID_ARG;
         }
+        __syncwarp();
         return;
     }
     // rounds of `retry_width` attempts, then 32 at a time (a round costs up to its width in divergent lanes; most
@@ -702,16 +782,23 @@ __device__ __forceinline__ void xw_reset_env_warp(const XwDev& d, int e) {
     uint32_t width = (uint32_t)d.retry_width;
     for (uint32_t base = 1; base < 64; base += width, width = 32) {
         const uint32_t att = base + lane;
-        st = ((uint32_t)lane < width && att < 64) ? xw_reset_attempt(d, gid, ep, att, task, level, c, o) : 0;
+        st = 0;
+        if ((uint32_t)lane < width && att < 64) {
+            mz.t = nullptr;
+            mz.q = xw_draw_seq(d.seed, gid, ep, att, XW_SITE_MAZE);
+            st = xw_reset_attempt_w(d, gid, ep, att, task, level, c, o, stk, mz);
+        }
         const unsigned done = __ballot_sync(0xffffffffu, st != 0);
         if (done) {
             if (lane == __ffs(done) - 1) {
                 if (st == 1) xw_reset_commit(d, e, ep, minstd, task, c, o);
                 else d.error[e] = XW_ERR_INVALID_ARG;
             }
+            __syncwarp();
             return;
         }
     }
     if (lane == 0) d.error[e] = XW_ERR_INVALID_ARG;
+    __syncwarp();
 }
 #endif
