@@ -414,7 +414,8 @@ def traffic_for(key, n):
     return ent["dram_bytes_per_launch"], rec.get("capture")
 
 
-KERNEL_NAMES = {3: "k_render_sp", 1: "k_render_sb", 2: "k_render", 0: "k_render_generic", 4: "k_render_fpv_generic", 5: "k_render_fpv"}
+KERNEL_NAMES = {3: "k_render_sp", 1: "k_render_sb", 2: "k_render", 0: "k_render_generic", 4: "k_render_fpv_generic", 5: "k_render_fpv",
+                6: "k_render_fpv_cells"}
 
 
 def run_xworld(key, n, steps, warmup, rank, world, local_rank, dist, dev, sampler=None, e2e_mode="full"):

@@ -325,7 +325,9 @@ int64_t xw_launch_count(const xw_sim* sim);
 /* Which render kernel the handle uses (diagnostics, tests): 0 = generic per-byte kernel, 1 = plan compositor with
  * one frame buffer per warp group, 2 = pipelined plan compositor, 3 = sparse painter (the default when the frame
  * geometry allows; XW_RENDER_MODE=sb|pipe selects the others); first-person view: 4 = per-pixel kernel (any frame size),
- * 5 = shared-memory frame kernel (frame width % 4 == 0 and frame bytes % 16 == 0); -1 = the game has no renderer.  No reference
+ * 5 = shared-memory frame kernel (frame width % 4 == 0 and frame bytes % 16 == 0), 6 = the same by whole cell blocks
+ * (geometries where every frame pixel takes its taps from one cell, e.g. visible_radius 7 on an 11x11 map);
+ * -1 = the game has no renderer.  No reference
  * counterpart: the reference has one OpenCV code path (xworld_simulator.cpp:278-307). */
 int32_t xw_render_kernel(const xw_sim* sim);
 /* CUDA-event timing of the render kernel alone: average ms over the launches since the last

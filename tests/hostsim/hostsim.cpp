@@ -34,7 +34,9 @@ struct HostSim {
     // first-person view
     XwFpv fpv;
     std::vector<int16_t> ft[12];
-    std::vector<uint8_t> agent4, gcache, pmap, Tb, Ta;
+    std::vector<uint8_t> agent4, pmap, Tb, Ta, c2b;
+    std::vector<uint32_t> gcache;
+    std::vector<uint16_t> taps;
     std::vector<int16_t> itab;
     std::vector<double> yaw_cs;
     int32_t n_invalid = 0;
@@ -131,11 +133,30 @@ HostSim* hs_create(const xw_config* c, const xw_catalog* cat, int n) {
         s->itab.resize(32 * 32 * 4);
         xw_fpv_build_itab(s->itab.data());
         F.itab = s->itab.data();
-        s->gcache.assign((size_t)n * F.G * 12288, 0);
+        s->gcache.assign((size_t)n * F.G * 4096, 0);
         F.gcache = s->gcache.data();
         s->pmap.assign((size_t)4 * OH * OW, 0); s->Tb.assign((size_t)12 * OH * OW, 0); s->Ta.assign((size_t)12 * OH * OW, 0);
         for (size_t i = 0; i < (size_t)4 * OH * OW; ++i) xw_fpv_table_entry(F, i, s->pmap.data(), s->Tb.data(), s->Ta.data());
         F.pmap = s->pmap.data(); F.Tb = s->Tb.data(); F.Ta = s->Ta.data();
+        if (OW % 4 == 0 && F.FB % 16 == 0 && OW == OH && OW % F.vr == 0 && (OW / F.vr) % 4 == 0) {  // create_fpv's "regular" test
+            const int bs = OW / F.vr, ncell = F.vr * F.vr;
+            s->c2b.assign((size_t)4 * ncell, 0xff);
+            bool regular = true;
+            for (int f = 0; f < 4 && regular; ++f)
+                for (int p = 0; p < OH * OW && regular; ++p) {
+                    const int blk = ((p / OW) / bs) * F.vr + (p % OW) / bs;
+                    const uint8_t cell = s->pmap[(size_t)f * OH * OW + p];
+                    if (cell == 0xff || cell >= ncell) { regular = false; break; }
+                    uint8_t& slot = s->c2b[(size_t)f * ncell + cell];
+                    if (slot == 0xff) slot = (uint8_t)blk; else if (slot != blk) regular = false;
+                }
+            for (uint8_t v : s->c2b) if (v == 0xff) regular = false;
+            if (regular) {
+                s->taps.assign((size_t)4 * OH * OW * 32, 0);
+                for (size_t i = 0; i < (size_t)4 * OH * OW; ++i) xw_fpv_tap_entry(F, i, s->taps.data());
+                F.regular = 1; F.bs = bs; F.taps = s->taps.data(); F.cell2block = s->c2b.data();
+            }
+        }
         s->r.OH = OH; s->r.OW = OW; s->r.FB = F.FB;
         return s;
     }
@@ -261,11 +282,9 @@ static void hs_warp_goals(HostSim* s, int e) {
         for (int i = 0; i < 64; ++i)
             xw_fpv_warp_coeffs(d.yaw_cs, d.goal_yaw[k], d.goal_scale[k], d.goal_offset[k], i, &co[0][i], &co[1][i], &co[2][i], &co[3][i]);
         const uint8_t* icon = F.atlas64 + (size_t)d.goal_icon[k] * 12288;
-        uint8_t* dst = F.gcache + ((size_t)e * F.G + g) * 12288;
-        for (int p = 0; p < 4096; ++p) {
-            const uint32_t v = xw_fpv_warp_px(icon, F.itab, (co[2][p >> 6] + co[0][p & 63]) >> 5, (co[3][p >> 6] + co[1][p & 63]) >> 5);
-            dst[p * 3] = (uint8_t)v; dst[p * 3 + 1] = (uint8_t)(v >> 8); dst[p * 3 + 2] = (uint8_t)(v >> 16);
-        }
+        uint32_t* dst = F.gcache + ((size_t)e * F.G + g) * 4096;
+        for (int p = 0; p < 4096; ++p)
+            dst[p] = xw_fpv_warp_px(icon, F.itab, (co[2][p >> 6] + co[0][p & 63]) >> 5, (co[3][p >> 6] + co[1][p & 63]) >> 5);
     }
 }
 static void hs_reset_one(HostSim* s, int e) { xw_reset_env(s->d, e); hs_warp_goals(s, e); }
@@ -300,9 +319,29 @@ static void hs_render_fpv(HostSim* s, uint8_t* frames, int mode) {
     for (int e = 0; e < d.n; ++e) {
         for (int k = 0; k < F.vr; ++k) xw_fpv_cells_line(d, e, k, ccode);
         XwFpvEnvFetch fe;
-        fe.F = &F; fe.ccode = ccode; fe.gc = F.gcache + (size_t)e * F.G * 12288; fe.facing = d.facing[e];
+        fe.F = &F; fe.ccode = ccode; fe.gc = F.gcache + (size_t)e * F.G * 4096; fe.facing = d.facing[e];
         uint8_t* out = frames + (size_t)e * F.FB;
         const int f = d.facing[e];
+        if (mode != 2 && F.regular) {  // k_render_fpv_cells: white fill, then cell blocks
+            memset(out, 0x5a, F.FB);   // (every cell block is written: nothing of this survives)
+            const int vr = F.vr, bs = F.bs;
+            for (int c = 0; c < vr * vr; ++c) {
+                const int code = ccode[c];
+                const int blk = F.cell2block[f * vr * vr + c], by = blk / vr, bx = blk % vr;
+                for (int i = 0; i < bs * bs; ++i) {
+                    const int p = (by * bs + i / bs) * F.OW + bx * bs + i % bs;
+                    uint32_t v = 0;
+                    if (code >= XW_CELL_GOAL0 && code != XW_FPV_BLACK) v = xw_fpv_px_taps(F.taps + ((size_t)f * plane + p) * 32, fe.gc + (size_t)(code - XW_CELL_GOAL0) * 4096);
+                    else if (code == XW_CELL_EMPTY) v = 0xffffffu;
+                    else if (code != XW_FPV_BLACK) {
+                        const uint8_t* t = (code == XW_CELL_BLOCK ? F.Tb : F.Ta) + (size_t)f * 3 * plane + p;
+                        v = (uint32_t)t[0] | ((uint32_t)t[plane] << 8) | ((uint32_t)t[2 * (size_t)plane] << 16);
+                    }
+                    out[p] = (uint8_t)v; out[plane + p] = (uint8_t)(v >> 8); out[2 * plane + p] = (uint8_t)(v >> 16);
+                }
+            }
+            continue;
+        }
         for (int p = 0; p < plane; ++p) {
             const int id = F.pmap[(size_t)f * plane + p];
             const int code = id == 255 ? -1 : ccode[id];

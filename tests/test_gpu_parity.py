@@ -544,7 +544,7 @@ def test_fpv_golden_frames_from_real_opencv(backend_cls):
         assert (got == want).all(), (tag, n, int((got != want).sum()))
         kernels.add(eng.sim.render_kernel())
         n += 1
-    assert n == 42 and kernels == {4, 5}   # both the shared-memory kernel and the any-size one ran
+    assert n == 42 and kernels == {4, 5, 6}   # the any-size kernel, the shared-memory one and the cell-block one all ran
 
 
 def test_fpv_auto_reset_and_context(backend_cls, synthetic_catalog):

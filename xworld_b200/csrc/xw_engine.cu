@@ -144,6 +144,7 @@ struct xw_sim {
     // first-person view
     XwFpv fpv;
     bool fpv_fast = false;
+    void (*fpv_cells_fn)(XwDev, XwFpv, uint8_t*, size_t) = nullptr;
     int fpv_smem = 0, fpv_grid = 0;
     uint8_t* d_bgr = nullptr;       // --color=false: the colour frames the gray pass reads
     // race
@@ -257,7 +258,7 @@ static int create_fpv(xw_sim* s, const xw_catalog* cat, int OH, int OW) {
         std::vector<double> cs = xw_fpv_yaw_table();
         rc |= dupload(s, &d.yaw_cs, cs.data(), cs.size());
     }
-    rc |= dalloc(s, &F.gcache, (size_t)s->n * F.G * 12288, false);
+    rc |= dalloc(s, &F.gcache, (size_t)s->n * F.G * 4096, false);
     uint8_t *pmap = nullptr, *Tb = nullptr, *Ta = nullptr;
     rc |= dalloc(s, &pmap, (size_t)4 * OH * OW);
     rc |= dalloc(s, &Tb, (size_t)4 * 3 * OH * OW);
@@ -268,7 +269,43 @@ static int create_fpv(xw_sim* s, const xw_catalog* cat, int OH, int OW) {
     s->launches++;
     CUDA_TRY(cudaGetLastError());
     s->fpv_fast = OW % 4 == 0 && F.FB % 16 == 0;
-    if (s->fpv_fast) {
+    if (s->fpv_fast && OW == OH && OW % F.vr == 0 && (OW / F.vr) % 4 == 0) {
+        // regular geometry?  every frame pixel inside one cell, every bs x bs block one cell (pmap, copied back)
+        const int bs = OW / F.vr, ncell = F.vr * F.vr;
+        std::vector<uint8_t> pm((size_t)4 * OH * OW);
+        CUDA_TRY(cudaStreamSynchronize(s->own_stream));
+        CUDA_TRY(cudaMemcpy(pm.data(), pmap, pm.size(), cudaMemcpyDeviceToHost));
+        std::vector<uint8_t> c2b((size_t)4 * ncell, 0xff);
+        bool regular = true;
+        for (int f = 0; f < 4 && regular; ++f)
+            for (int p = 0; p < OH * OW && regular; ++p) {
+                const int y = p / OW, x = p % OW, blk = (y / bs) * F.vr + x / bs;
+                const uint8_t cell = pm[(size_t)f * OH * OW + p];
+                if (cell == 0xff || cell >= ncell) { regular = false; break; }
+                uint8_t& slot = c2b[(size_t)f * ncell + cell];
+                if (slot == 0xff) slot = (uint8_t)blk; else if (slot != blk) regular = false;
+            }
+        for (uint8_t v : c2b) if (v == 0xff) regular = false;
+        if (regular) {
+            uint16_t* taps = nullptr;
+            rc |= dalloc(s, &taps, (size_t)4 * OH * OW * 32, false);
+            rc |= dupload(s, &F.cell2block, c2b.data(), c2b.size());
+            if (rc) return rc;
+            F.regular = 1; F.bs = bs; F.taps = taps;
+            k_fpv_build_taps<<<s->n_sms * 4, 256, 0, s->own_stream>>>(F, taps);
+            s->launches++;
+            CUDA_TRY(cudaGetLastError());
+        }
+    }
+    if (s->fpv_fast && F.regular) {
+        s->fpv_smem = F.FB + 256;
+        s->fpv_cells_fn = F.bs == 12 && F.vr == 7 ? k_render_fpv_cells<256, 12, 7> : F.bs == 28 && F.vr == 3 ? k_render_fpv_cells<256, 28, 3>
+                        : F.bs == 84 && F.vr == 1 ? k_render_fpv_cells<256, 84, 1> : k_render_fpv_cells<256, 0, 0>;
+        CUDA_TRY(cudaFuncSetAttribute(s->fpv_cells_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, s->fpv_smem));
+        int per_sm = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s->fpv_cells_fn, 256, s->fpv_smem));
+        s->fpv_grid = s->n_sms * (per_sm > 0 ? per_sm : 1);
+    } else if (s->fpv_fast) {
         s->fpv_smem = F.FB + 2 * OH * OW + 256;
         int max_optin = 0;
         CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
@@ -719,7 +756,7 @@ int xw_sentence_compose(const xw_sentence_query* q, char* buf, size_t cap) {
 int64_t xw_launch_count(const xw_sim* s) { return s->launches; }
 int32_t xw_render_kernel(const xw_sim* s) {
     if (s->cfg.game != XW_GAME_XWORLD) return -1;
-    if (s->d.vr > 0) return s->fpv_fast ? 5 : 4;
+    if (s->d.vr > 0) return s->fpv_fast ? (s->fpv.regular ? 6 : 5) : 4;
     if (!s->tab.fast_ok) return 0;
     return s->render_sp ? 3 : (s->render_sb ? 1 : 2);
 }
@@ -779,7 +816,8 @@ static int launch_render(xw_sim* s, uint8_t* d_frames, cudaStream_t st, const Re
     if (s->d.vr > 0) {
         if (s->fpv_fast && dst_stride % 16 == 0) {
             const int grid = s->fpv_grid < s->n ? s->fpv_grid : s->n;
-            k_render_fpv<256><<<grid, 256, s->fpv_smem, st>>>(s->d, s->fpv, dst, dst_stride);
+            if (s->fpv.regular) s->fpv_cells_fn<<<grid, 256, s->fpv_smem, st>>>(s->d, s->fpv, dst, dst_stride);
+            else k_render_fpv<256><<<grid, 256, s->fpv_smem, st>>>(s->d, s->fpv, dst, dst_stride);
         } else {
             k_render_fpv_generic<<<s->n_sms * 8 < s->n ? s->n_sms * 8 : s->n, 256, 0, st>>>(s->d, s->fpv, dst, dst_stride);
         }

@@ -44,7 +44,13 @@ struct XwFpv {
     const uint8_t* atlas64;   // [n_icons][64][64][3] BGR
     int32_t brick_icon, agent_icon;
     const uint8_t* agent4;    // [4][64][64][3] the agent's icon for headings right, down, left, up
-    uint8_t* gcache;          // [n][G][64][64][3] warped goal icons of the current episode
+    uint32_t* gcache;         // [n][G][64][64] warped goal icons of the current episode, B | G << 8 | R << 16 per pixel
+    // regular geometries (every frame pixel takes all its taps from one cell, cell blocks a multiple of 4 pixels wide --
+    // e.g. the 84x84 view of visible_radius 7 or 3 on a map it divides evenly): k_render_fpv_cells
+    int32_t regular, bs;      // bs = pixels per cell block (OW / vr)
+    const uint8_t* cell2block;// [4][vr * vr]: crop cell -> its block (by * vr + bx) in the frame, per heading (derived from pmap)
+    const uint16_t* taps;     // [4][OH][OW][32]: per heading and frame pixel the 16 in-cell pixel offsets (y * 64 + x) of its taps and
+                              // the 12 weights of the two resizes (xw_fpv_tap_entry)
     const int16_t* itab;      // [32][32][4] cv::warpAffine's bilinear weights (sum 32768)
     const uint8_t* pmap;      // [4][OH][OW] crop cell (cy * vr + cx) that holds the whole footprint of the pixel, 0xff = none
     const uint8_t* Tb;        // [4][3][OH][OW] the pixel if that cell is a brick
@@ -115,7 +121,7 @@ XW_HD uint32_t xw_px3(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1
 
 // A view pixel of one env (B | G << 8 | R << 16).
 struct XwFpvEnvFetch {
-    const XwFpv* F; const uint8_t* ccode; const uint8_t* gc; int facing;
+    const XwFpv* F; const uint8_t* ccode; const uint32_t* gc; int facing;
     XW_HD uint32_t operator()(int vy, int vx) const {
         int cy, cx;
         if (!xw_fpv_unrotate(F->N, facing, vy, vx, &cy, &cx)) return 0u;
@@ -125,7 +131,7 @@ struct XwFpvEnvFetch {
         const int off = (((cy & 63) << 6) + (cx & 63)) * 3;
         if (code == XW_CELL_BLOCK) return xw_px3(F->atlas64 + (size_t)F->brick_icon * 12288 + off);
         if (code == XW_CELL_AGENT) return xw_px3(F->agent4 + facing * 12288 + off);
-        return xw_px3(gc + (size_t)(code - XW_CELL_GOAL0) * 12288 + off);
+        return gc[(size_t)(code - XW_CELL_GOAL0) * 4096 + (off / 3)];
     }
 };
 // Table building: every cell holds `src` (a 64x64x3 icon); records which crop cells the taps touch.
@@ -184,6 +190,60 @@ XW_HD void xw_fpv_table_entry(const XwFpv& F, size_t i, uint8_t* pmap, uint8_t* 
         Tb[((size_t)f * 3 + c) * plane + (size_t)oy * F.OW + ox] = (uint8_t)(vb >> (8 * c));
         Ta[((size_t)f * 3 + c) * plane + (size_t)oy * F.OW + ox] = (uint8_t)(va >> (8 * c));
     }
+}
+
+// Regular geometries: the taps of frame pixel (oy, ox) under heading f, as offsets inside the one cell that holds them all,
+// and the weights of the two resizes.  e[0..15]: tap (s2 * 4 + s1) -- s2 = (row, column) of the pixel's 2x2 taps in the
+// intermediate image, s1 = (row, column) of that pixel's 2x2 taps in the view -- as y * 64 + x inside the cell;
+// e[16..19]: horizontal weights (a0, a1) of resize 1 for the left / right intermediate column, e[20..23]: vertical (b0, b1)
+// for the upper / lower intermediate row; e[24..27]: a0, a1, b0, b1 of resize 2.  A copy (equal sizes) is weights (2048, 0).
+struct XwFpvTapFetch {
+    const XwFpv* F; int facing; mutable uint16_t* out; mutable int n;
+    XW_HD uint32_t operator()(int vy, int vx) const {
+        int cy, cx;
+        xw_fpv_unrotate(F->N, facing, vy, vx, &cy, &cx);
+        if (n < 16) out[n] = (uint16_t)(((cy & 63) << 6) | (cx & 63));
+        ++n;
+        return 0u;
+    }
+};
+XW_HD void xw_fpv_tap_entry(const XwFpv& F, size_t i, uint16_t* taps) {
+    const int ox = (int)(i % F.OW), oy = (int)((i / F.OW) % F.OH), f = (int)(i / ((size_t)F.OW * F.OH));
+    uint16_t* e = taps + i * 32;
+    for (int k = 0; k < 32; ++k) e[k] = 0;
+    XwFpvTapFetch tf;
+    tf.F = &F; tf.facing = f; tf.out = e; tf.n = 0;
+    int jx[2] = {ox, ox}, jy[2] = {oy, oy};
+    if (!F.ident2) {
+        jx[0] = F.x2ofs[ox]; jx[1] = jx[0] + 1 < F.CH ? jx[0] + 1 : F.CH - 1;
+        jy[0] = xw_clampi(F.y2ofs[oy], 0, F.CH - 1); jy[1] = xw_clampi(F.y2ofs[oy] + 1, 0, F.CH - 1);
+        e[24] = (uint16_t)F.x2a0[ox]; e[25] = (uint16_t)F.x2a1[ox]; e[26] = (uint16_t)F.y2a0[oy]; e[27] = (uint16_t)F.y2a1[oy];
+    } else { e[24] = 2048; e[25] = 0; e[26] = 2048; e[27] = 0; }
+    for (int s2 = 0; s2 < 4; ++s2) {
+        const int my = jy[s2 >> 1], mx = jx[s2 & 1];
+        if (F.ident1) { for (int s1 = 0; s1 < 4; ++s1) tf(my, mx); }
+        else {
+            const int sx0 = F.x1ofs[mx], sx1 = sx0 + 1 < F.N ? sx0 + 1 : F.N - 1;
+            const int sy = F.y1ofs[my], sy0 = xw_clampi(sy, 0, F.N - 1), sy1 = xw_clampi(sy + 1, 0, F.N - 1);
+            tf(sy0, sx0); tf(sy0, sx1); tf(sy1, sx0); tf(sy1, sx1);
+        }
+    }
+    for (int q = 0; q < 2; ++q) {
+        if (F.ident1) { e[16 + 2 * q] = 2048; e[17 + 2 * q] = 0; e[20 + 2 * q] = 2048; e[21 + 2 * q] = 0; }
+        else {
+            e[16 + 2 * q] = (uint16_t)F.x1a0[jx[q]]; e[17 + 2 * q] = (uint16_t)F.x1a1[jx[q]];
+            e[20 + 2 * q] = (uint16_t)F.y1a0[jy[q]]; e[21 + 2 * q] = (uint16_t)F.y1a1[jy[q]];
+        }
+    }
+}
+// frame pixel from its tap entry and the (64 x 64, 4 bytes per pixel) icon of its cell
+XW_HD uint32_t xw_fpv_px_taps(const uint16_t* e, const uint32_t* icon) {
+    uint32_t mid[4];
+#pragma unroll
+    for (int s2 = 0; s2 < 4; ++s2)
+        mid[s2] = xw_resize_px3(icon[e[4 * s2]], icon[e[4 * s2 + 1]], icon[e[4 * s2 + 2]], icon[e[4 * s2 + 3]],
+                                (int16_t)e[16 + 2 * (s2 & 1)], (int16_t)e[17 + 2 * (s2 & 1)], (int16_t)e[20 + 2 * (s2 >> 1)], (int16_t)e[21 + 2 * (s2 >> 1)]);
+    return xw_resize_px3(mid[0], mid[1], mid[2], mid[3], (int16_t)e[24], (int16_t)e[25], (int16_t)e[26], (int16_t)e[27]);
 }
 
 // ---------------------------------------------------------------------------------------- goal icons (cv::warpAffine)
@@ -281,11 +341,10 @@ __global__ void __launch_bounds__(256) k_fpv_warp_goals(XwDev d, XwFpv F, const 
                                    &co[1][threadIdx.x], &co[2][threadIdx.x], &co[3][threadIdx.x]);
             __syncthreads();
             const uint8_t* icon = F.atlas64 + (size_t)d.goal_icon[k] * 12288;
-            uint8_t* dst = F.gcache + ((size_t)e * F.G + g) * 12288;
+            uint32_t* dst = F.gcache + ((size_t)e * F.G + g) * 4096;
             for (int p = threadIdx.x; p < 4096; p += blockDim.x) {
                 const int y = p >> 6, x = p & 63;
-                const uint32_t v = xw_fpv_warp_px(icon, F.itab, (co[2][y] + co[0][x]) >> 5, (co[3][y] + co[1][x]) >> 5);
-                dst[p * 3] = (uint8_t)v; dst[p * 3 + 1] = (uint8_t)(v >> 8); dst[p * 3 + 2] = (uint8_t)(v >> 16);
+                dst[p] = xw_fpv_warp_px(icon, F.itab, (co[2][y] + co[0][x]) >> 5, (co[3][y] + co[1][x]) >> 5);
             }
         }
     }
@@ -300,7 +359,7 @@ __global__ void __launch_bounds__(256) k_render_fpv_generic(XwDev d, XwFpv F, ui
         if ((int)threadIdx.x < F.vr) xw_fpv_cells_line(d, e, threadIdx.x, ccode);
         __syncthreads();
         XwFpvEnvFetch fe;
-        fe.F = &F; fe.ccode = ccode; fe.gc = F.gcache + (size_t)e * F.G * 12288; fe.facing = d.facing[e];
+        fe.F = &F; fe.ccode = ccode; fe.gc = F.gcache + (size_t)e * F.G * 4096; fe.facing = d.facing[e];
         uint8_t* out = frames + (size_t)e * env_stride;
         for (int p = threadIdx.x; p < plane; p += blockDim.x) {
             const uint32_t v = xw_fpv_px(F, p / F.OW, p % F.OW, fe);
@@ -360,13 +419,97 @@ __global__ void __launch_bounds__(NT) k_render_fpv(XwDev d, XwFpv F, uint8_t* __
         // pass 2: exact evaluation, tap by tap
         {
             XwFpvEnvFetch fe;
-            fe.F = &F; fe.ccode = ccode; fe.gc = F.gcache + (size_t)e * F.G * 12288; fe.facing = facing;
+            fe.F = &F; fe.ccode = ccode; fe.gc = F.gcache + (size_t)e * F.G * 4096; fe.facing = facing;
             uint8_t* fb8 = (uint8_t*)fb;
             const int ns = n_slow;
             for (int i = tid; i < ns; i += NT) {
                 const int p = slow[i];
                 const uint32_t v = xw_fpv_px(F, p / F.OW, p % F.OW, fe);
                 fb8[p] = (uint8_t)v; fb8[plane + p] = (uint8_t)(v >> 8); fb8[2 * plane + p] = (uint8_t)(v >> 16);
+            }
+        }
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) { tma_store_1d(frames + (size_t)e * env_stride, fb, (uint32_t)F.FB); tma_commit(); }
+    }
+    if (tid == 0) tma_wait_all<0>();
+}
+
+__global__ void k_fpv_build_taps(XwFpv F, uint16_t* taps) {
+    const size_t total = (size_t)4 * F.OH * F.OW;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+        xw_fpv_tap_entry(F, i, taps);
+}
+
+// Frame kernel for regular geometries (XwFpv::regular): a frame is vr x vr blocks of bs x bs pixels, each a pure function
+// of its crop cell.  One CTA per env at a time: the buffer is filled with white; each warp then takes cells -- black
+// (outside the map / in a wall's shadow), brick and agent blocks are word copies of constants / the per-heading tables, a
+// goal block is evaluated pixel by pixel from the goal's warped icon through the precomputed tap entries -- and the frame
+// leaves with one TMA bulk store.  Dynamic shared memory: frame buffer [FB] | ccode[256].
+// (BS_T, VR_T: compile-time block size and window side for the common geometries -- the index arithmetic of the block loops is
+// divisions by these; 0 = read them from F)
+template <int NT, int BS_T, int VR_T>
+__global__ void __launch_bounds__(NT) k_render_fpv_cells(XwDev d, XwFpv F, uint8_t* __restrict__ frames, size_t env_stride) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t* fb = (uint32_t*)smem;
+    uint8_t* ccode = smem + F.FB;
+    const int vr = VR_T ? VR_T : F.vr, bs = BS_T ? BS_T : F.bs, bw = bs >> 2;
+    const int OW = BS_T ? BS_T * VR_T : F.OW, WR = OW >> 2, plane_w = OW * WR, plane = OW * OW;  // (regular frames are square)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = NT >> 5;
+    const int n_cells = vr * vr;
+    // the words of one plane of a cell block, dealt to the lanes once: slot k of a lane is word (lane + 32 k) of the block
+    constexpr int NW_T = BS_T * (BS_T / 4), NSLOT = NW_T > 0 && NW_T <= 256 ? (NW_T + 31) / 32 : 1;
+    int off[NSLOT];
+#pragma unroll
+    for (int k = 0; k < NSLOT; ++k) {
+        const int idx = lane + 32 * k;
+        off[k] = (NW_T > 0 && idx < NW_T) ? (idx / (BS_T / 4 > 0 ? BS_T / 4 : 1)) * WR + idx % (BS_T / 4 > 0 ? BS_T / 4 : 1) : -1;
+    }
+    for (int e = blockIdx.x; e < d.n; e += gridDim.x) {
+        if (tid == 0) tma_wait_read<0>();   // the previous frame has left the buffer
+        if (tid < vr) xw_fpv_cells_line(d, e, tid, ccode);
+        __syncthreads();
+        const int facing = d.facing[e];
+        const uint32_t* tb = (const uint32_t*)(F.Tb + (size_t)facing * 3 * plane);
+        const uint32_t* ta = (const uint32_t*)(F.Ta + (size_t)facing * 3 * plane);
+        const uint16_t* taps = F.taps + (size_t)facing * plane * 32;
+        const uint32_t* gc = F.gcache + (size_t)e * F.G * 4096;
+        const uint8_t* c2b = F.cell2block + facing * n_cells;
+        // every cell's block is written by one warp: white / black constants, brick / agent words of the per-heading tables,
+        // a goal's block pixel by pixel
+        for (int c = warp; c < n_cells; c += n_warps) {
+            const int code = ccode[c];
+            const int blk = c2b[c], by = blk / vr, bx = blk - by * vr;   // the cell's block in the frame
+            const int w0 = by * bs * WR + bx * bw;   // first word of the block in a plane
+            if (code >= XW_CELL_GOAL0 && code != XW_FPV_BLACK) {
+                const uint32_t* icon = gc + (size_t)(code - XW_CELL_GOAL0) * 4096;
+                uint8_t* fb8 = (uint8_t*)fb;
+                for (int i = lane; i < bs * bs; i += 32) {
+                    const int y = by * bs + i / bs, x = bx * bs + i % bs, p = y * OW + x;
+                    const uint32_t v = xw_fpv_px_taps(taps + (size_t)p * 32, icon);
+                    fb8[p] = (uint8_t)v; fb8[plane + p] = (uint8_t)(v >> 8); fb8[2 * plane + p] = (uint8_t)(v >> 16);
+                }
+                continue;
+            }
+            const bool table = code == XW_CELL_BLOCK || code == XW_CELL_AGENT;
+            const uint32_t* src = code == XW_CELL_BLOCK ? tb : ta;
+            const uint32_t fill = code == XW_CELL_EMPTY ? 0xffffffffu : 0u;
+            if (NW_T > 0 && NW_T <= 256) {
+#pragma unroll
+                for (int pl = 0; pl < 3; ++pl)
+#pragma unroll
+                    for (int k = 0; k < NSLOT; ++k)
+                        if (off[k] >= 0) {
+                            const int w = pl * plane_w + w0 + off[k];
+                            fb[w] = table ? src[w] : fill;
+                        }
+            } else {
+                const int cell_words = 3 * bs * bw;
+                for (int i = lane; i < cell_words; i += 32) {
+                    const int pl = i / (bs * bw), r = i - pl * (bs * bw), y = r / bw, x = r - y * bw;
+                    const int w = pl * plane_w + w0 + y * WR + x;
+                    fb[w] = table ? src[w] : fill;
+                }
             }
         }
         fence_async_smem();
