@@ -144,8 +144,14 @@ struct xw_sim {
     // first-person view
     XwFpv fpv;
     bool fpv_fast = false;
-    void (*fpv_cells_fn)(XwDev, XwFpv, uint8_t*, size_t) = nullptr;
-    int fpv_smem = 0, fpv_grid = 0;
+    void (*fpv_cells_fn)(XwDev, XwFpv, uint8_t*, size_t, const int32_t*, const int32_t*, int, int, int, int, int, int) = nullptr;
+    void (*fpv_goal_fn)(XwFpv, uint8_t*, size_t, int, int) = nullptr;
+    int fpv_smem = 0, fpv_grid = 0, fpv_nt = 256, fpv_ng = 1, fpv_goal_grid = 0, fpv_goal_nt = 160;
+    // the batch is rendered in fpv_chunks chunks: k_fpv_goal_cells of chunk k runs on fpv_stream beside the frame kernel of chunk k + 1
+    enum { FPV_MAX_CHUNKS = 8 };
+    int fpv_chunks = 1, fpv_parity = 0;
+    cudaStream_t fpv_stream = nullptr;
+    cudaEvent_t fpv_ev[FPV_MAX_CHUNKS + 1] = {};
     uint8_t* d_bgr = nullptr;       // --color=false: the colour frames the gray pass reads
     // race
     XwRaceCfg race;
@@ -287,24 +293,48 @@ static int create_fpv(xw_sim* s, const xw_catalog* cat, int OH, int OW) {
             }
         for (uint8_t v : c2b) if (v == 0xff) regular = false;
         if (regular) {
-            uint16_t* taps = nullptr;
-            rc |= dalloc(s, &taps, (size_t)4 * OH * OW * 32, false);
+            uint4* taps = nullptr;
+            rc |= dalloc(s, &taps, (size_t)4 * OH * OW * 4, false);
             rc |= dupload(s, &F.cell2block, c2b.data(), c2b.size());
+            std::vector<uint8_t> b2c(c2b.size());
+            for (int f = 0; f < 4; ++f)
+                for (int cell = 0; cell < ncell; ++cell) b2c[(size_t)f * ncell + c2b[(size_t)f * ncell + cell]] = (uint8_t)cell;
+            rc |= dupload(s, &F.block2cell, b2c.data(), b2c.size());
             if (rc) return rc;
-            F.regular = 1; F.bs = bs; F.taps = taps;
-            k_fpv_build_taps<<<s->n_sms * 4, 256, 0, s->own_stream>>>(F, taps);
+            F.regular = 1; F.bs = bs; F.taps4 = taps;
+            rc |= dalloc(s, &F.goal_count, 2 * ((size_t)xw_sim::FPV_MAX_CHUNKS + 1));
+            rc |= dalloc(s, &F.goal_list, (size_t)s->n * F.G, false);
+            if (rc) return rc;
+            k_fpv_build_taps<<<s->n_sms * 4, 256, 0, s->own_stream>>>(F, taps);  // (F.taps4 == taps)
             s->launches++;
             CUDA_TRY(cudaGetLastError());
         }
     }
     if (s->fpv_fast && F.regular) {
-        s->fpv_smem = F.FB + 256;
-        s->fpv_cells_fn = F.bs == 12 && F.vr == 7 ? k_render_fpv_cells<256, 12, 7> : F.bs == 28 && F.vr == 3 ? k_render_fpv_cells<256, 28, 3>
-                        : F.bs == 84 && F.vr == 1 ? k_render_fpv_cells<256, 84, 1> : k_render_fpv_cells<256, 0, 0>;
+        const int ncell = F.vr * F.vr;
+        s->fpv_nt = 128;
+        const int per_group = (F.FB + d.CS + ((ncell + 15) & ~15) + 16 + 127) & ~127;
+        s->fpv_ng = 8;
+        while (s->fpv_ng > 1 && s->fpv_ng * per_group > 200 * 1024) s->fpv_ng >>= 1;
+        s->fpv_smem = s->fpv_ng * per_group;
+        s->fpv_nt = 128 * s->fpv_ng;
+#define XW_FPV_PICK(NG)                                                                                                                  \
+        (F.bs == 12 && F.vr == 7 ? k_render_fpv_cells<128, NG, 12, 7> : F.bs == 28 && F.vr == 3 ? k_render_fpv_cells<128, NG, 28, 3>       \
+         : F.bs == 84 && F.vr == 1 ? k_render_fpv_cells<128, NG, 84, 1> : k_render_fpv_cells<128, NG, 0, 0>)
+        s->fpv_cells_fn = s->fpv_ng == 8 ? XW_FPV_PICK(8) : s->fpv_ng == 4 ? XW_FPV_PICK(4) : s->fpv_ng == 2 ? XW_FPV_PICK(2) : XW_FPV_PICK(1);
+#undef XW_FPV_PICK
+        s->fpv_goal_fn = F.bs == 12 && F.vr == 7 ? k_fpv_goal_cells<12, 7> : F.bs == 28 && F.vr == 3 ? k_fpv_goal_cells<28, 3>
+                       : F.bs == 84 && F.vr == 1 ? k_fpv_goal_cells<84, 1> : k_fpv_goal_cells<0, 0>;
+        s->fpv_goal_nt = F.bs * F.bs >= 160 ? 160 : ((F.bs * F.bs + 31) & ~31);
+        {
+            int per_sm = 0;
+            CUDA_TRY(cudaFuncSetAttribute(s->fpv_goal_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 + 16));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s->fpv_goal_fn, s->fpv_goal_nt, 16384 + 16));
+            s->fpv_goal_grid = s->n_sms * (per_sm > 0 ? per_sm : 1);
+        }
         CUDA_TRY(cudaFuncSetAttribute(s->fpv_cells_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, s->fpv_smem));
-        int per_sm = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s->fpv_cells_fn, 256, s->fpv_smem));
-        s->fpv_grid = s->n_sms * (per_sm > 0 ? per_sm : 1);
+        if (const char* ev = getenv("XW_FPV_CHUNKS")) { const int v = atoi(ev); if (v >= 1 && v <= xw_sim::FPV_MAX_CHUNKS) s->fpv_chunks = v; }
+        s->fpv_grid = s->n_sms;
     } else if (s->fpv_fast) {
         s->fpv_smem = F.FB + 2 * OH * OW + 256;
         int max_optin = 0;
@@ -694,6 +724,7 @@ void xw_destroy(xw_sim* s) {
     for (auto ev : s->ev2) cudaEventDestroy(ev);
     if (s->copy_stream) { cudaStreamDestroy(s->copy_stream); cudaEventDestroy(s->ev_step); cudaEventDestroy(s->ev_copy); cudaEventDestroy(s->ev_h2d); }
     if (s->ev_frames) cudaEventDestroy(s->ev_frames);
+    if (s->fpv_stream) { cudaStreamSynchronize(s->fpv_stream); cudaStreamDestroy(s->fpv_stream); for (auto& e : s->fpv_ev) cudaEventDestroy(e); }
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
 }
@@ -815,9 +846,38 @@ static int launch_render(xw_sim* s, uint8_t* d_frames, cudaStream_t st, const Re
     }
     if (s->d.vr > 0) {
         if (s->fpv_fast && dst_stride % 16 == 0) {
-            const int grid = s->fpv_grid < s->n ? s->fpv_grid : s->n;
-            if (s->fpv.regular) s->fpv_cells_fn<<<grid, 256, s->fpv_smem, st>>>(s->d, s->fpv, dst, dst_stride);
-            else k_render_fpv<256><<<grid, 256, s->fpv_smem, st>>>(s->d, s->fpv, dst, dst_stride);
+            if (s->fpv.regular) {
+                const int nch = s->fpv_chunks, G = s->fpv.G;
+                const int slots = xw_sim::FPV_MAX_CHUNKS + 1, pbase = (s->fpv_parity ^= 1) * slots, zbase = (s->fpv_parity ^ 1) * slots;
+                if (nch > 1 && !s->fpv_stream) {
+                    CUDA_TRY(cudaStreamCreateWithFlags(&s->fpv_stream, cudaStreamNonBlocking));
+                    for (auto& e : s->fpv_ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                }
+                for (int k = 0; k < nch; ++k) {
+                    const int env0 = (int)((int64_t)s->n * k / nch), cnt = (int)((int64_t)s->n * (k + 1) / nch) - env0;
+                    if (cnt <= 0) continue;
+                    int grid = s->fpv_grid - (fix ? fix->reserve : 0);
+                    const int need = (cnt + s->fpv_ng - 1) / s->fpv_ng;
+                    if (grid > need) grid = need;
+                    if (grid < 1) grid = 1;
+                    s->fpv_cells_fn<<<grid, s->fpv_nt, s->fpv_smem, st>>>(s->d, s->fpv, dst, dst_stride, nullptr, nullptr, env0, cnt, pbase + k, env0 * G, zbase, slots);
+                    if (s->trace && s->tr[5]) CUDA_TRY(cudaEventRecord(s->tr[5], st));
+                    cudaStream_t gs = st;
+                    if (nch > 1) {
+                        gs = s->fpv_stream;
+                        CUDA_TRY(cudaEventRecord(s->fpv_ev[k], st));
+                        CUDA_TRY(cudaStreamWaitEvent(gs, s->fpv_ev[k], 0));
+                    }
+                    s->fpv_goal_fn<<<s->fpv_goal_grid, s->fpv_goal_nt, 16384 + 16, gs>>>(s->fpv, dst, dst_stride, pbase + k, env0 * G);
+                    s->launches += 2;
+                }
+                s->launches--;   // (the common increment below counts one)
+                if (nch > 1) {
+                    CUDA_TRY(cudaEventRecord(s->fpv_ev[xw_sim::FPV_MAX_CHUNKS], s->fpv_stream));
+                    CUDA_TRY(cudaStreamWaitEvent(st, s->fpv_ev[xw_sim::FPV_MAX_CHUNKS], 0));
+                }
+            }
+            else k_render_fpv<256><<<s->fpv_grid < s->n ? s->fpv_grid : s->n, 256, s->fpv_smem, st>>>(s->d, s->fpv, dst, dst_stride);
         } else {
             k_render_fpv_generic<<<s->n_sms * 8 < s->n ? s->n_sms * 8 : s->n, 256, 0, st>>>(s->d, s->fpv, dst, dst_stride);
         }
@@ -849,13 +909,23 @@ static int launch_render(xw_sim* s, uint8_t* d_frames, cudaStream_t st, const Re
         const int rc2 = fix->after_painter();  // (the painter is queued: now the reset launch on its own stream, then `done`)
         if (rc2) return rc2;
         CUDA_TRY(cudaStreamWaitEvent(st, fix->done, 0));
-        // the painter again, in list mode: about one env per warp group at the expected queue length
-        int blocks = (fix->est + r.G - 1) / r.G;
-        if (blocks > s->render_grid) blocks = s->render_grid;
-        XwRender rl = r;
-        rl.env_list = fix->list; rl.env_count = fix->count;
-        s->render_list_fn<<<blocks, r.G * r.GT, s->render_smem, st>>>(s->d, rl, dst, dst_stride);
-        s->launches++;
+        if (s->d.vr > 0) {  // first-person view: the frame kernel and the goal kernel again, over the queue (its own goal-list slot)
+            const int slot = s->fpv_parity * (xw_sim::FPV_MAX_CHUNKS + 1) + xw_sim::FPV_MAX_CHUNKS;   // (the main pass zeroed nothing of this half)
+            int blocks = (fix->est + s->fpv_ng - 1) / s->fpv_ng;
+            if (blocks > s->fpv_grid) blocks = s->fpv_grid;
+            s->fpv_cells_fn<<<blocks, s->fpv_nt, s->fpv_smem, st>>>(s->d, s->fpv, dst, dst_stride, fix->list, fix->count, 0, 0, slot, 0, 0, 0);
+            blocks = 2 * fix->est < s->fpv_goal_grid ? 2 * fix->est : s->fpv_goal_grid;
+            s->fpv_goal_fn<<<blocks, s->fpv_goal_nt, 16384 + 16, st>>>(s->fpv, dst, dst_stride, slot, 0);
+            s->launches += 2;
+        } else {
+            // the painter again, in list mode: about one env per warp group at the expected queue length
+            int blocks = (fix->est + r.G - 1) / r.G;
+            if (blocks > s->render_grid) blocks = s->render_grid;
+            XwRender rl = r;
+            rl.env_list = fix->list; rl.env_count = fix->count;
+            s->render_list_fn<<<blocks, r.G * r.GT, s->render_smem, st>>>(s->d, rl, dst, dst_stride);
+            s->launches++;
+        }
     }
     if (s->cfg.gray) {
         k_gray<<<s->n_sms * 8, 256, 0, st>>>(s->d_bgr, out, s->n, r.OH * r.OW, (size_t)r.FB, env_stride);
@@ -916,7 +986,8 @@ static int step_xworld(xw_sim* s, const int32_t* d_actions, int act_rep, float* 
         if (!s->tr[0]) for (auto& e : s->tr) CUDA_TRY(cudaEventCreate(&e));
         if (s->trace_steps > 0 && s->trace_steps % 16 == 8 && s->reset_stream) {  // report an earlier step (complete by now)
             cudaEventSynchronize(s->tr[4]); cudaEventSynchronize(s->tr[3]);
-            float a = 0, b = 0, c2 = 0, d2 = 0;
+            float a = 0, b = 0, c2 = 0, d2 = 0, f2 = 0;
+            if (s->d.vr > 0 && cudaEventElapsedTime(&f2, s->tr[0], s->tr[5]) == cudaSuccess) fprintf(stderr, "XW_TRACE fpv frame kernel end %.1f us (a later step's)\n", f2 * 1e3);
             cudaEventElapsedTime(&a, s->tr[0], s->tr[1]); cudaEventElapsedTime(&b, s->tr[0], s->tr[2]);
             cudaEventElapsedTime(&c2, s->tr[0], s->tr[3]); cudaEventElapsedTime(&d2, s->tr[0], s->tr[4]);
             fprintf(stderr, "XW_TRACE step %d: k_step end %.1f us | painter end %.1f | reset end %.1f | re-paint end %.1f (reset_avg %.0f)\n",
@@ -933,10 +1004,16 @@ static int step_xworld(xw_sim* s, const int32_t* d_actions, int act_rep, float* 
     const int32_t* q_count = s->d.reset_count + s->step_parity;
     const int parity = s->step_parity;
     s->step_parity ^= 1;
-    const bool overlap = s->overlap_reset && s->cfg.auto_reset && d_frames && s->cfg.context == 1 && s->d.vr == 0 && s->tab.fast_ok && s->render_list_fn;
+    const bool fpv_ok = s->d.vr > 0 && s->fpv_fast && s->fpv.regular && !s->cfg.gray && ((size_t)s->cfg.context * s->C * s->r.OH * s->r.OW) % 16 == 0;
+    const bool overlap = s->overlap_reset && s->cfg.auto_reset && d_frames && s->cfg.context == 1 &&
+                         (s->d.vr == 0 ? (s->tab.fast_ok && s->render_list_fn != nullptr) : fpv_ok);
     if (overlap) {
         if (!s->reset_stream) {
-            CUDA_TRY(cudaStreamCreateWithFlags(&s->reset_stream, cudaStreamNonBlocking));
+            // (highest priority: when CTA slots come free -- the first-person view's frame kernel ending -- the reset chain's CTAs
+            //  are placed before the goal kernel's, which is queued on the render stream)
+            int prio_lo = 0, prio_hi = 0;
+            CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            CUDA_TRY(cudaStreamCreateWithPriority(&s->reset_stream, cudaStreamNonBlocking, prio_hi));
             CUDA_TRY(cudaEventCreateWithFlags(&s->ev_a, cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&s->ev_b, cudaEventDisableTiming));
             CUDA_TRY(cudaMallocHost((void**)&s->h_reset_cnt, 2 * sizeof(int32_t)));
@@ -949,15 +1026,25 @@ static int step_xworld(xw_sim* s, const int32_t* d_actions, int act_rep, float* 
         // one warp per queued env, reset_ctas_per_sm CTAs of 4 warps per reserved SM, about three rounds inside a render
         int reserve = (int)(s->reset_avg / (float)(s->reset_ctas_per_sm * 4 * 3)) + 1;
         if (reserve > s->n_sms / 8) reserve = s->n_sms / 8;
+        const bool fpv = s->d.vr > 0;
+        int reset_grid = reserve * s->reset_ctas_per_sm;
+        static const int fdbg = [] { const char* e = getenv("XW_FPV_DBG"); return e ? atoi(e) : 0; }();
+        if (fpv && (fdbg & 4)) reserve = 0;
         if (t1) CUDA_TRY(cudaEventRecord(t1, st));
         CUDA_TRY(cudaEventRecord(s->ev_a, st));
         CUDA_TRY(cudaStreamWaitEvent(s->reset_stream, s->ev_a, 0));
         RenderFix fix = {reserve, s->ev_b, q_list, q_count, (int)(s->reset_avg * 1.5f) + 16, nullptr};
         // (the painter first: its CTAs take their SMs before the reset launch, which waits for an event, can be placed)
-        fix.after_painter = [s, reserve, q_list, q_count, parity, tracing, st]() -> int {
+        fix.after_painter = [s, reset_grid, fpv, q_list, q_count, parity, tracing, st]() -> int {
             if (tracing) CUDA_TRY(cudaEventRecord(s->tr[2], st));
-            k_reset_list<<<reserve * s->reset_ctas_per_sm, 128, 0, s->reset_stream>>>(s->d, q_list, q_count);
+            static const int fdbg = [] { const char* e = getenv("XW_FPV_DBG"); return e ? atoi(e) : 0; }();
+            if (!(fpv && (fdbg & 2))) k_reset_list<<<reset_grid, 128, 0, s->reset_stream>>>(s->d, q_list, q_count);
             s->launches++;
+            if (fpv && !(fdbg & 1)) {  // the new episodes' goal icons (one CTA per queued env and goal)
+                const int g2 = (int)(s->reset_avg * 1.25f) * s->fpv.G + 8;
+                k_fpv_warp_goals<<<g2 < s->n_sms * 8 ? g2 : s->n_sms * 8, 256, 0, s->reset_stream>>>(s->d, s->fpv, nullptr, q_list, q_count);
+                s->launches++;
+            }
             if (tracing) CUDA_TRY(cudaEventRecord(s->tr[3], s->reset_stream));
             CUDA_TRY(cudaEventRecord(s->ev_b, s->reset_stream));
             static const bool nocnt = [] { const char* e = getenv("XW_OVERLAP_NOCNT"); return e && atoi(e) != 0; }();

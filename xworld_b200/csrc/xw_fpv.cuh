@@ -49,8 +49,13 @@ struct XwFpv {
     // e.g. the 84x84 view of visible_radius 7 or 3 on a map it divides evenly): k_render_fpv_cells
     int32_t regular, bs;      // bs = pixels per cell block (OW / vr)
     const uint8_t* cell2block;// [4][vr * vr]: crop cell -> its block (by * vr + bx) in the frame, per heading (derived from pmap)
+    const uint8_t* block2cell;// [4][vr * vr]: the inverse
     const uint16_t* taps;     // [4][OH][OW][32]: per heading and frame pixel the 16 in-cell pixel offsets (y * 64 + x) of its taps and
-                              // the 12 weights of the two resizes (xw_fpv_tap_entry)
+                              // the 12 weights of the two resizes (xw_fpv_tap_entry) -- the host mirror's layout (tests/hostsim)
+    int32_t* goal_count;      // [2][slots] k_render_fpv_cells -> k_fpv_goal_cells: the launch's visible goal cells (ping-pong),
+    uint64_t* goal_list;      // [n * G] env | (block | slot << 8 | heading << 16) << 32
+    const void* taps4;        // (uint4) the same entries on the device (the 16 offsets in bytes: x 4), quarter-major: [4][4 quarters of 8 values][OH * OW], so that the lanes
+                              // of a warp (consecutive pixels) read consecutive 16-byte words
     const int16_t* itab;      // [32][32][4] cv::warpAffine's bilinear weights (sum 32768)
     const uint8_t* pmap;      // [4][OH][OW] crop cell (cy * vr + cx) that holds the whole footprint of the pixel, 0xff = none
     const uint8_t* Tb;        // [4][3][OH][OW] the pixel if that cell is a brick
@@ -84,10 +89,8 @@ XW_HD bool xw_fpv_agent_src(int facing, int y, int x, int* sy, int* sx) {
 // XMap::image_masking (xmap.cpp:273-362) + the crop: class of every cell of the vr x vr window, ccode[cy * vr + cx].
 // One call computes the major line `k` (a column of the window when the agent looks up / down, a row otherwise): the
 // lines are independent, so vr lanes do them side by side.
-XW_HD void xw_fpv_cells_line(const XwDev& d, int e, int k, uint8_t* ccode) {
-    const int vr = d.vr, h = vr / 2;
-    const uint8_t* g = d.grid + (size_t)e * d.CS;
-    const int ax = d.agent_x[e], ay = d.agent_y[e], facing = d.facing[e];
+XW_HD void xw_fpv_cells_line_at(const uint8_t* g, int W, int H, int vr, int ax, int ay, int facing, int k, uint8_t* ccode) {
+    const int h = vr / 2;
     // window origin in map cells: x_st - vr, y_st - vr of the reference (the padded canvas is shifted by vr)
     int ox = ax - h, oy = ay - h;
     int major_x = 0, major_y = 0, minor_x = 0, minor_y = 0, scan_x = 0, scan_y = 0;
@@ -102,18 +105,21 @@ XW_HD void xw_fpv_cells_line(const XwDev& d, int e, int k, uint8_t* ccode) {
         int rx = ax, ry = ay;
         for (int j = 1; j < steps; ++j) {
             rx += o * major_x; ry += o * major_y;
-            if (rx >= 0 && rx < d.W && ry >= 0 && ry < d.H && g[ry * d.W + rx] == XW_CELL_BLOCK) block = true;
+            if (rx >= 0 && rx < W && ry >= 0 && ry < H && g[ry * W + rx] == XW_CELL_BLOCK) block = true;
         }
     }
     int cx = scan_x + k * major_x, cy = scan_y + k * major_y;
     for (int j = 0; j < vr; ++j) {
         const int gx = ox + cx, gy = oy + cy;
-        const bool in = gx >= 0 && gx < d.W && gy >= 0 && gy < d.H;
-        const int code = in ? g[gy * d.W + gx] : XW_FPV_BLACK;        // copyMakeBorder(..., Scalar(0, 0, 0))
+        const bool in = gx >= 0 && gx < W && gy >= 0 && gy < H;
+        const int code = in ? g[gy * W + gx] : XW_FPV_BLACK;          // copyMakeBorder(..., Scalar(0, 0, 0))
         ccode[cy * vr + cx] = (uint8_t)(block ? XW_FPV_BLACK : code);  // shadow cells are painted black (xmap.cpp:170-185)
         if (code == XW_CELL_BLOCK) block = true;
         cx += minor_x; cy += minor_y;  // (never wraps: vr steps from one edge of the window to the other)
     }
+}
+XW_HD void xw_fpv_cells_line(const XwDev& d, int e, int k, uint8_t* ccode) {
+    xw_fpv_cells_line_at(d.grid + (size_t)e * d.CS, d.W, d.H, d.vr, d.agent_x[e], d.agent_y[e], d.facing[e], k, ccode);
 }
 
 // ---------------------------------------------------------------------------------------- pixels
@@ -207,9 +213,8 @@ struct XwFpvTapFetch {
         return 0u;
     }
 };
-XW_HD void xw_fpv_tap_entry(const XwFpv& F, size_t i, uint16_t* taps) {
+XW_HD void xw_fpv_tap_values(const XwFpv& F, size_t i, uint16_t* e) {   // e[32]: entry i = (f * OH + oy) * OW + ox
     const int ox = (int)(i % F.OW), oy = (int)((i / F.OW) % F.OH), f = (int)(i / ((size_t)F.OW * F.OH));
-    uint16_t* e = taps + i * 32;
     for (int k = 0; k < 32; ++k) e[k] = 0;
     XwFpvTapFetch tf;
     tf.F = &F; tf.facing = f; tf.out = e; tf.n = 0;
@@ -236,6 +241,7 @@ XW_HD void xw_fpv_tap_entry(const XwFpv& F, size_t i, uint16_t* taps) {
         }
     }
 }
+XW_HD void xw_fpv_tap_entry(const XwFpv& F, size_t i, uint16_t* taps) { xw_fpv_tap_values(F, i, taps + i * 32); }
 // frame pixel from its tap entry and the (64 x 64, 4 bytes per pixel) icon of its cell
 XW_HD uint32_t xw_fpv_px_taps(const uint16_t* e, const uint32_t* icon) {
     uint32_t mid[4];
@@ -330,22 +336,21 @@ __global__ void k_fpv_build_tables(XwFpv F, uint8_t* pmap, uint8_t* Tb, uint8_t*
 __global__ void __launch_bounds__(256) k_fpv_warp_goals(XwDev d, XwFpv F, const uint8_t* mask, const int32_t* list, const int32_t* count) {
     __shared__ int co[4][64];
     const int cnt = list ? *count : d.n;
-    for (int i = blockIdx.x; i < cnt; i += gridDim.x) {
-        const int e = list ? list[i] : i;
+    for (int i = blockIdx.x; i < cnt * F.G; i += gridDim.x) {   // one CTA per (env, goal)
+        const int ei = i / F.G, g = i - ei * F.G;
+        const int e = list ? list[ei] : ei;
         if (!list && mask && !mask[e]) continue;
-        for (int g = 0; g < F.G; ++g) {
-            const size_t k = (size_t)g * d.n + e;
-            __syncthreads();
-            if (threadIdx.x < 64)
-                xw_fpv_warp_coeffs(d.yaw_cs, d.goal_yaw[k], d.goal_scale[k], d.goal_offset[k], threadIdx.x, &co[0][threadIdx.x],
-                                   &co[1][threadIdx.x], &co[2][threadIdx.x], &co[3][threadIdx.x]);
-            __syncthreads();
-            const uint8_t* icon = F.atlas64 + (size_t)d.goal_icon[k] * 12288;
-            uint32_t* dst = F.gcache + ((size_t)e * F.G + g) * 4096;
-            for (int p = threadIdx.x; p < 4096; p += blockDim.x) {
-                const int y = p >> 6, x = p & 63;
-                dst[p] = xw_fpv_warp_px(icon, F.itab, (co[2][y] + co[0][x]) >> 5, (co[3][y] + co[1][x]) >> 5);
-            }
+        const size_t k = (size_t)g * d.n + e;
+        __syncthreads();
+        if (threadIdx.x < 64)
+            xw_fpv_warp_coeffs(d.yaw_cs, d.goal_yaw[k], d.goal_scale[k], d.goal_offset[k], threadIdx.x, &co[0][threadIdx.x],
+                               &co[1][threadIdx.x], &co[2][threadIdx.x], &co[3][threadIdx.x]);
+        __syncthreads();
+        const uint8_t* icon = F.atlas64 + (size_t)d.goal_icon[k] * 12288;
+        uint32_t* dst = F.gcache + ((size_t)e * F.G + g) * 4096;
+        for (int p = threadIdx.x; p < 4096; p += blockDim.x) {
+            const int y = p >> 6, x = p & 63;
+            dst[p] = xw_fpv_warp_px(icon, F.itab, (co[2][y] + co[0][x]) >> 5, (co[3][y] + co[1][x]) >> 5);
         }
     }
 }
@@ -435,88 +440,198 @@ __global__ void __launch_bounds__(NT) k_render_fpv(XwDev d, XwFpv F, uint8_t* __
     if (tid == 0) tma_wait_all<0>();
 }
 
-__global__ void k_fpv_build_taps(XwFpv F, uint16_t* taps) {
-    const size_t total = (size_t)4 * F.OH * F.OW;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
-        xw_fpv_tap_entry(F, i, taps);
+__global__ void k_fpv_build_taps(XwFpv F, uint4* taps4) {
+    const size_t plane = (size_t)F.OH * F.OW, total = 4 * plane;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        __align__(16) uint16_t e[32];
+        xw_fpv_tap_values(F, i, e);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) e[k] = (uint16_t)(e[k] * 4);   // byte offsets into the staged icon (k_fpv_goal_cells)
+        const size_t f = i / plane, p = i - f * plane;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) taps4[(f * 4 + q) * plane + p] = ((const uint4*)e)[q];
+    }
 }
 
-// Frame kernel for regular geometries (XwFpv::regular): a frame is vr x vr blocks of bs x bs pixels, each a pure function
-// of its crop cell.  One CTA per env at a time: the buffer is filled with white; each warp then takes cells -- black
-// (outside the map / in a wall's shadow), brick and agent blocks are word copies of constants / the per-heading tables, a
-// goal block is evaluated pixel by pixel from the goal's warped icon through the precomputed tap entries -- and the frame
-// leaves with one TMA bulk store.  Dynamic shared memory: frame buffer [FB] | ccode[256].
-// (BS_T, VR_T: compile-time block size and window side for the common geometries -- the index arithmetic of the block loops is
-// divisions by these; 0 = read them from F)
-template <int NT, int BS_T, int VR_T>
-__global__ void __launch_bounds__(NT) k_render_fpv_cells(XwDev d, XwFpv F, uint8_t* __restrict__ frames, size_t env_stride) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint32_t* fb = (uint32_t*)smem;
-    uint8_t* ccode = smem + F.FB;
+// Frame kernels for regular geometries (XwFpv::regular): a frame is vr x vr blocks of bs x bs pixels, each a pure function of
+// its crop cell and the heading.
+//
+// k_render_fpv_cells -- everything but the goal cells.  One persistent CTA per SM, NG groups of NT threads, one env at a time per group:
+//   * warp 0 keeps the NEXT env's pose and grid row in registers (loaded one env time ahead), and between the frame's TMA store
+//     and the next paint turns them into the window's cell codes (image_masking: one lane per major line) and appends the
+//     visible goal cells to the launch's goal list in HBM, while thread 32 waits for the store to have read the buffer --
+//     nothing on the per-env path waits for HBM;
+//   * paint: work item = (band of cells, colour plane); lane = word column, so a lane's cell is fixed per item: white / black
+//     (outside the map, wall shadow) are constant words, brick / agent words go from the per-heading tables (L1 / L2) to the
+//     frame buffer as 4-byte cp.async copies (SASS LDGSTS) -- all of a warp's items in flight at once, one wait per env;
+//     goal blocks are left as they are (k_fpv_goal_cells overwrites them);
+//   * fence.proxy.async, barrier, ONE TMA bulk store per frame (evict-first).
+// k_fpv_goal_cells -- the goal cells of the launch, one CTA per (env, cell) of the list: the goal's warped icon (16 KB of the
+//   per-env cache) comes into shared memory with one TMA bulk load, each thread evaluates pixels through the precomputed tap
+//   entries (16 taps, five fixed-point bilinear steps) and writes them into the finished frame.  Kept out of the frame kernel
+//   because it needs 16 KB of shared memory and ~60 registers that would halve the frame kernel's occupancy, and because taken
+//   straight from global memory the scattered taps made the L1 data pipe the frame kernel's bound (profiles/r02_summary.md).
+// (48 registers: a CTA of 1,024 threads then leaves 16 K registers of its SM to the CTAs of k_fpv_warp_goals, which runs on the
+// reset stream beside this kernel.)
+// list != NULL: the envs list[0 .. *count) instead of envs [env0, env0 + env_n) (the re-paint of a step's auto-reset queue).
+// A launch covers one chunk of the batch: its goal cells go to goal_list + list_base, counted in goal_count[chunk], and
+// k_fpv_goal_cells of chunk k runs on a second stream beside the frame kernel of chunk k + 1 (the frame kernel is bound by
+// HBM writes, the goal kernel by instruction issue).
+// Dynamic shared memory of k_render_fpv_cells, per group: frame [FB] | grid row [CS] | cell codes [ceil16(vr^2)] | misc [4 x i32].
+// (BS_T, VR_T: compile-time block size and window side of the common geometries; 0 = read them from F)
+template <int NT, int NG, int BS_T, int VR_T>
+__global__ void __maxnreg__(48) k_render_fpv_cells(XwDev d, XwFpv F, uint8_t* __restrict__ frames, size_t env_stride,
+                                                                 const int32_t* __restrict__ list, const int32_t* __restrict__ count,
+                                                                 int env0, int env_n, int chunk, int list_base, int zero_base, int zero_n) {
+    extern __shared__ __align__(128) uint8_t smem_all[];
+    // the goal counters of the PREVIOUS launch (the other half of the ping-pong; its goal kernel is done: stream order) -> 0,
+    // so that no memset node sits between the step kernel and this one
+    if (blockIdx.x == 0 && (int)threadIdx.x < zero_n) F.goal_count[zero_base + threadIdx.x] = 0;
     const int vr = VR_T ? VR_T : F.vr, bs = BS_T ? BS_T : F.bs, bw = bs >> 2;
-    const int OW = BS_T ? BS_T * VR_T : F.OW, WR = OW >> 2, plane_w = OW * WR, plane = OW * OW;  // (regular frames are square)
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = NT >> 5;
-    const int n_cells = vr * vr;
-    // the words of one plane of a cell block, dealt to the lanes once: slot k of a lane is word (lane + 32 k) of the block
-    constexpr int NW_T = BS_T * (BS_T / 4), NSLOT = NW_T > 0 && NW_T <= 256 ? (NW_T + 31) / 32 : 1;
-    int off[NSLOT];
-#pragma unroll
-    for (int k = 0; k < NSLOT; ++k) {
-        const int idx = lane + 32 * k;
-        off[k] = (NW_T > 0 && idx < NW_T) ? (idx / (BS_T / 4 > 0 ? BS_T / 4 : 1)) * WR + idx % (BS_T / 4 > 0 ? BS_T / 4 : 1) : -1;
-    }
-    for (int e = blockIdx.x; e < d.n; e += gridDim.x) {
-        if (tid == 0) tma_wait_read<0>();   // the previous frame has left the buffer
-        if (tid < vr) xw_fpv_cells_line(d, e, tid, ccode);
-        __syncthreads();
-        const int facing = d.facing[e];
+    const int OW = bs * vr, WR = OW >> 2, plane_w = OW * WR, plane = OW * OW;  // (regular frames are square)
+    const int n_cells = vr * vr, nc16 = (n_cells + 15) & ~15;
+    // NG groups of NT threads, each a frame pipeline of its own (buffer, barrier, TMA stores): one CTA per SM, so that a launch on
+    // fewer CTAs than SMs leaves whole SMs to the auto-reset kernels that run beside it (xw_engine.cu step_xworld)
+    const int grp = threadIdx.x / NT, tid = threadIdx.x - grp * NT;
+    uint8_t* smem = smem_all + (size_t)grp * ((F.FB + d.CS + nc16 + 16 + 127) & ~127);
+    const int vcta = blockIdx.x * NG + grp, vgrid = gridDim.x * NG;
+    uint32_t* fb = (uint32_t*)smem;
+    uint8_t* row = smem + F.FB;
+    uint8_t* ccode = row + d.CS;
+    int* misc = (int*)(ccode + nc16);   // [1] heading
+    const uint8_t* __restrict__ b2c = F.block2cell;
+    const uint8_t* __restrict__ c2b = F.cell2block;
+    const int lane = tid & 31, warp = tid >> 5, n_warps = NT >> 5;
+    const int total = list ? *count : env_n;
+    int32_t* goal_count = F.goal_count + chunk;
+    uint64_t* goal_list = F.goal_list + list_base;
+    // warp 0: pose + grid row of the env after this one, in registers
+    const int row_words = d.CS >> 2;
+    uint32_t pre0 = 0, pre1 = 0;
+    int pre_ax = 0, pre_ay = 0, pre_f = 0;
+    auto prefetch = [&](int idx) {
+        if (idx >= total) return;
+        const int e = list ? list[idx] : env0 + idx;
+        const uint32_t* g = (const uint32_t*)(d.grid + (size_t)e * d.CS);
+        if (lane < row_words) pre0 = g[lane];
+        if (lane + 32 < row_words) pre1 = g[lane + 32];
+        pre_ax = d.agent_x[e]; pre_ay = d.agent_y[e]; pre_f = d.facing[e];
+    };
+    if (warp == 0) prefetch(vcta);
+    for (int idx = vcta; idx < total; idx += vgrid) {
+        const int e = list ? list[idx] : env0 + idx;
+        if (warp == 0) {
+            if (lane < row_words) ((uint32_t*)row)[lane] = pre0;
+            if (lane + 32 < row_words) ((uint32_t*)row)[lane + 32] = pre1;
+            if (lane == 0) misc[1] = pre_f;
+            __syncwarp();
+            for (int k = lane; k < vr; k += 32) xw_fpv_cells_line_at(row, d.W, d.H, vr, pre_ax, pre_ay, pre_f, k, ccode);
+            __syncwarp();
+            for (int c = lane; c < n_cells; c += 32) {
+                const int code = ccode[c];
+                if (code >= XW_CELL_GOAL0 && code != XW_FPV_BLACK) {
+                    const int k = atomicAdd(goal_count, 1);
+                    goal_list[k] = (uint64_t)(uint32_t)e | ((uint64_t)((uint32_t)c2b[pre_f * n_cells + c] | ((uint32_t)(code - XW_CELL_GOAL0) << 8) | ((uint32_t)pre_f << 16)) << 32);
+                }
+            }
+            prefetch(idx + vgrid);
+        } else if (tid == 32) {
+            tma_wait_read<0>();   // the previous frame has left the buffer
+        }
+        group_bar(1 + grp, NT);
+        const int facing = misc[1];
         const uint32_t* tb = (const uint32_t*)(F.Tb + (size_t)facing * 3 * plane);
         const uint32_t* ta = (const uint32_t*)(F.Ta + (size_t)facing * 3 * plane);
-        const uint16_t* taps = F.taps + (size_t)facing * plane * 32;
-        const uint32_t* gc = F.gcache + (size_t)e * F.G * 4096;
-        const uint8_t* c2b = F.cell2block + facing * n_cells;
-        // every cell's block is written by one warp: white / black constants, brick / agent words of the per-heading tables,
-        // a goal's block pixel by pixel
-        for (int c = warp; c < n_cells; c += n_warps) {
-            const int code = ccode[c];
-            const int blk = c2b[c], by = blk / vr, bx = blk - by * vr;   // the cell's block in the frame
-            const int w0 = by * bs * WR + bx * bw;   // first word of the block in a plane
-            if (code >= XW_CELL_GOAL0 && code != XW_FPV_BLACK) {
-                const uint32_t* icon = gc + (size_t)(code - XW_CELL_GOAL0) * 4096;
-                uint8_t* fb8 = (uint8_t*)fb;
-                for (int i = lane; i < bs * bs; i += 32) {
-                    const int y = by * bs + i / bs, x = bx * bs + i % bs, p = y * OW + x;
-                    const uint32_t v = xw_fpv_px_taps(taps + (size_t)p * 32, icon);
-                    fb8[p] = (uint8_t)v; fb8[plane + p] = (uint8_t)(v >> 8); fb8[2 * plane + p] = (uint8_t)(v >> 16);
-                }
-                continue;
-            }
-            const bool table = code == XW_CELL_BLOCK || code == XW_CELL_AGENT;
-            const uint32_t* src = code == XW_CELL_BLOCK ? tb : ta;
-            const uint32_t fill = code == XW_CELL_EMPTY ? 0xffffffffu : 0u;
-            if (NW_T > 0 && NW_T <= 256) {
-#pragma unroll
-                for (int pl = 0; pl < 3; ++pl)
-#pragma unroll
-                    for (int k = 0; k < NSLOT; ++k)
-                        if (off[k] >= 0) {
-                            const int w = pl * plane_w + w0 + off[k];
-                            fb[w] = table ? src[w] : fill;
-                        }
-            } else {
-                const int cell_words = 3 * bs * bw;
-                for (int i = lane; i < cell_words; i += 32) {
-                    const int pl = i / (bs * bw), r = i - pl * (bs * bw), y = r / bw, x = r - y * bw;
-                    const int w = pl * plane_w + w0 + y * WR + x;
-                    fb[w] = table ? src[w] : fill;
+        // ---- bands: item = (band by, plane pl); lane = word column
+        for (int item = warp; item < 3 * vr; item += n_warps) {
+            const int by = item / 3, pl = item - 3 * by;
+            for (int col = lane; col < WR; col += 32) {
+                const int bx = col / bw;
+                const int code = ccode[b2c[facing * n_cells + by * vr + bx]];
+                const int w0 = pl * plane_w + by * bs * WR + col;
+                if (code == XW_CELL_BLOCK || code == XW_CELL_AGENT) {
+                    const uint32_t* src = (code == XW_CELL_BLOCK ? tb : ta) + w0;
+#pragma unroll 12
+                    for (int r = 0; r < bs; ++r) cp_async_4(fb + w0 + r * WR, src + r * WR);
+                } else if (code == XW_CELL_EMPTY || code == XW_FPV_BLACK) {
+                    const uint32_t fill = code == XW_CELL_EMPTY ? 0xffffffffu : 0u;
+#pragma unroll 12
+                    for (int r = 0; r < bs; ++r) fb[w0 + r * WR] = fill;
                 }
             }
         }
+        cp_async_wait_all();
         fence_async_smem();
-        __syncthreads();
-        if (tid == 0) { tma_store_1d(frames + (size_t)e * env_stride, fb, (uint32_t)F.FB); tma_commit(); }
+        group_bar(1 + grp, NT);
+        if (tid == 32) { tma_store_1d(frames + (size_t)e * env_stride, fb, (uint32_t)F.FB); tma_commit(); }
     }
-    if (tid == 0) tma_wait_all<0>();
+    if (tid == 32) tma_wait_all<0>();
+}
+
+// One bilinear step of cv::resize on three packed channels (B | G << 8 | R << 16): the horizontal pass of a row is one
+// two-way dot product (DP2A: 16-bit weights x 8-bit taps), a01 = a0 | a1 << 16.  Same integers as xw_resize_px3.
+__device__ __forceinline__ uint32_t xw_bilin3_dev(uint32_t p00, uint32_t p01, uint32_t p10, uint32_t p11, uint32_t a01, uint32_t b0, uint32_t b1) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const uint32_t sel = 0x40u + 0x11u * c;   // bytes (c of p?0, c of p?1)
+        const uint32_t s0 = __dp2a_lo(a01, __byte_perm(p00, p01, sel), 0u);
+        const uint32_t s1 = __dp2a_lo(a01, __byte_perm(p10, p11, sel), 0u);
+        const uint32_t v = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2u) >> 2;
+        o |= (v & 255u) << (8 * c);
+    }
+    return o;
+}
+// frame pixel from its device tap entry (xw_fpv_tap_values with the 16 offsets scaled to bytes) and the staged icon
+__device__ __forceinline__ uint32_t xw_fpv_px_taps_dev(const uint4 q0, const uint4 q1, const uint4 q2, const uint4 q3, const uint8_t* icon) {
+    const uint32_t ow[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};   // 16 byte offsets
+    const uint32_t a1[2] = {q2.x, q2.y}, b1[2] = {q2.z, q2.w};                  // resize 1: (a0, a1) left / right, (b0, b1) upper / lower
+    uint32_t mid[4];
+#pragma unroll
+    for (int s2 = 0; s2 < 4; ++s2) {
+        const uint32_t w01 = ow[2 * s2], w23 = ow[2 * s2 + 1], b = b1[s2 >> 1];
+        mid[s2] = xw_bilin3_dev(*(const uint32_t*)(icon + (w01 & 0xffffu)), *(const uint32_t*)(icon + (w01 >> 16)),
+                                *(const uint32_t*)(icon + (w23 & 0xffffu)), *(const uint32_t*)(icon + (w23 >> 16)),
+                                a1[s2 & 1], b & 0xffffu, b >> 16);
+    }
+    return xw_bilin3_dev(mid[0], mid[1], mid[2], mid[3], q3.x, q3.y & 0xffffu, q3.y >> 16);
+}
+
+// The goal cells k_render_fpv_cells listed for chunk `chunk`.  Dynamic shared memory: icon [16 KB] | mbarrier.
+template <int BS_T, int VR_T>
+__global__ void __launch_bounds__(160) k_fpv_goal_cells(XwFpv F, uint8_t* __restrict__ frames, size_t env_stride, int chunk, int list_base) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* bar = (uint64_t*)(smem + 16384);
+    const int vr = VR_T ? VR_T : F.vr, bs = BS_T ? BS_T : F.bs, OW = bs * vr, plane = OW * OW, bb = bs * bs;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    const int total = F.goal_count[chunk];
+    const uint64_t* __restrict__ glist = F.goal_list + list_base;
+    uint32_t phase = 0;
+    for (int i = blockIdx.x; i < total; i += gridDim.x) {
+        const uint64_t ent = glist[i];
+        const uint32_t lo = (uint32_t)ent, hi = (uint32_t)(ent >> 32);
+        const int e = (int)lo, blk = hi & 255, slot = (hi >> 8) & 255, facing = (hi >> 16) & 3;
+        if (tid == 0) {
+            mbar_expect_tx(bar, 16384u);
+            tma_load_1d(smem, F.gcache + ((size_t)e * F.G + slot) * 4096, 16384u, bar);
+        }
+        const int by = blk / vr, bx = blk - by * vr;
+        const uint4* t4 = (const uint4*)F.taps4 + (size_t)facing * 4 * plane;
+        uint8_t* out = frames + (size_t)e * env_stride;
+        bool waited = false;
+        for (int q = tid; q < bb; q += nt) {
+            const int qy = q / bs, p = (by * bs + qy) * OW + bx * bs + (q - qy * bs);
+            const uint4 q0 = __ldg(t4 + p), q1 = __ldg(t4 + (size_t)plane + p), q2 = __ldg(t4 + 2 * (size_t)plane + p), q3 = __ldg(t4 + 3 * (size_t)plane + p);
+            if (!waited) { mbar_wait(bar, phase); waited = true; }
+            const uint32_t v = xw_fpv_px_taps_dev(q0, q1, q2, q3, smem);
+            out[p] = (uint8_t)v; out[plane + p] = (uint8_t)(v >> 8); out[2 * (size_t)plane + p] = (uint8_t)(v >> 16);
+        }
+        if (!waited) mbar_wait(bar, phase);
+        phase ^= 1;
+        __syncthreads();   // every thread is done with the icon before the next load lands
+    }
 }
 
 // --color=false: cv::cvtColor(BGR2GRAY) of the finished frame, OpenCV 3.2.0's coefficients (include/xworld_b200.h xw_config.gray)
