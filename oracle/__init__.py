@@ -121,6 +121,8 @@ def lib():
         L.xo_race_reset.argtypes = [cfgp, C.POINTER(XoRace)]
         L.xo_race_act.argtypes = [cfgp, C.POINTER(XoRace), C.c_int, C.POINTER(C.c_float), C.POINTER(i32)]
         L.xo_race_act.restype = C.c_float
+        L.xo_race_take_actions.argtypes = [cfgp, C.POINTER(XoRace), C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(i32)]
+        L.xo_race_take_actions.restype = C.c_float
         assert L.xo_sizeof_env() == C.sizeof(XoEnv), (L.xo_sizeof_env(), C.sizeof(XoEnv))
         _lib = L
     return _lib

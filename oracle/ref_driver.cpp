@@ -72,6 +72,19 @@ float ref_race_step(void* p, int action_index, float* state4, int* game_over) {
     return r;
 }
 
+// the reference's own GameSimulator::take_actions (simulator.cpp:98-108) around SimpleRaceGame::take_action
+float ref_race_take_actions(void* p, int action_index, int act_rep, float* state4, int* game_over) {
+    auto* g = (simple_race::SimpleRaceGame*)p;
+    StatePacket act;
+    act.add_buffer_id("action", {action_index});
+    float r = g->take_actions(act, act_rep, false, 0.0f);
+    StatePacket s;
+    g->get_screen(s);
+    std::memcpy(state4, s.get_buffer("screen")->get_value<float>(), 4 * sizeof(float));
+    *game_over = g->game_over();
+    return r;
+}
+
 // ---- XMap + XAgent (xmap.cpp:76-101, xitem.cpp:89-155) ----
 struct RefMap {
     xwd::XMap map;

@@ -1163,6 +1163,17 @@ float xo_race_act(const xw_config* cfg, xo_race* r, int action_index, float stat
     return reward;
 }
 
+/* GameSimulator::take_actions (simulator.cpp:98-108): num_steps_++ once, the action act_rep times, float rewards summed */
+float xo_race_take_actions(const xw_config* cfg, xo_race* r, int action_index, int act_rep, float state[4], int32_t* game_over) {
+    const int32_t steps0 = r->steps;
+    float reward = 0;
+    for (int i = 0; i < act_rep; i++) reward += xo_race_act(cfg, r, action_index, state, game_over);
+    r->steps = steps0 + 1;
+    *game_over &= ~XW_MAX_STEP;
+    if (cfg->max_steps > 0 && r->steps >= cfg->max_steps) *game_over |= XW_MAX_STEP;
+    return reward;
+}
+
 double xo_race_batch(const xw_config* cfg, xo_race* envs, int n, const int32_t* actions, int steps) {
     double sum = 0;
     float st[4];

@@ -124,6 +124,7 @@ int xo_sg_game_over(const xo_simple_game* g);
 typedef struct { float pos_x, pos_y, angle; int32_t steps; } xo_race;
 void xo_race_reset(const xw_config* cfg, xo_race* r);
 float xo_race_act(const xw_config* cfg, xo_race* r, int action_index, float state[4], int32_t* game_over);
+float xo_race_take_actions(const xw_config* cfg, xo_race* r, int action_index, int act_rep, float state[4], int32_t* game_over);
 /* n envs x steps on one thread (bench.py's CPU leg): actions[steps][n]; a finished game is reset; returns the reward sum */
 double xo_race_batch(const xw_config* cfg, xo_race* envs, int n, const int32_t* actions, int steps);
 

@@ -296,7 +296,7 @@ void hs_reset(HostSim* s, const uint8_t* mask) {
 
 void hs_step(HostSim* s, const int32_t* actions, int act_rep, float* reward, int32_t* over) {
     if (s->cfg.game == XW_GAME_SIMPLE_RACE) {
-        for (int e = 0; e < s->race.n; ++e) if (xw_race_step_env(s->race, e, actions[e], &reward[e], &over[e])) xw_race_reset_env(s->race, e);
+        for (int e = 0; e < s->race.n; ++e) if (xw_race_step_env(s->race, e, actions[e], act_rep, &reward[e], &over[e])) xw_race_reset_env(s->race, e);
         return;
     }
     for (int e = 0; e < s->d.n; ++e)

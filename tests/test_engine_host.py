@@ -94,9 +94,9 @@ def test_hostsim_golden_frames_from_real_opencv():
 
 def test_hostsim_race_matches_oracle():
     lib = oracle.lib()
-    for tt, full, hard in [(0, 0, 0), (1, 1, 1)]:
+    for tt, full, hard, rep, ms in [(0, 0, 0, 1, 0), (1, 1, 1, 1, 0), (0, 1, 0, 3, 40), (1, 1, 1, 4, 0)]:
         cfg = _abi.default_config(game=_abi.XW_GAME_SIMPLE_RACE, track_type=tt, race_full_manouver=full, difficulty=hard,
-                                  auto_reset=1)
+                                  auto_reset=1, max_steps=ms)
         n = 64
         hs = parity.HostSim(cfg, None, n)
         hs.reset()
@@ -106,12 +106,12 @@ def test_hostsim_race_matches_oracle():
         rng = np.random.RandomState(5)
         for s in range(200):
             a = rng.randint(0, 9 if full else 2, n).astype(np.int32)
-            r, ov, _ = hs.step(a)
+            r, ov, _ = hs.step(a, act_rep=rep)
             st = hs.field("state")
             for i, o in enumerate(orcs):
                 st2, ov2 = (C.c_float * 4)(), C.c_int32()
-                r2 = lib.xo_race_act(C.byref(cfg), C.byref(o), int(a[i]), st2, C.byref(ov2))
-                assert np.float32(r2).view(np.uint32) == r[i].view(np.uint32) and ov2.value == ov[i]
+                r2 = lib.xo_race_take_actions(C.byref(cfg), C.byref(o), int(a[i]), rep, st2, C.byref(ov2))
+                assert np.float32(r2).view(np.uint32) == r[i].view(np.uint32) and ov2.value == ov[i], (tt, rep, s, i)
                 assert (np.array(list(st2), np.float32).view(np.uint32) == st[i].view(np.uint32)).all()
                 if ov2.value:
                     lib.xo_race_reset(C.byref(cfg), C.byref(o))

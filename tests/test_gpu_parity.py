@@ -206,7 +206,7 @@ def test_simple_race_vs_oracle_1e6(backend_cls):
     """BASELINE config 5 (tol 1e-6 on reward and the 4-float state); reports exact-bit agreement."""
     import torch
     lib = oracle.lib()
-    for tt, full, hard in [(0, 0, 0), (1, 1, 1)]:
+    for tt, full, hard, rep in [(0, 0, 0, 1), (1, 1, 1, 1), (1, 1, 0, 3)]:   # (the last: --act_rep 3, simulator.cpp:98-108)
         cfg = _abi.default_config(game=_abi.XW_GAME_SIMPLE_RACE, track_type=tt, race_full_manouver=full, difficulty=hard,
                                   auto_reset=1)
         n = 4096
@@ -219,14 +219,14 @@ def test_simple_race_vs_oracle_1e6(backend_cls):
         exact = total = 0
         for s in range(60):
             a = rng.randint(0, 9 if full else 2, n).astype(np.int32)
-            r, ov, _ = eng.step(a)
+            r, ov, _ = eng.step(a, act_rep=rep)
             st = eng.field("state")
             r2 = np.zeros(n, np.float32)
             st2 = np.zeros((n, 4), np.float32)
             ov2 = np.zeros(n, np.int32)
             for i in range(n):
                 buf, o2 = (C.c_float * 4)(), C.c_int32()
-                r2[i] = lib.xo_race_act(C.byref(cfg), C.byref(orcs[i]), int(a[i]), buf, C.byref(o2))
+                r2[i] = lib.xo_race_take_actions(C.byref(cfg), C.byref(orcs[i]), int(a[i]), rep, buf, C.byref(o2))
                 st2[i] = list(buf)
                 ov2[i] = o2.value
                 if o2.value:

@@ -280,6 +280,34 @@ def test_simple_race_port_vs_compiled_reference(oracle_lib):
                     break
 
 
+def test_simple_race_act_rep_vs_compiled_reference(oracle_lib):
+    """--act_rep > 1 and --max_steps: the reference's own GameSimulator::take_actions (simulator.cpp:98-108) around the
+    compiled SimpleRaceGame against the port's xo_race_take_actions, bit for bit (reward sum, state, game_over code)."""
+    R = _ref()
+    R.ref_race_take_actions.restype = C.c_float
+    R.ref_race_take_actions.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    for tt, full, hard, rep, ms in [(0, 0, 0, 3, 0), (0, 1, 1, 2, 25), (1, 1, 0, 4, 0), (1, 1, 1, 5, 12)]:
+        cfg = _abi.default_config(game=2, track_type=tt, race_full_manouver=full, difficulty=hard, max_steps=ms)
+        ref = R.ref_race_create(tt, 20.0, 100.0, 30.0, full, hard, 1.0, ms)
+        o = oracle.XoRace()
+        rng = np.random.RandomState(tt * 7 + full + rep)
+        for ep in range(30):
+            R.ref_race_reset(ref)
+            oracle_lib.xo_race_reset(C.byref(cfg), C.byref(o))
+            for s in range(120):
+                a = int(rng.randint(0, 9 if full else 2))
+                st1, ov1 = (C.c_float * 4)(), C.c_int()
+                st2, ov2 = (C.c_float * 4)(), C.c_int32()
+                r1 = R.ref_race_take_actions(ref, a, rep, st1, C.byref(ov1))
+                r2 = oracle_lib.xo_race_take_actions(C.byref(cfg), C.byref(o), a, rep, st2, C.byref(ov2))
+                a1 = np.array([r1] + list(st1), np.float32)
+                a2 = np.array([r2] + list(st2), np.float32)
+                assert (a1.view(np.uint32) == a2.view(np.uint32)).all() and ov1.value == ov2.value, (tt, full, hard, rep, ep, s)
+                if ov1.value:
+                    break
+        R.ref_race_destroy(ref)
+
+
 def test_step_rules_vs_compiled_xmap(oracle_lib, synthetic_catalog):
     """XAgent::act + XMap::move_item compiled from the reference vs the oracle's move rules, on
     generated maps with random action streams (position, success flag, contacted item)."""

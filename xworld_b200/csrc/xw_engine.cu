@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) k_race_reset(XwRaceCfg r, const uint8_t* 
 }
 // 46 registers (5 CTAs / SM).  Forcing 6 or 8 CTAs per SM (40 / 32 registers, spills) is slower: 18.4 / 21.1 us
 // against 18.2 us per step at 1,048,576 envs (profiles/r01_summary.md).
-__global__ void __launch_bounds__(256) k_race_step(XwRaceCfg r, const int32_t* __restrict__ actions, int n_actions,
+__global__ void __launch_bounds__(256) k_race_step(XwRaceCfg r, const int32_t* __restrict__ actions, int n_actions, int act_rep,
                                                    float* __restrict__ reward, int32_t* __restrict__ over, int32_t* error) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= r.n) return;
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256) k_race_step(XwRaceCfg r, const int32_t* _
     if (a == XW_ACTION_NONE) return;
     if (a < 0 || a >= n_actions) { error[e] = XW_ERR_INVALID_ACTION; reward[e] = 0.f; over[e] = 0; return; }
     float rw; int32_t o;
-    bool need = xw_race_step_env(r, e, a, &rw, &o);
+    bool need = xw_race_step_env(r, e, a, act_rep, &rw, &o);
     reward[e] = rw; over[e] = o;
     if (need) xw_race_reset_env(r, e);  // the race reset is two stores: done in place
 }
@@ -118,12 +118,15 @@ struct xw_sim {
     float reset_avg = 128.f;
     int reset_ctas_per_sm = 0;
     bool overlap_reset = false;
+    bool reset_pdl = true;   // fully observed view: the reset kernel as the painter's programmatic dependent (same stream) instead of a second stream
     // XW_TRACE=1 (diagnostics): timestamps of one overlapped step, printed by xw_sync: k_step start / end, painter end, reset
     // end, re-paint end -- relative to the step's start
     bool trace = false;
     cudaEvent_t tr[6] = {};
     int trace_steps = 0;
     double host_enq_us = 0, host_sync_us = 0;   // step_hd: host time spent queueing the step / waiting for it (trace)
+    cudaEvent_t tr_h0 = nullptr, tr_h1 = nullptr;   // trace: first / last operation of a synchronous step_hd on the handle's stream
+    double gpu_span_us = 0, h2d_us = 0;
     int host_n = 0;
     cudaEvent_t ev_step = nullptr, ev_copy = nullptr, ev_frames = nullptr, ev_h2d = nullptr;
     int64_t launches = 0;
@@ -391,6 +394,7 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
     s->C = c.gray ? 1 : 3;
     { const char* eo = getenv("XW_RESET_OVERLAP"); s->overlap_reset = !eo || atoi(eo) != 0; }
     { const char* et = getenv("XW_TRACE"); s->trace = et && atoi(et) != 0; }
+    { const char* ep = getenv("XW_RESET_PDL"); s->reset_pdl = !ep || atoi(ep) != 0; }
     { const char* ew = getenv("XW_RESET_RETRY_WIDTH"); int w = ew ? atoi(ew) : 8; d.retry_width = w < 1 ? 1 : (w > 32 ? 32 : w); }
     int rc = 0;
     rc |= dalloc(s, &d.grid, (size_t)n * d.CS);
@@ -908,7 +912,7 @@ static int launch_render(xw_sim* s, uint8_t* d_frames, cudaStream_t st, const Re
     if (fix) {
         const int rc2 = fix->after_painter();  // (the painter is queued: now the reset launch on its own stream, then `done`)
         if (rc2) return rc2;
-        CUDA_TRY(cudaStreamWaitEvent(st, fix->done, 0));
+        if (fix->done) CUDA_TRY(cudaStreamWaitEvent(st, fix->done, 0));
         if (s->d.vr > 0) {  // first-person view: the frame kernel and the goal kernel again, over the queue (its own goal-list slot)
             const int slot = s->fpv_parity * (xw_sim::FPV_MAX_CHUNKS + 1) + xw_sim::FPV_MAX_CHUNKS;   // (the main pass zeroed nothing of this half)
             int blocks = (fix->est + s->fpv_ng - 1) / s->fpv_ng;
@@ -1031,9 +1035,35 @@ static int step_xworld(xw_sim* s, const int32_t* d_actions, int act_rep, float* 
         static const int fdbg = [] { const char* e = getenv("XW_FPV_DBG"); return e ? atoi(e) : 0; }();
         if (fpv && (fdbg & 4)) reserve = 0;
         if (t1) CUDA_TRY(cudaEventRecord(t1, st));
+        RenderFix fix = {reserve, s->ev_b, q_list, q_count, (int)(s->reset_avg * 1.5f) + 16, nullptr};
+        if (!fpv && s->reset_pdl && !s->timing && !s->trace) {   // (kernel timing puts an event record right behind the painter)
+            // The reset kernel as the painter's PROGRAMMATIC DEPENDENT in the same stream: it may start as soon as every painter
+            // CTA has executed griddepcontrol.launch_dependents (the first instruction of k_render_sp), i.e. when the painter holds
+            // its SMs, and it never waits for the painter.  With the reset on a second stream behind an event both kernels become
+            // runnable together when k_step ends; when the reset's CTAs were placed first -- one per SM, the hardware spreads them --
+            // that many painter CTAs (a whole SM each) had to wait for a reset round before they could start: 100 us per step in the
+            // synchronous host-buffer call, where the GPU is idle when the step begins (profiles/r02_summary.md).
+            fix.done = nullptr;
+            fix.after_painter = [s, reset_grid, q_list, q_count, parity, tracing, st]() -> int {
+                cudaLaunchConfig_t lc;   // (nothing may sit between the painter and its dependent in the stream)
+                memset(&lc, 0, sizeof lc);
+                lc.gridDim = dim3(reset_grid); lc.blockDim = dim3(128); lc.stream = st;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[0].val.programmaticStreamSerializationAllowed = 1;
+                lc.attrs = at; lc.numAttrs = 1;
+                CUDA_TRY(cudaLaunchKernelEx(&lc, k_reset_list, s->d, q_list, q_count));
+                s->launches++;
+                if (tracing) { CUDA_TRY(cudaEventRecord(s->tr[2], st)); CUDA_TRY(cudaEventRecord(s->tr[3], st)); }   // (= painter and reset both done)
+                CUDA_TRY(cudaMemcpyAsync(s->h_reset_cnt + parity, q_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+                return 0;
+            };
+            const int rc3 = launch_render(s, d_frames, st, &fix);
+            if (tracing) CUDA_TRY(cudaEventRecord(s->tr[4], st));
+            return rc3;
+        }
         CUDA_TRY(cudaEventRecord(s->ev_a, st));
         CUDA_TRY(cudaStreamWaitEvent(s->reset_stream, s->ev_a, 0));
-        RenderFix fix = {reserve, s->ev_b, q_list, q_count, (int)(s->reset_avg * 1.5f) + 16, nullptr};
         // (the painter first: its CTAs take their SMs before the reset launch, which waits for an event, can be placed)
         fix.after_painter = [s, reset_grid, fpv, q_list, q_count, parity, tracing, st]() -> int {
             if (tracing) CUDA_TRY(cudaEventRecord(s->tr[2], st));
@@ -1079,11 +1109,9 @@ int xw_step(xw_sim* s, const int32_t* d_actions, int32_t act_rep, float* d_rewar
     cudaStream_t st = pick_stream(s, stream);
     if (s->cfg.game == XW_GAME_XWORLD) return step_xworld(s, d_actions, act_rep, d_reward, d_game_over, d_frames, st, nullptr);
     if (s->cfg.game == XW_GAME_SIMPLE_RACE) {
-        for (int rep = 0; rep < act_rep; ++rep) {  // GameSimulator::take_actions repeats the action
-            if (rep > 0) return set_err(XW_ERR_UNSUPPORTED, "simple_race: act_rep > 1 not implemented");
-            k_race_step<<<(s->n + 255) / 256, 256, 0, st>>>(s->race, d_actions, xw_num_actions(s), d_reward, d_game_over, s->race_error);
-            s->launches++;
-        }
+        // (GameSimulator::take_actions repeats the action act_rep times: inside the kernel, one launch per call)
+        k_race_step<<<(s->n + 255) / 256, 256, 0, st>>>(s->race, d_actions, xw_num_actions(s), act_rep, d_reward, d_game_over, s->race_error);
+        s->launches++;
         CUDA_TRY(cudaGetLastError());
         if (d_frames)  // "screen" of simple_race = the 4-float state vector
             CUDA_TRY(cudaMemcpyAsync(d_frames, s->race.state, sizeof(float) * 4 * s->n, cudaMemcpyDeviceToDevice, st));
@@ -1263,7 +1291,11 @@ static int step_hd(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float* 
     if (rc) return rc;
     cudaStream_t st = s->own_stream;
     struct timespec ts0, ts1, ts2;
-    if (s->trace) clock_gettime(CLOCK_MONOTONIC, &ts0);
+    if (s->trace) {
+        clock_gettime(CLOCK_MONOTONIC, &ts0);
+        if (!s->tr_h0) { CUDA_TRY(cudaEventCreate(&s->tr_h0)); CUDA_TRY(cudaEventCreate(&s->tr_h1)); }
+        if (wait_frames) CUDA_TRY(cudaEventRecord(s->tr_h0, st));
+    }
     const bool pin_a = is_pinned(h_actions), pin_r = is_pinned(h_reward), pin_o = is_pinned(h_game_over);
     const int32_t* src_a = h_actions;
     if (!pin_a) { memcpy(s->h_act, h_actions, sizeof(int32_t) * s->n); src_a = s->h_act; }
@@ -1312,15 +1344,22 @@ static int step_hd(xw_sim* s, const int32_t* h_actions, int32_t act_rep, float* 
             CUDA_TRY(cudaStreamWaitEvent(st, s->ev_copy, 0));
         }
     }
-    if (s->trace) clock_gettime(CLOCK_MONOTONIC, &ts1);
+    if (s->trace) { clock_gettime(CLOCK_MONOTONIC, &ts1); if (wait_frames) CUDA_TRY(cudaEventRecord(s->tr_h1, st)); }
     CUDA_TRY(cudaStreamSynchronize(split && !wait_frames ? cs : st));
     if (s->trace) {
         clock_gettime(CLOCK_MONOTONIC, &ts2);
+        if (wait_frames) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, s->tr_h0, s->tr_h1);
+            if (s->tr[0] && cudaEventElapsedTime(&b, s->tr_h0, s->tr[0]) == cudaSuccess) s->h2d_us += b * 1e3;
+            s->gpu_span_us += a * 1e3;
+        }
         s->host_enq_us += (ts1.tv_sec - ts0.tv_sec) * 1e6 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-3;
         s->host_sync_us += (ts2.tv_sec - ts1.tv_sec) * 1e6 + (ts2.tv_nsec - ts1.tv_nsec) * 1e-3;
         if (++s->host_n % 32 == 0) {
-            fprintf(stderr, "XW_TRACE step_hd: host enqueue %.1f us, wait %.1f us per call (last 32)\n", s->host_enq_us / 32, s->host_sync_us / 32);
-            s->host_enq_us = s->host_sync_us = 0;
+            fprintf(stderr, "XW_TRACE step_hd: host enqueue %.1f us, wait %.1f us per call (last 32); GPU first-to-last op %.1f us (last k_step-start sample at +%.1f)\n",
+                    s->host_enq_us / 32, s->host_sync_us / 32, s->gpu_span_us / 32, s->h2d_us / 32);
+            s->host_enq_us = s->host_sync_us = s->gpu_span_us = s->h2d_us = 0;
         }
     }
     if (!pin_r) memcpy(h_reward, s->h_rew, sizeof(float) * s->n);

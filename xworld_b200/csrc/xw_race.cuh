@@ -47,7 +47,10 @@ XW_HD void xw_race_reset_env(const XwRaceCfg& r, int e) {
     r.steps[e] = 0;
 }
 
-XW_HD bool xw_race_step_env(const XwRaceCfg& r, int e, int action_index, float* reward_out, int32_t* over_out) {
+// One GameSimulator::take_actions (simulator.cpp:98-108): num_steps counts the call, the action is applied act_rep times
+// (RaceEngine::act moves the car whether or not it has left the track) and the float rewards are summed; the state vector
+// and game_over describe the car after the last repeat.
+XW_HD bool xw_race_step_env(const XwRaceCfg& r, int e, int action_index, int act_rep, float* reward_out, int32_t* over_out) {
     int a = r.full_manouver ? action_index : (action_index == 0 ? 4 : 7);
     const float delta_ang = (float)(XW_RACE_PI / 10), delta_fwd = 1.f;
     float d_forward = 0.f, d_turn = 0.f;
@@ -55,42 +58,46 @@ XW_HD bool xw_race_step_env(const XwRaceCfg& r, int e, int action_index, float* 
     if (m == 1) d_forward = delta_fwd; else if (m == 2) d_forward = -delta_fwd;
     m = (a / 3) % 3;
     if (m == 1) d_turn = delta_ang; else if (m == 2) d_turn = -delta_ang;
-    float ang = XW_FA(r.angle[e], d_turn);
-    if ((double)ang > 2 * XW_RACE_PI) ang = (float)((double)ang - 2 * XW_RACE_PI);
-    else if (ang < 0) ang = (float)((double)ang + 2 * XW_RACE_PI);
-#if defined(__CUDA_ARCH__)
-    double ca, sa;
-    sincos((double)ang, &sa, &ca);  // one argument reduction for both (same polynomials as cos() / sin())
-#else
-    const double ca = cos((double)ang), sa = sin((double)ang);
-#endif
-    const float cx = (float)ca, sx = (float)sa;
-    const float px = XW_FA(r.pos_x[e], XW_FM(d_forward, cx));
-    const float py = XW_FA(r.pos_y[e], XW_FM(d_forward, sx));
+    float ang = r.angle[e], px = r.pos_x[e], py = r.pos_y[e];
     const int steps = r.steps[e] + 1;
-    // tangent
-    float tx, ty;
-    if (r.track_type == 0) { tx = 0.f; ty = 1.f; }
-    else {
-        float ax = XW_FA(r.mid_y, -py), ay = XW_FA(px, -r.mid_x);
-        double s = 1 / xw_race_norm(ax, ay);
-        tx = (float)((double)ax * s); ty = (float)((double)ay * s);
+    float total = 0.f, tx = 0.f, ty = 1.f, hd = 0.f;
+    double ca = 0, sa = 0;
+    bool oob = false;
+    for (int rep = 0; rep < act_rep; ++rep) {
+        ang = XW_FA(ang, d_turn);
+        if ((double)ang > 2 * XW_RACE_PI) ang = (float)((double)ang - 2 * XW_RACE_PI);
+        else if (ang < 0) ang = (float)((double)ang + 2 * XW_RACE_PI);
+#if defined(__CUDA_ARCH__)
+        sincos((double)ang, &sa, &ca);  // one argument reduction for both (same polynomials as cos() / sin())
+#else
+        ca = cos((double)ang); sa = sin((double)ang);
+#endif
+        const float cx = (float)ca, sx = (float)sa;
+        px = XW_FA(px, XW_FM(d_forward, cx));
+        py = XW_FA(py, XW_FM(d_forward, sx));
+        // tangent
+        if (r.track_type == 0) { tx = 0.f; ty = 1.f; }
+        else {
+            float ax = XW_FA(r.mid_y, -py), ay = XW_FA(px, -r.mid_x);
+            double s = 1 / xw_race_norm(ax, ay);
+            tx = (float)((double)ax * s); ty = (float)((double)ay * s);
+        }
+        const float reward_speed = XW_FM(XW_FA(XW_FM(cx, tx), XW_FM(sx, ty)), d_forward);
+        const bool finish = (r.track_type == 0) && (py > r.end_y);
+        if (r.track_type == 0) {
+            const float hw = XW_FD(r.width, 2.f);
+            oob = (px < XW_FA(r.mid_x, -hw)) || (px > XW_FA(r.mid_x, hw)) || (py < r.start_y) || (py > r.end_y);
+        } else {
+            float rr = (float)xw_race_norm(XW_FA(px, -r.mid_x), XW_FA(py, -r.mid_y));
+            oob = rr < r.inner || rr > r.outer;
+        }
+        hd = xw_race_hdisp(r, px, py);
+        const float reward_finish = finish ? 2.f : 0.f;
+        const float reward_boundary = r.difficulty == 0 ? (float)(-fabs((double)hd)) : ((oob && !finish) ? -2.f : 0.f);
+        float reward = XW_FA(XW_FA(reward_finish, reward_boundary), reward_speed);
+        reward = (float)((double)reward * r.reward_scale);
+        total = rep == 0 ? reward : XW_FA(total, reward);   // (0.f + x == x, also for x == -0.f + 0.f ... kept explicit)
     }
-    const float reward_speed = XW_FM(XW_FA(XW_FM(cx, tx), XW_FM(sx, ty)), d_forward);
-    const bool finish = (r.track_type == 0) && (py > r.end_y);
-    bool oob;
-    if (r.track_type == 0) {
-        const float hw = XW_FD(r.width, 2.f);
-        oob = (px < XW_FA(r.mid_x, -hw)) || (px > XW_FA(r.mid_x, hw)) || (py < r.start_y) || (py > r.end_y);
-    } else {
-        float rr = (float)xw_race_norm(XW_FA(px, -r.mid_x), XW_FA(py, -r.mid_y));
-        oob = rr < r.inner || rr > r.outer;
-    }
-    const float hd = xw_race_hdisp(r, px, py);
-    const float reward_finish = finish ? 2.f : 0.f;
-    const float reward_boundary = r.difficulty == 0 ? (float)(-fabs((double)hd)) : ((oob && !finish) ? -2.f : 0.f);
-    float reward = XW_FA(XW_FA(reward_finish, reward_boundary), reward_speed);
-    reward = (float)((double)reward * r.reward_scale);
     // state (get_screen)
     double ct = (double)tx * ca + (double)ty * sa;
     ct = ct < -1.0 ? -1.0 : (ct > 1.0 ? 1.0 : ct);
@@ -104,7 +111,7 @@ XW_HD bool xw_race_step_env(const XwRaceCfg& r, int e, int action_index, float* 
     if (r.max_steps > 0 && steps >= r.max_steps) over |= XW_MAX_STEP;
     if (oob) over |= XW_DEAD;
     r.pos_x[e] = px; r.pos_y[e] = py; r.angle[e] = ang; r.steps[e] = steps;
-    *reward_out = reward;
+    *reward_out = total;
     *over_out = over;
     return r.auto_reset && over != 0;
 }

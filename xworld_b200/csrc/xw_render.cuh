@@ -1257,6 +1257,10 @@ template <int WR_T, int NT_MAX, int XW_SP_ROWS, bool DISJ = false, bool LIST = f
 __global__ void __launch_bounds__(NT_MAX, 1)
 k_render_sp(XwDev d, XwRender r, uint8_t* __restrict__ frames, size_t env_stride) {
     extern __shared__ __align__(128) uint8_t smem[];
+    // Programmatic dependent launch: once every CTA of the painter is resident (it is one CTA per SM on fewer CTAs than SMs), the
+    // step's auto-reset kernel -- launched behind it in the same stream with programmatic stream serialization -- may start on
+    // the SMs the painter left free (xw_engine.cu step_xworld).  Without a dependent the instruction does nothing.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int G = r.G, GT = r.GT;
     const XwRenderSpSmem& L = r.sp;
     uint32_t* s_yb = (uint32_t*)(smem + L.yb);
