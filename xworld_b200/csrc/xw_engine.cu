@@ -824,7 +824,8 @@ double xw_step_reset_ms(xw_sim* s, int32_t reset) {
 
 // fix != NULL: the painter leaves `fix->reserve` SMs free, and once `fix->done` has fired the frames of the envs in the
 // step's auto-reset queue are painted again (the painter in list mode) -- see step_xworld.
-struct RenderFix { int reserve; cudaEvent_t done; const int32_t* list; const int32_t* count; int est; std::function<int()> after_painter; };
+struct RenderFix { int reserve; cudaEvent_t done; const int32_t* list; const int32_t* count; int est; std::function<int()> after_painter;
+                   std::function<int()> between; };   // between: first-person view, called right behind the frame kernel (before the goal kernel)
 static int launch_render(xw_sim* s, uint8_t* d_frames, cudaStream_t st, const RenderFix* fix = nullptr) {
     XwRender& r = s->r;
     const int K = s->cfg.context;
@@ -865,6 +866,7 @@ static int launch_render(xw_sim* s, uint8_t* d_frames, cudaStream_t st, const Re
                     if (grid > need) grid = need;
                     if (grid < 1) grid = 1;
                     s->fpv_cells_fn<<<grid, s->fpv_nt, s->fpv_smem, st>>>(s->d, s->fpv, dst, dst_stride, nullptr, nullptr, env0, cnt, pbase + k, env0 * G, zbase, slots);
+                    if (fix && fix->between) { const int rcb = fix->between(); if (rcb) return rcb; }
                     if (s->trace && s->tr[5]) CUDA_TRY(cudaEventRecord(s->tr[5], st));
                     cudaStream_t gs = st;
                     if (nch > 1) {
@@ -910,8 +912,10 @@ static int launch_render(xw_sim* s, uint8_t* d_frames, cudaStream_t st, const Re
     s->launches++;
     if (s->timing) CUDA_TRY(cudaEventRecord(e1, st));  // (the frame kernel alone: not the re-paint of the reset queue, not the gray pass)
     if (fix) {
-        const int rc2 = fix->after_painter();  // (the painter is queued: now the reset launch on its own stream, then `done`)
-        if (rc2) return rc2;
+        if (fix->after_painter) {
+            const int rc2 = fix->after_painter();  // (the painter is queued: now the reset launch on its own stream, then `done`)
+            if (rc2) return rc2;
+        }
         if (fix->done) CUDA_TRY(cudaStreamWaitEvent(st, fix->done, 0));
         if (s->d.vr > 0) {  // first-person view: the frame kernel and the goal kernel again, over the queue (its own goal-list slot)
             const int slot = s->fpv_parity * (xw_sim::FPV_MAX_CHUNKS + 1) + xw_sim::FPV_MAX_CHUNKS;   // (the main pass zeroed nothing of this half)
@@ -1060,6 +1064,32 @@ static int step_xworld(xw_sim* s, const int32_t* d_actions, int act_rep, float* 
             };
             const int rc3 = launch_render(s, d_frames, st, &fix);
             if (tracing) CUDA_TRY(cudaEventRecord(s->tr[4], st));
+            return rc3;
+        }
+        if (fpv && s->reset_pdl && s->fpv_chunks == 1) {
+            // first-person view: the reset kernel is the FRAME kernel's programmatic dependent (same reasons); the new episodes' goal
+            // icons are warped on the reset stream once frame kernel and reset are done, beside the main pass's goal kernel; the
+            // re-paint of the queue waits for both
+            fix.between = [s, reset_grid, q_list, q_count, parity, st]() -> int {
+                cudaLaunchConfig_t lc;
+                memset(&lc, 0, sizeof lc);
+                lc.gridDim = dim3(reset_grid); lc.blockDim = dim3(128); lc.stream = st;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[0].val.programmaticStreamSerializationAllowed = 1;
+                lc.attrs = at; lc.numAttrs = 1;
+                CUDA_TRY(cudaLaunchKernelEx(&lc, k_reset_list, s->d, q_list, q_count));
+                CUDA_TRY(cudaEventRecord(s->ev_a, st));
+                CUDA_TRY(cudaStreamWaitEvent(s->reset_stream, s->ev_a, 0));
+                const int g2 = (int)(s->reset_avg * 1.25f) * s->fpv.G + 8;
+                k_fpv_warp_goals<<<g2 < s->n_sms * 8 ? g2 : s->n_sms * 8, 256, 0, s->reset_stream>>>(s->d, s->fpv, nullptr, q_list, q_count);
+                CUDA_TRY(cudaEventRecord(s->ev_b, s->reset_stream));
+                CUDA_TRY(cudaMemcpyAsync(s->h_reset_cnt + parity, q_count, sizeof(int32_t), cudaMemcpyDeviceToHost, s->reset_stream));
+                s->launches += 2;
+                return 0;
+            };
+            const int rc3 = launch_render(s, d_frames, st, &fix);
+            if (tracing) { CUDA_TRY(cudaEventRecord(s->tr[2], st)); CUDA_TRY(cudaEventRecord(s->tr[3], st)); CUDA_TRY(cudaEventRecord(s->tr[4], st)); }
             return rc3;
         }
         CUDA_TRY(cudaEventRecord(s->ev_a, st));

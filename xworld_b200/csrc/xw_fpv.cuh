@@ -484,6 +484,9 @@ __global__ void __maxnreg__(48) k_render_fpv_cells(XwDev d, XwFpv F, uint8_t* __
                                                                  const int32_t* __restrict__ list, const int32_t* __restrict__ count,
                                                                  int env0, int env_n, int chunk, int list_base, int zero_base, int zero_n) {
     extern __shared__ __align__(128) uint8_t smem_all[];
+    // (programmatic dependent launch: the step's auto-reset kernel, queued behind this one, may start once every CTA is resident --
+    //  see k_render_sp)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // the goal counters of the PREVIOUS launch (the other half of the ping-pong; its goal kernel is done: stream order) -> 0,
     // so that no memset node sits between the step kernel and this one
     if (blockIdx.x == 0 && (int)threadIdx.x < zero_n) F.goal_count[zero_base + threadIdx.x] = 0;
