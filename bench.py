@@ -188,35 +188,13 @@ def race_cpu_arm(sample_envs, steps):
     return sample_envs * steps / dt, dt
 
 
-def bench_race(args, rank, world, local_rank):
-    """--workload c5: BASELINE configs[4].  One k_race_step launch per step; the kernel is the whole step."""
-    config = {"workload": RACE_NAME, "envs_per_gpu": args.envs_per_gpu, "auto_reset": True, "actions": "iid uniform{0,1}",
-              "l2": "per step the kernel touches 60 B x 1,048,576 envs = 63 MB of state (< 126 MB L2): state stays L2-resident "
-                    "between steps by design -- the roofline figure is against HBM and is an upper bound on DRAM traffic",
-              "bytes_per_env_step": RACE_BYTES_PER_ENV_STEP}
-    if args.impl == "reference":
-        if rank != 0:
-            return 0
-        v, dt = race_cpu_arm(65536, max(1, min(args.steps, 200)))
-        print(json.dumps({"impl": "reference", "metric": "env_steps_per_sec", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
-                          "steps": min(args.steps, 200), "warmup": 0, "ms_per_step": None, "higher_is_better": True,
-                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                          "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port",
-                                           "sample": "65536 envs x %d steps, C port, one thread" % min(args.steps, 200)},
-                          "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
-        return 0
+def measure_race(n, steps, warmup, rank, world, local_rank, dist, dev, sampler=None):
+    """SimpleRace at n envs per GPU: K timed xw_step launches with inputs in HBM, then the same through xw_step_hd.
+    Returns (ms of this rank, ms max over ranks, launches, total env-steps, per-rank records, e2e seconds max over ranks)."""
     import torch
     from xworld_b200 import _abi
     from xworld_b200.sharding import gather_throughput
     from xworld_b200.simulator import Simulator
-    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-    n = args.envs_per_gpu
     cfg = _abi.default_config(game=_abi.XW_GAME_SIMPLE_RACE, auto_reset=1)
     sim = Simulator("simple_race", cfg, None, n, local_rank)
     lib, h = sim._lib, sim._h
@@ -238,29 +216,27 @@ def bench_race(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()  # before the warm-up: nothing but the warm-up may sit between it and the timed region
-    for i in range(args.warmup):
+    for i in range(warmup):
         step(i)
     launches0 = sim.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    sampler.mark_begin()
+    if sampler:
+        sampler.mark_begin()
     e0.record()
-    for i in range(args.steps):
+    for i in range(steps):
         step(i)
     e1.record()
     barrier()
-    sampler.mark_end()
+    if sampler:
+        sampler.mark_end()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
     launches = sim.launch_count() - launches0
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    total_steps, _, per_rank = gather_throughput(n * args.steps, int(ms * 1e6), device=dev)
+    total_steps, _, per_rank = gather_throughput(n * steps, int(ms * 1e6), device=dev)
     h_act = [torch.randint(0, 2, (n,), dtype=torch.int32).pin_memory() for _ in range(4)]
     h_rew = torch.zeros(n, dtype=torch.float32).pin_memory()
     h_over = torch.zeros(n, dtype=torch.int32).pin_memory()
@@ -268,32 +244,98 @@ def bench_race(args, rank, world, local_rank):
         lib.xw_step_hd(h, h_act[i % 4].data_ptr(), 1, h_rew.data_ptr(), h_over.data_ptr(), None)
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
+    for i in range(steps):
         assert lib.xw_step_hd(h, h_act[i % 4].data_ptr(), 1, h_rew.data_ptr(), h_over.data_ptr(), None) == 0
     torch.cuda.synchronize()
     tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    # K steps per launch (xw_step_seq: open-loop action sequences, the car in registers between the steps)
+    K = 32
+    reps = max(2, steps // K)
+    seq_a = torch.randint(0, 2, (K, n), dtype=torch.int32, device=dev, generator=gen)
+    seq_r = torch.zeros((K, n), dtype=torch.float32, device=dev)
+    seq_o = torch.zeros((K, n), dtype=torch.int32, device=dev)
+    lib.xw_step_seq(h, seq_a.data_ptr(), K, 1, seq_r.data_ptr(), seq_o.data_ptr(), stream)
+    barrier()
+    e0.record()
+    for i in range(reps):
+        assert lib.xw_step_seq(h, seq_a.data_ptr(), K, 1, seq_r.data_ptr(), seq_o.data_ptr(), stream) == 0
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    measure_race.multi_step = {"value": n * world * K * reps / (float(t.item()) / 1e3), "unit": "env-steps/s", "steps_per_launch": K,
+                               "launches": reps, "bytes_per_env_step": 12,
+                               "what": "xw_step_seq: 32 take_actions calls per launch (actions / reward / game_over [32][n] in HBM), "
+                                       "the car in registers between the steps"}
+    del sim
+    return ms, ms_max, launches, total_steps, per_rank, float(tt.item())
+
+
+def race_fields(n, steps, world, ms, ms_max, total_steps, e2e_s):
+    """value / roofline / e2e of a SimpleRace measurement (the kernel is the whole step)."""
+    peak, peak_src = hbm_peak()
+    kernel_ms = ms / steps
+    achieved = RACE_BYTES_PER_ENV_STEP * n / (kernel_ms * 1e-3) / 1e9
+    return {
+        "value": total_steps / (ms_max / 1e3), "ms_per_step": ms_max / steps,
+        "roofline": {"bound": "hbm", "kernel": "k_race_step", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": kernel_ms,
+                     "kernel_share_of_step": 1.0, "algorithmic_bytes_per_launch": RACE_BYTES_PER_ENV_STEP * n,
+                     "note": "one launch per step (the agent's actions arrive per step); the 63 MB of state stay in L2 between "
+                             "steps, so this is an upper bound on DRAM traffic, not a bandwidth-bound kernel: launch + tail "
+                             "latency sets the time at this size"},
+        "multi_step": getattr(measure_race, "multi_step", None),
+        "e2e": {"value": n * world * steps / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": 4 * n,
+                "d2h_bytes_per_step": 8 * n, "steps": steps,
+                "what": "xw_step_hd: pinned host actions -> H2D, k_race_step, reward + game_over D2H, stream sync"}}
+
+
+def bench_race(args, rank, world, local_rank):
+    """--workload c5: BASELINE configs[4].  One k_race_step launch per step; the kernel is the whole step."""
+    config = {"workload": RACE_NAME, "envs_per_gpu": args.envs_per_gpu, "auto_reset": True, "actions": "iid uniform{0,1}",
+              "l2": "per step the kernel touches 60 B x 1,048,576 envs = 63 MB of state (< 126 MB L2): state stays L2-resident "
+                    "between steps by design -- the roofline figure is against HBM and is an upper bound on DRAM traffic",
+              "bytes_per_env_step": RACE_BYTES_PER_ENV_STEP}
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        v, dt = race_cpu_arm(65536, max(1, min(args.steps, 200)))
+        print(json.dumps({"impl": "reference", "metric": "env_steps_per_sec", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
+                          "steps": min(args.steps, 200), "warmup": 0, "ms_per_step": None, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port",
+                                           "sample": "65536 envs x %d steps, C port, one thread" % min(args.steps, 200)},
+                          "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+    import torch
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.envs_per_gpu
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # before the warm-up: nothing but the warm-up may sit between it and the timed region
+    ms, ms_max, launches, total_steps, per_rank, e2e_s = measure_race(n, args.steps, args.warmup, rank, world, local_rank, dist, dev,
+                                                                      sampler=sampler if rank == 0 else None)
+    clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         if dist is not None:
             dist.barrier()
             dist.destroy_process_group()
         return 0
-    peak, peak_src = hbm_peak()
-    kernel_ms = ms / args.steps  # the step is this one kernel
-    achieved = RACE_BYTES_PER_ENV_STEP * n / (kernel_ms * 1e-3) / 1e9
-    line = {"metric": "env_steps_per_sec", "value": total_steps / (ms_max / 1e3), "unit": "env-steps/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+    f = race_fields(n, args.steps, world, ms, ms_max, total_steps, e2e_s)
+    line = {"metric": "env_steps_per_sec", "value": f["value"], "unit": "env-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": f["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-            "roofline": {"bound": "hbm", "kernel": "k_race_step", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": kernel_ms,
-                         "kernel_share_of_step": 1.0, "algorithmic_bytes_per_launch": RACE_BYTES_PER_ENV_STEP * n,
-                         "note": "one launch per step (the agent's actions arrive per step): launch + tail latency, not "
-                                 "bandwidth, sets the time at this size"},
-            "gpu_launches": launches, "clocks": clocks, "per_rank": per_rank,
-            "e2e": {"value": n * world * args.steps / float(tt.item()), "unit": "env-steps/s", "h2d_bytes_per_step": 4 * n,
-                    "d2h_bytes_per_step": 8 * n, "steps": args.steps,
-                    "what": "xw_step_hd: pinned host actions -> H2D, k_race_step, reward + game_over D2H, stream sync"}}
+            "roofline": f["roofline"], "gpu_launches": launches, "clocks": clocks, "per_rank": per_rank, "e2e": f["e2e"],
+            "multi_step": f["multi_step"]}
     if world == 1 and not args.no_cpu_baseline:
         v, dt = race_cpu_arm(65536, 200)
         line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port",
@@ -647,6 +689,12 @@ def main():
                 others[key] = {"value": r["value"], "unit": "env-steps/s", "ms_per_step": r["ms_per_step"], "steps": r["steps"],
                                "workload": r["config"]["workload"], "envs_per_gpu": r["config"]["envs_per_gpu"],
                                "roofline": r["roofline"], "e2e": r["e2e"], "gpu_launches": r["gpu_launches"]}
+        ms5, ms5_max, l5, tot5, _, e2e5 = measure_race(1 << 20, 100, 10, rank, world, local_rank, dist, dev)
+        if rank == 0:
+            f5 = race_fields(1 << 20, 100, world, ms5, ms5_max, tot5, e2e5)
+            others["c5"] = {"value": f5["value"], "unit": "env-steps/s", "ms_per_step": f5["ms_per_step"], "steps": 100,
+                            "workload": RACE_NAME, "envs_per_gpu": 1 << 20, "dtype": "f32", "roofline": f5["roofline"], "e2e": f5["e2e"],
+                            "multi_step": f5["multi_step"], "gpu_launches": l5}
         select_workload(args.workload)
     if rank != 0:
         if dist is not None:

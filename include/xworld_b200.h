@@ -130,7 +130,8 @@ typedef struct {
     int32_t track_type;       /* 0 straight, 1 circle */
     float track_width, track_length, track_radius;
     int32_t race_full_manouver;
-    int32_t race_random;      /* only 0 implemented */
+    int32_t race_random;      /* --random (simple_race_simulator.cpp:24): start position / heading drawn per episode from the env's
+                                 std::default_random_engine, seeded like the reference's simulator threads (simulator_seed) */
     int32_t difficulty;       /* 0 easy, 1 hard */
     float reward_scale;
     /* ---- xworld curriculum (XWorldNav.py:36-56, xworld_env.py:103-110) ---- */
@@ -182,6 +183,14 @@ int xw_reset(xw_sim* sim, const uint8_t* d_mask, void* stream);
  * XW_ERR_INVALID_ACTION when an env of that step was flagged -- the other envs were stepped normally. */
 int xw_step(xw_sim* sim, const int32_t* d_actions, int32_t act_rep, float* d_reward,
             int32_t* d_game_over, uint8_t* d_frames, void* stream);
+
+/* k_steps consecutive SimulatorInterface::take_actions calls of every env, no frames: d_actions, d_reward, d_game_over are
+ * [k_steps][n_envs] (step-major); auto_reset applies between the steps.  Same results as k_steps xw_step calls with
+ * d_frames == NULL.  simple_race runs them in ONE launch with the car in registers (open-loop action sequences:
+ * evaluation roll-outs); xworld queues k_steps step (+ reset) launches.  No reference counterpart: the reference's
+ * simulation_loop (simulator_interface.cpp:361-435) is one request per step by construction. */
+int xw_step_seq(xw_sim* sim, const int32_t* d_actions, int32_t k_steps, int32_t act_rep, float* d_reward,
+                int32_t* d_game_over, void* stream);
 
 /* GameSimulator::make_context_screens -> XWorldSimulator::get_screen (simulator.cpp:62-85,
  * xworld_simulator.cpp:278-285): render the current state of every env. */

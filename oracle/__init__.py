@@ -53,7 +53,7 @@ class XoEnv(C.Structure):
 
 
 class XoRace(C.Structure):
-    _fields_ = [("pos_x", C.c_float), ("pos_y", C.c_float), ("angle", C.c_float), ("steps", C.c_int32)]
+    _fields_ = [("pos_x", C.c_float), ("pos_y", C.c_float), ("angle", C.c_float), ("steps", C.c_int32), ("minstd", C.c_uint32)]
 
 
 class XoSimpleGame(C.Structure):

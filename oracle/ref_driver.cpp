@@ -51,10 +51,15 @@ void ref_sg_screen(void* p, uint8_t* out, int n) {
 }
 
 // ---- SimpleRace ----
+// --random: RaceEngine reads FLAGS_random in its constructor (:257-258); the start state is drawn from the calling thread's
+// engine (util::get_rand_range_val), re-seeded here the way std::default_random_engine::seed does
+static bool g_race_random = false;
+void ref_race_set_random(int on) { g_race_random = on != 0; }   // applies to the next ref_race_create
+void ref_seed_thread_engine(unsigned seed) { util::thread_local_reng().seed(seed); }
 void* ref_race_create(int track_type, double width, double length, double radius, int full, int hard, double scale, int max_steps) {
     FLAGS_track_type = track_type == 0 ? "straight" : "circle";
     FLAGS_track_width = width; FLAGS_track_length = length; FLAGS_track_radius = radius;
-    FLAGS_race_full_manouver = full != 0; FLAGS_random = false;
+    FLAGS_race_full_manouver = full != 0; FLAGS_random = g_race_random;
     FLAGS_difficulty = hard ? "hard" : "easy"; FLAGS_reward_scale = scale; FLAGS_max_steps = max_steps;
     return new simple_race::SimpleRaceGame();
 }

@@ -1086,9 +1086,39 @@ static void race_track_init(const xw_config* cfg, race_track* t) {
 }
 static double race_norm(float x, float y) { return sqrt((double)x * x + (double)y * y); } /* cv::norm(Point2f) -> double */
 
-void xo_race_reset(const xw_config* cfg, xo_race* r) { /* RaceEngine::reset_game :267-284, random=false */
+/* util::get_rand_range_val (simulator_util.cpp:57-64): std::uniform_real_distribution<float>(0, upper) on the thread's
+ * std::default_random_engine (minstd_rand0).  libstdc++ (bits/random.tcc generate_canonical<float, 24>): the engine's range
+ * 2147483646 has floor(log2) = 30 >= 24 bits, so ONE draw: sum = float(x - min), tmp = float(1.0f * 2147483646.0L) = 2^31,
+ * ret = sum / tmp, clipped to nextafterf(1, 0) when it rounds to 1; then ret * (b - a) + a. */
+float xo_rand_range_val(uint32_t* st, float upper) {
+    const uint32_t x = minstd_next(st);
+    const float sum = (float)(x - 1u) * 1.0f;
+    const float tmp = (float)(1.0L * 2147483646.0L);
+    float ret = sum / tmp;
+    if (ret >= 1.0f) ret = nextafterf(1.0f, 0.0f);
+    return ret * (upper - 0.0f) + 0.0f;
+}
+
+void xo_race_reset(const xw_config* cfg, xo_race* r) { /* RaceEngine::reset_game :267-284 */
     race_track t;
     race_track_init(cfg, &t);
+    if (cfg->race_random) {
+        /* :268-273 the track draw (one track in the pool: the index is 0 either way, the draw is still taken) */
+        (void)xo_rand_range_val(&r->minstd, 1.0f);
+        if (cfg->track_type == 0) { /* StraightTrack::get_start_pos :192-199 */
+            float dy = xo_rand_range_val(&r->minstd, 1.0f) * t.length / 2;
+            float dx = (float)((xo_rand_range_val(&r->minstd, 1.0f) - 0.5) * t.width);
+            r->pos_x = dx + t.start_x; r->pos_y = dy + t.start_y;
+        } else { /* CircleTrack::get_start_pos :78-86 */
+            float theta = (float)(xo_rand_range_val(&r->minstd, 1.0f) * 2 * RACE_PI);
+            float rad = t.inner + xo_rand_range_val(&r->minstd, 1.0f) * t.width;
+            r->pos_x = (float)(rad * cos((double)theta)) + t.mid_x;
+            r->pos_y = (float)(rad * sin((double)theta)) + t.mid_y;
+        }
+        r->angle = (float)(xo_rand_range_val(&r->minstd, 1.0f) * 2 * RACE_PI); /* BaseCar::set_angle :237-243 */
+        r->steps = 0;
+        return;
+    }
     if (cfg->track_type == 0) { r->pos_x = t.start_x; r->pos_y = t.start_y; }
     else { r->pos_x = (t.inner + t.width / 2) + t.mid_x; r->pos_y = 0.0f + t.mid_y; } /* :76-79 */
     r->angle = (float)(RACE_PI / 2);

@@ -121,7 +121,8 @@ float xo_sg_act(xo_simple_game* g, int action);
 int xo_sg_game_over(const xo_simple_game* g);
 
 /* ---- simple_race (games/simple_race/simple_race_simulator.cpp) ---- */
-typedef struct { float pos_x, pos_y, angle; int32_t steps; } xo_race;
+typedef struct { float pos_x, pos_y, angle; int32_t steps; uint32_t minstd; /* --random: the env's (thread's) engine */ } xo_race;
+float xo_rand_range_val(uint32_t* minstd, float upper); /* util::get_rand_range_val, simulator_util.cpp:57-64 */
 void xo_race_reset(const xw_config* cfg, xo_race* r);
 float xo_race_act(const xw_config* cfg, xo_race* r, int action_index, float state[4], int32_t* game_over);
 float xo_race_take_actions(const xw_config* cfg, xo_race* r, int action_index, int act_rep, float state[4], int32_t* game_over);

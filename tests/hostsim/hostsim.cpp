@@ -76,6 +76,11 @@ HostSim* hs_create(const xw_config* c, const xw_catalog* cat, int n) {
         }
         r.pos_x = halloc<float>(s, n); r.pos_y = halloc<float>(s, n); r.angle = halloc<float>(s, n);
         r.state = halloc<float>(s, (size_t)n * 4); r.steps = halloc<int32_t>(s, n);
+        r.random = c->race_random != 0;
+        if (r.random) {
+            r.minstd = halloc<uint32_t>(s, n);
+            for (int i = 0; i < n; ++i) r.minstd[i] = minstd_seed(c->simulator_seed, c->env_id_offset + i + 1);
+        }
         return s;
     }
     XwDev& d = s->d;

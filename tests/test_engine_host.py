@@ -94,14 +94,16 @@ def test_hostsim_golden_frames_from_real_opencv():
 
 def test_hostsim_race_matches_oracle():
     lib = oracle.lib()
-    for tt, full, hard, rep, ms in [(0, 0, 0, 1, 0), (1, 1, 1, 1, 0), (0, 1, 0, 3, 40), (1, 1, 1, 4, 0)]:
+    for tt, full, hard, rep, ms, rnd in [(0, 0, 0, 1, 0, 0), (1, 1, 1, 1, 0, 0), (0, 1, 0, 3, 40, 0), (1, 1, 1, 4, 0, 0),
+                                         (0, 1, 0, 1, 0, 1), (1, 1, 1, 2, 30, 1)]:   # (the last two: --random start states)
         cfg = _abi.default_config(game=_abi.XW_GAME_SIMPLE_RACE, track_type=tt, race_full_manouver=full, difficulty=hard,
-                                  auto_reset=1, max_steps=ms)
+                                  auto_reset=1, max_steps=ms, race_random=rnd, simulator_seed=5, env_id_offset=3)
         n = 64
         hs = parity.HostSim(cfg, None, n)
         hs.reset()
         orcs = [oracle.XoRace() for _ in range(n)]
-        for o in orcs:
+        for i, o in enumerate(orcs):
+            o.minstd = lib.xo_minstd_seed_for_thread(5, 3 + i + 1)
             lib.xo_race_reset(C.byref(cfg), C.byref(o))
         rng = np.random.RandomState(5)
         for s in range(200):

@@ -206,14 +206,16 @@ def test_simple_race_vs_oracle_1e6(backend_cls):
     """BASELINE config 5 (tol 1e-6 on reward and the 4-float state); reports exact-bit agreement."""
     import torch
     lib = oracle.lib()
-    for tt, full, hard, rep in [(0, 0, 0, 1), (1, 1, 1, 1), (1, 1, 0, 3)]:   # (the last: --act_rep 3, simulator.cpp:98-108)
+    # (the third: --act_rep 3, simulator.cpp:98-108; the last two: --random start states, simple_race_simulator.cpp:267-284)
+    for tt, full, hard, rep, rnd in [(0, 0, 0, 1, 0), (1, 1, 1, 1, 0), (1, 1, 0, 3, 0), (0, 1, 0, 1, 1), (1, 1, 1, 2, 1)]:
         cfg = _abi.default_config(game=_abi.XW_GAME_SIMPLE_RACE, track_type=tt, race_full_manouver=full, difficulty=hard,
-                                  auto_reset=1)
+                                  auto_reset=1, race_random=rnd, simulator_seed=9)
         n = 4096
         eng = backend_cls(cfg, None, n)
         eng.reset()
         orcs = (oracle.XoRace * n)()
-        for o in orcs:
+        for i, o in enumerate(orcs):
+            o.minstd = lib.xo_minstd_seed_for_thread(9, i + 1)
             lib.xo_race_reset(C.byref(cfg), C.byref(o))
         rng = np.random.RandomState(11)
         exact = total = 0
@@ -235,6 +237,37 @@ def test_simple_race_vs_oracle_1e6(backend_cls):
             exact += int((r.view(np.uint32) == r2.view(np.uint32)).sum())
             total += n
         assert exact >= 0.999 * total, (exact, total)
+
+
+def test_step_seq_equals_single_steps(backend_cls, synthetic_catalog):
+    """xw_step_seq (K take_actions calls per launch, include/xworld_b200.h) against K xw_step calls on a twin handle: reward
+    bits, game_over and the final state, for SimpleRace (one launch, car in registers; --random and act_rep included) and xworld."""
+    import torch
+    K = 24
+    for kw, n, n_act, rep in [(dict(game=_abi.XW_GAME_SIMPLE_RACE, track_type=1, race_full_manouver=1, difficulty=1, auto_reset=1), 5000, 9, 1),
+                              (dict(game=_abi.XW_GAME_SIMPLE_RACE, track_type=0, race_full_manouver=1, race_random=1, simulator_seed=3,
+                                    auto_reset=1, max_steps=17), 3000, 9, 2),
+                              (dict(height=7, width=7, n_goals=4, n_blocks=12, rules=0, auto_reset=1, seed=5, simulator_seed=2), 2048, 4, 1)]:
+        cfg = _abi.default_config(**kw)
+        cat = None if cfg.game == _abi.XW_GAME_SIMPLE_RACE else synthetic_catalog
+        a_eng, b_eng = backend_cls(cfg, cat, n), backend_cls(cfg, cat, n)
+        a_eng.reset(); b_eng.reset()
+        rng = np.random.RandomState(2)
+        acts = rng.randint(0, n_act, (K, n)).astype(np.int32)
+        r1 = np.zeros((K, n), np.float32); o1 = np.zeros((K, n), np.int32)
+        for k in range(K):
+            r1[k], o1[k], _ = a_eng.step(acts[k], act_rep=rep)
+        sim = b_eng.sim
+        with torch.cuda.device(sim._dev):
+            da = torch.from_numpy(acts).cuda()
+            dr = torch.zeros((K, n), dtype=torch.float32, device="cuda")
+            do = torch.zeros((K, n), dtype=torch.int32, device="cuda")
+            rc = sim._lib.xw_step_seq(sim._h, da.data_ptr(), K, rep, dr.data_ptr(), do.data_ptr(), sim._stream())
+            assert rc == 0, sim._lib.xw_last_error()
+            r2, o2 = dr.cpu().numpy(), do.cpu().numpy()
+        assert (r1.view(np.uint32) == r2.view(np.uint32)).all() and (o1 == o2).all()
+        for f in (["state"] if cfg.game == _abi.XW_GAME_SIMPLE_RACE else ["grid", "agent_x", "agent_y", "num_steps", "episode"]):
+            assert (a_eng.field(f).view(np.uint8) == b_eng.field(f).view(np.uint8)).all(), f
 
 
 def test_action_none_and_batch_client(backend_cls, synthetic_catalog):

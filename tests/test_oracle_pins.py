@@ -308,6 +308,41 @@ def test_simple_race_act_rep_vs_compiled_reference(oracle_lib):
         R.ref_race_destroy(ref)
 
 
+def test_simple_race_random_start_vs_compiled_reference(oracle_lib):
+    """--random (simple_race_simulator.cpp:24,267-284): track draw, start position and heading from the thread's
+    std::default_random_engine through util::get_rand_range_val -- the compiled reference, its engine re-seeded, against the
+    port (libstdc++'s uniform_real_distribution<float> restated), bit for bit over the trajectories that follow each reset."""
+    R = _ref()
+    R.ref_seed_thread_engine.argtypes = [C.c_uint]
+    R.ref_race_set_random(1)
+    try:
+        for tt, full, hard in [(0, 0, 0), (0, 1, 1), (1, 1, 0), (1, 0, 1)]:
+            cfg = _abi.default_config(game=2, track_type=tt, race_full_manouver=full, difficulty=hard, race_random=1)
+            ref = R.ref_race_create(tt, 20.0, 100.0, 30.0, full, hard, 1.0, 0)
+            rng = np.random.RandomState(31 + tt + 2 * full)
+            for seed in [1, 2, 12345, 2147483646, 987654321, 16807, 77]:
+                R.ref_seed_thread_engine(seed)
+                o = oracle.XoRace()
+                o.minstd = seed % 2147483647 or 1   # linear_congruential_engine::seed
+                for ep in range(12):   # consecutive episodes: the engine state carries over
+                    R.ref_race_reset(ref)
+                    oracle_lib.xo_race_reset(C.byref(cfg), C.byref(o))
+                    for s in range(40):
+                        a = int(rng.randint(0, 9 if full else 2))
+                        st1, ov1 = (C.c_float * 4)(), C.c_int()
+                        st2, ov2 = (C.c_float * 4)(), C.c_int32()
+                        r1 = R.ref_race_step(ref, a, st1, C.byref(ov1))
+                        r2 = oracle_lib.xo_race_act(C.byref(cfg), C.byref(o), a, st2, C.byref(ov2))
+                        a1 = np.array([r1] + list(st1), np.float32)
+                        a2 = np.array([r2] + list(st2), np.float32)
+                        assert (a1.view(np.uint32) == a2.view(np.uint32)).all() and ov1.value == ov2.value, (tt, seed, ep, s, a1, a2)
+                        if ov1.value:
+                            break
+            R.ref_race_destroy(ref)
+    finally:
+        R.ref_race_set_random(0)
+
+
 def test_step_rules_vs_compiled_xmap(oracle_lib, synthetic_catalog):
     """XAgent::act + XMap::move_item compiled from the reference vs the oracle's move rules, on
     generated maps with random action streams (position, success flag, contacted item)."""

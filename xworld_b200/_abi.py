@@ -119,7 +119,7 @@ class XwWireRequest(C.Structure):
 
 # every symbol include/xworld_b200.h declares
 SYMBOLS = [
-    "xw_config_init", "xw_create", "xw_destroy", "xw_last_error", "xw_reset", "xw_step", "xw_render",
+    "xw_config_init", "xw_create", "xw_destroy", "xw_last_error", "xw_reset", "xw_step", "xw_step_seq", "xw_render",
     "xw_step_host", "xw_reset_host", "xw_step_hd", "xw_step_hd_async", "xw_wait_frames", "xw_sync", "xw_num_envs", "xw_num_actions", "xw_screen_dims",
     "xw_frame_bytes", "xw_num_steps", "xw_get_field", "xw_set_field", "xw_error_flags", "xw_get_fields",
     "xw_world_dimensions", "xw_extra_info", "xw_task_performance", "xw_launch_count", "xw_render_kernel", "xw_sentence_compose",
@@ -152,6 +152,8 @@ def load():
     lib.xw_reset.restype = C.c_int
     lib.xw_step.argtypes = [vp, vp, i32, vp, vp, vp, vp]
     lib.xw_step.restype = C.c_int
+    lib.xw_step_seq.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+    lib.xw_step_seq.restype = C.c_int
     lib.xw_render.argtypes = [vp, vp, vp]
     lib.xw_render.restype = C.c_int
     lib.xw_step_host.argtypes = [vp, vp, i32, vp, vp, vp]

@@ -97,9 +97,35 @@ __global__ void __launch_bounds__(256) k_race_step(XwRaceCfg r, const int32_t* _
     if (a == XW_ACTION_NONE) return;
     if (a < 0 || a >= n_actions) { error[e] = XW_ERR_INVALID_ACTION; reward[e] = 0.f; over[e] = 0; return; }
     float rw; int32_t o;
-    bool need = xw_race_step_env(r, e, a, act_rep, &rw, &o);
+    XwRaceCar c = xw_race_load(r, e);
+    const bool need = xw_race_step_car(r, c, a, act_rep, &rw, &o, r.state + (size_t)e * 4);
     reward[e] = rw; over[e] = o;
-    if (need) xw_race_reset_env(r, e);  // the race reset is two stores: done in place
+    if (need) xw_race_reset_car(r, c);  // the race reset is a few stores (four draws with --random): done in place
+    xw_race_store(r, e, c);
+}
+// K consecutive take_actions calls of every env in ONE launch (xw_step_seq): actions / reward / game_over are [K][n], the car
+// stays in registers between the steps, the state vector is written once (after the last step).  For open-loop action sequences
+// (evaluation roll-outs, action-repeat style agents): a step of this game is ~60 bytes and ~300 instructions per env, so at one
+// launch per step the launch itself is most of the time (profiles/r01_summary.md).
+__global__ void __launch_bounds__(256) k_race_step_seq(XwRaceCfg r, const int32_t* __restrict__ actions, int n_actions, int act_rep, int K,
+                                                       float* __restrict__ reward, int32_t* __restrict__ over, int32_t* error) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= r.n) return;
+    XwRaceCar c = xw_race_load(r, e);
+    float st[4] = {r.state[(size_t)e * 4], r.state[(size_t)e * 4 + 1], r.state[(size_t)e * 4 + 2], r.state[(size_t)e * 4 + 3]};
+    for (int k = 0; k < K; ++k) {
+        const size_t i = (size_t)k * r.n + e;
+        const int a = actions[i];
+        if (a == XW_ACTION_NONE) continue;
+        if (a < 0 || a >= n_actions) { error[e] = XW_ERR_INVALID_ACTION; reward[i] = 0.f; over[i] = 0; continue; }
+        float rw; int32_t o;
+        const bool need = xw_race_step_car(r, c, a, act_rep, &rw, &o, st);
+        reward[i] = rw; over[i] = o;
+        if (need) xw_race_reset_car(r, c);
+    }
+    xw_race_store(r, e, c);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) r.state[(size_t)e * 4 + q] = st[q];
 }
 
 // ------------------------------------------------------------------------------------ handle
@@ -638,7 +664,6 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
 
 static int create_race(xw_sim* s) {
     const xw_config& c = s->cfg;
-    if (c.race_random) return set_err(XW_ERR_UNSUPPORTED, "simple_race --random is not implemented");
     XwRaceCfg& r = s->race;
     memset(&r, 0, sizeof r);
     r.n = s->n; r.track_type = c.track_type; r.full_manouver = c.race_full_manouver; r.difficulty = c.difficulty;
@@ -660,6 +685,14 @@ static int create_race(xw_sim* s) {
     rc |= dalloc(s, &r.state, (size_t)s->n * 4);
     rc |= dalloc(s, &r.steps, (size_t)s->n);
     rc |= dalloc(s, &s->race_error, (size_t)s->n);
+    r.random = c.race_random != 0;
+    if (r.random && !rc) {  // env i = the reference's (i + 1)-th simulator thread (simulator_util.cpp:38-52)
+        rc |= dalloc(s, &r.minstd, (size_t)s->n);
+        if (rc) return rc;
+        std::vector<uint32_t> seeds(s->n);
+        for (int i = 0; i < s->n; ++i) seeds[i] = minstd_seed(c.simulator_seed, c.env_id_offset + i + 1);
+        CUDA_TRY(cudaMemcpy(r.minstd, seeds.data(), sizeof(uint32_t) * s->n, cudaMemcpyHostToDevice));
+    }
     return rc;
 }
 
@@ -1145,6 +1178,30 @@ int xw_step(xw_sim* s, const int32_t* d_actions, int32_t act_rep, float* d_rewar
         CUDA_TRY(cudaGetLastError());
         if (d_frames)  // "screen" of simple_race = the 4-float state vector
             CUDA_TRY(cudaMemcpyAsync(d_frames, s->race.state, sizeof(float) * 4 * s->n, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+    return set_err(XW_ERR_UNSUPPORTED, "simple_game runs on the host: use xw_step_host");
+}
+
+// K consecutive take_actions calls per env, no frames: d_actions / d_reward / d_game_over are [K][n_envs] (step-major).
+// simple_race: one launch (k_race_step_seq); xworld: K step (+ auto-reset) launches queued back to back.  Results are
+// those of K xw_step calls with d_frames == NULL.
+int xw_step_seq(xw_sim* s, const int32_t* d_actions, int32_t k_steps, int32_t act_rep, float* d_reward, int32_t* d_game_over, void* stream) {
+    DevGuard dev_guard(s);
+    if (!d_actions || !d_reward || !d_game_over) return set_err(XW_ERR_INVALID_ARG, "null buffer");
+    if (act_rep < 1 || k_steps < 1) return set_err(XW_ERR_INVALID_ARG, "act_rep and k_steps must be >= 1");
+    cudaStream_t st = pick_stream(s, stream);
+    if (s->cfg.game == XW_GAME_SIMPLE_RACE) {
+        k_race_step_seq<<<(s->n + 255) / 256, 256, 0, st>>>(s->race, d_actions, xw_num_actions(s), act_rep, k_steps, d_reward, d_game_over, s->race_error);
+        s->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
+    if (s->cfg.game == XW_GAME_XWORLD) {
+        for (int k = 0; k < k_steps; ++k) {
+            const int rc = step_xworld(s, d_actions + (size_t)k * s->n, act_rep, d_reward + (size_t)k * s->n, d_game_over + (size_t)k * s->n, nullptr, st, nullptr);
+            if (rc) return rc;
+        }
         return 0;
     }
     return set_err(XW_ERR_UNSUPPORTED, "simple_game runs on the host: use xw_step_host");
