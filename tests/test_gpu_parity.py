@@ -580,6 +580,27 @@ def test_fpv_golden_frames_from_real_opencv(backend_cls):
     assert n == 42 and kernels == {4, 5, 6}   # the any-size kernel, the shared-memory one and the cell-block one all ran
 
 
+def test_fpv_streaming_goal_kernel_same_frames(backend_cls, synthetic_catalog, monkeypatch):
+    """XW_FPV_STREAM=1 (the goal kernel beside the frame kernel: ready bits, launch sequence numbers, TMA ring) paints the
+    same frames as the default (goal kernel after the frame kernel), step after step with auto-reset."""
+    cfg = _abi.default_config(height=11, width=11, n_goals=4, n_blocks=30, rules=1, visible_radius=7, max_steps=40, auto_reset=1,
+                              seed=21, simulator_seed=3)
+    n = 3000
+    a_eng = backend_cls(cfg, synthetic_catalog, n)
+    monkeypatch.setenv("XW_FPV_STREAM", "1")
+    b_eng = backend_cls(cfg, synthetic_catalog, n)
+    monkeypatch.delenv("XW_FPV_STREAM")
+    assert a_eng.sim.render_kernel() == 6 and b_eng.sim.render_kernel() == 6
+    a_eng.reset(); b_eng.reset()
+    rng = np.random.RandomState(4)
+    for s in range(60):
+        a = rng.randint(0, 6, n).astype(np.int32)
+        r1, o1, f1 = a_eng.step(a, render=True)
+        r2, o2, f2 = b_eng.step(a, render=True)
+        assert (r1.view(np.uint32) == r2.view(np.uint32)).all() and (o1 == o2).all()
+        assert (f1 == f2).all(), (s, int((f1 != f2).sum()))
+
+
 def test_fpv_auto_reset_and_context(backend_cls, synthetic_catalog):
     """Auto-reset in the first-person view: the goal icons of re-started episodes are warped by the list-mode launch."""
     cfg = parity.make_cfg("fpv_nav3d_8x8_vr3_84", auto_reset=1, max_steps=30)

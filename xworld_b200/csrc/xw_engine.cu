@@ -173,7 +173,11 @@ struct xw_sim {
     // first-person view
     XwFpv fpv;
     bool fpv_fast = false;
-    void (*fpv_cells_fn)(XwDev, XwFpv, uint8_t*, size_t, const int32_t*, const int32_t*, int, int, int, int, int, int) = nullptr;
+    void (*fpv_cells_fn)(XwDev, XwFpv, uint8_t*, size_t, const int32_t*, const int32_t*, int, int, int, int, int, int, int) = nullptr;
+    void (*fpv_stream_fn)(XwFpv, uint8_t*, size_t, int, int, int, int, int) = nullptr;
+    bool fpv_streaming = false;  // XW_FPV_STREAM=1: the goal kernel BESIDE the frame kernel (k_fpv_goal_stream) -- measured slower than one
+                                 // after the other (0.45 ms against 0.38 ms per render at 65,536 envs, profiles/r02_summary.md): opt-in
+    int fpv_seq = 0;
     void (*fpv_goal_fn)(XwFpv, uint8_t*, size_t, int, int) = nullptr;
     int fpv_smem = 0, fpv_grid = 0, fpv_nt = 256, fpv_ng = 1, fpv_goal_grid = 0, fpv_goal_nt = 160;
     // the batch is rendered in fpv_chunks chunks: k_fpv_goal_cells of chunk k runs on fpv_stream beside the frame kernel of chunk k + 1
@@ -331,7 +335,7 @@ static int create_fpv(xw_sim* s, const xw_catalog* cat, int OH, int OW) {
             rc |= dupload(s, &F.block2cell, b2c.data(), b2c.size());
             if (rc) return rc;
             F.regular = 1; F.bs = bs; F.taps4 = taps;
-            rc |= dalloc(s, &F.goal_count, 2 * ((size_t)xw_sim::FPV_MAX_CHUNKS + 1));
+            rc |= dalloc(s, &F.goal_count, 2 * (size_t)XW_FPV_SLOTS);
             rc |= dalloc(s, &F.goal_list, (size_t)s->n * F.G, false);
             if (rc) return rc;
             k_fpv_build_taps<<<s->n_sms * 4, 256, 0, s->own_stream>>>(F, taps);  // (F.taps4 == taps)
@@ -342,7 +346,7 @@ static int create_fpv(xw_sim* s, const xw_catalog* cat, int OH, int OW) {
     if (s->fpv_fast && F.regular) {
         const int ncell = F.vr * F.vr;
         s->fpv_nt = 128;
-        const int per_group = (F.FB + d.CS + ((ncell + 15) & ~15) + 16 + 127) & ~127;
+        const int per_group = (F.FB + d.CS + ((ncell + 15) & ~15) + 16 + 128 + 127) & ~127;
         s->fpv_ng = 8;
         while (s->fpv_ng > 1 && s->fpv_ng * per_group > 200 * 1024) s->fpv_ng >>= 1;
         s->fpv_smem = s->fpv_ng * per_group;
@@ -355,6 +359,21 @@ static int create_fpv(xw_sim* s, const xw_catalog* cat, int OH, int OW) {
         s->fpv_goal_fn = F.bs == 12 && F.vr == 7 ? k_fpv_goal_cells<12, 7> : F.bs == 28 && F.vr == 3 ? k_fpv_goal_cells<28, 3>
                        : F.bs == 84 && F.vr == 1 ? k_fpv_goal_cells<84, 1> : k_fpv_goal_cells<0, 0>;
         s->fpv_goal_nt = F.bs * F.bs >= 160 ? 160 : ((F.bs * F.bs + 31) & ~31);
+        s->fpv_stream_fn = F.bs == 12 && F.vr == 7 ? k_fpv_goal_stream<12, 7> : F.bs == 28 && F.vr == 3 ? k_fpv_goal_stream<28, 3>
+                         : F.bs == 84 && F.vr == 1 ? k_fpv_goal_stream<84, 1> : k_fpv_goal_stream<0, 0>;
+        CUDA_TRY(cudaFuncSetAttribute(s->fpv_stream_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 16384 + 128));
+        // the largest shared-memory carve-out for both: the frame kernel alone would get the smallest configuration that holds its
+        // 172 KB (196 KB), and the carve-out of an SM cannot change while a CTA is resident -- the streaming kernel's 49 KB would
+        // then not fit beside it and it would only start when the frame kernel has left
+        if (const char* ev = getenv("XW_FPV_STREAM")) s->fpv_streaming = atoi(ev) != 0;
+        if (F.G > 6) s->fpv_streaming = false;   // (the frame kernel keeps six pending list positions per env)
+        if (s->fpv_streaming) {
+            CUDA_TRY(cudaFuncSetAttribute(s->fpv_stream_fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            CUDA_TRY(cudaFuncSetAttribute(s->fpv_cells_fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        } else {
+            CUDA_TRY(cudaFuncSetAttribute(s->fpv_cells_fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutDefault));
+        }
+        if (const char* ev = getenv("XW_FPV_STREAM")) s->fpv_streaming = atoi(ev) != 0;
         {
             int per_sm = 0;
             CUDA_TRY(cudaFuncSetAttribute(s->fpv_goal_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 + 16));
@@ -886,8 +905,9 @@ static int launch_render(xw_sim* s, uint8_t* d_frames, cudaStream_t st, const Re
         if (s->fpv_fast && dst_stride % 16 == 0) {
             if (s->fpv.regular) {
                 const int nch = s->fpv_chunks, G = s->fpv.G;
-                const int slots = xw_sim::FPV_MAX_CHUNKS + 1, pbase = (s->fpv_parity ^= 1) * slots, zbase = (s->fpv_parity ^ 1) * slots;
-                if (nch > 1 && !s->fpv_stream) {
+                const int slots = XW_FPV_SLOTS, pbase = (s->fpv_parity ^= 1) * slots, zbase = (s->fpv_parity ^ 1) * slots;
+                const bool streaming = s->fpv_streaming && nch == 1;
+                if ((nch > 1 || streaming) && !s->fpv_stream) {
                     CUDA_TRY(cudaStreamCreateWithFlags(&s->fpv_stream, cudaStreamNonBlocking));
                     for (auto& e : s->fpv_ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
                 }
@@ -898,9 +918,22 @@ static int launch_render(xw_sim* s, uint8_t* d_frames, cudaStream_t st, const Re
                     const int need = (cnt + s->fpv_ng - 1) / s->fpv_ng;
                     if (grid > need) grid = need;
                     if (grid < 1) grid = 1;
-                    s->fpv_cells_fn<<<grid, s->fpv_nt, s->fpv_smem, st>>>(s->d, s->fpv, dst, dst_stride, nullptr, nullptr, env0, cnt, pbase + k, env0 * G, zbase, slots);
+                    int seq = 0;
+                    if (streaming) {
+                        // the goal kernel BESIDE the frame kernel: on its own stream, behind everything queued so far (the previous
+                        // render's users of the list), one CTA per SM
+                        seq = s->fpv_seq = s->fpv_seq % 4000 + 1;
+                        CUDA_TRY(cudaEventRecord(s->fpv_ev[0], st));
+                        CUDA_TRY(cudaStreamWaitEvent(s->fpv_stream, s->fpv_ev[0], 0));
+                        s->fpv_stream_fn<<<s->n_sms, 512, 3 * 16384 + 128, s->fpv_stream>>>(s->fpv, dst, dst_stride, pbase, env0 * G, seq, grid * s->fpv_ng,
+                                                                                              s->n * G);
+                        CUDA_TRY(cudaEventRecord(s->fpv_ev[xw_sim::FPV_MAX_CHUNKS], s->fpv_stream));
+                    }
+                    s->fpv_cells_fn<<<grid, s->fpv_nt, s->fpv_smem, st>>>(s->d, s->fpv, dst, dst_stride, nullptr, nullptr, env0, cnt, pbase + k, env0 * G, zbase, slots, seq);
                     if (fix && fix->between) { const int rcb = fix->between(); if (rcb) return rcb; }
                     if (s->trace && s->tr[5]) CUDA_TRY(cudaEventRecord(s->tr[5], st));
+                    s->launches += 2;
+                    if (streaming) { CUDA_TRY(cudaStreamWaitEvent(st, s->fpv_ev[xw_sim::FPV_MAX_CHUNKS], 0)); continue; }
                     cudaStream_t gs = st;
                     if (nch > 1) {
                         gs = s->fpv_stream;
@@ -908,7 +941,6 @@ static int launch_render(xw_sim* s, uint8_t* d_frames, cudaStream_t st, const Re
                         CUDA_TRY(cudaStreamWaitEvent(gs, s->fpv_ev[k], 0));
                     }
                     s->fpv_goal_fn<<<s->fpv_goal_grid, s->fpv_goal_nt, 16384 + 16, gs>>>(s->fpv, dst, dst_stride, pbase + k, env0 * G);
-                    s->launches += 2;
                 }
                 s->launches--;   // (the common increment below counts one)
                 if (nch > 1) {
@@ -951,10 +983,10 @@ static int launch_render(xw_sim* s, uint8_t* d_frames, cudaStream_t st, const Re
         }
         if (fix->done) CUDA_TRY(cudaStreamWaitEvent(st, fix->done, 0));
         if (s->d.vr > 0) {  // first-person view: the frame kernel and the goal kernel again, over the queue (its own goal-list slot)
-            const int slot = s->fpv_parity * (xw_sim::FPV_MAX_CHUNKS + 1) + xw_sim::FPV_MAX_CHUNKS;   // (the main pass zeroed nothing of this half)
+            const int slot = s->fpv_parity * XW_FPV_SLOTS + xw_sim::FPV_MAX_CHUNKS;   // (the main pass zeroed nothing of this half)
             int blocks = (fix->est + s->fpv_ng - 1) / s->fpv_ng;
             if (blocks > s->fpv_grid) blocks = s->fpv_grid;
-            s->fpv_cells_fn<<<blocks, s->fpv_nt, s->fpv_smem, st>>>(s->d, s->fpv, dst, dst_stride, fix->list, fix->count, 0, 0, slot, 0, 0, 0);
+            s->fpv_cells_fn<<<blocks, s->fpv_nt, s->fpv_smem, st>>>(s->d, s->fpv, dst, dst_stride, fix->list, fix->count, 0, 0, slot, 0, 0, 0, 0);
             blocks = 2 * fix->est < s->fpv_goal_grid ? 2 * fix->est : s->fpv_goal_grid;
             s->fpv_goal_fn<<<blocks, s->fpv_goal_nt, 16384 + 16, st>>>(s->fpv, dst, dst_stride, slot, 0);
             s->launches += 2;
@@ -1329,15 +1361,12 @@ static int invalid_status(xw_sim* s) {
     return fresh > 0 ? set_err(XW_ERR_INVALID_ACTION, "invalid action for %d env(s): left untouched and flagged (xw_error_flags)", fresh) : 0;
 }
 
+// Is the caller's buffer page-locked (then it is used in place)?  Asked on every call (about a microsecond each): a cache of
+// addresses would mis-classify a buffer that was freed and whose address was handed out again as pageable memory.
 static bool is_pinned(const void* p) {
-    static thread_local const void* seen[16] = {};  // (a trainer passes the same few buffers every step)
-    for (const void* q : seen) if (q == p) return true;
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    if (a.type != cudaMemoryTypeHost) return false;
-    static thread_local int next = 0;
-    seen[next++ & 15] = p;
-    return true;
+    return a.type == cudaMemoryTypeHost;
 }
 
 // Host actions in, host reward / game_over out, frames stay on the device.  Page-locked caller buffers are used

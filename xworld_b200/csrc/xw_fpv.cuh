@@ -30,6 +30,11 @@
 
 // crop-cell classes (the grid's cell codes + black)
 #define XW_FPV_BLACK 0x80
+// goal counters of one render launch (XwFpv::goal_count[2][XW_FPV_SLOTS]): [0 .. 8] entries listed per chunk slot, [9] entries
+// claimed by the streaming goal kernel, [10] frame-kernel groups that have finished
+#define XW_FPV_SLOTS 11
+#define XW_FPV_HEAD 9
+#define XW_FPV_DONE 10
 
 struct XwFpv {
     int32_t vr, N;            // window side in cells / pixels (N = 64 * vr)
@@ -479,10 +484,25 @@ __global__ void k_fpv_build_taps(XwFpv F, uint4* taps4) {
 // HBM writes, the goal kernel by instruction issue).
 // Dynamic shared memory of k_render_fpv_cells, per group: frame [FB] | grid row [CS] | cell codes [ceil16(vr^2)] | misc [4 x i32].
 // (BS_T, VR_T: compile-time block size and window side of the common geometries; 0 = read them from F)
+// bar.sync with an IMMEDIATE barrier id per group: with the id in a register ptxas books all 16 barriers for the CTA, and the
+// barrier slots are an SM resource -- no CTA of another kernel (which needs one for __syncthreads) could then share the SM
+__device__ __forceinline__ void xw_group_bar_imm(int grp, int nthreads) {
+    switch (grp) {
+        case 0: asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); break;
+        case 1: asm volatile("bar.sync 2, %0;" ::"r"(nthreads) : "memory"); break;
+        case 2: asm volatile("bar.sync 3, %0;" ::"r"(nthreads) : "memory"); break;
+        case 3: asm volatile("bar.sync 4, %0;" ::"r"(nthreads) : "memory"); break;
+        case 4: asm volatile("bar.sync 5, %0;" ::"r"(nthreads) : "memory"); break;
+        case 5: asm volatile("bar.sync 6, %0;" ::"r"(nthreads) : "memory"); break;
+        case 6: asm volatile("bar.sync 7, %0;" ::"r"(nthreads) : "memory"); break;
+        default: asm volatile("bar.sync 8, %0;" ::"r"(nthreads) : "memory"); break;
+    }
+}
 template <int NT, int NG, int BS_T, int VR_T>
 __global__ void __maxnreg__(48) k_render_fpv_cells(XwDev d, XwFpv F, uint8_t* __restrict__ frames, size_t env_stride,
                                                                  const int32_t* __restrict__ list, const int32_t* __restrict__ count,
-                                                                 int env0, int env_n, int chunk, int list_base, int zero_base, int zero_n) {
+                                                                 int env0, int env_n, int chunk, int list_base, int zero_base, int zero_n,
+                                                                 int stream_seq) {
     extern __shared__ __align__(128) uint8_t smem_all[];
     // (programmatic dependent launch: the step's auto-reset kernel, queued behind this one, may start once every CTA is resident --
     //  see k_render_sp)
@@ -496,12 +516,15 @@ __global__ void __maxnreg__(48) k_render_fpv_cells(XwDev d, XwFpv F, uint8_t* __
     // NG groups of NT threads, each a frame pipeline of its own (buffer, barrier, TMA stores): one CTA per SM, so that a launch on
     // fewer CTAs than SMs leaves whole SMs to the auto-reset kernels that run beside it (xw_engine.cu step_xworld)
     const int grp = threadIdx.x / NT, tid = threadIdx.x - grp * NT;
-    uint8_t* smem = smem_all + (size_t)grp * ((F.FB + d.CS + nc16 + 16 + 127) & ~127);
+    uint8_t* smem = smem_all + (size_t)grp * ((F.FB + d.CS + nc16 + 16 + 128 + 127) & ~127);
     const int vcta = blockIdx.x * NG + grp, vgrid = gridDim.x * NG;
     uint32_t* fb = (uint32_t*)smem;
     uint8_t* row = smem + F.FB;
     uint8_t* ccode = row + d.CS;
-    int* misc = (int*)(ccode + nc16);   // [1] heading
+    int* misc = (int*)(ccode + nc16);   // [1] heading, [2] goal cells of the env being prepared
+    // streaming (stream_seq != 0: k_fpv_goal_stream runs BESIDE this kernel): the list entries of an env become valid for the goal
+    // kernel only when the env's frame has landed in HBM, i.e. when its TMA store is complete -- thread 32 marks them one env later
+    uint32_t* pend = (uint32_t*)(misc + 4);   // [4][6] list positions of the goal cells of the last four envs, [24 .. 27] their counts
     const uint8_t* __restrict__ b2c = F.block2cell;
     const uint8_t* __restrict__ c2b = F.cell2block;
     const int lane = tid & 31, warp = tid >> 5, n_warps = NT >> 5;
@@ -521,12 +544,21 @@ __global__ void __maxnreg__(48) k_render_fpv_cells(XwDev d, XwFpv F, uint8_t* __
         pre_ax = d.agent_x[e]; pre_ay = d.agent_y[e]; pre_f = d.facing[e];
     };
     if (warp == 0) prefetch(vcta);
-    for (int idx = vcta; idx < total; idx += vgrid) {
+    auto mark_ready = [&](int buf) {   // (thread 32) the env's frame is in HBM: its goal cells may be taken
+        const int np = (int)pend[24 + buf];
+        for (int j = 0; j < np; ++j) {
+            volatile uint32_t* hi = (volatile uint32_t*)(goal_list + pend[buf * 6 + j]) + 1;
+            *hi = *hi | 0x80000000u;
+        }
+    };
+    uint32_t it = 0;
+    for (int idx = vcta; idx < total; idx += vgrid, ++it) {
         const int e = list ? list[idx] : env0 + idx;
+        const int pb = (int)(it & 3u);
         if (warp == 0) {
             if (lane < row_words) ((uint32_t*)row)[lane] = pre0;
             if (lane + 32 < row_words) ((uint32_t*)row)[lane + 32] = pre1;
-            if (lane == 0) misc[1] = pre_f;
+            if (lane == 0) { misc[1] = pre_f; misc[2] = 0; }
             __syncwarp();
             for (int k = lane; k < vr; k += 32) xw_fpv_cells_line_at(row, d.W, d.H, vr, pre_ax, pre_ay, pre_f, k, ccode);
             __syncwarp();
@@ -534,14 +566,18 @@ __global__ void __maxnreg__(48) k_render_fpv_cells(XwDev d, XwFpv F, uint8_t* __
                 const int code = ccode[c];
                 if (code >= XW_CELL_GOAL0 && code != XW_FPV_BLACK) {
                     const int k = atomicAdd(goal_count, 1);
-                    goal_list[k] = (uint64_t)(uint32_t)e | ((uint64_t)((uint32_t)c2b[pre_f * n_cells + c] | ((uint32_t)(code - XW_CELL_GOAL0) << 8) | ((uint32_t)pre_f << 16)) << 32);
+                    goal_list[k] = (uint64_t)(uint32_t)e | ((uint64_t)((uint32_t)c2b[pre_f * n_cells + c] | ((uint32_t)(code - XW_CELL_GOAL0) << 8) | ((uint32_t)pre_f << 16) |
+                                                                       ((uint32_t)stream_seq << 18)) << 32);
+                    if (stream_seq) { const int j = atomicAdd(&misc[2], 1); if (j < 6) pend[pb * 6 + j] = (uint32_t)k; }
                 }
             }
+            __syncwarp();
+            if (lane == 0) pend[24 + pb] = (uint32_t)(misc[2] < 6 ? misc[2] : 6);
             prefetch(idx + vgrid);
         } else if (tid == 32) {
             tma_wait_read<0>();   // the previous frame has left the buffer
         }
-        group_bar(1 + grp, NT);
+        xw_group_bar_imm(grp, NT);
         const int facing = misc[1];
         const uint32_t* tb = (const uint32_t*)(F.Tb + (size_t)facing * 3 * plane);
         const uint32_t* ta = (const uint32_t*)(F.Ta + (size_t)facing * 3 * plane);
@@ -565,10 +601,27 @@ __global__ void __maxnreg__(48) k_render_fpv_cells(XwDev d, XwFpv F, uint8_t* __
         }
         cp_async_wait_all();
         fence_async_smem();
-        group_bar(1 + grp, NT);
-        if (tid == 32) { tma_store_1d(frames + (size_t)e * env_stride, fb, (uint32_t)F.FB); tma_commit(); }
+        xw_group_bar_imm(grp, NT);
+        if (tid == 32) {
+            tma_store_1d(frames + (size_t)e * env_stride, fb, (uint32_t)F.FB);
+            tma_commit();
+            if (stream_seq && it > 1) {   // the store of the env before the previous one (committed two env times ago) is complete by now
+                tma_wait_all<2>();
+                __threadfence();
+                mark_ready((int)((it + 2u) & 3u));
+            }
+        }
     }
-    if (tid == 32) tma_wait_all<0>();
+    if (tid == 32) {
+        tma_wait_all<0>();
+        if (stream_seq) {
+            __threadfence();
+            if (it > 1) mark_ready((int)((it + 2u) & 3u));   // the group's last two envs
+            if (it > 0) mark_ready((int)((it + 3u) & 3u));
+            __threadfence();
+            atomicAdd(F.goal_count + (chunk - chunk % XW_FPV_SLOTS) + XW_FPV_DONE, 1);
+        }
+    }
 }
 
 // One bilinear step of cv::resize on three packed channels (B | G << 8 | R << 16): the horizontal pass of a row is one
@@ -634,6 +687,106 @@ __global__ void __launch_bounds__(160) k_fpv_goal_cells(XwFpv F, uint8_t* __rest
         if (!waited) mbar_wait(bar, phase);
         phase ^= 1;
         __syncthreads();   // every thread is done with the icon before the next load lands
+    }
+}
+
+// The goal cells of a launch, taken WHILE k_render_fpv_cells runs (one CTA per SM beside the frame kernel's): warp 0 claims list
+// positions (atomic head), waits until the position holds an entry of this launch whose frame has landed (ready bit + launch
+// sequence number, set by the frame kernel when the env's TMA store is complete) and streams the goal's icon into a three-stage
+// shared-memory ring with TMA bulk loads; each stage has its own five warps that evaluate the cell's 144 pixels (full / empty mbarriers).  The
+// frame kernel is bound by HBM writes and this one by instruction issue and icon reads, so side by side they cost little more
+// than the frame kernel alone.  Ends when every group of the frame kernel has reported done and the list is exhausted.
+// Dynamic shared memory: 3 x icon [16 KB] | entries [3 x u64] | full [3], empty [3] mbarriers.
+template <int BS_T, int VR_T>
+__global__ void __maxnreg__(32) k_fpv_goal_stream(XwFpv F, uint8_t* __restrict__ frames, size_t env_stride, int ctr_base, int list_base,
+                                                  int seq, int expected_groups, int list_cap) {
+    // (512 threads x 32 registers: exactly what a 1,024-thread x 48-register frame CTA leaves of an SM's register file)
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int S = 3;   // stages = compute groups: warp 0 loads, threads 32 + 160 g .. 32 + 160 g + 159 evaluate the cells of stage g
+    uint64_t* ent_s = (uint64_t*)(smem + S * 16384);
+    uint64_t* full = ent_s + S;
+    uint64_t* empty = full + S;
+    const int vr = VR_T ? VR_T : F.vr, bs = BS_T ? BS_T : F.bs, OW = bs * vr, plane = OW * OW, bb = bs * bs;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int i = 0; i < S; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 5); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    volatile int32_t* ctr = F.goal_count + ctr_base;
+    uint64_t* __restrict__ glist = F.goal_list + list_base;
+    const uint64_t EXIT = ~0ull;
+    if (warp == 0) {
+        // the loader warp: 32 list positions are claimed at once and polled side by side (a claim and a poll are each an L2 round
+        // trip: one lane doing them one after the other was the whole kernel's pace), then handed to the stages in order
+        const long long t_start = clock64();
+        uint32_t it = 0;
+        for (bool more = true; more;) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd((int32_t*)F.goal_count + ctr_base + XW_FPV_HEAD, 32);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const int i = base + lane;
+            uint32_t e_lo = 0xffffffffu, e_hi = 0xffffffffu;   // EXIT
+            for (;;) {
+                if (i < list_cap) {
+                    const uint32_t hi = ((volatile uint32_t*)(glist + i))[1];
+                    if ((hi >> 31) && ((hi >> 18) & 0x1fffu) == (uint32_t)seq) {
+                        __threadfence();
+                        e_lo = ((volatile uint32_t*)(glist + i))[0]; e_hi = hi;
+                        ((volatile uint32_t*)(glist + i))[1] = 0u;   // consumed: a later launch never finds it ready
+                        break;
+                    }
+                }
+                if (ctr[XW_FPV_DONE] >= expected_groups) {
+                    __threadfence();
+                    if (i >= ctr[0] || i >= list_cap) break;   // the list is exhausted
+                }
+                if (clock64() - t_start > 400000000ll) break;  // (0.2 s: never hang the device on a protocol error)
+                __nanosleep(64);
+            }
+            __syncwarp();
+            for (int l = 0; l < 32 && more; ++l) {
+                const uint32_t lo = __shfl_sync(0xffffffffu, e_lo, l), hi = __shfl_sync(0xffffffffu, e_hi, l);
+                if (lo == 0xffffffffu && hi == 0xffffffffu) { more = false; break; }   // (positions past the end: every later one too)
+                if (lane == 0) {
+                    const int s = (int)(it % S);
+                    if (it >= S) mbar_wait(empty + s, ((it / S) & 1u) ^ 1u);
+                    ent_s[s] = (uint64_t)lo | ((uint64_t)hi << 32);
+                    mbar_expect_tx(full + s, 16384u);
+                    tma_load_1d(smem + s * 16384, F.gcache + ((size_t)lo * F.G + ((hi >> 8) & 255u)) * 4096, 16384u, full + s);
+                }
+                ++it;
+            }
+        }
+        if (lane == 0)
+            for (int k = 0; k < S; ++k, ++it) {   // every compute group gets its own EXIT
+                const int s = (int)(it % S);
+                if (it >= S) mbar_wait(empty + s, ((it / S) & 1u) ^ 1u);
+                ent_s[s] = EXIT;
+                mbar_arrive(full + s);
+            }
+        return;
+    }
+    const int g = (tid - 32) / 160, ct = tid - 32 - g * 160;
+    if (g >= S) return;
+    const uint8_t* icon = smem + g * 16384;
+    for (uint32_t k = 0;; ++k) {   // the group's k-th cell = stage g of iteration k * S + g
+        mbar_wait(full + g, k & 1u);
+        const uint64_t ent = ent_s[g];
+        if (ent == EXIT) break;
+        const uint32_t lo = (uint32_t)ent, hi = (uint32_t)(ent >> 32);
+        const int e = (int)lo, blk = hi & 255, facing = (hi >> 16) & 3;
+        const int by = blk / vr, bx = blk - by * vr;
+        const uint4* t4 = (const uint4*)F.taps4 + (size_t)facing * 4 * plane;
+        uint8_t* out = frames + (size_t)e * env_stride;
+        for (int q = ct; q < bb; q += 160) {
+            const int qy = q / bs, p = (by * bs + qy) * OW + bx * bs + (q - qy * bs);
+            const uint4 q0 = __ldg(t4 + p), q1 = __ldg(t4 + (size_t)plane + p), q2 = __ldg(t4 + 2 * (size_t)plane + p), q3 = __ldg(t4 + 3 * (size_t)plane + p);
+            const uint32_t v = xw_fpv_px_taps_dev(q0, q1, q2, q3, icon);
+            out[p] = (uint8_t)v; out[plane + p] = (uint8_t)(v >> 8); out[2 * (size_t)plane + p] = (uint8_t)(v >> 16);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + g);   // (the group's five warps are whole warps: 32 + 160 g is a multiple of 32)
     }
 }
 
