@@ -82,7 +82,7 @@ struct XwDev {
     const int32_t *name_first, *name_icons;
     const uint8_t* icon_colored;
     // ---- auto-reset queue (ping-pong counters) ----
-    int32_t* reset_count;      // [2]
+    int32_t* reset_count;      // [4]: [0..1] queue lengths, [2..3] positions claimed by the reset launch's warps (same ping-pong)
     int32_t* reset_list;       // [n]
 };
 

@@ -54,18 +54,31 @@ __global__ void __launch_bounds__(128) k_reset(XwDev d, const uint8_t* mask) {
     // an explicit reset (not the auto-reset of a step, whose game_over code is still to be read): the env is "alive", reward 0
     if (d.stage_over) { d.stage_over[i] = 0; d.stage_rew[i] = 0.f; }
 }
-__global__ void __launch_bounds__(128) k_reset_list(XwDev d, const int32_t* list, const int32_t* count) {
+// (`count` = reset_count + parity; the claim counter of the same parity sits two ints behind it.  Warps CLAIM queue positions
+//  instead of striding over them: beside the painter only the CTAs on the reserved SMs are resident, and with a static stride the
+//  positions of the CTAs that wait for an SM would wait with them -- with claims the resident warps drain a normal queue, and a
+//  burst (every env of a batch that was started in phase timing out in the same step) is finished by the whole grid once the
+//  painter has left, instead of by the dozen warps of the reserved SMs: 200 ms per such step before, profiles/r02_summary.md.)
+//  max_claims > 0 bounds what one warp takes: the launch that runs beside the painter on a second stream must end with the
+//  painter, a later launch on every SM sweeps up the rest of a burst.)
+__global__ void __launch_bounds__(128) k_reset_list(XwDev d, const int32_t* list, const int32_t* count, int max_claims) {
     __shared__ uint32_t s_stack[4][XW_RESET_STACK_WORDS];
     __shared__ uint32_t s_draws[4][XW_RESET_DRAW_WORDS];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n_warps = (gridDim.x * blockDim.x) >> 5, cnt = *count, wi = threadIdx.x >> 5;
-    for (int w = i >> 5; w < cnt; w += n_warps) xw_reset_env_warp(d, list[w], s_stack[wi], s_draws[wi]);
+    const int cnt = *count, wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int32_t* claim = const_cast<int32_t*>(count) + 2;
+    for (int taken = 0; max_claims <= 0 || taken < max_claims; ++taken) {
+        int w = 0;
+        if (lane == 0) w = atomicAdd(claim, 1);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= cnt) break;
+        xw_reset_env_warp(d, list[w], s_stack[wi], s_draws[wi]);
+    }
 }
 
 __global__ void __launch_bounds__(256) k_step(XwDev d, const int32_t* __restrict__ actions, int act_rep,
                                               float* __restrict__ reward, int32_t* __restrict__ over, int parity) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e == 0) d.reset_count[parity ^ 1] = 0;  // consumed by the previous step's reset launch
+    if (e == 0) { d.reset_count[parity ^ 1] = 0; d.reset_count[2 + (parity ^ 1)] = 0; }  // consumed by the previous step's reset launch
     if (e >= d.n) return;
     const int32_t a = actions[e];
     if (a == XW_ACTION_NONE) return;  // this env sits the step out: state and its reward / game_over slots untouched
@@ -452,7 +465,7 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
     int32_t** i32s[] = {&d.steps_in_task, &d.num_steps, &d.episode, &d.n_success, &d.n_failure, &d.success_steps, &d.error};
     for (auto p : i32s) rc |= dalloc(s, p, (size_t)n);
     rc |= dalloc(s, &d.minstd, (size_t)n);
-    rc |= dalloc(s, &d.reset_count, 2);
+    rc |= dalloc(s, &d.reset_count, 4);
     rc |= dalloc(s, &d.reset_list, (size_t)n);
     rc |= dalloc(s, &d.n_invalid, 1);
     rc |= dalloc(s, &d.task_perf, (size_t)XW_N_T3 * 3);
@@ -877,6 +890,8 @@ double xw_step_reset_ms(xw_sim* s, int32_t reset) {
 // fix != NULL: the painter leaves `fix->reserve` SMs free, and once `fix->done` has fired the frames of the envs in the
 // step's auto-reset queue are painted again (the painter in list mode) -- see step_xworld.
 struct RenderFix { int reserve; cudaEvent_t done; const int32_t* list; const int32_t* count; int est; std::function<int()> after_painter;
+                   bool pdl_painter = false;   // the reset kernel is launched by after_painter as the painter's programmatic dependent
+                   int sweep_grid = 0;   // > 0: a second reset launch on every SM once the painter and the first one are done (what a burst left)
                    std::function<int()> between; };   // between: first-person view, called right behind the frame kernel (before the goal kernel)
 static int launch_render(xw_sim* s, uint8_t* d_frames, cudaStream_t st, const RenderFix* fix = nullptr) {
     XwRender& r = s->r;
@@ -975,13 +990,26 @@ static int launch_render(xw_sim* s, uint8_t* d_frames, cudaStream_t st, const Re
         k_render_generic<<<s->n_sms * 8, 256, 0, st>>>(s->d, r, dst, dst_stride);
     }
     s->launches++;
-    if (s->timing) CUDA_TRY(cudaEventRecord(e1, st));  // (the frame kernel alone: not the re-paint of the reset queue, not the gray pass)
+    // kernel timing: the event behind the frame kernel(s) -- not the re-paint of the reset queue, not the gray pass.  When the reset
+    // kernel is the painter's programmatic dependent nothing may sit between the two launches: the event then follows the reset
+    // launch and measures painter || reset (the reset ends first on the bench workloads, so it is the painter's time; never less)
+    const bool e1_late = s->timing && fix && fix->pdl_painter;
+    if (s->timing && !e1_late) CUDA_TRY(cudaEventRecord(e1, st));
     if (fix) {
         if (fix->after_painter) {
-            const int rc2 = fix->after_painter();  // (the painter is queued: now the reset launch on its own stream, then `done`)
+            const int rc2 = fix->after_painter();  // (the painter is queued: now the reset launch -- its dependent, or on its own stream, then `done`)
             if (rc2) return rc2;
         }
+        if (e1_late) CUDA_TRY(cudaEventRecord(e1, st));
         if (fix->done) CUDA_TRY(cudaStreamWaitEvent(st, fix->done, 0));
+        if (fix->sweep_grid > 0) {
+            k_reset_list<<<fix->sweep_grid, 128, 0, st>>>(s->d, fix->list, fix->count, 0);
+            s->launches++;
+            if (s->d.vr > 0) {
+                k_fpv_warp_goals<<<s->n_sms * 8 < s->n ? s->n_sms * 8 : s->n, 256, 0, st>>>(s->d, s->fpv, nullptr, fix->list, fix->count);
+                s->launches++;
+            }
+        }
         if (s->d.vr > 0) {  // first-person view: the frame kernel and the goal kernel again, over the queue (its own goal-list slot)
             const int slot = s->fpv_parity * XW_FPV_SLOTS + xw_sim::FPV_MAX_CHUNKS;   // (the main pass zeroed nothing of this half)
             int blocks = (fix->est + s->fpv_ng - 1) / s->fpv_ng;
@@ -1100,12 +1128,16 @@ static int step_xworld(xw_sim* s, const int32_t* d_actions, int act_rep, float* 
         int reserve = (int)(s->reset_avg / (float)(s->reset_ctas_per_sm * 4 * 3)) + 1;
         if (reserve > s->n_sms / 8) reserve = s->n_sms / 8;
         const bool fpv = s->d.vr > 0;
-        int reset_grid = reserve * s->reset_ctas_per_sm;
+        // the CTAs that fit on the SMs the painter leaves free drain a normal queue; one more per SM starts when the painter's CTAs
+        // leave and finds the queue empty -- or finishes a burst (k_reset_list).  (A CTA for every slot of the device, 3 per SM,
+        // finishes a burst three times faster but costs every step 9 us of empty CTAs before the re-paint can start; this: 3 us.)
+        int reset_grid = reserve * s->reset_ctas_per_sm + s->n_sms;
+        if (reset_grid > (s->n + 3) / 4) reset_grid = (s->n + 3) / 4;
         static const int fdbg = [] { const char* e = getenv("XW_FPV_DBG"); return e ? atoi(e) : 0; }();
         if (fpv && (fdbg & 4)) reserve = 0;
         if (t1) CUDA_TRY(cudaEventRecord(t1, st));
         RenderFix fix = {reserve, s->ev_b, q_list, q_count, (int)(s->reset_avg * 1.5f) + 16, nullptr};
-        if (!fpv && s->reset_pdl && !s->timing && !s->trace) {   // (kernel timing puts an event record right behind the painter)
+        if (!fpv && s->reset_pdl && !s->trace) {
             // The reset kernel as the painter's PROGRAMMATIC DEPENDENT in the same stream: it may start as soon as every painter
             // CTA has executed griddepcontrol.launch_dependents (the first instruction of k_render_sp), i.e. when the painter holds
             // its SMs, and it never waits for the painter.  With the reset on a second stream behind an event both kernels become
@@ -1113,6 +1145,7 @@ static int step_xworld(xw_sim* s, const int32_t* d_actions, int act_rep, float* 
             // that many painter CTAs (a whole SM each) had to wait for a reset round before they could start: 100 us per step in the
             // synchronous host-buffer call, where the GPU is idle when the step begins (profiles/r02_summary.md).
             fix.done = nullptr;
+            fix.pdl_painter = true;
             fix.after_painter = [s, reset_grid, q_list, q_count, parity, tracing, st]() -> int {
                 cudaLaunchConfig_t lc;   // (nothing may sit between the painter and its dependent in the stream)
                 memset(&lc, 0, sizeof lc);
@@ -1121,7 +1154,7 @@ static int step_xworld(xw_sim* s, const int32_t* d_actions, int act_rep, float* 
                 at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
                 at[0].val.programmaticStreamSerializationAllowed = 1;
                 lc.attrs = at; lc.numAttrs = 1;
-                CUDA_TRY(cudaLaunchKernelEx(&lc, k_reset_list, s->d, q_list, q_count));
+                CUDA_TRY(cudaLaunchKernelEx(&lc, k_reset_list, s->d, q_list, q_count, 0));
                 s->launches++;
                 if (tracing) { CUDA_TRY(cudaEventRecord(s->tr[2], st)); CUDA_TRY(cudaEventRecord(s->tr[3], st)); }   // (= painter and reset both done)
                 CUDA_TRY(cudaMemcpyAsync(s->h_reset_cnt + parity, q_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -1143,7 +1176,7 @@ static int step_xworld(xw_sim* s, const int32_t* d_actions, int act_rep, float* 
                 at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
                 at[0].val.programmaticStreamSerializationAllowed = 1;
                 lc.attrs = at; lc.numAttrs = 1;
-                CUDA_TRY(cudaLaunchKernelEx(&lc, k_reset_list, s->d, q_list, q_count));
+                CUDA_TRY(cudaLaunchKernelEx(&lc, k_reset_list, s->d, q_list, q_count, 0));
                 CUDA_TRY(cudaEventRecord(s->ev_a, st));
                 CUDA_TRY(cudaStreamWaitEvent(s->reset_stream, s->ev_a, 0));
                 const int g2 = (int)(s->reset_avg * 1.25f) * s->fpv.G + 8;
@@ -1160,10 +1193,12 @@ static int step_xworld(xw_sim* s, const int32_t* d_actions, int act_rep, float* 
         CUDA_TRY(cudaEventRecord(s->ev_a, st));
         CUDA_TRY(cudaStreamWaitEvent(s->reset_stream, s->ev_a, 0));
         // (the painter first: its CTAs take their SMs before the reset launch, which waits for an event, can be placed)
-        fix.after_painter = [s, reset_grid, fpv, q_list, q_count, parity, tracing, st]() -> int {
+        const int small_grid = reserve * s->reset_ctas_per_sm;   // two-stream form: the launch beside the painter stays on the reserved SMs
+        fix.sweep_grid = reset_grid;
+        fix.after_painter = [s, small_grid, fpv, q_list, q_count, parity, tracing, st]() -> int {
             if (tracing) CUDA_TRY(cudaEventRecord(s->tr[2], st));
             static const int fdbg = [] { const char* e = getenv("XW_FPV_DBG"); return e ? atoi(e) : 0; }();
-            if (!(fpv && (fdbg & 2))) k_reset_list<<<reset_grid, 128, 0, s->reset_stream>>>(s->d, q_list, q_count);
+            if (!(fpv && (fdbg & 2))) k_reset_list<<<small_grid, 128, 0, s->reset_stream>>>(s->d, q_list, q_count, 8);
             s->launches++;
             if (fpv && !(fdbg & 1)) {  // the new episodes' goal icons (one CTA per queued env and goal)
                 const int g2 = (int)(s->reset_avg * 1.25f) * s->fpv.G + 8;
@@ -1183,7 +1218,7 @@ static int step_xworld(xw_sim* s, const int32_t* d_actions, int act_rep, float* 
     }
     if (s->cfg.auto_reset) {
         const int want = (s->n + 3) / 4, cap = s->n_sms * 16;  // CTAs of 4 warps: one warp per queued env, grid-stride past the cap
-        k_reset_list<<<want < cap ? want : cap, 128, 0, st>>>(s->d, q_list, q_count);
+        k_reset_list<<<want < cap ? want : cap, 128, 0, st>>>(s->d, q_list, q_count, 0);
         s->launches++;
         if (s->d.vr > 0) {
             k_fpv_warp_goals<<<s->n_sms * 8 < s->n ? s->n_sms * 8 : s->n, 256, 0, st>>>(s->d, s->fpv, nullptr, q_list, q_count);
