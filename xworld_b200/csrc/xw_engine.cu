@@ -1125,7 +1125,8 @@ static int step_xworld(xw_sim* s, const int32_t* d_actions, int act_rep, float* 
         const int32_t seen = s->h_reset_cnt[parity ^ 1];  // the previous step's queue length, if its copy has landed
         if (seen >= 0) s->reset_avg = 0.75f * s->reset_avg + 0.25f * (float)seen;
         // one warp per queued env, reset_ctas_per_sm CTAs of 4 warps per reserved SM, about three rounds inside a render
-        int reserve = (int)(s->reset_avg / (float)(s->reset_ctas_per_sm * 4 * 3)) + 1;
+        static const int rounds = [] { const char* e = getenv("XW_RESET_ROUNDS"); const int v = e ? atoi(e) : 0; return v >= 1 && v <= 16 ? v : 3; }();
+        int reserve = (int)(s->reset_avg / (float)(s->reset_ctas_per_sm * 4 * rounds)) + 1;
         if (reserve > s->n_sms / 8) reserve = s->n_sms / 8;
         const bool fpv = s->d.vr > 0;
         // the CTAs that fit on the SMs the painter leaves free drain a normal queue; one more per SM starts when the painter's CTAs
