@@ -182,6 +182,9 @@ HostSim* hs_create(const xw_config* c, const xw_catalog* cat, int n) {
     if (t.sp_ok) {
         r.cellgeo = t.cellgeo.data(); r.wcol = t.wcol.data(); r.wshare = t.wshare.data(); r.sr_ty = t.sr_ty.data();
         r.nwc = t.nwc; r.ns = t.ns; r.slot_magic = 65536 / t.nwc + 1;
+        r.n_sc = (int)t.sc.size(); r.n_sr = (int)t.sr.size();
+        r.ctab_merge = xw_want_ctab_merge(r, t, 232448) ? 1 : 0;   // (as xw_engine.cu: 227 KB of shared memory per CTA)
+        if (r.ctab_merge) { t.wshare = t.wshare_strad; t.ns = t.ns_strad; r.ns = t.ns; r.wshare = t.wshare.data(); }
         r.tc_rows = 12;  // (the host build always uses the 12-row instantiation)
     }
     r.n_sr = (int)t.sr.size();

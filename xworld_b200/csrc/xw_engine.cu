@@ -549,6 +549,8 @@ static int create_xworld(xw_sim* s, const xw_catalog* cat) {
         s->render_sp = t.sp_ok && !(em && (!strcmp(em, "pipe") || !strcmp(em, "sb")));
         if (s->render_sp) {
             r.nwc = t.nwc; r.ns = t.ns; r.n_sc = (int)t.sc.size();
+            r.ctab_merge = xw_want_ctab_merge(r, t, max_optin) ? 1 : 0;
+            if (r.ctab_merge) { r.ns = t.ns_strad; t.wshare = t.wshare_strad; t.ns = t.ns_strad; }
             r.slot_magic = 65536 / t.nwc + 1;
             const char* ef = getenv("XW_RENDER_SP_FILL");
             r.sp_fill = ef ? atoi(ef) : 0;

@@ -24,6 +24,7 @@
 // while the other groups keep composing.  The brick table -- the icon most non-empty cells hold --
 // is staged into shared memory once per CTA by a TMA bulk load; other tables stay L2-resident.
 #pragma once
+#include <stdlib.h>
 #include "xw_common.cuh"
 #include "xw_render_host.hpp"
 
@@ -88,7 +89,12 @@ struct XwRender {
     const uint8_t* wshare;    // [WR]
     const uint8_t* sr_ty;     // [n_sr]
     const uint32_t* ctab;     // class tables (xw_ctab_words), built by k_build_class_tables
-    int32_t ns;               // word columns shared by two cell columns
+    int32_t ns;               // word columns shared by two cell columns that have variant class tables (all of them, or --
+                              //   ctab_merge -- only those that hold a straddling pixel)
+    int32_t ctab_merge;       // 1: a brick|white / white|brick word of a shared column WITHOUT a straddling pixel is the brick|brick
+                              //   word with the white cell's bytes set (one PRMT with the column's byte-ownership selector) instead
+                              //   of a table of its own.  Chosen when that is what makes a third frame buffer fit (15x15 -> 128x128:
+                              //   class tables 86 -> 55 KB); costs an instruction per such word, so not otherwise.
     int32_t nwc;              // word-column slots per cell
     int32_t slot_magic;       // slot / nwc == (slot * slot_magic) >> 16 for slot < 4096
     const uint32_t* cornerP;  // [n_icons+1][4] corner tap of role (top-left cell's (63,63), top-right's (63,0), bottom-left's
@@ -769,32 +775,57 @@ XW_HD void xw_sp_brick_slot(const XwRender& r, const XwPaintCtx& g, const XwCell
     const uint32_t wk = g.wcol[k];
     const int lo = wk & 15, hi = (wk >> 4) & 15;
     int col = k;  // class-table column: brick | brick
+    uint32_t selm = 0;  // merge mode: != 0 = the brick|brick word with the white cell's bytes set (PRMT selector)
     if (lo != hi) {
         const int row = cell - (int)((cg.z >> 8) & 0xff);
         const bool left = row + lo == cell;
         const int ko = cells.code[row + (left ? hi : lo)];  // the other cell of the word
         if (ko >= XW_CELL_AGENT || (!left && ko == XW_CELL_BLOCK)) return;  // a special cell's, or the left brick's word
-        if (ko == XW_CELL_EMPTY) col = r.WR + (left ? 0 : r.ns) + g.wshare[k];
+        if (ko == XW_CELL_EMPTY) {
+            const int ws = g.wshare[k];
+            if (ws != 0xff) col = r.WR + (left ? 0 : r.ns) + ws;
+            else selm = ((wk >> 8) & 0xffffu) ^ (left ? 0u : 0x4444u);  // (ctab_merge only: every shared column has a table otherwise)
+        }
     }
     const int nrows = (int)((cg.x >> 16) & 0xff), y0 = (int)(cg.z & 0xff);
     const uint32_t* src = g.ctab + (size_t)col * ((3 * OH) | 1) + y0;
     uint32_t* dst = fb + y0 * WR + k;
     // (rows past the band are loaded -- the tables are followed by other shared memory -- and not stored)
+    if (selm == 0) {
 #pragma unroll
-    for (int p = 0; p < 3; ++p) {
-        uint32_t v[8];
+        for (int p = 0; p < 3; ++p) {
+            uint32_t v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = src[p * OH + j];
+            for (int j = 0; j < 8; ++j) v[j] = src[p * OH + j];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (j < nrows) dst[p * OH * WR + j * WR] = v[j];
-        if (XW_SP_ROWS > 8 && nrows > 8) {
-            uint32_t u[XW_SP_ROWS > 8 ? XW_SP_ROWS - 8 : 1];
+            for (int j = 0; j < 8; ++j)
+                if (j < nrows) dst[p * OH * WR + j * WR] = v[j];
+            if (XW_SP_ROWS > 8 && nrows > 8) {
+                uint32_t u[XW_SP_ROWS > 8 ? XW_SP_ROWS - 8 : 1];
 #pragma unroll
-            for (int j = 8; j < XW_SP_ROWS; ++j) u[j - 8] = src[p * OH + j];
+                for (int j = 8; j < XW_SP_ROWS; ++j) u[j - 8] = src[p * OH + j];
 #pragma unroll
-            for (int j = 8; j < XW_SP_ROWS; ++j)
-                if (j < nrows) dst[p * OH * WR + j * WR] = u[j - 8];
+                for (int j = 8; j < XW_SP_ROWS; ++j)
+                    if (j < nrows) dst[p * OH * WR + j * WR] = u[j - 8];
+            }
+        }
+    } else {
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            uint32_t v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = src[p * OH + j];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < nrows) dst[p * OH * WR + j * WR] = xw_prmt(v[j], 0xffffffffu, selm);
+            if (XW_SP_ROWS > 8 && nrows > 8) {
+                uint32_t u[XW_SP_ROWS > 8 ? XW_SP_ROWS - 8 : 1];
+#pragma unroll
+                for (int j = 8; j < XW_SP_ROWS; ++j) u[j - 8] = src[p * OH + j];
+#pragma unroll
+                for (int j = 8; j < XW_SP_ROWS; ++j)
+                    if (j < nrows) dst[p * OH * WR + j * WR] = xw_prmt(u[j - 8], 0xffffffffu, selm);
+            }
         }
     }
 }
@@ -839,6 +870,17 @@ XW_HD XwRenderSpSmem xw_render_sp_smem(const XwRender& r, int G) {
     s.bar = o; o += 16 + 16 * G;
     s.total = o;
     return s;
+}
+
+// Merge mode of the class tables (XwRender::ctab_merge)?  Yes when the full tables leave room for two frame buffers only and the
+// reduced ones for a third (15x15 -> 128x128: 195 KB at two groups, 245 KB at three with 86 KB of tables, 214 KB with 55 KB);
+// XW_RENDER_CTAB_MERGE=0|1 overrides.  r: OH, OW, WR, FB, H, W, n_sr, n_sc set.
+inline bool xw_want_ctab_merge(const XwRender& r, const XwRenderTables& t, int max_smem) {
+    if (const char* e = getenv("XW_RENDER_CTAB_MERGE")) return atoi(e) != 0 && t.ns_strad < t.ns;
+    if (t.ns_strad >= t.ns) return false;
+    XwRender a = r, b = r;
+    a.ns = t.ns; b.ns = t.ns_strad;
+    return xw_render_sp_smem(a, 3).total > max_smem && xw_render_sp_smem(b, 3).total <= max_smem;
 }
 
 #if defined(__CUDACC__)

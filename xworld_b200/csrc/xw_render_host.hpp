@@ -3,6 +3,7 @@
 // scale = 1/(dst/src) in double, fx in float, cvFloor, 11-bit rounded weights), plus the plan the
 // compositing kernel executes: one "band-column" item per (cell row, output word column).
 #pragma once
+#include <stdlib.h>
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
@@ -59,6 +60,9 @@ struct XwRenderTables {
     std::vector<XwU4> cellgeo;           // [H*W]
     std::vector<uint32_t> wcol;          // [WR]
     std::vector<uint8_t> wshare;         // [WR] index of word column k among the columns shared by two cell columns (0xff: not shared)
+    // merge mode (XwRender::ctab_merge): variant class tables only for the shared columns that hold a straddling pixel
+    std::vector<uint8_t> wshare_strad;   // [WR] index among those (0xff: not shared, or shared without a straddling pixel)
+    int ns_strad = 0;
     int ns = 0;                          // shared word columns
     std::vector<uint8_t> sr_ty;          // [n_sr] cell row above straddling row q
     int max_band_rows = 0;               // most rows of a band without its straddling row
@@ -215,6 +219,10 @@ inline void xw_build_paint_tables(XwRenderTables& t) {
     t.wshare.assign(WR, 0xff);
     t.ns = 0;
     for (int k = 0; k < WR; ++k) if ((t.wcol[k] & 15) != ((t.wcol[k] >> 4) & 15)) t.wshare[k] = (uint8_t)t.ns++;
+    t.wshare_strad.assign(WR, 0xff);
+    t.ns_strad = 0;
+    for (int k = 0; k < WR; ++k)
+        if ((t.wcol[k] & 15) != ((t.wcol[k] >> 4) & 15) && ((t.wcol[k] >> 24) & 1)) t.wshare_strad[k] = (uint8_t)t.ns_strad++;
     t.nwc = 0;
     for (int c = 0; c < W; ++c) {
         if (kfirst[c] < 0) return;
