@@ -162,6 +162,35 @@ def test_sparse_painter_and_plan_compositor_vs_per_pixel_rule(geom, synthetic_ca
     assert L.hs_sp_ok(hs.h) == L.hs_fast_ok(hs.h)
 
 
+@pytest.mark.parametrize("geom", [(11, 11, 84, 84), (15, 15, 128, 128), (16, 16, 128, 128), (10, 10, 84, 84), (5, 9, 60, 100), (13, 13, 128, 128)])
+def test_sparse_painter_merge_mode_forced(geom, synthetic_catalog, monkeypatch):
+    """The class tables' merge mode (XwRender::ctab_merge: brick|white words of shared word columns without a straddling pixel are
+    the brick|brick word with the white cell's bytes set) is chosen only where it buys a third frame buffer (15x15 -> 128x128);
+    forced on (XW_RENDER_CTAB_MERGE=1) it must stay pixel-exact on every geometry, maze-like grids included."""
+    monkeypatch.setenv("XW_RENDER_CTAB_MERGE", "1")
+    H, W, OH, OW = geom
+    cfg = _abi.default_config(height=H, width=W, n_goals=4, n_blocks=1, rules=_abi.XW_RULES_NAV3D, out_h=OH, out_w=OW)
+    n = 20
+    hs = parity.HostSim(cfg, synthetic_catalog, n)
+    L = hs.L
+    L.hs_set_grid_env.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    if not L.hs_sp_ok(hs.h):
+        pytest.skip("the painter does not take this geometry")
+    rng = np.random.RandomState(H * 77 + OW)
+    pool = rng.permutation(synthetic_catalog.as_c().n_icons)[:8]
+    for e in range(n):
+        grid = np.zeros(H * W, np.uint8)
+        grid[rng.rand(H * W) < [0.15, 0.3, 0.5, 0.8][e % 4]] = _abi.XW_CELL_BLOCK   # brick | white and white | brick borders of every kind
+        for i, c in enumerate(rng.permutation(H * W)[:5]):
+            grid[c] = _abi.XW_CELL_AGENT + i
+        icons = pool[rng.randint(0, len(pool), 4)].astype(np.int32)
+        L.hs_set_grid_env(hs.h, e, np.ascontiguousarray(grid).ctypes.data, icons.ctypes.data)
+    want = hs.render(mode=2)
+    got = hs.render(mode=1)
+    bad = np.argwhere(got != want)
+    assert bad.size == 0, ("merge mode", geom, len(bad), bad[:8].tolist())
+
+
 def test_hostsim_fpv_golden_frames_from_real_opencv():
     """The engine's first-person code (goal icon warp, crop-cell classes, table pass + exact pass) vs frames the real OpenCV
     produced from the reference call sequence (tests/golden/fpv_golden.npz)."""
