@@ -61,7 +61,14 @@ __global__ void __launch_bounds__(128) k_reset(XwDev d, const uint8_t* mask) {
 //  painter has left, instead of by the dozen warps of the reserved SMs: 200 ms per such step before, profiles/r02_summary.md.)
 //  max_claims > 0 bounds what one warp takes: the launch that runs beside the painter on a second stream must end with the
 //  painter, a later launch on every SM sweeps up the rest of a burst.)
-__global__ void __launch_bounds__(128) k_reset_list(XwDev d, const int32_t* list, const int32_t* count, int max_claims) {
+// (168 registers, 3 CTAs per SM.  Register caps were tried and are not better: -DXW_RESET_MINB=4 (128 registers, 4 CTAs per SM) C3
+//  195.1 M against 196-198 M env-steps/s, =6 (80 registers, spills) 167.7 M -- a reset is one long dependent chain per warp.)
+#ifdef XW_RESET_MINB
+#define XW_RESET_BOUNDS __launch_bounds__(128, XW_RESET_MINB)
+#else
+#define XW_RESET_BOUNDS __launch_bounds__(128)
+#endif
+__global__ void XW_RESET_BOUNDS k_reset_list(XwDev d, const int32_t* list, const int32_t* count, int max_claims) {
     __shared__ uint32_t s_stack[4][XW_RESET_STACK_WORDS];
     __shared__ uint32_t s_draws[4][XW_RESET_DRAW_WORDS];
     const int cnt = *count, wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1131,10 +1138,10 @@ static int step_xworld(xw_sim* s, const int32_t* d_actions, int act_rep, float* 
         int reserve = (int)(s->reset_avg / (float)(s->reset_ctas_per_sm * 4 * rounds)) + 1;
         if (reserve > s->n_sms / 8) reserve = s->n_sms / 8;
         const bool fpv = s->d.vr > 0;
-        // the CTAs that fit on the SMs the painter leaves free drain a normal queue; one more per SM starts when the painter's CTAs
-        // leave and finds the queue empty -- or finishes a burst (k_reset_list).  (A CTA for every slot of the device, 3 per SM,
-        // finishes a burst three times faster but costs every step 9 us of empty CTAs before the re-paint can start; this: 3 us.)
-        int reset_grid = reserve * s->reset_ctas_per_sm + s->n_sms;
+        // the CTAs that land on the SMs the painter leaves free drain a normal queue; the others -- a CTA for every slot of the
+        // device -- start when the painter's CTAs leave and find the queue empty, or finish a burst (k_reset_list).  (Measured: the
+        // empty CTAs cost a step nothing, 0.3315 ms with 444 and with 172 of them.)
+        int reset_grid = s->n_sms * s->reset_ctas_per_sm;
         if (reset_grid > (s->n + 3) / 4) reset_grid = (s->n + 3) / 4;
         static const int fdbg = [] { const char* e = getenv("XW_FPV_DBG"); return e ? atoi(e) : 0; }();
         if (fpv && (fdbg & 4)) reserve = 0;
