@@ -440,9 +440,24 @@ def lib_sha256():
         return hashlib.sha256(f.read()).hexdigest()
 
 
+def src_sha256():
+    """sha256 over the sources the library is built from (xworld_b200/csrc/* and the C header, names sorted): identifies the
+    build even when nvcc is run again (its output is not byte-reproducible)."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "xworld_b200", "csrc")
+    files = [os.path.join(d, f) for f in sorted(os.listdir(d))] + [os.path.join(ROOT, "include", "xworld_b200.h")]
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def traffic_for(key, n):
     """roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of the render kernel from the ncu --set full capture
-    recorded in profiles/render_traffic.json -- only if it was taken on THIS binary (sha256 of libxworld_b200.so) at this size."""
+    recorded in profiles/render_traffic.json -- only if it was taken on THIS build (sha256 of libxworld_b200.so, or of the sources
+    it is built from when the library has been re-linked) at this size."""
     tp = os.path.join(ROOT, "profiles", "render_traffic.json")
     if not os.path.exists(tp):
         return None, "no capture on record"
@@ -451,7 +466,7 @@ def traffic_for(key, n):
     ent = rec.get("workloads", {}).get(key)
     if not ent or ent.get("envs") != n:
         return None, "no capture of this workload / size on record"
-    if rec.get("lib_sha256") != lib_sha256():
+    if rec.get("lib_sha256") != lib_sha256() and rec.get("src_sha256") != src_sha256():
         return None, "the capture on record (%s) was taken on another build of libxworld_b200.so" % rec.get("capture")
     return ent["dram_bytes_per_launch"], rec.get("capture")
 

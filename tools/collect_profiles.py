@@ -42,7 +42,9 @@ def main(tag):
             ent["note"] = "frame kernel + goal kernel (bench.py's render time covers both)"
         W[key] = ent
         print(key, big["name"][:48], "%.1f us" % big["us"], ent["dram_bytes_per_launch"])
-    rec = dict(lib_sha256=sha, capture="%s: ncu --set full --clock-control none, one launch per kernel of `bench.py --workload <w> --steps 4 --warmup 4` "
+    sys.path.insert(0, ROOT)
+    import bench
+    rec = dict(lib_sha256=sha, src_sha256=bench.src_sha256(), capture="%s: ncu --set full --clock-control none, one launch per kernel of `bench.py --workload <w> --steps 4 --warmup 4` "
                                        "(tools/final_ncu.sh), on the binary with this sha256" % tag, workloads=W)
     json.dump(rec, open(os.path.join(pr, "render_traffic.json"), "w"), indent=1)
     for cap in ["c3_render", "c2_render", "c4_render", "fpv_frame", "fpv_goal", "c2_reset", "c3_step"]:
